@@ -1,0 +1,198 @@
+/*
+ * qcmrf_b200 -- C ABI of the B200-native statevector engine for QCMRF circuits.
+ *
+ * This is the drop-in boundary: it replaces what the reference reaches through
+ *     simulator = Aer.get_backend('qasm_simulator')
+ *     result    = simulator.run(T, shots=SHOTS).result()
+ *     counts    = result.get_counts()
+ * (/root/reference/run_experiment.py:54-57), i.e. qiskit-aer's C++ controller
+ * behind the pybind call inside ``.run()``; and the post-selection arithmetic of
+ * /root/reference/QCMRF.py:263-284 and /root/reference/eval.py:115-123, which it
+ * moves onto the GPU.  The Python side (qcmrf_b200/backend.py) lowers and fuses a
+ * circuit into a short list of ``qcm_op`` and calls the functions below through
+ * ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every function returns QCM_OK (0) or a negative qcm_status; nothing throws
+ *    across the ABI; ``qcm_last_error`` returns a human-readable message.
+ *  - all pointers in signatures are HOST pointers owned and sized by the caller,
+ *    except ``ext_state`` / ``ext_stream`` of qcm_create (device memory / a
+ *    cudaStream_t the caller owns, e.g. a torch tensor and torch's stream).
+ *  - a handle is bound to one device and one stream and is not thread-safe.
+ *  - basis-state index bit q <-> qubit q (Qiskit little-endian).  For a sharded
+ *    state the handle holds the 2^n_local amplitudes whose global index has the
+ *    high bits equal to ``rank`` (qcm_set_shard).
+ *  - coefficient tables are passed in fp64 and rounded once to the state's
+ *    precision, so fp32 kernels get correctly rounded coefficients.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with QCM_ERR_NO_DEVICE.
+ */
+#ifndef QCMRF_B200_H
+#define QCMRF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCM_ABI_VERSION 1
+#define QCM_MAX_CTRL 10      /* table-index qubits of one MUX1Q / DIAG op           */
+#define QCM_MAX_BLOCK 5      /* target qubits of one BLOCK pass (2^5 vectors/thread) */
+#define QCM_MAX_MEMBERS 16   /* MUX1Q members of one BLOCK pass                      */
+
+typedef struct qcm_sim_s *qcm_handle;
+
+enum qcm_status {
+    QCM_OK = 0,
+    QCM_ERR_INVALID = -1,      /* bad argument / malformed program        */
+    QCM_ERR_CUDA = -2,         /* a CUDA runtime call failed              */
+    QCM_ERR_NOMEM = -3,        /* device or host allocation failed        */
+    QCM_ERR_UNSUPPORTED = -4,  /* valid request this build cannot serve   */
+    QCM_ERR_NO_DEVICE = -5     /* no usable CUDA device                   */
+};
+
+enum qcm_precision { QCM_C64 = 32, QCM_C128 = 64 };   /* bits of the real type */
+
+enum qcm_op_kind {
+    /* state <- tensor product of per-qubit 2-vectors over the first n_active_out
+     * qubits; table = n_active_out * 4 doubles (amp0.re, amp0.im, amp1.re, amp1.im).
+     * The leading H layer of QCMRF._build (QCMRF.py:204-205) folds into this.     */
+    QCM_OP_INIT_PRODUCT = 1,
+    /* uniformly-controlled single-qubit gate: for every assignment c of the n_ctrl
+     * index qubits apply the 2x2 matrix table[c] (8 doubles, row-major re/im) on
+     * `target`.  One fused QCMRF clique block (QCMRF.py:216-236) is one of these;
+     * so is every h/x/sx/cx/mcx/AND of an unfused program.                        */
+    QCM_OP_MUX1Q = 2,
+    /* diagonal: amplitude *= table[c] (2 doubles per entry) -- rz, p, cp, cz ...   */
+    QCM_OP_DIAG = 3,
+    /* header of a blocked pass: the next `n_ctrl` ops (all MUX1Q, targets pairwise
+     * distinct or repeated, no member's index qubits among the block's targets) are
+     * applied in ONE sweep; `ctrl[0..target-1]` lists the block's `target` (= count)
+     * distinct target qubits in ascending order.                                   */
+    QCM_OP_BLOCK = 4,
+    /* exchange qubits `target` and `ctrl[0]` (both local)                          */
+    QCM_OP_SWAP = 5,
+    /* materialise qubits [n_active_in, n_active_out) as |0>: zero-fills the new part  */
+    QCM_OP_EXTEND = 6
+};
+
+/* Lazy materialisation: before an op the state is valid on the first
+ * 2^n_active_in amplitudes (every qubit >= n_active_in is known |0>, its
+ * amplitudes are not stored); the op leaves it valid on 2^n_active_out.  Ops
+ * never read beyond 2^n_active_in and write all of 2^n_active_out.  Qubits in
+ * [n_active_in, n_active_out) must be targets of the op (BLOCK: listed in ctrl[]).
+ * A fully materialised program has n_active_in == n_active_out == n_local.       */
+typedef struct qcm_op {
+    int32_t kind;
+    int32_t target;
+    int32_t n_ctrl;
+    int32_t n_active_in;
+    int32_t n_active_out;
+    int32_t flags;                 /* reserved, 0 */
+    int32_t ctrl[QCM_MAX_CTRL];
+    int64_t table_off;             /* offset, in doubles, into `tables` */
+} qcm_op;
+
+typedef struct qcm_timing {
+    double program_ms;             /* device time of the last qcm_run_program  */
+    double sample_ms;              /* device time of the last qcm_sample       */
+    double postselect_ms;          /* device time of the last qcm_postselect   */
+    uint64_t kernel_launches;      /* kernels launched by this handle so far   */
+    uint64_t bytes_read;           /* algorithmic bytes of the last program    */
+    uint64_t bytes_written;
+} qcm_timing;
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+/* -- library ------------------------------------------------------------------ */
+int qcm_abi_version(void);
+int qcm_device_count(int *n_out);
+const char *qcm_last_error(qcm_handle h);          /* h may be NULL: last global error */
+
+/* -- state -------------------------------------------------------------------- */
+/* n_local: qubits stored by this handle.  precision: QCM_C64 | QCM_C128.
+ * ext_state: device buffer of 2^n_local complex numbers, or NULL (library allocates).
+ * ext_stream: a cudaStream_t, or NULL for the legacy default stream.              */
+int qcm_create(qcm_handle *out, int device, int n_local, int precision,
+               void *ext_state, void *ext_stream);
+int qcm_destroy(qcm_handle h);
+/* the global index of local amplitude i is (rank << n_local) | i                  */
+int qcm_set_shard(qcm_handle h, int n_global_qubits, uint64_t rank);
+int qcm_get_amplitudes(qcm_handle h, uint64_t first, uint64_t count, void *host_out);
+int qcm_set_amplitudes(qcm_handle h, uint64_t first, uint64_t count, const void *host_in,
+                       int n_active);
+int qcm_synchronize(qcm_handle h);
+
+/* -- the hot path ---------------------------------------------------------------- */
+/* Executes the fused program (replaces Aer's per-gate statevector sweeps).        */
+int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops,
+                    const double *tables, size_t n_tables);
+
+/* Post-selection (QCMRF.py:263-284 / eval.py:115-123 on exact probabilities):
+ * kept = sum |amp_i|^2 over local i with (global(i) & mask) == value;
+ * probs_out (optional, 2^n_out_bits doubles) receives, for every kept i, |amp_i|^2
+ * accumulated at index (i & (2^n_out_bits - 1)); neither is normalised.
+ * For QCMRF: mask = all bits >= n, value = 0, n_out_bits = n  =>  probs/kept is the
+ * post-selected pmf with x_0 as MSB and kept is the success probability delta.     */
+int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits,
+                   double *probs_out, double *kept_out);
+
+/* Shot sampling (replaces Aer's measurement sampling + Result.get_counts keys).
+ * Draws `shots` basis states from |amp|^2 with Philox4x32-10 keyed by
+ * (seed, stream_id, shot) and returns classical-register integers: bit c of a key is
+ * the sampled value of qubit clbit_qubit[c] (negative entry: clbit reads 0, e.g.
+ * QCMRF's never-written clbit n).  clbit_qubit == NULL returns raw state indices.  */
+int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id,
+               const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out);
+
+/* Sharded sampling, three steps around one all-gather the caller performs:
+ *  1. qcm_sample_prepare : builds the local sum tree, returns this rank's mass
+ *  2. caller all-gathers the masses of all ranks
+ *  3. qcm_sample_sharded : every rank draws the same Philox stream and resolves the
+ *     shots that land in its shard; mine_out[s] = 1 where keys_out[s] is valid.    */
+int qcm_sample_prepare(qcm_handle h, double *local_mass_out);
+int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id,
+                       const double *rank_masses, int n_ranks,
+                       const int32_t *clbit_qubit, int n_clbits,
+                       uint64_t *keys_out, uint8_t *mine_out);
+
+/* Batched small circuits (all fixture-sized models in one launch: one thread block
+ * per circuit, state resident in shared memory, program + post-selection + sampling
+ * fused).  Circuit c has n_qubits[c] <= qcm_small_max_qubits(precision) qubits, ops
+ * ops[op_begin[c] .. op_begin[c+1]) (INIT_PRODUCT / MUX1Q / DIAG, fully materialised),
+ * clbit map clbit_qubit[64*c ..], post-selection as in qcm_postselect with
+ * ps_mask[c], ps_value[c], ps_bits[c]; probs_out is the concatenation of the
+ * 2^ps_bits[c] vectors, keys_out is [n_circuits][shots].                           */
+int qcm_small_max_qubits(int precision);
+int qcm_run_batch_small(int device, int precision, int n_circuits,
+                        const int32_t *n_qubits, const int64_t *op_begin,
+                        const qcm_op *ops, const double *tables, size_t n_tables,
+                        const int32_t *clbit_qubit, const int32_t *n_clbits,
+                        const uint64_t *ps_mask, const uint64_t *ps_value,
+                        const int32_t *ps_bits,
+                        uint64_t shots, uint64_t seed,
+                        uint64_t *keys_out, double *probs_out, double *kept_out,
+                        double *device_ms_out);
+
+/* -- multi-GPU plumbing ------------------------------------------------------------ */
+/* Packs/unpacks nothing: the qubit-swap all-to-all exchanges contiguous slabs of the
+ * top `g` local qubits, which the caller moves with NCCL (torch.distributed).  These
+ * two report the device pointer and byte size so the caller can wrap the state.     */
+int qcm_state_ptr(qcm_handle h, void **dev_ptr_out, uint64_t *bytes_out);
+int qcm_set_active(qcm_handle h, int n_active);
+int qcm_get_active(qcm_handle h, int *n_active_out);
+
+int qcm_get_timing(qcm_handle h, qcm_timing *out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCMRF_B200_H */

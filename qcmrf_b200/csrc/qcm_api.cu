@@ -1,0 +1,701 @@
+// C ABI of the qcmrf_b200 engine (see include/qcmrf_b200.h for the contract).
+// Host-side program validation, kernel selection and launch; no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "qcm_kernels.cuh"
+#include "qcmrf_b200.h"
+
+using namespace qcm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct qcm_sim_s {
+    int device = 0;
+    int n_local = 0;
+    int prec = QCM_C64;
+    int n_active = 0;
+    int n_global = 0;
+    uint64_t rank = 0;
+    void *state = nullptr;
+    bool own_state = false;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    std::string err;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    qcm_timing timing{};
+    DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree;
+    std::vector<double> h_top;
+    // sum tree (built by qcm_sample_prepare)
+    int tree_levels = 0;
+    double *tree_ptr[8] = {nullptr};
+    uint64_t tree_n[8] = {0};
+    int tree_for_active = -1;
+    double local_mass = 0.0;
+    bool tree_valid = false;
+};
+
+namespace {
+
+int fail(qcm_handle h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (h) h->err = buf;
+    return code;
+}
+
+#define QCM_CUDA(h, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? QCM_ERR_NOMEM : QCM_ERR_CUDA,    \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure(qcm_handle h, DevBuf &b, size_t bytes) {
+    if (b.cap >= bytes) return QCM_OK;
+    if (b.p) QCM_CUDA(h, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    QCM_CUDA(h, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return QCM_OK;
+}
+
+inline size_t amp_bytes(int prec) { return prec == QCM_C64 ? 8 : 16; }
+inline uint64_t rank_bits(const qcm_sim_s *h) { return h->n_global ? (h->rank << h->n_local) : 0ull; }
+
+template <typename K>
+int grid_for(qcm_handle h, K kernel, size_t smem, uint64_t work_items_per_block, uint64_t items) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
+    if (occ < 1) occ = 1;
+    uint64_t need = (items + work_items_per_block - 1) / work_items_per_block;
+    uint64_t cap = (uint64_t)h->num_sms * (uint64_t)occ;
+    if (need < 1) need = 1;
+    return (int)std::min<uint64_t>(need, cap);
+}
+
+// ---- block / mux launch -----------------------------------------------------------
+template <typename R, int V, int M, int U>
+int launch_block_t(qcm_handle h, const BlockArgs &a, size_t smem) {
+    auto kern = k_block<R, V, M, U>;
+    if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t nvec = (1ull << (a.n_out - M)) / V;
+    const int grid = grid_for(h, kern, smem, (uint64_t)kThreads * U, nvec);
+    kern<<<grid, kThreads, smem, h->stream>>>(a);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    return QCM_OK;
+}
+
+template <typename R, int V>
+int launch_block_m(qcm_handle h, int M, const BlockArgs &a, size_t smem) {
+    switch (M) {
+        case 1: return launch_block_t<R, V, 1, 4>(h, a, smem);
+        case 2: return launch_block_t<R, V, 2, 2>(h, a, smem);
+        case 3: return launch_block_t<R, V, 3, 1>(h, a, smem);
+        case 4: return launch_block_t<R, V, 4, 1>(h, a, smem);
+        case 5: return launch_block_t<R, V, 5, 1>(h, a, smem);
+    }
+    return fail(h, QCM_ERR_INVALID, "block size %d out of range", M);
+}
+
+// members: ops[0..n_mem) are MUX1Q; tq: block qubits ascending
+int launch_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_mem, int n_in, int n_out,
+                 size_t n_tables) {
+    if (M < 1 || M > QCM_MAX_BLOCK) return fail(h, QCM_ERR_INVALID, "block of %d qubits unsupported (max %d)", M, QCM_MAX_BLOCK);
+    if (n_mem > QCM_MAX_MEMBERS) return fail(h, QCM_ERR_INVALID, "block has %d members (max %d)", n_mem, QCM_MAX_MEMBERS);
+    if (n_out > h->n_local || n_in > n_out || n_in < 0) return fail(h, QCM_ERR_INVALID, "bad active range %d -> %d (n_local %d)", n_in, n_out, h->n_local);
+    BlockArgs a{};
+    a.state = h->state;
+    a.tables = h->tab_real.p;
+    a.n_in = n_in;
+    a.n_out = n_out;
+    a.n_members = n_mem;
+    a.rank_bits = rank_bits(h);
+    for (int j = 0; j < M; ++j) {
+        if (tq[j] < 0 || tq[j] >= n_out) return fail(h, QCM_ERR_INVALID, "block qubit %d outside the active state (%d)", tq[j], n_out);
+        if (j && tq[j] <= tq[j - 1]) return fail(h, QCM_ERR_INVALID, "block qubits must be strictly ascending");
+        a.tq[j] = tq[j];
+    }
+    for (int q = n_in; q < n_out; ++q)
+        if (!std::binary_search(tq, tq + M, q))
+            return fail(h, QCM_ERR_INVALID, "qubit %d is materialised by this op but is not one of its targets", q);
+    size_t smem_reals = 0;
+    for (int g = 0; g < n_mem; ++g) {
+        const qcm_op &op = members[g];
+        if (op.kind != QCM_OP_MUX1Q) return fail(h, QCM_ERR_INVALID, "block member %d is not MUX1Q", g);
+        if (op.n_ctrl < 0 || op.n_ctrl > QCM_MAX_CTRL) return fail(h, QCM_ERR_INVALID, "member %d: n_ctrl %d out of range", g, op.n_ctrl);
+        const int *pp = std::lower_bound(tq, tq + M, op.target);
+        if (pp == tq + M || *pp != op.target) return fail(h, QCM_ERR_INVALID, "member %d targets qubit %d which is not a block qubit", g, op.target);
+        a.mem[g].pos = (int8_t)(pp - tq);
+        a.mem[g].n_ctrl = (int8_t)op.n_ctrl;
+        for (int j = 0; j < op.n_ctrl; ++j) {
+            const int c = op.ctrl[j];
+            if (c < 0 || c >= h->n_local + h->n_global) return fail(h, QCM_ERR_INVALID, "member %d: index qubit %d out of range", g, c);
+            if (std::binary_search(tq, tq + M, c)) return fail(h, QCM_ERR_INVALID, "member %d: index qubit %d is a block target", g, c);
+            a.mem[g].ctrl[j] = (int8_t)c;
+        }
+        if (op.table_off < 0 || (size_t)op.table_off + (8ull << op.n_ctrl) > n_tables)
+            return fail(h, QCM_ERR_INVALID, "member %d: table [%lld, +%llu) outside tables (%zu)", g, (long long)op.table_off,
+                        (unsigned long long)(8ull << op.n_ctrl), n_tables);
+        a.mem[g].src_off = (int32_t)op.table_off;
+        a.mem[g].tab_off = (int32_t)smem_reals;
+        smem_reals += 8ull << op.n_ctrl;
+    }
+    const size_t real_sz = h->prec == QCM_C64 ? 4 : 8;
+    const size_t smem = smem_reals * real_sz;
+    if (smem > 160 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "block coefficient tables need %zu B of shared memory", smem);
+    int rc;
+    if (h->prec == QCM_C64) {
+        const bool vec2 = tq[0] >= 1 && (n_out - M) >= 1;
+        rc = vec2 ? launch_block_m<float, 2>(h, M, a, smem) : launch_block_m<float, 1>(h, M, a, smem);
+    } else {
+        rc = launch_block_m<double, 1>(h, M, a, smem);
+    }
+    if (rc) return rc;
+    // algorithmic traffic: read the materialised input, write the whole output
+    h->timing.bytes_read += amp_bytes(h->prec) << n_in;
+    h->timing.bytes_written += amp_bytes(h->prec) << n_out;
+    return QCM_OK;
+}
+
+int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
+    if (op.n_ctrl < 0 || op.n_ctrl > QCM_MAX_CTRL) return fail(h, QCM_ERR_INVALID, "DIAG: n_ctrl %d out of range", op.n_ctrl);
+    if (op.table_off < 0 || (size_t)op.table_off + (2ull << op.n_ctrl) > n_tables) return fail(h, QCM_ERR_INVALID, "DIAG: table outside tables");
+    if (op.n_active_in != op.n_active_out) return fail(h, QCM_ERR_INVALID, "DIAG cannot materialise qubits");
+    DiagArgs a{};
+    a.state = h->state;
+    a.n_ctrl = op.n_ctrl;
+    a.n_active = op.n_active_in;
+    a.rank_bits = rank_bits(h);
+    for (int j = 0; j < op.n_ctrl; ++j) {
+        if (op.ctrl[j] < 0 || op.ctrl[j] >= h->n_local + h->n_global) return fail(h, QCM_ERR_INVALID, "DIAG: qubit %d out of range", op.ctrl[j]);
+        a.ctrl[j] = (int8_t)op.ctrl[j];
+    }
+    const size_t real_sz = h->prec == QCM_C64 ? 4 : 8;
+    a.table = (const char *)h->tab_real.p + (size_t)op.table_off * real_sz;
+    const size_t smem = (2ull << op.n_ctrl) * real_sz;
+    if (h->prec == QCM_C64) {
+        if (a.n_active >= 1) {
+            auto k = k_diag<float, 2, 4>;
+            int grid = grid_for(h, k, smem, kThreads * 4, (1ull << a.n_active) / 2);
+            k<<<grid, kThreads, smem, h->stream>>>(a);
+        } else {
+            auto k = k_diag<float, 1, 4>;
+            k<<<1, kThreads, smem, h->stream>>>(a);
+        }
+    } else {
+        auto k = k_diag<double, 1, 4>;
+        int grid = grid_for(h, k, smem, kThreads * 4, 1ull << a.n_active);
+        k<<<grid, kThreads, smem, h->stream>>>(a);
+    }
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    h->timing.bytes_read += amp_bytes(h->prec) << a.n_active;
+    h->timing.bytes_written += amp_bytes(h->prec) << a.n_active;
+    return QCM_OK;
+}
+
+int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
+    const int n = op.n_active_out;
+    if (n < 0 || n > h->n_local) return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT over %d qubits (n_local %d)", n, h->n_local);
+    if (op.table_off < 0 || (size_t)op.table_off + 4ull * (size_t)std::max(n, 1) > n_tables + (n == 0 ? 4 : 0))
+        return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT: table outside tables");
+    const int L = n / 2;
+    int rc;
+    if ((rc = ensure(h, h->init_lo, sizeof(double2) << L))) return rc;
+    if ((rc = ensure(h, h->init_hi, sizeof(double2) << (n - L)))) return rc;
+    const double *qv = (const double *)h->tab_f64.p + op.table_off;
+    const uint64_t nt = (1ull << L) + (1ull << (n - L));
+    k_init_tables<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(qv, n, L, (double2 *)h->init_lo.p, (double2 *)h->init_hi.p);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    if (h->prec == QCM_C64) {
+        if (n >= 1) {
+            auto k = k_init<float, 2>;
+            int grid = grid_for(h, k, 0, kThreads, (1ull << n) / 2);
+            k<<<grid, kThreads, 0, h->stream>>>(h->state, (const double2 *)h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+        } else {
+            k_init<float, 1><<<1, kThreads, 0, h->stream>>>(h->state, (const double2 *)h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+        }
+    } else {
+        auto k = k_init<double, 1>;
+        int grid = grid_for(h, k, 0, kThreads, 1ull << n);
+        k<<<grid, kThreads, 0, h->stream>>>(h->state, (const double2 *)h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+    }
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    h->timing.bytes_written += amp_bytes(h->prec) << n;
+    return QCM_OK;
+}
+
+int launch_extend(qcm_handle h, int n_in, int n_out) {
+    if (n_in < 0 || n_out > h->n_local || n_in > n_out) return fail(h, QCM_ERR_INVALID, "EXTEND %d -> %d invalid", n_in, n_out);
+    if (n_in == n_out) return QCM_OK;
+    const uint64_t first = 1ull << n_in, count = (1ull << n_out) - first;
+    if (h->prec == QCM_C64) {
+        auto k = k_zero<float>;
+        k<<<grid_for(h, k, 0, kThreads, count), kThreads, 0, h->stream>>>(h->state, first, count);
+    } else {
+        auto k = k_zero<double>;
+        k<<<grid_for(h, k, 0, kThreads, count), kThreads, 0, h->stream>>>(h->state, first, count);
+    }
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    h->timing.bytes_written += amp_bytes(h->prec) * count;
+    return QCM_OK;
+}
+
+int launch_swap(qcm_handle h, const qcm_op &op) {
+    int qa = std::min(op.target, op.ctrl[0]), qb = std::max(op.target, op.ctrl[0]);
+    const int n = op.n_active_in;
+    if (qa == qb) return QCM_OK;
+    if (qa < 0 || qb >= n || op.n_active_in != op.n_active_out) return fail(h, QCM_ERR_INVALID, "SWAP(%d,%d) outside the active state (%d)", qa, qb, n);
+    const uint64_t quads = 1ull << (n - 2);
+    if (h->prec == QCM_C64) {
+        if (qa >= 1 && n >= 3) {
+            auto k = k_swap<float, 2>;
+            k<<<grid_for(h, k, 0, kThreads, quads / 2), kThreads, 0, h->stream>>>(h->state, qa, qb, n);
+        } else {
+            auto k = k_swap<float, 1>;
+            k<<<grid_for(h, k, 0, kThreads, quads), kThreads, 0, h->stream>>>(h->state, qa, qb, n);
+        }
+    } else {
+        auto k = k_swap<double, 1>;
+        k<<<grid_for(h, k, 0, kThreads, quads), kThreads, 0, h->stream>>>(h->state, qa, qb, n);
+    }
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    h->timing.bytes_read += (amp_bytes(h->prec) << n) / 2;
+    h->timing.bytes_written += (amp_bytes(h->prec) << n) / 2;
+    return QCM_OK;
+}
+
+int upload_tables(qcm_handle h, const double *tables, size_t n_tables) {
+    if (!n_tables) return QCM_OK;
+    int rc;
+    if ((rc = ensure(h, h->tab_f64, n_tables * sizeof(double)))) return rc;
+    QCM_CUDA(h, cudaMemcpyAsync(h->tab_f64.p, tables, n_tables * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->prec == QCM_C64) {
+        std::vector<float> f(n_tables);
+        for (size_t i = 0; i < n_tables; ++i) f[i] = (float)tables[i];
+        if ((rc = ensure(h, h->tab_real, n_tables * sizeof(float)))) return rc;
+        QCM_CUDA(h, cudaMemcpyAsync(h->tab_real.p, f.data(), n_tables * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        QCM_CUDA(h, cudaStreamSynchronize(h->stream));     // f goes out of scope
+    } else {
+        if ((rc = ensure(h, h->tab_real, n_tables * sizeof(double)))) return rc;
+        QCM_CUDA(h, cudaMemcpyAsync(h->tab_real.p, h->tab_f64.p, n_tables * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return QCM_OK;
+}
+
+// ---- sum tree -----------------------------------------------------------------------
+int build_tree(qcm_handle h) {
+    const int na = h->n_active;
+    const int cb = std::min(na, kChunkBits);
+    uint64_t n0 = 1ull << (na - cb);
+    uint64_t sizes[8];
+    int levels = 0;
+    uint64_t n = n0, total = 0;
+    while (true) {
+        if (levels >= 8) return fail(h, QCM_ERR_UNSUPPORTED, "sum tree too deep");
+        sizes[levels++] = n;
+        total += n;
+        if (n <= (1ull << kFanBits)) break;
+        n = (n + (1ull << kFanBits) - 1) >> kFanBits;
+    }
+    int rc;
+    if ((rc = ensure(h, h->tree, total * sizeof(double)))) return rc;
+    double *p = (double *)h->tree.p;
+    for (int l = 0; l < levels; ++l) {
+        h->tree_ptr[l] = p;
+        h->tree_n[l] = sizes[l];
+        p += sizes[l];
+    }
+    h->tree_levels = levels;
+    const uint64_t warps_per_block = kThreads / 32;
+    {
+        uint64_t blocks = std::min<uint64_t>((n0 + warps_per_block - 1) / warps_per_block, (uint64_t)h->num_sms * 8);
+        if (h->prec == QCM_C64) k_chunk_sums<float><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
+        else k_chunk_sums<double><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+    }
+    for (int l = 1; l < levels; ++l) {
+        uint64_t blocks = std::min<uint64_t>((sizes[l] + warps_per_block - 1) / warps_per_block, (uint64_t)h->num_sms * 8);
+        k_tree_level<<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->tree_ptr[l - 1], sizes[l - 1], h->tree_ptr[l], sizes[l]);
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+    }
+    const uint64_t ntop = sizes[levels - 1];
+    h->h_top.resize(ntop);
+    QCM_CUDA(h, cudaMemcpyAsync(h->h_top.data(), h->tree_ptr[levels - 1], ntop * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+    double m = 0.0;
+    for (uint64_t i = 0; i < ntop; ++i) m += h->h_top[i];
+    h->local_mass = m;
+    h->tree_valid = true;
+    h->tree_for_active = na;
+    return QCM_OK;
+}
+
+int check_device(qcm_handle h) {
+    QCM_CUDA(h, cudaSetDevice(h->device));
+    return QCM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int qcm_abi_version(void) { return QCM_ABI_VERSION; }
+
+int qcm_device_count(int *n_out) {
+    if (!n_out) return fail(nullptr, QCM_ERR_INVALID, "n_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *n_out = 0;
+        return fail(nullptr, QCM_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *n_out = n;
+    return QCM_OK;
+}
+
+const char *qcm_last_error(qcm_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int qcm_create(qcm_handle *out, int device, int n_local, int precision, void *ext_state, void *ext_stream) {
+    if (!out) return fail(nullptr, QCM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (precision != QCM_C64 && precision != QCM_C128) return fail(nullptr, QCM_ERR_INVALID, "precision must be 32 or 64");
+    if (n_local < 0 || n_local > 40) return fail(nullptr, QCM_ERR_INVALID, "n_local %d out of range [0, 40]", n_local);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, QCM_ERR_NO_DEVICE, "no CUDA device available: qcmrf_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, QCM_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    qcm_sim_s *h = new (std::nothrow) qcm_sim_s();
+    if (!h) return fail(nullptr, QCM_ERR_NOMEM, "host allocation failed");
+    h->device = device;
+    h->n_local = n_local;
+    h->prec = precision;
+    h->stream = (cudaStream_t)ext_stream;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) {
+        if (ext_state) {
+            h->state = ext_state;
+        } else {
+            e = cudaMalloc(&h->state, amp_bytes(precision) << n_local);
+            h->own_state = (e == cudaSuccess);
+        }
+    }
+    if (e != cudaSuccess) {
+        int code = fail(nullptr, e == cudaErrorMemoryAllocation ? QCM_ERR_NOMEM : QCM_ERR_CUDA, "qcm_create: %s", cudaGetErrorString(e));
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        delete h;
+        return code;
+    }
+    *out = h;
+    return QCM_OK;
+}
+
+int qcm_destroy(qcm_handle h) {
+    if (!h) return QCM_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (h->own_state && h->state) cudaFree(h->state);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return QCM_OK;
+}
+
+int qcm_set_shard(qcm_handle h, int n_global_qubits, uint64_t rank) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    if (n_global_qubits < 0 || h->n_local + n_global_qubits > 62) return fail(h, QCM_ERR_INVALID, "bad n_global_qubits %d", n_global_qubits);
+    if (n_global_qubits < 64 && rank >> n_global_qubits) return fail(h, QCM_ERR_INVALID, "rank %llu does not fit %d global qubits", (unsigned long long)rank, n_global_qubits);
+    h->n_global = n_global_qubits;
+    h->rank = rank;
+    h->tree_valid = false;
+    return QCM_OK;
+}
+
+int qcm_synchronize(qcm_handle h) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    int rc = check_device(h);
+    if (rc) return rc;
+    QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QCM_OK;
+}
+
+int qcm_get_amplitudes(qcm_handle h, uint64_t first, uint64_t count, void *host_out) {
+    if (!h || !host_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if (first + count > (1ull << h->n_local)) return fail(h, QCM_ERR_INVALID, "amplitude range outside the state");
+    int rc = check_device(h);
+    if (rc) return rc;
+    const size_t ab = amp_bytes(h->prec);
+    const uint64_t valid = 1ull << h->n_active;          // beyond: implicit zeros
+    const uint64_t vend = std::min(first + count, valid);
+    if (first < vend)
+        QCM_CUDA(h, cudaMemcpyAsync(host_out, (const char *)h->state + first * ab, (vend - first) * ab, cudaMemcpyDeviceToHost, h->stream));
+    QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (first + count > vend) {
+        const uint64_t z0 = std::max(first, vend);
+        memset((char *)host_out + (z0 - first) * ab, 0, (first + count - z0) * ab);
+    }
+    return QCM_OK;
+}
+
+int qcm_set_amplitudes(qcm_handle h, uint64_t first, uint64_t count, const void *host_in, int n_active) {
+    if (!h || !host_in) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if (first + count > (1ull << h->n_local)) return fail(h, QCM_ERR_INVALID, "amplitude range outside the state");
+    if (n_active < 0 || n_active > h->n_local) return fail(h, QCM_ERR_INVALID, "n_active out of range");
+    int rc = check_device(h);
+    if (rc) return rc;
+    const size_t ab = amp_bytes(h->prec);
+    QCM_CUDA(h, cudaMemcpyAsync((char *)h->state + first * ab, host_in, count * ab, cudaMemcpyHostToDevice, h->stream));
+    QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_active = n_active;
+    h->tree_valid = false;
+    return QCM_OK;
+}
+
+int qcm_state_ptr(qcm_handle h, void **dev_ptr_out, uint64_t *bytes_out) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    if (dev_ptr_out) *dev_ptr_out = h->state;
+    if (bytes_out) *bytes_out = amp_bytes(h->prec) << h->n_local;
+    return QCM_OK;
+}
+
+int qcm_set_active(qcm_handle h, int n_active) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    if (n_active < 0 || n_active > h->n_local) return fail(h, QCM_ERR_INVALID, "n_active out of range");
+    h->n_active = n_active;
+    h->tree_valid = false;
+    return QCM_OK;
+}
+
+int qcm_get_active(qcm_handle h, int *n_active_out) {
+    if (!h || !n_active_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    *n_active_out = h->n_active;
+    return QCM_OK;
+}
+
+int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    if (n_ops < 0 || (n_ops && !ops) || (n_tables && !tables)) return fail(h, QCM_ERR_INVALID, "NULL program");
+    int rc = check_device(h);
+    if (rc) return rc;
+    h->tree_valid = false;
+    h->timing.bytes_read = h->timing.bytes_written = 0;
+    QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    if ((rc = upload_tables(h, tables, n_tables))) return rc;
+    for (int i = 0; i < n_ops; ++i) {
+        const qcm_op &op = ops[i];
+        if (op.kind != QCM_OP_INIT_PRODUCT && op.n_active_in != h->n_active)
+            return fail(h, QCM_ERR_INVALID, "op %d expects %d materialised qubits, state has %d", i, op.n_active_in, h->n_active);
+        switch (op.kind) {
+            case QCM_OP_INIT_PRODUCT:
+                if ((rc = launch_init(h, op, n_tables))) return rc;
+                break;
+            case QCM_OP_MUX1Q: {
+                int tq[1] = {op.target};
+                if ((rc = launch_block(h, tq, 1, &op, 1, op.n_active_in, op.n_active_out, n_tables))) return rc;
+                break;
+            }
+            case QCM_OP_BLOCK: {
+                const int M = op.target, n_mem = op.n_ctrl;
+                if (M < 1 || M > QCM_MAX_BLOCK) return fail(h, QCM_ERR_INVALID, "op %d: block of %d qubits (max %d)", i, M, QCM_MAX_BLOCK);
+                if (n_mem < 0 || i + n_mem > n_ops - 1) return fail(h, QCM_ERR_INVALID, "op %d: block members run past the program", i);
+                if ((rc = launch_block(h, op.ctrl, M, ops + i + 1, n_mem, op.n_active_in, op.n_active_out, n_tables))) return rc;
+                i += n_mem;
+                break;
+            }
+            case QCM_OP_DIAG:
+                if ((rc = launch_diag(h, op, n_tables))) return rc;
+                break;
+            case QCM_OP_SWAP:
+                if ((rc = launch_swap(h, op))) return rc;
+                break;
+            case QCM_OP_EXTEND:
+                if ((rc = launch_extend(h, op.n_active_in, op.n_active_out))) return rc;
+                break;
+            default:
+                return fail(h, QCM_ERR_INVALID, "op %d: unknown kind %d", i, op.kind);
+        }
+        h->n_active = op.n_active_out;
+    }
+    QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    QCM_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->timing.program_ms = ms;
+    return QCM_OK;
+}
+
+int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *probs_out, double *kept_out) {
+    if (!h || !kept_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if (n_out_bits < 0 || n_out_bits > h->n_local || n_out_bits > 30) return fail(h, QCM_ERR_INVALID, "n_out_bits %d out of range", n_out_bits);
+    if (value & ~mask) return fail(h, QCM_ERR_INVALID, "value has bits outside mask");
+    int rc = check_device(h);
+    if (rc) return rc;
+    QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    const uint64_t nprob = 1ull << n_out_bits;
+    const uint64_t local_all = (h->n_local >= 64) ? ~0ull : ((1ull << h->n_local) - 1ull);
+    const uint64_t act_all = (1ull << h->n_active) - 1ull;
+    const uint64_t rb = rank_bits(h);
+    *kept_out = 0.0;
+    if (probs_out) memset(probs_out, 0, nprob * sizeof(double));
+    // global (rank) bits and never-materialised bits decide emptiness up front
+    bool empty = ((rb & mask & ~local_all) != (value & ~local_all));
+    if (value & local_all & ~act_all) empty = true;       // demands a 1 on a qubit known |0>
+    if (!empty) {
+        const uint64_t lmask = mask & act_all, lval = value & act_all;
+        const int nb = std::min(n_out_bits, h->n_active);
+        const uint64_t out_all = (1ull << nb) - 1ull;
+        const bool contiguous = (lval == 0) && (lmask == (act_all & ~out_all));
+        const int blocks = h->num_sms * 4;
+        if ((rc = ensure(h, h->partial, (blocks + 1) * sizeof(double)))) return rc;
+        if (probs_out && (rc = ensure(h, h->probs, nprob * sizeof(double)))) return rc;
+        double *dprobs = probs_out ? (double *)h->probs.p : nullptr;
+        if (contiguous) {
+            const uint64_t count = 1ull << nb;
+            if (dprobs && count < nprob) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * sizeof(double), h->stream));
+            if (h->prec == QCM_C64) k_probs_prefix<float><<<blocks, kThreads, 0, h->stream>>>(h->state, count, dprobs, (double *)h->partial.p);
+            else k_probs_prefix<double><<<blocks, kThreads, 0, h->stream>>>(h->state, count, dprobs, (double *)h->partial.p);
+        } else {
+            if (dprobs) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * sizeof(double), h->stream));
+            if (h->prec == QCM_C64)
+                k_postselect_general<float><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, dprobs, (double *)h->partial.p);
+            else
+                k_postselect_general<double><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, dprobs, (double *)h->partial.p);
+        }
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+        k_tree_level<<<1, kThreads, 0, h->stream>>>((const double *)h->partial.p, (uint64_t)blocks, (double *)h->partial.p + blocks, 1);
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+        QCM_CUDA(h, cudaMemcpyAsync(kept_out, (double *)h->partial.p + blocks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (probs_out) QCM_CUDA(h, cudaMemcpyAsync(probs_out, dprobs, nprob * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    QCM_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->timing.postselect_ms = ms;
+    return QCM_OK;
+}
+
+int qcm_sample_prepare(qcm_handle h, double *local_mass_out) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!h->tree_valid || h->tree_for_active != h->n_active)
+        if ((rc = build_tree(h))) return rc;
+    if (local_mass_out) *local_mass_out = h->local_mass;
+    return QCM_OK;
+}
+
+int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const double *rank_masses, int n_ranks,
+                       const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out, uint8_t *mine_out) {
+    if (!h || !keys_out || !rank_masses) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if (n_ranks < 1 || (uint64_t)n_ranks != (1ull << h->n_global)) return fail(h, QCM_ERR_INVALID, "n_ranks %d does not match %d global qubits", n_ranks, h->n_global);
+    if (n_clbits < 0 || n_clbits > 64 || (n_clbits && !clbit_qubit)) return fail(h, QCM_ERR_INVALID, "bad clbit map");
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!h->tree_valid || h->tree_for_active != h->n_active)
+        if ((rc = build_tree(h))) return rc;
+    if (shots == 0) return QCM_OK;
+    QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    SampleArgs a{};
+    a.state = h->state;
+    a.n_active = h->n_active;
+    a.n_levels = h->tree_levels;
+    for (int l = 0; l < h->tree_levels; ++l) {
+        a.level[l] = h->tree_ptr[l];
+        a.level_n[l] = h->tree_n[l];
+    }
+    a.shots = shots;
+    a.seed = seed;
+    a.stream = stream_id;
+    double lo = 0.0, total = 0.0;
+    for (int r = 0; r < n_ranks; ++r) {
+        if ((uint64_t)r == h->rank) lo = total;
+        total += rank_masses[r];
+    }
+    if (!(total > 0.0)) return fail(h, QCM_ERR_INVALID, "state has zero norm");
+    a.rank_lo = lo;
+    a.rank_hi = ((int)h->rank == n_ranks - 1) ? 1e300 : lo + rank_masses[h->rank];
+    a.total = total;
+    a.rank_bits = rank_bits(h);
+    a.n_clbits = n_clbits;
+    for (int c = 0; c < n_clbits; ++c) {
+        if (clbit_qubit[c] >= h->n_local + h->n_global) return fail(h, QCM_ERR_INVALID, "clbit %d maps to qubit %d out of range", c, clbit_qubit[c]);
+        a.clbit_qubit[c] = (int8_t)(clbit_qubit[c] < 0 ? -1 : clbit_qubit[c]);
+    }
+    if ((rc = ensure(h, h->keys, shots * sizeof(uint64_t)))) return rc;
+    if ((rc = ensure(h, h->mine, shots))) return rc;
+    a.keys_out = (uint64_t *)h->keys.p;
+    a.mine_out = (uint8_t *)h->mine.p;
+    const uint64_t wpb = kThreads / 32;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((shots + wpb - 1) / wpb, (uint64_t)h->num_sms * 8);
+    if (h->prec == QCM_C64) k_sample<float><<<blocks, kThreads, 0, h->stream>>>(a);
+    else k_sample<double><<<blocks, kThreads, 0, h->stream>>>(a);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (mine_out) QCM_CUDA(h, cudaMemcpyAsync(mine_out, h->mine.p, shots, cudaMemcpyDeviceToHost, h->stream));
+    QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    QCM_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->timing.sample_ms = ms;
+    return QCM_OK;
+}
+
+int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const int32_t *clbit_qubit, int n_clbits,
+               uint64_t *keys_out) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    if (h->n_global != 0) return fail(h, QCM_ERR_INVALID, "sharded state: use qcm_sample_prepare + qcm_sample_sharded");
+    double mass = 0.0;
+    int rc = qcm_sample_prepare(h, &mass);
+    if (rc) return rc;
+    return qcm_sample_sharded(h, shots, seed, stream_id, &mass, 1, clbit_qubit, n_clbits, keys_out, nullptr);
+}
+
+int qcm_get_timing(qcm_handle h, qcm_timing *out) {
+    if (!h || !out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    *out = h->timing;
+    return QCM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,606 @@
+// Device kernels of the qcmrf_b200 statevector engine (sm_100a).
+//
+// Everything here is HBM-bound amplitude streaming: 128-bit vector loads/stores,
+// coefficient tables staged in shared memory, enough independent loads in flight per
+// thread to cover DRAM latency, grids sized as a multiple of the SM count.  There is
+// no GEMM-shaped work on this path, so no tensor-core code ("Kernels").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qcmrf_b200.h"
+
+namespace qcm {
+
+constexpr int kThreads = 256;
+
+__host__ __device__ __forceinline__ uint64_t insert_zero(uint64_t x, int pos) {
+    const uint64_t lo = x & ((1ull << pos) - 1ull);
+    return ((x >> pos) << (pos + 1)) | lo;
+}
+
+// ----------------------------------------------------------------------------------
+// 128-bit (or 64-bit) amplitude vector IO.  V = complex numbers per vector.
+// ----------------------------------------------------------------------------------
+template <typename R, int V> struct VecIO;
+
+template <> struct VecIO<float, 2> {
+    using T = float4;
+    static __device__ __forceinline__ void load(const void *st, uint64_t amp, float (&re)[2], float (&im)[2]) {
+        const float4 t = __ldcs(reinterpret_cast<const float4 *>(st) + (amp >> 1));
+        re[0] = t.x; im[0] = t.y; re[1] = t.z; im[1] = t.w;
+    }
+    static __device__ __forceinline__ void store(void *st, uint64_t amp, const float (&re)[2], const float (&im)[2]) {
+        __stcs(reinterpret_cast<float4 *>(st) + (amp >> 1), make_float4(re[0], im[0], re[1], im[1]));
+    }
+};
+template <> struct VecIO<float, 1> {
+    using T = float2;
+    static __device__ __forceinline__ void load(const void *st, uint64_t amp, float (&re)[1], float (&im)[1]) {
+        const float2 t = __ldcs(reinterpret_cast<const float2 *>(st) + amp);
+        re[0] = t.x; im[0] = t.y;
+    }
+    static __device__ __forceinline__ void store(void *st, uint64_t amp, const float (&re)[1], const float (&im)[1]) {
+        __stcs(reinterpret_cast<float2 *>(st) + amp, make_float2(re[0], im[0]));
+    }
+};
+template <> struct VecIO<double, 1> {
+    using T = double2;
+    static __device__ __forceinline__ void load(const void *st, uint64_t amp, double (&re)[1], double (&im)[1]) {
+        const double2 t = __ldcs(reinterpret_cast<const double2 *>(st) + amp);
+        re[0] = t.x; im[0] = t.y;
+    }
+    static __device__ __forceinline__ void store(void *st, uint64_t amp, const double (&re)[1], const double (&im)[1]) {
+        __stcs(reinterpret_cast<double2 *>(st) + amp, make_double2(re[0], im[0]));
+    }
+};
+
+// ----------------------------------------------------------------------------------
+// Blocked multiplexer pass.
+//
+// One sweep applies a list of uniformly-controlled single-qubit gates ("members")
+// whose targets all lie in a set of M block qubits.  A thread owns, for one
+// assignment of the non-block bits, the 2^M amplitudes (x V consecutive ones) that
+// differ in the block bits: they sit in registers, every member is 2^(M-1)
+// register-to-register butterflies with ONE table lookup, and each amplitude crosses
+// HBM once per pass instead of once per gate.  M = 1 is the plain in-place gate pass.
+//
+// Lazy materialisation: block qubits >= n_in are known |0> on input; their upper
+// halves are not read (zero registers) and butterflies on all-zero pairs are skipped
+// (`nz` tracks which registers can be non-zero; it is uniform across the grid).
+// ----------------------------------------------------------------------------------
+struct MemberDesc {
+    int8_t pos;                     // position of the member's target inside tq[]
+    int8_t n_ctrl;
+    int8_t ctrl[QCM_MAX_CTRL];      // qubit feeding table-index bit j (may be global)
+    int32_t tab_off;                // offset, in reals, of this member's table in shared memory
+    int32_t src_off;                // offset, in reals, of the table in `tables` (global)
+};
+
+struct BlockArgs {
+    void *state;
+    const void *tables;             // device, already in the state's real type
+    int32_t n_in, n_out;
+    int32_t tq[QCM_MAX_BLOCK];      // block qubits, ascending
+    int32_t n_members;
+    uint64_t rank_bits;             // rank << n_local
+    MemberDesc mem[QCM_MAX_MEMBERS];
+};
+
+template <typename R, int V, int NR, int P>
+__device__ __forceinline__ void butterfly(R (&ar)[NR][V], R (&ai)[NR][V], const R (&m)[8], int v,
+                                          uint32_t nz) {
+    if constexpr ((1 << P) < NR) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (r & (1 << P)) continue;
+            const int r1 = r | (1 << P);
+            if (!(((nz >> r) | (nz >> r1)) & 1u)) continue;       // uniform branch
+            const R x0 = ar[r][v], y0 = ai[r][v], x1 = ar[r1][v], y1 = ai[r1][v];
+            ar[r][v] = m[0] * x0 - m[1] * y0 + m[2] * x1 - m[3] * y1;
+            ai[r][v] = m[0] * y0 + m[1] * x0 + m[2] * y1 + m[3] * x1;
+            ar[r1][v] = m[4] * x0 - m[5] * y0 + m[6] * x1 - m[7] * y1;
+            ai[r1][v] = m[4] * y0 + m[5] * x0 + m[6] * y1 + m[7] * x1;
+        }
+    }
+}
+
+template <typename R, int V, int M, int U>
+__global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
+    constexpr int NR = 1 << M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tab = reinterpret_cast<R *>(smem_raw);
+    for (int g = 0; g < a.n_members; ++g) {
+        const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
+        R *dst = tab + a.mem[g].tab_off;
+        for (int i = threadIdx.x; i < (8 << a.mem[g].n_ctrl); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    using IO = VecIO<R, V>;
+
+    uint64_t toff[M];
+    uint32_t zmask = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        toff[j] = 1ull << a.tq[j];
+        if (a.tq[j] >= a.n_in) zmask |= 1u << j;
+    }
+    uint32_t nz0 = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+        if ((r & zmask) == 0) nz0 |= 1u << r;
+
+    const uint64_t nvec = (1ull << (a.n_out - M)) / V;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
+    for (uint64_t bv0 = (uint64_t)blockIdx.x * blockDim.x * U + threadIdx.x; bv0 < nvec; bv0 += stride) {
+        R ar[U][NR][V], ai[U][NR][V];
+        uint64_t base[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t bv = bv0 + (uint64_t)u * blockDim.x;
+            ok[u] = bv < nvec;
+            uint64_t b = bv * V;
+#pragma unroll
+            for (int j = 0; j < M; ++j) b = insert_zero(b, a.tq[j]);
+            base[u] = b;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                if (ok[u] && ((nz0 >> r) & 1u)) {
+                    uint64_t off = b;
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+                        if ((r >> j) & 1) off += toff[j];
+                    IO::load(a.state, off, ar[u][r], ai[u][r]);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { ar[u][r][v] = R(0); ai[u][r][v] = R(0); }
+                }
+            }
+        }
+        uint32_t nz = nz0;
+        for (int g = 0; g < a.n_members; ++g) {
+            const int pos = a.mem[g].pos;
+            const int nc = a.mem[g].n_ctrl;
+            const R *mt = tab + a.mem[g].tab_off;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const uint64_t gi = (base[u] + v) | a.rank_bits;
+                    uint32_t idx = 0;
+                    for (int j = 0; j < nc; ++j) idx |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+                    R m[8];
+                    if constexpr (sizeof(R) == 4) {
+                        const float4 m0 = *reinterpret_cast<const float4 *>(mt + 8 * idx);
+                        const float4 m1 = *reinterpret_cast<const float4 *>(mt + 8 * idx + 4);
+                        m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w;
+                        m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const double2 t = *reinterpret_cast<const double2 *>(mt + 8 * idx + 2 * q);
+                            m[2 * q] = t.x; m[2 * q + 1] = t.y;
+                        }
+                    }
+                    switch (pos) {
+                        case 0: butterfly<R, V, NR, 0>(ar[u], ai[u], m, v, nz); break;
+                        case 1: butterfly<R, V, NR, 1>(ar[u], ai[u], m, v, nz); break;
+                        case 2: butterfly<R, V, NR, 2>(ar[u], ai[u], m, v, nz); break;
+                        case 3: butterfly<R, V, NR, 3>(ar[u], ai[u], m, v, nz); break;
+                        default: butterfly<R, V, NR, 4>(ar[u], ai[u], m, v, nz); break;
+                    }
+                }
+            }
+            // registers that can be non-zero after a butterfly on bit `pos`
+            const uint32_t sh = 1u << pos;
+            uint32_t lowsel = 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                if (!(r & sh)) lowsel |= 1u << r;
+            nz = nz | ((nz & lowsel) << sh) | ((nz & ~lowsel) >> sh);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                uint64_t off = base[u];
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    if ((r >> j) & 1) off += toff[j];
+                IO::store(a.state, off, ar[u][r], ai[u][r]);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Diagonal pass: amp *= table[index bits]
+// ----------------------------------------------------------------------------------
+struct DiagArgs {
+    void *state;
+    const void *table;              // device, 2 reals per entry
+    int32_t n_ctrl;
+    int32_t n_active;
+    int8_t ctrl[QCM_MAX_CTRL];
+    uint64_t rank_bits;
+};
+
+template <typename R, int V, int U>
+__global__ void __launch_bounds__(kThreads) k_diag(const DiagArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tab = reinterpret_cast<R *>(smem_raw);
+    {
+        const R *g = reinterpret_cast<const R *>(a.table);
+        for (int i = threadIdx.x; i < (2 << a.n_ctrl); i += blockDim.x) tab[i] = g[i];
+    }
+    __syncthreads();
+    using IO = VecIO<R, V>;
+    const uint64_t nvec = (1ull << a.n_active) / V;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
+    for (uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x * U + threadIdx.x; v0 < nvec; v0 += stride) {
+        R re[U][V], im[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+            if (vi < nvec) IO::load(a.state, vi * V, re[u], im[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+            if (vi >= nvec) continue;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint64_t gi = (vi * V + v) | a.rank_bits;
+                uint32_t idx = 0;
+                for (int j = 0; j < a.n_ctrl; ++j) idx |= (uint32_t)((gi >> a.ctrl[j]) & 1ull) << j;
+                const R c = tab[2 * idx], s = tab[2 * idx + 1];
+                const R x = re[u][v], y = im[u][v];
+                re[u][v] = c * x - s * y;
+                im[u][v] = c * y + s * x;
+            }
+            IO::store(a.state, vi * V, re[u], im[u]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Product-state initialisation (write-only).  amp[i] = lo[i & (2^L-1)] * hi[i >> L],
+// the two factor tables are built by k_init_tables from the per-qubit 2-vectors.
+// ----------------------------------------------------------------------------------
+static __global__ void k_init_tables(const double *qv /* n*4 */, int n, int L, double2 *lo, double2 *hi) {
+    const uint64_t nlo = 1ull << L, nhi = 1ull << (n - L);
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlo + nhi) return;
+    const bool is_hi = t >= nlo;
+    const uint64_t bits = is_hi ? t - nlo : t;
+    const int q0 = is_hi ? L : 0, q1 = is_hi ? n : L;
+    double re = 1.0, im = 0.0;
+    for (int q = q0; q < q1; ++q) {
+        const int b = (int)((bits >> (q - q0)) & 1ull);
+        const double fr = qv[4 * q + 2 * b], fi = qv[4 * q + 2 * b + 1];
+        const double nr = re * fr - im * fi;
+        im = re * fi + im * fr;
+        re = nr;
+    }
+    (is_hi ? hi[bits] : lo[bits]) = make_double2(re, im);
+}
+
+template <typename R, int V>
+__global__ void __launch_bounds__(kThreads) k_init(void *state, const double2 *lo, const double2 *hi, int n, int L) {
+    using IO = VecIO<R, V>;
+    const uint64_t nvec = (1ull << n) / V;
+    const uint64_t lmask = (1ull << L) - 1ull;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
+        const uint64_t i = vi * V;
+        const double2 h = __ldg(hi + (i >> L));
+        R re[V], im[V];
+        if (h.x == 0.0 && h.y == 0.0) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) { re[v] = R(0); im[v] = R(0); }
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const double2 l = __ldg(lo + ((i + v) & lmask));
+                re[v] = (R)(l.x * h.x - l.y * h.y);
+                im[v] = (R)(l.x * h.y + l.y * h.x);
+            }
+        }
+        IO::store(state, i, re, im);
+    }
+}
+
+// zero-fill amplitudes [first, first+count)
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_zero(void *state, uint64_t first, uint64_t count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        R re[1] = {R(0)}, im[1] = {R(0)};
+        VecIO<R, 1>::store(state, first + i, re, im);
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Qubit exchange (local): amplitudes with (bit a, bit b) = (1,0) <-> (0,1), a < b.
+// ----------------------------------------------------------------------------------
+template <typename R, int V>
+__global__ void __launch_bounds__(kThreads) k_swap(void *state, int qa, int qb, int n_active) {
+    using IO = VecIO<R, V>;
+    const uint64_t nvec = (1ull << (n_active - 2)) / V;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
+        uint64_t b = insert_zero(insert_zero(vi * V, qa), qb);
+        const uint64_t i10 = b | (1ull << qa), i01 = b | (1ull << qb);
+        R r0[V], m0[V], r1[V], m1[V];
+        IO::load(state, i10, r0, m0);
+        IO::load(state, i01, r1, m1);
+        IO::store(state, i10, r1, m1);
+        IO::store(state, i01, r0, m0);
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Reductions.  All sums are fp64 and use a fixed association (lane-strided partials,
+// shuffle tree) so that results do not depend on the grid or on the GPU count.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+constexpr int kChunkBits = 10;                  // 1024 amplitudes per leaf chunk
+constexpr int kFanBits = 10;                    // 1024 children per tree node
+
+// level 0: chunk c = sum_{i in chunk} |amp_i|^2 ; one warp per chunk
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int n_active, double *out) {
+    const int cb = n_active < kChunkBits ? n_active : kChunkBits;
+    const uint64_t nchunks = 1ull << (n_active - cb);
+    const uint64_t csz = 1ull << cb;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t c = warp0; c < nchunks; c += nwarps) {
+        double acc = 0.0;
+        if constexpr (sizeof(R) == 4) {
+            const float2 *p = reinterpret_cast<const float2 *>(state) + c * csz;
+            for (uint64_t i = lane; i < csz; i += 32) {
+                const float2 t = p[i];
+                acc += (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+            }
+        } else {
+            const double2 *p = reinterpret_cast<const double2 *>(state) + c * csz;
+            for (uint64_t i = lane; i < csz; i += 32) {
+                const double2 t = p[i];
+                acc += t.x * t.x + t.y * t.y;
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[c] = acc;
+    }
+}
+
+// level l+1: node j = sum of up to 1024 children ; one warp per node
+static __global__ void __launch_bounds__(kThreads) k_tree_level(const double *in, uint64_t n_in, double *out, uint64_t n_out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t j = warp0; j < n_out; j += nwarps) {
+        const uint64_t b = j << kFanBits;
+        const uint64_t e = (b + (1ull << kFanBits)) < n_in ? b + (1ull << kFanBits) : n_in;
+        double acc = 0.0;
+        for (uint64_t i = b + lane; i < e; i += 32) acc += in[i];
+        acc = warp_sum(acc);
+        if (lane == 0) out[j] = acc;
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based RNG; Salmon et al. 2011): key = seed, counter =
+// (shot, stream) -> one uniform double in [0,1) per shot, identical on every rank.
+// ----------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0];
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1];
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+
+__host__ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t stream, uint64_t shot) {
+    uint32_t c[4] = {(uint32_t)shot, (uint32_t)(shot >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    const uint64_t bits = ((uint64_t)c[0] << 21) ^ (uint64_t)(c[1] >> 11);   // 53 bits
+    return (double)(bits & ((1ull << 53) - 1ull)) * (1.0 / 9007199254740992.0);
+}
+
+// Warp-cooperative search inside one node: children [0, cnt) with masses w(i);
+// returns the first child whose inclusive prefix exceeds u (clamped to the last
+// child with non-zero mass) and subtracts the exclusive prefix from u.
+// Lane l owns children [32l, 32l+32).  Fixed evaluation order => deterministic.
+template <typename F>
+__device__ __forceinline__ uint32_t warp_pick(F w, uint32_t cnt, double &u, int lane) {
+    const uint32_t b = (uint32_t)lane * 32u;
+    double mine = 0.0;
+    for (uint32_t i = 0; i < 32u; ++i)
+        if (b + i < cnt) mine += w(b + i);
+    double incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, incl > u && mine > 0.0);
+    const unsigned any = __ballot_sync(0xffffffffu, mine > 0.0);
+    int sel;
+    if (hit) sel = __ffs(hit) - 1;
+    else if (any) sel = 31 - __clz(any);              // rounding pushed u past the total
+    else sel = 0;
+    const double excl = __shfl_sync(0xffffffffu, incl - mine, sel);
+    double rem = u - excl;
+    uint32_t child = 0;
+    double before = 0.0;
+    if (lane == sel) {
+        double acc = 0.0;
+        uint32_t last_nz = b;
+        double last_before = 0.0;
+        bool found = false;
+        for (uint32_t i = 0; i < 32u && b + i < cnt; ++i) {
+            const double wi = w(b + i);
+            if (wi > 0.0) {
+                last_nz = b + i; last_before = acc;
+                if (acc + wi > rem) { found = true; break; }
+            }
+            acc += wi;
+        }
+        (void)found;
+        child = last_nz; before = last_before;
+    }
+    child = __shfl_sync(0xffffffffu, child, sel);
+    before = __shfl_sync(0xffffffffu, before, sel);
+    rem -= before;
+    u = rem < 0.0 ? 0.0 : rem;
+    return child;
+}
+
+struct SampleArgs {
+    const void *state;
+    int32_t n_active;
+    int32_t n_levels;               // tree levels above the amplitudes (>= 1)
+    const double *level[8];         // level[0] = chunk sums ... level[n_levels-1] = top
+    uint64_t level_n[8];
+    uint64_t shots, seed, stream;
+    // sharding: rank_lo <= u*total < rank_hi selects this rank (single GPU: [0,total))
+    double rank_lo, rank_hi, total;
+    uint64_t rank_bits;
+    int32_t n_clbits;               // 0 => raw indices
+    int8_t clbit_qubit[64];
+    uint64_t *keys_out;
+    uint8_t *mine_out;              // may be null
+};
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_sample(const SampleArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int cb = a.n_active < kChunkBits ? a.n_active : kChunkBits;
+    for (uint64_t s = warp0; s < a.shots; s += nwarps) {
+        double u = philox_uniform(a.seed, a.stream, s) * a.total;
+        const bool mine = (u >= a.rank_lo) && (u < a.rank_hi);
+        if (a.mine_out && lane == 0) a.mine_out[s] = mine ? 1 : 0;
+        if (!mine) {
+            if (lane == 0) a.keys_out[s] = 0;
+            continue;
+        }
+        u -= a.rank_lo;
+        uint64_t node = 0;
+        for (int l = a.n_levels - 1; l >= 0; --l) {
+            const double *lv = a.level[l];
+            const uint64_t first = node << kFanBits;
+            const uint64_t left = a.level_n[l] - first;
+            const uint32_t cnt = left < (1ull << kFanBits) ? (uint32_t)left : (1u << kFanBits);
+            const uint32_t c = warp_pick([&](uint32_t i) { return lv[first + i]; }, cnt, u, lane);
+            node = first + c;
+        }
+        // node = chunk index; search the amplitudes of the chunk
+        const uint64_t afirst = node << cb;
+        uint32_t within;
+        if constexpr (sizeof(R) == 4) {
+            const float2 *p = reinterpret_cast<const float2 *>(a.state) + afirst;
+            within = warp_pick([&](uint32_t i) { const float2 t = p[i]; return (double)t.x * (double)t.x + (double)t.y * (double)t.y; },
+                               1u << cb, u, lane);
+        } else {
+            const double2 *p = reinterpret_cast<const double2 *>(a.state) + afirst;
+            within = warp_pick([&](uint32_t i) { const double2 t = p[i]; return t.x * t.x + t.y * t.y; },
+                               1u << cb, u, lane);
+        }
+        if (lane == 0) {
+            const uint64_t gi = (afirst + within) | a.rank_bits;
+            uint64_t key = gi;
+            if (a.n_clbits > 0) {
+                key = 0;
+                for (int c = 0; c < a.n_clbits; ++c) {
+                    const int q = a.clbit_qubit[c];
+                    if (q >= 0) key |= ((gi >> q) & 1ull) << c;
+                }
+            }
+            a.keys_out[s] = key;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Post-selection.
+// ----------------------------------------------------------------------------------
+// contiguous kept set (QCMRF: the first 2^n amplitudes): probs[i] = |amp_i|^2 and a
+// deterministic two-stage sum (per-block partials, then k_tree_level).
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_probs_prefix(const void *state, uint64_t count, double *probs, double *partial) {
+    __shared__ double wsum[kThreads / 32];
+    double acc = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        double w;
+        if constexpr (sizeof(R) == 4) {
+            const float2 t = reinterpret_cast<const float2 *>(state)[i];
+            w = (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+        } else {
+            const double2 t = reinterpret_cast<const double2 *>(state)[i];
+            w = t.x * t.x + t.y * t.y;
+        }
+        if (probs) probs[i] = w;
+        acc += w;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) t += wsum[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// general mask/value: fp64 atomics into probs, per-block partials for the kept mass
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_postselect_general(const void *state, int n_active, uint64_t rank_bits,
+                                                                  uint64_t mask, uint64_t value, uint64_t out_mask,
+                                                                  double *probs, double *partial) {
+    __shared__ double wsum[kThreads / 32];
+    double acc = 0.0;
+    const uint64_t count = 1ull << n_active;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint64_t gi = i | rank_bits;
+        if ((gi & mask) != value) continue;
+        double w;
+        if constexpr (sizeof(R) == 4) {
+            const float2 t = reinterpret_cast<const float2 *>(state)[i];
+            w = (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+        } else {
+            const double2 t = reinterpret_cast<const double2 *>(state)[i];
+            w = t.x * t.x + t.y * t.y;
+        }
+        if (probs && w != 0.0) atomicAdd(probs + (gi & out_mask), w);
+        acc += w;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kThreads / 32; ++i) t += wsum[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+}  // namespace qcm

@@ -1,0 +1,315 @@
+// Batched small-circuit path: one thread block per circuit, the whole statevector in
+// shared memory, gate program + post-selection + prefix sums + shot sampling in ONE
+// launch.  This is how the fixture-sized models of the reference's experiment
+// (70 circuits of 3..10 qubits, /root/reference/run_experiment.py:44-57) are served:
+// at those sizes a per-gate launch would be pure launch latency.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "qcm_kernels.cuh"
+#include "qcmrf_b200.h"
+
+using namespace qcm;
+
+namespace {
+
+constexpr int kSmallMaxQubits = 13;
+
+struct SmallArgs {
+    int n_circuits;
+    const int32_t *n_qubits;
+    const int64_t *op_begin;
+    const qcm_op *ops;
+    const double *tables;
+    const int32_t *clbit_qubit;   // [n_circuits][64]
+    const int32_t *n_clbits;
+    const uint64_t *ps_mask, *ps_value;
+    const int32_t *ps_bits;
+    const int64_t *probs_begin;   // offsets into probs_out
+    uint64_t shots, seed;
+    uint64_t *keys_out;
+    double *probs_out;
+    double *kept_out;
+    int32_t *status_out;          // per circuit: 0 ok, else offending op index + 1
+};
+
+template <typename R> struct Cx { R x, y; };
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_small(const SmallArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = blockIdx.x;
+    const int N = a.n_qubits[c];
+    const uint32_t dim = 1u << N;
+    Cx<R> *psi = reinterpret_cast<Cx<R> *>(smem_raw);
+    double *pre = reinterpret_cast<double *>(smem_raw + sizeof(Cx<R>) * dim);
+    __shared__ double wpart[kThreads];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    // |0...0> unless the program starts with INIT_PRODUCT
+    for (uint32_t i = tid; i < dim; i += kThreads) { psi[i].x = (i == 0) ? R(1) : R(0); psi[i].y = R(0); }
+    __syncthreads();
+
+    for (int64_t oi = a.op_begin[c]; oi < a.op_begin[c + 1]; ++oi) {
+        const qcm_op op = a.ops[oi];
+        const double *tab = a.tables + op.table_off;
+        if (op.kind == QCM_OP_INIT_PRODUCT) {
+            for (uint32_t i = tid; i < dim; i += kThreads) {
+                double re = 1.0, im = 0.0;
+                for (int q = 0; q < N; ++q) {
+                    const int b = (i >> q) & 1;
+                    const double fr = tab[4 * q + 2 * b], fi = tab[4 * q + 2 * b + 1];
+                    const double nr = re * fr - im * fi;
+                    im = re * fi + im * fr;
+                    re = nr;
+                }
+                psi[i].x = (R)re; psi[i].y = (R)im;
+            }
+        } else if (op.kind == QCM_OP_MUX1Q) {
+            const int t = op.target;
+            for (uint32_t p = tid; p < (dim >> 1); p += kThreads) {
+                const uint32_t i0 = (uint32_t)insert_zero(p, t), i1 = i0 | (1u << t);
+                uint32_t idx = 0;
+                for (int j = 0; j < op.n_ctrl; ++j) idx |= ((i0 >> op.ctrl[j]) & 1u) << j;
+                const double *m = tab + 8 * idx;
+                const R x0 = psi[i0].x, y0 = psi[i0].y, x1 = psi[i1].x, y1 = psi[i1].y;
+                const R m0 = (R)m[0], m1 = (R)m[1], m2 = (R)m[2], m3 = (R)m[3];
+                const R m4 = (R)m[4], m5 = (R)m[5], m6 = (R)m[6], m7 = (R)m[7];
+                psi[i0].x = m0 * x0 - m1 * y0 + m2 * x1 - m3 * y1;
+                psi[i0].y = m0 * y0 + m1 * x0 + m2 * y1 + m3 * x1;
+                psi[i1].x = m4 * x0 - m5 * y0 + m6 * x1 - m7 * y1;
+                psi[i1].y = m4 * y0 + m5 * x0 + m6 * y1 + m7 * x1;
+            }
+        } else if (op.kind == QCM_OP_DIAG) {
+            for (uint32_t i = tid; i < dim; i += kThreads) {
+                uint32_t idx = 0;
+                for (int j = 0; j < op.n_ctrl; ++j) idx |= ((i >> op.ctrl[j]) & 1u) << j;
+                const R cr = (R)tab[2 * idx], ci = (R)tab[2 * idx + 1];
+                const R x = psi[i].x, y = psi[i].y;
+                psi[i].x = cr * x - ci * y;
+                psi[i].y = cr * y + ci * x;
+            }
+        } else if (op.kind == QCM_OP_SWAP) {
+            const int qa = min(op.target, op.ctrl[0]), qb = max(op.target, op.ctrl[0]);
+            if (qa != qb)
+                for (uint32_t p = tid; p < (dim >> 2); p += kThreads) {
+                    const uint32_t b = (uint32_t)insert_zero(insert_zero(p, qa), qb);
+                    const uint32_t i10 = b | (1u << qa), i01 = b | (1u << qb);
+                    const Cx<R> t = psi[i10];
+                    psi[i10] = psi[i01];
+                    psi[i01] = t;
+                }
+        } else if (op.kind == QCM_OP_BLOCK || op.kind == QCM_OP_EXTEND) {
+            // members follow as plain MUX1Q ops; the state is always fully materialised here
+        } else {
+            if (tid == 0) bad = (int)(oi - a.op_begin[c]) + 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.status_out[c] = bad;
+
+    // ---- probabilities, inclusive prefix (fixed order) ---------------------------------
+    const uint32_t per = (dim + kThreads - 1) / kThreads;          // contiguous segment per thread
+    const uint32_t s0 = min(dim, tid * per), s1 = min(dim, s0 + per);
+    double acc = 0.0;
+    for (uint32_t i = s0; i < s1; ++i) {
+        const double w = (double)psi[i].x * (double)psi[i].x + (double)psi[i].y * (double)psi[i].y;
+        acc += w;
+        pre[i] = acc;
+    }
+    wpart[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double run = 0.0;
+        for (int i = 0; i < kThreads; ++i) { const double t = wpart[i]; wpart[i] = run; run += t; }
+    }
+    __syncthreads();
+    const double off = wpart[tid];
+    for (uint32_t i = s0; i < s1; ++i) pre[i] += off;
+    __syncthreads();
+    const double total = pre[dim - 1];
+
+    // ---- post-selection ------------------------------------------------------------------
+    {
+        const uint64_t mask = a.ps_mask[c], value = a.ps_value[c];
+        const uint32_t omask = (1u << a.ps_bits[c]) - 1u;
+        double *pout = a.probs_out ? a.probs_out + a.probs_begin[c] : nullptr;
+        double kept = 0.0;
+        for (uint32_t i = tid; i < dim; i += kThreads) {
+            if (((uint64_t)i & mask) != value) continue;
+            const double w = pre[i] - (i ? pre[i - 1] : 0.0);
+            const double wx = (double)psi[i].x * (double)psi[i].x + (double)psi[i].y * (double)psi[i].y;
+            (void)w;
+            kept += wx;
+            if (pout && wx != 0.0) atomicAdd(pout + (i & omask), wx);
+        }
+        kept = warp_sum(kept);
+        __syncthreads();
+        if ((tid & 31) == 0) wpart[tid >> 5] = kept;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int i = 0; i < kThreads / 32; ++i) t += wpart[i];
+            a.kept_out[c] = t;
+        }
+    }
+
+    // ---- shots --------------------------------------------------------------------------------
+    if (a.keys_out) {
+        const int ncl = a.n_clbits[c];
+        const int32_t *cq = a.clbit_qubit + 64 * c;
+        for (uint64_t s = tid; s < a.shots; s += kThreads) {
+            const double u = philox_uniform(a.seed, (uint64_t)c, s) * total;
+            uint32_t lo = 0, hi = dim - 1;             // first i with pre[i] > u
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (pre[mid] > u) hi = mid; else lo = mid + 1;
+            }
+            // rounding guard: never return a zero-probability state
+            while (lo > 0 && pre[lo] == pre[lo - 1]) --lo;
+            uint64_t key = lo;
+            if (ncl > 0) {
+                key = 0;
+                for (int b = 0; b < ncl; ++b) {
+                    const int q = cq[b];
+                    if (q >= 0) key |= (uint64_t)((lo >> q) & 1u) << b;
+                }
+            }
+            a.keys_out[(uint64_t)c * a.shots + s] = key;
+        }
+    }
+}
+
+thread_local std::string g_small_error;
+
+template <typename T>
+cudaError_t to_dev(T **d, const T *h, size_t n, cudaStream_t st) {
+    cudaError_t e = cudaMalloc((void **)d, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+}  // namespace
+
+
+
+extern "C" {
+
+int qcm_small_max_qubits(int precision) {
+    return (precision == QCM_C64 || precision == QCM_C128) ? kSmallMaxQubits : 0;
+}
+
+int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t *n_qubits, const int64_t *op_begin,
+                        const qcm_op *ops, const double *tables, size_t n_tables, const int32_t *clbit_qubit,
+                        const int32_t *n_clbits, const uint64_t *ps_mask, const uint64_t *ps_value, const int32_t *ps_bits,
+                        uint64_t shots, uint64_t seed, uint64_t *keys_out, double *probs_out, double *kept_out,
+                        double *device_ms_out) {
+    if (n_circuits <= 0 || !n_qubits || !op_begin || !ops || !ps_mask || !ps_value || !ps_bits || !kept_out) return QCM_ERR_INVALID;
+    if (precision != QCM_C64 && precision != QCM_C128) return QCM_ERR_INVALID;
+    if (shots && (!keys_out || !clbit_qubit || !n_clbits)) return QCM_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return QCM_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return QCM_ERR_INVALID;
+    int maxq = 0;
+    std::vector<int64_t> pbeg(n_circuits + 1, 0);
+    for (int c = 0; c < n_circuits; ++c) {
+        if (n_qubits[c] < 0 || n_qubits[c] > kSmallMaxQubits) return QCM_ERR_UNSUPPORTED;
+        if (ps_bits[c] < 0 || ps_bits[c] > n_qubits[c]) return QCM_ERR_INVALID;
+        if (op_begin[c + 1] < op_begin[c]) return QCM_ERR_INVALID;
+        maxq = std::max(maxq, n_qubits[c]);
+        pbeg[c + 1] = pbeg[c] + (1ll << ps_bits[c]);
+    }
+    const int64_t n_ops = op_begin[n_circuits];
+    for (int64_t i = 0; i < n_ops; ++i) {
+        const qcm_op &op = ops[i];
+        if (op.n_ctrl < 0 || (op.kind != QCM_OP_BLOCK && op.n_ctrl > QCM_MAX_CTRL)) return QCM_ERR_INVALID;
+        size_t need = op.kind == QCM_OP_MUX1Q ? (8ull << op.n_ctrl) : op.kind == QCM_OP_DIAG ? (2ull << op.n_ctrl) : 0;
+        if (need && (op.table_off < 0 || (size_t)op.table_off + need > n_tables)) return QCM_ERR_INVALID;
+    }
+#define SM_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            g_small_error = std::string(#call) + ": " + cudaGetErrorString(e_);         \
+            rc = (e_ == cudaErrorMemoryAllocation) ? QCM_ERR_NOMEM : QCM_ERR_CUDA;      \
+            goto done;                                                                  \
+        }                                                                               \
+    } while (0)
+    int rc = QCM_OK;
+    SmallArgs a{};
+    int32_t *d_nq = nullptr, *d_cq = nullptr, *d_ncl = nullptr, *d_psb = nullptr, *d_status = nullptr;
+    int64_t *d_ob = nullptr, *d_pb = nullptr;
+    qcm_op *d_ops = nullptr;
+    double *d_tab = nullptr, *d_probs = nullptr, *d_kept = nullptr;
+    uint64_t *d_pm = nullptr, *d_pv = nullptr, *d_keys = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st = nullptr;
+    std::vector<int32_t> status(n_circuits, 0);
+    const size_t amp = precision == QCM_C64 ? 8 : 16;
+    const size_t smem = ((size_t)amp + 8) << maxq;
+    SM_CUDA(cudaSetDevice(device));
+    SM_CUDA(cudaEventCreate(&e0));
+    SM_CUDA(cudaEventCreate(&e1));
+    SM_CUDA(to_dev(&d_nq, n_qubits, n_circuits, st));
+    SM_CUDA(to_dev(&d_ob, op_begin, n_circuits + 1, st));
+    SM_CUDA(to_dev(&d_ops, ops, (size_t)n_ops, st));
+    SM_CUDA(to_dev(&d_tab, tables, n_tables, st));
+    SM_CUDA(to_dev(&d_pm, ps_mask, n_circuits, st));
+    SM_CUDA(to_dev(&d_pv, ps_value, n_circuits, st));
+    SM_CUDA(to_dev(&d_psb, ps_bits, n_circuits, st));
+    SM_CUDA(to_dev(&d_pb, pbeg.data(), n_circuits + 1, st));
+    if (shots) {
+        SM_CUDA(to_dev(&d_cq, clbit_qubit, (size_t)64 * n_circuits, st));
+        SM_CUDA(to_dev(&d_ncl, n_clbits, n_circuits, st));
+        SM_CUDA(cudaMalloc((void **)&d_keys, shots * n_circuits * sizeof(uint64_t)));
+    }
+    SM_CUDA(cudaMalloc((void **)&d_kept, n_circuits * sizeof(double)));
+    SM_CUDA(cudaMalloc((void **)&d_status, n_circuits * sizeof(int32_t)));
+    if (probs_out) {
+        SM_CUDA(cudaMalloc((void **)&d_probs, pbeg[n_circuits] * sizeof(double)));
+        SM_CUDA(cudaMemsetAsync(d_probs, 0, pbeg[n_circuits] * sizeof(double), st));
+    }
+    a.n_circuits = n_circuits; a.n_qubits = d_nq; a.op_begin = d_ob; a.ops = d_ops; a.tables = d_tab;
+    a.clbit_qubit = d_cq; a.n_clbits = d_ncl; a.ps_mask = d_pm; a.ps_value = d_pv; a.ps_bits = d_psb;
+    a.probs_begin = d_pb; a.shots = shots; a.seed = seed; a.keys_out = d_keys; a.probs_out = d_probs;
+    a.kept_out = d_kept; a.status_out = d_status;
+    if (precision == QCM_C64) {
+        SM_CUDA(cudaFuncSetAttribute(k_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SM_CUDA(cudaEventRecord(e0, st));
+        k_small<float><<<n_circuits, kThreads, smem, st>>>(a);
+    } else {
+        SM_CUDA(cudaFuncSetAttribute(k_small<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SM_CUDA(cudaEventRecord(e0, st));
+        k_small<double><<<n_circuits, kThreads, smem, st>>>(a);
+    }
+    SM_CUDA(cudaGetLastError());
+    SM_CUDA(cudaEventRecord(e1, st));
+    SM_CUDA(cudaMemcpyAsync(kept_out, d_kept, n_circuits * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SM_CUDA(cudaMemcpyAsync(status.data(), d_status, n_circuits * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (probs_out) SM_CUDA(cudaMemcpyAsync(probs_out, d_probs, pbeg[n_circuits] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (shots) SM_CUDA(cudaMemcpyAsync(keys_out, d_keys, shots * n_circuits * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SM_CUDA(cudaStreamSynchronize(st));
+    if (device_ms_out) {
+        float ms = 0.f;
+        SM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *device_ms_out = ms;
+    }
+    for (int c = 0; c < n_circuits; ++c)
+        if (status[c]) { g_small_error = "circuit " + std::to_string(c) + ": unsupported op at position " + std::to_string(status[c] - 1); rc = QCM_ERR_INVALID; }
+done:
+    cudaFree(d_nq); cudaFree(d_cq); cudaFree(d_ncl); cudaFree(d_psb); cudaFree(d_status); cudaFree(d_ob); cudaFree(d_pb);
+    cudaFree(d_ops); cudaFree(d_tab); cudaFree(d_probs); cudaFree(d_kept); cudaFree(d_pm); cudaFree(d_pv); cudaFree(d_keys);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+#undef SM_CUDA
+}
+
+}  // extern "C"
