@@ -174,6 +174,7 @@ int qcm_run_batch_small(int device, int precision, int n_circuits,
                         const int32_t *clbit_qubit, const int32_t *n_clbits,
                         const uint64_t *ps_mask, const uint64_t *ps_value,
                         const int32_t *ps_bits,
+                        const uint64_t *stream_ids, /* Philox stream per circuit; NULL: index */
                         uint64_t shots, uint64_t seed,
                         uint64_t *keys_out, double *probs_out, double *kept_out,
                         double *device_ms_out);

@@ -1,0 +1,241 @@
+"""ctypes binding of the C ABI declared in include/qcmrf_b200.h.
+
+There is deliberately no fallback: if the shared library is missing, or the
+machine has no CUDA device, every compute call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .fusion import OP_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libqcmrf_b200.so')
+
+QCM_C64, QCM_C128 = 32, 64
+_STATUS = {0: 'QCM_OK', -1: 'QCM_ERR_INVALID', -2: 'QCM_ERR_CUDA', -3: 'QCM_ERR_NOMEM',
+           -4: 'QCM_ERR_UNSUPPORTED', -5: 'QCM_ERR_NO_DEVICE'}
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('%s (%d): %s' % (_STATUS.get(code, '?'), code, msg))
+        self.code = code
+
+
+class QcmTiming(ctypes.Structure):
+    _fields_ = [('program_ms', ctypes.c_double), ('sample_ms', ctypes.c_double),
+                ('postselect_ms', ctypes.c_double), ('kernel_launches', ctypes.c_uint64),
+                ('bytes_read', ctypes.c_uint64), ('bytes_written', ctypes.c_uint64)]
+
+
+_lib = None
+
+# every symbol include/qcmrf_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create', 'qcm_destroy',
+           'qcm_set_shard', 'qcm_get_amplitudes', 'qcm_set_amplitudes', 'qcm_synchronize',
+           'qcm_run_program', 'qcm_postselect', 'qcm_sample', 'qcm_sample_prepare', 'qcm_sample_sharded',
+           'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
+           'qcm_get_active', 'qcm_get_timing']
+
+
+def lib():
+    """Load libqcmrf_b200.so (built in-tree by qcmrf_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError('qcmrf_b200: CUDA engine %s is not built (run `python -m qcmrf_b200.build`); '
+                           'there is no CPU fallback' % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_double
+    L.qcm_abi_version.restype = i32
+    L.qcm_device_count.argtypes = [ctypes.POINTER(i32)]
+    L.qcm_last_error.argtypes = [vp]
+    L.qcm_last_error.restype = ctypes.c_char_p
+    L.qcm_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, vp, vp]
+    L.qcm_destroy.argtypes = [vp]
+    L.qcm_set_shard.argtypes = [vp, i32, u64]
+    L.qcm_get_amplitudes.argtypes = [vp, u64, u64, vp]
+    L.qcm_set_amplitudes.argtypes = [vp, u64, u64, vp, i32]
+    L.qcm_synchronize.argtypes = [vp]
+    L.qcm_run_program.argtypes = [vp, vp, i32, vp, ctypes.c_size_t]
+    L.qcm_postselect.argtypes = [vp, u64, u64, i32, vp, ctypes.POINTER(dbl)]
+    L.qcm_sample.argtypes = [vp, u64, u64, u64, vp, i32, vp]
+    L.qcm_sample_prepare.argtypes = [vp, ctypes.POINTER(dbl)]
+    L.qcm_sample_sharded.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp, vp]
+    L.qcm_small_max_qubits.argtypes = [i32]
+    L.qcm_run_batch_small.argtypes = [i32, i32, i32, vp, vp, vp, vp, ctypes.c_size_t, vp, vp, vp, vp, vp, vp,
+                                      u64, u64, vp, vp, vp, ctypes.POINTER(dbl)]
+    L.qcm_state_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
+    L.qcm_set_active.argtypes = [vp, i32]
+    L.qcm_get_active.argtypes = [vp, ctypes.POINTER(i32)]
+    L.qcm_get_timing.argtypes = [vp, ctypes.POINTER(QcmTiming)]
+    if L.qcm_abi_version() != 1:
+        raise RuntimeError('qcmrf_b200: ABI version mismatch')
+    assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
+    _lib = L
+    return L
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    rc = lib().qcm_device_count(ctypes.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Handle:
+    """One statevector on one GPU (see qcm_create)."""
+
+    def __init__(self, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None):
+        self._h = ctypes.c_void_p()
+        self.n_local = int(n_local)
+        self.prec = QCM_C64 if precision in ('single', 'c64', 32) else QCM_C128
+        self.cdtype = np.complex64 if self.prec == QCM_C64 else np.complex128
+        L = lib()
+        rc = L.qcm_create(ctypes.byref(self._h), int(device), self.n_local, self.prec,
+                          ctypes.c_void_p(ext_state_ptr), ctypes.c_void_p(ext_stream))
+        if rc:
+            self._h = ctypes.c_void_p()
+            raise NativeError(rc, (L.qcm_last_error(None) or b'').decode())
+
+    def _check(self, rc):
+        if rc:
+            raise NativeError(rc, (lib().qcm_last_error(self._h) or b'').decode())
+
+    def close(self):
+        if self._h:
+            lib().qcm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_shard(self, n_global, rank):
+        self._check(lib().qcm_set_shard(self._h, int(n_global), int(rank)))
+
+    def run_program(self, ops, tables):
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        tables = np.ascontiguousarray(tables, dtype=np.float64)
+        self._check(lib().qcm_run_program(self._h, _ptr(ops), len(ops), _ptr(tables), tables.size))
+
+    def postselect(self, mask, value, n_out_bits, want_probs=True):
+        probs = np.empty(1 << n_out_bits, dtype=np.float64) if want_probs else None
+        kept = ctypes.c_double()
+        self._check(lib().qcm_postselect(self._h, int(mask), int(value), int(n_out_bits), _ptr(probs),
+                                         ctypes.byref(kept)))
+        return probs, kept.value
+
+    def sample(self, shots, seed, stream_id=0, clbit_qubit=None):
+        keys = np.empty(int(shots), dtype=np.uint64)
+        cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
+        self._check(lib().qcm_sample(self._h, int(shots), int(seed), int(stream_id), _ptr(cq),
+                                     0 if cq is None else len(cq), _ptr(keys)))
+        return keys
+
+    def sample_prepare(self):
+        m = ctypes.c_double()
+        self._check(lib().qcm_sample_prepare(self._h, ctypes.byref(m)))
+        return m.value
+
+    def sample_sharded(self, shots, seed, stream_id, rank_masses, clbit_qubit=None):
+        keys = np.empty(int(shots), dtype=np.uint64)
+        mine = np.empty(int(shots), dtype=np.uint8)
+        rm = np.ascontiguousarray(rank_masses, dtype=np.float64)
+        cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
+        self._check(lib().qcm_sample_sharded(self._h, int(shots), int(seed), int(stream_id), _ptr(rm), len(rm),
+                                             _ptr(cq), 0 if cq is None else len(cq), _ptr(keys), _ptr(mine)))
+        return keys, mine.astype(bool)
+
+    def get_amplitudes(self, first=0, count=None):
+        if count is None:
+            count = (1 << self.n_local) - first
+        out = np.empty(int(count), dtype=self.cdtype)
+        self._check(lib().qcm_get_amplitudes(self._h, int(first), int(count), _ptr(out)))
+        return out
+
+    def set_amplitudes(self, amps, first=0, n_active=None):
+        amps = np.ascontiguousarray(amps, dtype=self.cdtype)
+        self._check(lib().qcm_set_amplitudes(self._h, int(first), amps.size, _ptr(amps),
+                                             self.n_local if n_active is None else int(n_active)))
+
+    def set_active(self, n_active):
+        self._check(lib().qcm_set_active(self._h, int(n_active)))
+
+    def get_active(self):
+        v = ctypes.c_int()
+        self._check(lib().qcm_get_active(self._h, ctypes.byref(v)))
+        return v.value
+
+    def state_ptr(self):
+        p, b = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(lib().qcm_state_ptr(self._h, ctypes.byref(p), ctypes.byref(b)))
+        return p.value, b.value
+
+    def synchronize(self):
+        self._check(lib().qcm_synchronize(self._h))
+
+    def timing(self):
+        t = QcmTiming()
+        self._check(lib().qcm_get_timing(self._h, ctypes.byref(t)))
+        return {f: getattr(t, f) for f, _ in QcmTiming._fields_}
+
+
+def small_max_qubits(precision='double'):
+    return lib().qcm_small_max_qubits(QCM_C64 if precision in ('single', 'c64', 32) else QCM_C128)
+
+
+def run_batch_small(plans, clbit_maps, ps, shots, seed, precision='double', device=0, want_probs=True,
+                    stream_ids=None):
+    """plans: list of fusion.Plan (fully materialised); clbit_maps: list of int arrays
+    (clbit -> physical qubit or -1); ps: list of (mask, value, bits).  Returns
+    (keys[n][shots] uint64, probs list, kept array, device_ms)."""
+    n = len(plans)
+    nq = np.array([p.n_phys for p in plans], dtype=np.int32)
+    op_begin = np.zeros(n + 1, dtype=np.int64)
+    ops, tabs, toff = [], [], 0
+    for i, p in enumerate(plans):
+        o = p.ops.copy()
+        o['table_off'] += toff
+        ops.append(o)
+        tabs.append(p.tables)
+        toff += p.tables.size
+        op_begin[i + 1] = op_begin[i] + len(o)
+    ops = np.concatenate(ops) if ops else np.zeros(0, dtype=OP_DTYPE)
+    tabs = np.concatenate(tabs) if tabs else np.zeros(0)
+    cq = np.full((n, 64), -1, dtype=np.int32)
+    ncl = np.zeros(n, dtype=np.int32)
+    for i, m in enumerate(clbit_maps):
+        cq[i, :len(m)] = m
+        ncl[i] = len(m)
+    pm = np.array([int(x[0]) for x in ps], dtype=np.uint64)
+    pv = np.array([int(x[1]) for x in ps], dtype=np.uint64)
+    pb = np.array([int(x[2]) for x in ps], dtype=np.int32)
+    keys = np.empty((n, int(shots)), dtype=np.uint64) if shots else None
+    pbeg = np.concatenate([[0], np.cumsum(1 << pb.astype(np.int64))])
+    probs = np.empty(int(pbeg[-1]), dtype=np.float64) if want_probs else None
+    kept = np.empty(n, dtype=np.float64)
+    ms = ctypes.c_double()
+    prec = QCM_C64 if precision in ('single', 'c64', 32) else QCM_C128
+    sid = None if stream_ids is None else np.ascontiguousarray(stream_ids, dtype=np.uint64)
+    rc = lib().qcm_run_batch_small(int(device), prec, n, _ptr(nq), _ptr(op_begin), _ptr(ops), _ptr(tabs), tabs.size,
+                                   _ptr(cq), _ptr(ncl), _ptr(pm), _ptr(pv), _ptr(pb), _ptr(sid), int(shots), int(seed),
+                                   _ptr(keys), _ptr(probs), _ptr(kept), ctypes.byref(ms))
+    if rc:
+        raise NativeError(rc, 'qcm_run_batch_small failed')
+    plist = [probs[pbeg[i]:pbeg[i + 1]] for i in range(n)] if want_probs else None
+    return keys, plist, kept, ms.value

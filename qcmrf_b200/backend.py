@@ -1,0 +1,319 @@
+"""Qiskit-style backend over the CUDA engine.
+
+Drop-in for the call the reference makes (/root/reference/run_experiment.py:54-57):
+
+    simulator = Aer.get_backend('qasm_simulator')
+    result = simulator.run(T, shots=SHOTS).result()
+    counts = result.get_counts()
+
+``run`` accepts one circuit or a list, transpiled (cx/id/rz/sx/x) or not, with or
+without measurements, and returns counts keyed exactly as Aer does (clbit N-1
+leftmost, one register, unmeasured clbits '0').  Beyond Aer's surface it offers the
+exact post-selected probability vector the reference otherwise estimates from
+counts (QCMRF.py:263-284, eval.py:115-123): ``Result.postselected_probabilities``
+and ``B200Simulator.exact``.
+
+All amplitude arithmetic, the post-selection reduction and the shot sampling run on
+the GPU through the C ABI (include/qcmrf_b200.h); this file only lowers, fuses,
+plans and formats.
+"""
+import os
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native, fusion, ir
+
+__all__ = ['B200Simulator', 'Job', 'Result', 'Counts']
+
+_FUSION_MODES = ('off', 'clique', 'blocked')
+
+
+class Counts(dict):
+    """get_counts() value: {bitstring: int}; plain-dict compatible (json.dumps works)."""
+
+    def shots(self):
+        return sum(self.values())
+
+    def int_outcomes(self):
+        return {int(k, 2): v for k, v in self.items()}
+
+    def most_frequent(self):
+        return max(self.items(), key=lambda kv: kv[1])[0]
+
+
+class _Prepared:
+    __slots__ = ('prog', 'fc', 'plan', 'clbit_map', 'n_vars', 'ps', 'name')
+
+
+def _keys_to_counts(keys, width):
+    vals, cnt = np.unique(keys, return_counts=True)
+    fmt = '0%db' % max(width, 1)
+    return Counts({format(int(v), fmt): int(c) for v, c in zip(vals, cnt)})
+
+
+class Result:
+    def __init__(self, entries, single, backend_name, seed, shots, time_taken):
+        self._entries = entries
+        self._single = single
+        self.backend_name = backend_name
+        self.seed = seed
+        self.shots = shots
+        self.time_taken = time_taken
+        self.success = True
+
+    def _idx(self, i):
+        if i is None:
+            if len(self._entries) != 1:
+                raise ValueError('result holds %d experiments: give an index' % len(self._entries))
+            return 0
+        if isinstance(i, (int, np.integer)):
+            return int(i)
+        for j, e in enumerate(self._entries):          # by circuit object or name
+            if e['circuit'] is i or e['name'] == i:
+                return j
+        raise KeyError(i)
+
+    def get_counts(self, experiment=None):
+        if experiment is None:
+            if self._single:
+                return self._entries[0]['counts']
+            return [e['counts'] for e in self._entries]
+        return self._entries[self._idx(experiment)]['counts']
+
+    def postselected_probabilities(self, experiment=None):
+        """(p, delta): exact pmf over the n variable qubits conditioned on every other
+        measured-out qubit being 0 (index: x_0 = MSB, as eval.py:100-101) and the success
+        probability delta."""
+        e = self._entries[self._idx(experiment)]
+        if e['probs'] is None:
+            raise ValueError('circuit has no known variable-register width: pass n= to exact() or run a QCMRF')
+        kept = e['kept']
+        p = e['probs'] / kept if kept > 0 else e['probs']
+        return p, kept
+
+    def success_probability(self, experiment=None):
+        return self._entries[self._idx(experiment)]['kept']
+
+    def metadata(self, experiment=None):
+        return self._entries[self._idx(experiment)]['meta']
+
+    def results(self):
+        return self._entries
+
+    def to_dict(self):
+        return {'backend_name': self.backend_name, 'success': True, 'shots': self.shots, 'seed': self.seed,
+                'time_taken': self.time_taken,
+                'results': [{'name': e['name'], 'counts': dict(e['counts']) if e['counts'] is not None else None,
+                             'success_probability': e['kept'], 'metadata': e['meta']} for e in self._entries]}
+
+
+class Job:
+    """Synchronous job object (the reference calls .result() immediately)."""
+
+    def __init__(self, result):
+        self._result = result
+
+    def result(self, timeout=None):
+        return self._result
+
+    def status(self):
+        return 'DONE'
+
+    def done(self):
+        return True
+
+    def job_id(self):
+        return 'qcmrf-b200-%x' % id(self)
+
+
+class B200Simulator:
+    """Statevector backend on one B200.
+
+    options: precision 'double'|'single'; fusion 'off'|'clique'|'blocked';
+    block_max 1..5 (targets per blocked pass); device; seed (None = fresh entropy, as
+    the unseeded Aer run of the reference)."""
+
+    def __init__(self, name='qasm_simulator', device=0, precision='double', fusion='blocked', block_max=4,
+                 seed=None, small_batch=True, small_fusion='off'):
+        if fusion not in _FUSION_MODES:
+            raise ValueError('fusion must be one of %r' % (_FUSION_MODES,))
+        self._name = name
+        self.device = device
+        self.precision = precision
+        self.fusion = fusion
+        self.block_max = block_max
+        self.seed = seed
+        self.small_batch = small_batch
+        self.small_fusion = small_fusion      # batched small circuits: a sweep over smem is ~free
+        self._handles = {}
+
+    def name(self):
+        return self._name
+
+    def __repr__(self):
+        return "B200Simulator('%s', precision=%s, fusion=%s)" % (self._name, self.precision, self.fusion)
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError('unknown option %s' % k)
+            setattr(self, k, v)
+
+    # -- host-side preparation -------------------------------------------------------
+    def prepare(self, circuit, n_vars=None, fusion_mode=None, block_max=None, small=False) -> _Prepared:
+        mode = fusion_mode or (self.small_fusion if small else self.fusion)
+        prog = ir.lower(circuit)
+        if prog.n_clbits > 64:
+            raise ValueError('at most 64 classical bits are supported')
+        fc = fusion.fuse(prog, 'off' if mode == 'off' else 'clique')
+        lazy = (mode == 'blocked') and not small
+        pl = fusion.plan(fc, lazy=lazy, block_max=block_max or self.block_max)
+        pr = _Prepared()
+        pr.prog, pr.fc, pr.plan = prog, fc, pl
+        pr.name = prog.name
+        pr.clbit_map = np.full(prog.n_clbits, -1, dtype=np.int32)
+        for c, q in prog.measures.items():
+            p = pl.layout[q]
+            pr.clbit_map[c] = p if p < pl.n_phys else -1
+        if n_vars is None:
+            n_vars = prog.metadata.get('num_vertices')
+        pr.n_vars = n_vars
+        pr.ps = None
+        if n_vars is not None:
+            if not 0 <= n_vars <= prog.n_qubits:
+                raise ValueError('n_vars out of range')
+            mask = 0
+            for q in range(n_vars, prog.n_qubits):
+                if pl.layout[q] < pl.n_phys:
+                    mask |= 1 << pl.layout[q]
+            pr.ps = (mask, 0, n_vars)
+        return pr
+
+    def _handle(self, n_phys, precision):
+        key = (n_phys, precision)
+        h = self._handles.get(key)
+        if h is None:
+            for k in list(self._handles):              # one big state at a time
+                self._handles.pop(k).close()
+            h = _native.Handle(n_phys, precision, self.device)
+            self._handles[key] = h
+        return h
+
+    def close(self):
+        for k in list(self._handles):
+            self._handles.pop(k).close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _probs_from_handle(self, h, pr):
+        pl = pr.plan
+        n = pr.n_vars
+        ident = all(pl.layout[q] == q for q in range(n))
+        mask, value, _ = pr.ps
+        if ident:
+            return h.postselect(mask, value, n)
+        # variables are not physical qubits 0..n-1: take the marginal on the host side
+        nb = pl.n_phys
+        if nb > 26:
+            raise ValueError('post-selected vector needs the variable qubits on the low physical qubits')
+        full, kept = h.postselect(mask, value, nb)
+        idx = np.arange(1 << nb)
+        out_idx = np.zeros(1 << nb, dtype=np.int64)
+        for q in range(n):
+            out_idx |= ((idx >> pl.layout[q]) & 1) << q
+        probs = np.zeros(1 << n)
+        np.add.at(probs, out_idx, full)
+        return probs, kept
+
+    # -- public API ---------------------------------------------------------------------
+    def run(self, circuits, shots=1024, seed=None, precision=None, n_vars=None, **options):
+        t0 = time.perf_counter()
+        single = not isinstance(circuits, (list, tuple))
+        circs = [circuits] if single else list(circuits)
+        precision = precision or self.precision
+        if seed is None:
+            seed = self.seed
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), 'little')
+        shots = int(shots)
+        small_max = _native.small_max_qubits(precision)
+        entries = [None] * len(circs)
+        small_ids, small_prep = [], []
+        for i, c in enumerate(circs):
+            nq = int(c.n_qubits if isinstance(c, ir.Program) else c.num_qubits)
+            if self.small_batch and nq <= small_max:
+                small_ids.append(i)
+                small_prep.append(self.prepare(c, n_vars=n_vars, small=True))
+            else:
+                pr = self.prepare(c, n_vars=n_vars)
+                entries[i] = self._run_large(c, pr, shots, seed, i, precision)
+        if small_ids:
+            ps = [pr.ps if pr.ps is not None else (0, 0, 0) for pr in small_prep]
+            keys, probs, kept, ms = _native.run_batch_small(
+                [pr.plan for pr in small_prep], [pr.clbit_map for pr in small_prep], ps, shots, seed,
+                precision=precision, device=self.device, want_probs=True, stream_ids=small_ids)
+            for j, (i, pr) in enumerate(zip(small_ids, small_prep)):
+                has_ps = pr.ps is not None
+                entries[i] = {
+                    'circuit': circs[i], 'name': pr.name,
+                    'counts': _keys_to_counts(keys[j], pr.prog.n_clbits) if shots else None,
+                    'probs': probs[j].copy() if has_ps else None, 'kept': float(kept[j]) if has_ps else None,
+                    'meta': {'path': 'batch_small', 'n_qubits': pr.prog.n_qubits, 'n_phys': pr.plan.n_phys,
+                             'passes': pr.plan.n_passes, 'gates_in': pr.fc.n_gates_in, 'batch_device_ms': ms,
+                             'philox_stream': i}}
+        res = Result(entries, single, self._name, seed, shots, time.perf_counter() - t0)
+        return Job(res)
+
+    def _run_large(self, circ, pr, shots, seed, stream, precision):
+        pl = pr.plan
+        h = self._handle(pl.n_phys, precision)
+        h.run_program(pl.ops, pl.tables)
+        probs = kept = None
+        if pr.ps is not None and pr.n_vars <= 30:
+            probs, kept = self._probs_from_handle(h, pr)
+        counts = None
+        if shots:
+            keys = h.sample(shots, seed, stream, pr.clbit_map if len(pr.clbit_map) else None)
+            counts = _keys_to_counts(keys, pr.prog.n_clbits)
+        t = h.timing()
+        return {'circuit': circ, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
+                'meta': {'path': 'statevector', 'n_qubits': pr.prog.n_qubits, 'n_phys': pl.n_phys,
+                         'passes': pl.n_passes, 'gates_in': pr.fc.n_gates_in, 'program_ms': t['program_ms'],
+                         'sample_ms': t['sample_ms'], 'postselect_ms': t['postselect_ms'],
+                         'bytes_read': t['bytes_read'], 'bytes_written': t['bytes_written'],
+                         'philox_stream': stream}}
+
+    def exact(self, circuit, n=None, precision=None):
+        """Exact post-selected probability vector and success probability (no shots)."""
+        res = self.run(circuit, shots=0, n_vars=n, precision=precision).result()
+        return res.postselected_probabilities(0)
+
+    def statevector(self, circuit, precision=None):
+        """Full logical statevector (small circuits; for tests and debugging)."""
+        precision = precision or self.precision
+        pr = self.prepare(circuit, fusion_mode=self.fusion)
+        pl = pr.plan
+        if pl.n_logical > 26:
+            raise ValueError('statevector() is meant for small circuits')
+        h = self._handle(pl.n_phys, precision)
+        h.run_program(pl.ops, pl.tables)
+        phys = h.get_amplitudes(0, 1 << pl.n_phys).astype(np.complex128)
+        N = pl.n_logical
+        idx = np.arange(1 << N)
+        pidx = np.zeros(1 << N, dtype=np.int64)
+        dead = np.zeros(1 << N, dtype=bool)
+        for q in range(N):
+            b = (idx >> q) & 1
+            if pl.layout[q] < pl.n_phys:
+                pidx |= b << pl.layout[q]
+            else:
+                dead |= b == 1
+        out = phys[pidx]
+        out[dead] = 0.0
+        return out * np.exp(1j * pl.global_phase)

@@ -221,8 +221,8 @@ int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
 int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
     const int n = op.n_active_out;
     if (n < 0 || n > h->n_local) return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT over %d qubits (n_local %d)", n, h->n_local);
-    if (op.table_off < 0 || (size_t)op.table_off + 4ull * (size_t)std::max(n, 1) > n_tables + (n == 0 ? 4 : 0))
-        return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT: table outside tables");
+    if (op.table_off < 0 || (size_t)op.table_off + 4ull * (size_t)std::max(n, 1) > n_tables)
+        return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT: table (max(n,1)*4 doubles) outside tables");
     const int L = n / 2;
     int rc;
     if ((rc = ensure(h, h->init_lo, sizeof(double2) << L))) return rc;

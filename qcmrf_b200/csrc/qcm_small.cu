@@ -31,6 +31,7 @@ struct SmallArgs {
     const uint64_t *ps_mask, *ps_value;
     const int32_t *ps_bits;
     const int64_t *probs_begin;   // offsets into probs_out
+    const uint64_t *stream_ids;   // may be null
     uint64_t shots, seed;
     uint64_t *keys_out;
     double *probs_out;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) k_small(const SmallArgs a) {
         const int ncl = a.n_clbits[c];
         const int32_t *cq = a.clbit_qubit + 64 * c;
         for (uint64_t s = tid; s < a.shots; s += kThreads) {
-            const double u = philox_uniform(a.seed, (uint64_t)c, s) * total;
+            const double u = philox_uniform(a.seed, a.stream_ids ? a.stream_ids[c] : (uint64_t)c, s) * total;
             uint32_t lo = 0, hi = dim - 1;             // first i with pre[i] > u
             while (lo < hi) {
                 const uint32_t mid = (lo + hi) >> 1;
@@ -209,7 +210,7 @@ int qcm_small_max_qubits(int precision) {
 int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t *n_qubits, const int64_t *op_begin,
                         const qcm_op *ops, const double *tables, size_t n_tables, const int32_t *clbit_qubit,
                         const int32_t *n_clbits, const uint64_t *ps_mask, const uint64_t *ps_value, const int32_t *ps_bits,
-                        uint64_t shots, uint64_t seed, uint64_t *keys_out, double *probs_out, double *kept_out,
+                        const uint64_t *stream_ids, uint64_t shots, uint64_t seed, uint64_t *keys_out, double *probs_out, double *kept_out,
                         double *device_ms_out) {
     if (n_circuits <= 0 || !n_qubits || !op_begin || !ops || !ps_mask || !ps_value || !ps_bits || !kept_out) return QCM_ERR_INVALID;
     if (precision != QCM_C64 && precision != QCM_C128) return QCM_ERR_INVALID;
@@ -248,7 +249,7 @@ int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t
     int64_t *d_ob = nullptr, *d_pb = nullptr;
     qcm_op *d_ops = nullptr;
     double *d_tab = nullptr, *d_probs = nullptr, *d_kept = nullptr;
-    uint64_t *d_pm = nullptr, *d_pv = nullptr, *d_keys = nullptr;
+    uint64_t *d_pm = nullptr, *d_pv = nullptr, *d_keys = nullptr, *d_sid = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaStream_t st = nullptr;
     std::vector<int32_t> status(n_circuits, 0);
@@ -265,6 +266,7 @@ int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t
     SM_CUDA(to_dev(&d_pv, ps_value, n_circuits, st));
     SM_CUDA(to_dev(&d_psb, ps_bits, n_circuits, st));
     SM_CUDA(to_dev(&d_pb, pbeg.data(), n_circuits + 1, st));
+    if (stream_ids) SM_CUDA(to_dev(&d_sid, stream_ids, n_circuits, st));
     if (shots) {
         SM_CUDA(to_dev(&d_cq, clbit_qubit, (size_t)64 * n_circuits, st));
         SM_CUDA(to_dev(&d_ncl, n_clbits, n_circuits, st));
@@ -279,7 +281,7 @@ int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t
     a.n_circuits = n_circuits; a.n_qubits = d_nq; a.op_begin = d_ob; a.ops = d_ops; a.tables = d_tab;
     a.clbit_qubit = d_cq; a.n_clbits = d_ncl; a.ps_mask = d_pm; a.ps_value = d_pv; a.ps_bits = d_psb;
     a.probs_begin = d_pb; a.shots = shots; a.seed = seed; a.keys_out = d_keys; a.probs_out = d_probs;
-    a.kept_out = d_kept; a.status_out = d_status;
+    a.kept_out = d_kept; a.status_out = d_status; a.stream_ids = d_sid;
     if (precision == QCM_C64) {
         SM_CUDA(cudaFuncSetAttribute(k_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SM_CUDA(cudaEventRecord(e0, st));
@@ -305,7 +307,7 @@ int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t
         if (status[c]) { g_small_error = "circuit " + std::to_string(c) + ": unsupported op at position " + std::to_string(status[c] - 1); rc = QCM_ERR_INVALID; }
 done:
     cudaFree(d_nq); cudaFree(d_cq); cudaFree(d_ncl); cudaFree(d_psb); cudaFree(d_status); cudaFree(d_ob); cudaFree(d_pb);
-    cudaFree(d_ops); cudaFree(d_tab); cudaFree(d_probs); cudaFree(d_kept); cudaFree(d_pm); cudaFree(d_pv); cudaFree(d_keys);
+    cudaFree(d_ops); cudaFree(d_tab); cudaFree(d_probs); cudaFree(d_kept); cudaFree(d_pm); cudaFree(d_pv); cudaFree(d_keys); cudaFree(d_sid);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return rc;

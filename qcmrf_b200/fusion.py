@@ -1,0 +1,491 @@
+"""Gate fusion and pass planning (host side of the hot path).
+
+Stage 1 ``fuse``: greedy qubit-set block fusion with structure classification.
+  Consecutive gates are accumulated into a small dense unitary over the qubits they
+  touch (<= ``q_max``); at every point where the next gate would bring in a new
+  qubit the block is *classified*, restricted to what is known about its inputs
+  (qubits never touched so far are |0>):
+    - qubits that provably return to |0> are dropped from the block (the AND
+      scratch qubit n of QCMRF.py:219-227 disappears here),
+    - what is left must be a diagonal (DIAG) or a uniformly-controlled single-qubit
+      gate (MUX1Q: block-diagonal over every qubit but one).
+  The longest prefix that classifies is emitted as ONE sweep.  For the program
+  QCMRF._build emits (QCMRF.py:216-236) -- and equally for its ``transpile``d
+  cx/rz/sx/x form -- every clique block becomes one MUX1Q on the clique's ancilla,
+  controlled by the clique's variable qubits: the uniformly-controlled RX(4 gamma)
+  of SURVEY.md App. A, found numerically rather than assumed.
+  Single-qubit gates on still-|0> qubits fold into the product-state initialiser.
+
+Stage 2 ``plan``: physical layout + lazy materialisation + blocked passes.
+  Qubits are laid out in order of first use, so the state grows from 2^n_init
+  amplitudes and a qubit that is never materialised (the scratch qubit) is never
+  stored.  Consecutive MUX1Q sweeps on distinct targets whose index qubits are not
+  block targets are merged into BLOCK passes of up to ``block_max`` targets, each
+  amplitude crossing HBM once per pass.
+
+Nothing here touches amplitudes: the output is a list of ``qcm_op`` + coefficient
+tables for the CUDA engine.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .ir import Gate, Program
+
+TOL = 1e-9
+
+QCM_OP_INIT_PRODUCT, QCM_OP_MUX1Q, QCM_OP_DIAG, QCM_OP_BLOCK, QCM_OP_SWAP, QCM_OP_EXTEND = 1, 2, 3, 4, 5, 6
+QCM_MAX_CTRL, QCM_MAX_BLOCK, QCM_MAX_MEMBERS = 10, 5, 16
+
+
+@dataclass
+class FusedOp:
+    kind: str                       # 'mux' | 'diag'
+    target: int                     # logical qubit ('mux'), -1 for 'diag'
+    ctrls: Tuple[int, ...]          # logical qubits; table-index bit j <-> ctrls[j]
+    table: np.ndarray               # mux: (2^m, 2, 2) ; diag: (2^m,)   complex128
+    zero_in: bool = False           # mux: target known |0> on input
+    n_gates: int = 0                # primitive gates folded into this op
+
+
+@dataclass
+class FusedCircuit:
+    n_qubits: int
+    init: Dict[int, np.ndarray]     # logical qubit -> its 2-vector after folded 1q gates
+    ops: List[FusedOp]
+    global_phase: float = 0.0
+    n_gates_in: int = 0
+
+
+# ------------------------------------------------------------------------------------------
+class _Block:
+    """Action of a run of gates on a growing little-endian qubit list, restricted to
+    the inputs that can occur: qubits known to be |0> when they join contribute no
+    input columns.  U has one row per basis state of all block qubits and one column
+    per basis state of the block qubits that were NOT known-|0>."""
+
+    def __init__(self, zero):
+        self.zero = zero
+        self.qubits: List[int] = []
+        self.pos: Dict[int, int] = {}
+        self.cpos: List[int] = []                  # block positions that own a column bit
+        self.U = np.ones((1, 1), dtype=np.complex128)
+        self.n_gates = 0
+
+    def add_qubit(self, q):
+        p = len(self.qubits)
+        self.pos[q] = p
+        self.qubits.append(q)
+        if q in self.zero:
+            self.U = np.concatenate([self.U, np.zeros_like(self.U)], axis=0)
+        else:
+            self.cpos.append(p)
+            self.U = np.kron(np.eye(2, dtype=np.complex128), self.U)
+
+    def apply(self, g: Gate):
+        for q in g.qubits:
+            if q not in self.pos:
+                self.add_qubit(q)
+        nq = len(self.qubits)
+        dim = 1 << nq
+        B = g.base_matrix()
+        U = self.U
+        ncol = U.shape[1]
+        p = self.pos[g.target]
+        if not g.controls:
+            Ur = U.reshape(1 << (nq - 1 - p), 2, (1 << p) * ncol)
+            a0 = Ur[:, 0, :].copy()
+            a1 = Ur[:, 1, :]
+            Ur[:, 0, :] = B[0, 0] * a0 + B[0, 1] * a1
+            Ur[:, 1, :] = B[1, 0] * a0 + B[1, 1] * a1
+        else:
+            rows = np.arange(dim)
+            cmask = cval = 0
+            for q, v in zip(g.controls, g.ctrl_values):
+                cmask |= 1 << self.pos[q]
+                cval |= v << self.pos[q]
+            tb = 1 << p
+            r0 = rows[((rows & cmask) == cval) & ((rows & tb) == 0)]
+            r1 = r0 | tb
+            a0 = U[r0]
+            a1 = U[r1]
+            U[r0] = B[0, 0] * a0 + B[0, 1] * a1
+            U[r1] = B[1, 0] * a0 + B[1, 1] * a1
+        self.n_gates += 1
+
+
+def _spread(values, positions):
+    """Scatter bit j of every value to bit positions[j]."""
+    out = np.zeros_like(values)
+    for j, p in enumerate(positions):
+        out |= ((values >> j) & 1) << p
+    return out
+
+
+def _classify(blk: _Block, tol=TOL):
+    """None if the block is not a single sweep, else (ops, touched_qubits, phase).
+    Known-|0> qubits that provably return to |0> are dropped from the sweep."""
+    Q = blk.qubits
+    nq = len(Q)
+    U = blk.U
+    ridx = np.arange(1 << nq)
+    zpos = [p for p in range(nq) if p not in blk.cpos]
+    restored = [p for p in zpos if np.abs(U[((ridx >> p) & 1) == 1]).max(initial=0.0) < tol]
+    rmask = sum(1 << p for p in restored)
+    kpos = [p for p in range(nq) if p not in restored]             # kept block positions
+    kof = {p: j for j, p in enumerate(kpos)}
+    nk = len(kpos)
+    Vc = U[(ridx & rmask) == 0]                                     # rows over kept qubits
+    kidx = np.arange(1 << nk)
+    ccols = np.arange(U.shape[1])
+    cols_k = _spread(ccols, [kof[p] for p in blk.cpos])             # column -> kept-space index
+    zk = [kof[p] for p in zpos if p not in restored]                # materialised |0> qubits
+    kq = [Q[p] for p in kpos]
+    D = kidx[:, None] ^ cols_k[None, :]
+
+    if not zk and np.abs(Vc[D != 0]).max(initial=0.0) < tol:        # ---- diagonal
+        d = Vc[cols_k, ccols]
+        if np.abs(d - d[0]).max(initial=0.0) < tol:
+            return [], [], float(np.angle(d[0]))
+        dep = [j for j in range(nk)
+               if np.abs(d[((cols_k >> j) & 1) == 0] - d[((cols_k >> j) & 1) == 1]).max() >= tol]
+        if len(dep) > QCM_MAX_CTRL:
+            return None
+        dfull = np.empty(1 << nk, dtype=np.complex128)
+        dfull[cols_k] = d
+        table = dfull[_spread(np.arange(1 << len(dep)), dep)]
+        qs = tuple(kq[j] for j in dep)
+        return [FusedOp('diag', -1, qs, table, False, blk.n_gates)], list(qs), 0.0
+
+    col_of = np.full(1 << nk, -1, dtype=np.int64)
+    col_of[cols_k] = ccols
+    for tp in range(nk):                                            # ---- multiplexer on tp
+        if zk and zk != [tp]:
+            continue                    # a materialised |0> qubit must be THE target
+        tb = 1 << tp
+        if np.abs(Vc[(D != 0) & (D != tb)]).max(initial=0.0) >= tol:
+            continue
+        others = [j for j in range(nk) if j != tp]
+        m = len(others)
+        i0 = _spread(np.arange(1 << m), others)
+        i1 = i0 | tb
+        c0 = col_of[i0]
+        table = np.zeros((1 << m, 2, 2), dtype=np.complex128)
+        table[:, 0, 0] = Vc[i0, c0]
+        table[:, 1, 0] = Vc[i1, c0]
+        zero_in = tp in zk
+        if zero_in:                     # |1> input never occurs: complete the matrix unitarily
+            table[:, 0, 1] = -np.conj(table[:, 1, 0])
+            table[:, 1, 1] = np.conj(table[:, 0, 0])
+        else:
+            c1 = col_of[i1]
+            table[:, 0, 1] = Vc[i0, c1]
+            table[:, 1, 1] = Vc[i1, c1]
+        tsel = np.arange(1 << m)
+        dep = [jj for jj in range(m)
+               if np.abs(table[((tsel >> jj) & 1) == 0] - table[((tsel >> jj) & 1) == 1]).max() >= tol]
+        if len(dep) > QCM_MAX_CTRL:
+            return None
+        table = table[_spread(np.arange(1 << len(dep)), dep)]
+        ctrls = tuple(kq[others[jj]] for jj in dep)
+        op = FusedOp('mux', kq[tp], ctrls, table, zero_in, blk.n_gates)
+        return [op], [kq[tp]] + list(ctrls), 0.0
+    return None
+
+
+def _single_gate_op(g: Gate, zero: set):
+    blk = _Block(zero)
+    blk.apply(g)
+    res = _classify(blk)
+    if res is None:
+        blk = _Block(set())
+        blk.apply(g)
+        res = _classify(blk)
+    assert res is not None, 'primitive gate must classify'
+    return res
+
+
+def direct_ops(prog: Program) -> 'FusedCircuit':
+    """One sweep per primitive gate, no matrix classification (fusion='off', and the
+    batched small-circuit path where a sweep over shared memory is almost free)."""
+    ops: List[FusedOp] = []
+    for g in prog.gates:
+        B = g.base_matrix()
+        m = len(g.controls)
+        pat = sum(v << j for j, v in enumerate(g.ctrl_values))
+        if B[0, 1] == 0 and B[1, 0] == 0:
+            if m == 0 and B[0, 0] == B[1, 1]:
+                continue                                           # identity up to phase
+            table = np.ones(2 << m, dtype=np.complex128)
+            table[pat] = B[0, 0]
+            table[pat | (1 << m)] = B[1, 1]
+            ops.append(FusedOp('diag', -1, tuple(g.controls) + (g.target,), table, False, 1))
+        else:
+            table = np.tile(np.eye(2, dtype=np.complex128), (1 << m, 1, 1))
+            table[pat] = B
+            ops.append(FusedOp('mux', g.target, tuple(g.controls), table, False, 1))
+    return FusedCircuit(prog.n_qubits, {}, ops, prog.global_phase, len(prog.gates))
+
+
+def fuse(prog: Program, mode: str = 'clique', q_max: int = 8) -> FusedCircuit:
+    """mode 'off': one sweep per primitive gate; 'clique': block fusion."""
+    if mode == 'off':
+        return direct_ops(prog)
+    zero = set(range(prog.n_qubits))
+    ops: List[FusedOp] = []
+    phase = prog.global_phase
+    gates: List[Gate] = prog.gates
+    n = len(gates)
+    last_use: Dict[int, int] = {}
+    for gi, g in enumerate(gates):
+        for q in g.qubits:
+            last_use[q] = gi
+
+    def emit(res):
+        nonlocal phase
+        new_ops, touched_q, ph = res
+        phase += ph
+        ops.extend(new_ops)
+        zero.difference_update(touched_q)
+
+    def retired(res, j):
+        """The classified sweep's target has no gate at or after position j: extending
+        the block further cannot keep it a single-target sweep."""
+        new_ops = res[0]
+        return len(new_ops) == 1 and new_ops[0].kind == 'mux' and last_use.get(new_ops[0].target, -1) < j
+
+    def lifetime_fits(t, i):
+        """Do the gates from i to the last use of qubit t touch at most q_max qubits?"""
+        seen = set()
+        for g in gates[i:last_use[t] + 1]:
+            seen.update(g.qubits)
+            if len(seen) > q_max:
+                return False
+        return True
+
+    i = 0
+    while i < n:
+        g0 = gates[i]
+        if not g0.controls and g0.target in zero and not lifetime_fits(g0.target, i):
+            # a lone preparation gate on a qubit that lives too long to be the target of
+            # one fused block (the H layer, QCMRF.py:204-205): emit now, it folds into INIT
+            emit(_single_gate_op(g0, zero))
+            i += 1
+            continue
+        blk = _Block(zero)
+        best = None
+        j = i
+        while j < n:
+            g = gates[j]
+            new = [q for q in g.qubits if q not in blk.pos]
+            if new and blk.qubits:
+                res = _classify(blk)
+                if res is not None:
+                    best = (j, res)
+                    if retired(res, j):
+                        break
+                if len(blk.qubits) + len(new) > q_max:
+                    break
+            blk.apply(g)
+            j += 1
+        else:
+            res = _classify(blk)
+            if res is not None:
+                best = (j, res)
+        if best is None:
+            best = (i + 1, _single_gate_op(gates[i], zero))
+        emit(best[1])
+        i = best[0]
+
+    # uncontrolled sweeps on still-|0> qubits belong to the product-state initialiser
+    init: Dict[int, np.ndarray] = {}
+    kept: List[FusedOp] = []
+    for op in ops:
+        if op.kind == 'mux' and not op.ctrls and op.zero_in and op.target not in init:
+            init[op.target] = op.table[0][:, 0].copy()
+        else:
+            kept.append(op)
+    return FusedCircuit(prog.n_qubits, init, kept, phase, len(prog.gates))
+
+
+# ------------------------------------------------------------------------------------------
+@dataclass
+class Plan:
+    """Engine program for one circuit."""
+    n_logical: int
+    n_phys: int                         # qubits the state buffer must hold
+    layout: List[int]                   # logical qubit -> physical (>= n_phys: never stored, always 0)
+    ops: np.ndarray                     # structured array matching qcm_op
+    tables: np.ndarray                  # float64
+    n_passes: int = 0
+    n_sweeps_unblocked: int = 0
+    bytes_algorithmic: int = 0          # per amplitude byte: filled by the backend
+    final_active: int = 0
+    global_phase: float = 0.0
+
+
+OP_DTYPE = np.dtype([('kind', '<i4'), ('target', '<i4'), ('n_ctrl', '<i4'), ('n_active_in', '<i4'),
+                     ('n_active_out', '<i4'), ('flags', '<i4'), ('ctrl', '<i4', (QCM_MAX_CTRL,)),
+                     ('table_off', '<i8')], align=True)
+
+
+class _Emitter:
+    def __init__(self):
+        self.ops = []
+        self.tabs = []
+        self.off = 0
+
+    def table(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        if self.off % 2:                           # keep 16-byte alignment of fp64 pairs
+            self.tabs.append(np.zeros(1))
+            self.off += 1
+        o = self.off
+        self.tabs.append(arr)
+        self.off += arr.size
+        return o
+
+    def op(self, kind, target=0, ctrl=(), n_in=0, n_out=0, table_off=0, n_ctrl=None):
+        rec = np.zeros((), dtype=OP_DTYPE)
+        rec['kind'], rec['target'] = kind, target
+        rec['n_ctrl'] = len(ctrl) if n_ctrl is None else n_ctrl
+        rec['n_active_in'], rec['n_active_out'] = n_in, n_out
+        rec['table_off'] = table_off
+        c = np.zeros(QCM_MAX_CTRL, dtype=np.int32)
+        c[:len(ctrl)] = ctrl
+        rec['ctrl'] = c
+        self.ops.append(rec)
+
+    def finish(self):
+        ops = np.array(self.ops, dtype=OP_DTYPE) if self.ops else np.zeros(0, dtype=OP_DTYPE)
+        tabs = np.concatenate(self.tabs) if self.tabs else np.zeros(0)
+        return ops, tabs
+
+
+def _mux_table_f64(table):
+    t = np.empty((table.shape[0], 8))
+    flat = table.reshape(-1, 4)
+    t[:, 0::2] = flat.real
+    t[:, 1::2] = flat.imag
+    return t
+
+
+def _diag_table_f64(table):
+    t = np.empty((table.shape[0], 2))
+    t[:, 0], t[:, 1] = table.real, table.imag
+    return t
+
+
+def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optional[bool] = None,
+         keep_order: bool = False) -> Plan:
+    """Lay the fused circuit out for the engine.
+
+    lazy=False  : identity layout, every qubit materialised up front, one pass per
+                  fused op (the plain in-place "gate pass" execution, Aer-like width).
+    lazy=True   : first-use layout, lazy materialisation, BLOCK passes of up to
+                  ``block_max`` targets; never-materialised qubits are not stored
+                  unless elide=False.
+    """
+    N = fc.n_qubits
+    em = _Emitter()
+    if elide is None:
+        elide = lazy
+    if not lazy:
+        layout = list(range(N))
+        order = list(range(N))
+    else:
+        order = sorted(fc.init.keys())
+        seen = set(order)
+        for op in fc.ops:
+            for q in ((op.target,) if op.kind == 'mux' else ()) + tuple(op.ctrls):
+                if q not in seen:
+                    seen.add(q)
+                    order.append(q)
+        rest = [q for q in range(N) if q not in seen]
+        layout = [0] * N
+        for p, q in enumerate(order):
+            layout[q] = p
+        for p, q in enumerate(rest):
+            layout[q] = len(order) + p
+        if not elide:
+            order = order + rest
+    n_phys = len(order)
+
+    # ---- INIT_PRODUCT ------------------------------------------------------------------
+    if lazy:
+        n_init = len(fc.init)
+        if not elide and not fc.ops:
+            n_init = n_phys
+    else:
+        n_init = n_phys
+    qv = np.zeros((max(n_init, 1), 4))
+    qv[:, 0] = 1.0
+    for q, v in fc.init.items():
+        p = layout[q]
+        if p < n_init:
+            qv[p] = [v[0].real, v[0].imag, v[1].real, v[1].imag]
+    em.op(QCM_OP_INIT_PRODUCT, n_in=0, n_out=n_init, table_off=em.table(qv))
+    active = n_init
+    n_passes = 1
+
+    # ---- sweeps ----------------------------------------------------------------------------
+    pend: List[Tuple[int, Tuple[int, ...], int]] = []      # (phys target, phys ctrls, table_off)
+    pend_targets: List[int] = []
+    pend_in = active
+
+    def flush():
+        nonlocal pend, pend_targets, pend_in, active, n_passes
+        if not pend:
+            return
+        tq = sorted(pend_targets)
+        n_out = max(active, max(tq) + 1)
+        if len(pend) == 1:
+            t, c, off = pend[0]
+            em.op(QCM_OP_MUX1Q, target=t, ctrl=c, n_in=pend_in, n_out=n_out, table_off=off)
+        else:
+            em.op(QCM_OP_BLOCK, target=len(tq), ctrl=tq, n_in=pend_in, n_out=n_out, n_ctrl=len(pend))
+            for t, c, off in pend:
+                em.op(QCM_OP_MUX1Q, target=t, ctrl=c, n_in=pend_in, n_out=n_out, table_off=off)
+        active = n_out
+        n_passes += 1
+        pend, pend_targets = [], []
+        pend_in = active
+
+    for op in fc.ops:
+        if op.kind == 'diag':
+            flush()
+            ctrl = tuple(layout[q] for q in op.ctrls)
+            em.op(QCM_OP_DIAG, ctrl=ctrl, n_in=active, n_out=active, table_off=em.table(_diag_table_f64(op.table)))
+            n_passes += 1
+            continue
+        t = layout[op.target]
+        ctrl = tuple(layout[q] for q in op.ctrls)
+        if len(ctrl) > QCM_MAX_CTRL:
+            raise ValueError('fused op has %d index qubits (max %d)' % (len(ctrl), QCM_MAX_CTRL))
+        if t >= active and t not in pend_targets:
+            # first touch of a never-materialised qubit: first-use layout makes it the
+            # next physical qubit after everything materialised or pending
+            expected = active + sum(1 for x in pend_targets if x >= active)
+            if t != expected:
+                raise AssertionError('layout/materialisation order mismatch: target %d, expected %d' % (t, expected))
+        limit = block_max if lazy else 1
+        new_targets = set(pend_targets) | {t}
+        conflict = (len(new_targets) > limit or len(pend) >= QCM_MAX_MEMBERS or
+                    any(c in new_targets for c in ctrl) or
+                    any(t in pc for _, pc, _ in pend))
+        if conflict:
+            flush()
+        if not pend:
+            pend_in = active
+        off = em.table(_mux_table_f64(op.table))
+        pend.append((t, ctrl, off))
+        if t not in pend_targets:
+            pend_targets.append(t)
+    flush()
+    if not lazy or not elide:
+        if active < n_phys:
+            em.op(QCM_OP_EXTEND, n_in=active, n_out=n_phys)
+            active = n_phys
+    ops, tabs = em.finish()
+    return Plan(N, n_phys, layout, ops, tabs, n_passes, len(fc.ops) + 1, 0, active, fc.global_phase)

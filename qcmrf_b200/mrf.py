@@ -1,0 +1,176 @@
+"""Host-side mirror of the reference's circuit constructor and result helpers.
+
+The GPU box has no /root/reference, so the product carries its own constructor with
+the reference's interface -- same class name, argument meaning, properties and
+error conditions as ``QCMRF`` in /root/reference/QCMRF.py:13-245 -- written against
+this package's circuit layer.  The gate program it records is the one
+``QCMRF._build`` emits (QCMRF.py:199-243); tests pin that equality against programs
+captured from the reference module itself (tests/golden/ref_programs.json).
+
+``extract_probs``, ``fidelity`` and ``KL`` mirror QCMRF.py:247-284 for callers that
+post-select sampled counts on the host; the exact, on-GPU version of that
+post-selection is ``Result.postselected_probabilities``.
+"""
+import itertools
+import math
+
+import numpy as np
+
+from .circuit import AND, QuantumCircuit
+
+__all__ = ['QCMRF', 'extract_probs', 'fidelity', 'KL']
+
+
+def _is_clique_list(cliques):
+    return (type(cliques) is list and len(cliques) > 0 and type(cliques[0]) is list and
+            len(cliques[0]) > 0 and type(cliques[0][0]) is int)
+
+
+class QCMRF(QuantumCircuit):
+    """Quantum-circuit Markov random field over binary variables.
+
+    Register: n variable qubits (variable v on qubit n-1-v), one scratch qubit n for
+    the clique-state AND, one ancilla per clique (qubit n+1+ii); as many clbits.
+    Measuring all ancillas as 0 leaves the variables distributed as
+    p(x) ~ exp(beta * sum_C theta[C, x_C]).
+    """
+
+    def __init__(self, cliques=None, theta=None, gamma=None, beta: float = 1, name: str = 'QCMRF',
+                 with_measurements=True, with_barriers=False,
+                 basis_gates=('cx', 'id', 'rz', 'sx', 'x')):
+        if not _is_clique_list(cliques):
+            raise ValueError('cliques must be a non-empty list of lists of int')
+        self._mrf_cliques = cliques
+        self._mrf_beta = beta
+        self._mrf_measure = with_measurements
+        self._mrf_barriers = with_barriers
+        self.basis_gates = list(basis_gates)
+        self._mrf_n = max(max(C) for C in cliques) + 1
+        self._mrf_dim = sum(2 ** len(C) for C in cliques)
+        self._mrf_cmax = max(len(C) for C in cliques)
+        for label, vec in (('theta', theta), ('gamma', gamma)):
+            if vec is not None and len(vec) != self._mrf_dim:
+                raise ValueError('%s has %d entries, the clique structure needs %d' % (label, len(vec), self._mrf_dim))
+        self._mrf_theta = None if theta is None else [float(t) for t in theta]
+        self._mrf_gamma = None if gamma is None else [float(g) for g in gamma]
+        width = self._mrf_n + len(cliques) + 1
+        super().__init__(width, width, name=name)
+        self._emit_program()
+
+    # -- the reference's read-only surface (QCMRF.py:82-157) ------------------------------
+    @property
+    def dimension(self):
+        return self._mrf_dim
+
+    @property
+    def cliques(self):
+        return self._mrf_cliques
+
+    @property
+    def num_vertices(self):
+        return self._mrf_n
+
+    num_nodes = num_vertices
+
+    @property
+    def num_cliques(self):
+        return len(self._mrf_cliques)
+
+    @property
+    def max_clique(self):
+        return self._mrf_cmax
+
+    @property
+    def beta(self):
+        return self._mrf_beta
+
+    @property
+    def theta(self):
+        """theta_i = 2 ln(cos 2 gamma_i) / beta when only gamma was given."""
+        if self._mrf_theta is None:
+            self._mrf_theta = [2.0 * math.log(math.cos(2.0 * g)) / self._mrf_beta for g in self._mrf_gamma]
+        return self._mrf_theta
+
+    @property
+    def gamma(self):
+        """gamma_i = arccos(exp(beta theta_i / 2)) / 2; theta > 0 has no circuit angle (NaN,
+        as in the reference, which only ever draws theta <= 0)."""
+        if self._mrf_gamma is None:
+            with np.errstate(invalid='ignore'):
+                self._mrf_gamma = [float(0.5 * np.arccos(np.exp(self._mrf_beta * 0.5 * t))) for t in self._mrf_theta]
+        return self._mrf_gamma
+
+    # -- program ---------------------------------------------------------------------------
+    def _clique_unitary(self, index, clique, angles):
+        """cU_C: on (variables..., scratch, ancilla) -- for every clique state y add the
+        phase 2*gamma_{C,y} to ancilla=1 where x_C == y, via AND / CP / AND."""
+        n = self._mrf_n
+        block = QuantumCircuit(n + 2, name='cU_C%d' % index)
+        wires = [n - 1 - v for v in clique] + [n]
+        for y, g in zip(itertools.product((0, 1), repeat=len(clique)), angles):
+            if np.isclose(g, 0):
+                continue
+            marker = AND(len(clique), [2 * b - 1 for b in y])
+            block.append(marker, wires)
+            block.cp(2 * g, n, n + 1)
+            block.append(marker, wires)
+        return block
+
+    def _emit_program(self):
+        n = self._mrf_n
+        for q in range(n):
+            self.h(q)
+        if self._mrf_barriers:
+            self.barrier()
+        if self._mrf_theta is None and self._mrf_gamma is None:
+            # the reference draws theta ~ U(-5, 0) from numpy's global state here
+            self._mrf_theta = [float(np.random.uniform(low=-5.0, high=0)) for _ in range(self._mrf_dim)]
+        gam = self.gamma
+        offset = 0
+        main = list(range(n + 1))
+        for ii, C in enumerate(self._mrf_cliques):
+            anc = n + 1 + ii
+            block = self._clique_unitary(ii, C, gam[offset:offset + 2 ** len(C)])
+            offset += 2 ** len(C)
+            self.h(anc)
+            self.append(block, main + [anc])
+            self.x([anc])
+            self.append(block.inverse(), main + [anc])
+            self.x([anc])
+            self.h(anc)
+            if self._mrf_measure:
+                self.measure(anc, anc)
+            if self._mrf_barriers:
+                self.barrier()
+        if self._mrf_measure:
+            self.measure(range(n), range(n))
+
+
+def fidelity(P, Q):
+    """(sum_i sqrt(P_i Q_i))^2 over entries where both are positive."""
+    P = np.asarray(P, dtype=np.float64)
+    Q = np.asarray(Q, dtype=np.float64)
+    both = (P > 0) & (Q > 0)
+    return float(np.sqrt(P[both] * Q[both]).sum() ** 2)
+
+
+def KL(P, Q):
+    """sum_i P_i ln(P_i / Q_i) over entries where both are positive."""
+    P = np.asarray(P, dtype=np.float64)
+    Q = np.asarray(Q, dtype=np.float64)
+    both = (P > 0) & (Q > 0)
+    return float((P[both] * np.log(P[both] / Q[both])).sum())
+
+
+def extract_probs(R, n, a):
+    """Post-select a counts dict: keep keys '0'*a + x_0..x_{n-1}.  Returns
+    (pmf over x with x_0 as MSB, kept fraction), or (zeros, 0) when nothing survives."""
+    P = np.zeros(2 ** n)
+    prefix = '0' * a
+    for key, val in R.items():
+        if len(key) == a + n and key.startswith(prefix):
+            P[int(key[a:], 2)] += val
+    kept = P.sum()
+    if kept == 0:
+        return P, 0
+    return P / kept, kept / sum(R.values())
