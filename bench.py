@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Headline benchmark: QCMRF circuits/sec on the 34-qubit complex64 synthetic tree MRF
+(BASELINE.json config 4; config 3's 33-qubit graph with --workload q33), with the
+achieved HBM GB/s of the dominant gate pass against the measured B200 roofline and the
+CPU restatement of the reference path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one circuit: product-state init (+H layer), the fused clique passes, the
+ancilla post-selection reduction with the exact 2^n pmf, and 10000 sampled shots
+(the reference's SHOTS, run_experiment.py:16).  `value` times that with the fused
+program already planned and its coefficient tables on the host (the state never
+leaves HBM: it is 64 GiB, far beyond the 126 MB L2, so no L2 flush is needed); `e2e`
+times the public call -- ``B200Simulator.run(QCMRF(cliques, theta), shots)`` from host
+objects to a counts dict and the pmf in host memory, including lowering, fusion,
+planning, table upload and result download -- with a fresh theta every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SHOTS = 10000
+METRIC = 'QCMRF circuits/sec'
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference(target_cliques, steps=1, warmup=0, sample_vars=None):
+    """The reference path on the host cores: one OpenMP sweep of a dense complex128 state per
+    gate of QCMRF._build's program (what Aer's statevector does for run_experiment.py:56),
+    post-selection, 10000 shots.  The 34-qubit state (256 GiB complex128) cannot be held on
+    the host, so a member of the same family (random tree MRF) with fewer variables is
+    timed and scaled by (gate sweeps x 2^N): the path is DRAM-bound, time is linear in both."""
+    from oracle import cbridge, program
+    from qcmrf_b200 import workloads
+    cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    n_t, k_t, N_t, _ = program.sizes(target_cliques)
+    if sample_vars is None:
+        sample_vars = 12 if cores < 32 else 13
+    Cs = workloads.random_tree(sample_vars, 0)
+    ths = workloads.theta_for(Cs)
+    n_s, k_s, N_s, _ = program.sizes(Cs)
+    ops_s, _ = program.qcmrf_program(Cs, ths)
+    arr, n_ops, meas = cbridge.compile_unfused(ops_s)
+    ops_t, _ = program.qcmrf_program(target_cliques, workloads.theta_for(target_cliques))
+    g_t = sum(1 for g in ops_t if g[0] not in ('measure', 'barrier'))
+    mask = ((1 << N_s) - 1) & ~((1 << n_s) - 1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        psi = cbridge.run(N_s, arr, n_ops)
+        cbridge.postselect(N_s, psi, mask, 0, n_s)
+        cbridge.sample(N_s, psi, SHOTS, 1984 + it)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        del psi
+    t_s = float(np.mean(times))
+    scale = (g_t * 2.0 ** N_t) / (n_ops * 2.0 ** N_s)
+    t_target = t_s * scale
+    sample = ('random tree MRF n=%d (N=%d qubits, %d gate sweeps, complex128, %d shots): %.3f s/circuit on %d '
+              'threads; scaled x%.4g = (%d sweeps x 2^%d)/(%d sweeps x 2^%d) to the %d-qubit workload'
+              % (n_s, N_s, n_ops, SHOTS, t_s, cores, scale, g_t, N_t, n_ops, N_s, N_t))
+    return {'value': 1.0 / t_target, 'unit': 'circuits/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+            'sample_seconds_per_circuit': t_s, 'sample_amp_updates_per_sec': n_ops * 2.0 ** N_s / t_s,
+            'steps_timed': len(times)}, t_target
+
+
+def run_reference_arm(args, cliques, N):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    base, t_target = cpu_reference(cliques, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'circuits/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t_target * 1e3,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args, cliques, N), 'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': 'circuits/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cliques, N):
+    n = max(max(c) for c in cliques) + 1
+    return {'workload': '%s: synthetic random-tree MRF, n=%d variables, k=%d pair cliques, N=%d total qubits, '
+                        'complex64, %d shots + exact post-selected pmf per circuit' % (args.workload, n, len(cliques), N, SHOTS),
+            'total_qubits': N, 'variables': n, 'cliques': len(cliques), 'shots': SHOTS,
+            'l2': 'state (>= 8 GiB per GPU) far exceeds the 126 MB L2; no flush needed'}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='q34')
+    ap.add_argument('--block-max', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'b200':
+        args.warmup = 3
+
+    from qcmrf_b200 import workloads
+    cliques, N = workloads.named(args.workload)
+    if args.impl == 'reference':
+        run_reference_arm(args, cliques, N)
+        return
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('bench.py --gpus %d must be launched with torch.distributed.run (one rank per GPU)' % args.gpus)
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; qcmrf_b200 has no CPU path (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from qcmrf_b200 import QCMRF, B200Simulator
+    if world > 1:
+        from qcmrf_b200.sharded import ShardedSimulator
+        sim = ShardedSimulator(precision='single', block_max=args.block_max, device=local_rank, seed=1984)
+    else:
+        sim = B200Simulator(precision='single', fusion='blocked', block_max=args.block_max, device=local_rank,
+                            seed=1984, small_batch=False)
+    thetas = [workloads.theta_for(cliques, seed=1984 + i) for i in range(args.warmup + args.steps + 2)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-timed arm: planned program resident, tables on the host -----------------
+    circ = QCMRF(cliques, thetas[0])
+    prep = sim.prepare(circ)
+    n_vars = prep.n_vars
+    for _ in range(args.warmup):
+        out = sim.execute(prep, SHOTS, seed=1984, stream=0)
+    launches0 = sim.kernel_launches()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    prof = None
+    for _ in range(args.steps):
+        out = sim.execute(prep, SHOTS, seed=1984, stream=0)
+        if prof is None:
+            prof = sim.op_profile()
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = sim.kernel_launches() - launches0
+    ms = torch.tensor([max(dev_ms, 0.0), wall_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = (float(x) for x in ms.cpu())
+    ms_per_step = dev_ms / args.steps
+
+    # ---- end-to-end arm: the public call, host objects in, host results out ------------
+    e2e_ms = []
+    h2d = d2h = 0
+    for i in range(args.steps):
+        th = thetas[args.warmup + i + 1]
+        barrier()
+        t1 = time.perf_counter()
+        res = sim.run(QCMRF(cliques, th), shots=SHOTS, seed=1984 + i).result()
+        counts = res.get_counts()
+        p, delta = res.postselected_probabilities(0)
+        torch.cuda.synchronize()
+        e2e_ms.append((time.perf_counter() - t1) * 1e3)
+        meta = res.metadata(0)
+        h2d, d2h = meta.get('h2d_bytes', 0), meta.get('d2h_bytes', 0)
+    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_mean = float(e2e_t.cpu())
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        # dominant launch of one program
+        top = max(prof, key=lambda r: r[1])
+        kind, top_ms, rd, wr = top
+        achieved = (rd + wr) / (top_ms * 1e-3) / 1e9
+        total_bytes = sum(r[2] + r[3] for r in prof)
+        prog_ms = sum(r[1] for r in prof)
+        line = {'metric': METRIC, 'value': world_value(1e3 / ms_per_step), 'unit': 'circuits/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': workload_config(args, cliques, N),
+                'clocks': clk,
+                'e2e': {'value': 1e3 / e2e_ms_mean, 'unit': 'circuits/s', 'h2d_bytes_per_step': int(h2d),
+                        'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms_mean},
+                'gpu_launches': int(launches),
+                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                             'traffic': None, 'peak_source': peak_src,
+                             'kernel': 'k_block (op kind %d): reads %d B, writes %d B in %.3f ms' % (kind, rd, wr, top_ms)},
+                'program': {'passes': [{'kind': r[0], 'ms': r[1], 'read': r[2], 'written': r[3],
+                                        'gbs': (r[2] + r[3]) / max(r[1], 1e-9) / 1e6} for r in prof],
+                            'program_ms': prog_ms, 'program_gbs': total_bytes / max(prog_ms, 1e-9) / 1e6,
+                            'wall_ms_per_step': wall_ms / args.steps},
+                'hbm_gbs_program': total_bytes / max(prog_ms, 1e-9) / 1e6,
+                'check': {'delta': float(delta), 'p_sum': float(np.sum(p)), 'shots': int(sum(counts.values()))}}
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'], _ = cpu_reference(cliques, steps=1, warmup=0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    sim.close()
+
+
+def world_value(v):
+    return float(v)
+
+
+if __name__ == '__main__':
+    main()

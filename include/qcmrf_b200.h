@@ -188,6 +188,12 @@ int qcm_set_active(qcm_handle h, int n_active);
 int qcm_get_active(qcm_handle h, int *n_active_out);
 
 int qcm_get_timing(qcm_handle h, qcm_timing *out);
+/* Per-launch record of the last qcm_run_program (one entry per executed op; a BLOCK and
+ * its members are one entry): device milliseconds (CUDA events on the handle's stream)
+ * and algorithmic bytes read / written.  Up to `cap` entries are copied; *n_out receives
+ * the number available.  bench.py derives roofline.achieved from these.                */
+int qcm_get_op_profile(qcm_handle h, int cap, int32_t *kind_out, float *ms_out,
+                       uint64_t *bytes_read_out, uint64_t *bytes_written_out, int *n_out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -37,7 +37,7 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_set_shard', 'qcm_get_amplitudes', 'qcm_set_amplitudes', 'qcm_synchronize',
            'qcm_run_program', 'qcm_postselect', 'qcm_sample', 'qcm_sample_prepare', 'qcm_sample_sharded',
            'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
-           'qcm_get_active', 'qcm_get_timing']
+           'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile']
 
 
 def lib():
@@ -72,6 +72,7 @@ def lib():
     L.qcm_set_active.argtypes = [vp, i32]
     L.qcm_get_active.argtypes = [vp, ctypes.POINTER(i32)]
     L.qcm_get_timing.argtypes = [vp, ctypes.POINTER(QcmTiming)]
+    L.qcm_get_op_profile.argtypes = [vp, i32, vp, vp, vp, vp, ctypes.POINTER(i32)]
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
     assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
@@ -188,6 +189,15 @@ class Handle:
 
     def synchronize(self):
         self._check(lib().qcm_synchronize(self._h))
+
+    def op_profile(self):
+        """[(kind, ms, bytes_read, bytes_written)] for every launch of the last program."""
+        n = ctypes.c_int()
+        self._check(lib().qcm_get_op_profile(self._h, 0, None, None, None, None, ctypes.byref(n)))
+        k = np.zeros(n.value, dtype=np.int32); ms = np.zeros(n.value, dtype=np.float32)
+        rd = np.zeros(n.value, dtype=np.uint64); wr = np.zeros(n.value, dtype=np.uint64)
+        self._check(lib().qcm_get_op_profile(self._h, n.value, _ptr(k), _ptr(ms), _ptr(rd), _ptr(wr), ctypes.byref(n)))
+        return [(int(a), float(b), int(c), int(d)) for a, b, c, d in zip(k, ms, rd, wr)]
 
     def timing(self):
         t = QcmTiming()

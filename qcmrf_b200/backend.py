@@ -148,6 +148,7 @@ class B200Simulator:
         self.small_batch = small_batch
         self.small_fusion = small_fusion      # batched small circuits: a sweep over smem is ~free
         self._handles = {}
+        self._last = None
 
     def name(self):
         return self._name
@@ -270,24 +271,43 @@ class B200Simulator:
         res = Result(entries, single, self._name, seed, shots, time.perf_counter() - t0)
         return Job(res)
 
-    def _run_large(self, circ, pr, shots, seed, stream, precision):
+    def execute(self, pr, shots, seed=0, stream=0, precision=None, want_probs=True):
+        """Run one prepared circuit on the large-state path: program, post-selection, shots.
+        Returns (keys or None, probs or None, kept or None)."""
         pl = pr.plan
-        h = self._handle(pl.n_phys, precision)
+        h = self._handle(pl.n_phys, precision or self.precision)
+        self._last = h
         h.run_program(pl.ops, pl.tables)
         probs = kept = None
-        if pr.ps is not None and pr.n_vars <= 30:
+        if want_probs and pr.ps is not None and pr.n_vars <= 30:
             probs, kept = self._probs_from_handle(h, pr)
-        counts = None
+        keys = None
         if shots:
             keys = h.sample(shots, seed, stream, pr.clbit_map if len(pr.clbit_map) else None)
-            counts = _keys_to_counts(keys, pr.prog.n_clbits)
+        return keys, probs, kept
+
+    def kernel_launches(self):
+        """Kernels launched so far by the live state handles (bench.py's gpu_launches)."""
+        return sum(h.timing()['kernel_launches'] for h in self._handles.values())
+
+    def op_profile(self):
+        """Per-launch (kind, ms, bytes_read, bytes_written) of the last executed program."""
+        return self._last.op_profile()
+
+    def _run_large(self, circ, pr, shots, seed, stream, precision):
+        pl = pr.plan
+        keys, probs, kept = self.execute(pr, shots, seed, stream, precision)
+        h = self._last
+        counts = _keys_to_counts(keys, pr.prog.n_clbits) if shots else None
         t = h.timing()
+        h2d = pl.ops.nbytes + pl.tables.nbytes + (pr.clbit_map.nbytes if shots else 0)
+        d2h = (probs.nbytes + 8 if probs is not None else 0) + (keys.nbytes if keys is not None else 0)
         return {'circuit': circ, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
                 'meta': {'path': 'statevector', 'n_qubits': pr.prog.n_qubits, 'n_phys': pl.n_phys,
                          'passes': pl.n_passes, 'gates_in': pr.fc.n_gates_in, 'program_ms': t['program_ms'],
                          'sample_ms': t['sample_ms'], 'postselect_ms': t['postselect_ms'],
                          'bytes_read': t['bytes_read'], 'bytes_written': t['bytes_written'],
-                         'philox_stream': stream}}
+                         'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': stream}}
 
     def exact(self, circuit, n=None, precision=None):
         """Exact post-selected probability vector and success probability (no shots)."""

@@ -49,6 +49,11 @@ struct qcm_sim_s {
     int tree_for_active = -1;
     double local_mass = 0.0;
     bool tree_valid = false;
+    // per-op profile of the last program
+    std::vector<cudaEvent_t> op_ev;
+    std::vector<int32_t> op_kind;
+    std::vector<uint64_t> op_rd, op_wr;
+    std::vector<float> op_ms;
 };
 
 namespace {
@@ -435,6 +440,7 @@ int qcm_destroy(qcm_handle h) {
     if (h->own_state && h->state) cudaFree(h->state);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->op_ev) cudaEventDestroy(e);
     delete h;
     return QCM_OK;
 }
@@ -519,8 +525,21 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     h->timing.bytes_read = h->timing.bytes_written = 0;
     QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if ((rc = upload_tables(h, tables, n_tables))) return rc;
+    h->op_kind.clear(); h->op_rd.clear(); h->op_wr.clear(); h->op_ms.clear();
+    size_t n_ev = 0;
+    auto mark = [&](void) -> cudaError_t {
+        if (n_ev >= h->op_ev.size()) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            h->op_ev.push_back(e);
+        }
+        return cudaEventRecord(h->op_ev[n_ev++], h->stream);
+    };
+    QCM_CUDA(h, mark());
     for (int i = 0; i < n_ops; ++i) {
         const qcm_op &op = ops[i];
+        const uint64_t rd0 = h->timing.bytes_read, wr0 = h->timing.bytes_written;
         if (op.kind != QCM_OP_INIT_PRODUCT && op.n_active_in != h->n_active)
             return fail(h, QCM_ERR_INVALID, "op %d expects %d materialised qubits, state has %d", i, op.n_active_in, h->n_active);
         switch (op.kind) {
@@ -553,12 +572,32 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 return fail(h, QCM_ERR_INVALID, "op %d: unknown kind %d", i, op.kind);
         }
         h->n_active = op.n_active_out;
+        QCM_CUDA(h, mark());
+        h->op_kind.push_back(op.kind);
+        h->op_rd.push_back(h->timing.bytes_read - rd0);
+        h->op_wr.push_back(h->timing.bytes_written - wr0);
     }
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->timing.program_ms = ms;
+    h->op_ms.resize(h->op_kind.size());
+    for (size_t k = 0; k < h->op_kind.size(); ++k) QCM_CUDA(h, cudaEventElapsedTime(&h->op_ms[k], h->op_ev[k], h->op_ev[k + 1]));
+    return QCM_OK;
+}
+
+int qcm_get_op_profile(qcm_handle h, int cap, int32_t *kind_out, float *ms_out, uint64_t *bytes_read_out,
+                       uint64_t *bytes_written_out, int *n_out) {
+    if (!h || !n_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    const int n = (int)h->op_ms.size();
+    *n_out = n;
+    for (int k = 0; k < n && k < cap; ++k) {
+        if (kind_out) kind_out[k] = h->op_kind[k];
+        if (ms_out) ms_out[k] = h->op_ms[k];
+        if (bytes_read_out) bytes_read_out[k] = h->op_rd[k];
+        if (bytes_written_out) bytes_written_out[k] = h->op_wr[k];
+    }
     return QCM_OK;
 }
 

@@ -1,0 +1,171 @@
+"""The reference-facing surface: the QCMRF mirror, the compat shims, and -- when the
+reference checkout is present (build container only) -- the reference's own
+QCMRF.py / run_experiment.py / eval.py running UNCHANGED on this package.
+CPU only; the engine is replaced by tests/fake_native.py where a run is needed."""
+import contextlib
+import io
+import json
+import os
+import runpy
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+import fake_native
+from conftest import GOLDEN
+from oracle import mrf as omrf, program, statevector as sv
+from qcmrf_b200 import QCMRF, KL, compat, extract_probs, fidelity, ir
+
+REF = '/root/reference'
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'QCMRF.py')),
+                               reason='reference checkout not present (GPU box)')
+
+
+def test_qcmrf_validation_and_properties():
+    with pytest.raises(ValueError):
+        QCMRF([0, 1], [0.0] * 4)                      # not a list of lists
+    with pytest.raises(ValueError):
+        QCMRF([[0.0, 1.0]], [0.0] * 4)                # not ints
+    with pytest.raises(ValueError):
+        QCMRF([[0, 1]], [0.0] * 3)                    # wrong theta length (QCMRF.py:68-71)
+    with pytest.raises(ValueError):
+        QCMRF([[0, 1]], gamma=[0.1] * 5)              # wrong gamma length (QCMRF.py:73-76)
+    c = QCMRF([[0, 1], [1, 2, 3]], [-0.1] * 12)
+    assert (c.num_vertices, c.num_nodes, c.num_cliques, c.max_clique, c.dimension) == (4, 4, 2, 3, 12)
+    assert c.num_qubits == 4 + 2 + 1 == c.num_clbits   # QCMRF.py:78
+    assert c.cliques == [[0, 1], [1, 2, 3]]
+    assert np.allclose(c.gamma, program.theta_to_gamma([-0.1] * 12))
+    assert c.basis_gates == ['cx', 'id', 'rz', 'sx', 'x']
+    ops = c.count_ops()
+    assert ops['h'] == 4 + 2 * 2 and ops['x'] == 4 and ops['measure'] == 6
+
+
+def test_random_default_parameters_follow_numpy_global_state():
+    """No theta/gamma: theta ~ U(-5,0) from the global numpy RNG (QCMRF.py:210-213)."""
+    np.random.seed(7)
+    c = QCMRF([[0, 1]])
+    np.random.seed(7)
+    expect = [np.random.uniform(low=-5.0, high=0) for _ in range(4)]
+    assert c.theta == expect
+
+
+def test_host_side_postselection_helpers(aer_counts):
+    Q = aer_counts['0.5'][10]
+    a, b = extract_probs(Q, 2, 2), omrf.extract_probs(Q, 2, 2)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+    P, s = extract_probs({'1000': 3}, 2, 2)
+    assert s == 0 and not P.any()
+    p = np.array([0.5, 0.5, 0, 0]); q = np.array([0.25, 0.25, 0.5, 0])
+    assert abs(fidelity(p, q) - omrf.fidelity(p, q)) < 1e-16 and abs(KL(p, q) - omrf.kl(p, q)) < 1e-16
+
+
+def test_shims_serve_only_missing_names():
+    served = compat.install()
+    for name in served:
+        assert name in compat.SHIMMED
+    import qiskit
+    from qiskit import Aer, QuantumCircuit, transpile               # noqa: F401
+    from qiskit.circuit.library import AND
+    from qiskit.converters import circuit_to_gate                   # noqa: F401
+    from qiskit.opflow import I, Z
+    if getattr(qiskit, '__qcmrf_b200_shim__', False):
+        assert Aer.get_backend('qasm_simulator').name() == 'qasm_simulator'
+        with pytest.raises(LookupError):
+            Aer.get_backend('ibmq_whatever')
+        proj1 = (I - Z) / 2
+        assert np.allclose(proj1.to_matrix(), np.diag([0, 1]))
+        assert np.allclose(((I + Z) / 2 ^ proj1).to_matrix(), np.diag([0, 1, 0, 0]))
+        a = AND(3, [1, -1, 0])
+        g = ir.lower(a).gates
+        assert len(g) == 1 and g[0].qubits == (0, 1, 3) and g[0].ctrl_values == (1, 0)
+    import kiopto_native as px
+    b = px.backend([[0, 1], [1, 2]], np.array([2, 2, 2]))
+    w = px.weights(b)
+    assert len(w) == 8
+    th = -np.abs(np.random.RandomState(1).randn(8))
+    w[:] = th
+    pb, _, lnZ = omrf.brute_force_pmf([[0, 1], [1, 2]], th)
+    assert abs(px.infer(b, task='partition') - lnZ) < 1e-13
+    assert np.allclose([np.exp(px.logpot(b, x) - lnZ) for x in range(8)], pb)
+
+
+@needs_ref
+def test_reference_constructor_emits_the_golden_programs(models):
+    """The reference's own QCMRF.py, imported under the shim, produces the programs stored in
+    tests/golden/ref_programs.json -- and so does the product's constructor."""
+    compat.install()
+    sys.path.insert(0, REF)
+    try:
+        import QCMRF as ref_mod
+    finally:
+        sys.path.remove(REF)
+    golden = json.load(open(os.path.join(GOLDEN, 'ref_programs.json')))
+    for key, want in golden.items():
+        scale, j, wm = key.split('/')
+        C = models[scale]['GRAPHS'][int(j)]
+        th = models[scale]['THETAS'][j][0]
+        ref = ir.to_jsonable(ir.lower(ref_mod.QCMRF(C, th, with_measurements=bool(int(wm)))))
+        mine = ir.to_jsonable(ir.lower(QCMRF(C, th, with_measurements=bool(int(wm)))))
+        assert ref == want
+        assert mine == want
+
+
+def test_product_constructor_matches_golden_reference_programs(models):
+    """Same pin, runnable without the reference checkout."""
+    golden = json.load(open(os.path.join(GOLDEN, 'ref_programs.json')))
+    assert len(golden) == 42
+    for key, want in golden.items():
+        scale, j, wm = key.split('/')
+        C = models[scale]['GRAPHS'][int(j)]
+        th = models[scale]['THETAS'][j][0]
+        assert ir.to_jsonable(ir.lower(QCMRF(C, th, with_measurements=bool(int(wm))))) == want
+        # ... and the oracle's restatement executes to the same state
+        prog = ir.from_jsonable(want)
+        N = prog.n_qubits
+        a, _ = sv.run_program(ir.to_oracle_ops(prog), N)
+        b, _ = sv.run_program(program.qcmrf_program(C, th, with_measurements=bool(int(wm)))[0], N)
+        assert np.abs(a - b).max() < 1e-15
+
+
+@needs_ref
+def test_reference_scripts_run_unchanged(tmp_path, monkeypatch, models):
+    """run_experiment.py then eval.py, byte-for-byte from /root/reference, against this
+    package (engine emulated on CPU here; the GPU twin is tests/test_gpu_parity.py)."""
+    compat.install()
+    fake_native.install(monkeypatch)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(REF)
+    monkeypatch.setattr(sys, 'argv', ['run_experiment.py'])
+    for m in ('QCMRF',):
+        sys.modules.pop(m, None)
+    with pytest.raises(SystemExit):
+        runpy.run_path(os.path.join(REF, 'run_experiment.py'), run_name='__main__')
+    got_models = json.load(open(tmp_path / 'models_0.5.json'))
+    assert got_models == models['0.5']
+    counts = json.load(open(tmp_path / 'result_simulation_0.5.json'))
+    widths = [3, 4, 8, 10, 5, 8, 6]
+    assert len(counts) == 70
+    for idx, Q in enumerate(counts):
+        assert sum(Q.values()) == 10000
+        j = idx // 10
+        n = max(max(c) for c in models['0.5']['GRAPHS'][j]) + 1
+        for k in Q:
+            assert len(k) == widths[j] and k[widths[j] - 1 - n] == '0'
+    os.makedirs(tmp_path / 'res_0.5')
+    shutil.move(str(tmp_path / 'result_simulation_0.5.json'), str(tmp_path / 'res_0.5' / 'result_simulation.json'))
+    monkeypatch.setattr(sys, 'argv', ['eval.py', '--scale', '0.5', '--results', 'result_simulation.json'])
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        runpy.run_path(os.path.join(REF, 'eval.py'), run_name='__main__')
+    table = buf.getvalue()
+    rows = [r for r in table.splitlines() if r.startswith('|') and 'graph' not in r]
+    assert len(rows) == 7
+    exact_delta = [0.6936, 0.7300, 0.3526, 0.2733, 0.6956, 0.4560, 0.7018]
+    for r, d in zip(rows, exact_delta):
+        cells = [c.strip() for c in r.strip('|').split('|')]
+        fid = float(cells[1].split()[0])
+        succ = float(cells[3].split()[0])
+        assert fid > 0.99
+        assert abs(succ - d) < 0.01

@@ -1,0 +1,402 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on
+the same seeded inputs.  Bars: bit-exact keys / masks / orderings; post-selected
+probabilities within 1e-10 (complex128) or 1e-5 (complex64) absolute of brute-force MRF
+enumeration and of the oracle statevector; sampled histograms within shot-noise bounds.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import engine_emulator as em
+from conftest import all_models, has_cuda
+from oracle import mrf, program, statevector as sv
+from qcmrf_b200 import QCMRF, B200Simulator, _native, fusion, ir, transpile
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason='needs a CUDA device')]
+
+TOL_P = {'double': 1e-10, 'single': 1e-5}
+TOL_AMP = {'double': 1e-12, 'single': 2e-6}
+
+
+def weissman_tv_bound(K, S, alpha=1e-6):
+    """P(TV > bound) <= alpha for S draws over K outcomes."""
+    return 0.5 * np.sqrt(2.0 * (K * np.log(2.0) + np.log(1.0 / alpha)) / S)
+
+
+def counts_to_vec(counts, N):
+    v = np.zeros(1 << N)
+    for k, c in counts.items():
+        assert len(k) == N
+        v[int(k, 2)] = c
+    return v
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_all_fixture_models_batched(models, aer_counts, precision):
+    """BASELINE config 2: all 210 res_* models in one batch -- exact post-selected pmf +
+    8192 shots each, checked against the brute-force MRF distribution."""
+    sim = B200Simulator(precision=precision, seed=1984)
+    items = list(all_models(models))
+    circs = [QCMRF(C, th) for _, _, _, C, th in items]
+    res = sim.run(circs, shots=8192).result()
+    counts = res.get_counts()
+    assert len(counts) == 210
+    worst_p = worst_d = 0.0
+    tv_ok = 0
+    for e, (scale, j, i, C, th) in enumerate(items):
+        n, k, N, _ = program.sizes(C)
+        p, delta = res.postselected_probabilities(e)
+        pb, db, _ = mrf.brute_force_pmf(C, th)
+        worst_p = max(worst_p, np.abs(p - pb).max())
+        worst_d = max(worst_d, abs(delta - db))
+        psi, meas = sv.run_program(program.qcmrf_program(C, th)[0], N)
+        kp = sv.key_probabilities(psi, N, meas)
+        obs = counts_to_vec(counts[e], N)
+        assert obs.sum() == 8192
+        assert obs[kp == 0].sum() == 0                              # support incl. clbit n == '0'
+        K = int((kp > 0).sum())
+        assert 0.5 * np.abs(obs / 8192 - kp).sum() < weissman_tv_bound(K, 8192)
+        tv_ok += 1
+    assert worst_p < TOL_P[precision] and worst_d < TOL_P[precision]
+    assert tv_ok == 210
+    # same seed -> same histograms; the stream is the experiment index, so a sub-batch agrees too
+    again = sim.run(circs[:5], shots=8192).result().get_counts()
+    assert again == counts[:5]
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('fusion_mode,block_max', [('off', 1), ('clique', 1), ('blocked', 1), ('blocked', 2),
+                                                   ('blocked', 4), ('blocked', 5)])
+def test_statevector_path_all_modes(models, precision, fusion_mode, block_max):
+    """The large-state kernels (init, blocked multiplexer pass, diag, lazy materialisation) on
+    the fixture models: full statevector vs the oracle's gate-by-gate execution."""
+    sim = B200Simulator(precision=precision, fusion=fusion_mode, block_max=block_max, small_batch=False, seed=7)
+    worst = 0.0
+    for scale, j, i, C, th in all_models(models):
+        if i not in (0, 7):
+            continue
+        n, k, N, _ = program.sizes(C)
+        psi, _ = sv.run_program(program.qcmrf_program(C, th)[0], N)
+        got = sim.statevector(QCMRF(C, th), precision=precision)
+        worst = max(worst, np.abs(got - psi).max())
+        p, delta = sim.exact(QCMRF(C, th))
+        pb, db, _ = mrf.brute_force_pmf(C, th)
+        assert np.abs(p - pb).max() < TOL_P[precision] and abs(delta - db) < TOL_P[precision]
+    assert worst < TOL_AMP[precision]
+
+
+def test_large_path_counts_and_keys(models):
+    sim = B200Simulator(precision='double', small_batch=False, seed=99)
+    for j in (1, 3, 5):
+        C = models['0.5']['GRAPHS'][j]
+        th = models['0.5']['THETAS'][str(j)][2]
+        n, k, N, _ = program.sizes(C)
+        res = sim.run(QCMRF(C, th), shots=20000).result()
+        counts = res.get_counts()
+        assert isinstance(counts, dict) and sum(counts.values()) == 20000
+        psi, meas = sv.run_program(program.qcmrf_program(C, th)[0], N)
+        kp = sv.key_probabilities(psi, N, meas)
+        obs = counts_to_vec(counts, N)
+        assert obs[kp == 0].sum() == 0
+        assert 0.5 * np.abs(obs / 2e4 - kp).sum() < weissman_tv_bound(int((kp > 0).sum()), 20000)
+        # host-side post-selection of the sampled counts, as the reference does it
+        from qcmrf_b200 import extract_probs
+        q, succ = extract_probs(counts, n, N - n)
+        _, delta = res.postselected_probabilities()
+        assert abs(succ - delta) < 0.02
+        assert res.get_counts(0) == counts
+        json.dumps(res.get_counts())                                # run_experiment.py:60
+
+
+@pytest.mark.parametrize('graph', [0, 1, 2, 4])
+def test_transpiled_circuits(models, graph):
+    """run_experiment.py:52-56: transpile to cx/id/rz/sx/x, then run."""
+    C = models['0.25']['GRAPHS'][graph]
+    th = models['0.25']['THETAS'][str(graph)][5]
+    n, k, N, _ = program.sizes(C)
+    T = transpile([QCMRF(C, th)], basis_gates=['cx', 'id', 'rz', 'sx', 'x'])
+    pb, db, _ = mrf.brute_force_pmf(C, th)
+    for sim in (B200Simulator(seed=3), B200Simulator(seed=3, small_batch=False)):
+        res = sim.run(T, shots=4096, n_vars=n).result()
+        p, delta = res.postselected_probabilities(0)
+        assert np.abs(p - pb).max() < 1e-10 and abs(delta - db) < 1e-10
+        assert isinstance(res.get_counts(), list) and len(res.get_counts()) == 1
+        psi, meas = sv.run_program(program.qcmrf_program(C, th)[0], N)
+        kp = sv.key_probabilities(psi, N, meas)
+        obs = counts_to_vec(res.get_counts(0), N)
+        assert obs[kp == 0].sum() == 0
+
+
+def test_aer_histograms_vs_gpu_exact_distribution(models, aer_counts):
+    """The stored Aer outputs are statistically consistent with the GPU's exact |psi|^2."""
+    sim = B200Simulator(precision='double', small_batch=False)
+    pvals = []
+    for scale, j, i, C, th in all_models(models):
+        if i % 3:
+            continue
+        n, k, N, _ = program.sizes(C)
+        psi = sim.statevector(QCMRF(C, th))
+        prog = ir.lower(QCMRF(C, th))
+        kp = sv.key_probabilities(psi, N, prog.measures)
+        Q = aer_counts[scale][10 * j + i]
+        obs = counts_to_vec(Q, N)
+        assert obs[kp < 1e-20].sum() == 0
+        m = kp > 1e-20
+        exp = 1e4 * kp[m]
+        big = exp >= 5
+        o = np.append(obs[m][big], obs[m][~big].sum())
+        e = np.append(exp[big], exp[~big].sum())
+        if e[-1] == 0:
+            o, e = o[:-1], e[:-1]
+        pvals.append(stats.chi2.sf(((o - e) ** 2 / e).sum(), len(e) - 1))
+    assert min(pvals) > 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+def _random_program(rng, N, n_ops, kinds=('mux', 'diag', 'block', 'swap')):
+    """Fully materialised random engine program over N qubits."""
+    e = fusion._Emitter()
+    qv = np.zeros((N, 4))
+    v = rng.randn(N, 2) + 1j * rng.randn(N, 2)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    qv[:, 0], qv[:, 1], qv[:, 2], qv[:, 3] = v[:, 0].real, v[:, 0].imag, v[:, 1].real, v[:, 1].imag
+    e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=N, table_off=e.table(qv))
+
+    def rand_u(m):
+        a = rng.randn(1 << m, 2, 2) + 1j * rng.randn(1 << m, 2, 2)
+        q, _ = np.linalg.qr(a)
+        return q
+
+    for _ in range(n_ops):
+        kind = kinds[rng.randint(len(kinds))]
+        if kind == 'mux':
+            t = int(rng.randint(N))
+            m = int(rng.randint(0, min(N - 1, 4) + 1))
+            ctrl = [int(c) for c in rng.permutation([q for q in range(N) if q != t])[:m]]
+            e.op(fusion.QCM_OP_MUX1Q, target=t, ctrl=ctrl, n_in=N, n_out=N,
+                 table_off=e.table(fusion._mux_table_f64(rand_u(m))))
+        elif kind == 'diag':
+            m = int(rng.randint(1, min(N, 5) + 1))
+            ctrl = [int(c) for c in rng.permutation(N)[:m]]
+            d = np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << m))
+            e.op(fusion.QCM_OP_DIAG, ctrl=ctrl, n_in=N, n_out=N, table_off=e.table(fusion._diag_table_f64(d)))
+        elif kind == 'swap' and N >= 2:
+            a, b = (int(x) for x in rng.permutation(N)[:2])
+            e.op(fusion.QCM_OP_SWAP, target=a, ctrl=[b], n_in=N, n_out=N)
+        elif kind == 'block' and N >= 3:
+            M = int(rng.randint(1, min(5, N - 1) + 1))
+            tq = sorted(int(c) for c in rng.permutation(N)[:M])
+            others = [q for q in range(N) if q not in tq]
+            n_mem = int(rng.randint(1, 7))
+            e.op(fusion.QCM_OP_BLOCK, target=M, ctrl=tq, n_in=N, n_out=N, n_ctrl=n_mem)
+            for _g in range(n_mem):
+                t = tq[rng.randint(M)]
+                m = int(rng.randint(0, min(len(others), 3) + 1))
+                ctrl = [int(c) for c in rng.permutation(others)[:m]]
+                e.op(fusion.QCM_OP_MUX1Q, target=t, ctrl=ctrl, n_in=N, n_out=N,
+                     table_off=e.table(fusion._mux_table_f64(rand_u(m))))
+    ops, tabs = e.finish()
+    return ops, tabs
+
+
+class _P:
+    pass
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('N', [1, 2, 3, 5, 8, 11, 14])
+def test_random_engine_programs_vs_op_semantics(precision, N):
+    """Raw C-ABI: random MUX1Q (every target incl. qubit 0 and the shuffle/low range), DIAG,
+    SWAP and BLOCK ops on random product states vs the numpy statement of the op semantics."""
+    rng = np.random.RandomState(1000 + N)
+    with _native.Handle(N, precision) as h:
+        for trial in range(6):
+            ops, tabs = _random_program(rng, N, 12)
+            pl = _P()
+            pl.ops, pl.tables, pl.n_phys = ops, tabs, N
+            want, act = em.run_plan(pl)
+            h.run_program(ops, tabs)
+            got = h.get_amplitudes().astype(np.complex128)
+            assert np.abs(got - want).max() < (1e-12 if precision == 'double' else 3e-6)
+            assert abs(np.sum(np.abs(got) ** 2) - 1.0) < (1e-12 if precision == 'double' else 1e-5)
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_lazy_materialisation_ops(precision):
+    """Ops that materialise qubits: zero-input targets are never read (the buffer holds NaN
+    there), EXTEND zero-fills, get_amplitudes reports implicit zeros."""
+    N = 12
+    rng = np.random.RandomState(5)
+    with _native.Handle(N, precision) as h:
+        h.set_amplitudes(np.full(1 << N, np.nan + 1j * np.nan), 0, n_active=0)
+        e = fusion._Emitter()
+        qv = np.zeros((4, 4)); qv[:, 0] = qv[:, 2] = np.sqrt(0.5)
+        e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=4, table_off=e.table(qv))
+
+        def rand_u(m):
+            q, _ = np.linalg.qr(rng.randn(1 << m, 2, 2) + 1j * rng.randn(1 << m, 2, 2))
+            return q
+        e.op(fusion.QCM_OP_MUX1Q, target=4, ctrl=[0, 2], n_in=4, n_out=5, table_off=e.table(fusion._mux_table_f64(rand_u(2))))
+        e.op(fusion.QCM_OP_BLOCK, target=4, ctrl=[3, 5, 6, 7], n_in=5, n_out=8, n_ctrl=5)
+        for t, c in ((5, [0, 1]), (3, [4]), (6, [2]), (7, [1, 4]), (5, [])):
+            e.op(fusion.QCM_OP_MUX1Q, target=t, ctrl=c, n_in=5, n_out=8, table_off=e.table(fusion._mux_table_f64(rand_u(len(c)))))
+        e.op(fusion.QCM_OP_EXTEND, n_in=8, n_out=10)
+        e.op(fusion.QCM_OP_DIAG, ctrl=[9, 0, 5], n_in=10, n_out=10,
+             table_off=e.table(fusion._diag_table_f64(np.exp(1j * rng.uniform(0, 6, 8)))))
+        ops, tabs = e.finish()
+        pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, N
+        want, act = em.run_plan(pl)
+        h.run_program(ops, tabs)
+        assert h.get_active() == act == 10
+        got = h.get_amplitudes().astype(np.complex128)
+        assert not np.isnan(got).any()
+        assert np.abs(got - want).max() < (1e-12 if precision == 'double' else 3e-6)
+        assert np.all(got[1 << 10:] == 0)
+        t = h.timing()
+        assert t['kernel_launches'] >= 6 and t['bytes_written'] > 0
+
+
+def test_invalid_programs_are_rejected():
+    with _native.Handle(6, 'double') as h:
+        e = fusion._Emitter()
+        qv = np.zeros((6, 4)); qv[:, 0] = 1
+        e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=6, table_off=e.table(qv))
+        e.op(fusion.QCM_OP_BLOCK, target=2, ctrl=[1, 2], n_in=6, n_out=6, n_ctrl=1)
+        e.op(fusion.QCM_OP_MUX1Q, target=1, ctrl=[2], n_in=6, n_out=6, table_off=e.table(np.zeros(16)))  # ctrl is a block target
+        ops, tabs = e.finish()
+        with pytest.raises(_native.NativeError) as ei:
+            h.run_program(ops, tabs)
+        assert ei.value.code == -1
+        e = fusion._Emitter()
+        e.op(fusion.QCM_OP_MUX1Q, target=9, ctrl=[], n_in=0, n_out=6, table_off=e.table(np.zeros(8)))
+        ops, tabs = e.finish()
+        with pytest.raises(_native.NativeError):
+            h.run_program(ops, tabs)
+        e = fusion._Emitter()
+        e.op(99, n_in=0, n_out=0)
+        ops, tabs = e.finish()
+        with pytest.raises(_native.NativeError):
+            h.run_program(ops, np.zeros(1))
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('N', [3, 10, 13, 21])
+def test_sampler(precision, N):
+    """Sum tree + Philox + warp search: deterministic, never returns a zero-probability state,
+    matches the exact distribution, honours the clbit map (N=21 exercises a 2-level tree)."""
+    rng = np.random.RandomState(N)
+    dim = 1 << N
+    if N <= 13:
+        psi = rng.randn(dim) + 1j * rng.randn(dim)
+        psi[rng.rand(dim) < 0.3] = 0
+    else:                                            # sparse-ish support so TV is testable
+        psi = np.zeros(dim, dtype=np.complex128)
+        support = rng.choice(dim, 3000, replace=False)
+        psi[support] = rng.randn(3000) + 1j * rng.randn(3000)
+    psi /= np.linalg.norm(psi)
+    with _native.Handle(N, precision) as h:
+        h.set_amplitudes(psi)
+        S = 200000
+        a = h.sample(S, seed=1984, stream_id=3)
+        b = h.sample(S, seed=1984, stream_id=3)
+        c = h.sample(S, seed=1984, stream_id=4)
+        assert np.array_equal(a, b) and not np.array_equal(a, c)
+        assert a.max() < dim
+        pr = np.abs(h.get_amplitudes().astype(np.complex128)) ** 2
+        assert np.all(pr[a.astype(np.int64)] > 0)
+        vals, cnt = np.unique(a, return_counts=True)
+        K = int((pr > 0).sum())
+        emp = np.zeros(dim); emp[vals.astype(np.int64)] = cnt / S
+        assert 0.5 * np.abs(emp - pr / pr.sum()).sum() < weissman_tv_bound(K, S)
+        # clbit map: reverse the low 3 qubits, leave clbit 3 unmeasured, clbit 4 <- top qubit
+        cmap = np.array([2, 1, 0, -1, N - 1], dtype=np.int32)
+        k = h.sample(S, seed=1984, stream_id=3, clbit_qubit=cmap)
+        ai = a.astype(np.int64)
+        want = ((ai >> 2) & 1) | (((ai >> 1) & 1) << 1) | ((ai & 1) << 2) | (((ai >> (N - 1)) & 1) << 4)
+        assert np.array_equal(k.astype(np.int64), want)
+        # the first uniforms are Philox4x32-10 of (seed, stream, shot): spot-check shot 0 via the CDF
+        small = h.sample(1, seed=1984, stream_id=3)
+        assert small[0] == a[0]
+
+
+def test_sharded_sampling_equals_single_gpu():
+    """Two 'ranks' (two handles on this GPU, run one after the other) draw the same Philox
+    stream and split the shots exactly as the single-state sampler does."""
+    N = 21
+    rng = np.random.RandomState(42)
+    psi = rng.randn(1 << N) + 1j * rng.randn(1 << N)
+    psi /= np.linalg.norm(psi)
+    S = 50000
+    with _native.Handle(N, 'double') as h:
+        h.set_amplitudes(psi)
+        ref = h.sample(S, seed=5, stream_id=1)
+    half = 1 << (N - 1)
+    keys, mines, masses = [], [], []
+    hs = []
+    for r in range(2):
+        h = _native.Handle(N - 1, 'double')
+        h.set_shard(1, r)
+        h.set_amplitudes(psi[r * half:(r + 1) * half])
+        masses.append(h.sample_prepare())
+        hs.append(h)
+    for r, h in enumerate(hs):
+        k, m = h.sample_sharded(S, 5, 1, masses)
+        keys.append(k); mines.append(m)
+        h.close()
+    assert np.all(mines[0] ^ mines[1])                   # every shot resolved by exactly one rank
+    merged = np.where(mines[0], keys[0], keys[1])
+    assert np.array_equal(merged, ref)
+
+
+def test_postselect_general_mask():
+    N = 9
+    rng = np.random.RandomState(3)
+    psi = rng.randn(1 << N) + 1j * rng.randn(1 << N)
+    psi /= np.linalg.norm(psi)
+    pr = np.abs(psi) ** 2
+    idx = np.arange(1 << N)
+    with _native.Handle(N, 'double') as h:
+        h.set_amplitudes(psi)
+        for mask, value, nb in ((0b110000000, 0, 7), (0b101000100, 0b001000100, 4), (0, 0, 3), (0b111111111, 5, 2)):
+            probs, kept = h.postselect(mask, value, nb)
+            sel = (idx & mask) == value
+            want = np.zeros(1 << nb)
+            np.add.at(want, idx[sel] & ((1 << nb) - 1), pr[sel])
+            assert abs(kept - pr[sel].sum()) < 1e-14
+            assert np.abs(probs - want).max() < 1e-14
+
+
+def test_mid_size_tree_mrf_properties():
+    """A 13-variable random-tree MRF (N = 26 total qubits, complex64): blocked execution;
+    post-selected pmf vs brute force at the fp32 tolerance, unit norm, success probability."""
+    rng = np.random.RandomState(1984)
+    n = 13
+    cliques = [[int(rng.randint(0, v)), v] for v in range(1, n)]
+    th = -np.abs(rng.randn(4 * len(cliques))) * 0.5
+    circ = QCMRF(cliques, list(th))
+    assert circ.num_qubits == 26
+    pb, db, _ = mrf.brute_force_pmf(cliques, th)
+    for bm in (4, 5):
+        sim = B200Simulator(precision='single', fusion='blocked', block_max=bm, seed=1)
+        res = sim.run(circ, shots=10000).result()
+        p, delta = res.postselected_probabilities(0)
+        assert np.abs(p - pb).max() < 1e-5 and abs(delta - db) < 1e-5
+        meta = res.metadata(0)
+        assert meta['path'] == 'statevector' and meta['n_phys'] == 25
+        assert meta['passes'] == 1 + -(-12 // bm)
+        counts = res.get_counts(0)
+        kept = sum(v for k, v in counts.items() if int(k, 2) < (1 << n))
+        assert abs(kept / 1e4 - db) < 5 * np.sqrt(db * (1 - db) / 1e4) + 1e-3
+        for k in counts:
+            assert len(k) == 26 and k[26 - 1 - n] == '0'
+        sim.close()
+    # dense in-place gate passes (one per clique, full 2^26 width) give the same answer
+    sim = B200Simulator(precision='single', fusion='clique', seed=1)
+    p2, d2 = sim.exact(circ)
+    assert np.abs(p2 - pb).max() < 1e-5 and abs(d2 - db) < 1e-5
+    sim.close()

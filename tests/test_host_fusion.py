@@ -1,0 +1,227 @@
+"""Host logic: lowering, fusion, planning.  Every emitted engine program is executed
+by the numpy op-semantics emulator and compared with the oracle's gate-by-gate
+statevector.  CPU only."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import engine_emulator as em
+from conftest import all_models
+from oracle import mrf, program, statevector as sv
+from qcmrf_b200 import QCMRF, fusion, ir, transpile
+
+CONFIGS = [('off', False, 1), ('clique', False, 1), ('clique', True, 1), ('clique', True, 2), ('clique', True, 4),
+           ('clique', True, 5)]
+
+
+def _logical(prog, mode, lazy, bm, elide=None):
+    fc = fusion.fuse(prog, mode)
+    pl = fusion.plan(fc, lazy=lazy, block_max=bm, elide=elide)
+    phys, act = em.run_plan(pl)
+    return em.logical_state(pl, phys), fc, pl
+
+
+def test_product_program_equals_oracle_program(models):
+    """The product's QCMRF emits gate-for-gate what the oracle's restatement of
+    QCMRF._build (QCMRF.py:199-243) emits."""
+    for scale, j, i, C, th in all_models(models):
+        if i > 2:
+            continue
+        for wm in (True, False):
+            prog = ir.lower(QCMRF(C, th, with_measurements=wm))
+            ops, N = program.qcmrf_program(C, th, with_measurements=wm)
+            mine = [g for g in ir.to_oracle_ops(prog)]
+            ref = []
+            for g in ops:
+                if g[0] == 'cp':
+                    ref.append(('mcp', g[1], (g[2],), (1,), g[3]))
+                elif g[0] == 'measure':
+                    continue
+                else:
+                    ref.append(g)
+            mine_g = [g for g in mine if g[0] != 'measure']
+            assert len(mine_g) == len(ref)
+            for a, b in zip(mine_g, ref):
+                assert a[0] == b[0]
+                if a[0] == 'mcp':
+                    assert a[2:] == b[2:] and abs(a[1] - b[1]) < 1e-15
+                else:
+                    assert a == b
+            assert prog.measures == {g[2]: g[1] for g in ops if g[0] == 'measure'}
+            assert prog.n_qubits == N == prog.n_clbits
+
+
+def test_fused_plans_match_oracle_on_all_fixture_models(models):
+    worst = 0.0
+    for scale, j, i, C, th in all_models(models):
+        ops, N = program.qcmrf_program(C, th)
+        psi, _ = sv.run_program(ops, N)
+        prog = ir.lower(QCMRF(C, th))
+        cfgs = CONFIGS if i == 0 else [('clique', True, 4)]
+        for mode, lazy, bm in cfgs:
+            lg, fc, pl = _logical(prog, mode, lazy, bm)
+            worst = max(worst, np.abs(lg - psi).max())
+            if mode == 'clique':
+                # one multiplexer sweep per clique, on that clique's ancilla, scratch qubit gone
+                n = program.sizes(C)[0]
+                assert sorted(fc.init) == list(range(n))
+                assert [o.kind for o in fc.ops] == ['mux'] * len(C)
+                assert [o.target for o in fc.ops] == [n + 1 + ii for ii in range(len(C))]
+                for o, cl in zip(fc.ops, C):
+                    assert sorted(o.ctrls) == sorted(n - 1 - v for v in cl) and o.zero_in
+                if lazy:
+                    assert pl.n_phys == N - 1 and pl.layout[n] >= pl.n_phys
+    assert worst < 1e-14
+
+
+def test_fused_tables_are_the_closed_form_rx(models):
+    """App. A: the block is RX(4 gamma) selected by the clique state."""
+    for scale, j, i, C, th in all_models(models):
+        if i:
+            continue
+        fc = fusion.fuse(ir.lower(QCMRF(C, th)), 'clique')
+        for op, (ctrl, c, s) in zip(fc.ops, program.rx_tables(C, th)):
+            assert sorted(op.ctrls) == sorted(ctrl)
+            perm = [ctrl.index(q) for q in op.ctrls]               # my bit j <-> oracle bit perm[j]
+            for t in range(len(c)):
+                to = sum(((t >> jj) & 1) << perm[jj] for jj in range(len(perm)))
+                assert abs(op.table[t, 0, 0] - c[to]) < 1e-14
+                assert abs(op.table[t, 1, 0] - (-1j * s[to])) < 1e-14
+
+
+@pytest.mark.parametrize('graph', [0, 1, 2, 4, 5])
+def test_transpiled_circuits_fuse_back(models, graph):
+    """cx/id/rz/sx/x form (run_experiment.py:52) collapses to the same sweeps."""
+    C = models['0.25']['GRAPHS'][graph]
+    th = models['0.25']['THETAS'][str(graph)][3]
+    ops, N = program.qcmrf_program(C, th)
+    psi, _ = sv.run_program(ops, N)
+    t = transpile(QCMRF(C, th), basis_gates=['cx', 'id', 'rz', 'sx', 'x'])
+    assert set(t.count_ops()) <= {'cx', 'id', 'rz', 'sx', 'x', 'measure'}
+    prog = ir.lower(t)
+    # the translation itself is exact including the tracked global phase
+    psi_t, _ = sv.run_program(ir.to_oracle_ops(prog), N)
+    assert np.abs(psi_t - psi).max() < 1e-11
+    for mode, lazy, bm in [('off', False, 1), ('clique', True, 4)]:
+        lg, fc, pl = _logical(prog, mode, lazy, bm)
+        assert np.abs(lg - psi).max() < 1e-11
+    assert sum(1 for o in fc.ops if o.kind == 'mux' and o.zero_in) == len(C)
+    assert len(fc.ops) <= len(C) + 2
+
+
+def test_gamma_zero_terms_and_beta(models):
+    C = [[0, 1], [1, 2]]
+    th = [0.0, -0.3, 0.0, -1.2, -0.4, 0.0, -0.1, -2.0]           # theta = 0 -> gamma = 0 -> term skipped
+    for beta in (1.0, 0.25, 3.0):
+        ops, N = program.qcmrf_program(C, th, beta=beta)
+        psi, _ = sv.run_program(ops, N)
+        prog = ir.lower(QCMRF(C, th, beta=beta))
+        assert len(prog.gates) == len([g for g in ops if g[0] not in ('measure', 'barrier')])
+        lg, fc, pl = _logical(prog, 'clique', True, 4)
+        assert np.abs(lg - psi).max() < 1e-14
+        p, d = sv.postselected(lg, 3)
+        pb, db, _ = mrf.brute_force_pmf(C, th, beta)
+        assert np.abs(p - pb).max() < 1e-13 and abs(d - db) < 1e-13
+
+
+def test_gamma_parametrisation_and_no_measurements():
+    C = [[0], [0, 1, 2]]
+    g = list(np.linspace(0.05, 0.7, 10))
+    ops, N = program.qcmrf_program(C, gamma=g, with_measurements=False)
+    psi, _ = sv.run_program(ops, N)
+    circ = QCMRF(C, gamma=g, with_measurements=False, with_barriers=True)
+    prog = ir.lower(circ)
+    assert prog.measures == {}
+    lg, _, _ = _logical(prog, 'clique', True, 3)
+    assert np.abs(lg - psi).max() < 1e-14
+    assert np.allclose(circ.theta, program.gamma_to_theta(g))
+
+
+def test_no_elision_keeps_full_width():
+    C, th = [[0, 1], [1, 2]], [-0.3, -0.1, -0.7, -0.2, -0.5, -0.9, -0.05, -0.4]
+    prog = ir.lower(QCMRF(C, th))
+    psi, _ = sv.run_program(program.qcmrf_program(C, th)[0], 6)
+    lg, fc, pl = _logical(prog, 'clique', True, 4, elide=False)
+    assert pl.n_phys == 6 and pl.final_active == 6
+    assert np.abs(lg - psi).max() < 1e-14
+
+
+@st.composite
+def clique_sets(draw):
+    n = draw(st.integers(1, 6))
+    k = draw(st.integers(1, 4))
+    cliques = []
+    for _ in range(k):
+        m = draw(st.integers(1, min(4, n)))
+        cliques.append(draw(st.permutations(list(range(n))))[:m])
+    cliques[0] = sorted(set(cliques[0]) | {n - 1})[:4] if n - 1 not in cliques[0] and len(cliques[0]) < 4 else cliques[0]
+    if not any(n - 1 in c for c in cliques):
+        cliques.append([n - 1])
+    return [list(map(int, c)) for c in cliques]
+
+
+@settings(max_examples=25, deadline=None)
+@given(clique_sets(), st.integers(0, 2 ** 31 - 1), st.sampled_from([1, 2, 4, 5]))
+def test_random_clique_sets(cliques, seed, bm):
+    """T6: random clique sets (|C| 1..4, unordered vertex lists, repeated cliques): fused vs
+    unfused vs brute force."""
+    rng = np.random.RandomState(seed)
+    dim = sum(2 ** len(c) for c in cliques)
+    th = -np.abs(rng.randn(dim)) * 0.7
+    n, k, N, _ = program.sizes(cliques)
+    if N > 11:
+        return
+    ops, _ = program.qcmrf_program(cliques, th)
+    psi, _ = sv.run_program(ops, N)
+    prog = ir.lower(QCMRF(cliques, list(th)))
+    lg, fc, pl = _logical(prog, 'clique', True, bm)
+    assert np.abs(lg - psi).max() < 1e-13
+    lg2, _, _ = _logical(prog, 'off', False, 1)
+    assert np.abs(lg2 - psi).max() < 1e-13
+    p, d = sv.postselected(lg, n)
+    pb, db, _ = mrf.brute_force_pmf(cliques, th)
+    assert np.abs(p - pb).max() < 1e-12 and abs(d - db) < 1e-12
+
+
+def test_foreign_circuit_generic_gates():
+    """Circuits that are not QCMRF: every primitive still runs (as its own sweep when no
+    block structure is found)."""
+    from qcmrf_b200 import QuantumCircuit
+    qc = QuantumCircuit(4, 4)
+    qc.h(0); qc.cx(0, 1); qc.ry(0.3, 2); qc.cz(1, 2); qc.t(0); qc.swap(0, 3); qc.rx(1.1, 1)
+    qc.mcx([0, 1], 2); qc.cp(0.7, 3, 0); qc.sdg(3); qc.u(0.1, 0.2, 0.3, 2); qc.crz(0.4, 2, 3)
+    qc.measure_all()
+    prog = ir.lower(qc)
+    psi, meas = sv.run_program([g for g in _oracle_ops(prog)], 4)
+    for mode, lazy, bm in CONFIGS:
+        lg, fc, pl = _logical(prog, mode, lazy, bm)
+        assert np.abs(lg - psi).max() < 1e-14, (mode, lazy, bm)
+
+
+def _oracle_ops(prog):
+    """ir.to_oracle_ops lacks a few gate names the oracle executor has no tuple for:
+    expand them through their matrices."""
+    out = []
+    for g in prog.gates:
+        if g.name == 'u':
+            # u(theta, phi, lam) = rz(phi) ry(theta) rz(lam) up to phase e^{i(phi+lam)/2}
+            th, ph, lm = g.params
+            out += [('rz', lm, g.target), ('ry', th, g.target), ('rz', ph, g.target), ('gphase', (ph + lm) / 2)]
+        elif g.name == 'crz':
+            c, t = g.qubits
+            out += [('rz', g.params[0] / 2, t), ('mcx', (c,), (1,), t), ('rz', -g.params[0] / 2, t), ('mcx', (c,), (1,), t)]
+        else:
+            out += ir.to_oracle_ops(ir.Program(prog.n_qubits, prog.n_clbits, [g]))
+    return out
+
+
+def test_plan_limits_are_respected(models):
+    C = models['0.1']['GRAPHS'][3]
+    th = models['0.1']['THETAS']['3'][0]
+    fc = fusion.fuse(ir.lower(QCMRF(C, th)), 'clique')
+    for bm in (1, 2, 3, 4, 5):
+        pl = fusion.plan(fc, lazy=True, block_max=bm)
+        for op in pl.ops:
+            if op['kind'] == fusion.QCM_OP_BLOCK:
+                assert op['target'] <= bm and op['n_ctrl'] <= fusion.QCM_MAX_MEMBERS
+        assert pl.n_passes == 1 + -(-len(C) // bm)
