@@ -67,10 +67,11 @@ enum qcm_op_kind {
     QCM_OP_MUX1Q = 2,
     /* diagonal: amplitude *= table[c] (2 doubles per entry) -- rz, p, cp, cz ...   */
     QCM_OP_DIAG = 3,
-    /* header of a blocked pass: the next `n_ctrl` ops (all MUX1Q, targets pairwise
-     * distinct or repeated, no member's index qubits among the block's targets) are
-     * applied in ONE sweep; `ctrl[0..target-1]` lists the block's `target` (= count)
-     * distinct target qubits in ascending order.                                   */
+    /* header of a blocked pass: the next `n_ctrl` ops (MUX1Q with targets among the
+     * block's qubits, pairwise distinct or repeated; or DIAG, a diagonal factor applied
+     * in the same sweep; no member's index qubits among the block's targets) are
+     * applied in ONE sweep, in order; `ctrl[0..target-1]` lists the block's `target`
+     * (= count) distinct target qubits in ascending order.                         */
     QCM_OP_BLOCK = 4,
     /* exchange qubits `target` and `ctrl[0]` (both local)                          */
     QCM_OP_SWAP = 5,
@@ -84,13 +85,19 @@ enum qcm_op_kind {
  * never read beyond 2^n_active_in and write all of 2^n_active_out.  Qubits in
  * [n_active_in, n_active_out) must be targets of the op (BLOCK: listed in ctrl[]).
  * A fully materialised program has n_active_in == n_active_out == n_local.       */
+/* op.flags, on the LAST op of a program: shots will be drawn from the result.  When that
+ * op only materialises new qubits (every block qubit new, one MUX1Q each), the engine
+ * builds the sampler's sum tree on its 2^M-times smaller input and samples the new
+ * qubits conditionally, instead of re-reading the whole result.                      */
+#define QCM_FLAG_SAMPLE_CHECKPOINT 1
+
 typedef struct qcm_op {
     int32_t kind;
     int32_t target;
     int32_t n_ctrl;
     int32_t n_active_in;
     int32_t n_active_out;
-    int32_t flags;                 /* reserved, 0 */
+    int32_t flags;                 /* QCM_FLAG_* */
     int32_t ctrl[QCM_MAX_CTRL];
     int64_t table_off;             /* offset, in doubles, into `tables` */
 } qcm_op;

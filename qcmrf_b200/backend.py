@@ -277,7 +277,11 @@ class B200Simulator:
         pl = pr.plan
         h = self._handle(pl.n_phys, precision or self.precision)
         self._last = h
-        h.run_program(pl.ops, pl.tables)
+        ops = pl.ops
+        if not shots and len(ops) and ops['flags'].any():
+            ops = ops.copy()
+            ops['flags'] = 0                   # no shots follow: skip the sampler's checkpoint tree
+        h.run_program(ops, pl.tables)
         probs = kept = None
         if want_probs and pr.ps is not None and pr.n_vars <= 30:
             probs, kept = self._probs_from_handle(h, pr)

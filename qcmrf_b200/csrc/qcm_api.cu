@@ -40,13 +40,16 @@ struct qcm_sim_s {
     std::string err;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     qcm_timing timing{};
-    DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree;
+    DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab;
     std::vector<double> h_top;
     // sum tree (built by qcm_sample_prepare)
     int tree_levels = 0;
     double *tree_ptr[8] = {nullptr};
     uint64_t tree_n[8] = {0};
-    int tree_for_active = -1;
+    int tree_for_active = -1;       // n_active of the state the tree describes
+    int tree_base_bits = 0;         // qubits the tree indexes (tree_for_active - tree_cond_bits)
+    int tree_cond_bits = 0;         // expansion qubits materialised after the tree was built
+    uint64_t n_expand = 0, n_checkpoint = 0;
     double local_mass = 0.0;
     bool tree_valid = false;
     // per-op profile of the last program
@@ -102,9 +105,9 @@ int grid_for(qcm_handle h, K kernel, size_t smem, uint64_t work_items_per_block,
 }
 
 // ---- block / mux launch -----------------------------------------------------------
-template <typename R, int V, int M, int U>
+template <typename R, int V, int M, int U, bool LAZY>
 int launch_block_t(qcm_handle h, const BlockArgs &a, size_t smem) {
-    auto kern = k_block<R, V, M, U>;
+    auto kern = k_block<R, V, M, U, LAZY>;
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t nvec = (1ull << (a.n_out - M)) / V;
     const int grid = grid_for(h, kern, smem, (uint64_t)kThreads * U, nvec);
@@ -114,25 +117,61 @@ int launch_block_t(qcm_handle h, const BlockArgs &a, size_t smem) {
     return QCM_OK;
 }
 
-template <typename R, int V>
+template <typename R, int V, bool LAZY>
 int launch_block_m(qcm_handle h, int M, const BlockArgs &a, size_t smem) {
     switch (M) {
-        case 1: return launch_block_t<R, V, 1, 4>(h, a, smem);
-        case 2: return launch_block_t<R, V, 2, 2>(h, a, smem);
-        case 3: return launch_block_t<R, V, 3, 1>(h, a, smem);
-        case 4: return launch_block_t<R, V, 4, 1>(h, a, smem);
-        case 5: return launch_block_t<R, V, 5, 1>(h, a, smem);
+        case 1: return launch_block_t<R, V, 1, 4, LAZY>(h, a, smem);
+        case 2: return launch_block_t<R, V, 2, 2, LAZY>(h, a, smem);
+        case 3: return launch_block_t<R, V, 3, 1, LAZY>(h, a, smem);
+        case 4: return launch_block_t<R, V, 4, 1, LAZY>(h, a, smem);
+        case 5: return launch_block_t<R, V, 5, 1, LAZY>(h, a, smem);
     }
     return fail(h, QCM_ERR_INVALID, "block size %d out of range", M);
 }
 
-// members: ops[0..n_mem) are MUX1Q; tq: block qubits ascending
-int launch_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_mem, int n_in, int n_out,
-                 size_t n_tables) {
+template <typename R, int V, int M, int U>
+int launch_expand_t(qcm_handle h, const ExpandArgs &a, size_t smem) {
+    auto kern = k_expand<R, V, M, U>;
+    if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t nvec = (1ull << a.n_in) / V;
+    const int grid = grid_for(h, kern, smem, (uint64_t)kThreads * U, nvec);
+    kern<<<grid, kThreads, smem, h->stream>>>(a);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    return QCM_OK;
+}
+
+template <typename R, int V>
+int launch_expand_m(qcm_handle h, int M, const ExpandArgs &a, size_t smem) {
+    switch (M) {
+        case 1: return launch_expand_t<R, V, 1, 4>(h, a, smem);
+        case 2: return launch_expand_t<R, V, 2, 4>(h, a, smem);
+        case 3: return launch_expand_t<R, V, 3, 2>(h, a, smem);
+        case 4: return launch_expand_t<R, V, 4, 2>(h, a, smem);
+        case 5: return launch_expand_t<R, V, 5, 2>(h, a, smem);
+    }
+    return fail(h, QCM_ERR_INVALID, "expansion of %d qubits out of range", M);
+}
+
+struct BlockPlan {
+    BlockArgs args{};
+    int M = 0;
+    size_t smem = 0;
+    bool expand = false;            // eligible for the expansion fast path
+    ExpandTableArgs targs{};
+    ExpandArgs eargs{};
+    bool norm_preserving = false;   // expansion without diagonal members: sum_a |out[x,a]|^2 == |in[x]|^2
+};
+
+// members: ops[0..n_mem) are MUX1Q (or DIAG: a diagonal factor applied in the same sweep);
+// tq: block qubits ascending.  Validates and fills `bp`; launches nothing.
+int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_mem, int n_in, int n_out,
+               size_t n_tables, BlockPlan &bp) {
     if (M < 1 || M > QCM_MAX_BLOCK) return fail(h, QCM_ERR_INVALID, "block of %d qubits unsupported (max %d)", M, QCM_MAX_BLOCK);
     if (n_mem > QCM_MAX_MEMBERS) return fail(h, QCM_ERR_INVALID, "block has %d members (max %d)", n_mem, QCM_MAX_MEMBERS);
     if (n_out > h->n_local || n_in > n_out || n_in < 0) return fail(h, QCM_ERR_INVALID, "bad active range %d -> %d (n_local %d)", n_in, n_out, h->n_local);
-    BlockArgs a{};
+    BlockArgs &a = bp.args;
+    bp.M = M;
     a.state = h->state;
     a.tables = h->tab_real.p;
     a.n_in = n_in;
@@ -148,13 +187,22 @@ int launch_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int 
         if (!std::binary_search(tq, tq + M, q))
             return fail(h, QCM_ERR_INVALID, "qubit %d is materialised by this op but is not one of its targets", q);
     size_t smem_reals = 0;
+    int per_target[QCM_MAX_BLOCK] = {0};
+    int n_diag = 0;
     for (int g = 0; g < n_mem; ++g) {
         const qcm_op &op = members[g];
-        if (op.kind != QCM_OP_MUX1Q) return fail(h, QCM_ERR_INVALID, "block member %d is not MUX1Q", g);
+        const bool diag = op.kind == QCM_OP_DIAG;
+        if (op.kind != QCM_OP_MUX1Q && !diag) return fail(h, QCM_ERR_INVALID, "block member %d is neither MUX1Q nor DIAG", g);
         if (op.n_ctrl < 0 || op.n_ctrl > QCM_MAX_CTRL) return fail(h, QCM_ERR_INVALID, "member %d: n_ctrl %d out of range", g, op.n_ctrl);
-        const int *pp = std::lower_bound(tq, tq + M, op.target);
-        if (pp == tq + M || *pp != op.target) return fail(h, QCM_ERR_INVALID, "member %d targets qubit %d which is not a block qubit", g, op.target);
-        a.mem[g].pos = (int8_t)(pp - tq);
+        if (diag) {
+            a.mem[g].pos = -1;
+            ++n_diag;
+        } else {
+            const int *pp = std::lower_bound(tq, tq + M, op.target);
+            if (pp == tq + M || *pp != op.target) return fail(h, QCM_ERR_INVALID, "member %d targets qubit %d which is not a block qubit", g, op.target);
+            a.mem[g].pos = (int8_t)(pp - tq);
+            per_target[pp - tq]++;
+        }
         a.mem[g].n_ctrl = (int8_t)op.n_ctrl;
         for (int j = 0; j < op.n_ctrl; ++j) {
             const int c = op.ctrl[j];
@@ -162,24 +210,83 @@ int launch_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int 
             if (std::binary_search(tq, tq + M, c)) return fail(h, QCM_ERR_INVALID, "member %d: index qubit %d is a block target", g, c);
             a.mem[g].ctrl[j] = (int8_t)c;
         }
-        if (op.table_off < 0 || (size_t)op.table_off + (8ull << op.n_ctrl) > n_tables)
+        const size_t need = (diag ? 2ull : 8ull) << op.n_ctrl;
+        if (op.table_off < 0 || (size_t)op.table_off + need > n_tables)
             return fail(h, QCM_ERR_INVALID, "member %d: table [%lld, +%llu) outside tables (%zu)", g, (long long)op.table_off,
-                        (unsigned long long)(8ull << op.n_ctrl), n_tables);
+                        (unsigned long long)need, n_tables);
         a.mem[g].src_off = (int32_t)op.table_off;
         a.mem[g].tab_off = (int32_t)smem_reals;
-        smem_reals += 8ull << op.n_ctrl;
+        smem_reals += (need + 3) & ~size_t(3);          // keep every table 16-byte aligned
     }
     const size_t real_sz = h->prec == QCM_C64 ? 4 : 8;
-    const size_t smem = smem_reals * real_sz;
-    if (smem > 160 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "block coefficient tables need %zu B of shared memory", smem);
-    int rc;
-    if (h->prec == QCM_C64) {
-        const bool vec2 = tq[0] >= 1 && (n_out - M) >= 1;
-        rc = vec2 ? launch_block_m<float, 2>(h, M, a, smem) : launch_block_m<float, 1>(h, M, a, smem);
-    } else {
-        rc = launch_block_m<double, 1>(h, M, a, smem);
+    bp.smem = smem_reals * real_sz;
+    if (bp.smem > 160 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "block coefficient tables need %zu B of shared memory", bp.smem);
+
+    // expansion fast path: every block qubit is new (known |0>) and the target of exactly one member
+    bool expand = (n_out - n_in == M) && tq[0] == n_in;
+    for (int j = 0; j < M && expand; ++j) expand = per_target[j] == 1;
+    if (expand) {
+        int8_t cu[QCM_MAX_MEMBERS * QCM_MAX_CTRL];
+        int nu = 0;
+        ExpandTableArgs &t = bp.targs;
+        for (int g = 0; g < n_mem && expand; ++g) {
+            t.mpos[g] = a.mem[g].pos;
+            t.mnc[g] = a.mem[g].n_ctrl;
+            t.moff[g] = members[g].table_off;
+            for (int j = 0; j < a.mem[g].n_ctrl; ++j) {
+                const int8_t c = a.mem[g].ctrl[j];
+                int k = 0;
+                while (k < nu && cu[k] != c) ++k;
+                if (k == nu) cu[nu++] = c;
+                t.mbit[g][j] = (int8_t)k;
+            }
+            if (nu + M > kExpandMaxBits) expand = false;
+        }
+        if (expand) {
+            t.M = M; t.nu = nu; t.n_members = n_mem; t.is_double = h->prec == QCM_C128;
+            ExpandArgs &e = bp.eargs;
+            e.state = h->state;
+            e.n_in = n_in;
+            e.nu = nu;
+            for (int k = 0; k < nu; ++k) e.cu[k] = cu[k];
+            e.rank_bits = rank_bits(h);
+        }
     }
-    if (rc) return rc;
+    bp.expand = expand;
+    bp.norm_preserving = expand && n_diag == 0;
+    return QCM_OK;
+}
+
+int launch_block_plan(qcm_handle h, BlockPlan &bp) {
+    const BlockArgs &a = bp.args;
+    const int M = bp.M, n_in = a.n_in, n_out = a.n_out;
+    int rc;
+    if (bp.expand) {
+        const size_t centry = h->prec == QCM_C64 ? 8 : 16;
+        const size_t nent = 1ull << (M + bp.targs.nu);
+        if ((rc = ensure(h, h->ctab, nent * centry))) return rc;
+        bp.targs.tables = (const double *)h->tab_f64.p;
+        bp.targs.ctab = h->ctab.p;
+        k_expand_table<<<(unsigned)((nent + 255) / 256), 256, 0, h->stream>>>(bp.targs);
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+        bp.eargs.ctab = h->ctab.p;
+        const size_t smem = nent * centry;
+        if (h->prec == QCM_C64) rc = n_in >= 1 ? launch_expand_m<float, 2>(h, M, bp.eargs, smem) : launch_expand_m<float, 1>(h, M, bp.eargs, smem);
+        else rc = launch_expand_m<double, 1>(h, M, bp.eargs, smem);
+        if (rc) return rc;
+        h->n_expand++;
+    } else {
+        const bool lazy = n_in != n_out;
+        if (h->prec == QCM_C64) {
+            const bool vec2 = a.tq[0] >= 1 && (n_out - M) >= 1;
+            if (vec2) rc = lazy ? launch_block_m<float, 2, true>(h, M, a, bp.smem) : launch_block_m<float, 2, false>(h, M, a, bp.smem);
+            else rc = lazy ? launch_block_m<float, 1, true>(h, M, a, bp.smem) : launch_block_m<float, 1, false>(h, M, a, bp.smem);
+        } else {
+            rc = lazy ? launch_block_m<double, 1, true>(h, M, a, bp.smem) : launch_block_m<double, 1, false>(h, M, a, bp.smem);
+        }
+        if (rc) return rc;
+    }
     // algorithmic traffic: read the materialised input, write the whole output
     h->timing.bytes_read += amp_bytes(h->prec) << n_in;
     h->timing.bytes_written += amp_bytes(h->prec) << n_out;
@@ -228,7 +335,7 @@ int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
     if (n < 0 || n > h->n_local) return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT over %d qubits (n_local %d)", n, h->n_local);
     if (op.table_off < 0 || (size_t)op.table_off + 4ull * (size_t)std::max(n, 1) > n_tables)
         return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT: table (max(n,1)*4 doubles) outside tables");
-    const int L = n / 2;
+    const int L = n >= 1 ? std::max(1, n / 2) : 0;   // a 2-amplitude vector must share one `hi` factor
     int rc;
     if ((rc = ensure(h, h->init_lo, sizeof(double2) << L))) return rc;
     if ((rc = ensure(h, h->init_hi, sizeof(double2) << (n - L)))) return rc;
@@ -363,6 +470,8 @@ int build_tree(qcm_handle h) {
     h->local_mass = m;
     h->tree_valid = true;
     h->tree_for_active = na;
+    h->tree_base_bits = na;
+    h->tree_cond_bits = 0;
     return QCM_OK;
 }
 
@@ -434,7 +543,7 @@ int qcm_destroy(qcm_handle h) {
     if (!h) return QCM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree};
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->own_state && h->state) cudaFree(h->state);
@@ -522,6 +631,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     int rc = check_device(h);
     if (rc) return rc;
     h->tree_valid = false;
+    bool keep_tree = false;
     h->timing.bytes_read = h->timing.bytes_written = 0;
     QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if ((rc = upload_tables(h, tables, n_tables))) return rc;
@@ -546,17 +656,38 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
             case QCM_OP_INIT_PRODUCT:
                 if ((rc = launch_init(h, op, n_tables))) return rc;
                 break;
-            case QCM_OP_MUX1Q: {
-                int tq[1] = {op.target};
-                if ((rc = launch_block(h, tq, 1, &op, 1, op.n_active_in, op.n_active_out, n_tables))) return rc;
-                break;
-            }
+            case QCM_OP_MUX1Q:
             case QCM_OP_BLOCK: {
-                const int M = op.target, n_mem = op.n_ctrl;
-                if (M < 1 || M > QCM_MAX_BLOCK) return fail(h, QCM_ERR_INVALID, "op %d: block of %d qubits (max %d)", i, M, QCM_MAX_BLOCK);
-                if (n_mem < 0 || i + n_mem > n_ops - 1) return fail(h, QCM_ERR_INVALID, "op %d: block members run past the program", i);
-                if ((rc = launch_block(h, op.ctrl, M, ops + i + 1, n_mem, op.n_active_in, op.n_active_out, n_tables))) return rc;
-                i += n_mem;
+                BlockPlan bp;
+                int n_mem = 1;
+                if (op.kind == QCM_OP_MUX1Q) {
+                    int tq[1] = {op.target};
+                    if ((rc = plan_block(h, tq, 1, &op, 1, op.n_active_in, op.n_active_out, n_tables, bp))) return rc;
+                } else {
+                    const int M = op.target;
+                    n_mem = op.n_ctrl;
+                    if (M < 1 || M > QCM_MAX_BLOCK) return fail(h, QCM_ERR_INVALID, "op %d: block of %d qubits (max %d)", i, M, QCM_MAX_BLOCK);
+                    if (n_mem < 0 || i + n_mem > n_ops - 1) return fail(h, QCM_ERR_INVALID, "op %d: block members run past the program", i);
+                    if ((rc = plan_block(h, op.ctrl, M, ops + i + 1, n_mem, op.n_active_in, op.n_active_out, n_tables, bp))) return rc;
+                }
+                // Sampling checkpoint: the final pass only multiplies every stored amplitude
+                // into 2^M images whose squared moduli add up to the original, so the sum tree
+                // can be built on the 2^M-times smaller input instead of re-reading the result.
+                const bool last = (i + (op.kind == QCM_OP_BLOCK ? n_mem : 0)) == n_ops - 1;
+                bool checkpoint = last && (op.flags & QCM_FLAG_SAMPLE_CHECKPOINT) && bp.norm_preserving &&
+                                  h->n_global == 0 && op.n_active_in >= kChunkBits;
+                if (checkpoint) {
+                    if ((rc = build_tree(h))) return rc;
+                    h->timing.bytes_read += amp_bytes(h->prec) << op.n_active_in;     // the tree's level-0 read
+                }
+                if ((rc = launch_block_plan(h, bp))) return rc;
+                if (checkpoint) {
+                    h->tree_cond_bits = bp.M;
+                    h->tree_for_active = op.n_active_out;
+                    h->n_checkpoint++;
+                    keep_tree = true;
+                }
+                if (op.kind == QCM_OP_BLOCK) i += n_mem;
                 break;
             }
             case QCM_OP_DIAG:
@@ -572,6 +703,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 return fail(h, QCM_ERR_INVALID, "op %d: unknown kind %d", i, op.kind);
         }
         h->n_active = op.n_active_out;
+        if (!keep_tree) h->tree_valid = false;
         QCM_CUDA(h, mark());
         h->op_kind.push_back(op.kind);
         h->op_rd.push_back(h->timing.bytes_read - rd0);
@@ -677,7 +809,8 @@ int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t str
     QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     SampleArgs a{};
     a.state = h->state;
-    a.n_active = h->n_active;
+    a.n_active = h->tree_base_bits;
+    a.cond_bits = h->tree_cond_bits;
     a.n_levels = h->tree_levels;
     for (int l = 0; l < h->tree_levels; ++l) {
         a.level[l] = h->tree_ptr[l];

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "qcmrf_b200.h"
 
 namespace qcm {
@@ -70,7 +72,8 @@ template <> struct VecIO<double, 1> {
 // (`nz` tracks which registers can be non-zero; it is uniform across the grid).
 // ----------------------------------------------------------------------------------
 struct MemberDesc {
-    int8_t pos;                     // position of the member's target inside tq[]
+    int8_t pos;                     // position of the member's target inside tq[]; -1: diagonal member
+                                    // (amp *= table[idx], 2 reals per entry) applied to every register
     int8_t n_ctrl;
     int8_t ctrl[QCM_MAX_CTRL];      // qubit feeding table-index bit j (may be global)
     int32_t tab_off;                // offset, in reals, of this member's table in shared memory
@@ -87,7 +90,7 @@ struct BlockArgs {
     MemberDesc mem[QCM_MAX_MEMBERS];
 };
 
-template <typename R, int V, int NR, int P>
+template <typename R, int V, int NR, int P, bool LAZY>
 __device__ __forceinline__ void butterfly(R (&ar)[NR][V], R (&ai)[NR][V], const R (&m)[8], int v,
                                           uint32_t nz) {
     if constexpr ((1 << P) < NR) {
@@ -95,7 +98,8 @@ __device__ __forceinline__ void butterfly(R (&ar)[NR][V], R (&ai)[NR][V], const 
         for (int r = 0; r < NR; ++r) {
             if (r & (1 << P)) continue;
             const int r1 = r | (1 << P);
-            if (!(((nz >> r) | (nz >> r1)) & 1u)) continue;       // uniform branch
+            if constexpr (LAZY)
+                if (!(((nz >> r) | (nz >> r1)) & 1u)) continue;   // uniform branch
             const R x0 = ar[r][v], y0 = ai[r][v], x1 = ar[r1][v], y1 = ai[r1][v];
             ar[r][v] = m[0] * x0 - m[1] * y0 + m[2] * x1 - m[3] * y1;
             ai[r][v] = m[0] * y0 + m[1] * x0 + m[2] * y1 + m[3] * x1;
@@ -105,7 +109,24 @@ __device__ __forceinline__ void butterfly(R (&ar)[NR][V], R (&ai)[NR][V], const 
     }
 }
 
-template <typename R, int V, int M, int U>
+template <typename R>
+__device__ __forceinline__ void load_m8(const R *p, R (&m)[8]) {
+    if constexpr (sizeof(R) == 4) {
+        const float4 m0 = *reinterpret_cast<const float4 *>(p);
+        const float4 m1 = *reinterpret_cast<const float4 *>(p + 4);
+        m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w;
+        m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double2 t = *reinterpret_cast<const double2 *>(p + 2 * q);
+            m[2 * q] = t.x; m[2 * q + 1] = t.y;
+        }
+    }
+}
+
+// LAZY = false: every block qubit is materialised on input (n_in == n_out): no zero tracking.
+template <typename R, int V, int M, int U, bool LAZY>
 __global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
     constexpr int NR = 1 << M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -113,7 +134,8 @@ __global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
     for (int g = 0; g < a.n_members; ++g) {
         const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
         R *dst = tab + a.mem[g].tab_off;
-        for (int i = threadIdx.x; i < (8 << a.mem[g].n_ctrl); i += blockDim.x) dst[i] = src[i];
+        const int cnt = (a.mem[g].pos < 0 ? 2 : 8) << a.mem[g].n_ctrl;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
     using IO = VecIO<R, V>;
@@ -123,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
         toff[j] = 1ull << a.tq[j];
-        if (a.tq[j] >= a.n_in) zmask |= 1u << j;
+        if (LAZY && a.tq[j] >= a.n_in) zmask |= 1u << j;
     }
     uint32_t nz0 = 0;
 #pragma unroll
@@ -146,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
             base[u] = b;
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
-                if (ok[u] && ((nz0 >> r) & 1u)) {
+                if (ok[u] && (!LAZY || ((nz0 >> r) & 1u))) {
                     uint64_t off = b;
 #pragma unroll
                     for (int j = 0; j < M; ++j)
@@ -170,35 +192,36 @@ __global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
                     const uint64_t gi = (base[u] + v) | a.rank_bits;
                     uint32_t idx = 0;
                     for (int j = 0; j < nc; ++j) idx |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
-                    R m[8];
-                    if constexpr (sizeof(R) == 4) {
-                        const float4 m0 = *reinterpret_cast<const float4 *>(mt + 8 * idx);
-                        const float4 m1 = *reinterpret_cast<const float4 *>(mt + 8 * idx + 4);
-                        m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w;
-                        m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
-                    } else {
+                    if (pos < 0) {                                  // diagonal member
+                        const R c = mt[2 * idx], sn = mt[2 * idx + 1];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const double2 t = *reinterpret_cast<const double2 *>(mt + 8 * idx + 2 * q);
-                            m[2 * q] = t.x; m[2 * q + 1] = t.y;
+                        for (int r = 0; r < NR; ++r) {
+                            const R x = ar[u][r][v], y = ai[u][r][v];
+                            ar[u][r][v] = c * x - sn * y;
+                            ai[u][r][v] = c * y + sn * x;
                         }
+                        continue;
                     }
+                    R m[8];
+                    load_m8<R>(mt + 8 * idx, m);
                     switch (pos) {
-                        case 0: butterfly<R, V, NR, 0>(ar[u], ai[u], m, v, nz); break;
-                        case 1: butterfly<R, V, NR, 1>(ar[u], ai[u], m, v, nz); break;
-                        case 2: butterfly<R, V, NR, 2>(ar[u], ai[u], m, v, nz); break;
-                        case 3: butterfly<R, V, NR, 3>(ar[u], ai[u], m, v, nz); break;
-                        default: butterfly<R, V, NR, 4>(ar[u], ai[u], m, v, nz); break;
+                        case 0: butterfly<R, V, NR, 0, LAZY>(ar[u], ai[u], m, v, nz); break;
+                        case 1: butterfly<R, V, NR, 1, LAZY>(ar[u], ai[u], m, v, nz); break;
+                        case 2: butterfly<R, V, NR, 2, LAZY>(ar[u], ai[u], m, v, nz); break;
+                        case 3: butterfly<R, V, NR, 3, LAZY>(ar[u], ai[u], m, v, nz); break;
+                        default: butterfly<R, V, NR, 4, LAZY>(ar[u], ai[u], m, v, nz); break;
                     }
                 }
             }
-            // registers that can be non-zero after a butterfly on bit `pos`
-            const uint32_t sh = 1u << pos;
-            uint32_t lowsel = 0;
+            if (LAZY && pos >= 0) {
+                // registers that can be non-zero after a butterfly on bit `pos`
+                const uint32_t sh = 1u << pos;
+                uint32_t lowsel = 0;
 #pragma unroll
-            for (int r = 0; r < NR; ++r)
-                if (!(r & sh)) lowsel |= 1u << r;
-            nz = nz | ((nz & lowsel) << sh) | ((nz & ~lowsel) >> sh);
+                for (int r = 0; r < NR; ++r)
+                    if (!(r & sh)) lowsel |= 1u << r;
+                nz = nz | ((nz & lowsel) << sh) | ((nz & ~lowsel) >> sh);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -210,6 +233,117 @@ __global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
                 for (int j = 0; j < M; ++j)
                     if ((r >> j) & 1) off += toff[j];
                 IO::store(a.state, off, ar[u][r], ai[u][r]);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// Expansion pass (lazy materialisation fast path).
+//
+// All M block qubits are the new qubits n_in .. n_in+M-1, each the target of exactly
+// one member, all known |0> on input.  Then
+//     out[x | a << n_in] = in[x] * prod_j table_j[idx_j(x)][a_j][0] * prod_d diag_d[idx_d(x)]
+// -- one complex multiply per output amplitude.  The products are precombined by
+// k_expand_table over the union of the members' index qubits (nu bits) into
+// ctab[a][cidx]; the pass stages ctab in shared memory, reads each input amplitude
+// once and writes its 2^M images: read 2^n_in, write 2^(n_in+M), nothing else.
+// ----------------------------------------------------------------------------------
+constexpr int kExpandMaxBits = 12;          // nu + M: 4096 entries (32 KB c64, 64 KB c128)
+
+struct ExpandArgs {
+    void *state;
+    const void *ctab;               // device, [2^M][2^nu] complex in the state's real type
+    int32_t n_in, nu;
+    int8_t cu[kExpandMaxBits];      // union of index qubits: cidx bit j <-> qubit cu[j]
+    uint64_t rank_bits;
+};
+
+struct ExpandTableArgs {
+    const double *tables;           // fp64 tables of the program
+    void *ctab;
+    int32_t M, nu, n_members, is_double;
+    int8_t mpos[QCM_MAX_MEMBERS];   // target position 0..M-1, or -1 for a diagonal member
+    int8_t mnc[QCM_MAX_MEMBERS];
+    int8_t mbit[QCM_MAX_MEMBERS][QCM_MAX_CTRL];     // member index bit j <-> cidx bit mbit[g][j]
+    int64_t moff[QCM_MAX_MEMBERS];
+};
+
+static __global__ void k_expand_table(const ExpandTableArgs a) {
+    const uint32_t n = 1u << (a.M + a.nu);
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint32_t cidx = e & ((1u << a.nu) - 1u), r = e >> a.nu;
+    double re = 1.0, im = 0.0;
+    for (int g = 0; g < a.n_members; ++g) {
+        uint32_t idx = 0;
+        for (int j = 0; j < a.mnc[g]; ++j) idx |= ((cidx >> a.mbit[g][j]) & 1u) << j;
+        double fr, fi;
+        if (a.mpos[g] < 0) {
+            fr = a.tables[a.moff[g] + 2 * idx];
+            fi = a.tables[a.moff[g] + 2 * idx + 1];
+        } else {
+            const int bit = (r >> a.mpos[g]) & 1u;                  // column 0 of the 2x2: m00 / m10
+            fr = a.tables[a.moff[g] + 8 * idx + 4 * bit];
+            fi = a.tables[a.moff[g] + 8 * idx + 4 * bit + 1];
+        }
+        const double nr = re * fr - im * fi;
+        im = re * fi + im * fr;
+        re = nr;
+    }
+    if (a.is_double) reinterpret_cast<double2 *>(a.ctab)[e] = make_double2(re, im);
+    else reinterpret_cast<float2 *>(a.ctab)[e] = make_float2((float)re, (float)im);
+}
+
+template <typename R, int V, int M, int U>
+__global__ void __launch_bounds__(kThreads) k_expand(const ExpandArgs a) {
+    constexpr int NR = 1 << M;
+    using IO = VecIO<R, V>;
+    using C2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C2 *tab = reinterpret_cast<C2 *>(smem_raw);
+    {
+        const C2 *src = reinterpret_cast<const C2 *>(a.ctab);
+        for (int i = threadIdx.x; i < (NR << a.nu); i += blockDim.x) tab[i] = src[i];
+    }
+    __syncthreads();
+    const int nu = a.nu;
+    uint32_t low_bit = 0;                      // cidx bit fed by qubit 0 (differs between the V amplitudes)
+    for (int j = 0; j < nu; ++j)
+        if (a.cu[j] == 0) low_bit |= 1u << j;
+    const uint64_t nvec = (1ull << a.n_in) / V;
+    const uint64_t ostride = 1ull << a.n_in;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
+    for (uint64_t bv0 = (uint64_t)blockIdx.x * blockDim.x * U + threadIdx.x; bv0 < nvec; bv0 += stride) {
+        R xr[U][V], xi[U][V];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t bv = bv0 + (uint64_t)u * blockDim.x;
+            ok[u] = bv < nvec;
+            if (ok[u]) IO::load(a.state, bv * V, xr[u], xi[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const uint64_t b = (bv0 + (uint64_t)u * blockDim.x) * V;
+            const uint64_t gi = b | a.rank_bits;
+            uint32_t cidx = 0;
+            for (int j = 0; j < nu; ++j) cidx |= (uint32_t)((gi >> a.cu[j]) & 1ull) << j;
+            const C2 *t0 = tab + cidx;
+            const C2 *t1 = tab + (cidx | low_bit);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                R orr[V], oi[V];
+                const C2 c0 = t0[r << nu];
+                orr[0] = c0.x * xr[u][0] - c0.y * xi[u][0];
+                oi[0] = c0.x * xi[u][0] + c0.y * xr[u][0];
+                if constexpr (V == 2) {
+                    const C2 c1 = t1[r << nu];
+                    orr[1] = c1.x * xr[u][1] - c1.y * xi[u][1];
+                    oi[1] = c1.x * xi[u][1] + c1.y * xr[u][1];
+                }
+                IO::store(a.state, b + (uint64_t)r * ostride, orr, oi);
             }
         }
     }
@@ -354,7 +488,8 @@ __device__ __forceinline__ double warp_sum(double x) {
 constexpr int kChunkBits = 10;                  // 1024 amplitudes per leaf chunk
 constexpr int kFanBits = 10;                    // 1024 children per tree node
 
-// level 0: chunk c = sum_{i in chunk} |amp_i|^2 ; one warp per chunk
+// level 0: chunk c = sum_{i in chunk} |amp_i|^2 ; one warp per chunk.  Full-size chunks
+// stream 128-bit loads, eight in flight per lane; the lane-strided order is fixed.
 template <typename R>
 __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int n_active, double *out) {
     const int cb = n_active < kChunkBits ? n_active : kChunkBits;
@@ -366,16 +501,43 @@ __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int 
     for (uint64_t c = warp0; c < nchunks; c += nwarps) {
         double acc = 0.0;
         if constexpr (sizeof(R) == 4) {
-            const float2 *p = reinterpret_cast<const float2 *>(state) + c * csz;
-            for (uint64_t i = lane; i < csz; i += 32) {
-                const float2 t = p[i];
-                acc += (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+            if (cb == kChunkBits) {
+                const float4 *p = reinterpret_cast<const float4 *>(state) + c * (csz / 2);
+                constexpr int kIter = (1 << kChunkBits) / 2 / 32;        // 16 vectors per lane
+#pragma unroll
+                for (int i0 = 0; i0 < kIter; i0 += 8) {
+                    float4 t[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) t[k] = __ldcs(p + lane + 32 * (i0 + k));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        acc += ((double)t[k].x * (double)t[k].x + (double)t[k].y * (double)t[k].y) +
+                               ((double)t[k].z * (double)t[k].z + (double)t[k].w * (double)t[k].w);
+                }
+            } else {
+                const float2 *p = reinterpret_cast<const float2 *>(state) + c * csz;
+                for (uint64_t i = lane; i < csz; i += 32) {
+                    const float2 t = p[i];
+                    acc += (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+                }
             }
         } else {
             const double2 *p = reinterpret_cast<const double2 *>(state) + c * csz;
-            for (uint64_t i = lane; i < csz; i += 32) {
-                const double2 t = p[i];
-                acc += t.x * t.x + t.y * t.y;
+            if (cb == kChunkBits) {
+                constexpr int kIter = (1 << kChunkBits) / 32;            // 32 amplitudes per lane
+#pragma unroll
+                for (int i0 = 0; i0 < kIter; i0 += 8) {
+                    double2 t[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) t[k] = __ldcs(p + lane + 32 * (i0 + k));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc += t[k].x * t[k].x + t[k].y * t[k].y;
+                }
+            } else {
+                for (uint64_t i = lane; i < csz; i += 32) {
+                    const double2 t = p[i];
+                    acc += t.x * t.x + t.y * t.y;
+                }
             }
         }
         acc = warp_sum(acc);
@@ -473,7 +635,10 @@ __device__ __forceinline__ uint32_t warp_pick(F w, uint32_t cnt, double &u, int 
 
 struct SampleArgs {
     const void *state;
-    int32_t n_active;
+    int32_t n_active;               // qubits the sum tree indexes (its leaves are x < 2^n_active)
+    int32_t cond_bits;              // > 0: the state holds 2^cond_bits images of every leaf x, at
+                                    // x | a << n_active (an expansion pass ran after the tree was built):
+                                    // leaf weight = sum_a |amp|^2, then a is drawn given x
     int32_t n_levels;               // tree levels above the amplitudes (>= 1)
     const double *level[8];         // level[0] = chunk sums ... level[n_levels-1] = top
     uint64_t level_n[8];
@@ -513,15 +678,30 @@ __global__ void __launch_bounds__(kThreads) k_sample(const SampleArgs a) {
         }
         // node = chunk index; search the amplitudes of the chunk
         const uint64_t afirst = node << cb;
-        uint32_t within;
-        if constexpr (sizeof(R) == 4) {
-            const float2 *p = reinterpret_cast<const float2 *>(a.state) + afirst;
-            within = warp_pick([&](uint32_t i) { const float2 t = p[i]; return (double)t.x * (double)t.x + (double)t.y * (double)t.y; },
-                               1u << cb, u, lane);
+        const int nb = 1 << a.cond_bits;
+        auto amp_w = [&](uint64_t i) -> double {
+            if constexpr (sizeof(R) == 4) {
+                const float2 t = reinterpret_cast<const float2 *>(a.state)[i];
+                return (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+            } else {
+                const double2 t = reinterpret_cast<const double2 *>(a.state)[i];
+                return t.x * t.x + t.y * t.y;
+            }
+        };
+        uint64_t within;
+        if (a.cond_bits == 0) {
+            within = warp_pick([&](uint32_t i) { return amp_w(afirst + i); }, 1u << cb, u, lane);
         } else {
-            const double2 *p = reinterpret_cast<const double2 *>(a.state) + afirst;
-            within = warp_pick([&](uint32_t i) { const double2 t = p[i]; return t.x * t.x + t.y * t.y; },
-                               1u << cb, u, lane);
+            const uint32_t x = warp_pick(
+                [&](uint32_t i) {
+                    double sacc = 0.0;
+                    for (int br = 0; br < nb; ++br) sacc += amp_w(afirst + i + ((uint64_t)br << a.n_active));
+                    return sacc;
+                },
+                1u << cb, u, lane);
+            const uint32_t br = warp_pick([&](uint32_t i) { return amp_w(afirst + x + ((uint64_t)i << a.n_active)); },
+                                          (uint32_t)nb, u, lane);
+            within = (uint64_t)x + ((uint64_t)br << a.n_active);
         }
         if (lane == 0) {
             const uint64_t gi = (afirst + within) | a.rank_bits;

@@ -377,6 +377,19 @@ def _diag_table_f64(table):
     return t
 
 
+QCM_FLAG_SAMPLE_CHECKPOINT = 1
+
+
+def _flag_last_pass(ops):
+    """Set QCM_FLAG_SAMPLE_CHECKPOINT on the header of the program's last pass."""
+    i, last = 0, -1
+    while i < len(ops):
+        last = i
+        i += 1 + (int(ops[i]['n_ctrl']) if ops[i]['kind'] == QCM_OP_BLOCK else 0)
+    if last >= 0 and ops[last]['kind'] in (QCM_OP_BLOCK, QCM_OP_MUX1Q):
+        ops[last]['flags'] = QCM_FLAG_SAMPLE_CHECKPOINT
+
+
 def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optional[bool] = None,
          keep_order: bool = False) -> Plan:
     """Lay the fused circuit out for the engine.
@@ -488,4 +501,6 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
             em.op(QCM_OP_EXTEND, n_in=active, n_out=n_phys)
             active = n_phys
     ops, tabs = em.finish()
+    # shots follow the program: let the engine build the sampler's tree before a final expansion pass
+    _flag_last_pass(ops)
     return Plan(N, n_phys, layout, ops, tabs, n_passes, len(fc.ops) + 1, 0, active, fc.global_phase)

@@ -38,6 +38,16 @@ def run_plan(plan, n_global=0, rank=0, n_local=None):
         psi[i0] = M[:, 0, 0] * a0 + M[:, 0, 1] * a1
         psi[i0 | (1 << t)] = M[:, 1, 0] * a0 + M[:, 1, 1] * a1
 
+    def diag(op, n_out):
+        m = int(op['n_ctrl'])
+        tab = tabs[int(op['table_off']):int(op['table_off']) + (2 << m)].reshape(-1, 2)
+        tab = tab[:, 0] + 1j * tab[:, 1]
+        idx = np.arange(1 << n_out, dtype=np.int64) | rank_bits
+        ti = np.zeros(1 << n_out, dtype=np.int64)
+        for j, c in enumerate(op['ctrl'][:m]):
+            ti |= ((idx >> int(c)) & 1) << j
+        psi[: 1 << n_out] *= tab[ti]
+
     while i < len(ops):
         op = ops[i]
         kind = int(op['kind'])
@@ -66,21 +76,17 @@ def run_plan(plan, n_global=0, rank=0, n_local=None):
             assert not np.isnan(psi[: 1 << n_in]).any()
             psi[1 << n_in: 1 << n_out] = 0.0
             for mb in members:
-                assert int(mb['kind']) == F.QCM_OP_MUX1Q and int(mb['target']) in tq
                 for c in mb['ctrl'][:int(mb['n_ctrl'])]:
                     assert int(c) not in tq
+                if int(mb['kind']) == F.QCM_OP_DIAG and kind == F.QCM_OP_BLOCK:
+                    diag(mb, n_out)                    # diagonal factor riding in the same sweep
+                    continue
+                assert int(mb['kind']) == F.QCM_OP_MUX1Q and int(mb['target']) in tq
                 mux(mb, n_in, n_out)
             if kind == F.QCM_OP_BLOCK:
                 i += len(members)
         elif kind == F.QCM_OP_DIAG:
-            m = int(op['n_ctrl'])
-            tab = tabs[int(op['table_off']):int(op['table_off']) + (2 << m)].reshape(-1, 2)
-            tab = tab[:, 0] + 1j * tab[:, 1]
-            idx = np.arange(1 << n_out, dtype=np.int64) | rank_bits
-            ti = np.zeros(1 << n_out, dtype=np.int64)
-            for j, c in enumerate(op['ctrl'][:m]):
-                ti |= ((idx >> int(c)) & 1) << j
-            psi[: 1 << n_out] *= tab[ti]
+            diag(op, n_out)
         elif kind == F.QCM_OP_EXTEND:
             psi[1 << n_in: 1 << n_out] = 0.0
         elif kind == F.QCM_OP_SWAP:

@@ -400,3 +400,88 @@ def test_mid_size_tree_mrf_properties():
     p2, d2 = sim.exact(circ)
     assert np.abs(p2 - pb).max() < 1e-5 and abs(d2 - db) < 1e-5
     sim.close()
+
+
+# ------------------------------------------------------------------------------------------
+def _expansion_program(rng, n0, Ms, with_diag, flags_last):
+    """INIT over n0 qubits, then pure expansion passes (every block qubit new, one MUX1Q each,
+    optional diagonal members): the fast path of the lazily materialised schedule."""
+    e = fusion._Emitter()
+    v = rng.randn(n0, 2) + 1j * rng.randn(n0, 2)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    qv = np.stack([v[:, 0].real, v[:, 0].imag, v[:, 1].real, v[:, 1].imag], axis=1)
+    e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=n0, table_off=e.table(qv))
+
+    def rand_u(m):
+        q, _ = np.linalg.qr(rng.randn(1 << m, 2, 2) + 1j * rng.randn(1 << m, 2, 2))
+        return q
+    act = n0
+    for M in Ms:
+        tq = list(range(act, act + M))
+        members = []
+        for t in rng.permutation(tq):
+            m = int(rng.randint(0, 3))
+            ctrl = [int(c) for c in rng.permutation(act)[:m]]
+            if act >= 1 and rng.rand() < 0.3 and 0 not in ctrl and m < 2:
+                ctrl.append(0)                                       # qubit 0 splits the 2-amplitude vector
+            members.append((fusion.QCM_OP_MUX1Q, int(t), ctrl, fusion._mux_table_f64(rand_u(len(ctrl)))))
+        if with_diag:
+            ctrl = [int(c) for c in rng.permutation(act)[:2]]
+            d = np.exp(1j * rng.uniform(0, 6, 4))
+            members.insert(int(rng.randint(len(members) + 1)), (fusion.QCM_OP_DIAG, 0, ctrl, fusion._diag_table_f64(d)))
+        if len(members) == 1:
+            k, t, c, tab = members[0]
+            e.op(k, target=t, ctrl=c, n_in=act, n_out=act + M, table_off=e.table(tab))
+        else:
+            e.op(fusion.QCM_OP_BLOCK, target=M, ctrl=tq, n_in=act, n_out=act + M, n_ctrl=len(members))
+            for k, t, c, tab in members:
+                e.op(k, target=t, ctrl=c, n_in=act, n_out=act + M, table_off=e.table(tab))
+        act += M
+    ops, tabs = e.finish()
+    if flags_last:
+        fusion._flag_last_pass(ops)
+    return ops, tabs, act
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('with_diag', [False, True])
+def test_expansion_fast_path(precision, with_diag):
+    rng = np.random.RandomState(77)
+    for n0, Ms in ((1, [1, 2, 3]), (3, [4, 5]), (2, [5, 1, 4]), (6, [3, 3, 2]), (0, [2, 2])):
+        ops, tabs, act = _expansion_program(rng, n0, Ms, with_diag, False)
+        with _native.Handle(act, precision) as h:
+            h.set_amplitudes(np.full(1 << act, np.nan + 1j * np.nan), 0, n_active=0)
+            pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, act
+            want, a2 = em.run_plan(pl)
+            h.run_program(ops, tabs)
+            got = h.get_amplitudes().astype(np.complex128)
+            assert h.get_active() == a2 == act
+            assert np.abs(got - want).max() < (1e-12 if precision == 'double' else 3e-6)
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_sampling_checkpoint_matches_full_tree(precision):
+    """Shots drawn through the checkpoint tree (built before the final expansion pass, new
+    qubits sampled conditionally) follow the same distribution as shots drawn from a tree
+    over the whole result."""
+    rng = np.random.RandomState(5)
+    n0, Ms = 11, [3, 4]
+    ops, tabs, act = _expansion_program(rng, n0, Ms, False, True)
+    assert ops['flags'].sum() == 1
+    S = 400000
+    with _native.Handle(act, precision) as h:
+        h.run_program(ops, tabs)
+        pr = np.abs(h.get_amplitudes().astype(np.complex128)) ** 2
+        a = h.sample(S, seed=9, stream_id=0)
+        a2 = h.sample(S, seed=9, stream_id=0)
+        plain = ops.copy(); plain['flags'] = 0
+        h.run_program(plain, tabs)
+        b = h.sample(S, seed=9, stream_id=0)
+    assert np.array_equal(a, a2)
+    assert np.all(pr[a.astype(np.int64)] > 0)
+    # the two trees order the outcomes differently (x-major vs index order), so the same uniforms
+    # give different shots: compare both histograms with the exact distribution
+    assert not np.array_equal(a, b)
+    for keys in (a, b):
+        emp = np.bincount(keys.astype(np.int64), minlength=1 << act) / S
+        assert 0.5 * np.abs(emp - pr / pr.sum()).sum() < weissman_tv_bound(int((pr > 0).sum()), S)
