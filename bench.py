@@ -165,6 +165,7 @@ def main():
     ap.add_argument('--workload', default='q34')
     ap.add_argument('--block-max', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-dense', action='store_true', help='skip the dense in-place gate-pass measurement')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3
@@ -252,6 +253,11 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms_mean = float(e2e_t.cpu())
     clk = clocks.stop() if rank == 0 else None
+    last_timing = sim.last_timing() if hasattr(sim, 'last_timing') else None
+    dense = None
+    if world == 1 and not args.no_dense:
+        sim.close()
+        dense = dense_gate_pass(args, cliques, local_rank)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -277,6 +283,7 @@ def main():
                             'program_ms': prog_ms, 'program_gbs': total_bytes / max(prog_ms, 1e-9) / 1e6,
                             'wall_ms_per_step': wall_ms / args.steps},
                 'hbm_gbs_program': total_bytes / max(prog_ms, 1e-9) / 1e6,
+                'device_timing_last_step': last_timing, 'dense_gate_pass': dense,
                 'check': {'delta': float(delta), 'p_sum': float(np.sum(p)), 'shots': int(sum(counts.values()))}}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_reference(cliques, steps=1, warmup=0)
@@ -285,6 +292,30 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     sim.close()
+
+
+def dense_gate_pass(args, cliques, device):
+    """The plain in-place gate pass (one fused clique = one read+write sweep of the whole,
+    fully materialised state; Aer-like width incl. the scratch qubit when it fits): the
+    kernel BASELINE.json's 70%-of-roofline target is about.  Not the product's default
+    schedule -- the lazily materialised one above moves ~30x fewer bytes per circuit."""
+    from qcmrf_b200 import QCMRF, B200Simulator, workloads
+    peak, _ = load_peaks()
+    sim = B200Simulator(precision='single', fusion='clique', device=device, seed=1, small_batch=False)
+    cliques, _ = workloads.named('q33')              # 33 physical qubits = 64 GiB, identity layout
+    circ = QCMRF(cliques, workloads.theta_for(cliques))
+    prep = sim.prepare(circ)
+    sim.execute(prep, 0, want_probs=False)
+    sim.execute(prep, 0, want_probs=False)
+    prof = sim.op_profile()
+    passes = [r for r in prof if r[0] == 2 and r[2] == r[3] and r[2] > 0]
+    ms = float(np.median([r[1] for r in passes]))
+    by = passes[0][2] + passes[0][3]
+    out = {'workload': 'q33 (n=16, k=16), fusion=clique: one in-place pass per clique', 'n_phys': prep.plan.n_phys, 'passes': len(passes), 'bytes_per_pass': by, 'median_ms': ms,
+           'gbs': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak,
+           'amp_updates_per_sec': (by / 16) / (ms * 1e-3), 'circuit_ms': sum(r[1] for r in prof)}
+    sim.close()
+    return out
 
 
 def world_value(v):

@@ -163,14 +163,14 @@ class B200Simulator:
             setattr(self, k, v)
 
     # -- host-side preparation -------------------------------------------------------
-    def prepare(self, circuit, n_vars=None, fusion_mode=None, block_max=None, small=False) -> _Prepared:
+    def prepare(self, circuit, n_vars=None, fusion_mode=None, block_max=None, small=False, elide=None) -> _Prepared:
         mode = fusion_mode or (self.small_fusion if small else self.fusion)
         prog = ir.lower(circuit)
         if prog.n_clbits > 64:
             raise ValueError('at most 64 classical bits are supported')
         fc = fusion.fuse(prog, 'off' if mode == 'off' else 'clique')
         lazy = (mode == 'blocked') and not small
-        pl = fusion.plan(fc, lazy=lazy, block_max=block_max or self.block_max)
+        pl = fusion.plan(fc, lazy=lazy, block_max=block_max or self.block_max, elide=elide)
         pr = _Prepared()
         pr.prog, pr.fc, pr.plan = prog, fc, pl
         pr.name = prog.name
@@ -293,6 +293,9 @@ class B200Simulator:
     def kernel_launches(self):
         """Kernels launched so far by the live state handles (bench.py's gpu_launches)."""
         return sum(h.timing()['kernel_launches'] for h in self._handles.values())
+
+    def last_timing(self):
+        return self._last.timing() if self._last is not None else None
 
     def op_profile(self):
         """Per-launch (kind, ms, bytes_read, bytes_written) of the last executed program."""

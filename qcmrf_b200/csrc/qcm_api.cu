@@ -129,26 +129,41 @@ int launch_block_m(qcm_handle h, int M, const BlockArgs &a, size_t smem) {
     return fail(h, QCM_ERR_INVALID, "block size %d out of range", M);
 }
 
-template <typename R, int V, int M, int U>
+int expand_threads() {
+    static int v = [] {
+        const char *e = getenv("QCM_EXPAND_THREADS");          // tuning knob for profiling runs
+        int t = e ? atoi(e) : 512;
+        if (t < 64 || t > kExpandThreadsMax || (t & (t - 1))) t = 512;
+        return t;
+    }();
+    return v;
+}
+
+template <typename R, int V, int M, int U, bool Q0>
 int launch_expand_t(qcm_handle h, const ExpandArgs &a, size_t smem) {
-    auto kern = k_expand<R, V, M, U>;
+    auto kern = k_expand<R, V, M, U, Q0>;
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = expand_threads();
     const uint64_t nvec = (1ull << a.n_in) / V;
-    const int grid = grid_for(h, kern, smem, (uint64_t)kThreads * U, nvec);
-    kern<<<grid, kThreads, smem, h->stream>>>(a);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (occ < 1) occ = 1;
+    const uint64_t need = std::max<uint64_t>(1, (nvec + (uint64_t)threads * U - 1) / ((uint64_t)threads * U));
+    const int grid = (int)std::min<uint64_t>(need, (uint64_t)h->num_sms * occ);
+    kern<<<grid, threads, smem, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;
 }
 
-template <typename R, int V>
+template <typename R, int V, bool Q0>
 int launch_expand_m(qcm_handle h, int M, const ExpandArgs &a, size_t smem) {
     switch (M) {
-        case 1: return launch_expand_t<R, V, 1, 4>(h, a, smem);
-        case 2: return launch_expand_t<R, V, 2, 4>(h, a, smem);
-        case 3: return launch_expand_t<R, V, 3, 2>(h, a, smem);
-        case 4: return launch_expand_t<R, V, 4, 2>(h, a, smem);
-        case 5: return launch_expand_t<R, V, 5, 2>(h, a, smem);
+        case 1: return launch_expand_t<R, V, 1, 4, Q0>(h, a, smem);
+        case 2: return launch_expand_t<R, V, 2, 4, Q0>(h, a, smem);
+        case 3: return launch_expand_t<R, V, 3, 2, Q0>(h, a, smem);
+        case 4: return launch_expand_t<R, V, 4, 2, Q0>(h, a, smem);
+        case 5: return launch_expand_t<R, V, 5, 2, Q0>(h, a, smem);
     }
     return fail(h, QCM_ERR_INVALID, "expansion of %d qubits out of range", M);
 }
@@ -226,21 +241,24 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     bool expand = (n_out - n_in == M) && tq[0] == n_in;
     for (int j = 0; j < M && expand; ++j) expand = per_target[j] == 1;
     if (expand) {
+        // union of the members' index qubits, ascending: the qubits that differ between the lanes
+        // of a warp get the low cidx bits (conflict-free shared loads), qubit 0 gets bit 0
         int8_t cu[QCM_MAX_MEMBERS * QCM_MAX_CTRL];
         int nu = 0;
         ExpandTableArgs &t = bp.targs;
+        for (int g = 0; g < n_mem; ++g)
+            for (int j = 0; j < a.mem[g].n_ctrl; ++j) {
+                const int8_t c = a.mem[g].ctrl[j];
+                if (std::find(cu, cu + nu, c) == cu + nu) cu[nu++] = c;
+            }
+        std::sort(cu, cu + nu);
+        if (nu + M > kExpandMaxBits) expand = false;
         for (int g = 0; g < n_mem && expand; ++g) {
             t.mpos[g] = a.mem[g].pos;
             t.mnc[g] = a.mem[g].n_ctrl;
             t.moff[g] = members[g].table_off;
-            for (int j = 0; j < a.mem[g].n_ctrl; ++j) {
-                const int8_t c = a.mem[g].ctrl[j];
-                int k = 0;
-                while (k < nu && cu[k] != c) ++k;
-                if (k == nu) cu[nu++] = c;
-                t.mbit[g][j] = (int8_t)k;
-            }
-            if (nu + M > kExpandMaxBits) expand = false;
+            for (int j = 0; j < a.mem[g].n_ctrl; ++j)
+                t.mbit[g][j] = (int8_t)(std::find(cu, cu + nu, a.mem[g].ctrl[j]) - cu);
         }
         if (expand) {
             t.M = M; t.nu = nu; t.n_members = n_mem; t.is_double = h->prec == QCM_C128;
@@ -249,6 +267,7 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
             e.n_in = n_in;
             e.nu = nu;
             for (int k = 0; k < nu; ++k) e.cu[k] = cu[k];
+            e.cu_below_32 = (nu == 0 || cu[nu - 1] < 32) ? 1 : 0;
             e.rank_bits = rank_bits(h);
         }
     }
@@ -272,8 +291,13 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
         h->timing.kernel_launches++;
         bp.eargs.ctab = h->ctab.p;
         const size_t smem = nent * centry;
-        if (h->prec == QCM_C64) rc = n_in >= 1 ? launch_expand_m<float, 2>(h, M, bp.eargs, smem) : launch_expand_m<float, 1>(h, M, bp.eargs, smem);
-        else rc = launch_expand_m<double, 1>(h, M, bp.eargs, smem);
+        const bool q0 = bp.eargs.nu > 0 && bp.eargs.cu[0] == 0;
+        if (h->prec == QCM_C64) {
+            if (n_in >= 1) rc = q0 ? launch_expand_m<float, 2, true>(h, M, bp.eargs, smem) : launch_expand_m<float, 2, false>(h, M, bp.eargs, smem);
+            else rc = launch_expand_m<float, 1, false>(h, M, bp.eargs, smem);
+        } else {
+            rc = launch_expand_m<double, 1, false>(h, M, bp.eargs, smem);
+        }
         if (rc) return rc;
         h->n_expand++;
     } else {

@@ -127,7 +127,7 @@ __device__ __forceinline__ void load_m8(const R *p, R (&m)[8]) {
 
 // LAZY = false: every block qubit is materialised on input (n_in == n_out): no zero tracking.
 template <typename R, int V, int M, int U, bool LAZY>
-__global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
+__global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ BlockArgs a) {
     constexpr int NR = 1 << M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tab = reinterpret_cast<R *>(smem_raw);
@@ -249,12 +249,14 @@ __global__ void __launch_bounds__(kThreads) k_block(const BlockArgs a) {
 // ctab[a][cidx]; the pass stages ctab in shared memory, reads each input amplitude
 // once and writes its 2^M images: read 2^n_in, write 2^(n_in+M), nothing else.
 // ----------------------------------------------------------------------------------
+constexpr int kExpandThreadsMax = 1024;
 constexpr int kExpandMaxBits = 12;          // nu + M: 4096 entries (32 KB c64, 64 KB c128)
 
 struct ExpandArgs {
     void *state;
     const void *ctab;               // device, [2^M][2^nu] complex in the state's real type
     int32_t n_in, nu;
+    int32_t cu_below_32;            // every index qubit is below 32: 32-bit index arithmetic
     int8_t cu[kExpandMaxBits];      // union of index qubits: cidx bit j <-> qubit cu[j]
     uint64_t rank_bits;
 };
@@ -269,7 +271,7 @@ struct ExpandTableArgs {
     int64_t moff[QCM_MAX_MEMBERS];
 };
 
-static __global__ void k_expand_table(const ExpandTableArgs a) {
+static __global__ void k_expand_table(const __grid_constant__ ExpandTableArgs a) {
     const uint32_t n = 1u << (a.M + a.nu);
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
@@ -295,8 +297,10 @@ static __global__ void k_expand_table(const ExpandTableArgs a) {
     else reinterpret_cast<float2 *>(a.ctab)[e] = make_float2((float)re, (float)im);
 }
 
-template <typename R, int V, int M, int U>
-__global__ void __launch_bounds__(kThreads) k_expand(const ExpandArgs a) {
+// Q0: qubit 0 is an index qubit; the host puts it at cidx bit 0, so the coefficients of the two
+// amplitudes of a 128-bit vector are adjacent table entries (one 128-bit shared load for c64).
+template <typename R, int V, int M, int U, bool Q0>
+__global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_constant__ ExpandArgs a) {
     constexpr int NR = 1 << M;
     using IO = VecIO<R, V>;
     using C2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
@@ -308,9 +312,6 @@ __global__ void __launch_bounds__(kThreads) k_expand(const ExpandArgs a) {
     }
     __syncthreads();
     const int nu = a.nu;
-    uint32_t low_bit = 0;                      // cidx bit fed by qubit 0 (differs between the V amplitudes)
-    for (int j = 0; j < nu; ++j)
-        if (a.cu[j] == 0) low_bit |= 1u << j;
     const uint64_t nvec = (1ull << a.n_in) / V;
     const uint64_t ostride = 1ull << a.n_in;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
@@ -328,18 +329,29 @@ __global__ void __launch_bounds__(kThreads) k_expand(const ExpandArgs a) {
             if (!ok[u]) continue;
             const uint64_t b = (bv0 + (uint64_t)u * blockDim.x) * V;
             const uint64_t gi = b | a.rank_bits;
-            uint32_t cidx = 0;
-            for (int j = 0; j < nu; ++j) cidx |= (uint32_t)((gi >> a.cu[j]) & 1ull) << j;
-            const C2 *t0 = tab + cidx;
-            const C2 *t1 = tab + (cidx | low_bit);
+ uint32_t cidx = 0;
+            if (a.cu_below_32) {
+                const uint32_t lo = (uint32_t)gi;
+                for (int j = 0; j < nu; ++j) cidx |= ((lo >> a.cu[j]) & 1u) << j;
+            } else {
+                for (int j = 0; j < nu; ++j) cidx |= (uint32_t)((gi >> a.cu[j]) & 1ull) << j;
+            }
+            const C2 *t0 = tab + cidx;          // V == 2: b is even, so cidx bit 0 is clear when Q0
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
                 R orr[V], oi[V];
-                const C2 c0 = t0[r << nu];
+                C2 c0, c1;
+                if constexpr (V == 2 && Q0 && sizeof(R) == 4) {
+                    const float4 cc = *reinterpret_cast<const float4 *>(t0 + (r << nu));
+                    c0 = make_float2(cc.x, cc.y);
+                    c1 = make_float2(cc.z, cc.w);
+                } else {
+                    c0 = t0[r << nu];
+                    c1 = c0;
+                }
                 orr[0] = c0.x * xr[u][0] - c0.y * xi[u][0];
                 oi[0] = c0.x * xi[u][0] + c0.y * xr[u][0];
                 if constexpr (V == 2) {
-                    const C2 c1 = t1[r << nu];
                     orr[1] = c1.x * xr[u][1] - c1.y * xi[u][1];
                     oi[1] = c1.x * xi[u][1] + c1.y * xr[u][1];
                 }
@@ -362,7 +374,7 @@ struct DiagArgs {
 };
 
 template <typename R, int V, int U>
-__global__ void __launch_bounds__(kThreads) k_diag(const DiagArgs a) {
+__global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tab = reinterpret_cast<R *>(smem_raw);
     {
@@ -584,16 +596,15 @@ __host__ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_
     return (double)(bits & ((1ull << 53) - 1ull)) * (1.0 / 9007199254740992.0);
 }
 
-// Warp-cooperative search inside one node: children [0, cnt) with masses w(i);
-// returns the first child whose inclusive prefix exceeds u (clamped to the last
-// child with non-zero mass) and subtracts the exclusive prefix from u.
-// Lane l owns children [32l, 32l+32).  Fixed evaluation order => deterministic.
+// Warp-cooperative search inside one node: children [0, cnt) with masses w(i).  Lane l
+// owns children l, l+32, l+64, ... (so that a warp's loads are coalesced); the node's
+// mass is laid out lane-major: lane 0's children in ascending order, then lane 1's, ...
+// Returns the child whose interval contains u (clamped to a child with non-zero mass)
+// and subtracts the mass laid out before it from u.  Fixed evaluation order => deterministic.
 template <typename F>
 __device__ __forceinline__ uint32_t warp_pick(F w, uint32_t cnt, double &u, int lane) {
-    const uint32_t b = (uint32_t)lane * 32u;
     double mine = 0.0;
-    for (uint32_t i = 0; i < 32u; ++i)
-        if (b + i < cnt) mine += w(b + i);
+    for (uint32_t i = lane; i < cnt; i += 32u) mine += w(i);
     double incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -612,18 +623,16 @@ __device__ __forceinline__ uint32_t warp_pick(F w, uint32_t cnt, double &u, int 
     double before = 0.0;
     if (lane == sel) {
         double acc = 0.0;
-        uint32_t last_nz = b;
+        uint32_t last_nz = (uint32_t)lane < cnt ? (uint32_t)lane : 0u;
         double last_before = 0.0;
-        bool found = false;
-        for (uint32_t i = 0; i < 32u && b + i < cnt; ++i) {
-            const double wi = w(b + i);
+        for (uint32_t i = lane; i < cnt; i += 32u) {
+            const double wi = w(i);
             if (wi > 0.0) {
-                last_nz = b + i; last_before = acc;
-                if (acc + wi > rem) { found = true; break; }
+                last_nz = i; last_before = acc;
+                if (acc + wi > rem) break;
             }
             acc += wi;
         }
-        (void)found;
         child = last_nz; before = last_before;
     }
     child = __shfl_sync(0xffffffffu, child, sel);
@@ -653,7 +662,7 @@ struct SampleArgs {
 };
 
 template <typename R>
-__global__ void __launch_bounds__(kThreads) k_sample(const SampleArgs a) {
+__global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ SampleArgs a) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
