@@ -255,9 +255,9 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     last_timing = sim.last_timing() if hasattr(sim, 'last_timing') else None
     dense = None
-    if world == 1 and not args.no_dense:
+    if not args.no_dense:
         sim.close()
-        dense = dense_gate_pass(args, cliques, local_rank)
+        dense = dense_gate_pass(args, cliques, local_rank, world)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -294,16 +294,23 @@ def main():
     sim.close()
 
 
-def dense_gate_pass(args, cliques, device):
+def dense_gate_pass(args, cliques, device, world=1):
     """The plain in-place gate pass (one fused clique = one read+write sweep of the whole,
-    fully materialised state; Aer-like width incl. the scratch qubit when it fits): the
-    kernel BASELINE.json's 70%-of-roofline target is about.  Not the product's default
-    schedule -- the lazily materialised one above moves ~30x fewer bytes per circuit."""
+    fully materialised state): the kernel BASELINE.json's 70%-of-roofline target is about.
+    Not the product's default schedule -- the lazily materialised one above moves ~30x fewer
+    bytes per circuit.  Sharded (world > 1): canonical layout, the last log2(world) clique
+    ancillas are global and come on-GPU through ONE qubit-swap all-to-all (NCCL send/recv
+    over NVLink), which is timed here."""
     from qcmrf_b200 import QCMRF, B200Simulator, workloads
     peak, _ = load_peaks()
-    sim = B200Simulator(precision='single', fusion='clique', device=device, seed=1, small_batch=False)
-    cliques, _ = workloads.named('q33')              # 33 physical qubits = 64 GiB, identity layout
+    cliques, _ = workloads.named('q33')              # 33 physical qubits = 64 GiB in total, identity layout
     circ = QCMRF(cliques, workloads.theta_for(cliques))
+    if world == 1:
+        sim = B200Simulator(precision='single', fusion='clique', device=device, seed=1, small_batch=False)
+    else:
+        from qcmrf_b200.sharded import ShardedSimulator
+        sim = ShardedSimulator(precision='single', fusion='clique', layout='canonical', device=device, seed=1,
+                               staging_bytes=2 << 30)
     prep = sim.prepare(circ)
     sim.execute(prep, 0, want_probs=False)
     sim.execute(prep, 0, want_probs=False)
@@ -311,9 +318,14 @@ def dense_gate_pass(args, cliques, device):
     passes = [r for r in prof if r[0] == 2 and r[2] == r[3] and r[2] > 0]
     ms = float(np.median([r[1] for r in passes]))
     by = passes[0][2] + passes[0][3]
-    out = {'workload': 'q33 (n=16, k=16), fusion=clique: one in-place pass per clique', 'n_phys': prep.plan.n_phys, 'passes': len(passes), 'bytes_per_pass': by, 'median_ms': ms,
-           'gbs': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak,
-           'amp_updates_per_sec': (by / 16) / (ms * 1e-3), 'circuit_ms': sum(r[1] for r in prof)}
+    out = {'workload': 'q33 (n=16, k=16), fusion=clique: one in-place pass per clique', 'n_phys': prep.plan.n_phys,
+           'ranks': world, 'passes': len(passes), 'bytes_per_pass_per_gpu': by, 'median_ms': ms,
+           'gbs_per_gpu': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak,
+           'amp_updates_per_sec_all_gpus': world * (by / 16) / (ms * 1e-3), 'circuit_ms': sum(r[1] for r in prof)}
+    ex = [r for r in prof if r[0] == -1]
+    if ex:
+        out['exchange'] = [{'ms': r[1], 'bytes_sent_per_gpu': r[2], 'gbs_per_direction_per_gpu': r[2] / r[1] / 1e6}
+                           for r in ex]
     sim.close()
     return out
 

@@ -699,7 +699,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 // can be built on the 2^M-times smaller input instead of re-reading the result.
                 const bool last = (i + (op.kind == QCM_OP_BLOCK ? n_mem : 0)) == n_ops - 1;
                 bool checkpoint = last && (op.flags & QCM_FLAG_SAMPLE_CHECKPOINT) && bp.norm_preserving &&
-                                  h->n_global == 0 && op.n_active_in >= kChunkBits;
+                                  op.n_active_in >= kChunkBits;
                 if (checkpoint) {
                     if ((rc = build_tree(h))) return rc;
                     h->timing.bytes_read += amp_bytes(h->prec) << op.n_active_in;     // the tree's level-0 read

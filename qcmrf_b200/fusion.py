@@ -323,6 +323,11 @@ class Plan:
     bytes_algorithmic: int = 0          # per amplitude byte: filled by the backend
     final_active: int = 0
     global_phase: float = 0.0
+    #: sharded layouts only: the n_global highest physical positions hold product-state qubits that
+    #: are never targeted again (pure controls); position -> their 2-vector.  Ops cover positions
+    #: below n_phys - n_global only.
+    n_global: int = 0
+    global_init: Dict[int, np.ndarray] = field(default_factory=dict)
 
 
 OP_DTYPE = np.dtype([('kind', '<i4'), ('target', '<i4'), ('n_ctrl', '<i4'), ('n_active_in', '<i4'),
@@ -390,8 +395,15 @@ def _flag_last_pass(ops):
         ops[last]['flags'] = QCM_FLAG_SAMPLE_CHECKPOINT
 
 
+def control_only_qubits(fc: FusedCircuit) -> List[int]:
+    """Product-state qubits that no later sweep targets: they only ever select table entries, so a
+    state can be split on them across GPUs with no communication at all."""
+    targeted = {op.target for op in fc.ops if op.kind == 'mux'}
+    return [q for q in sorted(fc.init) if q not in targeted]
+
+
 def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optional[bool] = None,
-         keep_order: bool = False) -> Plan:
+         keep_order: bool = False, n_global: int = 0) -> Plan:
     """Lay the fused circuit out for the engine.
 
     lazy=False  : identity layout, every qubit materialised up front, one pass per
@@ -399,6 +411,9 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
     lazy=True   : first-use layout, lazy materialisation, BLOCK passes of up to
                   ``block_max`` targets; never-materialised qubits are not stored
                   unless elide=False.
+    n_global=g  : (lazy only) the g highest-numbered control-only qubits are laid out on the g
+                  highest physical positions, to be held by the rank index of a 2^g-way
+                  sharded state; raises ValueError if the circuit has fewer than g of them.
     """
     N = fc.n_qubits
     em = _Emitter()
@@ -416,6 +431,13 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
                     seen.add(q)
                     order.append(q)
         rest = [q for q in range(N) if q not in seen]
+        gq: List[int] = []
+        if n_global:
+            cand = control_only_qubits(fc)
+            if len(cand) < n_global:
+                raise ValueError('circuit has %d control-only qubits, %d needed' % (len(cand), n_global))
+            gq = cand[-n_global:]
+            order = [q for q in order if q not in gq] + gq
         layout = [0] * N
         for p, q in enumerate(order):
             layout[q] = p
@@ -424,10 +446,16 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
         if not elide:
             order = order + rest
     n_phys = len(order)
+    if n_global and (not lazy or not elide):
+        raise ValueError('n_global needs the lazy, eliding layout')
+    global_init = {}
+    if n_global:
+        for q in gq:
+            global_init[layout[q]] = fc.init[q]
 
     # ---- INIT_PRODUCT ------------------------------------------------------------------
     if lazy:
-        n_init = len(fc.init)
+        n_init = len(fc.init) - n_global
         if not elide and not fc.ops:
             n_init = n_phys
     else:
@@ -503,4 +531,5 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
     ops, tabs = em.finish()
     # shots follow the program: let the engine build the sampler's tree before a final expansion pass
     _flag_last_pass(ops)
-    return Plan(N, n_phys, layout, ops, tabs, n_passes, len(fc.ops) + 1, 0, active, fc.global_phase)
+    return Plan(N, n_phys, layout, ops, tabs, n_passes, len(fc.ops) + 1, 0, active, fc.global_phase,
+                n_global, global_init)

@@ -1,0 +1,605 @@
+"""State sharded over 2^g GPUs of one box: one process per GPU, torch.distributed for the
+plumbing (NCCL over NVLink; gloo in the CPU tests).
+
+Rank r holds the 2^n_local amplitudes whose g highest physical qubits spell r.  The
+engine already reads index bits of global qubits from the rank (qcm_set_shard), so
+controls and diagonal terms on global qubits cost nothing.  What needs care is a
+gate whose *target* is global:
+
+* a global qubit that is materialised by the op itself (known |0> on input, one
+  member) needs no data from other ranks: rank r keeps the branch its own bit
+  selects, i.e. the member degenerates to a diagonal factor table[idx][bit][0] that
+  rides in the same sweep.  With the lazily materialised schedule every global qubit
+  of a QCMRF circuit is of this kind (the last ancillas), so the whole gate program
+  is communication-free; until the first global qubit materialises all ranks hold
+  identical replicas of the small state.
+* a global qubit that is already materialised must be brought on-GPU first: a
+  qubit-swap all-to-all exchanges s global qubits with the s highest local qubits
+  (contiguous slabs: rank with coordinate c sends slab j to the rank with coordinate
+  j and stores what it receives as slab j).  The dense (fully materialised, one
+  in-place pass per clique) schedule of SURVEY.md 8e needs exactly one such exchange
+  for a QCMRF circuit; lookahead gathers every global qubit that is still going to
+  be targeted into one exchange.
+
+``shard_plan`` is pure (plan in, per-rank segments out) so its index arithmetic is
+tested on the CPU for 2, 4 and 8 virtual ranks; ``ShardedSimulator`` executes the
+segments on a real handle and does the collectives.
+"""
+import os
+import time
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import _native, fusion, ir
+from .fusion import (OP_DTYPE, QCM_MAX_CTRL, QCM_OP_BLOCK, QCM_OP_DIAG, QCM_OP_EXTEND, QCM_OP_INIT_PRODUCT,
+                     QCM_OP_MUX1Q, QCM_OP_SWAP, _Emitter)
+
+__all__ = ['shard_plan', 'ShardedPlan', 'ShardedSimulator']
+
+
+@dataclass
+class ShardedPlan:
+    g: int
+    rank: int
+    n_local: int
+    n_phys: int
+    #: ('run', ops, tables, rank_mask) | ('exchange', betas) -- betas: rank-bit indices, ascending
+    segments: List[tuple] = field(default_factory=list)
+    pos: List[int] = field(default_factory=list)      # plan-physical qubit -> final position
+    mat_mask: int = 0                                  # rank bits whose global qubit is materialised at the end
+    n_exchanges: int = 0
+    exchange_amps: int = 0                             # amplitudes this rank sends in total
+
+
+def _headers(ops):
+    """Yield (index, header op, member ops) over a flat qcm_op array."""
+    i = 0
+    while i < len(ops):
+        op = ops[i]
+        if int(op['kind']) == QCM_OP_BLOCK:
+            n = int(op['n_ctrl'])
+            yield i, op, [ops[i + 1 + k] for k in range(n)]
+            i += 1 + n
+        else:
+            yield i, op, ([op] if int(op['kind']) == QCM_OP_MUX1Q else [])
+            i += 1
+
+
+def _targets(op, members):
+    k = int(op['kind'])
+    if k == QCM_OP_BLOCK:
+        return [int(x) for x in op['ctrl'][:int(op['target'])]]
+    if k == QCM_OP_MUX1Q:
+        return [int(op['target'])]
+    return []
+
+
+def shard_plan(pl: fusion.Plan, g: int, rank: int) -> ShardedPlan:
+    """Rewrite a single-device plan for rank ``rank`` of 2^g."""
+    n_phys = pl.n_phys
+    n_local = n_phys - g
+    if n_local < 1:
+        raise ValueError('state of %d qubits cannot be sharded over 2^%d ranks' % (n_phys, g))
+    sp = ShardedPlan(g, rank, n_local, n_phys)
+    if pl.n_global not in (0, g):
+        raise ValueError('plan was laid out for %d global qubits, not %d' % (pl.n_global, g))
+    if g == 0:
+        sp.segments.append(('run', pl.ops, pl.tables, 0))
+        sp.pos = list(range(n_phys))
+        return sp
+    tabs = pl.tables
+    pos = list(range(n_phys))              # plan-physical qubit -> current position
+    occ = list(range(n_phys))              # position -> plan-physical qubit
+    mat_mask = 0                           # rank bits of materialised global qubits
+    active = 0                             # plan-level n_active
+    em = _Emitter()
+    seg_mask = [0]
+
+    def flush():
+        if em.ops:
+            ops, tb = em.finish()
+            sp.segments.append(('run', ops, tb, seg_mask[0]))
+        em.ops, em.tabs, em.off = [], [], 0
+
+    def set_mask(m):
+        if m != seg_mask[0]:
+            flush()
+            seg_mask[0] = m
+
+    def rbit(position):
+        return (rank >> (position - n_local)) & 1
+
+    def lact(a):
+        return min(a, n_local)
+
+    headers = list(_headers(pl.ops))
+
+    def future_targets(from_h):
+        out = {}
+        for hi in range(from_h, len(headers)):
+            _, op, members = headers[hi]
+            for t in _targets(op, members):
+                out.setdefault(t, hi)
+        return out
+
+    def exchange_for(need, from_h):
+        """Bring the materialised global qubits ``need`` (plan-physical) on-GPU, together with every
+        other materialised global qubit that a later op targets, in one all-to-all."""
+        nonlocal mat_mask
+        fut = future_targets(from_h)
+        cur_targets = set(_targets(headers[from_h][1], headers[from_h][2]))
+        want = list(need)
+        for q, _hi in sorted(fut.items(), key=lambda kv: kv[1]):
+            p = pos[q]
+            if q not in want and p >= n_local and (mat_mask >> (p - n_local)) & 1:
+                want.append(q)
+        # partners: the highest local positions whose occupants are not targeted by the current op,
+        # preferring occupants that are never targeted again
+        cand = [p for p in range(lact(active) - 1, -1, -1) if occ[p] not in cur_targets]
+        done = [p for p in cand if occ[p] not in fut]
+        s = min(len(want), len(cand))
+        if s < len(need):
+            raise ValueError('not enough local qubits to exchange %d global targets' % len(need))
+        s = min(s, max(len(need), len(done)))
+        want = want[:s]
+        top = list(range(lact(active) - s, lact(active)))
+        chosen = (done + [p for p in cand if p not in done])[:s]
+        # make the chosen occupants sit on the top s local positions (local swaps, rarely needed)
+        for tp in top:
+            if tp in chosen:
+                continue
+            src = next(p for p in chosen if p not in top)
+            chosen[chosen.index(src)] = tp
+            em.op(QCM_OP_SWAP, target=src, ctrl=[tp], n_in=lact(active), n_out=lact(active))
+            qa, qb = occ[src], occ[tp]
+            occ[src], occ[tp] = qb, qa
+            pos[qa], pos[qb] = tp, src
+        flush()
+        gpos = sorted(pos[q] for q in want)
+        betas = [p - n_local for p in gpos]
+        sp.segments.append(('exchange', betas))
+        sp.n_exchanges += 1
+        sp.exchange_amps += ((1 << s) - 1) << (n_local - s)
+        for gp, lp in zip(gpos, top):                 # ascending global <-> ascending top-local
+            qa, qb = occ[gp], occ[lp]
+            occ[gp], occ[lp] = qb, qa
+            pos[qa], pos[qb] = lp, gp
+        # every exchanged position stays materialised (both sides were)
+
+    def force_materialise(position):
+        """Global qubit known |0> becomes an explicit sharded qubit: ranks whose bit is 1 hold zeros."""
+        nonlocal mat_mask
+        if rbit(position):
+            em.op(QCM_OP_DIAG, ctrl=[], n_in=lact(active), n_out=lact(active), table_off=em.table(np.zeros(2)))
+        mat_mask |= 1 << (position - n_local)
+
+    def member_table(mb):
+        nc = int(mb['n_ctrl'])
+        per = 2 if int(mb['kind']) == QCM_OP_DIAG else 8
+        o = int(mb['table_off'])
+        return tabs[o:o + (per << nc)]
+
+    for hi, (_, op, members) in enumerate(headers):
+        kind = int(op['kind'])
+        n_in, n_out = int(op['n_active_in']), int(op['n_active_out'])
+        if kind == QCM_OP_INIT_PRODUCT:
+            set_mask(mat_mask)
+            qv = tabs[int(op['table_off']):int(op['table_off']) + 4 * max(n_out, 1)].reshape(-1, 4).copy()
+            scale = 1.0 + 0j
+            if pl.n_global:
+                # control-only qubits on the global positions: this rank holds the branch its bits select
+                f = 1.0 + 0j
+                for p, v in pl.global_init.items():
+                    f *= complex(v[rbit(p)])
+                    mat_mask |= 1 << (p - n_local)
+                v0 = complex(qv[0, 0], qv[0, 1]) * f
+                v1 = complex(qv[0, 2], qv[0, 3]) * f
+                qv[0] = [v0.real, v0.imag, v1.real, v1.imag]
+                scale = f
+            elif n_out > n_local:
+                f = 1.0 + 0j
+                for p in range(n_local, n_out):
+                    b = rbit(p)
+                    f *= complex(qv[p, 2 * b], qv[p, 2 * b + 1])
+                    mat_mask |= 1 << (p - n_local)
+                v0 = complex(qv[0, 0], qv[0, 1]) * f
+                v1 = complex(qv[0, 2], qv[0, 3]) * f
+                qv = qv[:n_local].copy()
+                qv[0] = [v0.real, v0.imag, v1.real, v1.imag]
+            em.op(QCM_OP_INIT_PRODUCT, n_in=0, n_out=lact(n_out), table_off=em.table(qv))
+            if lact(n_out) == 0 and scale != 1.0:
+                # no local product qubit to carry the branch amplitude: scale the single amplitude
+                em.op(QCM_OP_DIAG, ctrl=[], n_in=0, n_out=0, table_off=em.table(np.array([scale.real, scale.imag])))
+            active = n_out
+            set_mask(mat_mask)
+            continue
+        if kind == QCM_OP_EXTEND:
+            set_mask(mat_mask)
+            if lact(n_out) > lact(n_in):
+                em.op(QCM_OP_EXTEND, n_in=lact(n_in), n_out=lact(n_out))
+            active = max(active, min(n_out, n_local))
+            for p in range(max(n_in, n_local), n_out):
+                force_materialise(p)
+            active = n_out
+            set_mask(mat_mask)
+            continue
+        if kind == QCM_OP_SWAP:
+            a, b = pos[int(op['target'])], pos[int(op['ctrl'][0])]
+            if a >= n_local or b >= n_local:
+                raise NotImplementedError('SWAP on a global qubit')
+            set_mask(mat_mask)
+            em.op(QCM_OP_SWAP, target=a, ctrl=[b], n_in=lact(active), n_out=lact(active))
+            continue
+        if kind == QCM_OP_DIAG:
+            set_mask(mat_mask)
+            ctrl = [pos[int(c)] for c in op['ctrl'][:int(op['n_ctrl'])]]
+            em.op(QCM_OP_DIAG, ctrl=ctrl, n_in=lact(active), n_out=lact(active), table_off=em.table(member_table(op)))
+            continue
+        # ---- MUX1Q / BLOCK ---------------------------------------------------------------
+        tq = _targets(op, members)
+        per_target = {t: 0 for t in tq}
+        for mb in members:
+            if int(mb['kind']) == QCM_OP_MUX1Q:
+                per_target[int(mb['target'])] += 1
+        set_mask(mat_mask)
+        new_global = [t for t in tq if t >= n_in and pos[t] >= n_local]
+        branch = {}                                       # target -> this rank's bit (diag rewrite)
+        for t in new_global:
+            if per_target[t] == 1:
+                branch[t] = rbit(pos[t])
+            else:
+                force_materialise(pos[t])
+        old_global = [t for t in tq if t not in branch and pos[t] >= n_local]
+        if old_global:
+            # new local qubits of this op are not materialised yet; exchange among materialised ones
+            exchange_for(old_global, hi)
+            set_mask(mat_mask)
+        local_t = sorted(pos[t] for t in tq if t not in branch)
+        l_in = lact(n_in)
+        l_out = max([l_in] + [p + 1 for p in local_t])
+        out_members = []
+        for mb in members:
+            nc = int(mb['n_ctrl'])
+            ctrl = [pos[int(c)] for c in mb['ctrl'][:nc]]
+            tab = member_table(mb)
+            if int(mb['kind']) == QCM_OP_DIAG:
+                out_members.append((QCM_OP_DIAG, 0, ctrl, tab))
+                continue
+            t = int(mb['target'])
+            if t in branch:
+                m = tab.reshape(-1, 8)
+                b = branch[t]
+                out_members.append((QCM_OP_DIAG, 0, ctrl, np.ascontiguousarray(m[:, 4 * b:4 * b + 2])))
+            else:
+                out_members.append((QCM_OP_MUX1Q, pos[t], ctrl, tab))
+        flags = int(op['flags'])
+        if not local_t:
+            # every target was a new global qubit: only diagonal factors remain -- merge them
+            for d in _merge_diags(out_members):
+                em.op(QCM_OP_DIAG, ctrl=d[0], n_in=l_in, n_out=l_in, table_off=em.table(d[1]))
+        elif len(out_members) == 1 and out_members[0][0] == QCM_OP_MUX1Q:
+            k, t, c, tab = out_members[0]
+            em.op(QCM_OP_MUX1Q, target=t, ctrl=c, n_in=l_in, n_out=l_out, table_off=em.table(tab))
+            em.ops[-1]['flags'] = flags
+        else:
+            em.op(QCM_OP_BLOCK, target=len(local_t), ctrl=local_t, n_in=l_in, n_out=l_out, n_ctrl=len(out_members))
+            em.ops[-1]['flags'] = flags
+            for k, t, c, tab in out_members:
+                em.op(k, target=t, ctrl=c, n_in=l_in, n_out=l_out, table_off=em.table(tab))
+        for t in branch:
+            mat_mask |= 1 << (pos[t] - n_local)
+        active = max(active, n_out)
+        set_mask(mat_mask)
+    flush()
+    sp.pos = pos
+    sp.mat_mask = mat_mask
+    return sp
+
+
+def _merge_diags(members):
+    """Product of diagonal members over the union of their index qubits (<= QCM_MAX_CTRL bits per
+    merged table).  Returns [(ctrl positions, table (2^m, 2) float64)]."""
+    out = []
+    cur_ctrl, cur_tab = [], np.ones(1, dtype=np.complex128)
+    for k, _t, ctrl, tab in members:
+        assert k == QCM_OP_DIAG
+        d = tab.reshape(-1, 2)
+        d = d[:, 0] + 1j * d[:, 1]
+        union = list(cur_ctrl) + [c for c in ctrl if c not in cur_ctrl]
+        if len(union) > QCM_MAX_CTRL:
+            out.append((cur_ctrl, cur_tab))
+            cur_ctrl, cur_tab, union = [], np.ones(1, dtype=np.complex128), list(ctrl)
+        idx = np.arange(1 << len(union))
+        a = np.zeros_like(idx)
+        for j, c in enumerate(cur_ctrl):
+            a |= ((idx >> union.index(c)) & 1) << j
+        b = np.zeros_like(idx)
+        for j, c in enumerate(ctrl):
+            b |= ((idx >> union.index(c)) & 1) << j
+        cur_tab = cur_tab[a] * d[b]
+        cur_ctrl = union
+    out.append((cur_ctrl, cur_tab))
+    return [(c, np.stack([t.real, t.imag], axis=1)) for c, t in out]
+
+
+# ------------------------------------------------------------------------------------------
+class _ShardPrepared:
+    __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions')
+
+
+class ShardedSimulator:
+    """One rank of a statevector sharded on its g highest physical qubits over the
+    2^g ranks of the default (or given) process group.  Same surface as B200Simulator for
+    what bench.py and the tests use: prepare / execute / run / exact / close."""
+
+    def __init__(self, precision='single', fusion='blocked', block_max=4, device=0, seed=None, group=None,
+                 staging_bytes=1 << 30, name='qasm_simulator', layout='auto'):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.g = self.world.bit_length() - 1
+        if 1 << self.g != self.world:
+            raise ValueError('world size %d is not a power of two' % self.world)
+        self.precision = precision
+        self.fusion = fusion
+        self.block_max = block_max
+        self.device = device
+        self.seed = seed
+        self.staging_bytes = int(staging_bytes)
+        if layout not in ('auto', 'canonical'):
+            raise ValueError("layout must be 'auto' or 'canonical'")
+        self.layout = layout      # auto: shard on control-only qubits when the circuit has them (no communication)
+        self._name = name
+        self._h = None
+        self._state = None
+        self._stage = None
+        self._n_local = None
+        self._profile = []
+        self._launches_closed = 0
+        self.exchange_ms = 0.0
+        self.exchange_bytes = 0
+
+    # ---- storage ---------------------------------------------------------------------------
+    def _tensor_device(self):
+        return self.torch.device('cuda', self.device)
+
+    def _alloc_state(self, n_local):
+        """(handle, flat real tensor of 2 * 2^n_local elements aliasing the state)."""
+        t = self.torch
+        rdt = t.float32 if self.precision in ('single', 'c64', 32) else t.float64
+        state = t.empty(2 << n_local, dtype=rdt, device=self._tensor_device())
+        h = _native.Handle(n_local, self.precision, self.device, ext_state_ptr=state.data_ptr())
+        return h, state
+
+    def _handle(self, n_local):
+        if self._h is not None and self._n_local == n_local:
+            return self._h
+        self.close()
+        self._h, self._state = self._alloc_state(n_local)
+        self._n_local = n_local
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            try:
+                self._launches_closed += self._h.timing()['kernel_launches']
+            except Exception:
+                pass
+            self._h.close()
+        self._h = self._state = self._stage = None
+        self._n_local = None
+
+    # ---- preparation -----------------------------------------------------------------------
+    def prepare(self, circuit, n_vars=None):
+        prog = ir.lower(circuit)
+        fc = fusion.fuse(prog, 'off' if self.fusion == 'off' else 'clique')
+        lazy = self.fusion == 'blocked'
+        ng = 0
+        if lazy and self.layout == 'auto' and len(fusion.control_only_qubits(fc)) >= self.g:
+            ng = self.g
+        pl = fusion.plan(fc, lazy=lazy, block_max=self.block_max, n_global=ng)
+        sp = shard_plan(pl, self.g, self.rank)
+        pr = _ShardPrepared()
+        pr.prog, pr.fc, pr.plan, pr.sp, pr.name = prog, fc, pl, sp, prog.name
+
+        def position(q):
+            p = pl.layout[q]
+            return sp.pos[p] if p < pl.n_phys else -1
+        pr.clbit_map = np.full(prog.n_clbits, -1, dtype=np.int32)
+        for c, q in prog.measures.items():
+            pr.clbit_map[c] = position(q)
+        if n_vars is None:
+            n_vars = prog.metadata.get('num_vertices')
+        pr.n_vars, pr.ps, pr.var_positions = n_vars, None, None
+        if n_vars is not None:
+            mask = 0
+            for q in range(n_vars, prog.n_qubits):
+                if position(q) >= 0:
+                    mask |= 1 << position(q)
+            pr.ps = (mask, 0, n_vars)
+            pr.var_positions = [position(q) for q in range(n_vars)]
+        return pr
+
+    # ---- execution -------------------------------------------------------------------------
+    def _exchange(self, betas):
+        """Qubit-swap all-to-all: global qubits (rank bits ``betas``) <-> the top len(betas) local qubits."""
+        t, dist = self.torch, self.dist
+        s = len(betas)
+        nl = self._n_local
+        slab = 1 << (nl - s)
+        st = self._state.view(1 << s, slab, 2)
+        c_me = sum(((self.rank >> b) & 1) << i for i, b in enumerate(betas))
+        base = self.rank
+        for b in betas:
+            base &= ~(1 << b)
+        peers = []
+        for j in range(1 << s):
+            if j != c_me:
+                pr = base
+                for i, b in enumerate(betas):
+                    pr |= ((j >> i) & 1) << b
+                peers.append((j, pr))
+        esz = self._state.element_size() * 2
+        chunk = max(1, min(slab, self.staging_bytes // (2 * len(peers) * esz)))
+        if self._stage is None or self._stage.shape[1] < len(peers) or self._stage.shape[2] < chunk:
+            self._stage = t.empty((2, len(peers), chunk, 2), dtype=self._state.dtype, device=self._state.device)
+        stage = self._stage
+        grank = (lambda r: r) if self.group is None else (lambda r: dist.get_global_rank(self.group, r))
+        pending = None
+        n_chunks = (slab + chunk - 1) // chunk
+        for ci in range(n_chunks + 1):
+            works = None
+            if ci < n_chunks:
+                off = ci * chunk
+                n = min(chunk, slab - off)
+                buf = stage[ci & 1]
+                ops = []
+                for k, (j, pr) in enumerate(peers):
+                    ops.append(dist.P2POp(dist.isend, st[j, off:off + n], grank(pr), group=self.group))
+                    ops.append(dist.P2POp(dist.irecv, buf[k, :n], grank(pr), group=self.group))
+                works = (dist.batch_isend_irecv(ops), off, n, ci & 1)
+            if pending is not None:
+                ws, poff, pn, pb = pending
+                for w in ws:
+                    w.wait()
+                for k, (j, pr) in enumerate(peers):
+                    st[j, poff:poff + pn].copy_(stage[pb, k, :pn])
+            pending = works
+        self.exchange_bytes += len(peers) * slab * esz
+
+    def _run_segments(self, sp):
+        h = self._handle(sp.n_local)
+        t = self.torch
+        self._profile = []
+        self.exchange_ms = 0.0
+        self.exchange_bytes = 0
+        for seg in sp.segments:
+            if seg[0] == 'run':
+                _, ops, tabs, mask = seg
+                h.set_shard(sp.g, sp.rank & mask)
+                h.run_program(ops, tabs)
+                self._profile.extend(h.op_profile())
+            else:
+                if self._state.is_cuda:
+                    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                    e0.record()
+                    self._exchange(seg[1])
+                    e1.record()
+                    e1.synchronize()
+                    ms = e0.elapsed_time(e1)
+                else:
+                    t0 = time.perf_counter()
+                    self._exchange(seg[1])
+                    ms = (time.perf_counter() - t0) * 1e3
+                self.exchange_ms += ms
+                sent = ((1 << len(seg[1])) - 1) * (1 << (sp.n_local - len(seg[1]))) * self._state.element_size() * 2
+                self._profile.append((-1, ms, sent, sent))
+        h.set_shard(sp.g, sp.rank & sp.mat_mask)
+        return h
+
+    def _is_replica(self, sp):
+        """This rank only mirrors another one (a global qubit that never materialised has bit 1 here)."""
+        return (sp.rank & ~sp.mat_mask) != 0
+
+    def _reduce(self, arr, op='sum'):
+        t, dist = self.torch, self.dist
+        dev = self._state.device
+        x = t.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
+        return x.cpu().numpy()
+
+    def execute(self, pr, shots, seed=0, stream=0, want_probs=True):
+        """Returns (keys or None, probs or None, kept or None); identical on every rank."""
+        sp = pr.sp
+        if not shots and any(seg[0] == 'run' and seg[1]['flags'].any() for seg in sp.segments):
+            pass                                    # checkpoint flags are ignored on sharded handles
+        h = self._run_segments(sp)
+        replica = self._is_replica(sp)
+        probs = kept = None
+        if want_probs and pr.ps is not None and pr.n_vars <= 30:
+            probs, kept = self._postselect(h, pr, replica)
+        keys = None
+        if shots:
+            mass = 0.0 if replica else h.sample_prepare()
+            m = np.zeros(self.world)
+            m[self.rank] = mass
+            masses = self._reduce(m)
+            # replicas mirror a rank that is sampling: they contribute nothing
+            if replica:
+                k = np.zeros(shots, dtype=np.int64)
+            else:
+                # masses are indexed by the rank the handle believes it is (bits of never-materialised
+                # qubits are 0 for every non-replica)
+                kk, mine = h.sample_sharded(shots, seed, stream, masses, pr.clbit_map if len(pr.clbit_map) else None)
+                k = np.where(mine, kk, 0).astype(np.int64)
+            keys = self._reduce(k).astype(np.uint64)
+        return keys, probs, kept
+
+    def _postselect(self, h, pr, replica):
+        """Exact post-selected pmf (index: variable q <-> bit q) and success probability, on every rank.
+        Variables on local positions 0..m-1 come from the engine's contiguous reduction; variables on
+        global positions select which slice of the pmf this rank owns."""
+        n, sp = pr.n_vars, pr.sp
+        vp = pr.var_positions
+        local_v = [q for q in range(n) if 0 <= vp[q] < sp.n_local]
+        glob_v = [q for q in range(n) if vp[q] >= sp.n_local]
+        m = len(local_v)
+        mask, value, _ = pr.ps
+        if [vp[q] for q in local_v] != list(range(m)) or any(vp[q] < 0 for q in range(n)):
+            raise NotImplementedError('post-selected vector needs the local variable qubits on positions 0..m-1')
+        out = np.zeros((1 << n) + 1)
+        if not replica:
+            p, k = h.postselect(mask, value, m)
+            idx = np.zeros(1 << m, dtype=np.int64)
+            loc = np.arange(1 << m, dtype=np.int64)
+            for j, q in enumerate(local_v):
+                idx |= ((loc >> j) & 1) << q
+            for q in glob_v:
+                idx |= ((sp.rank >> (vp[q] - sp.n_local)) & 1) << q
+            out[idx] = p
+            out[-1] = k
+        red = self._reduce(out)
+        return red[:-1], float(red[-1])
+
+    def run(self, circuits, shots=1024, seed=None, n_vars=None):
+        from .backend import Job, Result, _keys_to_counts
+        t0 = time.perf_counter()
+        single = not isinstance(circuits, (list, tuple))
+        circs = [circuits] if single else list(circuits)
+        if seed is None:
+            seed = self.seed if self.seed is not None else 0
+        entries = []
+        for i, c in enumerate(circs):
+            pr = self.prepare(c, n_vars=n_vars)
+            keys, probs, kept = self.execute(pr, int(shots), seed, i)
+            counts = _keys_to_counts(keys, pr.prog.n_clbits) if shots else None
+            h2d = sum(seg[1].nbytes + seg[2].nbytes for seg in pr.sp.segments if seg[0] == 'run')
+            d2h = (probs.nbytes + 8 if probs is not None else 0) + (keys.nbytes if keys is not None else 0)
+            entries.append({'circuit': c, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
+                            'meta': {'path': 'sharded', 'ranks': self.world, 'n_qubits': pr.prog.n_qubits,
+                                     'n_phys': pr.plan.n_phys, 'n_local': pr.sp.n_local, 'passes': pr.plan.n_passes,
+                                     'exchanges': pr.sp.n_exchanges, 'exchange_ms': self.exchange_ms,
+                                     'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': i}})
+        return Job(Result(entries, single, self._name, seed, int(shots), time.perf_counter() - t0))
+
+    def exact(self, circuit, n=None):
+        return self.run(circuit, shots=0, n_vars=n).result().postselected_probabilities(0)
+
+    # ---- introspection ---------------------------------------------------------------------
+    def op_profile(self):
+        return list(self._profile)
+
+    def kernel_launches(self):
+        live = self._h.timing()['kernel_launches'] if self._h is not None else 0
+        return self._launches_closed + live
+
+    def last_timing(self):
+        return self._h.timing() if self._h is not None else None
+
+    def local_amplitudes(self):
+        return self._h.get_amplitudes()

@@ -9,12 +9,16 @@ import numpy as np
 from qcmrf_b200 import fusion as F
 
 
-def run_plan(plan, n_global=0, rank=0, n_local=None):
+def run_plan(plan, n_global=0, rank=0, n_local=None, psi0=None, active0=0):
     """Execute plan.ops/plan.tables; returns the physical state (2^n_local complex128, implicit
-    zeros beyond the materialised part) and the final n_active."""
+    zeros beyond the materialised part) and the final n_active.  psi0/active0 continue from an
+    earlier call (segments of a sharded plan)."""
     nl = plan.n_phys if n_local is None else n_local
-    psi = np.full(1 << nl, np.nan + 0j, dtype=np.complex128)      # NaN = never written
-    active = 0
+    if psi0 is None:
+        psi = np.full(1 << nl, np.nan + 0j, dtype=np.complex128)      # NaN = never written
+    else:
+        psi = psi0.copy()
+    active = active0
     tabs = plan.tables
     ops = plan.ops
     rank_bits = rank << nl

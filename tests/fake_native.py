@@ -53,20 +53,54 @@ def run_batch_small(plans, clbit_maps, ps, shots, seed, precision='double', devi
 
 
 class Handle:
+    """numpy stand-in for _native.Handle.  With ``ext_state_ptr`` the state aliases caller memory
+    (a torch CPU tensor in the gloo tests), as the real handle aliases a torch CUDA tensor."""
+
     def __init__(self, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None):
+        import ctypes
         self.n_local = n_local
         self.cdtype = np.complex64 if precision in ('single', 'c64', 32) else np.complex128
-        self.state = np.zeros(1 << n_local, dtype=np.complex128)
+        self.ext = None
+        if ext_state_ptr:
+            rt = ctypes.c_float if self.cdtype == np.complex64 else ctypes.c_double
+            buf = (rt * (2 << n_local)).from_address(ext_state_ptr)
+            self.ext = np.ctypeslib.as_array(buf).view(self.cdtype)
+        self._own = np.zeros(1 << n_local, dtype=np.complex128)
         self.active = 0
+        self.n_global = 0
+        self.rank = 0
+        self._prof = []
+
+    @property
+    def state(self):
+        return self.ext.astype(np.complex128) if self.ext is not None else self._own
+
+    def _store(self, psi):
+        psi = np.where(np.isnan(psi), 0, psi)
+        if self.ext is not None:
+            self.ext[:] = psi.astype(self.cdtype)
+        else:
+            self._own = psi
+
+    def set_shard(self, n_global, rank):
+        self.n_global, self.rank = n_global, rank
 
     def run_program(self, ops, tables):
         pl = FakePlanHolder()
         pl.ops, pl.tables, pl.n_phys = ops, tables, self.n_local
-        self.state, self.active = em.run_plan(pl)
+        psi0 = self.state if self.active else None
+        psi, self.active = em.run_plan(pl, n_global=self.n_global, rank=self.rank, n_local=self.n_local,
+                                       psi0=psi0, active0=self.active if psi0 is not None else 0)
+        self._store(psi)
+        self._prof = [(int(o['kind']), 0.0, 0, 0) for o in ops]
+
+    def _global_index(self):
+        return np.arange(1 << self.n_local, dtype=np.int64) | (self.rank << self.n_local)
 
     def postselect(self, mask, value, n_out_bits, want_probs=True):
         w = np.abs(self.state) ** 2
-        idx = np.arange(len(w))
+        w[1 << self.active:] = 0
+        idx = self._global_index()
         sel = (idx & mask) == value
         out = np.zeros(1 << n_out_bits)
         np.add.at(out, idx[sel] & ((1 << n_out_bits) - 1), w[sel])
@@ -76,9 +110,46 @@ class Handle:
         rng = np.random.default_rng([seed & 0xffffffff, stream_id])
         return _keys_from_probs(np.abs(self.state) ** 2, shots, rng, clbit_qubit)
 
+    def sample_prepare(self):
+        w = np.abs(self.state) ** 2
+        w[1 << self.active:] = 0
+        return float(w.sum())
+
+    def sample_sharded(self, shots, seed, stream_id, rank_masses, clbit_qubit=None):
+        """Every rank draws the same uniforms; a shot belongs to the rank whose mass interval holds it."""
+        rng = np.random.default_rng([seed & 0xffffffff, stream_id])
+        u = rng.random(shots) * float(np.sum(rank_masses))
+        edges = np.concatenate([[0.0], np.cumsum(rank_masses)])
+        lo, hi = edges[self.rank], edges[self.rank + 1]
+        if self.rank == len(rank_masses) - 1:
+            hi = np.inf
+        mine = (u >= lo) & (u < hi)
+        w = np.abs(self.state) ** 2
+        w[1 << self.active:] = 0
+        cdf = np.cumsum(w)
+        loc = np.searchsorted(cdf, np.clip(u - lo, 0, cdf[-1] * (1 - 1e-15)), side='right')
+        loc = np.minimum(loc, len(w) - 1)
+        gi = loc.astype(np.int64) | (self.rank << self.n_local)
+        keys = np.zeros(shots, dtype=np.uint64)
+        if clbit_qubit is None or len(clbit_qubit) == 0:
+            keys = gi.astype(np.uint64)
+        else:
+            for c, q in enumerate(clbit_qubit):
+                if q >= 0:
+                    keys |= ((gi >> int(q)) & 1).astype(np.uint64) << np.uint64(c)
+        keys[~mine] = 0
+        return keys, mine
+
     def get_amplitudes(self, first=0, count=None):
-        count = len(self.state) - first if count is None else count
-        return self.state[first:first + count].astype(self.cdtype)
+        st = self.state
+        count = len(st) - first if count is None else count
+        return st[first:first + count].astype(self.cdtype)
+
+    def get_active(self):
+        return self.active
+
+    def op_profile(self):
+        return list(self._prof)
 
     def timing(self):
         return dict(program_ms=0.0, sample_ms=0.0, postselect_ms=0.0, kernel_launches=0, bytes_read=0,

@@ -1,0 +1,91 @@
+"""ShardedSimulator's host logic and collectives on 2 CPU ranks (gloo): the engine is replaced by
+the numpy emulator (tests/fake_native.py), the state lives in torch CPU tensors, and the
+qubit-swap exchange, pmf gather and shot merge run through torch.distributed for real."""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, HERE)
+        sys.path.insert(0, os.path.dirname(HERE))
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        import fake_native
+        from oracle import mrf, program, statevector as sv
+        from qcmrf_b200 import QCMRF, _native, sharded
+
+        _native.Handle = fake_native.Handle
+
+        class CpuSharded(sharded.ShardedSimulator):
+            def _tensor_device(self):
+                return torch.device('cpu')
+
+        rng = np.random.RandomState(7)
+        out = {}
+        for C in ([[0, 1], [1, 2], [2, 3]], [[0, 1, 2], [1, 3]]):
+            th = list(-np.abs(rng.randn(sum(2 ** len(c) for c in C))) * 0.6)
+            n, k, N, _ = program.sizes(C)
+            pb, db, _ = mrf.brute_force_pmf(C, th)
+            psi, meas = sv.run_program(program.qcmrf_program(C, th)[0], N)
+            kp = sv.key_probabilities(psi, N, meas)
+            for fus, layout, prec in (('blocked', 'auto', 'double'), ('blocked', 'canonical', 'double'),
+                                      ('clique', 'canonical', 'double'), ('clique', 'canonical', 'single')):
+                sim = CpuSharded(precision=prec, fusion=fus, layout=layout, block_max=2, seed=5,
+                                 staging_bytes=1 << 9)           # tiny staging: several chunks per exchange
+                res = sim.run(QCMRF(C, th), shots=20000).result()
+                p, delta = res.postselected_probabilities(0)
+                tol = 1e-10 if prec == 'double' else 1e-5
+                assert np.abs(p - pb).max() < tol and abs(delta - db) < tol, (fus, layout, np.abs(p - pb).max())
+                counts = res.get_counts()
+                assert sum(counts.values()) == 20000
+                obs = np.zeros(1 << N)
+                for key, v in counts.items():
+                    assert len(key) == N
+                    obs[int(key, 2)] = v
+                assert obs[kp < 1e-14].sum() == 0, (fus, layout)
+                assert 0.5 * np.abs(obs / 2e4 - kp).sum() < 0.06
+                meta = res.metadata(0)
+                assert meta['exchanges'] == (1 if fus == 'clique' else 0)
+                out[(tuple(map(tuple, C)), fus, layout, prec)] = (dict(counts), float(delta))
+                sim.close()
+        q.put((rank, 'ok', out))
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, 'fail', traceback.format_exc()))
+
+
+def test_two_rank_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in procs:
+        rank, status, payload = q.get(timeout=300)
+        assert status == 'ok', payload
+        results[rank] = payload
+    for p in procs:
+        p.join(timeout=60)
+    assert results[0] == results[1]                   # every rank returns the same counts and delta
