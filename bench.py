@@ -254,6 +254,7 @@ def main():
     e2e_ms_mean = float(e2e_t.cpu())
     clk = clocks.stop() if rank == 0 else None
     last_timing = sim.last_timing() if hasattr(sim, 'last_timing') else None
+    breakdown = getattr(sim, 'breakdown_ms', None)
     dense = None
     if not args.no_dense:
         sim.close()
@@ -283,7 +284,7 @@ def main():
                             'program_ms': prog_ms, 'program_gbs': total_bytes / max(prog_ms, 1e-9) / 1e6,
                             'wall_ms_per_step': wall_ms / args.steps},
                 'hbm_gbs_program': total_bytes / max(prog_ms, 1e-9) / 1e6,
-                'device_timing_last_step': last_timing, 'dense_gate_pass': dense,
+                'device_timing_last_step': last_timing, 'host_breakdown_ms': breakdown, 'dense_gate_pass': dense,
                 'check': {'delta': float(delta), 'p_sum': float(np.sum(p)), 'shots': int(sum(counts.values()))}}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_reference(cliques, steps=1, warmup=0)

@@ -583,8 +583,7 @@ int qcm_set_shard(qcm_handle h, int n_global_qubits, uint64_t rank) {
     if (n_global_qubits < 0 || h->n_local + n_global_qubits > 62) return fail(h, QCM_ERR_INVALID, "bad n_global_qubits %d", n_global_qubits);
     if (n_global_qubits < 64 && rank >> n_global_qubits) return fail(h, QCM_ERR_INVALID, "rank %llu does not fit %d global qubits", (unsigned long long)rank, n_global_qubits);
     h->n_global = n_global_qubits;
-    h->rank = rank;
-    h->tree_valid = false;
+    h->rank = rank;                 // the sum tree holds |amp|^2 of local amplitudes: unaffected
     return QCM_OK;
 }
 

@@ -326,7 +326,7 @@ def _merge_diags(members):
 
 # ------------------------------------------------------------------------------------------
 class _ShardPrepared:
-    __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions')
+    __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions', 'pmf_map')
 
 
 class ShardedSimulator:
@@ -363,6 +363,7 @@ class ShardedSimulator:
         self._launches_closed = 0
         self.exchange_ms = 0.0
         self.exchange_bytes = 0
+        self.breakdown_ms = {}
 
     # ---- storage ---------------------------------------------------------------------------
     def _tensor_device(self):
@@ -415,7 +416,7 @@ class ShardedSimulator:
             pr.clbit_map[c] = position(q)
         if n_vars is None:
             n_vars = prog.metadata.get('num_vertices')
-        pr.n_vars, pr.ps, pr.var_positions = n_vars, None, None
+        pr.n_vars, pr.ps, pr.var_positions, pr.pmf_map = n_vars, None, None, None
         if n_vars is not None:
             mask = 0
             for q in range(n_vars, prog.n_qubits):
@@ -518,11 +519,14 @@ class ShardedSimulator:
         sp = pr.sp
         if not shots and any(seg[0] == 'run' and seg[1]['flags'].any() for seg in sp.segments):
             pass                                    # checkpoint flags are ignored on sharded handles
+        t0 = time.perf_counter()
         h = self._run_segments(sp)
+        t1 = time.perf_counter()
         replica = self._is_replica(sp)
         probs = kept = None
         if want_probs and pr.ps is not None and pr.n_vars <= 30:
             probs, kept = self._postselect(h, pr, replica)
+        t2 = time.perf_counter()
         keys = None
         if shots:
             mass = 0.0 if replica else h.sample_prepare()
@@ -538,30 +542,45 @@ class ShardedSimulator:
                 kk, mine = h.sample_sharded(shots, seed, stream, masses, pr.clbit_map if len(pr.clbit_map) else None)
                 k = np.where(mine, kk, 0).astype(np.int64)
             keys = self._reduce(k).astype(np.uint64)
+        self.breakdown_ms = {'program': (t1 - t0) * 1e3, 'postselect': (t2 - t1) * 1e3,
+                             'sample': (time.perf_counter() - t2) * 1e3}
         return keys, probs, kept
 
-    def _postselect(self, h, pr, replica):
-        """Exact post-selected pmf (index: variable q <-> bit q) and success probability, on every rank.
-        Variables on local positions 0..m-1 come from the engine's contiguous reduction; variables on
-        global positions select which slice of the pmf this rank owns."""
+    def _pmf_map(self, pr):
+        """Where this rank's post-selected block lands in the 2^n pmf: (m, slice) when it is a
+        contiguous run (local variables are qubits 0..m-1, global ones the higher variables in
+        order -- the layouts the planner produces), else (m, index array)."""
         n, sp = pr.n_vars, pr.sp
         vp = pr.var_positions
         local_v = [q for q in range(n) if 0 <= vp[q] < sp.n_local]
         glob_v = [q for q in range(n) if vp[q] >= sp.n_local]
         m = len(local_v)
-        mask, value, _ = pr.ps
         if [vp[q] for q in local_v] != list(range(m)) or any(vp[q] < 0 for q in range(n)):
             raise NotImplementedError('post-selected vector needs the local variable qubits on positions 0..m-1')
+        off = 0
+        for q in glob_v:
+            off |= ((sp.rank >> (vp[q] - sp.n_local)) & 1) << q
+        if local_v == list(range(m)):
+            return m, slice(off, off + (1 << m))
+        loc = np.arange(1 << m, dtype=np.int64)
+        idx = np.full(1 << m, off, dtype=np.int64)
+        for j, q in enumerate(local_v):
+            idx |= ((loc >> j) & 1) << q
+        return m, idx
+
+    def _postselect(self, h, pr, replica):
+        """Exact post-selected pmf (index: variable q <-> bit q) and success probability, on every rank.
+        Variables on local positions 0..m-1 come from the engine's contiguous reduction; variables on
+        global positions select which part of the pmf this rank owns."""
+        n = pr.n_vars
+        if pr.pmf_map is None:
+            pr.pmf_map = self._pmf_map(pr)
+        m, where = pr.pmf_map
+        mask, value, _ = pr.ps
         out = np.zeros((1 << n) + 1)
         if not replica:
             p, k = h.postselect(mask, value, m)
-            idx = np.zeros(1 << m, dtype=np.int64)
-            loc = np.arange(1 << m, dtype=np.int64)
-            for j, q in enumerate(local_v):
-                idx |= ((loc >> j) & 1) << q
-            for q in glob_v:
-                idx |= ((sp.rank >> (vp[q] - sp.n_local)) & 1) << q
-            out[idx] = p
+            out[:-1][where] = p
             out[-1] = k
         red = self._reduce(out)
         return red[:-1], float(red[-1])
