@@ -1,11 +1,6 @@
 #!/bin/bash
-# bench, then launch list + one full capture of the dominant kernel with the same command line
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dense"
-$CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_expand -s 12 -c 4 -f -o gpurun_out/prof_expand $CMD > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log
-cat gpurun_out/bench.json | head -c 5000
+ncu --set full --clock-control none --import-source on -k regex:'^k_expand$' -s 15 -c 1 -f -o gpurun_out/prof_expand $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'^k_block$' -s 20 -c 1 -f -o gpurun_out/prof_block $CMD > gpurun_out/ncu_full2.log 2>&1
+tail -2 gpurun_out/ncu_full.log gpurun_out/ncu_full2.log
