@@ -33,6 +33,22 @@ SHOTS = 10000
 METRIC = 'QCMRF circuits/sec'
 
 
+def ncu_traffic(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture of this same workload (profiles/), or None."""
+    if workload != 'q34' or world != 1:
+        return None
+    try:
+        import csv
+        tot = 0.0
+        for row in csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_prof_expand.csv'))):
+            if row and row[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                tot += float(row[2].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[row[1]]
+        return tot or None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -166,6 +182,8 @@ def main():
     ap.add_argument('--block-max', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-dense', action='store_true', help='skip the dense in-place gate-pass measurement')
+    ap.add_argument('--dense-workload', default='q33')
+    ap.add_argument('--dense-only', action='store_true', help='tuning aid: only the dense schedule, prints its dict')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'b200':
         args.warmup = 3
@@ -196,6 +214,15 @@ def main():
     else:
         sim = B200Simulator(precision='single', fusion='blocked', block_max=args.block_max, device=local_rank,
                             seed=1984, small_batch=False)
+    if args.dense_only:
+        sim.close()
+        d = dense_gate_pass(args, cliques, local_rank, world)
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     thetas = [workloads.theta_for(cliques, seed=1984 + i) for i in range(args.warmup + args.steps + 2)]
 
     def barrier():
@@ -277,7 +304,8 @@ def main():
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms_mean},
                 'gpu_launches': int(launches),
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                             'traffic': None, 'peak_source': peak_src,
+                             'traffic': ncu_traffic(args.workload, world), 'peak_source': peak_src,
+                             'traffic_source': 'profiles/r01_ncu_prof_expand.csv (ncu --set full, same workload, 1 GPU)',
                              'kernel': 'k_block (op kind %d): reads %d B, writes %d B in %.3f ms' % (kind, rd, wr, top_ms)},
                 'program': {'passes': [{'kind': r[0], 'ms': r[1], 'read': r[2], 'written': r[3],
                                         'gbs': (r[2] + r[3]) / max(r[1], 1e-9) / 1e6} for r in prof],
@@ -304,7 +332,7 @@ def dense_gate_pass(args, cliques, device, world=1):
     over NVLink), which is timed here."""
     from qcmrf_b200 import QCMRF, B200Simulator, workloads
     peak, _ = load_peaks()
-    cliques, _ = workloads.named('q33')              # 33 physical qubits = 64 GiB in total, identity layout
+    cliques, _ = workloads.named(args.dense_workload)   # q33: 33 physical qubits = 64 GiB in total, identity layout
     circ = QCMRF(cliques, workloads.theta_for(cliques))
     if world == 1:
         sim = B200Simulator(precision='single', fusion='clique', device=device, seed=1, small_batch=False)
@@ -312,6 +340,7 @@ def dense_gate_pass(args, cliques, device, world=1):
         from qcmrf_b200.sharded import ShardedSimulator
         sim = ShardedSimulator(precision='single', fusion='clique', layout='canonical', device=device, seed=1,
                                staging_bytes=2 << 30)
+        sim.sync_before_exchange = True
     prep = sim.prepare(circ)
     sim.execute(prep, 0, want_probs=False)
     sim.execute(prep, 0, want_probs=False)
@@ -319,7 +348,7 @@ def dense_gate_pass(args, cliques, device, world=1):
     passes = [r for r in prof if r[0] == 2 and r[2] == r[3] and r[2] > 0]
     ms = float(np.median([r[1] for r in passes]))
     by = passes[0][2] + passes[0][3]
-    out = {'workload': 'q33 (n=16, k=16), fusion=clique: one in-place pass per clique', 'n_phys': prep.plan.n_phys,
+    out = {'workload': '%s, fusion=clique: one in-place pass per clique' % args.dense_workload, 'n_phys': prep.plan.n_phys,
            'ranks': world, 'passes': len(passes), 'bytes_per_pass_per_gpu': by, 'median_ms': ms,
            'gbs_per_gpu': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak,
            'amp_updates_per_sec_all_gpus': world * (by / 16) / (ms * 1e-3), 'circuit_ms': sum(r[1] for r in prof)}

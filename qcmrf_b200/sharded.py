@@ -364,6 +364,7 @@ class ShardedSimulator:
         self.exchange_ms = 0.0
         self.exchange_bytes = 0
         self.breakdown_ms = {}
+        self.sync_before_exchange = False
 
     # ---- storage ---------------------------------------------------------------------------
     def _tensor_device(self):
@@ -447,6 +448,8 @@ class ShardedSimulator:
                 peers.append((j, pr))
         esz = self._state.element_size() * 2
         chunk = max(1, min(slab, self.staging_bytes // (2 * len(peers) * esz)))
+        if chunk >= 1 << 16:
+            chunk &= ~((1 << 16) - 1)       # keep every send/recv buffer 512 KiB-aligned (NCCL's fast path)
         if self._stage is None or self._stage.shape[1] < len(peers) or self._stage.shape[2] < chunk:
             self._stage = t.empty((2, len(peers), chunk, 2), dtype=self._state.dtype, device=self._state.device)
         stage = self._stage
@@ -486,6 +489,8 @@ class ShardedSimulator:
                 h.run_program(ops, tabs)
                 self._profile.extend(h.op_profile())
             else:
+                if self.sync_before_exchange:
+                    self.dist.barrier(group=self.group)        # measurement aid: keep rank skew out of exchange_ms
                 if self._state.is_cuda:
                     e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
                     e0.record()
