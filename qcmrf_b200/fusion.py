@@ -88,31 +88,45 @@ class _Block:
             if q not in self.pos:
                 self.add_qubit(q)
         nq = len(self.qubits)
-        dim = 1 << nq
         B = g.base_matrix()
         U = self.U
-        ncol = U.shape[1]
-        p = self.pos[g.target]
-        if not g.controls:
-            Ur = U.reshape(1 << (nq - 1 - p), 2, (1 << p) * ncol)
-            a0 = Ur[:, 0, :].copy()
-            a1 = Ur[:, 1, :]
-            Ur[:, 0, :] = B[0, 0] * a0 + B[0, 1] * a1
-            Ur[:, 1, :] = B[1, 0] * a0 + B[1, 1] * a1
+        cmask = cval = 0
+        for q, v in zip(g.controls, g.ctrl_values):
+            cmask |= 1 << self.pos[q]
+            cval |= v << self.pos[q]
+        r0, r1 = _pair_rows(nq, cmask, cval, 1 << self.pos[g.target])
+        b00, b01, b10, b11 = B[0, 0], B[0, 1], B[1, 0], B[1, 1]
+        if b01 == 0 and b10 == 0:                       # diagonal: scale rows
+            if b00 != 1:
+                U[r0] *= b00
+            if b11 != 1:
+                U[r1] *= b11
+        elif b00 == 0 and b11 == 0 and b01 == 1 and b10 == 1:   # X-type: swap rows
+            a0 = U[r0]
+            U[r0] = U[r1]
+            U[r1] = a0
         else:
-            rows = np.arange(dim)
-            cmask = cval = 0
-            for q, v in zip(g.controls, g.ctrl_values):
-                cmask |= 1 << self.pos[q]
-                cval |= v << self.pos[q]
-            tb = 1 << p
-            r0 = rows[((rows & cmask) == cval) & ((rows & tb) == 0)]
-            r1 = r0 | tb
             a0 = U[r0]
             a1 = U[r1]
-            U[r0] = B[0, 0] * a0 + B[0, 1] * a1
-            U[r1] = B[1, 0] * a0 + B[1, 1] * a1
+            U[r0] = b00 * a0 + b01 * a1
+            U[r1] = b10 * a0 + b11 * a1
         self.n_gates += 1
+
+
+_PAIR_ROWS = {}
+
+
+def _pair_rows(nq, cmask, cval, tb):
+    """Row index pairs (target bit 0 / 1) of a 2^nq-row matrix selected by a control pattern."""
+    key = (nq, cmask, cval, tb)
+    hit = _PAIR_ROWS.get(key)
+    if hit is None:
+        rows = np.arange(1 << nq)
+        r0 = rows[((rows & cmask) == cval) & ((rows & tb) == 0)]
+        hit = (r0, r0 | tb)
+        if len(_PAIR_ROWS) < 4096:
+            _PAIR_ROWS[key] = hit
+    return hit
 
 
 def _spread(values, positions):
@@ -194,6 +208,77 @@ def _classify(blk: _Block, tol=TOL):
     return None
 
 
+_MATCH = {}
+
+
+def _match_patterns(m, pos, vals):
+    """Indices c in [0, 2^m) whose bits at ``pos`` equal ``vals``."""
+    key = (m, pos, vals)
+    hit = _MATCH.get(key)
+    if hit is None:
+        c = np.arange(1 << m)
+        sel = np.ones(1 << m, dtype=bool)
+        for p, v in zip(pos, vals):
+            sel &= ((c >> p) & 1) == v
+        hit = c[sel]
+        if len(_MATCH) < 4096:
+            _MATCH[key] = hit
+    return hit
+
+
+def _b4(g: Gate):
+    """Base 2x2 of a gate as four Python complex numbers (no numpy on the per-gate path)."""
+    B = g.base_matrix()
+    return complex(B[0, 0]), complex(B[0, 1]), complex(B[1, 0]), complex(B[1, 1])
+
+
+def _run_mux(run: List[Gate], zero_in: bool, tol=TOL):
+    """Consecutive gates with one common target: the product is a uniformly-controlled gate on that
+    target over the union of their controls.  Built entry by entry from 2x2 products (a gate with a
+    full control pattern touches ONE table entry).  None if the union exceeds QCM_MAX_CTRL."""
+    t = run[0].qubits[-1]
+    ctrls: List[int] = []
+    for g in run:
+        for q in g.qubits[:-1]:
+            if q not in ctrls:
+                ctrls.append(q)
+    m = len(ctrls)
+    if m > QCM_MAX_CTRL:
+        return None
+    cpos = {q: k for k, q in enumerate(ctrls)}
+    tab = [[1 + 0j, 0j, 0j, 1 + 0j] for _ in range(1 << m)]        # row-major 2x2 per control pattern
+    for g in run:
+        b00, b01, b10, b11 = _b4(g)
+        qs = g.qubits
+        if len(qs) - 1 == m:
+            k = 0
+            for q, v in zip(qs, g.ctrl_values):
+                k |= v << cpos[q]
+            idx = (k,)
+        else:
+            idx = _match_patterns(m, tuple(cpos[q] for q in qs[:-1]), tuple(g.ctrl_values))
+        for k in idx:
+            e = tab[k]
+            e[0], e[1], e[2], e[3] = (b00 * e[0] + b01 * e[2], b00 * e[1] + b01 * e[3],
+                                      b10 * e[0] + b11 * e[2], b10 * e[1] + b11 * e[3])
+    table = np.array(tab, dtype=np.complex128).reshape(1 << m, 2, 2)
+    if m:
+        tsel = np.arange(1 << m)
+        sub = table[:, :, :1] if zero_in else table         # a |0> input only ever sees column 0
+        dep = [j for j in range(m)
+               if np.abs(sub[((tsel >> j) & 1) == 0] - sub[((tsel >> j) & 1) == 1]).max() >= tol]
+        if len(dep) < m:
+            table = table[_spread(np.arange(1 << len(dep)), dep)]
+            ctrls = [ctrls[j] for j in dep]
+    if not zero_in and not ctrls and np.abs(table[0] - table[0][0, 0] * np.eye(2)).max() < tol:
+        return [], [], float(np.angle(table[0][0, 0]))     # identity up to a phase
+    if zero_in:                                            # same completion as _classify: unitary 2x2
+        table[:, 0, 1] = -np.conj(table[:, 1, 0])
+        table[:, 1, 1] = np.conj(table[:, 0, 0])
+    op = FusedOp('mux', t, tuple(ctrls), table, zero_in, len(run))
+    return [op], [t] + list(ctrls), 0.0
+
+
 def _single_gate_op(g: Gate, zero: set):
     blk = _Block(zero)
     blk.apply(g)
@@ -228,6 +313,67 @@ def direct_ops(prog: Program) -> 'FusedCircuit':
     return FusedCircuit(prog.n_qubits, {}, ops, prog.global_phase, len(prog.gates))
 
 
+def fold_clean_scratch(gates: List[Gate], n_qubits: int) -> List[Gate]:
+    """Compute / use / uncompute on a clean scratch qubit:
+
+        mcx(A == v -> s) ; G_1 .. G_m (s only as a closed control) ; mcx(A == v -> s),  s known |0>
+
+    equals G_1 .. G_m with the control on s replaced by controls A == v, and s is never
+    touched.  This is the AND . CP . AND of QCMRF.py:224-227 (one multi-controlled phase per
+    clique state); folding it first shrinks every clique block from |C|+2 to |C|+1 qubits and
+    a third of the gates before the matrix-based fusion sees it.  Anything else passes through."""
+    clean = set(range(n_qubits))
+    out: List[Gate] = []
+    i, n = 0, len(gates)
+    while i < n:
+        g = gates[i]
+        gq = g.qubits
+        s_q = gq[-1]
+        folded = False
+        if len(gq) > 1 and g.name in ('cx', 'mcx') and s_q in clean:
+            A = set(gq[:-1])
+            j = i + 1
+            while j < n:
+                hq = gates[j].qubits
+                ht = hq[-1]
+                if ht == s_q or ht in A:
+                    break
+                if s_q in hq and gates[j].ctrl_values[hq.index(s_q)] != 1:
+                    break
+                j += 1
+            if (j < n and j > i + 1 and gates[j].qubits == gq and gates[j].name in ('cx', 'mcx')
+                    and gates[j].ctrl_values == g.ctrl_values):
+                inner = gates[i + 1:j]
+                if all(A.isdisjoint(h.qubits) for h in inner):
+                    for h in inner:
+                        hq = h.qubits
+                        if s_q not in hq:
+                            out.append(h)
+                            clean.discard(hq[-1])
+                            continue
+                        k = hq.index(s_q)
+                        ctrls = hq[:k] + hq[k + 1:-1] + gq[:-1]
+                        vals = h.ctrl_values[:k] + h.ctrl_values[k + 1:] + g.ctrl_values
+                        out.append(Gate(ir_ctrl_base(h.name), ctrls + (hq[-1],), h.params, vals))
+                        clean.discard(hq[-1])
+                    i = j + 1
+                    folded = True
+        if not folded:
+            out.append(g)
+            clean.discard(s_q)
+            i += 1
+    return out
+
+
+_MC_NAME = {'cx': 'mcx', 'mcx': 'mcx', 'cp': 'mcp', 'mcp': 'mcp'}
+
+
+def ir_ctrl_base(name):
+    """Name of a controlled primitive once it has more controls ('cp' -> 'mcp', 'cx' -> 'mcx'; the
+    other controlled names already stand for any number of controls in this IR)."""
+    return _MC_NAME.get(name, name)
+
+
 def fuse(prog: Program, mode: str = 'clique', q_max: int = 8) -> FusedCircuit:
     """mode 'off': one sweep per primitive gate; 'clique': block fusion."""
     if mode == 'off':
@@ -235,12 +381,16 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8) -> FusedCircuit:
     zero = set(range(prog.n_qubits))
     ops: List[FusedOp] = []
     phase = prog.global_phase
-    gates: List[Gate] = prog.gates
+    gates: List[Gate] = fold_clean_scratch(prog.gates, prog.n_qubits)
     n = len(gates)
     last_use: Dict[int, int] = {}
+    first_use: Dict[int, int] = {}
+    last_target: Dict[int, int] = {}
     for gi, g in enumerate(gates):
         for q in g.qubits:
             last_use[q] = gi
+            first_use.setdefault(q, gi)
+        last_target[g.qubits[-1]] = gi
 
     def emit(res):
         nonlocal phase
@@ -267,12 +417,27 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8) -> FusedCircuit:
     i = 0
     while i < n:
         g0 = gates[i]
-        if not g0.controls and g0.target in zero and not lifetime_fits(g0.target, i):
+        if (len(g0.qubits) == 1 and g0.target in zero and
+                (last_target[g0.target] == i or not lifetime_fits(g0.target, i))):
             # a lone preparation gate on a qubit that lives too long to be the target of
             # one fused block (the H layer, QCMRF.py:204-205): emit now, it folds into INIT
-            emit(_single_gate_op(g0, zero))
+            B = g0.base_matrix()
+            emit(([FusedOp('mux', g0.target, (), np.array([B], dtype=np.complex128), True, 1)], [g0.target], 0.0))
             i += 1
             continue
+        # a qubit whose whole life is one run of consecutive gates targeting it (a clique ancilla
+        # after fold_clean_scratch): the run IS a multiplexer on it -- no dense block needed
+        t = g0.target
+        if first_use[t] == i:
+            j = i
+            while j < n and gates[j].target == t:
+                j += 1
+            if last_use[t] == j - 1:
+                res = _run_mux(gates[i:j], t in zero)
+                if res is not None:
+                    emit(res)
+                    i = j
+                    continue
         blk = _Block(zero)
         best = None
         j = i

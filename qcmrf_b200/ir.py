@@ -188,6 +188,11 @@ def lower(circuit) -> Program:
     """Flatten a circuit object into a Program."""
     if isinstance(circuit, Program):
         return circuit
+    fast = getattr(circuit, '_lower_program', None)
+    if fast is not None:
+        prog = fast()
+        if prog is not None:
+            return prog
     nq, nc = int(circuit.num_qubits), int(circuit.num_clbits)
     prog = Program(nq, nc, name=str(getattr(circuit, 'name', '') or ''))
     prog.global_phase = float(getattr(circuit, 'global_phase', 0.0) or 0.0)

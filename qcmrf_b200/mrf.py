@@ -55,7 +55,71 @@ class QCMRF(QuantumCircuit):
         self._mrf_gamma = None if gamma is None else [float(g) for g in gamma]
         width = self._mrf_n + len(cliques) + 1
         super().__init__(width, width, name=name)
-        self._emit_program()
+        if self._mrf_theta is None and self._mrf_gamma is None:
+            # the reference draws theta ~ U(-5, 0) from numpy's global state while building
+            self._mrf_theta = [float(np.random.uniform(low=-5.0, high=0)) for _ in range(self._mrf_dim)]
+        # The instruction list (nested cU_C / AND objects, what `.data`, `transpile` and a generic
+        # backend walk) is materialised on first access; the engine's own lowering takes the flat
+        # gate program of `_lower_program` -- the same gates, without building ~700 objects.
+        self.__dict__['_mrf_data'] = None
+
+    @property
+    def _qc_data(self):
+        d = self.__dict__.get('_mrf_data')
+        if d is None:
+            d = self.__dict__['_mrf_data'] = []
+            self._emit_program()
+        return d
+
+    @_qc_data.setter
+    def _qc_data(self, value):
+        self.__dict__['_mrf_data'] = value
+
+    def _lower_program(self):
+        """Flat primitive gate program of this circuit (ir.Program), or None once the instruction
+        list has been materialised (it may have been edited; the generic walk is used then).
+        Emits exactly what ir.lower finds in `.data` (tests/test_circuit_api.py pins the equality)."""
+        if self.__dict__.get('_mrf_data') is not None:
+            return None
+        from .ir import Gate, Program
+        n = self._mrf_n
+        width = self.num_qubits
+        prog = Program(width, width, name=str(self.name))
+        gates = prog.gates
+        for q in range(n):
+            gates.append(Gate('h', (q,)))
+        gam = self.gamma
+        offset = 0
+        for ii, C in enumerate(self._mrf_cliques):
+            anc = n + 1 + ii
+            m = len(C)
+            wires = tuple(n - 1 - v for v in C) + (n,)
+            fwd = []
+            for y, g in zip(itertools.product((0, 1), repeat=m), gam[offset:offset + 2 ** m]):
+                if abs(g) <= 1e-8:                              # np.isclose(g, 0)
+                    continue
+                mark = Gate('mcx', wires, (), tuple(y))
+                fwd.append((mark, 2.0 * g))
+            offset += 2 ** m
+            gates.append(Gate('h', (anc,)))
+            for mark, lam in fwd:
+                gates.append(mark)
+                gates.append(Gate('cp', (n, anc), (lam,), (1,)))
+                gates.append(mark)
+            gates.append(Gate('x', (anc,)))
+            for mark, lam in reversed(fwd):
+                gates.append(mark)
+                gates.append(Gate('cp', (n, anc), (-lam,), (1,)))
+                gates.append(mark)
+            gates.append(Gate('x', (anc,)))
+            gates.append(Gate('h', (anc,)))
+            if self._mrf_measure:
+                prog.measures[anc] = anc
+        if self._mrf_measure:
+            for q in range(n):
+                prog.measures[q] = q
+        prog.metadata['num_vertices'] = n
+        return prog
 
     # -- the reference's read-only surface (QCMRF.py:82-157) ------------------------------
     @property
@@ -108,7 +172,7 @@ class QCMRF(QuantumCircuit):
         block = QuantumCircuit(n + 2, name='cU_C%d' % index)
         wires = [n - 1 - v for v in clique] + [n]
         for y, g in zip(itertools.product((0, 1), repeat=len(clique)), angles):
-            if np.isclose(g, 0):
+            if abs(g) <= 1e-8:                                  # np.isclose(g, 0) (QCMRF.py:223)
                 continue
             marker = AND(len(clique), [2 * b - 1 for b in y])
             block.append(marker, wires)
@@ -122,9 +186,6 @@ class QCMRF(QuantumCircuit):
             self.h(q)
         if self._mrf_barriers:
             self.barrier()
-        if self._mrf_theta is None and self._mrf_gamma is None:
-            # the reference draws theta ~ U(-5, 0) from numpy's global state here
-            self._mrf_theta = [float(np.random.uniform(low=-5.0, high=0)) for _ in range(self._mrf_dim)]
         gam = self.gamma
         offset = 0
         main = list(range(n + 1))

@@ -169,3 +169,30 @@ def test_reference_scripts_run_unchanged(tmp_path, monkeypatch, models):
         succ = float(cells[3].split()[0])
         assert fid > 0.99
         assert abs(succ - d) < 0.01
+
+
+def test_direct_lowering_equals_walking_the_instruction_list(models):
+    """QCMRF materialises its nested instruction list lazily; the engine's direct lowering must be
+    the very program the generic walk finds in `.data`, and an edited circuit must fall back."""
+    from qcmrf_b200 import ir
+    rng = np.random.RandomState(0)
+    cases = [(C, models['0.5']['THETAS'][str(j)][0]) for j, C in enumerate(models['0.5']['GRAPHS'])]
+    cases.append(([[0, 1], [1, 2]], [0.0, -0.3, 0.0, -1.0, -0.2, 0.0, -0.5, -0.1]))      # skipped (gamma ~ 0) terms
+    for C, th in cases:
+        for kw in ({}, {'with_measurements': False}, {'beta': 0.5}):
+            fast = ir.lower(QCMRF(C, th, **kw))
+            slow_c = QCMRF(C, th, **kw)
+            assert slow_c.__dict__['_mrf_data'] is None
+            n_inst = len(slow_c.data)                                 # materialises
+            assert n_inst > 0 and slow_c._lower_program() is None
+            slow = ir.lower(slow_c)
+            assert fast.n_qubits == slow.n_qubits and fast.n_clbits == slow.n_clbits
+            assert fast.measures == slow.measures
+            assert len(fast.gates) == len(slow.gates)
+            for a, b in zip(fast.gates, slow.gates):
+                assert (a.name, a.qubits, a.ctrl_values) == (b.name, b.qubits, b.ctrl_values)
+                assert np.allclose(a.params, b.params, rtol=0, atol=0)
+    # gamma-only construction and an edited circuit
+    c = QCMRF([[0, 1]], gamma=[0.1, 0.2, 0.3, 0.4])
+    c.h(0)
+    assert ir.lower(c).gates[-1].name == 'h' and len(ir.lower(c).gates) == len(ir.lower(QCMRF([[0, 1]], gamma=[0.1, 0.2, 0.3, 0.4])).gates) + 1
