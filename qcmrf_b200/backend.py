@@ -44,13 +44,20 @@ class Counts(dict):
 
 
 class _Prepared:
-    __slots__ = ('prog', 'fc', 'plan', 'clbit_map', 'n_vars', 'ps', 'name')
+    __slots__ = ('prog', 'fc', 'plan', 'clbit_map', 'n_vars', 'ps', 'name', 'virtual', 'proj')
 
 
 def _keys_to_counts(keys, width):
-    vals, cnt = np.unique(keys, return_counts=True)
-    fmt = '0%db' % max(width, 1)
-    return Counts({format(int(v), fmt): int(c) for v, c in zip(vals, cnt)})
+    """uint64 keys -> Counts with Aer's key format (clbit width-1 leftmost).  The bit strings are cut
+    out of one unpacked byte buffer: no per-key formatting."""
+    width = max(int(width), 1)
+    vals, cnt = np.unique(np.asarray(keys, dtype=np.uint64), return_counts=True)
+    bits = np.unpackbits(vals.astype('>u8').view(np.uint8).reshape(-1, 8), axis=1)[:, 64 - width:] if width <= 64 else None
+    if bits is None:
+        fmt = '0%db' % width
+        return Counts({format(int(v), fmt): int(c) for v, c in zip(vals, cnt)})
+    text = (bits + np.uint8(48)).tobytes().decode('ascii')
+    return Counts({text[i * width:(i + 1) * width]: c for i, c in enumerate(cnt.tolist())})
 
 
 class Result:
@@ -136,9 +143,15 @@ class B200Simulator:
     the unseeded Aer run of the reference)."""
 
     def __init__(self, name='qasm_simulator', device=0, precision='double', fusion='blocked', block_max=4,
-                 seed=None, small_batch=True, small_fusion='off'):
+                 seed=None, small_batch=True, small_fusion='off', width='full'):
         if fusion not in _FUSION_MODES:
             raise ValueError('fusion must be one of %r' % (_FUSION_MODES,))
+        if width not in ('full', 'release'):
+            raise ValueError("width must be 'full' or 'release'")
+        # 'release': measure-and-release -- qubits materialised by one sweep and never used again (the
+        # clique ancillas) are not stored; their outcomes are drawn from the sweep's coefficients and
+        # the post-selected vector is obtained by projecting them on 0 (SURVEY.md App. E.2)
+        self.width = width
         self._name = name
         self.device = device
         self.precision = precision
@@ -163,23 +176,32 @@ class B200Simulator:
             setattr(self, k, v)
 
     # -- host-side preparation -------------------------------------------------------
-    def prepare(self, circuit, n_vars=None, fusion_mode=None, block_max=None, small=False, elide=None) -> _Prepared:
+    def prepare(self, circuit, n_vars=None, fusion_mode=None, block_max=None, small=False, elide=None,
+                width=None) -> _Prepared:
         mode = fusion_mode or (self.small_fusion if small else self.fusion)
+        width = width or self.width
         prog = ir.lower(circuit)
         if prog.n_clbits > 64:
             raise ValueError('at most 64 classical bits are supported')
-        fc = fusion.fuse(prog, 'off' if mode == 'off' else 'clique')
+        if n_vars is None:
+            n_vars = prog.metadata.get('num_vertices')
+        release = width == 'release' and not small
+        fc = fusion.fuse(prog, 'clique' if release or mode != 'off' else 'off')
+        virtual = []
+        if release:
+            fc, virtual = fusion.split_releasable(fc, keep_below=n_vars or 0)
         lazy = (mode == 'blocked') and not small
         pl = fusion.plan(fc, lazy=lazy, block_max=block_max or self.block_max, elide=elide)
         pr = _Prepared()
         pr.prog, pr.fc, pr.plan = prog, fc, pl
         pr.name = prog.name
+        pr.virtual, pr.proj = [], None
+        if virtual:
+            self._prepare_release(pr, virtual)
         pr.clbit_map = np.full(prog.n_clbits, -1, dtype=np.int32)
         for c, q in prog.measures.items():
             p = pl.layout[q]
             pr.clbit_map[c] = p if p < pl.n_phys else -1
-        if n_vars is None:
-            n_vars = prog.metadata.get('num_vertices')
         pr.n_vars = n_vars
         pr.ps = None
         if n_vars is not None:
@@ -191,6 +213,26 @@ class B200Simulator:
                     mask |= 1 << pl.layout[q]
             pr.ps = (mask, 0, n_vars)
         return pr
+
+    def _prepare_release(self, pr, virtual):
+        """Released sweeps: per sweep the physical index qubits and P(outcome 1 | index); and the
+        diagonal passes that project every released qubit on 0 (merged, <= QCM_MAX_CTRL index bits each)."""
+        pl = pr.plan
+        diag = []
+        for op in virtual:
+            ctrl = [pl.layout[q] for q in op.ctrls]
+            if any(c >= pl.n_phys for c in ctrl):
+                raise ValueError('released sweep is controlled by a qubit that is never stored')
+            a0, a1 = op.table[:, 0, 0], op.table[:, 1, 0]
+            w0, w1 = np.abs(a0) ** 2, np.abs(a1) ** 2
+            pr.virtual.append({'qubit': op.target, 'ctrl': ctrl, 'p1': w1 / (w0 + w1)})
+            diag.append((ctrl, a0))
+        em = fusion._Emitter()
+        act = pl.final_active
+        for ctrl, tab in fusion.merge_diagonals(diag):
+            em.op(fusion.QCM_OP_DIAG, ctrl=ctrl, n_in=act, n_out=act,
+                  table_off=em.table(fusion._diag_table_f64(tab)))
+        pr.proj = em.finish()
 
     def _handle(self, n_phys, precision):
         key = (n_phys, precision)
@@ -233,7 +275,9 @@ class B200Simulator:
         return probs, kept
 
     # -- public API ---------------------------------------------------------------------
-    def run(self, circuits, shots=1024, seed=None, precision=None, n_vars=None, **options):
+    def run(self, circuits, shots=1024, seed=None, precision=None, n_vars=None, stream_ids=None, **options):
+        """stream_ids: Philox stream per circuit (default: its index in the list) -- a batch split over
+        several GPUs passes the global indices so that the counts do not depend on the partition."""
         t0 = time.perf_counter()
         single = not isinstance(circuits, (list, tuple))
         circs = [circuits] if single else list(circuits)
@@ -245,6 +289,7 @@ class B200Simulator:
         shots = int(shots)
         small_max = _native.small_max_qubits(precision)
         entries = [None] * len(circs)
+        sid = (lambda i: i) if stream_ids is None else (lambda i: int(stream_ids[i]))
         small_ids, small_prep = [], []
         for i, c in enumerate(circs):
             nq = int(c.n_qubits if isinstance(c, ir.Program) else c.num_qubits)
@@ -253,12 +298,12 @@ class B200Simulator:
                 small_prep.append(self.prepare(c, n_vars=n_vars, small=True))
             else:
                 pr = self.prepare(c, n_vars=n_vars)
-                entries[i] = self._run_large(c, pr, shots, seed, i, precision)
+                entries[i] = self._run_large(c, pr, shots, seed, sid(i), precision)
         if small_ids:
             ps = [pr.ps if pr.ps is not None else (0, 0, 0) for pr in small_prep]
             keys, probs, kept, ms = _native.run_batch_small(
                 [pr.plan for pr in small_prep], [pr.clbit_map for pr in small_prep], ps, shots, seed,
-                precision=precision, device=self.device, want_probs=True, stream_ids=small_ids)
+                precision=precision, device=self.device, want_probs=True, stream_ids=[sid(i) for i in small_ids])
             for j, (i, pr) in enumerate(zip(small_ids, small_prep)):
                 has_ps = pr.ps is not None
                 entries[i] = {
@@ -267,7 +312,7 @@ class B200Simulator:
                     'probs': probs[j].copy() if has_ps else None, 'kept': float(kept[j]) if has_ps else None,
                     'meta': {'path': 'batch_small', 'n_qubits': pr.prog.n_qubits, 'n_phys': pr.plan.n_phys,
                              'passes': pr.plan.n_passes, 'gates_in': pr.fc.n_gates_in, 'batch_device_ms': ms,
-                             'philox_stream': i}}
+                             'philox_stream': sid(i)}}
         res = Result(entries, single, self._name, seed, shots, time.perf_counter() - t0)
         return Job(res)
 
@@ -278,17 +323,43 @@ class B200Simulator:
         h = self._handle(pl.n_phys, precision or self.precision)
         self._last = h
         ops = pl.ops
-        if not shots and len(ops) and ops['flags'].any():
+        if (not shots or pr.virtual) and len(ops) and ops['flags'].any():
             ops = ops.copy()
             ops['flags'] = 0                   # no shots follow: skip the sampler's checkpoint tree
         h.run_program(ops, pl.tables)
+        keys = None
+        if shots and pr.virtual:
+            keys = self._sample_released(h, pr, shots, seed, stream)
+        elif shots:
+            keys = h.sample(shots, seed, stream, pr.clbit_map if len(pr.clbit_map) else None)
         probs = kept = None
         if want_probs and pr.ps is not None and pr.n_vars <= 30:
+            if pr.virtual:
+                h.run_program(*pr.proj)        # project the released qubits on 0 (after the shots were drawn)
             probs, kept = self._probs_from_handle(h, pr)
-        keys = None
-        if shots:
-            keys = h.sample(shots, seed, stream, pr.clbit_map if len(pr.clbit_map) else None)
         return keys, probs, kept
+
+    def _sample_released(self, h, pr, shots, seed, stream):
+        """Shots of a circuit whose released qubits are not stored: basis states of the stored qubits
+        come from the GPU sampler, each released qubit's outcome from its sweep's coefficients at that
+        basis state (uniforms: numpy Philox keyed by (seed, stream), one column per released qubit)."""
+        pl = pr.plan
+        raw = h.sample(shots, seed, stream, None).astype(np.int64)
+        rng = np.random.Generator(np.random.Philox(key=[int(seed) & (2 ** 64 - 1), int(stream) & (2 ** 64 - 1)]))
+        u = rng.random((len(pr.virtual), shots))
+        vbits = {}
+        for k, v in enumerate(pr.virtual):
+            idx = np.zeros(shots, dtype=np.int64)
+            for j, c in enumerate(v['ctrl']):
+                idx |= ((raw >> c) & 1) << j
+            vbits[v['qubit']] = (u[k] < v['p1'][idx]).astype(np.uint64)
+        keys = np.zeros(shots, dtype=np.uint64)
+        for c, q in pr.prog.measures.items():
+            if q in vbits:
+                keys |= vbits[q] << np.uint64(c)
+            elif pl.layout[q] < pl.n_phys:
+                keys |= ((raw >> pl.layout[q]) & 1).astype(np.uint64) << np.uint64(c)
+        return keys
 
     def kernel_launches(self):
         """Kernels launched so far by the live state handles (bench.py's gpu_launches)."""
@@ -310,7 +381,8 @@ class B200Simulator:
         h2d = pl.ops.nbytes + pl.tables.nbytes + (pr.clbit_map.nbytes if shots else 0)
         d2h = (probs.nbytes + 8 if probs is not None else 0) + (keys.nbytes if keys is not None else 0)
         return {'circuit': circ, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
-                'meta': {'path': 'statevector', 'n_qubits': pr.prog.n_qubits, 'n_phys': pl.n_phys,
+                'meta': {'path': 'statevector', 'width': 'release' if pr.virtual else 'full',
+                         'released_qubits': len(pr.virtual), 'n_qubits': pr.prog.n_qubits, 'n_phys': pl.n_phys,
                          'passes': pl.n_passes, 'gates_in': pr.fc.n_gates_in, 'program_ms': t['program_ms'],
                          'sample_ms': t['sample_ms'], 'postselect_ms': t['postselect_ms'],
                          'bytes_read': t['bytes_read'], 'bytes_written': t['bytes_written'],

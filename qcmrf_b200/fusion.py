@@ -560,6 +560,49 @@ def _flag_last_pass(ops):
         ops[last]['flags'] = QCM_FLAG_SAMPLE_CHECKPOINT
 
 
+def split_releasable(fc: FusedCircuit, keep_below: int = 0):
+    """Measure-and-release: a qubit that is materialised from |0> by one
+    sweep and never used again -- a QCMRF clique ancilla, measured right after its block
+    (QCMRF.py:231-239) -- need not be stored at all.  Returns (core circuit without those sweeps,
+    list of the released sweeps).  Qubits below ``keep_below`` (the variable register) are kept."""
+    used_later = {}
+    for k, op in enumerate(fc.ops):
+        for q in ((op.target,) if op.kind == 'mux' else ()) + tuple(op.ctrls):
+            used_later[q] = k
+    core, virtual = [], []
+    for k, op in enumerate(fc.ops):
+        if (op.kind == 'mux' and op.zero_in and op.target >= keep_below and used_later[op.target] == k
+                and op.target not in fc.init):
+            virtual.append(op)
+        else:
+            core.append(op)
+    return FusedCircuit(fc.n_qubits, dict(fc.init), core, fc.global_phase, fc.n_gates_in), virtual
+
+
+def merge_diagonals(members):
+    """Product of diagonal factors [(ctrl positions, complex table 2^m)] over the union of their index
+    qubits, at most QCM_MAX_CTRL bits per merged table.  Returns [(ctrl positions, complex table)]."""
+    out = []
+    cur_ctrl, cur_tab = [], np.ones(1, dtype=np.complex128)
+    for ctrl, d in members:
+        ctrl = list(ctrl)
+        union = list(cur_ctrl) + [c for c in ctrl if c not in cur_ctrl]
+        if len(union) > QCM_MAX_CTRL:
+            out.append((cur_ctrl, cur_tab))
+            cur_ctrl, cur_tab, union = [], np.ones(1, dtype=np.complex128), ctrl
+        idx = np.arange(1 << len(union))
+        a = np.zeros_like(idx)
+        for j, c in enumerate(cur_ctrl):
+            a |= ((idx >> union.index(c)) & 1) << j
+        b = np.zeros_like(idx)
+        for j, c in enumerate(ctrl):
+            b |= ((idx >> union.index(c)) & 1) << j
+        cur_tab = cur_tab[a] * np.asarray(d)[b]
+        cur_ctrl = union
+    out.append((cur_ctrl, cur_tab))
+    return out
+
+
 def control_only_qubits(fc: FusedCircuit) -> List[int]:
     """Product-state qubits that no later sweep targets: they only ever select table entries, so a
     state can be split on them across GPUs with no communication at all."""

@@ -299,29 +299,13 @@ def shard_plan(pl: fusion.Plan, g: int, rank: int) -> ShardedPlan:
 
 
 def _merge_diags(members):
-    """Product of diagonal members over the union of their index qubits (<= QCM_MAX_CTRL bits per
-    merged table).  Returns [(ctrl positions, table (2^m, 2) float64)]."""
-    out = []
-    cur_ctrl, cur_tab = [], np.ones(1, dtype=np.complex128)
+    """[(kind, target, ctrl, table (2^m, 2) float64)] of diagonal members -> merged [(ctrl, table (2^m, 2))]."""
+    items = []
     for k, _t, ctrl, tab in members:
         assert k == QCM_OP_DIAG
         d = tab.reshape(-1, 2)
-        d = d[:, 0] + 1j * d[:, 1]
-        union = list(cur_ctrl) + [c for c in ctrl if c not in cur_ctrl]
-        if len(union) > QCM_MAX_CTRL:
-            out.append((cur_ctrl, cur_tab))
-            cur_ctrl, cur_tab, union = [], np.ones(1, dtype=np.complex128), list(ctrl)
-        idx = np.arange(1 << len(union))
-        a = np.zeros_like(idx)
-        for j, c in enumerate(cur_ctrl):
-            a |= ((idx >> union.index(c)) & 1) << j
-        b = np.zeros_like(idx)
-        for j, c in enumerate(ctrl):
-            b |= ((idx >> union.index(c)) & 1) << j
-        cur_tab = cur_tab[a] * d[b]
-        cur_ctrl = union
-    out.append((cur_ctrl, cur_tab))
-    return [(c, np.stack([t.real, t.imag], axis=1)) for c, t in out]
+        items.append((ctrl, d[:, 0] + 1j * d[:, 1]))
+    return [(c, np.stack([t.real, t.imag], axis=1)) for c, t in fusion.merge_diagonals(items)]
 
 
 # ------------------------------------------------------------------------------------------

@@ -485,3 +485,48 @@ def test_sampling_checkpoint_matches_full_tree(precision):
     for keys in (a, b):
         emp = np.bincount(keys.astype(np.int64), minlength=1 << act) / S
         assert 0.5 * np.abs(emp - pr / pr.sum()).sum() < weissman_tv_bound(int((pr > 0).sum()), S)
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_release_mode_chain(precision):
+    """Measure-and-release (BASELINE config 2's enabler): a 12-variable chain (N = 24 qubits at Aer
+    width) with only the 12 variable qubits stored; pmf/delta vs brute force, full-width keys vs the
+    product-form key distribution, agreement with the full-width engine run."""
+    n = 12
+    C = [[i, i + 1] for i in range(n - 1)]
+    rng = np.random.RandomState(4)
+    th = list(-np.abs(rng.randn(4 * len(C))) * 0.5)
+    pb, db, _ = mrf.brute_force_pmf(C, th)
+    sim = B200Simulator(precision=precision, width='release', seed=8)
+    res = sim.run(QCMRF(C, th, beta=0.7), shots=0).result()
+    pbeta, dbeta, _ = mrf.brute_force_pmf(C, th, beta=0.7)
+    p, d = res.postselected_probabilities()
+    assert np.abs(p - pbeta).max() < TOL_P[precision] and abs(d - dbeta) < TOL_P[precision]
+    res = sim.run(QCMRF(C, th), shots=50000).result()
+    meta = res.metadata(0)
+    assert meta['width'] == 'release' and meta['n_phys'] == n and meta['released_qubits'] == n - 1
+    p, d = res.postselected_probabilities()
+    assert np.abs(p - pb).max() < TOL_P[precision] and abs(d - db) < TOL_P[precision]
+    counts = res.get_counts()
+    N = 2 * n
+    assert sum(counts.values()) == 50000 and all(len(k) == N and k[N - 1 - n] == '0' for k in counts)
+    # post-selected shots reproduce the pmf; success fraction reproduces delta
+    kept = {k: v for k, v in counts.items() if int(k, 2) < (1 << n)}
+    succ = sum(kept.values()) / 5e4
+    assert abs(succ - db) < 5 * np.sqrt(db * (1 - db) / 5e4) + 1e-3
+    q = np.zeros(1 << n)
+    for k, v in kept.items():
+        q[int(k, 2)] = v
+    q /= q.sum()
+    assert 0.5 * np.abs(q - pb).sum() < weissman_tv_bound(1 << n, sum(kept.values()))
+    # each ancilla's marginal failure rate matches the full-width engine's exact state
+    full = B200Simulator(precision='double', small_batch=False)
+    psi = full.statevector(QCMRF(C, th))
+    pr = np.abs(psi) ** 2
+    idx = np.arange(1 << N)
+    for ii in (0, 5, n - 2):
+        qb = n + 1 + ii
+        exact = pr[((idx >> qb) & 1) == 1].sum()
+        got = sum(v for k, v in counts.items() if k[N - 1 - qb] == '1') / 5e4
+        assert abs(got - exact) < 5 * np.sqrt(exact * (1 - exact) / 5e4) + 1e-3
+    sim.close(); full.close()

@@ -225,3 +225,32 @@ def test_plan_limits_are_respected(models):
             if op['kind'] == fusion.QCM_OP_BLOCK:
                 assert op['target'] <= bm and op['n_ctrl'] <= fusion.QCM_MAX_MEMBERS
         assert pl.n_passes == 1 + -(-len(C) // bm)
+
+
+def test_release_mode_on_the_emulator(monkeypatch, models):
+    """width='release': clique ancillas are never stored; pmf/delta by projection, shots from the
+    sweep coefficients.  Host logic on the numpy engine emulator vs brute force and the oracle."""
+    import fake_native
+    from oracle import mrf, program, statevector as sv
+    from qcmrf_b200 import QCMRF, B200Simulator
+    fake_native.install(monkeypatch)
+    for j in (2, 3, 5):
+        C = models['0.5']['GRAPHS'][j]
+        th = models['0.5']['THETAS'][str(j)][4]
+        n, k, N, _ = program.sizes(C)
+        pb, db, _ = mrf.brute_force_pmf(C, th)
+        sim = B200Simulator(precision='double', width='release', small_batch=False, seed=3)
+        pr = sim.prepare(QCMRF(C, th))
+        assert pr.plan.n_phys == n and len(pr.virtual) == k           # only the variables are stored
+        res = sim.run(QCMRF(C, th), shots=30000).result()
+        p, delta = res.postselected_probabilities()
+        assert np.abs(p - pb).max() < 1e-12 and abs(delta - db) < 1e-12
+        assert res.metadata(0)['width'] == 'release'
+        psi, meas = sv.run_program(program.qcmrf_program(C, th)[0], N)
+        kp = sv.key_probabilities(psi, N, meas)
+        obs = np.zeros(1 << N)
+        for key, v in res.get_counts().items():
+            assert len(key) == N
+            obs[int(key, 2)] = v
+        assert obs.sum() == 30000 and obs[kp < 1e-15].sum() == 0
+        assert 0.5 * np.abs(obs / 3e4 - kp).sum() < 0.5 * np.sqrt(2 * ((kp > 0).sum() * np.log(2) + np.log(1e6)) / 3e4)
