@@ -40,7 +40,7 @@ struct qcm_sim_s {
     std::string err;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     qcm_timing timing{};
-    DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab;
+    DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab, tilectr;
     std::vector<double> h_top;
     // sum tree (built by qcm_sample_prepare)
     int tree_levels = 0;
@@ -93,13 +93,26 @@ int ensure(qcm_handle h, DevBuf &b, size_t bytes) {
 inline size_t amp_bytes(int prec) { return prec == QCM_C64 ? 8 : 16; }
 inline uint64_t rank_bits(const qcm_sim_s *h) { return h->n_global ? (h->rank << h->n_local) : 0ull; }
 
+int grid_mult() {
+    static int v = [] {
+        // Streaming kernels run one tile per CTA, in launch (= address) order: resident CTAs then share
+        // a compact window of the state, which keeps DRAM pages open.  A persistent grid-stride grid of
+        // 148 x occupancy CTAs measured 5.7-5.8 TB/s on the dense in-place pass, this 6.9-7.0 TB/s
+        // (profiles/r01_notes.md).  QCM_GRID_MULT=k caps the grid at k waves of resident CTAs (tuning knob).
+        const char *e = getenv("QCM_GRID_MULT");
+        int t = e ? atoi(e) : 65536;
+        return (t < 1 || t > 65536) ? 65536 : t;
+    }();
+    return v;
+}
+
 template <typename K>
 int grid_for(qcm_handle h, K kernel, size_t smem, uint64_t work_items_per_block, uint64_t items) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
     if (occ < 1) occ = 1;
     uint64_t need = (items + work_items_per_block - 1) / work_items_per_block;
-    uint64_t cap = (uint64_t)h->num_sms * (uint64_t)occ;
+    uint64_t cap = (uint64_t)h->num_sms * (uint64_t)occ * (uint64_t)grid_mult();
     if (need < 1) need = 1;
     return (int)std::min<uint64_t>(need, cap);
 }
@@ -139,18 +152,35 @@ int expand_threads() {
     return v;
 }
 
+// How k_expand's tiles are handed out (both in address order, see the kernel): 1 = persistent CTAs
+// pulling from a global counter (the coefficient table is staged once per CTA), 0 = one tile per CTA
+// in launch order.  QCM_EXPAND_SCHED=launch|counter overrides (tuning knob).
+int expand_use_counter() {
+    static int v = [] {
+        const char *e = getenv("QCM_EXPAND_SCHED");
+        if (e && !strcmp(e, "launch")) return 0;
+        if (e && !strcmp(e, "counter")) return 1;
+        return 0;                    // measured: launch order 11.9 ms vs counter 12.1 ms on the 29->33 qubit pass
+    }();
+    return v;
+}
+
 template <typename R, int V, int M, int U, bool Q0>
 int launch_expand_t(qcm_handle h, const ExpandArgs &a, size_t smem) {
     auto kern = k_expand<R, V, M, U, Q0>;
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = expand_threads();
     const uint64_t nvec = (1ull << a.n_in) / V;
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-    if (occ < 1) occ = 1;
     const uint64_t need = std::max<uint64_t>(1, (nvec + (uint64_t)threads * U - 1) / ((uint64_t)threads * U));
-    const int grid = (int)std::min<uint64_t>(need, (uint64_t)h->num_sms * occ);
-    kern<<<grid, threads, smem, h->stream>>>(a);
+    uint64_t grid = need;
+    if (a.tile_counter) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        if (occ < 1) occ = 1;
+        grid = std::min<uint64_t>(need, (uint64_t)h->num_sms * occ);
+    }
+    grid = std::min<uint64_t>(grid, 0x7fffffffull);
+    kern<<<(unsigned)grid, threads, smem, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;
@@ -192,6 +222,7 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     a.n_in = n_in;
     a.n_out = n_out;
     a.n_members = n_mem;
+    a.ctrl_below_32 = 1;
     a.rank_bits = rank_bits(h);
     for (int j = 0; j < M; ++j) {
         if (tq[j] < 0 || tq[j] >= n_out) return fail(h, QCM_ERR_INVALID, "block qubit %d outside the active state (%d)", tq[j], n_out);
@@ -219,8 +250,11 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
             per_target[pp - tq]++;
         }
         a.mem[g].n_ctrl = (int8_t)op.n_ctrl;
+        a.mem[g].low_bit = 0;
         for (int j = 0; j < op.n_ctrl; ++j) {
             const int c = op.ctrl[j];
+            if (c == 0) a.mem[g].low_bit = (uint16_t)(1u << j);
+            if (c >= 32) a.ctrl_below_32 = 0;
             if (c < 0 || c >= h->n_local + h->n_global) return fail(h, QCM_ERR_INVALID, "member %d: index qubit %d out of range", g, c);
             if (std::binary_search(tq, tq + M, c)) return fail(h, QCM_ERR_INVALID, "member %d: index qubit %d is a block target", g, c);
             a.mem[g].ctrl[j] = (int8_t)c;
@@ -284,8 +318,11 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
         const size_t centry = h->prec == QCM_C64 ? 8 : 16;
         const size_t nent = 1ull << (M + bp.targs.nu);
         if ((rc = ensure(h, h->ctab, nent * centry))) return rc;
+        if ((rc = ensure(h, h->tilectr, sizeof(unsigned long long)))) return rc;
         bp.targs.tables = (const double *)h->tab_f64.p;
         bp.targs.ctab = h->ctab.p;
+        bp.targs.tile_counter = expand_use_counter() ? (unsigned long long *)h->tilectr.p : nullptr;
+        bp.eargs.tile_counter = bp.targs.tile_counter;
         k_expand_table<<<(unsigned)((nent + 255) / 256), 256, 0, h->stream>>>(bp.targs);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
@@ -473,7 +510,8 @@ int build_tree(qcm_handle h) {
     h->tree_levels = levels;
     const uint64_t warps_per_block = kThreads / 32;
     {
-        uint64_t blocks = std::min<uint64_t>((n0 + warps_per_block - 1) / warps_per_block, (uint64_t)h->num_sms * 8);
+        // one warp per chunk, CTAs in address order (see grid_mult)
+        uint64_t blocks = std::min<uint64_t>((n0 + warps_per_block - 1) / warps_per_block, 0x7fffffffull);
         if (h->prec == QCM_C64) k_chunk_sums<float><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
         else k_chunk_sums<double><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
         QCM_CUDA(h, cudaGetLastError());
@@ -567,7 +605,7 @@ int qcm_destroy(qcm_handle h) {
     if (!h) return QCM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab};
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->own_state && h->state) cudaFree(h->state);

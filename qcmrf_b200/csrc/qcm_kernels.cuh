@@ -76,6 +76,7 @@ struct MemberDesc {
                                     // (amp *= table[idx], 2 reals per entry) applied to every register
     int8_t n_ctrl;
     int8_t ctrl[QCM_MAX_CTRL];      // qubit feeding table-index bit j (may be global)
+    uint16_t low_bit;               // 1 << j for the j with ctrl[j] == 0, else 0
     int32_t tab_off;                // offset, in reals, of this member's table in shared memory
     int32_t src_off;                // offset, in reals, of the table in `tables` (global)
 };
@@ -86,6 +87,7 @@ struct BlockArgs {
     int32_t n_in, n_out;
     int32_t tq[QCM_MAX_BLOCK];      // block qubits, ascending
     int32_t n_members;
+    int32_t ctrl_below_32;          // every index qubit of every member is below 32
     uint64_t rank_bits;             // rank << n_local
     MemberDesc mem[QCM_MAX_MEMBERS];
 };
@@ -185,13 +187,21 @@ __global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ Bloc
             const int pos = a.mem[g].pos;
             const int nc = a.mem[g].n_ctrl;
             const R *mt = tab + a.mem[g].tab_off;
+            const uint32_t low_bit = a.mem[g].low_bit;      // table-index bit fed by qubit 0 (V == 2 only)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
+                // table index of the vector's first amplitude; its second one differs in qubit 0 only
+                const uint64_t gi = base[u] | a.rank_bits;
+                uint32_t idx0 = 0;
+                if (a.ctrl_below_32) {
+                    const uint32_t lo = (uint32_t)gi;
+                    for (int j = 0; j < nc; ++j) idx0 |= ((lo >> a.mem[g].ctrl[j]) & 1u) << j;
+                } else {
+                    for (int j = 0; j < nc; ++j) idx0 |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+                }
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    const uint64_t gi = (base[u] + v) | a.rank_bits;
-                    uint32_t idx = 0;
-                    for (int j = 0; j < nc; ++j) idx |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+                    const uint32_t idx = v ? (idx0 | low_bit) : idx0;
                     if (pos < 0) {                                  // diagonal member
                         const R c = mt[2 * idx], sn = mt[2 * idx + 1];
 #pragma unroll
@@ -259,6 +269,7 @@ struct ExpandArgs {
     int32_t cu_below_32;            // every index qubit is below 32: 32-bit index arithmetic
     int8_t cu[kExpandMaxBits];      // union of index qubits: cidx bit j <-> qubit cu[j]
     uint64_t rank_bits;
+    unsigned long long *tile_counter;   // non-null: persistent CTAs fetch tiles in order from this counter
 };
 
 struct ExpandTableArgs {
@@ -269,11 +280,13 @@ struct ExpandTableArgs {
     int8_t mnc[QCM_MAX_MEMBERS];
     int8_t mbit[QCM_MAX_MEMBERS][QCM_MAX_CTRL];     // member index bit j <-> cidx bit mbit[g][j]
     int64_t moff[QCM_MAX_MEMBERS];
+    unsigned long long *tile_counter;   // reset to 0 here for the pass that follows
 };
 
 static __global__ void k_expand_table(const __grid_constant__ ExpandTableArgs a) {
     const uint32_t n = 1u << (a.M + a.nu);
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && a.tile_counter) *a.tile_counter = 0ull;
     if (e >= n) return;
     const uint32_t cidx = e & ((1u << a.nu) - 1u), r = e >> a.nu;
     double re = 1.0, im = 0.0;
@@ -314,8 +327,23 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
     const int nu = a.nu;
     const uint64_t nvec = (1ull << a.n_in) / V;
     const uint64_t ostride = 1ull << a.n_in;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
-    for (uint64_t bv0 = (uint64_t)blockIdx.x * blockDim.x * U + threadIdx.x; bv0 < nvec; bv0 += stride) {
+    // Tiles (blockDim * U vectors) are taken in address order: either one per CTA in launch order, or by
+    // persistent CTAs from a global counter.  CTAs that are resident together then work on one compact
+    // window of the state, which is what keeps the 2^M write streams on open DRAM pages; a grid-stride
+    // loop lets the CTAs drift apart and costs ~20 % of the bandwidth (profiles/r01_notes.md).
+    const uint64_t tile_vecs = (uint64_t)blockDim.x * U;
+    const uint64_t ntiles = (nvec + tile_vecs - 1) / tile_vecs;
+    __shared__ unsigned long long s_tile[2];
+    int parity = 0;
+    for (uint64_t tile = blockIdx.x;; tile += gridDim.x) {
+        if (a.tile_counter) {
+            if (threadIdx.x == 0) s_tile[parity] = atomicAdd(a.tile_counter, 1ull);
+            __syncthreads();
+            tile = s_tile[parity];
+            parity ^= 1;
+        }
+        if (tile >= ntiles) break;
+        const uint64_t bv0 = tile * tile_vecs + threadIdx.x;
         R xr[U][V], xi[U][V];
         bool ok[U];
 #pragma unroll
@@ -329,7 +357,7 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
             if (!ok[u]) continue;
             const uint64_t b = (bv0 + (uint64_t)u * blockDim.x) * V;
             const uint64_t gi = b | a.rank_bits;
- uint32_t cidx = 0;
+            uint32_t cidx = 0;
             if (a.cu_below_32) {
                 const uint32_t lo = (uint32_t)gi;
                 for (int j = 0; j < nu; ++j) cidx |= ((lo >> a.cu[j]) & 1u) << j;
