@@ -495,7 +495,8 @@ def dense_gate_pass(args, cliques, device, world=1):
     out = {'workload': '%s, fusion=clique: one in-place pass per clique' % args.dense_workload, 'n_phys': prep.plan.n_phys,
            'ranks': world, 'passes': len(passes), 'bytes_per_pass_per_gpu': by, 'median_ms': ms,
            'gbs_per_gpu': by / ms / 1e6, 'frac_of_measured_peak': by / ms / 1e6 / peak,
-           'amp_updates_per_sec_all_gpus': world * (by / 16) / (ms * 1e-3), 'circuit_ms': sum(r[1] for r in prof)}
+           'amp_updates_per_sec_all_gpus': world * (by / 16) / (ms * 1e-3), 'circuit_ms': sum(r[1] for r in prof),
+           'init_ms': [r[1] for r in prof if r[0] == 1][0], 'init_gbs': [r[3] / r[1] / 1e6 for r in prof if r[0] == 1][0]}
     ex = [r for r in prof if r[0] == -1]
     if ex:
         out['exchange'] = [{'ms': r[1], 'bytes_sent_per_gpu': r[2], 'gbs_per_direction_per_gpu': r[2] / r[1] / 1e6}

@@ -402,21 +402,21 @@ int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
     if ((rc = ensure(h, h->init_hi, sizeof(double2) << (n - L)))) return rc;
     const double *qv = (const double *)h->tab_f64.p + op.table_off;
     const uint64_t nt = (1ull << L) + (1ull << (n - L));
-    k_init_tables<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(qv, n, L, (double2 *)h->init_lo.p, (double2 *)h->init_hi.p);
+    k_init_tables<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(qv, n, L, h->init_lo.p, (double2 *)h->init_hi.p, h->prec == QCM_C64 ? 1 : 0);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     if (h->prec == QCM_C64) {
         if (n >= 1) {
             auto k = k_init<float, 2>;
-            int grid = grid_for(h, k, 0, kThreads, (1ull << n) / 2);
-            k<<<grid, kThreads, 0, h->stream>>>(h->state, (const double2 *)h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+            int grid = grid_for(h, k, 0, (uint64_t)kThreads * kInitU, (1ull << n) / 2);
+            k<<<grid, kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
         } else {
-            k_init<float, 1><<<1, kThreads, 0, h->stream>>>(h->state, (const double2 *)h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+            k_init<float, 1><<<1, kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
         }
     } else {
         auto k = k_init<double, 1>;
-        int grid = grid_for(h, k, 0, kThreads, 1ull << n);
-        k<<<grid, kThreads, 0, h->stream>>>(h->state, (const double2 *)h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+        int grid = grid_for(h, k, 0, (uint64_t)kThreads * kInitU, 1ull << n);
+        k<<<grid, kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
@@ -430,10 +430,10 @@ int launch_extend(qcm_handle h, int n_in, int n_out) {
     const uint64_t first = 1ull << n_in, count = (1ull << n_out) - first;
     if (h->prec == QCM_C64) {
         auto k = k_zero<float>;
-        k<<<grid_for(h, k, 0, kThreads, count), kThreads, 0, h->stream>>>(h->state, first, count);
+        k<<<grid_for(h, k, 0, (uint64_t)kThreads * kInitU, count), kThreads, 0, h->stream>>>(h->state, first, count);
     } else {
         auto k = k_zero<double>;
-        k<<<grid_for(h, k, 0, kThreads, count), kThreads, 0, h->stream>>>(h->state, first, count);
+        k<<<grid_for(h, k, 0, (uint64_t)kThreads * kInitU, count), kThreads, 0, h->stream>>>(h->state, first, count);
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;

@@ -35,6 +35,10 @@ template <> struct VecIO<float, 2> {
     static __device__ __forceinline__ void store(void *st, uint64_t amp, const float (&re)[2], const float (&im)[2]) {
         __stcs(reinterpret_cast<float4 *>(st) + (amp >> 1), make_float4(re[0], im[0], re[1], im[1]));
     }
+    static __device__ __forceinline__ void load_nc(const void *st, uint64_t amp, float (&re)[2], float (&im)[2]) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(st) + (amp >> 1));
+        re[0] = t.x; im[0] = t.y; re[1] = t.z; im[1] = t.w;
+    }
 };
 template <> struct VecIO<float, 1> {
     using T = float2;
@@ -45,6 +49,10 @@ template <> struct VecIO<float, 1> {
     static __device__ __forceinline__ void store(void *st, uint64_t amp, const float (&re)[1], const float (&im)[1]) {
         __stcs(reinterpret_cast<float2 *>(st) + amp, make_float2(re[0], im[0]));
     }
+    static __device__ __forceinline__ void load_nc(const void *st, uint64_t amp, float (&re)[1], float (&im)[1]) {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(st) + amp);
+        re[0] = t.x; im[0] = t.y;
+    }
 };
 template <> struct VecIO<double, 1> {
     using T = double2;
@@ -54,6 +62,10 @@ template <> struct VecIO<double, 1> {
     }
     static __device__ __forceinline__ void store(void *st, uint64_t amp, const double (&re)[1], const double (&im)[1]) {
         __stcs(reinterpret_cast<double2 *>(st) + amp, make_double2(re[0], im[0]));
+    }
+    static __device__ __forceinline__ void load_nc(const void *st, uint64_t amp, double (&re)[1], double (&im)[1]) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(st) + amp);
+        re[0] = t.x; im[0] = t.y;
     }
 };
 
@@ -443,7 +455,10 @@ __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagA
 // Product-state initialisation (write-only).  amp[i] = lo[i & (2^L-1)] * hi[i >> L],
 // the two factor tables are built by k_init_tables from the per-qubit 2-vectors.
 // ----------------------------------------------------------------------------------
-static __global__ void k_init_tables(const double *qv /* n*4 */, int n, int L, double2 *lo, double2 *hi) {
+// lo is stored in the state's real type (a lane's vector of V amplitudes is then ONE 128-bit load of
+// V adjacent lo entries, so the factor tables cost no more L2 traffic than the state costs HBM traffic);
+// hi stays fp64: it is warp-uniform and read once per thread.
+static __global__ void k_init_tables(const double *qv /* n*4 */, int n, int L, void *lo, double2 *hi, int lo_is_float) {
     const uint64_t nlo = 1ull << L, nhi = 1ull << (n - L);
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nlo + nhi) return;
@@ -458,41 +473,56 @@ static __global__ void k_init_tables(const double *qv /* n*4 */, int n, int L, d
         im = re * fi + im * fr;
         re = nr;
     }
-    (is_hi ? hi[bits] : lo[bits]) = make_double2(re, im);
+    if (is_hi) hi[bits] = make_double2(re, im);
+    else if (lo_is_float) reinterpret_cast<float2 *>(lo)[bits] = make_float2((float)re, (float)im);
+    else reinterpret_cast<double2 *>(lo)[bits] = make_double2(re, im);
 }
 
+constexpr int kInitU = 8;                       // vectors per thread: a CTA writes 32 KiB (c64), in address order
+
 template <typename R, int V>
-__global__ void __launch_bounds__(kThreads) k_init(void *state, const double2 *lo, const double2 *hi, int n, int L) {
+__global__ void __launch_bounds__(kThreads) k_init(void *state, const void *lo, const double2 *hi, int n, int L) {
     using IO = VecIO<R, V>;
     const uint64_t nvec = (1ull << n) / V;
     const uint64_t lmask = (1ull << L) - 1ull;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
-        const uint64_t i = vi * V;
-        const double2 h = __ldg(hi + (i >> L));
-        R re[V], im[V];
-        if (h.x == 0.0 && h.y == 0.0) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kInitU;
+    for (uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x * kInitU + threadIdx.x; v0 < nvec; v0 += stride) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) { re[v] = R(0); im[v] = R(0); }
-        } else {
+        for (int u = 0; u < kInitU; ++u) {
+            const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+            if (vi >= nvec) break;
+            const uint64_t i = vi * V;
+            const double2 h = __ldg(hi + (i >> L));
+            R re[V], im[V];
+            if (h.x == 0.0 && h.y == 0.0) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const double2 l = __ldg(lo + ((i + v) & lmask));
-                re[v] = (R)(l.x * h.x - l.y * h.y);
-                im[v] = (R)(l.x * h.y + l.y * h.x);
+                for (int v = 0; v < V; ++v) { re[v] = R(0); im[v] = R(0); }
+            } else {
+                R lr[V], li[V];
+                IO::load_nc(lo, i & lmask, lr, li);      // V adjacent entries (i is a multiple of V, L >= 1 when V == 2)
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    re[v] = (R)((double)lr[v] * h.x - (double)li[v] * h.y);
+                    im[v] = (R)((double)lr[v] * h.y + (double)li[v] * h.x);
+                }
             }
+            IO::store(state, i, re, im);
         }
-        IO::store(state, i, re, im);
     }
 }
 
 // zero-fill amplitudes [first, first+count)
 template <typename R>
 __global__ void __launch_bounds__(kThreads) k_zero(void *state, uint64_t first, uint64_t count) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        R re[1] = {R(0)}, im[1] = {R(0)};
-        VecIO<R, 1>::store(state, first + i, re, im);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kInitU;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * kInitU + threadIdx.x; i0 < count; i0 += stride) {
+#pragma unroll
+        for (int u = 0; u < kInitU; ++u) {
+            const uint64_t i = i0 + (uint64_t)u * blockDim.x;
+            if (i >= count) break;
+            R re[1] = {R(0)}, im[1] = {R(0)};
+            VecIO<R, 1>::store(state, first + i, re, im);
+        }
     }
 }
 
