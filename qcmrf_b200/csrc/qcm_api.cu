@@ -169,7 +169,7 @@ template <typename R, int V, int M, int U, bool Q0>
 int launch_expand_t(qcm_handle h, const ExpandArgs &a, size_t smem) {
     auto kern = k_expand<R, V, M, U, Q0>;
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = expand_threads();
+    const int threads = a.tree_out ? (1 << kChunkBits) / V : expand_threads();    // fused tree: sub-tile == chunk
     const uint64_t nvec = (1ull << a.n_in) / V;
     const uint64_t need = std::max<uint64_t>(1, (nvec + (uint64_t)threads * U - 1) / ((uint64_t)threads * U));
     uint64_t grid = need;
@@ -485,13 +485,12 @@ int upload_tables(qcm_handle h, const double *tables, size_t n_tables) {
 }
 
 // ---- sum tree -----------------------------------------------------------------------
-int build_tree(qcm_handle h) {
-    const int na = h->n_active;
+// level sizes + buffers for a tree over 2^na amplitudes
+int tree_layout(qcm_handle h, int na) {
     const int cb = std::min(na, kChunkBits);
-    uint64_t n0 = 1ull << (na - cb);
     uint64_t sizes[8];
     int levels = 0;
-    uint64_t n = n0, total = 0;
+    uint64_t n = 1ull << (na - cb), total = 0;
     while (true) {
         if (levels >= 8) return fail(h, QCM_ERR_UNSUPPORTED, "sum tree too deep");
         sizes[levels++] = n;
@@ -508,22 +507,32 @@ int build_tree(qcm_handle h) {
         p += sizes[l];
     }
     h->tree_levels = levels;
+    return QCM_OK;
+}
+
+// level 0 from the state: one warp per chunk, CTAs in address order (see grid_mult)
+int tree_level0(qcm_handle h, int na) {
     const uint64_t warps_per_block = kThreads / 32;
-    {
-        // one warp per chunk, CTAs in address order (see grid_mult)
-        uint64_t blocks = std::min<uint64_t>((n0 + warps_per_block - 1) / warps_per_block, 0x7fffffffull);
-        if (h->prec == QCM_C64) k_chunk_sums<float><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
-        else k_chunk_sums<double><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
-        QCM_CUDA(h, cudaGetLastError());
-        h->timing.kernel_launches++;
-    }
+    const uint64_t n0 = h->tree_n[0];
+    uint64_t blocks = std::min<uint64_t>((n0 + warps_per_block - 1) / warps_per_block, 0x7fffffffull);
+    if (h->prec == QCM_C64) k_chunk_sums<float><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
+    else k_chunk_sums<double><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    return QCM_OK;
+}
+
+// upper levels, total mass; the tree then describes a state of `na` base qubits
+int tree_finish(qcm_handle h, int na) {
+    const uint64_t warps_per_block = kThreads / 32;
+    const int levels = h->tree_levels;
     for (int l = 1; l < levels; ++l) {
-        uint64_t blocks = std::min<uint64_t>((sizes[l] + warps_per_block - 1) / warps_per_block, (uint64_t)h->num_sms * 8);
-        k_tree_level<<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->tree_ptr[l - 1], sizes[l - 1], h->tree_ptr[l], sizes[l]);
+        uint64_t blocks = std::min<uint64_t>((h->tree_n[l] + warps_per_block - 1) / warps_per_block, (uint64_t)h->num_sms * 8);
+        k_tree_level<<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->tree_ptr[l - 1], h->tree_n[l - 1], h->tree_ptr[l], h->tree_n[l]);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
     }
-    const uint64_t ntop = sizes[levels - 1];
+    const uint64_t ntop = h->tree_n[levels - 1];
     h->h_top.resize(ntop);
     QCM_CUDA(h, cudaMemcpyAsync(h->h_top.data(), h->tree_ptr[levels - 1], ntop * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -535,6 +544,14 @@ int build_tree(qcm_handle h) {
     h->tree_base_bits = na;
     h->tree_cond_bits = 0;
     return QCM_OK;
+}
+
+int build_tree(qcm_handle h) {
+    const int na = h->n_active;
+    int rc;
+    if ((rc = tree_layout(h, na))) return rc;
+    if ((rc = tree_level0(h, na))) return rc;
+    return tree_finish(h, na);
 }
 
 int check_device(qcm_handle h) {
@@ -738,11 +755,14 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 bool checkpoint = last && (op.flags & QCM_FLAG_SAMPLE_CHECKPOINT) && bp.norm_preserving &&
                                   op.n_active_in >= kChunkBits;
                 if (checkpoint) {
-                    if ((rc = build_tree(h))) return rc;
-                    h->timing.bytes_read += amp_bytes(h->prec) << op.n_active_in;     // the tree's level-0 read
+                    // level 0 of the tree: fused into the expansion pass (it reads every input amplitude
+                    // anyway); a generic block pass cannot be norm-preserving, so bp.expand holds here
+                    if ((rc = tree_layout(h, op.n_active_in))) return rc;
+                    bp.eargs.tree_out = h->tree_ptr[0];
                 }
                 if ((rc = launch_block_plan(h, bp))) return rc;
                 if (checkpoint) {
+                    if ((rc = tree_finish(h, op.n_active_in))) return rc;
                     h->tree_cond_bits = bp.M;
                     h->tree_for_active = op.n_active_out;
                     h->n_checkpoint++;

@@ -271,6 +271,15 @@ __global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ Bloc
 // ctab[a][cidx]; the pass stages ctab in shared memory, reads each input amplitude
 // once and writes its 2^M images: read 2^n_in, write 2^(n_in+M), nothing else.
 // ----------------------------------------------------------------------------------
+constexpr int kChunkBits = 10;                  // 1024 amplitudes per leaf chunk of the sampler's sum tree
+constexpr int kFanBits = 10;                    // 1024 children per tree node
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
 constexpr int kExpandThreadsMax = 1024;
 constexpr int kExpandMaxBits = 12;          // nu + M: 4096 entries (32 KB c64, 64 KB c128)
 
@@ -282,6 +291,8 @@ struct ExpandArgs {
     int8_t cu[kExpandMaxBits];      // union of index qubits: cidx bit j <-> qubit cu[j]
     uint64_t rank_bits;
     unsigned long long *tile_counter;   // non-null: persistent CTAs fetch tiles in order from this counter
+    double *tree_out;                   // non-null: also emit sum |in|^2 per 2^kChunkBits input amplitudes (the
+                                        // sampler's level-0 sums); requires blockDim.x * V == 2^kChunkBits
 };
 
 struct ExpandTableArgs {
@@ -363,6 +374,28 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
             const uint64_t bv = bv0 + (uint64_t)u * blockDim.x;
             ok[u] = bv < nvec;
             if (ok[u]) IO::load(a.state, bv * V, xr[u], xi[u]);
+        }
+        if (a.tree_out) {
+            // level-0 sums of the sampler's tree over the INPUT (sum_a |out[x,a]|^2 = |in[x]|^2): sub-tile
+            // u of this tile is exactly one chunk.  Fixed association: xor-shuffle tree, then warps in order.
+            __shared__ double s_w[U][32];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double w = 0.0;
+                if (ok[u]) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) w += (double)xr[u][v] * (double)xr[u][v] + (double)xi[u][v] * (double)xi[u][v];
+                }
+                w = warp_sum(w);
+                if ((threadIdx.x & 31) == 0) s_w[u][threadIdx.x >> 5] = w;
+            }
+            __syncthreads();
+            if (threadIdx.x < U && tile * U + threadIdx.x < (nvec * V) >> kChunkBits) {
+                double t = 0.0;
+                for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_w[threadIdx.x][i];
+                a.tree_out[tile * U + threadIdx.x] = t;
+            }
+            __syncthreads();
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -549,14 +582,6 @@ __global__ void __launch_bounds__(kThreads) k_swap(void *state, int qa, int qb, 
 // Reductions.  All sums are fp64 and use a fixed association (lane-strided partials,
 // shuffle tree) so that results do not depend on the grid or on the GPU count.
 // ----------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-}
-
-constexpr int kChunkBits = 10;                  // 1024 amplitudes per leaf chunk
-constexpr int kFanBits = 10;                    // 1024 children per tree node
 
 // level 0: chunk c = sum_{i in chunk} |amp_i|^2 ; one warp per chunk.  Full-size chunks
 // stream 128-bit loads, eight in flight per lane; the lane-strided order is fixed.
