@@ -460,7 +460,7 @@ class ShardedSimulator:
             pending = works
         self.exchange_bytes += len(peers) * slab * esz
 
-    def _run_segments(self, sp):
+    def _run_segments(self, sp, keep_flags=True):
         h = self._handle(sp.n_local)
         t = self.torch
         self._profile = []
@@ -469,6 +469,9 @@ class ShardedSimulator:
         for seg in sp.segments:
             if seg[0] == 'run':
                 _, ops, tabs, mask = seg
+                if not keep_flags and ops['flags'].any():
+                    ops = ops.copy()
+                    ops['flags'] = 0               # no shots follow: skip the sampler's checkpoint tree
                 h.set_shard(sp.g, sp.rank & mask)
                 h.run_program(ops, tabs)
                 self._profile.extend(h.op_profile())
@@ -506,28 +509,27 @@ class ShardedSimulator:
     def execute(self, pr, shots, seed=0, stream=0, want_probs=True):
         """Returns (keys or None, probs or None, kept or None); identical on every rank."""
         sp = pr.sp
-        if not shots and any(seg[0] == 'run' and seg[1]['flags'].any() for seg in sp.segments):
-            pass                                    # checkpoint flags are ignored on sharded handles
         t0 = time.perf_counter()
-        h = self._run_segments(sp)
+        h = self._run_segments(sp, keep_flags=bool(shots))
         t1 = time.perf_counter()
         replica = self._is_replica(sp)
-        probs = kept = None
+        probs = kept = masses = None
+        mass = None
+        if shots:
+            mass = 0.0 if replica else h.sample_prepare()
         if want_probs and pr.ps is not None and pr.n_vars <= 30:
-            probs, kept = self._postselect(h, pr, replica)
+            probs, kept, masses = self._postselect(h, pr, replica, mass)
         t2 = time.perf_counter()
         keys = None
         if shots:
-            mass = 0.0 if replica else h.sample_prepare()
-            m = np.zeros(self.world)
-            m[self.rank] = mass
-            masses = self._reduce(m)
+            if masses is None:
+                mvec = np.zeros(self.world)
+                mvec[self.rank] = mass
+                masses = self._reduce(mvec)
             # replicas mirror a rank that is sampling: they contribute nothing
             if replica:
                 k = np.zeros(shots, dtype=np.int64)
             else:
-                # masses are indexed by the rank the handle believes it is (bits of never-materialised
-                # qubits are 0 for every non-replica)
                 kk, mine = h.sample_sharded(shots, seed, stream, masses, pr.clbit_map if len(pr.clbit_map) else None)
                 k = np.where(mine, kk, 0).astype(np.int64)
             keys = self._reduce(k).astype(np.uint64)
@@ -557,22 +559,78 @@ class ShardedSimulator:
             idx |= ((loc >> j) & 1) << q
         return m, idx
 
-    def _postselect(self, h, pr, replica):
+    def _postselect(self, h, pr, replica, mass=None):
         """Exact post-selected pmf (index: variable q <-> bit q) and success probability, on every rank.
         Variables on local positions 0..m-1 come from the engine's contiguous reduction; variables on
-        global positions select which part of the pmf this rank owns."""
+        global positions select which part of the pmf this rank owns.  One all-gather moves every
+        rank's block, its kept mass and (for the sampler) its total mass.  Returns (pmf, kept, masses)."""
         n = pr.n_vars
         if pr.pmf_map is None:
             pr.pmf_map = self._pmf_map(pr)
         m, where = pr.pmf_map
         mask, value, _ = pr.ps
-        out = np.zeros((1 << n) + 1)
+        mine = np.zeros((1 << m) + 2)
         if not replica:
             p, k = h.postselect(mask, value, m)
-            out[:-1][where] = p
-            out[-1] = k
-        red = self._reduce(out)
-        return red[:-1], float(red[-1])
+            mine[:-2] = p
+            mine[-2] = k
+            mine[-1] = 0.0 if mass is None else mass
+        t, dist = self.torch, self.dist
+        x = t.from_numpy(mine).to(self._state.device)
+        allx = t.empty(self.world * mine.size, dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(allx, x, group=self.group)
+        allx = allx.cpu().numpy().reshape(self.world, mine.size)
+        masses = allx[:, -1].copy()
+        kept = float(allx[:, -2].sum())
+        if isinstance(where, slice) and where.stop - where.start == 1 << m and self._slices_tile(pr, m):
+            # rank r's block is pmf[r_off : r_off + 2^m] and the offsets ascend with the rank
+            order = self._slice_order(pr, m)
+            return np.concatenate([allx[r, :-2] for r in order]), kept, masses
+        out = np.zeros(1 << n)
+        for r in range(self.world):
+            wr = self._pmf_where_for_rank(pr, r, m)
+            if wr is None:
+                continue
+            if isinstance(wr, slice):
+                out[wr] += allx[r, :-2]
+            else:
+                np.add.at(out, wr, allx[r, :-2])
+        return out, kept, masses
+
+    def _pmf_where_for_rank(self, pr, r, m):
+        """Index set of rank r's block in the pmf, or None if r is a replica."""
+        sp = pr.sp
+        if r & ~sp.mat_mask:
+            return None
+        n, vp = pr.n_vars, pr.var_positions
+        local_v = [q for q in range(n) if 0 <= vp[q] < sp.n_local]
+        off = 0
+        for q in range(n):
+            if vp[q] >= sp.n_local:
+                off |= ((r >> (vp[q] - sp.n_local)) & 1) << q
+        if local_v == list(range(m)):
+            return slice(off, off + (1 << m))
+        loc = np.arange(1 << m, dtype=np.int64)
+        idx = np.full(1 << m, off, dtype=np.int64)
+        for j, q in enumerate(local_v):
+            idx |= ((loc >> j) & 1) << q
+        return idx
+
+    def _slices_tile(self, pr, m):
+        """Do the ranks' blocks tile the pmf exactly once (every global qubit a variable, no replicas)?"""
+        sp = pr.sp
+        if sp.mat_mask != (1 << sp.g) - 1:
+            return False
+        offs = set()
+        for r in range(self.world):
+            w = self._pmf_where_for_rank(pr, r, m)
+            if not isinstance(w, slice):
+                return False
+            offs.add(w.start)
+        return len(offs) == self.world and (self.world << m) == (1 << pr.n_vars)
+
+    def _slice_order(self, pr, m):
+        return sorted(range(self.world), key=lambda r: self._pmf_where_for_rank(pr, r, m).start)
 
     def run(self, circuits, shots=1024, seed=None, n_vars=None):
         from .backend import Job, Result, _keys_to_counts
