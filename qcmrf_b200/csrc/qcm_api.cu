@@ -40,7 +40,7 @@ struct qcm_sim_s {
     std::string err;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     qcm_timing timing{};
-    DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab, tilectr;
+    DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab, tilectr, subtree;
     std::vector<double> h_top;
     // sum tree (built by qcm_sample_prepare)
     int tree_levels = 0;
@@ -49,6 +49,7 @@ struct qcm_sim_s {
     int tree_for_active = -1;       // n_active of the state the tree describes
     int tree_base_bits = 0;         // qubits the tree indexes (tree_for_active - tree_cond_bits)
     int tree_cond_bits = 0;         // expansion qubits materialised after the tree was built
+    int tree_sub_bits = 0;          // > 0: subtree holds sums over 2^tree_sub_bits amplitudes (fused checkpoint only)
     uint64_t n_expand = 0, n_checkpoint = 0;
     double local_mass = 0.0;
     bool tree_valid = false;
@@ -543,6 +544,7 @@ int tree_finish(qcm_handle h, int na) {
     h->tree_for_active = na;
     h->tree_base_bits = na;
     h->tree_cond_bits = 0;
+    h->tree_sub_bits = 0;
     return QCM_OK;
 }
 
@@ -622,7 +624,7 @@ int qcm_destroy(qcm_handle h) {
     if (!h) return QCM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr};
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->own_state && h->state) cudaFree(h->state);
@@ -757,13 +759,17 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 if (checkpoint) {
                     // level 0 of the tree: fused into the expansion pass (it reads every input amplitude
                     // anyway); a generic block pass cannot be norm-preserving, so bp.expand holds here
+                    const int sub_bits = h->prec == QCM_C64 ? 6 : 5;           // one warp's vectors: 32 * V amplitudes
                     if ((rc = tree_layout(h, op.n_active_in))) return rc;
+                    if ((rc = ensure(h, h->subtree, sizeof(double) << (op.n_active_in - sub_bits)))) return rc;
                     bp.eargs.tree_out = h->tree_ptr[0];
+                    bp.eargs.sub_out = (double *)h->subtree.p;
                 }
                 if ((rc = launch_block_plan(h, bp))) return rc;
                 if (checkpoint) {
                     if ((rc = tree_finish(h, op.n_active_in))) return rc;
                     h->tree_cond_bits = bp.M;
+                    h->tree_sub_bits = h->prec == QCM_C64 ? 6 : 5;
                     h->tree_for_active = op.n_active_out;
                     h->n_checkpoint++;
                     keep_tree = true;
@@ -892,6 +898,8 @@ int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t str
     a.state = h->state;
     a.n_active = h->tree_base_bits;
     a.cond_bits = h->tree_cond_bits;
+    a.sub = h->tree_sub_bits ? (const double *)h->subtree.p : nullptr;
+    a.sub_bits = h->tree_sub_bits;
     a.n_levels = h->tree_levels;
     for (int l = 0; l < h->tree_levels; ++l) {
         a.level[l] = h->tree_ptr[l];

@@ -293,6 +293,8 @@ struct ExpandArgs {
     unsigned long long *tile_counter;   // non-null: persistent CTAs fetch tiles in order from this counter
     double *tree_out;                   // non-null: also emit sum |in|^2 per 2^kChunkBits input amplitudes (the
                                         // sampler's level-0 sums); requires blockDim.x * V == 2^kChunkBits
+    double *sub_out;                    // with tree_out: the per-warp sums (32*V amplitudes each), a finer level the
+                                        // sampler uses to avoid scanning a whole chunk times 2^M branches
 };
 
 struct ExpandTableArgs {
@@ -387,7 +389,10 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
                     for (int v = 0; v < V; ++v) w += (double)xr[u][v] * (double)xr[u][v] + (double)xi[u][v] * (double)xi[u][v];
                 }
                 w = warp_sum(w);
-                if ((threadIdx.x & 31) == 0) s_w[u][threadIdx.x >> 5] = w;
+                if ((threadIdx.x & 31) == 0) {
+                    s_w[u][threadIdx.x >> 5] = w;
+                    if (ok[u]) a.sub_out[(tile * U + u) * (blockDim.x >> 5) + (threadIdx.x >> 5)] = w;
+                }
             }
             __syncthreads();
             if (threadIdx.x < U && tile * U + threadIdx.x < (nvec * V) >> kChunkBits) {
@@ -732,6 +737,8 @@ struct SampleArgs {
                                     // x | a << n_active (an expansion pass ran after the tree was built):
                                     // leaf weight = sum_a |amp|^2, then a is drawn given x
     int32_t n_levels;               // tree levels above the amplitudes (>= 1)
+    const double *sub;              // optional finer level under level[0]: sums over 2^sub_bits amplitudes
+    int32_t sub_bits;
     const double *level[8];         // level[0] = chunk sums ... level[n_levels-1] = top
     uint64_t level_n[8];
     uint64_t shots, seed, stream;
@@ -768,8 +775,16 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
             const uint32_t c = warp_pick([&](uint32_t i) { return lv[first + i]; }, cnt, u, lane);
             node = first + c;
         }
-        // node = chunk index; search the amplitudes of the chunk
-        const uint64_t afirst = node << cb;
+        // node = chunk index; search the amplitudes of the chunk (through the finer level if there is one)
+        uint64_t afirst = node << cb;
+        uint32_t leaf_cnt = 1u << cb;
+        if (a.sub) {
+            const uint32_t nsub = 1u << (cb - a.sub_bits);
+            const double *sp = a.sub + (node << (cb - a.sub_bits));
+            const uint32_t c = warp_pick([&](uint32_t i) { return sp[i]; }, nsub, u, lane);
+            afirst += (uint64_t)c << a.sub_bits;
+            leaf_cnt = 1u << a.sub_bits;
+        }
         const int nb = 1 << a.cond_bits;
         auto amp_w = [&](uint64_t i) -> double {
             if constexpr (sizeof(R) == 4) {
@@ -782,7 +797,7 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
         };
         uint64_t within;
         if (a.cond_bits == 0) {
-            within = warp_pick([&](uint32_t i) { return amp_w(afirst + i); }, 1u << cb, u, lane);
+            within = warp_pick([&](uint32_t i) { return amp_w(afirst + i); }, leaf_cnt, u, lane);
         } else {
             const uint32_t x = warp_pick(
                 [&](uint32_t i) {
@@ -790,7 +805,7 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
                     for (int br = 0; br < nb; ++br) sacc += amp_w(afirst + i + ((uint64_t)br << a.n_active));
                     return sacc;
                 },
-                1u << cb, u, lane);
+                leaf_cnt, u, lane);
             const uint32_t br = warp_pick([&](uint32_t i) { return amp_w(afirst + x + ((uint64_t)i << a.n_active)); },
                                           (uint32_t)nb, u, lane);
             within = (uint64_t)x + ((uint64_t)br << a.n_active);
