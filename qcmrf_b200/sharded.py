@@ -310,7 +310,7 @@ def _merge_diags(members):
 
 # ------------------------------------------------------------------------------------------
 class _ShardPrepared:
-    __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions', 'pmf_map')
+    __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions', 'pmf_map', 'pmf_order')
 
 
 class ShardedSimulator:
@@ -401,7 +401,7 @@ class ShardedSimulator:
             pr.clbit_map[c] = position(q)
         if n_vars is None:
             n_vars = prog.metadata.get('num_vertices')
-        pr.n_vars, pr.ps, pr.var_positions, pr.pmf_map = n_vars, None, None, None
+        pr.n_vars, pr.ps, pr.var_positions, pr.pmf_map, pr.pmf_order = n_vars, None, None, None, None
         if n_vars is not None:
             mask = 0
             for q in range(n_vars, prog.n_qubits):
@@ -582,10 +582,15 @@ class ShardedSimulator:
         allx = allx.cpu().numpy().reshape(self.world, mine.size)
         masses = allx[:, -1].copy()
         kept = float(allx[:, -2].sum())
-        if isinstance(where, slice) and where.stop - where.start == 1 << m and self._slices_tile(pr, m):
-            # rank r's block is pmf[r_off : r_off + 2^m] and the offsets ascend with the rank
-            order = self._slice_order(pr, m)
-            return np.concatenate([allx[r, :-2] for r in order]), kept, masses
+        if pr.pmf_order is None:
+            tiles = isinstance(where, slice) and where.stop - where.start == 1 << m and self._slices_tile(pr, m)
+            pr.pmf_order = self._slice_order(pr, m) if tiles else False
+        if pr.pmf_order:
+            # rank r's block is pmf[r_off : r_off + 2^m]; the blocks tile the pmf
+            blocks = allx[:, :-2]
+            if pr.pmf_order != list(range(self.world)):
+                blocks = blocks[pr.pmf_order]
+            return np.ascontiguousarray(blocks).reshape(-1), kept, masses
         out = np.zeros(1 << n)
         for r in range(self.world):
             wr = self._pmf_where_for_rank(pr, r, m)
