@@ -189,7 +189,7 @@ def main():
         args.warmup = 3
 
     from qcmrf_b200 import workloads
-    cliques, N = workloads.named(args.workload)
+    cliques, N = ([[0]], 3) if args.workload == 'fixtures' else workloads.named(args.workload)
     if args.impl == 'reference':
         run_reference_arm(args, cliques, N)
         return

@@ -26,6 +26,7 @@ Stage 2 ``plan``: physical layout + lazy materialisation + blocked passes.
 Nothing here touches amplitudes: the output is a list of ``qcm_op`` + coefficient
 tables for the CUDA engine.
 """
+import cmath
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -226,10 +227,25 @@ def _match_patterns(m, pos, vals):
     return hit
 
 
+_B4_CONST = {}
+
+
 def _b4(g: Gate):
     """Base 2x2 of a gate as four Python complex numbers (no numpy on the per-gate path)."""
-    B = g.base_matrix()
-    return complex(B[0, 0]), complex(B[0, 1]), complex(B[1, 0]), complex(B[1, 1])
+    from .ir import _CTRL_BASE, _ONEQ
+    name = _CTRL_BASE.get(g.name, g.name) if len(g.qubits) > 1 else g.name
+    if name == 'p':
+        return 1 + 0j, 0j, 0j, cmath.exp(1j * g.params[0])
+    if name == 'rz':
+        return cmath.exp(-0.5j * g.params[0]), 0j, 0j, cmath.exp(0.5j * g.params[0])
+    hit = _B4_CONST.get(name)
+    if hit is None:
+        if name not in _ONEQ:
+            B = g.base_matrix()
+            return complex(B[0, 0]), complex(B[0, 1]), complex(B[1, 0]), complex(B[1, 1])
+        B = _ONEQ[name]
+        hit = _B4_CONST[name] = (complex(B[0, 0]), complex(B[0, 1]), complex(B[1, 0]), complex(B[1, 1]))
+    return hit
 
 
 def _run_mux(run: List[Gate], zero_in: bool, tol=TOL):

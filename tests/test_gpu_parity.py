@@ -530,3 +530,53 @@ def test_release_mode_chain(precision):
         got = sum(v for k, v in counts.items() if k[N - 1 - qb] == '1') / 5e4
         assert abs(got - exact) < 5 * np.sqrt(exact * (1 - exact) / 5e4) + 1e-3
     sim.close(); full.close()
+
+
+def _free_gpu_bytes():
+    try:
+        import torch
+        return torch.cuda.mem_get_info()[0]
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(has_cuda() and _free_gpu_bytes() < 72 * 2 ** 30, reason='needs ~66 GiB of free device memory')
+def test_full_size_33_qubit_state():
+    """BASELINE config 3 at full size (33 total qubits, complex64, 32 stored qubits = 32 GiB): the
+    post-selected pmf and delta against brute-force enumeration (2^16 states), shot bookkeeping, and
+    the dense one-pass-per-clique schedule (33 stored qubits, 64 GiB, identity layout) against the
+    lazily materialised one."""
+    from qcmrf_b200 import workloads
+    C, N = workloads.named('q33')
+    assert N == 33
+    th = workloads.theta_for(C)
+    n = 16
+    pb, db, _ = mrf.brute_force_pmf(C, th)
+    sim = B200Simulator(precision='single', seed=2024, small_batch=False)
+    res = sim.run(QCMRF(C, th), shots=100000).result()
+    p, delta = res.postselected_probabilities()
+    assert abs(p.sum() - 1.0) < 1e-6
+    assert np.abs(p - pb).max() < 1e-5 and abs(delta - db) < 1e-5
+    assert np.argmax(p) == np.argmax(pb)
+    meta = res.metadata()
+    assert meta['n_phys'] == 32 and meta['passes'] == 5
+    counts = res.get_counts()
+    assert sum(counts.values()) == 100000
+    kept = 0
+    for k, v in counts.items():
+        assert len(k) == 33 and k[33 - 1 - n] == '0'                  # clbit n (scratch qubit) never written
+        if int(k, 2) < (1 << n):
+            kept += v
+    assert abs(kept / 1e5 - db) < 5 * np.sqrt(db * (1 - db) / 1e5) + 1e-4
+    # each ancilla's failure marginal: P(a_c = 1) = 2^-n sum_x sin^2(2 gamma_{c, x_c})
+    gam = program.theta_to_gamma(np.asarray(th))
+    for ii in (0, 7, 15):
+        want = float(np.mean(np.sin(2 * gam[4 * ii:4 * ii + 4]) ** 2))   # pair clique: 4 states, uniform x
+        got = sum(v for k, v in counts.items() if k[33 - 1 - (n + 1 + ii)] == '1') / 1e5
+        assert abs(got - want) < 5 * np.sqrt(want * (1 - want) / 1e5) + 1e-4
+    sim.close()
+    dense = B200Simulator(precision='single', fusion='clique', seed=2024, small_batch=False)
+    p2, d2 = dense.exact(QCMRF(C, th))
+    assert np.abs(p2 - pb).max() < 1e-5 and abs(d2 - db) < 1e-5
+    assert np.abs(p2 - p).max() < 2e-6
+    dense.close()
