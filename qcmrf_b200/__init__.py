@@ -9,6 +9,7 @@ from .circuit import AND, QuantumCircuit
 from .mrf import KL, QCMRF, extract_probs, fidelity
 from .transpile import transpile
 from .backend import B200Simulator, Counts, Job, Result
+from . import qasm, workloads
 
 __version__ = '0.1.0'
 
