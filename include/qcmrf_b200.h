@@ -40,6 +40,7 @@ extern "C" {
 #define QCM_ABI_VERSION 1
 #define QCM_MAX_CTRL 10      /* table-index qubits of one MUX1Q / DIAG op           */
 #define QCM_MAX_BLOCK 5      /* target qubits of one BLOCK pass (2^5 vectors/thread) */
+#define QCM_MAX_EXPAND 8     /* ... of a BLOCK pass whose qubits are all new (one MUX1Q each) */
 #define QCM_MAX_MEMBERS 16   /* MUX1Q members of one BLOCK pass                      */
 
 typedef struct qcm_sim_s *qcm_handle;

@@ -139,11 +139,12 @@ class B200Simulator:
     """Statevector backend on one B200.
 
     options: precision 'double'|'single'; fusion 'off'|'clique'|'blocked';
-    block_max 1..5 (targets per blocked pass); device; seed (None = fresh entropy, as
+    block_max 1..5 (targets per blocked pass), expand_max <= 8 (targets of a pass that only
+    materialises new qubits); device; seed (None = fresh entropy, as
     the unseeded Aer run of the reference)."""
 
     def __init__(self, name='qasm_simulator', device=0, precision='double', fusion='blocked', block_max=4,
-                 seed=None, small_batch=True, small_fusion='clique', width='full'):
+                 seed=None, small_batch=True, small_fusion='clique', width='full', expand_max=8):
         if fusion not in _FUSION_MODES:
             raise ValueError('fusion must be one of %r' % (_FUSION_MODES,))
         if width not in ('full', 'release'):
@@ -157,6 +158,7 @@ class B200Simulator:
         self.precision = precision
         self.fusion = fusion
         self.block_max = block_max
+        self.expand_max = expand_max          # width of passes that only materialise new qubits (<= 8)
         self.seed = seed
         self.small_batch = small_batch
         self.small_fusion = small_fusion      # batched small circuits: fused programs are ~30x shorter to plan and ship
@@ -191,7 +193,8 @@ class B200Simulator:
         if release:
             fc, virtual = fusion.split_releasable(fc, keep_below=n_vars or 0)
         lazy = (mode == 'blocked') and not small
-        pl = fusion.plan(fc, lazy=lazy, block_max=block_max or self.block_max, elide=elide)
+        pl = fusion.plan(fc, lazy=lazy, block_max=block_max or self.block_max, elide=elide,
+                         expand_max=max(block_max or self.block_max, self.expand_max) if block_max is None else block_max)
         pr = _Prepared()
         pr.prog, pr.fc, pr.plan = prog, fc, pl
         pr.name = prog.name

@@ -206,6 +206,9 @@ struct BlockPlan {
     bool expand = false;            // eligible for the expansion fast path
     ExpandTableArgs targs{};
     ExpandArgs eargs{};
+    bool tree = false;              // wide expansion: product-tree kernel
+    ExpandTreeArgs trargs{};
+    size_t tree_smem = 0;
     bool norm_preserving = false;   // expansion without diagonal members: sum_a |out[x,a]|^2 == |in[x]|^2
 };
 
@@ -213,7 +216,10 @@ struct BlockPlan {
 // tq: block qubits ascending.  Validates and fills `bp`; launches nothing.
 int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_mem, int n_in, int n_out,
                size_t n_tables, BlockPlan &bp) {
-    if (M < 1 || M > QCM_MAX_BLOCK) return fail(h, QCM_ERR_INVALID, "block of %d qubits unsupported (max %d)", M, QCM_MAX_BLOCK);
+    // a block whose qubits are all new (n_in .. n_in+M-1) may be wider than a general one
+    const bool all_new = (n_out - n_in == M) && M >= 1 && tq[0] == n_in;
+    const int max_m = all_new ? QCM_MAX_EXPAND : QCM_MAX_BLOCK;
+    if (M < 1 || M > max_m) return fail(h, QCM_ERR_INVALID, "block of %d qubits unsupported (max %d)", M, max_m);
     if (n_mem > QCM_MAX_MEMBERS) return fail(h, QCM_ERR_INVALID, "block has %d members (max %d)", n_mem, QCM_MAX_MEMBERS);
     if (n_out > h->n_local || n_in > n_out || n_in < 0) return fail(h, QCM_ERR_INVALID, "bad active range %d -> %d (n_local %d)", n_in, n_out, h->n_local);
     BlockArgs &a = bp.args;
@@ -228,13 +234,13 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     for (int j = 0; j < M; ++j) {
         if (tq[j] < 0 || tq[j] >= n_out) return fail(h, QCM_ERR_INVALID, "block qubit %d outside the active state (%d)", tq[j], n_out);
         if (j && tq[j] <= tq[j - 1]) return fail(h, QCM_ERR_INVALID, "block qubits must be strictly ascending");
-        a.tq[j] = tq[j];
+        if (j < QCM_MAX_BLOCK) a.tq[j] = tq[j];
     }
     for (int q = n_in; q < n_out; ++q)
         if (!std::binary_search(tq, tq + M, q))
             return fail(h, QCM_ERR_INVALID, "qubit %d is materialised by this op but is not one of its targets", q);
     size_t smem_reals = 0;
-    int per_target[QCM_MAX_BLOCK] = {0};
+    int per_target[QCM_MAX_EXPAND] = {0};
     int n_diag = 0;
     for (int g = 0; g < n_mem; ++g) {
         const qcm_op &op = members[g];
@@ -273,8 +279,38 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     if (bp.smem > 160 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "block coefficient tables need %zu B of shared memory", bp.smem);
 
     // expansion fast path: every block qubit is new (known |0>) and the target of exactly one member
-    bool expand = (n_out - n_in == M) && tq[0] == n_in;
+    bool expand = all_new;
     for (int j = 0; j < M && expand; ++j) expand = per_target[j] == 1;
+    if (M > QCM_MAX_BLOCK && !expand)
+        return fail(h, QCM_ERR_INVALID, "a block of %d qubits must materialise every one of them with exactly one MUX1Q", M);
+    // wide expansions (and ones whose index-qubit union overflows the precombined table) use the product tree
+    bool tree = expand && M >= kTreeLow && n_diag <= 4;
+    if (tree) {
+        ExpandTreeArgs &t = bp.trargs;
+        t.state = h->state;
+        t.tables = h->tab_real.p;
+        t.n_in = n_in;
+        t.M = M;
+        t.n_diag = 0;
+        t.ctrl_below_32 = a.ctrl_below_32;
+        t.rank_bits = rank_bits(h);
+        size_t off = 0;
+        for (int g = 0; g < n_mem; ++g) {
+            TreeMember &m = a.mem[g].pos < 0 ? t.diag[t.n_diag++] : t.mem[a.mem[g].pos];
+            m.n_ctrl = a.mem[g].n_ctrl;
+            for (int j = 0; j < m.n_ctrl; ++j) m.ctrl[j] = a.mem[g].ctrl[j];
+            m.low_bit = a.mem[g].low_bit;
+            m.src_off = a.mem[g].src_off;
+            m.tab_off = (int32_t)off;
+            off += (a.mem[g].pos < 0 ? 2ull : 4ull) << m.n_ctrl;
+            off = (off + 3) & ~size_t(3);
+        }
+        bp.tree_smem = off * real_sz;
+        if (bp.tree_smem > 160 * 1024) tree = false;
+    }
+    bp.tree = tree;
+    if (M > QCM_MAX_BLOCK && !tree)
+        return fail(h, QCM_ERR_UNSUPPORTED, "wide expansion of %d qubits cannot be served", M);
     if (expand) {
         // union of the members' index qubits, ascending: the qubits that differ between the lanes
         // of a warp get the low cidx bits (conflict-free shared loads), qubit 0 gets bit 0
@@ -287,7 +323,7 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
                 if (std::find(cu, cu + nu, c) == cu + nu) cu[nu++] = c;
             }
         std::sort(cu, cu + nu);
-        if (nu + M > kExpandMaxBits) expand = false;
+        if (nu + M > kExpandMaxBits || M > QCM_MAX_BLOCK) expand = false;
         for (int g = 0; g < n_mem && expand; ++g) {
             t.mpos[g] = a.mem[g].pos;
             t.mnc[g] = a.mem[g].n_ctrl;
@@ -306,8 +342,10 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
             e.rank_bits = rank_bits(h);
         }
     }
+    if (expand && tree && M >= 5) expand = false;             // M <= 4: the precombined table wins; wider: the tree
+    if (expand) bp.tree = false;
     bp.expand = expand;
-    bp.norm_preserving = expand && n_diag == 0;
+    bp.norm_preserving = (expand || bp.tree) && n_diag == 0;
     return QCM_OK;
 }
 
@@ -315,7 +353,28 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
     const BlockArgs &a = bp.args;
     const int M = bp.M, n_in = a.n_in, n_out = a.n_out;
     int rc;
-    if (bp.expand) {
+    if (bp.tree) {
+        const int V = (h->prec == QCM_C64 && n_in >= 1) ? 2 : 1;
+        const int threads = bp.trargs.tree_out ? (1 << kChunkBits) / V : 256;     // fused tree: tile == chunk
+        const uint64_t nvec = (1ull << n_in) / V;
+        const uint64_t grid = std::min<uint64_t>(std::max<uint64_t>(1, (nvec + threads - 1) / threads), 0x7fffffffull);
+        const size_t smem = bp.tree_smem;
+        if (h->prec == QCM_C64) {
+            if (V == 2) {
+                if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k_expand_tree<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_expand_tree<float, 2><<<(unsigned)grid, threads, smem, h->stream>>>(bp.trargs);
+            } else {
+                if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k_expand_tree<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_expand_tree<float, 1><<<(unsigned)grid, threads, smem, h->stream>>>(bp.trargs);
+            }
+        } else {
+            if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k_expand_tree<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_expand_tree<double, 1><<<(unsigned)grid, threads, smem, h->stream>>>(bp.trargs);
+        }
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+        h->n_expand++;
+    } else if (bp.expand) {
         const size_t centry = h->prec == QCM_C64 ? 8 : 16;
         const size_t nent = 1ull << (M + bp.targs.nu);
         if ((rc = ensure(h, h->ctab, nent * centry))) return rc;
@@ -746,7 +805,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 } else {
                     const int M = op.target;
                     n_mem = op.n_ctrl;
-                    if (M < 1 || M > QCM_MAX_BLOCK) return fail(h, QCM_ERR_INVALID, "op %d: block of %d qubits (max %d)", i, M, QCM_MAX_BLOCK);
+                    if (M < 1 || M > QCM_MAX_EXPAND) return fail(h, QCM_ERR_INVALID, "op %d: block of %d qubits (max %d)", i, M, QCM_MAX_EXPAND);
                     if (n_mem < 0 || i + n_mem > n_ops - 1) return fail(h, QCM_ERR_INVALID, "op %d: block members run past the program", i);
                     if ((rc = plan_block(h, op.ctrl, M, ops + i + 1, n_mem, op.n_active_in, op.n_active_out, n_tables, bp))) return rc;
                 }
@@ -756,20 +815,23 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 const bool last = (i + (op.kind == QCM_OP_BLOCK ? n_mem : 0)) == n_ops - 1;
                 bool checkpoint = last && (op.flags & QCM_FLAG_SAMPLE_CHECKPOINT) && bp.norm_preserving &&
                                   op.n_active_in >= kChunkBits;
+                int sub_bits = 0;
                 if (checkpoint) {
                     // level 0 of the tree: fused into the expansion pass (it reads every input amplitude
-                    // anyway); a generic block pass cannot be norm-preserving, so bp.expand holds here
-                    const int sub_bits = h->prec == QCM_C64 ? 6 : 5;           // one warp's vectors: 32 * V amplitudes
+                    // anyway); a generic block pass cannot be norm-preserving, so an expansion kernel runs here.
+                    // Finer level: per warp (table kernel) or per vector (tree kernel, whose input is small).
+                    const int vbits = (h->prec == QCM_C64) ? 1 : 0;
+                    sub_bits = bp.tree ? vbits : vbits + 5;
                     if ((rc = tree_layout(h, op.n_active_in))) return rc;
                     if ((rc = ensure(h, h->subtree, sizeof(double) << (op.n_active_in - sub_bits)))) return rc;
-                    bp.eargs.tree_out = h->tree_ptr[0];
-                    bp.eargs.sub_out = (double *)h->subtree.p;
+                    bp.eargs.tree_out = bp.trargs.tree_out = h->tree_ptr[0];
+                    bp.eargs.sub_out = bp.trargs.sub_out = (double *)h->subtree.p;
                 }
                 if ((rc = launch_block_plan(h, bp))) return rc;
                 if (checkpoint) {
                     if ((rc = tree_finish(h, op.n_active_in))) return rc;
                     h->tree_cond_bits = bp.M;
-                    h->tree_sub_bits = h->prec == QCM_C64 ? 6 : 5;
+                    h->tree_sub_bits = sub_bits;
                     h->tree_for_active = op.n_active_out;
                     h->n_checkpoint++;
                     keep_tree = true;

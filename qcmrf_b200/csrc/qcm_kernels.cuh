@@ -440,6 +440,187 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
 }
 
 // ----------------------------------------------------------------------------------
+// Wide expansion pass (5..QCM_MAX_EXPAND new qubits): product tree instead of a precombined table.
+//
+//     out[x | a << n_in] = in[x] * prod_d diag_d[idx_d(x)] * prod_j f_j[a_j],   f_j[a] = table_j[idx_j(x)][a][0]
+//
+// A thread reads one vector of V input amplitudes, looks up the 2M factors once (the member tables
+// are tiny and live in shared memory) and walks the 2^M outputs as a product tree: the low ML levels
+// are unrolled (one complex multiply per tree node, stores in ascending address order), the high
+// M-ML levels are a loop with a short multiply chain per iteration.  ~2 complex multiplies per
+// output instead of 1, but no 2^(M+nu)-entry table, so M is only limited by the register file; a
+// 16-ancilla circuit becomes two passes and the intermediate levels all but vanish from the byte
+// count (34 qubits: 77.9 GB -> 69.5 GB per circuit).  2^M write streams per thread are fine as long
+// as tiles are handed out in address order (tools/membench3.cu: 6.3-6.7 TB/s for 16..256 streams).
+// ----------------------------------------------------------------------------------
+constexpr int kTreeLow = 4;                     // unrolled levels
+
+struct TreeMember {
+    int8_t n_ctrl;
+    int8_t ctrl[QCM_MAX_CTRL];
+    uint16_t low_bit;               // table-index bit fed by qubit 0
+    int32_t tab_off;                // reals, in shared memory: per index 4 reals (f0.re f0.im f1.re f1.im); diag: 2
+    int32_t src_off;                // reals, in the program's tables (8 per index; diag: 2)
+};
+
+struct ExpandTreeArgs {
+    void *state;
+    const void *tables;             // device, state's real type
+    int32_t n_in, M, n_diag;
+    int32_t ctrl_below_32;
+    uint64_t rank_bits;
+    double *tree_out;               // see ExpandArgs
+    double *sub_out;                // per-vector |in|^2 sums (the sampler's finest level)
+    TreeMember mem[QCM_MAX_EXPAND]; // member j targets qubit n_in + j
+    TreeMember diag[4];
+};
+
+template <typename R> struct CplxOf { using T = float2; };
+template <> struct CplxOf<double> { using T = double2; };
+
+template <typename R, int V, int L>
+struct TreeEmit {
+    using C2 = typename CplxOf<R>::T;
+    // p: partial product for the levels above L; f[l][a][v]: factor of level l; r: output index bits above level L
+    static __device__ __forceinline__ void run(void *state, uint64_t base, uint64_t ostride, const R (&pr)[V], const R (&pi)[V],
+                                               const R (&fr)[kTreeLow][2][V], const R (&fi)[kTreeLow][2][V], uint32_t r) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            R qr[V], qi[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                qr[v] = pr[v] * fr[L - 1][a][v] - pi[v] * fi[L - 1][a][v];
+                qi[v] = pr[v] * fi[L - 1][a][v] + pi[v] * fr[L - 1][a][v];
+            }
+            TreeEmit<R, V, L - 1>::run(state, base, ostride, qr, qi, fr, fi, r | ((uint32_t)a << (L - 1)));
+        }
+    }
+};
+template <typename R, int V>
+struct TreeEmit<R, V, 0> {
+    static __device__ __forceinline__ void run(void *state, uint64_t base, uint64_t ostride, const R (&pr)[V], const R (&pi)[V],
+                                               const R (&)[kTreeLow][2][V], const R (&)[kTreeLow][2][V], uint32_t r) {
+        VecIO<R, V>::store(state, base + (uint64_t)r * ostride, pr, pi);
+    }
+};
+
+template <typename R, int V>
+__global__ void __launch_bounds__(kExpandThreadsMax) k_expand_tree(const __grid_constant__ ExpandTreeArgs a) {
+    using IO = VecIO<R, V>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tab = reinterpret_cast<R *>(smem_raw);
+    const R *gt = reinterpret_cast<const R *>(a.tables);
+    for (int j = 0; j < a.M; ++j) {                       // column 0 of every 2x2: (m00, m10)
+        const int n = 1 << a.mem[j].n_ctrl;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const R *src = gt + a.mem[j].src_off + 8 * i;
+            R *dst = tab + a.mem[j].tab_off + 4 * i;
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[4]; dst[3] = src[5];
+        }
+    }
+    for (int d = 0; d < a.n_diag; ++d) {
+        const int n = 2 << a.diag[d].n_ctrl;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tab[a.diag[d].tab_off + i] = gt[a.diag[d].src_off + i];
+    }
+    __syncthreads();
+
+    const uint64_t nvec = (1ull << a.n_in) / V;
+    const uint64_t ostride = 1ull << a.n_in;
+    const int MH = a.M - kTreeLow;                        // >= 1
+    auto index_of = [&](const TreeMember &m, uint64_t gi) -> uint32_t {
+        uint32_t idx = 0;
+        if (a.ctrl_below_32) {
+            const uint32_t lo = (uint32_t)gi;
+            for (int j = 0; j < m.n_ctrl; ++j) idx |= ((lo >> m.ctrl[j]) & 1u) << j;
+        } else {
+            for (int j = 0; j < m.n_ctrl; ++j) idx |= (uint32_t)((gi >> m.ctrl[j]) & 1ull) << j;
+        }
+        return idx;
+    };
+    // one tile (blockDim vectors) per CTA, in launch = address order
+    for (uint64_t tile = blockIdx.x; tile * blockDim.x < nvec; tile += gridDim.x) {
+        const uint64_t bv = tile * blockDim.x + threadIdx.x;
+        const bool ok = bv < nvec;
+        const uint64_t b = bv * V;
+        const uint64_t gi = b | a.rank_bits;
+        R xr[V], xi[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { xr[v] = R(0); xi[v] = R(0); }
+        if (ok) IO::load(a.state, b, xr, xi);
+        if (a.tree_out) {
+            __shared__ double s_w[32];
+            double w = 0.0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) w += (double)xr[v] * (double)xr[v] + (double)xi[v] * (double)xi[v];
+            if (ok) a.sub_out[bv] = w;
+            w = warp_sum(w);
+            if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = w;
+            __syncthreads();
+            if (threadIdx.x == 0 && tile < (nvec * V) >> kChunkBits) {
+                double t = 0.0;
+                for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_w[i];
+                a.tree_out[tile] = t;
+            }
+            __syncthreads();
+        }
+        if (!ok) continue;
+        for (int d = 0; d < a.n_diag; ++d) {
+            const uint32_t i0 = index_of(a.diag[d], gi);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint32_t idx = v ? (i0 | a.diag[d].low_bit) : i0;
+                const R c = tab[a.diag[d].tab_off + 2 * idx], sn = tab[a.diag[d].tab_off + 2 * idx + 1];
+                const R x = xr[v], y = xi[v];
+                xr[v] = c * x - sn * y;
+                xi[v] = c * y + sn * x;
+            }
+        }
+        // factors of the unrolled low levels
+        R fr[kTreeLow][2][V], fi[kTreeLow][2][V];
+#pragma unroll
+        for (int l = 0; l < kTreeLow; ++l) {
+            const uint32_t i0 = index_of(a.mem[l], gi);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint32_t idx = v ? (i0 | a.mem[l].low_bit) : i0;
+                const R *f = tab + a.mem[l].tab_off + 4 * idx;
+                fr[l][0][v] = f[0]; fi[l][0][v] = f[1]; fr[l][1][v] = f[2]; fi[l][1][v] = f[3];
+            }
+        }
+        // table entries of the high levels (at most QCM_MAX_EXPAND - kTreeLow of them)
+        uint32_t hidx[QCM_MAX_EXPAND - kTreeLow][V];
+#pragma unroll
+        for (int l = 0; l < QCM_MAX_EXPAND - kTreeLow; ++l) {
+            if (l < MH) {
+                const uint32_t i0 = index_of(a.mem[kTreeLow + l], gi);
+#pragma unroll
+                for (int v = 0; v < V; ++v) hidx[l][v] = v ? (i0 | a.mem[kTreeLow + l].low_bit) : i0;
+            }
+        }
+        for (uint32_t rh = 0; rh < (1u << MH); ++rh) {
+            R pr[V], pi[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) { pr[v] = xr[v]; pi[v] = xi[v]; }
+#pragma unroll
+            for (int l = 0; l < QCM_MAX_EXPAND - kTreeLow; ++l) {
+                if (l < MH) {
+                    const int bit = (rh >> l) & 1u;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const R *f = tab + a.mem[kTreeLow + l].tab_off + 4 * hidx[l][v] + 2 * bit;
+                        const R c = f[0], sn = f[1];
+                        const R x = pr[v], y = pi[v];
+                        pr[v] = c * x - sn * y;
+                        pi[v] = c * y + sn * x;
+                    }
+                }
+            }
+            TreeEmit<R, V, kTreeLow>::run(a.state, b + ((uint64_t)rh << (a.n_in + kTreeLow)), ostride, pr, pi, fr, fi, 0u);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
 // Diagonal pass: amp *= table[index bits]
 // ----------------------------------------------------------------------------------
 struct DiagArgs {
@@ -795,20 +976,15 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
                 return t.x * t.x + t.y * t.y;
             }
         };
+        // leaf: the remaining x's, each with its 2^cond_bits images -- one flat, lane-strided search over
+        // the (x, image) pairs (image-major, so that consecutive lanes read consecutive amplitudes)
         uint64_t within;
-        if (a.cond_bits == 0) {
-            within = warp_pick([&](uint32_t i) { return amp_w(afirst + i); }, leaf_cnt, u, lane);
-        } else {
-            const uint32_t x = warp_pick(
-                [&](uint32_t i) {
-                    double sacc = 0.0;
-                    for (int br = 0; br < nb; ++br) sacc += amp_w(afirst + i + ((uint64_t)br << a.n_active));
-                    return sacc;
-                },
-                leaf_cnt, u, lane);
-            const uint32_t br = warp_pick([&](uint32_t i) { return amp_w(afirst + x + ((uint64_t)i << a.n_active)); },
-                                          (uint32_t)nb, u, lane);
-            within = (uint64_t)x + ((uint64_t)br << a.n_active);
+        {
+            const uint32_t lbits = 31u - (uint32_t)__clz(leaf_cnt);
+            const uint32_t c = warp_pick(
+                [&](uint32_t i) { return amp_w(afirst + (i & (leaf_cnt - 1u)) + ((uint64_t)(i >> lbits) << a.n_active)); },
+                leaf_cnt * (uint32_t)nb, u, lane);
+            within = (uint64_t)(c & (leaf_cnt - 1u)) + ((uint64_t)(c >> lbits) << a.n_active);
         }
         if (lane == 0) {
             const uint64_t gi = (afirst + within) | a.rank_bits;

@@ -37,7 +37,7 @@ from .ir import Gate, Program
 TOL = 1e-9
 
 QCM_OP_INIT_PRODUCT, QCM_OP_MUX1Q, QCM_OP_DIAG, QCM_OP_BLOCK, QCM_OP_SWAP, QCM_OP_EXTEND = 1, 2, 3, 4, 5, 6
-QCM_MAX_CTRL, QCM_MAX_BLOCK, QCM_MAX_MEMBERS = 10, 5, 16
+QCM_MAX_CTRL, QCM_MAX_BLOCK, QCM_MAX_MEMBERS, QCM_MAX_EXPAND = 10, 5, 16, 8
 
 
 @dataclass
@@ -627,14 +627,18 @@ def control_only_qubits(fc: FusedCircuit) -> List[int]:
 
 
 def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optional[bool] = None,
-         keep_order: bool = False, n_global: int = 0) -> Plan:
+         keep_order: bool = False, n_global: int = 0, expand_max: int = QCM_MAX_EXPAND) -> Plan:
     """Lay the fused circuit out for the engine.
 
     lazy=False  : identity layout, every qubit materialised up front, one pass per
                   fused op (the plain in-place "gate pass" execution, Aer-like width).
     lazy=True   : first-use layout, lazy materialisation, BLOCK passes of up to
-                  ``block_max`` targets; never-materialised qubits are not stored
-                  unless elide=False.
+                  ``block_max`` targets -- up to ``expand_max`` when every target of the pass is
+                  a new qubit materialised by exactly one sweep (an "expansion" pass: wider is
+                  better, the intermediate states all but vanish from the byte count); in a run
+                  of such sweeps the FIRST pass takes the remainder so that the last, largest
+                  state is written by a full-width pass.  Never-materialised qubits are not
+                  stored unless elide=False.
     n_global=g  : (lazy only) the g highest-numbered control-only qubits are laid out on the g
                   highest physical positions, to be held by the rank index of a 2^g-way
                   sharded state; raises ValueError if the circuit has fewer than g of them.
@@ -717,7 +721,25 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
         pend, pend_targets = [], []
         pend_in = active
 
-    for op in fc.ops:
+    # expansion sweeps: a mux whose target has not been stored or used before it (lazy layouts only)
+    n_ops = len(fc.ops)
+    is_exp = [False] * n_ops
+    if lazy:
+        seen_q = set(fc.init)
+        for k, op in enumerate(fc.ops):
+            if op.kind == 'mux' and op.zero_in and op.target not in seen_q:
+                is_exp[k] = True
+            seen_q.update(op.ctrls)
+            if op.kind == 'mux':
+                seen_q.add(op.target)
+    run_left = [0] * (n_ops + 1)                   # expansion sweeps from k to the end of their run
+    for k in range(n_ops - 1, -1, -1):
+        run_left[k] = run_left[k + 1] + 1 if is_exp[k] else 0
+    emax = max(block_max, min(expand_max, QCM_MAX_EXPAND)) if lazy else 1
+    pend_exp = True                                # every pending member is an expansion sweep
+    exp_limit = emax
+
+    for k, op in enumerate(fc.ops):
         if op.kind == 'diag':
             flush()
             ctrl = tuple(layout[q] for q in op.ctrls)
@@ -734,15 +756,28 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
             expected = active + sum(1 for x in pend_targets if x >= active)
             if t != expected:
                 raise AssertionError('layout/materialisation order mismatch: target %d, expected %d' % (t, expected))
-        limit = block_max if lazy else 1
         new_targets = set(pend_targets) | {t}
+        wide = pend_exp and is_exp[k] and t not in pend_targets
+        if not lazy:
+            limit = 1
+        elif wide:
+            limit = exp_limit
+        else:
+            limit = block_max
         conflict = (len(new_targets) > limit or len(pend) >= QCM_MAX_MEMBERS or
                     any(c in new_targets for c in ctrl) or
-                    any(t in pc for _, pc, _ in pend))
+                    any(t in pc for _, pc, _ in pend) or
+                    (pend and not wide and len(pend_targets) > block_max))
         if conflict:
             flush()
         if not pend:
             pend_in = active
+            pend_exp = True
+            # start of a pass inside a run of expansion sweeps: the first pass of the run takes the remainder
+            exp_limit = emax
+            if is_exp[k] and (k == 0 or not is_exp[k - 1]) and run_left[k] > emax and run_left[k] % emax:
+                exp_limit = run_left[k] % emax
+        pend_exp = pend_exp and is_exp[k] and t not in pend_targets
         off = em.table(_mux_table_f64(op.table))
         pend.append((t, ctrl, off))
         if t not in pend_targets:

@@ -319,7 +319,7 @@ class ShardedSimulator:
     what bench.py and the tests use: prepare / execute / run / exact / close."""
 
     def __init__(self, precision='single', fusion='blocked', block_max=4, device=0, seed=None, group=None,
-                 staging_bytes=1 << 30, name='qasm_simulator', layout='auto'):
+                 staging_bytes=1 << 30, name='qasm_simulator', layout='auto', expand_max=8):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -332,6 +332,7 @@ class ShardedSimulator:
         self.precision = precision
         self.fusion = fusion
         self.block_max = block_max
+        self.expand_max = expand_max
         self.device = device
         self.seed = seed
         self.staging_bytes = int(staging_bytes)
@@ -388,7 +389,8 @@ class ShardedSimulator:
         ng = 0
         if lazy and self.layout == 'auto' and len(fusion.control_only_qubits(fc)) >= self.g:
             ng = self.g
-        pl = fusion.plan(fc, lazy=lazy, block_max=self.block_max, n_global=ng)
+        pl = fusion.plan(fc, lazy=lazy, block_max=self.block_max, n_global=ng,
+                         expand_max=max(self.block_max, self.expand_max))
         sp = shard_plan(pl, self.g, self.rank)
         pr = _ShardPrepared()
         pr.prog, pr.fc, pr.plan, pr.sp, pr.name = prog, fc, pl, sp, prog.name

@@ -70,7 +70,11 @@ def run_plan(plan, n_global=0, rank=0, n_local=None, psi0=None, active0=0):
                 M, n_mem = int(op['target']), int(op['n_ctrl'])
                 tq = [int(x) for x in op['ctrl'][:M]]
                 members = [ops[i + 1 + g] for g in range(n_mem)]
-                assert M <= F.QCM_MAX_BLOCK and n_mem <= F.QCM_MAX_MEMBERS
+                wide_ok = tq == list(range(n_in, n_out))            # every block qubit new: up to QCM_MAX_EXPAND
+                assert M <= (F.QCM_MAX_EXPAND if wide_ok else F.QCM_MAX_BLOCK) and n_mem <= F.QCM_MAX_MEMBERS
+                if M > F.QCM_MAX_BLOCK:
+                    per = [sum(1 for mb in members if int(mb['kind']) == F.QCM_OP_MUX1Q and int(mb['target']) == q) for q in tq]
+                    assert per == [1] * M, 'a wide block needs exactly one MUX1Q per qubit'
                 assert tq == sorted(set(tq))
             else:
                 tq, members = [int(op['target'])], [op]

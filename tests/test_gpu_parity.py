@@ -69,12 +69,14 @@ def test_all_fixture_models_batched(models, aer_counts, precision):
 
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
-@pytest.mark.parametrize('fusion_mode,block_max', [('off', 1), ('clique', 1), ('blocked', 1), ('blocked', 2),
-                                                   ('blocked', 4), ('blocked', 5)])
-def test_statevector_path_all_modes(models, precision, fusion_mode, block_max):
+@pytest.mark.parametrize('fusion_mode,block_max,expand_max', [('off', 1, 1), ('clique', 1, 1), ('blocked', 1, 1),
+                                                              ('blocked', 2, 2), ('blocked', 4, 4), ('blocked', 5, 5),
+                                                              ('blocked', 4, 8), ('blocked', 2, 6)])
+def test_statevector_path_all_modes(models, precision, fusion_mode, block_max, expand_max):
     """The large-state kernels (init, blocked multiplexer pass, diag, lazy materialisation) on
     the fixture models: full statevector vs the oracle's gate-by-gate execution."""
-    sim = B200Simulator(precision=precision, fusion=fusion_mode, block_max=block_max, small_batch=False, seed=7)
+    sim = B200Simulator(precision=precision, fusion=fusion_mode, block_max=block_max, expand_max=expand_max,
+                        small_batch=False, seed=7)
     worst = 0.0
     for scale, j, i, C, th in all_models(models):
         if i not in (0, 7):
@@ -382,7 +384,7 @@ def test_mid_size_tree_mrf_properties():
     assert circ.num_qubits == 26
     pb, db, _ = mrf.brute_force_pmf(cliques, th)
     for bm in (4, 5):
-        sim = B200Simulator(precision='single', fusion='blocked', block_max=bm, seed=1)
+        sim = B200Simulator(precision='single', fusion='blocked', block_max=bm, expand_max=bm, seed=1)
         res = sim.run(circ, shots=10000).result()
         p, delta = res.postselected_probabilities(0)
         assert np.abs(p - pb).max() < 1e-5 and abs(delta - db) < 1e-5
@@ -447,7 +449,8 @@ def _expansion_program(rng, n0, Ms, with_diag, flags_last):
 @pytest.mark.parametrize('with_diag', [False, True])
 def test_expansion_fast_path(precision, with_diag):
     rng = np.random.RandomState(77)
-    for n0, Ms in ((1, [1, 2, 3]), (3, [4, 5]), (2, [5, 1, 4]), (6, [3, 3, 2]), (0, [2, 2])):
+    for n0, Ms in ((1, [1, 2, 3]), (3, [4, 5]), (2, [5, 1, 4]), (6, [3, 3, 2]), (0, [2, 2]),
+                   (3, [6, 8]), (2, [7, 4]), (5, [8, 5]), (0, [8]), (1, [8, 8])):
         ops, tabs, act = _expansion_program(rng, n0, Ms, with_diag, False)
         with _native.Handle(act, precision) as h:
             h.set_amplitudes(np.full(1 << act, np.nan + 1j * np.nan), 0, n_active=0)
@@ -460,12 +463,13 @@ def test_expansion_fast_path(precision, with_diag):
 
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
-def test_sampling_checkpoint_matches_full_tree(precision):
+@pytest.mark.parametrize('Ms', [[3, 4], [2, 8], [7]])
+def test_sampling_checkpoint_matches_full_tree(precision, Ms):
     """Shots drawn through the checkpoint tree (built before the final expansion pass, new
     qubits sampled conditionally) follow the same distribution as shots drawn from a tree
     over the whole result."""
     rng = np.random.RandomState(5)
-    n0, Ms = 11, [3, 4]
+    n0 = 11
     ops, tabs, act = _expansion_program(rng, n0, Ms, False, True)
     assert ops['flags'].sum() == 1
     S = 400000
@@ -482,9 +486,17 @@ def test_sampling_checkpoint_matches_full_tree(precision):
     # the two trees order the outcomes differently (x-major vs index order), so the same uniforms
     # give different shots: compare both histograms with the exact distribution
     assert not np.array_equal(a, b)
+    idx = np.arange(1 << act)
+    M = Ms[-1]
     for keys in (a, b):
-        emp = np.bincount(keys.astype(np.int64), minlength=1 << act) / S
+        k = keys.astype(np.int64)
+        emp = np.bincount(k, minlength=1 << act) / S
         assert 0.5 * np.abs(emp - pr / pr.sum()).sum() < weissman_tv_bound(int((pr > 0).sum()), S)
+        # sharper: marginals over the qubits of the final pass (drawn conditionally) and over the low 8 qubits
+        for shift, bits in ((act - M, M), (0, 8), (act - M - 3, 6)):
+            want = np.bincount((idx >> shift) & ((1 << bits) - 1), weights=pr / pr.sum(), minlength=1 << bits)
+            got = np.bincount((k >> shift) & ((1 << bits) - 1), minlength=1 << bits) / S
+            assert 0.5 * np.abs(got - want).sum() < weissman_tv_bound(1 << bits, S)
 
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
@@ -559,7 +571,7 @@ def test_full_size_33_qubit_state():
     assert np.abs(p - pb).max() < 1e-5 and abs(delta - db) < 1e-5
     assert np.argmax(p) == np.argmax(pb)
     meta = res.metadata()
-    assert meta['n_phys'] == 32 and meta['passes'] == 5
+    assert meta['n_phys'] == 32 and meta['passes'] == 3             # init + two 8-qubit expansion passes
     counts = res.get_counts()
     assert sum(counts.values()) == 100000
     kept = 0

@@ -220,11 +220,21 @@ def test_plan_limits_are_respected(models):
     th = models['0.1']['THETAS']['3'][0]
     fc = fusion.fuse(ir.lower(QCMRF(C, th)), 'clique')
     for bm in (1, 2, 3, 4, 5):
-        pl = fusion.plan(fc, lazy=True, block_max=bm)
+        pl = fusion.plan(fc, lazy=True, block_max=bm, expand_max=bm)
         for op in pl.ops:
             if op['kind'] == fusion.QCM_OP_BLOCK:
                 assert op['target'] <= bm and op['n_ctrl'] <= fusion.QCM_MAX_MEMBERS
         assert pl.n_passes == 1 + -(-len(C) // bm)
+        wide = fusion.plan(fc, lazy=True, block_max=bm)              # expansion passes may be wider
+        for op in wide.ops:
+            if op['kind'] == fusion.QCM_OP_BLOCK:
+                assert op['target'] <= fusion.QCM_MAX_EXPAND and op['n_ctrl'] <= fusion.QCM_MAX_MEMBERS
+        assert wide.n_passes == 2                                   # init + one pass for all 4 ancillas
+    # remainder-first sizing: 18 expansion sweeps -> passes of 2, 8, 8 targets
+    from qcmrf_b200 import workloads
+    C37, _ = workloads.named('q37')
+    pl = fusion.plan(fusion.fuse(ir.lower(QCMRF(C37, workloads.theta_for(C37))), 'clique'), lazy=True, block_max=4)
+    assert [int(op['target']) for op in pl.ops if op['kind'] == fusion.QCM_OP_BLOCK] == [2, 8, 8]
 
 
 def test_release_mode_on_the_emulator(monkeypatch, models):
