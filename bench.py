@@ -118,26 +118,32 @@ def cpu_reference(target_cliques, steps=1, warmup=0, sample_vars=None):
     cores = len(os.sched_getaffinity(0))
     os.environ.setdefault('OMP_NUM_THREADS', str(cores))
     n_t, k_t, N_t, _ = program.sizes(target_cliques)
-    if sample_vars is None:
-        sample_vars = 12 if cores < 32 else 13
-    Cs = workloads.random_tree(sample_vars, 0)
-    ths = workloads.theta_for(Cs)
-    n_s, k_s, N_s, _ = program.sizes(Cs)
-    ops_s, _ = program.qcmrf_program(Cs, ths)
-    arr, n_ops, meas = cbridge.compile_unfused(ops_s)
     ops_t, _ = program.qcmrf_program(target_cliques, workloads.theta_for(target_cliques))
     g_t = sum(1 for g in ops_t if g[0] not in ('measure', 'barrier'))
-    mask = ((1 << N_s) - 1) & ~((1 << n_s) - 1)
-    times = []
-    for it in range(warmup + steps):
+
+    def one(nv, seed):
+        Cs = workloads.random_tree(nv, 0)
+        n_s, k_s, N_s, _ = program.sizes(Cs)
+        ops_s, _ = program.qcmrf_program(Cs, workloads.theta_for(Cs))
+        arr, n_ops, meas = cbridge.compile_unfused(ops_s)
+        mask = ((1 << N_s) - 1) & ~((1 << n_s) - 1)
         t0 = time.perf_counter()
         psi = cbridge.run(N_s, arr, n_ops)
         cbridge.postselect(N_s, psi, mask, 0, n_s)
-        cbridge.sample(N_s, psi, SHOTS, 1984 + it)
+        cbridge.sample(N_s, psi, SHOTS, seed)
         dt = time.perf_counter() - t0
+        del psi
+        return dt, n_s, N_s, n_ops
+
+    if sample_vars is None:
+        # size the sample for about 10-30 s of CPU work: a 12-variable probe, then +1 variable = x4.4
+        t12 = one(12, 1)[0]
+        sample_vars = int(min(14, max(12, 12 + np.floor(np.log(max(15.0 / t12, 1.0)) / np.log(4.4)))))
+    times = []
+    for it in range(warmup + steps):
+        dt, n_s, N_s, n_ops = one(sample_vars, 1984 + it)
         if it >= warmup:
             times.append(dt)
-        del psi
     t_s = float(np.mean(times))
     scale = (g_t * 2.0 ** N_t) / (n_ops * 2.0 ** N_s)
     t_target = t_s * scale
