@@ -49,7 +49,8 @@ struct qcm_sim_s {
     int tree_for_active = -1;       // n_active of the state the tree describes
     int tree_base_bits = 0;         // qubits the tree indexes (tree_for_active - tree_cond_bits)
     int tree_cond_bits = 0;         // expansion qubits materialised after the tree was built
-    int tree_sub_bits = 0;          // > 0: subtree holds sums over 2^tree_sub_bits amplitudes (fused checkpoint only)
+    int tree_sub_bits = 0;          // subtree holds sums over 2^tree_sub_bits amplitudes ...
+    bool tree_has_sub = false;      // ... when this is set (fused checkpoint only)
     uint64_t n_expand = 0, n_checkpoint = 0;
     double local_mass = 0.0;
     bool tree_valid = false;
@@ -604,6 +605,7 @@ int tree_finish(qcm_handle h, int na) {
     h->tree_base_bits = na;
     h->tree_cond_bits = 0;
     h->tree_sub_bits = 0;
+    h->tree_has_sub = false;
     return QCM_OK;
 }
 
@@ -832,6 +834,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                     if ((rc = tree_finish(h, op.n_active_in))) return rc;
                     h->tree_cond_bits = bp.M;
                     h->tree_sub_bits = sub_bits;
+                    h->tree_has_sub = true;
                     h->tree_for_active = op.n_active_out;
                     h->n_checkpoint++;
                     keep_tree = true;
@@ -960,7 +963,7 @@ int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t str
     a.state = h->state;
     a.n_active = h->tree_base_bits;
     a.cond_bits = h->tree_cond_bits;
-    a.sub = h->tree_sub_bits ? (const double *)h->subtree.p : nullptr;
+    a.sub = h->tree_has_sub ? (const double *)h->subtree.p : nullptr;
     a.sub_bits = h->tree_sub_bits;
     a.n_levels = h->tree_levels;
     for (int l = 0; l < h->tree_levels; ++l) {
