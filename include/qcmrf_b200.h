@@ -168,6 +168,18 @@ int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t str
                        const int32_t *clbit_qubit, int n_clbits,
                        uint64_t *keys_out, uint8_t *mine_out);
 
+/* Device-resident variants for callers that continue on the GPU (the sharded executor all-gathers
+ * pmf blocks and all-reduces keys with NCCL): the outputs are DEVICE pointers, written in stream
+ * order on the handle's stream; nothing is copied to the host and nothing synchronises.
+ * dev_probs_out: 2^n_out_bits doubles (may be NULL), dev_kept_out: 1 double;
+ * dev_keys_out: `shots` uint64, dev_mine_out: `shots` bytes.                                    */
+int qcm_postselect_device(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits,
+                          void *dev_probs_out, void *dev_kept_out);
+int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id,
+                              const double *rank_masses, int n_ranks,
+                              const int32_t *clbit_qubit, int n_clbits,
+                              void *dev_keys_out, void *dev_mine_out);
+
 /* Batched small circuits (all fixture-sized models in one launch: one thread block
  * per circuit, state resident in shared memory, program + post-selection + sampling
  * fused).  Circuit c has n_qubits[c] <= qcm_small_max_qubits(precision) qubits, ops

@@ -37,7 +37,8 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_set_shard', 'qcm_get_amplitudes', 'qcm_set_amplitudes', 'qcm_synchronize',
            'qcm_run_program', 'qcm_postselect', 'qcm_sample', 'qcm_sample_prepare', 'qcm_sample_sharded',
            'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
-           'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile']
+           'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile', 'qcm_postselect_device',
+           'qcm_sample_sharded_device']
 
 
 def lib():
@@ -73,6 +74,8 @@ def lib():
     L.qcm_get_active.argtypes = [vp, ctypes.POINTER(i32)]
     L.qcm_get_timing.argtypes = [vp, ctypes.POINTER(QcmTiming)]
     L.qcm_get_op_profile.argtypes = [vp, i32, vp, vp, vp, vp, ctypes.POINTER(i32)]
+    L.qcm_postselect_device.argtypes = [vp, u64, u64, i32, vp, vp]
+    L.qcm_sample_sharded_device.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp, vp]
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
     assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
@@ -147,6 +150,18 @@ class Handle:
         self._check(lib().qcm_sample(self._h, int(shots), int(seed), int(stream_id), _ptr(cq),
                                      0 if cq is None else len(cq), _ptr(keys)))
         return keys
+
+    def postselect_device(self, mask, value, n_out_bits, dev_probs_ptr, dev_kept_ptr):
+        """qcm_postselect_device: results stay on the GPU (device pointers), no synchronisation."""
+        self._check(lib().qcm_postselect_device(self._h, int(mask), int(value), int(n_out_bits),
+                                                ctypes.c_void_p(dev_probs_ptr), ctypes.c_void_p(dev_kept_ptr)))
+
+    def sample_sharded_device(self, shots, seed, stream_id, rank_masses, clbit_qubit, dev_keys_ptr, dev_mine_ptr):
+        rm = np.ascontiguousarray(rank_masses, dtype=np.float64)
+        cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
+        self._check(lib().qcm_sample_sharded_device(self._h, int(shots), int(seed), int(stream_id), _ptr(rm), len(rm),
+                                                    _ptr(cq), 0 if cq is None else len(cq),
+                                                    ctypes.c_void_p(dev_keys_ptr), ctypes.c_void_p(dev_mine_ptr)))
 
     def sample_prepare(self):
         m = ctypes.c_double()

@@ -885,7 +885,7 @@ int qcm_get_op_profile(qcm_handle h, int cap, int32_t *kind_out, float *ms_out, 
     return QCM_OK;
 }
 
-int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *probs_out, double *kept_out) {
+static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *probs_out, double *kept_out, bool dev) {
     if (!h || !kept_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if (n_out_bits < 0 || n_out_bits > h->n_local || n_out_bits > 30) return fail(h, QCM_ERR_INVALID, "n_out_bits %d out of range", n_out_bits);
     if (value & ~mask) return fail(h, QCM_ERR_INVALID, "value has bits outside mask");
@@ -896,8 +896,12 @@ int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, 
     const uint64_t local_all = (h->n_local >= 64) ? ~0ull : ((1ull << h->n_local) - 1ull);
     const uint64_t act_all = (1ull << h->n_active) - 1ull;
     const uint64_t rb = rank_bits(h);
-    *kept_out = 0.0;
-    if (probs_out) memset(probs_out, 0, nprob * sizeof(double));
+    if (dev) {
+        QCM_CUDA(h, cudaMemsetAsync(kept_out, 0, sizeof(double), h->stream));
+    } else {
+        *kept_out = 0.0;
+        if (probs_out) memset(probs_out, 0, nprob * sizeof(double));
+    }
     // global (rank) bits and never-materialised bits decide emptiness up front
     bool empty = ((rb & mask & ~local_all) != (value & ~local_all));
     if (value & local_all & ~act_all) empty = true;       // demands a 1 on a qubit known |0>
@@ -908,8 +912,8 @@ int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, 
         const bool contiguous = (lval == 0) && (lmask == (act_all & ~out_all));
         const int blocks = h->num_sms * 4;
         if ((rc = ensure(h, h->partial, (blocks + 1) * sizeof(double)))) return rc;
-        if (probs_out && (rc = ensure(h, h->probs, nprob * sizeof(double)))) return rc;
-        double *dprobs = probs_out ? (double *)h->probs.p : nullptr;
+        if (probs_out && !dev && (rc = ensure(h, h->probs, nprob * sizeof(double)))) return rc;
+        double *dprobs = probs_out ? (dev ? probs_out : (double *)h->probs.p) : nullptr;
         if (contiguous) {
             const uint64_t count = 1ull << nb;
             if (dprobs && count < nprob) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * sizeof(double), h->stream));
@@ -924,18 +928,32 @@ int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, 
         }
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
-        k_tree_level<<<1, kThreads, 0, h->stream>>>((const double *)h->partial.p, (uint64_t)blocks, (double *)h->partial.p + blocks, 1);
+        k_tree_level<<<1, kThreads, 0, h->stream>>>((const double *)h->partial.p, (uint64_t)blocks,
+                                                    dev ? kept_out : (double *)h->partial.p + blocks, 1);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
-        QCM_CUDA(h, cudaMemcpyAsync(kept_out, (double *)h->partial.p + blocks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (probs_out) QCM_CUDA(h, cudaMemcpyAsync(probs_out, dprobs, nprob * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (!dev) {
+            QCM_CUDA(h, cudaMemcpyAsync(kept_out, (double *)h->partial.p + blocks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            if (probs_out) QCM_CUDA(h, cudaMemcpyAsync(probs_out, dprobs, nprob * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+    } else if (dev && probs_out) {
+        QCM_CUDA(h, cudaMemsetAsync(probs_out, 0, nprob * sizeof(double), h->stream));
     }
+    if (dev) return QCM_OK;                 // results stay on the device, in stream order: no synchronisation
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->timing.postselect_ms = ms;
     return QCM_OK;
+}
+
+int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *probs_out, double *kept_out) {
+    return postselect_impl(h, mask, value, n_out_bits, probs_out, kept_out, false);
+}
+
+int qcm_postselect_device(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, void *dev_probs_out, void *dev_kept_out) {
+    return postselect_impl(h, mask, value, n_out_bits, (double *)dev_probs_out, (double *)dev_kept_out, true);
 }
 
 int qcm_sample_prepare(qcm_handle h, double *local_mass_out) {
@@ -948,8 +966,8 @@ int qcm_sample_prepare(qcm_handle h, double *local_mass_out) {
     return QCM_OK;
 }
 
-int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const double *rank_masses, int n_ranks,
-                       const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out, uint8_t *mine_out) {
+static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const double *rank_masses, int n_ranks,
+                               const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out, uint8_t *mine_out, bool dev) {
     if (!h || !keys_out || !rank_masses) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if (n_ranks < 1 || (uint64_t)n_ranks != (1ull << h->n_global)) return fail(h, QCM_ERR_INVALID, "n_ranks %d does not match %d global qubits", n_ranks, h->n_global);
     if (n_clbits < 0 || n_clbits > 64 || (n_clbits && !clbit_qubit)) return fail(h, QCM_ERR_INVALID, "bad clbit map");
@@ -988,16 +1006,22 @@ int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t str
         if (clbit_qubit[c] >= h->n_local + h->n_global) return fail(h, QCM_ERR_INVALID, "clbit %d maps to qubit %d out of range", c, clbit_qubit[c]);
         a.clbit_qubit[c] = (int8_t)(clbit_qubit[c] < 0 ? -1 : clbit_qubit[c]);
     }
-    if ((rc = ensure(h, h->keys, shots * sizeof(uint64_t)))) return rc;
-    if ((rc = ensure(h, h->mine, shots))) return rc;
-    a.keys_out = (uint64_t *)h->keys.p;
-    a.mine_out = (uint8_t *)h->mine.p;
+    if (dev) {
+        a.keys_out = keys_out;
+        a.mine_out = mine_out;
+    } else {
+        if ((rc = ensure(h, h->keys, shots * sizeof(uint64_t)))) return rc;
+        if ((rc = ensure(h, h->mine, shots))) return rc;
+        a.keys_out = (uint64_t *)h->keys.p;
+        a.mine_out = (uint8_t *)h->mine.p;
+    }
     const uint64_t wpb = kThreads / 32;
     const unsigned blocks = (unsigned)std::min<uint64_t>((shots + wpb - 1) / wpb, (uint64_t)h->num_sms * 8);
     if (h->prec == QCM_C64) k_sample<float><<<blocks, kThreads, 0, h->stream>>>(a);
     else k_sample<double><<<blocks, kThreads, 0, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
+    if (dev) return QCM_OK;                 // keys / mine stay on the device, in stream order
     QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     if (mine_out) QCM_CUDA(h, cudaMemcpyAsync(mine_out, h->mine.p, shots, cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -1006,6 +1030,18 @@ int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t str
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->timing.sample_ms = ms;
     return QCM_OK;
+}
+
+int qcm_sample_sharded(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const double *rank_masses, int n_ranks,
+                       const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out, uint8_t *mine_out) {
+    return sample_sharded_impl(h, shots, seed, stream_id, rank_masses, n_ranks, clbit_qubit, n_clbits, keys_out, mine_out, false);
+}
+
+int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const double *rank_masses, int n_ranks,
+                              const int32_t *clbit_qubit, int n_clbits, void *dev_keys_out, void *dev_mine_out) {
+    if (!dev_mine_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    return sample_sharded_impl(h, shots, seed, stream_id, rank_masses, n_ranks, clbit_qubit, n_clbits, (uint64_t *)dev_keys_out,
+                               (uint8_t *)dev_mine_out, true);
 }
 
 int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const int32_t *clbit_qubit, int n_clbits,

@@ -515,6 +515,12 @@ class ShardedSimulator:
         h = self._run_segments(sp, keep_flags=bool(shots))
         t1 = time.perf_counter()
         replica = self._is_replica(sp)
+        if (want_probs and pr.ps is not None and pr.n_vars <= 30 and shots and self._state.is_cuda
+                and hasattr(h, 'postselect_device') and self._device_path_ok(pr)):
+            keys, probs, kept = self._finish_on_device(h, pr, shots, seed, stream, replica)
+            t2 = time.perf_counter()
+            self.breakdown_ms = {'program': (t1 - t0) * 1e3, 'results (device path)': (t2 - t1) * 1e3}
+            return keys, probs, kept
         probs = kept = masses = None
         mass = None
         if shots:
@@ -560,6 +566,66 @@ class ShardedSimulator:
         for j, q in enumerate(local_v):
             idx |= ((loc >> j) & 1) << q
         return m, idx
+
+    def _device_path_ok(self, pr):
+        """The ranks' pmf blocks tile the pmf (every global qubit a variable, no replicas): the layout
+        the planner produces for QCMRF circuits -- results can then stay on the GPU until the end."""
+        if pr.pmf_map is None:
+            pr.pmf_map = self._pmf_map(pr)
+        m, where = pr.pmf_map
+        if pr.pmf_order is None:
+            tiles = isinstance(where, slice) and where.stop - where.start == 1 << m and self._slices_tile(pr, m)
+            pr.pmf_order = self._slice_order(pr, m) if tiles else False
+        return bool(pr.pmf_order)
+
+    def _finish_on_device(self, h, pr, shots, seed, stream, replica):
+        """Post-selection, all-gather of (pmf block, kept, mass), sharded sampling and the key merge with
+        every intermediate on the GPU: one tiny device->host read (the masses, which the sampler takes as
+        arguments) and one final read of pmf + keys into pinned memory."""
+        t, dist = self.torch, self.dist
+        dev = self._state.device
+        m, _ = pr.pmf_map
+        blk = (1 << m) + 2
+        key = (blk, shots)
+        if getattr(self, '_dbuf_key', None) != key:
+            self._dbuf = {
+                'mine': t.zeros(blk, dtype=t.float64, device=dev),
+                'all': t.empty(self.world * blk, dtype=t.float64, device=dev),
+                'keys': t.zeros(shots, dtype=t.int64, device=dev),
+                'flag': t.zeros(shots, dtype=t.uint8, device=dev),
+                'h_all': t.empty(self.world * blk, dtype=t.float64, pin_memory=True),
+                'h_keys': t.empty(shots, dtype=t.int64, pin_memory=True),
+            }
+            self._dbuf_key = key
+        b = self._dbuf
+        mask, value, _ = pr.ps
+        if replica:
+            b['mine'].zero_()
+        else:
+            mass = h.sample_prepare()
+            h.postselect_device(mask, value, m, b['mine'].data_ptr(), b['mine'].data_ptr() + 8 * (1 << m))
+            b['mine'][-1:].fill_(mass)
+        dist.all_gather_into_tensor(b['all'], b['mine'], group=self.group)
+        b['h_all'].copy_(b['all'], non_blocking=True)
+        allv = b['all'].view(self.world, blk)
+        masses = allv[:, -1].cpu().numpy()                       # the one mid-way synchronisation (world doubles)
+        if replica:
+            b['keys'].zero_()
+        else:
+            h.sample_sharded_device(shots, seed, stream, masses, pr.clbit_map if len(pr.clbit_map) else None,
+                                    b['keys'].data_ptr(), b['flag'].data_ptr())
+            b['keys'].mul_(b['flag'])                             # keys of shots that landed elsewhere are 0 already; be explicit
+        dist.all_reduce(b['keys'], op=dist.ReduceOp.SUM, group=self.group)
+        b['h_keys'].copy_(b['keys'], non_blocking=True)
+        t.cuda.current_stream(dev).synchronize()
+        hall = b['h_all'].numpy().reshape(self.world, blk)
+        kept = float(hall[:, -2].sum())
+        blocks = hall[:, :-2]
+        if pr.pmf_order != list(range(self.world)):
+            blocks = blocks[pr.pmf_order]
+        probs = np.ascontiguousarray(blocks).reshape(-1)
+        keys = b['h_keys'].numpy().astype(np.uint64)
+        return keys, probs, kept
 
     def _postselect(self, h, pr, replica, mass=None):
         """Exact post-selected pmf (index: variable q <-> bit q) and success probability, on every rank.
