@@ -169,6 +169,35 @@ def run_reference_arm(args, cliques, N):
     print(json.dumps(line), flush=True)
 
 
+def brute_force_pmf(cliques, theta, beta=1.0):
+    """p(x) ~ exp(beta * sum_C theta[C, x_C]) by enumeration, index x_0 = MSB (eval.py:100-101), and
+    delta = Z / 2^n -- the check printed with every bench line (plain numpy, independent of oracle/)."""
+    n = max(max(c) for c in cliques) + 1
+    x = np.arange(1 << n, dtype=np.int64)
+    e = np.zeros(1 << n)
+    off = 0
+    for c in cliques:
+        idx = np.zeros(1 << n, dtype=np.int64)
+        for v in c:
+            idx = (idx << 1) | ((x >> (n - 1 - v)) & 1)
+        e += np.asarray(theta[off:off + (1 << len(c))], dtype=np.float64)[idx]
+        off += 1 << len(c)
+    w = np.exp(beta * e)
+    return w / w.sum(), float(w.sum() / (1 << n))
+
+
+def parity_check(cliques, theta, p, delta, counts):
+    """Last e2e step vs brute-force enumeration: max |p - p_exact| (complex64 tolerance 1e-5), delta, and
+    the post-selected fraction of the sampled shots."""
+    n = max(max(c) for c in cliques) + 1
+    if n > 24:
+        return {}
+    pb, db = brute_force_pmf(cliques, theta)
+    kept = sum(v for k, v in counts.items() if int(k, 2) < (1 << n))
+    return {'max_abs_p_error_vs_brute_force': float(np.abs(p - pb).max()), 'delta_error_vs_brute_force': abs(float(delta) - db),
+            'tolerance': 1e-5, 'sampled_success_fraction': kept / max(sum(counts.values()), 1), 'exact_delta': db}
+
+
 def workload_config(args, cliques, N):
     n = max(max(c) for c in cliques) + 1
     return {'workload': '%s: synthetic random-tree MRF, n=%d variables, k=%d pair cliques, N=%d total qubits, '
@@ -329,7 +358,8 @@ def main():
                             'wall_ms_per_step': wall_ms / args.steps},
                 'hbm_gbs_program': total_bytes / max(prog_ms, 1e-9) / 1e6,
                 'device_timing_last_step': last_timing, 'host_breakdown_ms': breakdown, 'dense_gate_pass': dense,
-                'check': {'delta': float(delta), 'p_sum': float(np.sum(p)), 'shots': int(sum(counts.values()))}}
+                'check': dict({'delta': float(delta), 'p_sum': float(np.sum(p)), 'shots': int(sum(counts.values()))},
+                              **parity_check(cliques, th, p, delta, counts))}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_reference(cliques, steps=1, warmup=0)
         print(json.dumps(line), flush=True)

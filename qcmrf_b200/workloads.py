@@ -43,6 +43,8 @@ def named(name):
         c = random_tree(16, 1)
     elif name == 'q34':                    # config 4: 34 total qubits, n=17, tree
         c = random_tree(17, 0)
+    elif name == 'q35':                    # the largest QCMRF one B200 holds: 34 stored qubits = 128 GiB complex64
+        c = random_tree(17, 1)
     elif name == 'q37':                    # config 4: 37 total qubits, n=18, tree + 1 edge
         c = random_tree(18, 1)
     elif name == 'chain20':                # config 2: 20-variable chain
