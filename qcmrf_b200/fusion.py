@@ -277,20 +277,30 @@ def _run_mux(run: List[Gate], zero_in: bool, tol=TOL):
             e = tab[k]
             e[0], e[1], e[2], e[3] = (b00 * e[0] + b01 * e[2], b00 * e[1] + b01 * e[3],
                                       b10 * e[0] + b11 * e[2], b10 * e[1] + b11 * e[3])
-    table = np.array(tab, dtype=np.complex128).reshape(1 << m, 2, 2)
-    if m:
-        tsel = np.arange(1 << m)
-        sub = table[:, :, :1] if zero_in else table         # a |0> input only ever sees column 0
-        dep = [j for j in range(m)
-               if np.abs(sub[((tsel >> j) & 1) == 0] - sub[((tsel >> j) & 1) == 1]).max() >= tol]
-        if len(dep) < m:
-            table = table[_spread(np.arange(1 << len(dep)), dep)]
-            ctrls = [ctrls[j] for j in dep]
-    if not zero_in and not ctrls and np.abs(table[0] - table[0][0, 0] * np.eye(2)).max() < tol:
-        return [], [], float(np.angle(table[0][0, 0]))     # identity up to a phase
+    # index qubits the table does not depend on (a |0> input only ever sees column 0), in plain Python:
+    # the tables have at most a few dozen entries
+    cols = (0, 2) if zero_in else (0, 1, 2, 3)
+    dep = []
+    for j in range(m):
+        bit = 1 << j
+        if any(abs(tab[c][k] - tab[c | bit][k]) >= tol for c in range(1 << m) if not c & bit for k in cols):
+            dep.append(j)
+    if len(dep) < m:
+        sel = []
+        for c in range(1 << len(dep)):
+            full = 0
+            for jj, j in enumerate(dep):
+                full |= ((c >> jj) & 1) << j
+            sel.append(tab[full])
+        tab = sel
+        ctrls = [ctrls[j] for j in dep]
+    if not zero_in and not ctrls:
+        e = tab[0]
+        if abs(e[1]) < tol and abs(e[2]) < tol and abs(e[3] - e[0]) < tol:
+            return [], [], float(cmath.phase(e[0]))         # identity up to a phase
     if zero_in:                                            # same completion as _classify: unitary 2x2
-        table[:, 0, 1] = -np.conj(table[:, 1, 0])
-        table[:, 1, 1] = np.conj(table[:, 0, 0])
+        tab = [[e[0], -e[2].conjugate(), e[2], e[0].conjugate()] for e in tab]
+    table = np.array(tab, dtype=np.complex128).reshape(len(tab), 2, 2)
     op = FusedOp('mux', t, tuple(ctrls), table, zero_in, len(run))
     return [op], [t] + list(ctrls), 0.0
 
@@ -349,7 +359,12 @@ def fold_clean_scratch(gates: List[Gate], n_qubits: int) -> List[Gate]:
         if len(gq) > 1 and g.name in ('cx', 'mcx') and s_q in clean:
             A = set(gq[:-1])
             j = i + 1
-            while j < n:
+            if i + 2 < n and gates[i + 2] is g:          # the common shape: compute, ONE use, uncompute
+                hq = gates[j].qubits
+                if (hq[-1] != s_q and hq[-1] not in A and
+                        (s_q not in hq or gates[j].ctrl_values[hq.index(s_q)] == 1)):
+                    j = i + 2
+            while j < n and j != i + 2:
                 hq = gates[j].qubits
                 ht = hq[-1]
                 if ht == s_q or ht in A:
@@ -357,6 +372,8 @@ def fold_clean_scratch(gates: List[Gate], n_qubits: int) -> List[Gate]:
                 if s_q in hq and gates[j].ctrl_values[hq.index(s_q)] != 1:
                     break
                 j += 1
+            if j == i + 2 and gates[j].qubits[-1] != s_q:
+                j = n                                    # the scan stopped for another reason
             if (j < n and j > i + 1 and gates[j].qubits == gq and gates[j].name in ('cx', 'mcx')
                     and gates[j].ctrl_values == g.ctrl_values):
                 inner = gates[i + 1:j]

@@ -60,14 +60,30 @@ def one_qubit_matrix(name, params=()):
     raise ValueError('qcmrf_b200: unsupported gate %r' % name)
 
 
-@dataclass(frozen=True)
 class Gate:
     """``base`` single-qubit gate on ``qubits[-1]``, applied where every control
-    ``qubits[j]`` equals ``ctrl_values[j]`` (no controls => plain 1-qubit gate)."""
-    name: str                       # canonical primitive name
-    qubits: Tuple[int, ...]         # controls..., target
-    params: Tuple[float, ...] = ()
-    ctrl_values: Tuple[int, ...] = ()
+    ``qubits[j]`` equals ``ctrl_values[j]`` (no controls => plain 1-qubit gate).
+    Immutable by convention; a slotted plain class because programs hold hundreds of them
+    and are rebuilt for every circuit."""
+    __slots__ = ('name', 'qubits', 'params', 'ctrl_values')
+
+    def __init__(self, name, qubits, params=(), ctrl_values=()):
+        self.name = name                # canonical primitive name
+        self.qubits = qubits            # controls..., target
+        self.params = params
+        self.ctrl_values = ctrl_values
+
+    def _key(self):
+        return (self.name, self.qubits, self.params, self.ctrl_values)
+
+    def __eq__(self, other):
+        return isinstance(other, Gate) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return 'Gate(%r, %r, %r, %r)' % self._key()
 
     @property
     def target(self):
