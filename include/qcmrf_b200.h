@@ -40,6 +40,7 @@ extern "C" {
 #define QCM_ABI_VERSION 1
 #define QCM_MAX_CTRL 10      /* table-index qubits of one MUX1Q / DIAG op           */
 #define QCM_MAX_BLOCK 5      /* target qubits of one BLOCK pass (2^5 vectors/thread) */
+#define QCM_MAX_GATHER 3     /* global qubits one fused exchange+gate pass swaps in (8 ranks) */
 #define QCM_MAX_EXPAND 8     /* ... of a BLOCK pass whose qubits are all new (one MUX1Q each) */
 #define QCM_MAX_MEMBERS 16   /* MUX1Q members of one BLOCK pass                      */
 
@@ -179,6 +180,18 @@ int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint6
                               const double *rank_masses, int n_ranks,
                               const int32_t *clbit_qubit, int n_clbits,
                               void *dev_keys_out, void *dev_mine_out);
+
+/* Fused qubit-swap + blocked gate pass over NVLink peer memory (sharded states, one box).
+ * Replaces "all-to-all that swaps the s global qubits with the s highest local qubits, then the
+ * sweeps that target them": ops = a MUX1Q or a BLOCK header + members whose targets are exactly those
+ * s highest local qubits (positions n_local-s .. n_local-1 AFTER the swap).  src_slabs[r] (r < 2^s) is a
+ * device pointer, valid in this process (CUDA IPC / peer mapped), to the slab with index c_me of the
+ * rank with coordinate r, i.e. peer_state + c_me * 2^(n_local-s) amplitudes; dst_state is a local
+ * buffer of 2^n_local amplitudes that becomes the handle's state.  The caller must set the shard to the
+ * rank bits that hold AFTER the swap (unchanged: the rank keeps its number) and must bracket the
+ * call with cross-rank barriers (see qcm_kernels.cuh, k_block_gather).  No CPU fallback.          */
+int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
+                         const void *const *src_slabs, int s, void *dst_state);
 
 /* Batched small circuits (all fixture-sized models in one launch: one thread block
  * per circuit, state resident in shared memory, program + post-selection + sampling

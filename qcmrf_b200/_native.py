@@ -38,7 +38,7 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_run_program', 'qcm_postselect', 'qcm_sample', 'qcm_sample_prepare', 'qcm_sample_sharded',
            'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
            'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile', 'qcm_postselect_device',
-           'qcm_sample_sharded_device']
+           'qcm_sample_sharded_device', 'qcm_run_gather_block']
 
 
 def lib():
@@ -76,6 +76,7 @@ def lib():
     L.qcm_get_op_profile.argtypes = [vp, i32, vp, vp, vp, vp, ctypes.POINTER(i32)]
     L.qcm_postselect_device.argtypes = [vp, u64, u64, i32, vp, vp]
     L.qcm_sample_sharded_device.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp, vp]
+    L.qcm_run_gather_block.argtypes = [vp, vp, i32, vp, ctypes.c_size_t, vp, i32, vp]
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
     assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
@@ -150,6 +151,15 @@ class Handle:
         self._check(lib().qcm_sample(self._h, int(shots), int(seed), int(stream_id), _ptr(cq),
                                      0 if cq is None else len(cq), _ptr(keys)))
         return keys
+
+    def run_gather_block(self, ops, tables, src_slab_ptrs, dst_ptr):
+        """qcm_run_gather_block: fused qubit swap + blocked pass reading the peers' shards."""
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        tables = np.ascontiguousarray(tables, dtype=np.float64)
+        src = (ctypes.c_void_p * len(src_slab_ptrs))(*[ctypes.c_void_p(int(p)) for p in src_slab_ptrs])
+        s = len(src_slab_ptrs).bit_length() - 1
+        self._check(lib().qcm_run_gather_block(self._h, _ptr(ops), len(ops), _ptr(tables), tables.size, src, s,
+                                               ctypes.c_void_p(int(dst_ptr))))
 
     def postselect_device(self, mask, value, n_out_bits, dev_probs_ptr, dev_kept_ptr):
         """qcm_postselect_device: results stay on the GPU (device pointers), no synchronisation."""

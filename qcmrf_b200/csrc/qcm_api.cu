@@ -617,6 +617,28 @@ int build_tree(qcm_handle h) {
     return tree_finish(h, na);
 }
 
+template <typename R, int V, int M>
+static int launch_gather_t(qcm_handle h, const GatherArgs &a, size_t smem) {
+    constexpr int U = 2;
+    auto kern = k_block_gather<R, V, M, U>;
+    const uint64_t nvec = (1ull << (a.n_local - M)) / V;
+    const uint64_t grid = std::min<uint64_t>(std::max<uint64_t>(1, (nvec + (uint64_t)kThreads * U - 1) / ((uint64_t)kThreads * U)), 0x7fffffffull);
+    kern<<<(unsigned)grid, kThreads, smem, h->stream>>>(a);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    return QCM_OK;
+}
+
+template <typename R, int V>
+static int launch_gather_m(qcm_handle h, int M, const GatherArgs &a, size_t smem) {
+    switch (M) {
+        case 1: return launch_gather_t<R, V, 1>(h, a, smem);
+        case 2: return launch_gather_t<R, V, 2>(h, a, smem);
+        case 3: return launch_gather_t<R, V, 3>(h, a, smem);
+    }
+    return fail(h, QCM_ERR_INVALID, "gather block of %d qubits out of range", M);
+}
+
 int check_device(qcm_handle h) {
     QCM_CUDA(h, cudaSetDevice(h->device));
     return QCM_OK;
@@ -868,6 +890,66 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     h->timing.program_ms = ms;
     h->op_ms.resize(h->op_kind.size());
     for (size_t k = 0; k < h->op_kind.size(); ++k) QCM_CUDA(h, cudaEventElapsedTime(&h->op_ms[k], h->op_ev[k], h->op_ev[k + 1]));
+    return QCM_OK;
+}
+
+int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
+                         const void *const *src_slabs, int s, void *dst_state) {
+    if (!h || !ops || n_ops < 1 || !src_slabs || !dst_state) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if (s < 1 || s > QCM_MAX_GATHER || s > h->n_global || s >= h->n_local) return fail(h, QCM_ERR_INVALID, "cannot gather %d qubits", s);
+    if (h->n_active != h->n_local) return fail(h, QCM_ERR_INVALID, "gather needs a fully materialised shard");
+    if (h->own_state) return fail(h, QCM_ERR_INVALID, "gather needs a caller-owned state buffer (ext_state): peers map it");
+    int rc = check_device(h);
+    if (rc) return rc;
+    const qcm_op &hd = ops[0];
+    const qcm_op *members = &hd;
+    int n_mem = 1;
+    int tq[QCM_MAX_GATHER];
+    if (hd.kind == QCM_OP_BLOCK) {
+        if (hd.target != s || hd.n_ctrl != n_ops - 1) return fail(h, QCM_ERR_INVALID, "gather block header does not match");
+        members = ops + 1;
+        n_mem = hd.n_ctrl;
+        for (int j = 0; j < s; ++j) tq[j] = hd.ctrl[j];
+    } else if (hd.kind == QCM_OP_MUX1Q && s == 1 && n_ops == 1) {
+        tq[0] = hd.target;
+    } else {
+        return fail(h, QCM_ERR_INVALID, "gather block must be a MUX1Q (s = 1) or a BLOCK over the s swapped-in qubits");
+    }
+    for (int j = 0; j < s; ++j)
+        if (tq[j] != h->n_local - s + j) return fail(h, QCM_ERR_INVALID, "gather block targets must be the %d highest local qubits", s);
+    BlockPlan bp;
+    if ((rc = plan_block(h, tq, s, members, n_mem, h->n_local, h->n_local, n_tables, bp))) return rc;
+    h->tree_valid = false;
+    QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    if ((rc = upload_tables(h, tables, n_tables))) return rc;
+    GatherArgs a{};
+    for (int r = 0; r < (1 << s); ++r) {
+        if (!src_slabs[r]) return fail(h, QCM_ERR_INVALID, "src_slabs[%d] is NULL", r);
+        a.src[r] = src_slabs[r];
+    }
+    a.dst = dst_state;
+    a.tables = h->tab_real.p;
+    a.n_local = h->n_local;
+    a.s = s;
+    a.n_members = n_mem;
+    a.ctrl_below_32 = bp.args.ctrl_below_32;
+    a.rank_bits = rank_bits(h);
+    for (int g = 0; g < n_mem; ++g) a.mem[g] = bp.args.mem[g];
+    if (h->prec == QCM_C64) rc = launch_gather_m<float, 2>(h, s, a, bp.smem);
+    else rc = launch_gather_m<double, 1>(h, s, a, bp.smem);
+    if (rc) return rc;
+    QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    QCM_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->timing.program_ms = ms;
+    h->timing.bytes_read = amp_bytes(h->prec) << h->n_local;
+    h->timing.bytes_written = amp_bytes(h->prec) << h->n_local;
+    h->state = dst_state;                   // the handle continues on the gathered buffer (caller-owned, like the old one)
+    h->op_kind.assign(1, hd.kind);
+    h->op_rd.assign(1, h->timing.bytes_read);
+    h->op_wr.assign(1, h->timing.bytes_written);
+    h->op_ms.assign(1, ms);
     return QCM_OK;
 }
 

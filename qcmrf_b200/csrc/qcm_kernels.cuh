@@ -261,6 +261,111 @@ __global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ Bloc
 }
 
 // ----------------------------------------------------------------------------------
+// Fused qubit-swap + gate pass over NVLink peer memory (sharded states).
+//
+// A qubit-swap all-to-all brings the s global qubits on-GPU as the s highest local qubits, and the
+// sweeps that wanted them as targets follow.  Fused: for every rest-index i the 2^s amplitudes a
+// blocked pass over those qubits needs are exactly  peer_r.state[(c_me << (n_local - s)) | i],
+// r = 0 .. 2^s-1  (c_me: this rank's coordinate, peer_r: the rank with coordinate r; r == c_me is
+// local).  The kernel loads its 2^s register vectors straight from the peers' shards (mapped
+// through CUDA IPC, plain 128-bit loads over NVLink), applies the members in registers and
+// stores to an out-of-place local buffer: one kernel instead of an all-to-all plus s passes, and
+// the transfer overlaps the arithmetic tile by tile.  No flags, no spinning: the host brackets
+// the launch with barriers (peers must have finished writing the state that is read here, and
+// must have finished reading before the old buffer is reused).
+// ----------------------------------------------------------------------------------
+struct GatherArgs {
+    const void *src[1 << QCM_MAX_GATHER];   // src[r]: peer r's slab c_me (device pointers, peer-mapped)
+    void *dst;                              // local output state (2^n_local amplitudes)
+    const void *tables;
+    int32_t n_local, s;
+    int32_t n_members;
+    int32_t ctrl_below_32;
+    uint64_t rank_bits;                     // NEW rank bits (after the swap), rank << n_local
+    MemberDesc mem[QCM_MAX_MEMBERS];        // pos = index among the s swapped-in qubits
+};
+
+template <typename R, int V, int M, int U>
+__global__ void __launch_bounds__(kThreads) k_block_gather(const __grid_constant__ GatherArgs a) {
+    constexpr int NR = 1 << M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tab = reinterpret_cast<R *>(smem_raw);
+    for (int g = 0; g < a.n_members; ++g) {
+        const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
+        R *dst = tab + a.mem[g].tab_off;
+        const int cnt = (a.mem[g].pos < 0 ? 2 : 8) << a.mem[g].n_ctrl;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    using IO = VecIO<R, V>;
+    const uint64_t slab = 1ull << (a.n_local - M);
+    const uint64_t nvec = slab / V;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
+    for (uint64_t bv0 = (uint64_t)blockIdx.x * blockDim.x * U + threadIdx.x; bv0 < nvec; bv0 += stride) {
+        R ar[U][NR][V], ai[U][NR][V];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t bv = bv0 + (uint64_t)u * blockDim.x;
+            ok[u] = bv < nvec;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                if (ok[u]) IO::load(a.src[r], bv * V, ar[u][r], ai[u][r]);
+                else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { ar[u][r][v] = R(0); ai[u][r][v] = R(0); }
+                }
+            }
+        }
+        for (int g = 0; g < a.n_members; ++g) {
+            const int pos = a.mem[g].pos;
+            const int nc = a.mem[g].n_ctrl;
+            const R *mt = tab + a.mem[g].tab_off;
+            const uint32_t low_bit = a.mem[g].low_bit;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t gi = ((bv0 + (uint64_t)u * blockDim.x) * V) | a.rank_bits;
+                uint32_t idx0 = 0;
+                if (a.ctrl_below_32) {
+                    const uint32_t lo = (uint32_t)gi;
+                    for (int j = 0; j < nc; ++j) idx0 |= ((lo >> a.mem[g].ctrl[j]) & 1u) << j;
+                } else {
+                    for (int j = 0; j < nc; ++j) idx0 |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const uint32_t idx = v ? (idx0 | low_bit) : idx0;
+                    if (pos < 0) {
+                        const R c = mt[2 * idx], sn = mt[2 * idx + 1];
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            const R x = ar[u][r][v], y = ai[u][r][v];
+                            ar[u][r][v] = c * x - sn * y;
+                            ai[u][r][v] = c * y + sn * x;
+                        }
+                        continue;
+                    }
+                    R m[8];
+                    load_m8<R>(mt + 8 * idx, m);
+                    switch (pos) {
+                        case 0: butterfly<R, V, NR, 0, false>(ar[u], ai[u], m, v, 0u); break;
+                        case 1: butterfly<R, V, NR, 1, false>(ar[u], ai[u], m, v, 0u); break;
+                        default: butterfly<R, V, NR, 2, false>(ar[u], ai[u], m, v, 0u); break;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const uint64_t bv = bv0 + (uint64_t)u * blockDim.x;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) IO::store(a.dst, (uint64_t)r * slab + bv * V, ar[u][r], ai[u][r]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
 // Expansion pass (lazy materialisation fast path).
 //
 // All M block qubits are the new qubits n_in .. n_in+M-1, each the target of exactly

@@ -592,3 +592,66 @@ def test_full_size_33_qubit_state():
     assert np.abs(p2 - pb).max() < 1e-5 and abs(d2 - db) < 1e-5
     assert np.abs(p2 - p).max() < 2e-6
     dense.close()
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('s', [1, 2, 3])
+def test_gather_block_on_virtual_peers(precision, s):
+    """qcm_run_gather_block (fused qubit swap + blocked pass that reads the peers' shards): all 2^s
+    'ranks' live on this GPU, so the peer pointers are ordinary device pointers; expected = numpy qubit
+    swap of the full state followed by the op semantics (engine emulator) per rank."""
+    import torch
+    rng = np.random.RandomState(50 + s)
+    nl = 11
+    N = nl + s
+    world = 1 << s
+    cdt = np.complex128 if precision == 'double' else np.complex64
+    tdt = torch.float64 if precision == 'double' else torch.float32
+    psi = (rng.randn(1 << N) + 1j * rng.randn(1 << N))
+    psi /= np.linalg.norm(psi)
+    # the block: targets = the s highest local qubits after the swap; controls among low local and global qubits
+    e = fusion._Emitter()
+    tq = list(range(nl - s, nl))
+
+    def rand_u(m):
+        q, _ = np.linalg.qr(rng.randn(1 << m, 2, 2) + 1j * rng.randn(1 << m, 2, 2))
+        return q
+    members = []
+    for t in tq + [tq[0]]:
+        ctrl = [int(c) for c in rng.permutation(nl - s)[:2]] + ([int(nl + rng.randint(s))] if rng.rand() < 0.6 else [])
+        if rng.rand() < 0.4 and 0 not in ctrl:
+            ctrl[0] = 0
+        members.append((fusion.QCM_OP_MUX1Q, t, ctrl, fusion._mux_table_f64(rand_u(len(ctrl)))))
+    members.append((fusion.QCM_OP_DIAG, 0, [1, nl - s - 1], fusion._diag_table_f64(np.exp(1j * rng.uniform(0, 6, 4)))))
+    if s == 1:
+        members = members[:1]
+        k, t, c, tab = members[0]
+        e.op(k, target=t, ctrl=c, n_in=nl, n_out=nl, table_off=e.table(tab))
+    else:
+        e.op(fusion.QCM_OP_BLOCK, target=s, ctrl=tq, n_in=nl, n_out=nl, n_ctrl=len(members))
+        for k, t, c, tab in members:
+            e.op(k, target=t, ctrl=c, n_in=nl, n_out=nl, table_off=e.table(tab))
+    ops, tabs = e.finish()
+    # expected: swap global qubits (nl .. nl+s-1) with local qubits (nl-s .. nl-1), then the block per rank
+    idx = np.arange(1 << N)
+    lo_mask = (1 << (nl - s)) - 1
+    a = (idx >> (nl - s)) & (world - 1)
+    b = idx >> nl
+    swapped = psi[(idx & lo_mask) | (b << (nl - s)) | (a << nl)]
+    old = [torch.from_numpy(np.ascontiguousarray(psi[r << nl:(r + 1) << nl].astype(cdt)).view(np.float64 if precision == 'double' else np.float32)).cuda()
+           for r in range(world)]
+    new = [torch.empty_like(x) for x in old]
+    slab_bytes = (1 << (nl - s)) * np.dtype(cdt).itemsize
+    worst = 0.0
+    for r in range(world):
+        with _native.Handle(nl, precision, ext_state_ptr=old[r].data_ptr()) as h:
+            h.set_shard(s, r)
+            h.set_active(nl)
+            src = [old[j].data_ptr() + r * slab_bytes for j in range(world)]
+            h.run_gather_block(ops, tabs, src, new[r].data_ptr())
+            got = h.get_amplitudes().astype(np.complex128)
+        pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, nl
+        init = swapped[r << nl:(r + 1) << nl].astype(cdt).astype(np.complex128)
+        want, _ = em.run_plan(pl, n_global=s, rank=r, n_local=nl, psi0=init, active0=nl)
+        worst = max(worst, np.abs(got - want).max())
+    assert worst < (1e-12 if precision == 'double' else 3e-6)
