@@ -538,6 +538,28 @@ def dense_gate_pass(args, cliques, device, world=1):
         out['exchange'] = [{'ms': r[1], 'bytes_sent_per_gpu': r[2], 'gbs_per_direction_per_gpu': r[2] / r[1] / 1e6}
                            for r in ex]
     sim.close()
+    if world > 1 and prep.plan.n_phys - (world.bit_length() - 1) <= 32:
+        # the same schedule with the qubit swap and the sweeps on the swapped-in qubits fused into ONE kernel
+        # that reads the peers' shards over NVLink (needs a second local buffer: shards <= 32 GiB here)
+        from qcmrf_b200.sharded import ShardedSimulator
+        sim = ShardedSimulator(precision='single', fusion='clique', layout='canonical', device=device, seed=1,
+                               exchange='p2p')
+        prep = sim.prepare(circ)
+        sim.execute(prep, 0, want_probs=False)
+        sim.execute(prep, 0, want_probs=False)
+        prof2 = sim.op_profile()
+        fx = [r for r in prof2 if r[0] == -2]
+        s = world.bit_length() - 1
+        if fx:
+            remote = fx[0][2] // 2 * (world - 1) // world
+            out['fused_exchange'] = {'kernel': 'k_block_gather: qubit swap + the %d sweeps on the swapped-in qubits, peers read over '
+                                               'NVLink (CUDA IPC)' % s, 'ms': fx[0][1],
+                                     'replaces_ms': (ex[0][1] if ex else 0.0) + s * ms,
+                                     'remote_bytes_read_per_gpu': remote, 'nvlink_gbs_per_gpu': remote / fx[0][1] / 1e6,
+                                     'circuit_ms': sum(r[1] for r in prof2)}
+        else:
+            out['fused_exchange'] = {'unavailable': getattr(sim, 'p2p_error', 'no fused segment in the plan')}
+        sim.close()
     return out
 
 

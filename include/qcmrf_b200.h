@@ -190,6 +190,9 @@ int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint6
  * buffer of 2^n_local amplitudes that becomes the handle's state.  The caller must set the shard to the
  * rank bits that hold AFTER the swap (unchanged: the rank keeps its number) and must bracket the
  * call with cross-rank barriers (see qcm_kernels.cuh, k_block_gather).  No CPU fallback.          */
+/* cudaDeviceEnablePeerAccess(device -> peer), idempotent; needed before qcm_run_gather_block reads
+ * buffers that live on `peer`.                                                                    */
+int qcm_enable_peer_access(int device, int peer);
 int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
                          const void *const *src_slabs, int s, void *dst_state);
 

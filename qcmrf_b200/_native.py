@@ -38,7 +38,7 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_run_program', 'qcm_postselect', 'qcm_sample', 'qcm_sample_prepare', 'qcm_sample_sharded',
            'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
            'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile', 'qcm_postselect_device',
-           'qcm_sample_sharded_device', 'qcm_run_gather_block']
+           'qcm_sample_sharded_device', 'qcm_run_gather_block', 'qcm_enable_peer_access']
 
 
 def lib():
@@ -77,11 +77,19 @@ def lib():
     L.qcm_postselect_device.argtypes = [vp, u64, u64, i32, vp, vp]
     L.qcm_sample_sharded_device.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp, vp]
     L.qcm_run_gather_block.argtypes = [vp, vp, i32, vp, ctypes.c_size_t, vp, i32, vp]
+    L.qcm_enable_peer_access.argtypes = [i32, i32]
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
     assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
     _lib = L
     return L
+
+
+def enable_peer_access(device, peer):
+    """Let kernels running on `device` dereference pointers into `peer`'s memory (NVLink P2P)."""
+    rc = lib().qcm_enable_peer_access(int(device), int(peer))
+    if rc:
+        raise NativeError(rc, (lib().qcm_last_error(None) or b'').decode())
 
 
 def device_count():

@@ -663,6 +663,21 @@ int qcm_device_count(int *n_out) {
     return QCM_OK;
 }
 
+int qcm_enable_peer_access(int device, int peer) {
+    if (device == peer) return QCM_OK;
+    int can = 0;
+    cudaError_t e = cudaDeviceCanAccessPeer(&can, device, peer);
+    if (e != cudaSuccess || !can) return fail(nullptr, QCM_ERR_UNSUPPORTED, "device %d cannot access device %d directly", device, peer);
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        e = cudaSuccess;
+    }
+    if (e != cudaSuccess) return fail(nullptr, QCM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer, cudaGetErrorString(e));
+    return QCM_OK;
+}
+
 const char *qcm_last_error(qcm_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
 int qcm_create(qcm_handle *out, int device, int n_local, int precision, void *ext_state, void *ext_stream) {

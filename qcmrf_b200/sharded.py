@@ -33,6 +33,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _native, fusion, ir
+QCM_MAX_GATHER = 3
 from .fusion import (OP_DTYPE, QCM_MAX_CTRL, QCM_OP_BLOCK, QCM_OP_DIAG, QCM_OP_EXTEND, QCM_OP_INIT_PRODUCT,
                      QCM_OP_MUX1Q, QCM_OP_SWAP, _Emitter)
 
@@ -45,7 +46,8 @@ class ShardedPlan:
     rank: int
     n_local: int
     n_phys: int
-    #: ('run', ops, tables, rank_mask) | ('exchange', betas) -- betas: rank-bit indices, ascending
+    #: ('run', ops, tables, rank_mask) | ('exchange', betas) | ('xblock', betas, ops, tables, rank_mask)
+    #: -- betas: rank-bit indices, ascending
     segments: List[tuple] = field(default_factory=list)
     pos: List[int] = field(default_factory=list)      # plan-physical qubit -> final position
     mat_mask: int = 0                                  # rank bits whose global qubit is materialised at the end
@@ -76,8 +78,10 @@ def _targets(op, members):
     return []
 
 
-def shard_plan(pl: fusion.Plan, g: int, rank: int) -> ShardedPlan:
-    """Rewrite a single-device plan for rank ``rank`` of 2^g."""
+def shard_plan(pl: fusion.Plan, g: int, rank: int, fuse_exchange: bool = False) -> ShardedPlan:
+    """Rewrite a single-device plan for rank ``rank`` of 2^g.  fuse_exchange: where a qubit swap is
+    followed by sweeps on the swapped-in qubits, emit ONE ('xblock', ...) segment (the engine's fused
+    gather pass over peer memory) instead of ('exchange', ...) plus local passes."""
     n_phys = pl.n_phys
     n_local = n_phys - g
     if n_local < 1:
@@ -159,14 +163,45 @@ def shard_plan(pl: fusion.Plan, g: int, rank: int) -> ShardedPlan:
         flush()
         gpos = sorted(pos[q] for q in want)
         betas = [p - n_local for p in gpos]
-        sp.segments.append(('exchange', betas))
-        sp.n_exchanges += 1
-        sp.exchange_amps += ((1 << s) - 1) << (n_local - s)
         for gp, lp in zip(gpos, top):                 # ascending global <-> ascending top-local
             qa, qb = occ[gp], occ[lp]
             occ[gp], occ[lp] = qb, qa
             pos[qa], pos[qb] = lp, gp
         # every exchanged position stays materialised (both sides were)
+        sp.n_exchanges += 1
+        sp.exchange_amps += ((1 << s) - 1) << (n_local - s)
+        if fuse_exchange and s <= QCM_MAX_GATHER and lact(active) == n_local:
+            # sweeps that follow and only touch the swapped-in qubits ride in the same kernel
+            topset = set(top)
+            fused, nh = [], from_h
+            while nh < len(headers):
+                _, fop, fmem = headers[nh]
+                if int(fop['kind']) not in (QCM_OP_MUX1Q, QCM_OP_BLOCK):
+                    break
+                if any(pos[t] not in topset for t in _targets(fop, fmem)):
+                    break
+                cand = []
+                for mb in fmem:
+                    ctrl = [pos[int(c)] for c in mb['ctrl'][:int(mb['n_ctrl'])]]
+                    if any(c in topset for c in ctrl):
+                        cand = None
+                        break
+                    kind = int(mb['kind'])
+                    cand.append((kind, pos[int(mb['target'])] if kind == QCM_OP_MUX1Q else 0, ctrl, member_table(mb)))
+                if cand is None or len(fused) + len(cand) > fusion.QCM_MAX_MEMBERS:
+                    break
+                fused.extend(cand)
+                nh += 1
+            if nh > from_h:
+                xe = _Emitter()
+                xe.op(QCM_OP_BLOCK, target=s, ctrl=top, n_in=n_local, n_out=n_local, n_ctrl=len(fused))
+                for k, t, c, tab in fused:
+                    xe.op(k, target=t, ctrl=c, n_in=n_local, n_out=n_local, table_off=xe.table(tab))
+                xops, xtabs = xe.finish()
+                sp.segments.append(('xblock', betas, xops, xtabs, mat_mask))
+                return nh
+        sp.segments.append(('exchange', betas))
+        return None
 
     def force_materialise(position):
         """Global qubit known |0> becomes an explicit sharded qubit: ranks whose bit is 1 hold zeros."""
@@ -181,7 +216,10 @@ def shard_plan(pl: fusion.Plan, g: int, rank: int) -> ShardedPlan:
         o = int(mb['table_off'])
         return tabs[o:o + (per << nc)]
 
+    skip_to = 0
     for hi, (_, op, members) in enumerate(headers):
+        if hi < skip_to:
+            continue
         kind = int(op['kind'])
         n_in, n_out = int(op['n_active_in']), int(op['n_active_out'])
         if kind == QCM_OP_INIT_PRODUCT:
@@ -254,8 +292,11 @@ def shard_plan(pl: fusion.Plan, g: int, rank: int) -> ShardedPlan:
         old_global = [t for t in tq if t not in branch and pos[t] >= n_local]
         if old_global:
             # new local qubits of this op are not materialised yet; exchange among materialised ones
-            exchange_for(old_global, hi)
+            nxt = exchange_for(old_global, hi)
             set_mask(mat_mask)
+            if nxt is not None:                       # this op (and maybe more) went into the fused gather pass
+                skip_to = nxt
+                continue
         local_t = sorted(pos[t] for t in tq if t not in branch)
         l_in = lact(n_in)
         l_out = max([l_in] + [p + 1 for p in local_t])
@@ -319,7 +360,7 @@ class ShardedSimulator:
     what bench.py and the tests use: prepare / execute / run / exact / close."""
 
     def __init__(self, precision='single', fusion='blocked', block_max=4, device=0, seed=None, group=None,
-                 staging_bytes=1 << 30, name='qasm_simulator', layout='auto', expand_max=8):
+                 staging_bytes=1 << 30, name='qasm_simulator', layout='auto', expand_max=8, exchange='nccl'):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -339,6 +380,15 @@ class ShardedSimulator:
         if layout not in ('auto', 'canonical'):
             raise ValueError("layout must be 'auto' or 'canonical'")
         self.layout = layout      # auto: shard on control-only qubits when the circuit has them (no communication)
+        if exchange not in ('nccl', 'p2p'):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        # 'p2p': a qubit swap followed by sweeps on the swapped-in qubits runs as ONE kernel that reads the
+        # peers' shards over NVLink (CUDA IPC mapped) and writes a second local buffer -- needs 2x the
+        # shard in memory; anything it cannot serve falls back to the NCCL all-to-all + local passes
+        self.exchange = exchange
+        self._bufs = None          # p2p: [A, B] local state tensors
+        self._peer_bufs = None     # p2p: rank -> [A, B] tensors mapped from that rank
+        self._cur = 0
         self._name = name
         self._h = None
         self._state = None
@@ -369,7 +419,33 @@ class ShardedSimulator:
         self.close()
         self._h, self._state = self._alloc_state(n_local)
         self._n_local = n_local
+        if self.exchange == 'p2p' and self._state.is_cuda:
+            try:
+                self._map_peers()
+            except Exception as e:                       # IPC not available: stay on NCCL
+                self._bufs = self._peer_bufs = None
+                self.p2p_error = repr(e)
         return self._h
+
+    def _map_peers(self):
+        """Second local buffer + CUDA-IPC mappings of every rank's two buffers (torch's own tensor
+        sharing machinery: cudaIpcGetMemHandle / cudaIpcOpenMemHandle under the hood)."""
+        t, dist = self.torch, self.dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        other = t.empty_like(self._state)
+        self._bufs = [self._state, other]
+        self._cur = 0
+        meta = [reduce_tensor(x) for x in self._bufs]
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, meta, group=self.group)
+        self._peer_bufs = {}
+        for r in range(self.world):
+            if r == self.rank:
+                self._peer_bufs[r] = self._bufs
+            else:
+                self._peer_bufs[r] = [fn(*args) for fn, args in gathered[r]]
+                _native.enable_peer_access(self.device, self._peer_bufs[r][0].device.index)
+        dist.barrier(group=self.group)
 
     def close(self):
         if self._h is not None:
@@ -379,6 +455,7 @@ class ShardedSimulator:
                 pass
             self._h.close()
         self._h = self._state = self._stage = None
+        self._bufs = self._peer_bufs = None
         self._n_local = None
 
     # ---- preparation -----------------------------------------------------------------------
@@ -391,7 +468,7 @@ class ShardedSimulator:
             ng = self.g
         pl = fusion.plan(fc, lazy=lazy, block_max=self.block_max, n_global=ng,
                          expand_max=max(self.block_max, self.expand_max))
-        sp = shard_plan(pl, self.g, self.rank)
+        sp = shard_plan(pl, self.g, self.rank, fuse_exchange=(self.exchange == 'p2p'))
         pr = _ShardPrepared()
         pr.prog, pr.fc, pr.plan, pr.sp, pr.name = prog, fc, pl, sp, prog.name
 
@@ -477,6 +554,12 @@ class ShardedSimulator:
                 h.set_shard(sp.g, sp.rank & mask)
                 h.run_program(ops, tabs)
                 self._profile.extend(h.op_profile())
+            elif seg[0] == 'xblock' and self._peer_bufs is not None:
+                _, betas, ops, tabs, mask = seg
+                ms = self._gather_block(h, sp, betas, ops, tabs, mask)
+                by = self._state.element_size() * (2 << sp.n_local)
+                self._profile.append((-2, ms, by, by))
+                self.exchange_ms += ms
             else:
                 if self.sync_before_exchange:
                     self.dist.barrier(group=self.group)        # measurement aid: keep rank skew out of exchange_ms
@@ -494,8 +577,43 @@ class ShardedSimulator:
                 self.exchange_ms += ms
                 sent = ((1 << len(seg[1])) - 1) * (1 << (sp.n_local - len(seg[1]))) * self._state.element_size() * 2
                 self._profile.append((-1, ms, sent, sent))
+                if seg[0] == 'xblock':                         # no peer mapping: all-to-all, then the sweeps locally
+                    _, _, ops, tabs, mask = seg
+                    h.set_shard(sp.g, sp.rank & mask)
+                    h.run_program(ops, tabs)
+                    self._profile.extend(h.op_profile())
         h.set_shard(sp.g, sp.rank & sp.mat_mask)
         return h
+
+    def _gather_block(self, h, sp, betas, ops, tabs, mask):
+        """Fused qubit swap + sweeps on the swapped-in qubits: one kernel reading the peers' current
+        buffers (slab c_me of the rank with coordinate j, for every j) and writing this rank's other buffer."""
+        t, dist = self.torch, self.dist
+        s = len(betas)
+        c_me = sum(((self.rank >> b) & 1) << i for i, b in enumerate(betas))
+        base = self.rank
+        for b in betas:
+            base &= ~(1 << b)
+        slab_bytes = self._state.element_size() * (2 << (sp.n_local - s))
+        src = []
+        for j in range(1 << s):
+            pr = base
+            for i, b in enumerate(betas):
+                pr |= ((j >> i) & 1) << b
+            src.append(self._peer_bufs[pr][self._cur].data_ptr() + c_me * slab_bytes)
+        dst = self._bufs[1 - self._cur]
+        t.cuda.synchronize()
+        dist.barrier(group=self.group)          # every peer has finished writing the buffers read below
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        h.set_shard(sp.g, sp.rank & mask)
+        h.run_gather_block(ops, tabs, src, dst.data_ptr())
+        e1.record()
+        t.cuda.synchronize()
+        dist.barrier(group=self.group)          # every peer has finished reading this rank's old buffer
+        self._cur = 1 - self._cur
+        self._state = dst
+        return e0.elapsed_time(e1)
 
     def _is_replica(self, sp):
         """This rank only mirrors another one (a global qubit that never materialised has bit 1 here)."""
@@ -723,6 +841,7 @@ class ShardedSimulator:
                             'meta': {'path': 'sharded', 'ranks': self.world, 'n_qubits': pr.prog.n_qubits,
                                      'n_phys': pr.plan.n_phys, 'n_local': pr.sp.n_local, 'passes': pr.plan.n_passes,
                                      'exchanges': pr.sp.n_exchanges, 'exchange_ms': self.exchange_ms,
+                                     'exchange_path': 'p2p-fused' if self._peer_bufs is not None else 'nccl',
                                      'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': i}})
         return Job(Result(entries, single, self._name, seed, int(shots), time.perf_counter() - t0))
 

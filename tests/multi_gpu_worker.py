@@ -32,9 +32,10 @@ def main():
         single.close()
         kp_full = np.abs(psi) ** 2
     for prec, tol in (('double', 1e-10), ('single', 1e-5)):
-        for fus, layout in (('blocked', 'auto'), ('blocked', 'canonical'), ('clique', 'canonical')):
+        for fus, layout, xch in (('blocked', 'auto', 'nccl'), ('blocked', 'canonical', 'nccl'), ('clique', 'canonical', 'nccl'),
+                                 ('clique', 'canonical', 'p2p')):
             sim = ShardedSimulator(precision=prec, fusion=fus, layout=layout, device=lr, seed=77, block_max=3,
-                                   staging_bytes=1 << 22)
+                                   staging_bytes=1 << 22, exchange=xch)
             res = sim.run(QCMRF(C, th), shots=200000).result()
             p, delta = res.postselected_probabilities(0)
             err = float(np.abs(p - pb).max())
@@ -43,6 +44,8 @@ def main():
             assert sum(counts.values()) == 200000
             meta = res.metadata(0)
             assert meta['exchanges'] == (1 if fus == 'clique' else 0), meta
+            if xch == 'p2p':
+                assert meta['exchange_path'] == 'p2p-fused', (meta, getattr(sim, 'p2p_error', None))
             # every rank must hold identical results
             blob = json.dumps(sorted(counts.items())) + repr(float(delta))
             gathered = [None] * world
@@ -64,7 +67,7 @@ def main():
                 assert tv < bound, (tv, bound)
                 succ = obs[: 1 << n].sum() / 2e5
                 assert abs(succ - db) < 5 * np.sqrt(db * (1 - db) / 2e5) + 1e-4, (succ, db)
-                report['%s/%s/%s' % (prec, fus, layout)] = {'max_p_err': err, 'tv': float(tv), 'exchanges': meta['exchanges']}
+                report['%s/%s/%s/%s' % (prec, fus, layout, xch)] = {'max_p_err': err, 'tv': float(tv), 'exchanges': meta['exchanges']}
             sim.close()
     if rank == 0:
         print('MULTI_GPU_OK ' + json.dumps(report), flush=True)

@@ -47,10 +47,11 @@ def _worker(rank, world, port, q):
             pb, db, _ = mrf.brute_force_pmf(C, th)
             psi, meas = sv.run_program(program.qcmrf_program(C, th)[0], N)
             kp = sv.key_probabilities(psi, N, meas)
-            for fus, layout, prec in (('blocked', 'auto', 'double'), ('blocked', 'canonical', 'double'),
-                                      ('clique', 'canonical', 'double'), ('clique', 'canonical', 'single')):
+            for fus, layout, prec, xch in (('blocked', 'auto', 'double', 'nccl'), ('blocked', 'canonical', 'double', 'nccl'),
+                                           ('clique', 'canonical', 'double', 'nccl'), ('clique', 'canonical', 'single', 'nccl'),
+                                           ('clique', 'canonical', 'double', 'p2p')):   # p2p on CPU: fused plan, fallback path
                 sim = CpuSharded(precision=prec, fusion=fus, layout=layout, block_max=2, seed=5,
-                                 staging_bytes=1 << 9)           # tiny staging: several chunks per exchange
+                                 staging_bytes=1 << 9, exchange=xch)   # tiny staging: several chunks per exchange
                 res = sim.run(QCMRF(C, th), shots=20000).result()
                 p, delta = res.postselected_probabilities(0)
                 tol = 1e-10 if prec == 'double' else 1e-5
@@ -65,7 +66,7 @@ def _worker(rank, world, port, q):
                 assert 0.5 * np.abs(obs / 2e4 - kp).sum() < 0.06
                 meta = res.metadata(0)
                 assert meta['exchanges'] == (1 if fus == 'clique' else 0)
-                out[(tuple(map(tuple, C)), fus, layout, prec)] = (dict(counts), float(delta))
+                out[(tuple(map(tuple, C)), fus, layout, prec, xch)] = (dict(counts), float(delta))
                 sim.close()
         q.put((rank, 'ok', out))
         dist.destroy_process_group()

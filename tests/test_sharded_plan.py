@@ -21,14 +21,14 @@ def _theta(C, seed):
 
 
 @pytest.mark.parametrize('g', [1, 2, 3])
-@pytest.mark.parametrize('mode', ['lazy-canonical', 'lazy-auto', 'dense'])
+@pytest.mark.parametrize('mode', ['lazy-canonical', 'lazy-auto', 'dense', 'dense-fused'])
 def test_qcmrf_sharded_matches_oracle(g, mode):
     for C, seed in CASES:
         th = _theta(C, seed)
         n, k, N, _ = program.sizes(C)
         want, _ = sv.run_program(program.qcmrf_program(C, th)[0], N)
         fc = fusion.fuse(ir.lower(QCMRF(C, th)), 'clique')
-        if mode == 'dense':
+        if mode.startswith('dense'):
             pl = fusion.plan(fc, lazy=False)
         elif mode == 'lazy-auto':
             if len(fusion.control_only_qubits(fc)) < g:
@@ -38,10 +38,14 @@ def test_qcmrf_sharded_matches_oracle(g, mode):
             pl = fusion.plan(fc, lazy=True, block_max=3)
         if pl.n_phys - g < 1:
             continue
-        psi, sps = vc.run_virtual(pl, g)
+        psi, sps = vc.run_virtual(pl, g, fuse_exchange=(mode == 'dense-fused'))
         got = vc.logical_state(pl, psi, sps)
         assert np.abs(got - want).max() < 1e-12, (C, mode, g)
-        if mode == 'dense':
+        if mode == 'dense-fused':
+            kinds = [seg[0] for seg in sps[0].segments]
+            assert kinds.count('xblock') == 1 and 'exchange' not in kinds     # swap + the last g clique sweeps: one kernel
+            assert kinds[-1] == 'xblock'
+        if mode.startswith('dense'):
             assert sps[0].n_exchanges == 1               # one all-to-all moves every global ancilla on-GPU
         else:
             assert sps[0].n_exchanges == 0               # lazily materialised: communication-free
@@ -70,7 +74,8 @@ def test_generic_circuit_with_repeated_global_targets(g):
     for lazy, mode in ((False, 'off'), (True, 'off'), (True, 'clique'), (False, 'clique')):
         fc = fusion.fuse(prog, mode)
         pl = fusion.plan(fc, lazy=lazy, block_max=2)
-        psi, sps = vc.run_virtual(pl, g)
-        got = vc.logical_state(pl, psi, sps)
-        assert np.abs(got - want).max() < 1e-12, (lazy, mode)
+        for fused in (False, True):
+            psi, sps = vc.run_virtual(pl, g, fuse_exchange=fused)
+            got = vc.logical_state(pl, psi, sps)
+            assert np.abs(got - want).max() < 1e-12, (lazy, mode, fused)
     assert sps[0].n_exchanges >= 1

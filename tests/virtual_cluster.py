@@ -11,10 +11,10 @@ class _P:
     pass
 
 
-def run_virtual(pl, g):
+def run_virtual(pl, g, fuse_exchange=False):
     """Returns (list of per-rank local states, list of ShardedPlans)."""
     world = 1 << g
-    sps = [sharded.shard_plan(pl, g, r) for r in range(world)]
+    sps = [sharded.shard_plan(pl, g, r, fuse_exchange=fuse_exchange) for r in range(world)]
     nl = sps[0].n_local
     psi = [None] * world
     act = [0] * world
@@ -48,6 +48,12 @@ def run_virtual(pl, g):
                         peer |= ((j >> i) & 1) << b
                     new[j] = old[peer][c]
                 psi[r] = new.reshape(-1)
+            if kind == 'xblock':                       # fused: the sweeps on the swapped-in qubits follow at once
+                for r, sp in enumerate(sps):
+                    _, _, ops, tabs, mask = sp.segments[si]
+                    p = _P()
+                    p.ops, p.tables, p.n_phys = ops, tabs, nl
+                    psi[r], act[r] = em.run_plan(p, n_global=g, rank=r & mask, n_local=nl, psi0=psi[r], active0=act[r])
     return psi, sps
 
 
