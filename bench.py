@@ -551,9 +551,9 @@ def dense_gate_pass(args, cliques, device, world=1):
         fx = [r for r in prof2 if r[0] == -2]
         s = world.bit_length() - 1
         if fx:
-            remote = fx[0][2] // 2 * (world - 1) // world
+            remote = fx[0][2] * (world - 1) // world        # every output pair takes 2^s inputs, all but one from peers
             out['fused_exchange'] = {'kernel': 'k_block_gather: qubit swap + the %d sweeps on the swapped-in qubits, peers read over '
-                                               'NVLink (CUDA IPC)' % s, 'ms': fx[0][1],
+                                               'NVLink (CUDA IPC, TMA bulk copies into a shared-memory ring)' % s, 'ms': fx[0][1],
                                      'replaces_ms': (ex[0][1] if ex else 0.0) + s * ms,
                                      'remote_bytes_read_per_gpu': remote, 'nvlink_gbs_per_gpu': remote / fx[0][1] / 1e6,
                                      'circuit_ms': sum(r[1] for r in prof2)}

@@ -193,6 +193,17 @@ int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint6
 /* cudaDeviceEnablePeerAccess(device -> peer), idempotent; needed before qcm_run_gather_block reads
  * buffers that live on `peer`.                                                                    */
 int qcm_enable_peer_access(int device, int peer);
+
+/* CUDA IPC for the peer mappings qcm_run_gather_block reads through (one process per GPU):
+ * qcm_ipc_export: handle (64 bytes) of the cudaMalloc allocation that contains dev_ptr + dev_ptr's
+ * offset inside it -- works on pointers handed out by a sub-allocator (torch's caching allocator).
+ * qcm_ipc_open: maps an exported allocation into THIS process with `device` (the GPU that will read
+ * it) current, cudaIpcMemLazyEnablePeerAccess; *base_out is the allocation's base (add the offset).
+ * One open per (process, allocation): the caller caches by handle bytes.  qcm_ipc_close unmaps.   */
+#define QCM_IPC_HANDLE_BYTES 64
+int qcm_ipc_export(int device, const void *dev_ptr, unsigned char *handle_out, uint64_t *offset_out);
+int qcm_ipc_open(int device, const unsigned char *handle, void **base_out);
+int qcm_ipc_close(int device, void *base);
 int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
                          const void *const *src_slabs, int s, void *dst_state);
 

@@ -38,7 +38,8 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_run_program', 'qcm_postselect', 'qcm_sample', 'qcm_sample_prepare', 'qcm_sample_sharded',
            'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
            'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile', 'qcm_postselect_device',
-           'qcm_sample_sharded_device', 'qcm_run_gather_block', 'qcm_enable_peer_access']
+           'qcm_sample_sharded_device', 'qcm_run_gather_block', 'qcm_enable_peer_access',
+           'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close']
 
 
 def lib():
@@ -78,6 +79,9 @@ def lib():
     L.qcm_sample_sharded_device.argtypes = [vp, u64, u64, u64, vp, i32, vp, i32, vp, vp]
     L.qcm_run_gather_block.argtypes = [vp, vp, i32, vp, ctypes.c_size_t, vp, i32, vp]
     L.qcm_enable_peer_access.argtypes = [i32, i32]
+    L.qcm_ipc_export.argtypes = [i32, vp, vp, vp]
+    L.qcm_ipc_open.argtypes = [i32, vp, vp]
+    L.qcm_ipc_close.argtypes = [i32, vp]
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
     assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
@@ -90,6 +94,31 @@ def enable_peer_access(device, peer):
     rc = lib().qcm_enable_peer_access(int(device), int(peer))
     if rc:
         raise NativeError(rc, (lib().qcm_last_error(None) or b'').decode())
+
+
+def _check_global(rc):
+    if rc:
+        raise NativeError(rc, (lib().qcm_last_error(None) or b'').decode())
+
+
+def ipc_export(device, dev_ptr):
+    """(handle bytes, offset) of the cudaMalloc allocation containing dev_ptr (qcm_ipc_export)."""
+    hd = (ctypes.c_ubyte * 64)()
+    off = ctypes.c_uint64()
+    _check_global(lib().qcm_ipc_export(int(device), ctypes.c_void_p(int(dev_ptr)), hd, ctypes.byref(off)))
+    return bytes(hd), off.value
+
+
+def ipc_open(device, handle):
+    """Map an exported allocation for kernels on `device`; returns its base address in this process."""
+    hd = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    base = ctypes.c_void_p()
+    _check_global(lib().qcm_ipc_open(int(device), hd, ctypes.byref(base)))
+    return base.value
+
+
+def ipc_close(device, base):
+    _check_global(lib().qcm_ipc_close(int(device), ctypes.c_void_p(int(base))))
 
 
 def device_count():

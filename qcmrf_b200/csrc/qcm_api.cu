@@ -617,9 +617,13 @@ int build_tree(qcm_handle h) {
     return tree_finish(h, na);
 }
 
-template <typename R, int V, int M>
-static int launch_gather_t(qcm_handle h, const GatherArgs &a, size_t smem) {
-    constexpr int U = 2;
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <typename R, int V, int M, int U>
+static int launch_gather_ldg(qcm_handle h, const GatherArgs &a, size_t smem) {
     auto kern = k_block_gather<R, V, M, U>;
     const uint64_t nvec = (1ull << (a.n_local - M)) / V;
     const uint64_t grid = std::min<uint64_t>(std::max<uint64_t>(1, (nvec + (uint64_t)kThreads * U - 1) / ((uint64_t)kThreads * U)), 0x7fffffffull);
@@ -627,6 +631,46 @@ static int launch_gather_t(qcm_handle h, const GatherArgs &a, size_t smem) {
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;
+}
+
+// stages of the TMA ring: as deep as keeps the ring at 64-96 KB for U = 1 (two CTAs per SM)
+template <int M> struct GatherStages { static constexpr int value = M == 1 ? 8 : (M == 2 ? 6 : 3); };
+
+template <typename R, int V, int M, int U>
+static int launch_gather_tma(qcm_handle h, const GatherArgs &a, size_t tab_bytes, int tiles_per_cta) {
+    constexpr int S = GatherStages<M>::value;
+    auto kern = k_block_gather_tma<R, V, M, U, S>;
+    const size_t smem = 256 + (size_t)S * (1 << M) * kGatherTileBytes * U + tab_bytes;
+    if (smem > 227 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "gather ring needs %zu B of shared memory", smem);
+    QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t tiles = ((1ull << (a.n_local - M)) / V) / ((uint64_t)kThreads * U);
+    while (tiles_per_cta > 1 && (tiles % tiles_per_cta || tiles / tiles_per_cta < 1)) tiles_per_cta >>= 1;
+    const uint64_t grid = tiles / tiles_per_cta;
+    if (grid > 0x7fffffffull) return fail(h, QCM_ERR_UNSUPPORTED, "gather grid too large");
+    kern<<<(unsigned)grid, kThreads + 32, smem, h->stream>>>(a, tiles_per_cta);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    return QCM_OK;
+}
+
+// QCM_GATHER = tma | ldg, QCM_GATHER_U = vectors per thread per tile, QCM_GATHER_K = tiles per CTA (tma): tuning knobs
+template <typename R, int V, int M>
+static int launch_gather_t(qcm_handle h, const GatherArgs &a, size_t tab_bytes) {
+    const char *mode = getenv("QCM_GATHER");
+    const bool want_tma = !(mode && !strcmp(mode, "ldg"));
+    const uint64_t nvec = (1ull << (a.n_local - M)) / V;
+    int U = env_int("QCM_GATHER_U", want_tma ? 1 : 2);
+    if (want_tma && nvec >= (uint64_t)kThreads * 2 && nvec % ((uint64_t)kThreads * 2) == 0) {
+        int K = env_int("QCM_GATHER_K", 16);
+        if (K < 1) K = 1;
+        int p2 = 1;
+        while (p2 * 2 <= K) p2 *= 2;                      // power of two, so it divides the tile count
+        if (U >= 2) return launch_gather_tma<R, V, M, 2>(h, a, tab_bytes, p2);
+        return launch_gather_tma<R, V, M, 1>(h, a, tab_bytes, p2);
+    }
+    if (U >= 4) return launch_gather_ldg<R, V, M, 4>(h, a, tab_bytes);
+    if (U <= 1) return launch_gather_ldg<R, V, M, 1>(h, a, tab_bytes);
+    return launch_gather_ldg<R, V, M, 2>(h, a, tab_bytes);
 }
 
 template <typename R, int V>
@@ -675,6 +719,55 @@ int qcm_enable_peer_access(int device, int peer) {
         e = cudaSuccess;
     }
     if (e != cudaSuccess) return fail(nullptr, QCM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer, cudaGetErrorString(e));
+    return QCM_OK;
+}
+
+int qcm_ipc_export(int device, const void *dev_ptr, unsigned char *handle_out, uint64_t *offset_out) {
+    if (!dev_ptr || !handle_out || !offset_out) return fail(nullptr, QCM_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == QCM_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, QCM_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    // base of the containing allocation: driver entry point through the runtime (no libcuda link dependency)
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    void *fp = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qr);
+    if (e != cudaSuccess || !fp) return fail(nullptr, QCM_ERR_CUDA, "cuMemGetAddressRange entry point: %s", cudaGetErrorString(e));
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int cr = reinterpret_cast<range_fn>(fp)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+    if (cr != 0) return fail(nullptr, QCM_ERR_CUDA, "cuMemGetAddressRange failed (CUresult %d)", cr);
+    cudaIpcMemHandle_t hd;
+    e = cudaIpcGetMemHandle(&hd, reinterpret_cast<void *>((uintptr_t)base));
+    if (e != cudaSuccess) return fail(nullptr, QCM_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    memcpy(handle_out, &hd, sizeof(hd));
+    *offset_out = (uint64_t)((uintptr_t)dev_ptr - (uintptr_t)base);
+    return QCM_OK;
+}
+
+int qcm_ipc_open(int device, const unsigned char *handle, void **base_out) {
+    if (!handle || !base_out) return fail(nullptr, QCM_ERR_INVALID, "NULL argument");
+    *base_out = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, QCM_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, sizeof(hd));
+    e = cudaIpcOpenMemHandle(base_out, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, QCM_ERR_CUDA, "cudaIpcOpenMemHandle on device %d: %s", device, cudaGetErrorString(e));
+    }
+    return QCM_OK;
+}
+
+int qcm_ipc_close(int device, void *base) {
+    if (!base) return QCM_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaIpcCloseMemHandle(base);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, QCM_ERR_CUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e));
+    }
     return QCM_OK;
 }
 

@@ -366,6 +366,151 @@ __global__ void __launch_bounds__(kThreads) k_block_gather(const __grid_constant
 }
 
 // ----------------------------------------------------------------------------------
+// The same fused pass with the peers' slabs streamed by the TMA engine (cp.async.bulk) through a
+// shared-memory ring: one producer thread keeps STAGES x 2^M bulk copies of kGatherTileBytes x U
+// in flight per CTA (NVLink reads need far more bytes in flight than a few LDG.128 per thread),
+// completion is counted on an mbarrier per stage (expect_tx), the 256 consumer threads take their
+// 2^M register vectors from shared memory, apply the members, store to the local output buffer and
+// release the stage (one arrive per warp).  A CTA handles K consecutive tiles, CTAs are
+// launched in address order.
+// ----------------------------------------------------------------------------------
+constexpr int kGatherTileBytes = kThreads * 16;         // one 16-byte vector per consumer thread
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <typename R, int V, int M, int U, int STAGES>
+__global__ void __launch_bounds__(kThreads + 32) k_block_gather_tma(const __grid_constant__ GatherArgs a, const int tiles_per_cta) {
+    constexpr int NR = 1 << M;
+    constexpr uint32_t kTile = kGatherTileBytes * U;             // bytes per source per stage
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);     // full[STAGES], empty[STAGES]
+    unsigned char *ring = smem_raw + 256;
+    R *tab = reinterpret_cast<R *>(ring + (size_t)STAGES * NR * kTile);
+    static_assert(2 * STAGES * 8 <= 256, "barrier block");
+    for (int g = 0; g < a.n_members; ++g) {
+        const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
+        R *dst = tab + a.mem[g].tab_off;
+        const int cnt = (a.mem[g].pos < 0 ? 2 : 8) << a.mem[g].n_ctrl;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < STAGES; ++st) {
+            mbar_init(smem_u32(bars + st), 1);                       // producer's arrive.expect_tx
+            mbar_init(smem_u32(bars + STAGES + st), kThreads / 32);  // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t slab = 1ull << (a.n_local - M);
+    const uint64_t tile0 = (uint64_t)blockIdx.x * tiles_per_cta;     // tile = kThreads * U vectors of V amplitudes
+    if (threadIdx.x >= kThreads) {
+        if (threadIdx.x == kThreads) {
+            for (int k = 0; k < tiles_per_cta; ++k) {
+                const int st = k % STAGES;
+                if (k >= STAGES) mbar_wait(smem_u32(bars + STAGES + st), ((k / STAGES) - 1) & 1);
+                const uint32_t full = smem_u32(bars + st);
+                mbar_expect_tx(full, NR * kTile);
+#pragma unroll
+                for (int r = 0; r < NR; ++r)
+                    bulk_g2s(smem_u32(ring + ((size_t)st * NR + r) * kTile),
+                             reinterpret_cast<const unsigned char *>(a.src[r]) + (tile0 + k) * kTile, kTile, full);
+            }
+        }
+        return;
+    }
+    using IO = VecIO<R, V>;
+    for (int k = 0; k < tiles_per_cta; ++k) {
+        const int st = k % STAGES;
+        mbar_wait(smem_u32(bars + st), (k / STAGES) & 1);
+        R ar[U][NR][V], ai[U][NR][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const unsigned char *sp = ring + ((size_t)st * NR + r) * kTile + ((size_t)u * kThreads + threadIdx.x) * 16;
+                if constexpr (V == 2) {
+                    const float4 t = *reinterpret_cast<const float4 *>(sp);
+                    ar[u][r][0] = t.x; ai[u][r][0] = t.y; ar[u][r][1] = t.z; ai[u][r][1] = t.w;
+                } else {
+                    const double2 d = *reinterpret_cast<const double2 *>(sp);
+                    ar[u][r][0] = d.x; ai[u][r][0] = d.y;
+                }
+            }
+        const uint64_t bv0 = (tile0 + k) * ((uint64_t)kThreads * U) + threadIdx.x;   // vector index of u = 0
+        for (int g = 0; g < a.n_members; ++g) {
+            const int pos = a.mem[g].pos;
+            const int nc = a.mem[g].n_ctrl;
+            const R *mt = tab + a.mem[g].tab_off;
+            const uint32_t low_bit = a.mem[g].low_bit;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t gi = ((bv0 + (uint64_t)u * kThreads) * V) | a.rank_bits;
+                uint32_t idx0 = 0;
+                if (a.ctrl_below_32) {
+                    const uint32_t lo = (uint32_t)gi;
+                    for (int j = 0; j < nc; ++j) idx0 |= ((lo >> a.mem[g].ctrl[j]) & 1u) << j;
+                } else {
+                    for (int j = 0; j < nc; ++j) idx0 |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const uint32_t idx = v ? (idx0 | low_bit) : idx0;
+                    if (pos < 0) {
+                        const R c = mt[2 * idx], sn = mt[2 * idx + 1];
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            const R x = ar[u][r][v], y = ai[u][r][v];
+                            ar[u][r][v] = c * x - sn * y;
+                            ai[u][r][v] = c * y + sn * x;
+                        }
+                        continue;
+                    }
+                    R m[8];
+                    load_m8<R>(mt + 8 * idx, m);
+                    switch (pos) {
+                        case 0: butterfly<R, V, NR, 0, false>(ar[u], ai[u], m, v, 0u); break;
+                        case 1: butterfly<R, V, NR, 1, false>(ar[u], ai[u], m, v, 0u); break;
+                        default: butterfly<R, V, NR, 2, false>(ar[u], ai[u], m, v, 0u); break;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                IO::store(a.dst, (uint64_t)r * slab + (bv0 + (uint64_t)u * kThreads) * V, ar[u][r], ai[u][r]);
+        // Release the stage only here, after the stores: they depend on the shared-memory loads above, so
+        // those have completed.  An arrive issued right behind the LDS can overtake them (LDS queue behind
+        // this SM's global stores, SYNCS does not): the producer's next bulk copy then lands in the stage
+        // while a warp is still reading it -- measured as rare 128-512 B stale chunks (tools/gather_check.py).
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(bars + STAGES + st));
+    }
+}
+
+// ----------------------------------------------------------------------------------
 // Expansion pass (lazy materialisation fast path).
 //
 // All M block qubits are the new qubits n_in .. n_in+M-1, each the target of exactly

@@ -387,7 +387,8 @@ class ShardedSimulator:
         # shard in memory; anything it cannot serve falls back to the NCCL all-to-all + local passes
         self.exchange = exchange
         self._bufs = None          # p2p: [A, B] local state tensors
-        self._peer_bufs = None     # p2p: rank -> [A, B] tensors mapped from that rank
+        self._peer_bufs = None     # p2p: rank -> [A, B] device addresses mapped from that rank (CUDA IPC)
+        self._ipc_open = {}
         self._cur = 0
         self._name = name
         self._h = None
@@ -428,24 +429,52 @@ class ShardedSimulator:
         return self._h
 
     def _map_peers(self):
-        """Second local buffer + CUDA-IPC mappings of every rank's two buffers (torch's own tensor
-        sharing machinery: cudaIpcGetMemHandle / cudaIpcOpenMemHandle under the hood)."""
+        """Second local buffer + CUDA-IPC mappings of every rank's two buffers, opened with THIS rank's
+        GPU current (qcm_ipc_open: cudaIpcOpenMemHandle + lazy peer access, the way NCCL's P2P transport
+        maps its peers), so kernels launched here dereference them over NVLink."""
         t, dist = self.torch, self.dist
-        from torch.multiprocessing.reductions import reduce_tensor
         other = t.empty_like(self._state)
         self._bufs = [self._state, other]
         self._cur = 0
-        meta = [reduce_tensor(x) for x in self._bufs]
+        meta = [_native.ipc_export(self.device, x.data_ptr()) for x in self._bufs]
         gathered = [None] * self.world
         dist.all_gather_object(gathered, meta, group=self.group)
-        self._peer_bufs = {}
-        for r in range(self.world):
-            if r == self.rank:
-                self._peer_bufs[r] = self._bufs
-            else:
-                self._peer_bufs[r] = [fn(*args) for fn, args in gathered[r]]
-                _native.enable_peer_access(self.device, self._peer_bufs[r][0].device.index)
-        dist.barrier(group=self.group)
+        peer_ptrs = {}
+        self._ipc_open = {}                              # handle bytes -> base address in this process
+        err = None
+        try:
+            for r in range(self.world):
+                if r == self.rank:
+                    peer_ptrs[r] = [x.data_ptr() for x in self._bufs]
+                    continue
+                ptrs = []
+                for hd, off in gathered[r]:
+                    if hd not in self._ipc_open:
+                        self._ipc_open[hd] = _native.ipc_open(self.device, hd)
+                    ptrs.append(self._ipc_open[hd] + off)
+                peer_ptrs[r] = ptrs
+        except Exception as e:
+            err = repr(e)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err, group=self.group)      # all ranks take the same path
+        if any(errs):
+            self._unmap_peers()
+            raise RuntimeError('peer mapping failed: %s' % [e for e in errs if e][0])
+        self._peer_bufs = peer_ptrs
+
+    def _unmap_peers(self):
+        if getattr(self, '_ipc_open', None):
+            for base in self._ipc_open.values():
+                try:
+                    _native.ipc_close(self.device, base)
+                except Exception:
+                    pass
+            self._ipc_open = {}
+            try:
+                self.torch.cuda.synchronize()
+                self.dist.barrier(group=self.group)      # nobody frees a buffer a peer still has mapped
+            except Exception:
+                pass
 
     def close(self):
         if self._h is not None:
@@ -454,6 +483,7 @@ class ShardedSimulator:
             except Exception:
                 pass
             self._h.close()
+        self._unmap_peers()
         self._h = self._state = self._stage = None
         self._bufs = self._peer_bufs = None
         self._n_local = None
@@ -600,7 +630,7 @@ class ShardedSimulator:
             pr = base
             for i, b in enumerate(betas):
                 pr |= ((j >> i) & 1) << b
-            src.append(self._peer_bufs[pr][self._cur].data_ptr() + c_me * slab_bytes)
+            src.append(self._peer_bufs[pr][self._cur] + c_me * slab_bytes)
         dst = self._bufs[1 - self._cur]
         t.cuda.synchronize()
         dist.barrier(group=self.group)          # every peer has finished writing the buffers read below

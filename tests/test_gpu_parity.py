@@ -596,13 +596,18 @@ def test_full_size_33_qubit_state():
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
 @pytest.mark.parametrize('s', [1, 2, 3])
-def test_gather_block_on_virtual_peers(precision, s):
+@pytest.mark.parametrize('variant', [('tma', 1, 32), ('tma', 2, 4), ('ldg', 2, 0), ('ldg', 4, 0)])
+def test_gather_block_on_virtual_peers(precision, s, variant, monkeypatch):
     """qcm_run_gather_block (fused qubit swap + blocked pass that reads the peers' shards): all 2^s
     'ranks' live on this GPU, so the peer pointers are ordinary device pointers; expected = numpy qubit
-    swap of the full state followed by the op semantics (engine emulator) per rank."""
+    swap of the full state followed by the op semantics (engine emulator) per rank.  Variants: the
+    TMA-ring kernel (deep enough that the ring wraps) and the plain 128-bit-load kernel."""
     import torch
+    monkeypatch.setenv('QCM_GATHER', variant[0])
+    monkeypatch.setenv('QCM_GATHER_U', str(variant[1]))
+    monkeypatch.setenv('QCM_GATHER_K', str(variant[2] or 16))
     rng = np.random.RandomState(50 + s)
-    nl = 11
+    nl = 15
     N = nl + s
     world = 1 << s
     cdt = np.complex128 if precision == 'double' else np.complex64
@@ -655,3 +660,44 @@ def test_gather_block_on_virtual_peers(precision, s):
         want, _ = em.run_plan(pl, n_global=s, rank=r, n_local=nl, psi0=init, active0=nl)
         worst = max(worst, np.abs(got - want).max())
     assert worst < (1e-12 if precision == 'double' else 3e-6)
+
+
+@pytest.mark.parametrize('s', [1, 2, 3])
+def test_gather_tma_ring_is_bit_identical_to_plain_loads(s, monkeypatch):
+    """The TMA-ring variant of the fused gather pass against the plain-load variant on a state large
+    enough for several resident CTAs per SM and many ring wraps, repeated: bit-identical every time
+    (guards the ring's stage release, see k_block_gather_tma)."""
+    import torch
+    nl = 24
+    world = 1 << s
+    rng = np.random.RandomState(7)
+    old = [torch.randn(2 << nl, dtype=torch.float32, device='cuda') for _ in range(world)]
+    out = torch.empty(2 << nl, dtype=torch.float32, device='cuda')
+    e = fusion._Emitter()
+    tq = list(range(nl - s, nl))
+    q, _ = np.linalg.qr(rng.randn(4, 2, 2) + 1j * rng.randn(4, 2, 2))
+    if s == 1:
+        e.op(fusion.QCM_OP_MUX1Q, target=tq[0], ctrl=[3, 7], n_in=nl, n_out=nl, table_off=e.table(fusion._mux_table_f64(q)))
+    else:
+        e.op(fusion.QCM_OP_BLOCK, target=s, ctrl=tq, n_in=nl, n_out=nl, n_ctrl=s)
+        for t in tq:
+            e.op(fusion.QCM_OP_MUX1Q, target=t, ctrl=[3, 7], n_in=nl, n_out=nl, table_off=e.table(fusion._mux_table_f64(q)))
+    ops, tabs = e.finish()
+    src = [x.data_ptr() for x in old]
+    with _native.Handle(nl, 'single', ext_state_ptr=old[0].data_ptr()) as h:
+        h.set_shard(s, 0)
+        h.set_active(nl)
+        monkeypatch.setenv('QCM_GATHER', 'ldg')
+        h.run_gather_block(ops, tabs, src, out.data_ptr())
+        torch.cuda.synchronize()
+        ref = out.clone()
+        monkeypatch.setenv('QCM_GATHER', 'tma')
+        for U, K in ((1, 16), (1, 64), (2, 16)):
+            monkeypatch.setenv('QCM_GATHER_U', str(U))
+            monkeypatch.setenv('QCM_GATHER_K', str(K))
+            for _ in range(10):
+                out.zero_()
+                torch.cuda.synchronize()
+                h.run_gather_block(ops, tabs, src, out.data_ptr())
+                torch.cuda.synchronize()
+                assert torch.equal(out, ref), (U, K)
