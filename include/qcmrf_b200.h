@@ -92,6 +92,13 @@ enum qcm_op_kind {
  * builds the sampler's sum tree on its 2^M-times smaller input and samples the new
  * qubits conditionally, instead of re-reading the whole result.                      */
 #define QCM_FLAG_SAMPLE_CHECKPOINT 1
+/* op.flags, on the LAST op of a program: the engine may store the result of that op in an
+ * engine-internal ("rotated") address order -- for a wide expansion pass, with the new qubits as
+ * the low address bits, which turns its 2^M write streams into one sequential stream.  Every
+ * entry point that reads the state (qcm_postselect*, qcm_sample*, qcm_get_amplitudes) undoes the
+ * rotation: callers keep seeing logical indices.  The next program must start with INIT_PRODUCT
+ * (or qcm_set_amplitudes); qcm_state_ptr contents are not in logical order until then.        */
+#define QCM_FLAG_ROTATED_OUTPUT_OK 2
 
 typedef struct qcm_op {
     int32_t kind;

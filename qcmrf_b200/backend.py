@@ -328,7 +328,10 @@ class B200Simulator:
         ops = pl.ops
         if (not shots or pr.virtual) and len(ops) and ops['flags'].any():
             ops = ops.copy()
-            ops['flags'] = 0                   # no shots follow: skip the sampler's checkpoint tree
+            if pr.virtual:
+                ops['flags'] = 0               # projection passes follow on the same state: plain layout, no checkpoint
+            else:
+                ops['flags'] &= ~fusion.QCM_FLAG_SAMPLE_CHECKPOINT     # no shots follow: skip the sampler's checkpoint tree
         h.run_program(ops, pl.tables)
         keys = None
         if shots and pr.virtual:

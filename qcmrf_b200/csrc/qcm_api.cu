@@ -41,6 +41,11 @@ struct qcm_sim_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     qcm_timing timing{};
     DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab, tilectr, subtree;
+    DevBuf scratch;                 // input copy of a rotated expansion pass
+    // rotated storage (QCM_FLAG_ROTATED_OUTPUT_OK): logical index i of the 2^n_active state lives at
+    // physical address ((i & (2^rot_nin - 1)) << rot_m) | (i >> rot_nin); rot_m == 0: identity
+    int rot_m = 0, rot_nin = 0;
+    bool tree_cond_low = false;     // the checkpoint tree's conditional images are the low address bits
     std::vector<double> h_top;
     // sum tree (built by qcm_sample_prepare)
     int tree_levels = 0;
@@ -157,6 +162,15 @@ int expand_threads() {
 // How k_expand's tiles are handed out (both in address order, see the kernel): 1 = persistent CTAs
 // pulling from a global counter (the coefficient table is staged once per CTA), 0 = one tile per CTA
 // in launch order.  QCM_EXPAND_SCHED=launch|counter overrides (tuning knob).
+int rotate_enabled() {
+    // QCM_ROTATE=0: keep the last expansion pass in logical address order (A/B measurement knob)
+    static int v = [] {
+        const char *e = getenv("QCM_ROTATE");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return v;
+}
+
 int expand_use_counter() {
     static int v = [] {
         const char *e = getenv("QCM_EXPAND_SCHED");
@@ -211,6 +225,7 @@ struct BlockPlan {
     ExpandTreeArgs trargs{};
     size_t tree_smem = 0;
     bool norm_preserving = false;   // expansion without diagonal members: sum_a |out[x,a]|^2 == |in[x]|^2
+    bool rotate = false;            // store the result rotated (k_expand_low); decided by the program loop
 };
 
 // members: ops[0..n_mem) are MUX1Q (or DIAG: a diagonal factor applied in the same sweep);
@@ -350,11 +365,49 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     return QCM_OK;
 }
 
+template <typename R, int V, int MH>
+static int launch_low(qcm_handle h, unsigned grid, BlockPlan &bp) {
+    auto kern = k_expand_low<R, V, MH>;
+    const size_t smem = low_warp_bytes<R, MH>() * (low_threads<R>() / 32) + bp.tree_smem;
+    if (smem > 200 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "rotated expansion needs %zu B of shared memory", smem);
+    if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, low_threads<R>(), smem, h->stream>>>(bp.trargs, h->scratch.p);
+    return QCM_OK;
+}
+
+template <typename R, int V>
+static int launch_low_mh(qcm_handle h, int MH, unsigned grid, BlockPlan &bp) {
+    switch (MH) {
+        case 0: return launch_low<R, V, 0>(h, grid, bp);
+        case 1: return launch_low<R, V, 1>(h, grid, bp);
+        case 2: return launch_low<R, V, 2>(h, grid, bp);
+        case 3:
+            if constexpr (V == 1) return launch_low<R, V, 3>(h, grid, bp);
+    }
+    return fail(h, QCM_ERR_INVALID, "rotated expansion: %d loop levels out of range", MH);
+}
+
 int launch_block_plan(qcm_handle h, BlockPlan &bp) {
     const BlockArgs &a = bp.args;
     const int M = bp.M, n_in = a.n_in, n_out = a.n_out;
     int rc;
-    if (bp.tree) {
+    if (bp.tree && bp.rotate) {
+        // sequential-write variant: input from a scratch copy, output rotated (see k_expand_low)
+        const size_t in_bytes = amp_bytes(h->prec) << n_in;
+        if ((rc = ensure(h, h->scratch, in_bytes))) return rc;
+        QCM_CUDA(h, cudaMemcpyAsync(h->scratch.p, h->state, in_bytes, cudaMemcpyDeviceToDevice, h->stream));
+        const unsigned grid = 1u << (n_in - kChunkBits);
+        if (h->prec == QCM_C64) rc = launch_low_mh<float, 2>(h, M - 6, grid, bp);
+        else rc = launch_low_mh<double, 1>(h, M - 5, grid, bp);
+        if (rc) return rc;
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+        h->n_expand++;
+        h->rot_m = M;
+        h->rot_nin = n_in;
+        h->timing.bytes_read += in_bytes;          // the scratch copy: one more read and write of the input
+        h->timing.bytes_written += in_bytes;
+    } else if (bp.tree) {
         const int V = (h->prec == QCM_C64 && n_in >= 1) ? 2 : 1;
         const int threads = bp.trargs.tree_out ? (1 << kChunkBits) / V : 256;     // fused tree: tile == chunk
         const uint64_t nvec = (1ull << n_in) / V;
@@ -851,7 +904,18 @@ int qcm_get_amplitudes(qcm_handle h, uint64_t first, uint64_t count, void *host_
     const size_t ab = amp_bytes(h->prec);
     const uint64_t valid = 1ull << h->n_active;          // beyond: implicit zeros
     const uint64_t vend = std::min(first + count, valid);
-    if (first < vend)
+    if (h->rot_m && first < vend) {
+        // rotated storage: fetch the active state and undo the rotation on the host (inspection path)
+        if (h->n_active > 30) return fail(h, QCM_ERR_UNSUPPORTED, "qcm_get_amplitudes on a rotated state of %d qubits", h->n_active);
+        std::vector<char> tmp((size_t)valid * ab);
+        QCM_CUDA(h, cudaMemcpyAsync(tmp.data(), h->state, (size_t)valid * ab, cudaMemcpyDeviceToHost, h->stream));
+        QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+        const uint64_t lowm = (1ull << h->rot_nin) - 1ull;
+        for (uint64_t i = first; i < vend; ++i) {
+            const uint64_t phys = ((i & lowm) << h->rot_m) | (i >> h->rot_nin);
+            memcpy((char *)host_out + (i - first) * ab, tmp.data() + phys * ab, ab);
+        }
+    } else if (first < vend)
         QCM_CUDA(h, cudaMemcpyAsync(host_out, (const char *)h->state + first * ab, (vend - first) * ab, cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaStreamSynchronize(h->stream));
     if (first + count > vend) {
@@ -872,6 +936,7 @@ int qcm_set_amplitudes(qcm_handle h, uint64_t first, uint64_t count, const void 
     QCM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n_active = n_active;
     h->tree_valid = false;
+    h->rot_m = h->rot_nin = 0;
     return QCM_OK;
 }
 
@@ -885,6 +950,7 @@ int qcm_state_ptr(qcm_handle h, void **dev_ptr_out, uint64_t *bytes_out) {
 int qcm_set_active(qcm_handle h, int n_active) {
     if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
     if (n_active < 0 || n_active > h->n_local) return fail(h, QCM_ERR_INVALID, "n_active out of range");
+    if (h->rot_m && n_active != h->n_active) return fail(h, QCM_ERR_INVALID, "the state is stored rotated; start a new program first");
     h->n_active = n_active;
     h->tree_valid = false;
     return QCM_OK;
@@ -923,6 +989,10 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
         const uint64_t rd0 = h->timing.bytes_read, wr0 = h->timing.bytes_written;
         if (op.kind != QCM_OP_INIT_PRODUCT && op.n_active_in != h->n_active)
             return fail(h, QCM_ERR_INVALID, "op %d expects %d materialised qubits, state has %d", i, op.n_active_in, h->n_active);
+        if (op.kind != QCM_OP_INIT_PRODUCT && h->rot_m)
+            return fail(h, QCM_ERR_INVALID, "op %d: the state is stored rotated (the previous program ended with "
+                        "QCM_FLAG_ROTATED_OUTPUT_OK); start with INIT_PRODUCT", i);
+        if (op.kind == QCM_OP_INIT_PRODUCT) h->rot_m = h->rot_nin = 0;
         switch (op.kind) {
             case QCM_OP_INIT_PRODUCT:
                 if ((rc = launch_init(h, op, n_tables))) return rc;
@@ -947,6 +1017,15 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 const bool last = (i + (op.kind == QCM_OP_BLOCK ? n_mem : 0)) == n_ops - 1;
                 bool checkpoint = last && (op.flags & QCM_FLAG_SAMPLE_CHECKPOINT) && bp.norm_preserving &&
                                   op.n_active_in >= kChunkBits;
+                // rotated output: last op, wide expansion on the product-tree path, enough image bits for a warp store
+                bp.rotate = last && (op.flags & QCM_FLAG_ROTATED_OUTPUT_OK) && bp.tree && rotate_enabled() &&
+                            op.n_active_in >= kChunkBits && bp.M >= (h->prec == QCM_C64 ? 6 : 5) &&
+                            op.n_active_out - op.n_active_in == bp.M;
+                if (bp.rotate) {                          // its product tables + the member tables must fit shared memory
+                    const int mh = bp.M - (h->prec == QCM_C64 ? 6 : 5);
+                    const size_t per_warp = ((size_t)512 << mh) + 12 * kLowRow * 2 * (h->prec == QCM_C64 ? 4 : 8) + 512;
+                    if (per_warp * (h->prec == QCM_C64 ? 16 : 8) + bp.tree_smem > 200 * 1024) bp.rotate = false;
+                }
                 int sub_bits = 0;
                 if (checkpoint) {
                     // level 0 of the tree: fused into the expansion pass (it reads every input amplitude
@@ -963,6 +1042,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 if (checkpoint) {
                     if ((rc = tree_finish(h, op.n_active_in))) return rc;
                     h->tree_cond_bits = bp.M;
+                    h->tree_cond_low = bp.rotate;
                     h->tree_sub_bits = sub_bits;
                     h->tree_has_sub = true;
                     h->tree_for_active = op.n_active_out;
@@ -1006,6 +1086,7 @@ int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const doubl
     if (!h || !ops || n_ops < 1 || !src_slabs || !dst_state) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if (s < 1 || s > QCM_MAX_GATHER || s > h->n_global || s >= h->n_local) return fail(h, QCM_ERR_INVALID, "cannot gather %d qubits", s);
     if (h->n_active != h->n_local) return fail(h, QCM_ERR_INVALID, "gather needs a fully materialised shard");
+    if (h->rot_m) return fail(h, QCM_ERR_INVALID, "gather on a rotated state");
     if (h->own_state) return fail(h, QCM_ERR_INVALID, "gather needs a caller-owned state buffer (ext_state): peers map it");
     int rc = check_device(h);
     if (rc) return rc;
@@ -1100,21 +1181,24 @@ static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_ou
         const int nb = std::min(n_out_bits, h->n_active);
         const uint64_t out_all = (1ull << nb) - 1ull;
         const bool contiguous = (lval == 0) && (lmask == (act_all & ~out_all));
+        // rotated storage: logical i lives at ((i & low) << rot_m) | (i >> rot_nin); the kept prefix
+        // (i < 2^nb <= 2^rot_nin) is then the stride-2^rot_m sequence i << rot_m
+        const int pshift = (h->rot_m && nb <= h->rot_nin) ? h->rot_m : 0;
         const int blocks = h->num_sms * 4;
         if ((rc = ensure(h, h->partial, (blocks + 1) * sizeof(double)))) return rc;
         if (probs_out && !dev && (rc = ensure(h, h->probs, nprob * sizeof(double)))) return rc;
         double *dprobs = probs_out ? (dev ? probs_out : (double *)h->probs.p) : nullptr;
-        if (contiguous) {
+        if (contiguous && (!h->rot_m || pshift)) {
             const uint64_t count = 1ull << nb;
             if (dprobs && count < nprob) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * sizeof(double), h->stream));
-            if (h->prec == QCM_C64) k_probs_prefix<float><<<blocks, kThreads, 0, h->stream>>>(h->state, count, dprobs, (double *)h->partial.p);
-            else k_probs_prefix<double><<<blocks, kThreads, 0, h->stream>>>(h->state, count, dprobs, (double *)h->partial.p);
+            if (h->prec == QCM_C64) k_probs_prefix<float><<<blocks, kThreads, 0, h->stream>>>(h->state, count, pshift, dprobs, (double *)h->partial.p);
+            else k_probs_prefix<double><<<blocks, kThreads, 0, h->stream>>>(h->state, count, pshift, dprobs, (double *)h->partial.p);
         } else {
             if (dprobs) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * sizeof(double), h->stream));
             if (h->prec == QCM_C64)
-                k_postselect_general<float><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, dprobs, (double *)h->partial.p);
+                k_postselect_general<float><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, h->rot_m, h->rot_nin, dprobs, (double *)h->partial.p);
             else
-                k_postselect_general<double><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, dprobs, (double *)h->partial.p);
+                k_postselect_general<double><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, h->rot_m, h->rot_nin, dprobs, (double *)h->partial.p);
         }
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
@@ -1171,6 +1255,9 @@ static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint
     a.state = h->state;
     a.n_active = h->tree_base_bits;
     a.cond_bits = h->tree_cond_bits;
+    a.cond_low = (h->tree_cond_bits && h->tree_cond_low) ? 1 : 0;
+    a.rot_m = h->rot_m;
+    a.rot_nin = h->rot_nin;
     a.sub = h->tree_has_sub ? (const double *)h->subtree.p : nullptr;
     a.sub_bits = h->tree_sub_bits;
     a.n_levels = h->tree_levels;

@@ -402,7 +402,7 @@ template <typename R, int V, int M, int U, int STAGES>
 __global__ void __launch_bounds__(kThreads + 32) k_block_gather_tma(const __grid_constant__ GatherArgs a, const int tiles_per_cta) {
     constexpr int NR = 1 << M;
     constexpr uint32_t kTile = kGatherTileBytes * U;             // bytes per source per stage
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);     // full[STAGES], empty[STAGES]
     unsigned char *ring = smem_raw + 256;
     R *tab = reinterpret_cast<R *>(ring + (size_t)STAGES * NR * kTile);
@@ -871,6 +871,201 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand_tree(const __grid_
 }
 
 // ----------------------------------------------------------------------------------
+// Wide expansion pass, ROTATED output (the last pass of a program; QCM_FLAG_ROTATED_OUTPUT_OK).
+//
+// Same maths as k_expand_tree, but the result is stored with the M new qubits as the LOW address
+// bits:   out_phys[(x << M) | a] = in[x] * prod_d diag_d[idx_d(x)] * prod_j f_j[a_j].
+// The 2^M images of an input amplitude are then one contiguous run and the whole pass is a single
+// sequential write stream (the layout k_init and memset reach 7.4-7.6 TB/s on) instead of 2^M
+// streams 2^n_in amplitudes apart (6.3-6.9 TB/s, tools/membench3.cu).  The engine undoes the
+// rotation in every reader (post-selection, sampler, qcm_get_amplitudes): callers keep seeing
+// logical indices x | a << n_in.
+//
+// A warp owns 32 inputs per batch (pairs, interleaved with the CTA's other warps).  Phase A (lane i
+// owns one input): one load, the sampler's sums, every table index of x, and the part of the product that does not depend
+// on the lane's image bits -- U[s][v] = in[x] * diag * f_0[v] * prod_{j >= LB} f_j[s_j] (LB = 5 + log2 V
+// image bits are covered by one warp store: vector slot v and the lane) -- parked in shared memory
+// together with the table offsets of the lane-indexed members.  Phase B (all lanes, one input at a
+// time, everything about x is a shared-memory broadcast): L = prod of the lane-indexed members'
+// factors at the lane's bits (LB - 1 - (V == 2) complex multiplies... 4), then out[s] = L * U[s] -- one
+// complex multiply per output amplitude, one 512-byte warp store per s, addresses ascending.
+// The input comes from a scratch copy (the output overwrites it).  A CTA covers 2^kChunkBits
+// inputs, so the sampler's level-0 sum is one value per CTA.
+// ----------------------------------------------------------------------------------
+constexpr int kLowRow = 33;                              // padded row of the lane-indexed product tables (bank spread)
+
+// shared memory per warp: U[NS][32] 16-byte vectors, A[4][33] + B[8][33] complex, 32 x 8 16-bit table offsets
+template <typename R, int MH> __host__ __device__ constexpr size_t low_warp_bytes() {
+    return (size_t)(1 << MH) * 32 * 16 + (size_t)12 * kLowRow * 2 * sizeof(R) + 32 * 16;
+}
+template <typename R> __host__ __device__ constexpr int low_threads() { return sizeof(R) == 4 ? 512 : 256; }
+
+template <typename R, int V, int MH>
+__global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_constant__ ExpandTreeArgs a, const void *__restrict__ in) {
+    constexpr int LB = V == 2 ? 6 : 5;                   // image bits covered by one warp store
+    constexpr int J0 = V == 2 ? 1 : 0;                   // first lane-indexed member (member 0 is the vector slot for V == 2)
+    constexpr int NS = 1 << MH;                          // warp stores per input
+    constexpr int M = LB + MH;
+    constexpr int kWarps = low_threads<R>() / 32;
+    static_assert(QCM_MAX_EXPAND == 8, "offset records hold 8 members");
+    using C2 = typename CplxOf<R>::T;
+    using V16 = typename VecIO<R, V>::T;                  // float4 (two complex64) or double2 (one complex128)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tab = reinterpret_cast<R *>(smem_raw + low_warp_bytes<R, MH>() * kWarps);
+    const R *gt = reinterpret_cast<const R *>(a.tables);
+    for (int j = 0; j < M; ++j) {                         // column 0 of every 2x2: (m00, m10)
+        const int n = 1 << a.mem[j].n_ctrl;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const R *src = gt + a.mem[j].src_off + 8 * i;
+            R *dst = tab + a.mem[j].tab_off + 4 * i;
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[4]; dst[3] = src[5];
+        }
+    }
+    for (int d = 0; d < a.n_diag; ++d) {
+        const int n = 2 << a.diag[d].n_ctrl;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tab[a.diag[d].tab_off + i] = gt[a.diag[d].src_off + i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + low_warp_bytes<R, MH>() * warp;
+    V16 *Us = reinterpret_cast<V16 *>(wbase);                                      // [NS][32]
+    C2 *As = reinterpret_cast<C2 *>(wbase + (size_t)NS * 32 * 16);                 // [4][kLowRow]
+    C2 *Bs = As + 4 * kLowRow;                                                     // [8][kLowRow]
+    uint16_t *Os = reinterpret_cast<uint16_t *>(Bs + 8 * kLowRow);                 // [32][8]
+    auto index_of = [&](const TreeMember &m, uint64_t gi) -> uint32_t {
+        uint32_t idx = 0;
+#pragma unroll 1
+        for (int j = 0; j < m.n_ctrl; ++j) idx |= (uint32_t)((gi >> m.ctrl[j]) & 1ull) << j;
+        return idx;
+    };
+    auto cmul = [](R ar, R ai, R br, R bi, R &cr, R &ci) { cr = ar * br - ai * bi; ci = ar * bi + ai * br; };
+    const C2 *my_a = As + (lane & 3) * kLowRow, *my_b = Bs + (lane >> 2) * kLowRow;
+    constexpr int kPerWarp = (1 << kChunkBits) / kWarps;                // inputs per warp per tile
+    const uint64_t tile = blockIdx.x;                                   // grid = 2^(n_in - kChunkBits), launch = address order
+    double wacc = 0.0;
+#pragma unroll 1
+    for (int batch = 0; batch < kPerWarp / 32; ++batch) {
+        // The warps of a CTA interleave at a granularity of two inputs (a pair shares the sampler's finest
+        // sum): at step i of phase B the warps write runs 2 * 2^M amplitudes apart, so the CTA's stores
+        // stay inside one moving window instead of one stream per warp (DRAM row locality).
+        const uint64_t x0 = (tile << kChunkBits) + (uint64_t)batch * (32 * kWarps) + 2u * warp;
+        auto x_of = [&](int i) -> uint64_t { return x0 + (uint64_t)(i >> 1) * (2 * kWarps) + (i & 1); };
+        // ---- phase A: lane i prepares input x_of(i)
+        {
+            const uint64_t x = x_of(lane);
+            const uint64_t gi = x | a.rank_bits;
+            const C2 mine = reinterpret_cast<const C2 *>(in)[x];
+            if (a.tree_out) {
+                const double w = (double)mine.x * (double)mine.x + (double)mine.y * (double)mine.y;
+                if constexpr (V == 2) {
+                    const double w2 = w + __shfl_xor_sync(0xffffffffu, w, 1);
+                    if (!(lane & 1)) a.sub_out[x >> 1] = w2;
+                } else {
+                    a.sub_out[x] = w;
+                }
+                wacc += w;
+            }
+            R pr = mine.x, pi = mine.y;
+#pragma unroll 1
+            for (int d = 0; d < a.n_diag; ++d) {
+                const uint32_t idx = index_of(a.diag[d], gi);
+                cmul(pr, pi, tab[a.diag[d].tab_off + 2 * idx], tab[a.diag[d].tab_off + 2 * idx + 1], pr, pi);
+            }
+            __syncwarp();                                 // the previous batch's phase B is done with the tables
+#pragma unroll 1
+            for (int j = 0; j < M; ++j) Os[lane * 8 + j] = (uint16_t)((uint32_t)a.mem[j].tab_off + 4u * index_of(a.mem[j], gi));
+            const uint4 ow = *reinterpret_cast<const uint4 *>(Os + lane * 8);
+            const uint32_t off[8] = {ow.x & 0xffffu, ow.x >> 16, ow.y & 0xffffu, ow.y >> 16,
+                                     ow.z & 0xffffu, ow.z >> 16, ow.w & 0xffffu, ow.w >> 16};
+            auto fac = [&](int member, int bit, R &fr, R &fi) {          // f_member[bit] at this input's table index
+                const C2 f = *reinterpret_cast<const C2 *>(tab + off[member] + 2 * bit);
+                fr = f.x; fi = f.y;
+            };
+            // U[s][v] = in * diag * f_0[v] * prod_{l < MH} f_{LB+l}[s_l]
+            R qr[V], qi[V];
+            if constexpr (V == 2) {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    R fr, fi;
+                    fac(0, v, fr, fi);
+                    cmul(pr, pi, fr, fi, qr[v], qi[v]);
+                }
+            } else {
+                qr[0] = pr; qi[0] = pi;
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                R gr = R(1), gim = R(0);
+#pragma unroll
+                for (int l = 0; l < MH; ++l) {
+                    R fr, fi;
+                    fac(LB + l, (s >> l) & 1, fr, fi);
+                    cmul(gr, gim, fr, fi, gr, gim);
+                }
+                R ur[V], ui[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) cmul(qr[v], qi[v], gr, gim, ur[v], ui[v]);
+                if constexpr (V == 2) Us[s * 32 + lane] = make_float4(ur[0], ui[0], ur[1], ui[1]);
+                else Us[s * 32 + lane] = make_double2(ur[0], ui[0]);
+            }
+            // A[a] = f_{J0}[a_0] f_{J0+1}[a_1],  B[b] = f_{J0+2}[b_0] f_{J0+3}[b_1] f_{J0+4}[b_2]  (lane = a | b << 2)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                R xr, xi, yr, yi;
+                fac(J0, t & 1, xr, xi);
+                fac(J0 + 1, t >> 1, yr, yi);
+                C2 o;
+                cmul(xr, xi, yr, yi, o.x, o.y);
+                As[t * kLowRow + lane] = o;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                R xr, xi, yr, yi, zr, zi;
+                fac(J0 + 2, t & 1, xr, xi);
+                fac(J0 + 3, (t >> 1) & 1, yr, yi);
+                fac(J0 + 4, t >> 2, zr, zi);
+                cmul(xr, xi, yr, yi, xr, xi);
+                C2 o;
+                cmul(xr, xi, zr, zi, o.x, o.y);
+                Bs[t * kLowRow + lane] = o;
+            }
+            __syncwarp();
+        }
+        // ---- phase B: all lanes, one input at a time
+#pragma unroll 2
+        for (int i = 0; i < 32; ++i) {
+            const C2 fa = my_a[i], fb = my_b[i];
+            R lr, li;
+            cmul(fa.x, fa.y, fb.x, fb.y, lr, li);
+            const uint64_t obase = (x_of(i) << M) + (uint64_t)lane * V;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const V16 u = Us[s * 32 + i];
+                R orr[V], oi[V];
+                if constexpr (V == 2) {
+                    cmul(lr, li, u.x, u.y, orr[0], oi[0]);
+                    cmul(lr, li, u.z, u.w, orr[1], oi[1]);
+                } else {
+                    cmul(lr, li, u.x, u.y, orr[0], oi[0]);
+                }
+                VecIO<R, V>::store(a.state, obase + ((uint64_t)s << LB), orr, oi);
+            }
+        }
+    }
+    if (a.tree_out) {
+        __shared__ double s_w[kWarps];
+        wacc = warp_sum(wacc);
+        if (lane == 0) s_w[warp] = wacc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < kWarps; ++i) t += s_w[i];
+            a.tree_out[tile] = t;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
 // Diagonal pass: amp *= table[index bits]
 // ----------------------------------------------------------------------------------
 struct DiagArgs {
@@ -1167,6 +1362,9 @@ struct SampleArgs {
     int32_t cond_bits;              // > 0: the state holds 2^cond_bits images of every leaf x, at
                                     // x | a << n_active (an expansion pass ran after the tree was built):
                                     // leaf weight = sum_a |amp|^2, then a is drawn given x
+    int32_t cond_low;               // the images are the LOW address bits: (x << cond_bits) | a  (rotated expansion)
+    int32_t rot_m, rot_nin;         // rotated storage without a checkpoint tree: the tree indexes physical
+                                    // addresses p; logical index = (p >> rot_m) | ((p & (2^rot_m - 1)) << rot_nin)
     int32_t n_levels;               // tree levels above the amplitudes (>= 1)
     const double *sub;              // optional finer level under level[0]: sums over 2^sub_bits amplitudes
     int32_t sub_bits;
@@ -1229,7 +1427,12 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
         // leaf: the remaining x's, each with its 2^cond_bits images -- one flat, lane-strided search over
         // the (x, image) pairs (image-major, so that consecutive lanes read consecutive amplitudes)
         uint64_t within;
-        {
+        if (a.cond_low) {
+            // rotated expansion: the (x, image) pairs of the leaf are one contiguous run, x-major
+            const uint32_t c = warp_pick([&](uint32_t i) { return amp_w((afirst << a.cond_bits) + i); },
+                                         leaf_cnt * (uint32_t)nb, u, lane);
+            within = (uint64_t)(c >> a.cond_bits) + ((uint64_t)(c & (uint32_t)(nb - 1)) << a.n_active);
+        } else {
             const uint32_t lbits = 31u - (uint32_t)__clz(leaf_cnt);
             const uint32_t c = warp_pick(
                 [&](uint32_t i) { return amp_w(afirst + (i & (leaf_cnt - 1u)) + ((uint64_t)(i >> lbits) << a.n_active)); },
@@ -1237,7 +1440,9 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
             within = (uint64_t)(c & (leaf_cnt - 1u)) + ((uint64_t)(c >> lbits) << a.n_active);
         }
         if (lane == 0) {
-            const uint64_t gi = (afirst + within) | a.rank_bits;
+            uint64_t li = afirst + within;
+            if (a.rot_m && !a.cond_bits) li = (li >> a.rot_m) | ((li & ((1ull << a.rot_m) - 1ull)) << a.rot_nin);
+            const uint64_t gi = li | a.rank_bits;
             uint64_t key = gi;
             if (a.n_clbits > 0) {
                 key = 0;
@@ -1257,17 +1462,17 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
 // contiguous kept set (QCMRF: the first 2^n amplitudes): probs[i] = |amp_i|^2 and a
 // deterministic two-stage sum (per-block partials, then k_tree_level).
 template <typename R>
-__global__ void __launch_bounds__(kThreads) k_probs_prefix(const void *state, uint64_t count, double *probs, double *partial) {
+__global__ void __launch_bounds__(kThreads) k_probs_prefix(const void *state, uint64_t count, int shift, double *probs, double *partial) {
     __shared__ double wsum[kThreads / 32];
     double acc = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         double w;
         if constexpr (sizeof(R) == 4) {
-            const float2 t = reinterpret_cast<const float2 *>(state)[i];
+            const float2 t = reinterpret_cast<const float2 *>(state)[i << shift];
             w = (double)t.x * (double)t.x + (double)t.y * (double)t.y;
         } else {
-            const double2 t = reinterpret_cast<const double2 *>(state)[i];
+            const double2 t = reinterpret_cast<const double2 *>(state)[i << shift];
             w = t.x * t.x + t.y * t.y;
         }
         if (probs) probs[i] = w;
@@ -1287,13 +1492,15 @@ __global__ void __launch_bounds__(kThreads) k_probs_prefix(const void *state, ui
 template <typename R>
 __global__ void __launch_bounds__(kThreads) k_postselect_general(const void *state, int n_active, uint64_t rank_bits,
                                                                   uint64_t mask, uint64_t value, uint64_t out_mask,
-                                                                  double *probs, double *partial) {
+                                                                  int rot_m, int rot_nin, double *probs, double *partial) {
     __shared__ double wsum[kThreads / 32];
     double acc = 0.0;
     const uint64_t count = 1ull << n_active;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-        const uint64_t gi = i | rank_bits;
+        // i walks physical addresses; rotated storage: logical = (i >> rot_m) | ((i & (2^rot_m - 1)) << rot_nin)
+        const uint64_t li = rot_m ? ((i >> rot_m) | ((i & ((1ull << rot_m) - 1ull)) << rot_nin)) : i;
+        const uint64_t gi = li | rank_bits;
         if ((gi & mask) != value) continue;
         double w;
         if constexpr (sizeof(R) == 4) {

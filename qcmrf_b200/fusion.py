@@ -581,16 +581,19 @@ def _diag_table_f64(table):
 
 
 QCM_FLAG_SAMPLE_CHECKPOINT = 1
+QCM_FLAG_ROTATED_OUTPUT_OK = 2          # the engine may store the last pass's result in its own address order
 
 
 def _flag_last_pass(ops):
-    """Set QCM_FLAG_SAMPLE_CHECKPOINT on the header of the program's last pass."""
+    """Set QCM_FLAG_SAMPLE_CHECKPOINT | QCM_FLAG_ROTATED_OUTPUT_OK on the header of the program's last
+    pass: shots will be drawn from it, and nothing but post-selection / sampling / read-back follows, so
+    a wide expansion may write its result as one sequential stream (include/qcmrf_b200.h)."""
     i, last = 0, -1
     while i < len(ops):
         last = i
         i += 1 + (int(ops[i]['n_ctrl']) if ops[i]['kind'] == QCM_OP_BLOCK else 0)
     if last >= 0 and ops[last]['kind'] in (QCM_OP_BLOCK, QCM_OP_MUX1Q):
-        ops[last]['flags'] = QCM_FLAG_SAMPLE_CHECKPOINT
+        ops[last]['flags'] = QCM_FLAG_SAMPLE_CHECKPOINT | QCM_FLAG_ROTATED_OUTPUT_OK
 
 
 def split_releasable(fc: FusedCircuit, keep_below: int = 0):

@@ -580,7 +580,7 @@ class ShardedSimulator:
                 _, ops, tabs, mask = seg
                 if not keep_flags and ops['flags'].any():
                     ops = ops.copy()
-                    ops['flags'] = 0               # no shots follow: skip the sampler's checkpoint tree
+                    ops['flags'] &= ~fusion.QCM_FLAG_SAMPLE_CHECKPOINT     # no shots follow: skip the sampler's checkpoint tree
                 h.set_shard(sp.g, sp.rank & mask)
                 h.run_program(ops, tabs)
                 self._profile.extend(h.op_profile())

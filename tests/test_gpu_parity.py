@@ -471,7 +471,7 @@ def test_sampling_checkpoint_matches_full_tree(precision, Ms):
     rng = np.random.RandomState(5)
     n0 = 11
     ops, tabs, act = _expansion_program(rng, n0, Ms, False, True)
-    assert ops['flags'].sum() == 1
+    assert ops['flags'].sum() == 3            # checkpoint + rotated-output permission on the last pass
     S = 400000
     with _native.Handle(act, precision) as h:
         h.run_program(ops, tabs)
@@ -701,3 +701,53 @@ def test_gather_tma_ring_is_bit_identical_to_plain_loads(s, monkeypatch):
                 h.run_gather_block(ops, tabs, src, out.data_ptr())
                 torch.cuda.synchronize()
                 assert torch.equal(out, ref), (U, K)
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('with_diag', [False, True])
+@pytest.mark.parametrize('flags', [2, 3])
+def test_rotated_expansion_is_transparent(precision, with_diag, flags):
+    """QCM_FLAG_ROTATED_OUTPUT_OK: the last wide expansion pass stores its result with the new qubits as
+    the low address bits (k_expand_low: one sequential write stream).  Every reader undoes the rotation:
+    amplitudes, post-selection (prefix and general masks) and shots are those of the logical state."""
+    rng = np.random.RandomState(91 + flags)
+    tol = 1e-12 if precision == 'double' else 3e-6
+    for n0, Ms in ((10, [8]), (11, [6]), (10, [2, 7]), (12, [5]), (13, [8])):
+        ops, tabs, act = _expansion_program(rng, n0, Ms, with_diag, False)
+        fusion._flag_last_pass(ops)
+        ops['flags'][ops['flags'] != 0] = flags
+        pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, act
+        want, _ = em.run_plan(pl)
+        pw = np.abs(want) ** 2
+        with _native.Handle(act, precision) as h:
+            h.run_program(ops, tabs)
+            got = h.get_amplitudes().astype(np.complex128)
+            assert np.abs(got - want).max() < tol, (n0, Ms)
+            part = h.get_amplitudes(5, 1000).astype(np.complex128)
+            assert np.abs(part - want[5:1005]).max() < tol
+            # prefix post-selection: every qubit >= nb on 0
+            for nb in (n0, n0 - 3, act - Ms[-1]):
+                mask = ((1 << act) - 1) & ~((1 << nb) - 1)
+                p, kept = h.postselect(mask, 0, nb)
+                assert np.abs(p - pw[:1 << nb]).max() < 10 * tol and abs(kept - pw[:1 << nb].sum()) < 10 * tol
+            # general mask: a new qubit on 1, an old one on 0; marginal over the low 6 qubits
+            mask, value = (1 << (act - 1)) | (1 << 7), 1 << (act - 1)
+            p, kept = h.postselect(mask, value, 6)
+            idx = np.arange(1 << act)
+            sel = (idx & mask) == value
+            wantp = np.bincount(idx[sel] & 63, weights=pw[sel], minlength=64)
+            assert np.abs(p - wantp).max() < 10 * tol and abs(kept - pw[sel].sum()) < 10 * tol
+            S = 200000
+            k = h.sample(S, seed=3, stream_id=1).astype(np.int64)
+            assert np.all(pw[k] > 0)
+            emp = np.bincount(k, minlength=1 << act) / S
+            assert 0.5 * np.abs(emp - pw / pw.sum()).sum() < weissman_tv_bound(int((pw > 0).sum()), S)
+            M = Ms[-1]
+            for shift, bits in ((act - M, M), (0, 8)):
+                wm = np.bincount((idx >> shift) & ((1 << bits) - 1), weights=pw / pw.sum(), minlength=1 << bits)
+                gm = np.bincount((k >> shift) & ((1 << bits) - 1), minlength=1 << bits) / S
+                assert 0.5 * np.abs(gm - wm).sum() < weissman_tv_bound(1 << bits, S)
+            # the next program starts from INIT: plain again
+            plain = ops.copy(); plain['flags'] = 0
+            h.run_program(plain, tabs)
+            assert np.abs(h.get_amplitudes().astype(np.complex128) - want).max() < tol
