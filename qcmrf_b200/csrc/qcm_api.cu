@@ -42,6 +42,7 @@ struct qcm_sim_s {
     qcm_timing timing{};
     DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab, tilectr, subtree;
     DevBuf scratch;                 // input copy of a rotated expansion pass
+    DevBuf lowpart;                 // its per-CTA partial sums when a CTA covers fewer inputs than a tree chunk
     // rotated storage (QCM_FLAG_ROTATED_OUTPUT_OK): logical index i of the 2^n_active state lives at
     // physical address ((i & (2^rot_nin - 1)) << rot_m) | (i >> rot_nin); rot_m == 0: identity
     int rot_m = 0, rot_nin = 0;
@@ -226,6 +227,7 @@ struct BlockPlan {
     size_t tree_smem = 0;
     bool norm_preserving = false;   // expansion without diagonal members: sum_a |out[x,a]|^2 == |in[x]|^2
     bool rotate = false;            // store the result rotated (k_expand_low); decided by the program loop
+    bool input_in_scratch = false;  // ... and its input already lives in h->scratch (the program prefix ran there)
 };
 
 // members: ops[0..n_mem) are MUX1Q (or DIAG: a diagonal factor applied in the same sweep);
@@ -365,24 +367,58 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     return QCM_OK;
 }
 
-template <typename R, int V, int MH>
-static int launch_low(qcm_handle h, unsigned grid, BlockPlan &bp) {
-    auto kern = k_expand_low<R, V, MH>;
+int low_tile_bits() {
+    // QCM_LOW_TB: log2 of the inputs per CTA of the rotated expansion pass (10, 8 or 7): tuning knob.
+    // q34 last pass on a B200: 9.83 ms with 1024 inputs per CTA, 9.70 ms with 256 (profiles/r01_notes.md)
+    static int v = [] {
+        const char *e = getenv("QCM_LOW_TB");
+        const int t = e ? atoi(e) : 8;
+        return (t == 10 || t == 7) ? t : 8;
+    }();
+    return v;
+}
+
+template <typename R, int V, int MH, int TB>
+static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
+    auto kern = k_expand_low<R, V, MH, TB>;
     const size_t smem = low_warp_bytes<R, MH>() * (low_threads<R>() / 32) + bp.tree_smem;
     if (smem > 200 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "rotated expansion needs %zu B of shared memory", smem);
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, low_threads<R>(), smem, h->stream>>>(bp.trargs, h->scratch.p);
+    ExpandTreeArgs args = bp.trargs;
+    double *level0 = args.tree_out;
+    if (level0 && TB != kChunkBits) {                      // per-CTA partial sums, grouped into level 0 below
+        int rc = ensure(h, h->lowpart, sizeof(double) << (n_in - TB));
+        if (rc) return rc;
+        args.tree_out = (double *)h->lowpart.p;
+    }
+    kern<<<1u << (n_in - TB), low_threads<R>(), smem, h->stream>>>(args, h->scratch.p);
+    QCM_CUDA(h, cudaGetLastError());
+    if (level0 && TB != kChunkBits) {
+        const uint64_t n_out = 1ull << (n_in - kChunkBits);
+        k_group_sum<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>((const double *)h->lowpart.p, kChunkBits - TB, n_out, level0);
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+    }
     return QCM_OK;
 }
 
+template <typename R, int V, int MH>
+static int launch_low(qcm_handle h, int n_in, BlockPlan &bp) {
+    const int tb = low_tile_bits();
+    if (tb == 10) return launch_low_tb<R, V, MH, 10>(h, n_in, bp);
+    if constexpr (low_threads<R>() <= 128)
+        if (tb == 7) return launch_low_tb<R, V, MH, 7>(h, n_in, bp);
+    return launch_low_tb<R, V, MH, 8>(h, n_in, bp);
+}
+
 template <typename R, int V>
-static int launch_low_mh(qcm_handle h, int MH, unsigned grid, BlockPlan &bp) {
+static int launch_low_mh(qcm_handle h, int MH, int n_in, BlockPlan &bp) {
     switch (MH) {
-        case 0: return launch_low<R, V, 0>(h, grid, bp);
-        case 1: return launch_low<R, V, 1>(h, grid, bp);
-        case 2: return launch_low<R, V, 2>(h, grid, bp);
+        case 0: return launch_low<R, V, 0>(h, n_in, bp);
+        case 1: return launch_low<R, V, 1>(h, n_in, bp);
+        case 2: return launch_low<R, V, 2>(h, n_in, bp);
         case 3:
-            if constexpr (V == 1) return launch_low<R, V, 3>(h, grid, bp);
+            if constexpr (V == 1) return launch_low<R, V, 3>(h, n_in, bp);
     }
     return fail(h, QCM_ERR_INVALID, "rotated expansion: %d loop levels out of range", MH);
 }
@@ -394,19 +430,20 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
     if (bp.tree && bp.rotate) {
         // sequential-write variant: input from a scratch copy, output rotated (see k_expand_low)
         const size_t in_bytes = amp_bytes(h->prec) << n_in;
-        if ((rc = ensure(h, h->scratch, in_bytes))) return rc;
-        QCM_CUDA(h, cudaMemcpyAsync(h->scratch.p, h->state, in_bytes, cudaMemcpyDeviceToDevice, h->stream));
-        const unsigned grid = 1u << (n_in - kChunkBits);
-        if (h->prec == QCM_C64) rc = launch_low_mh<float, 2>(h, M - 6, grid, bp);
-        else rc = launch_low_mh<double, 1>(h, M - 5, grid, bp);
+        if (!bp.input_in_scratch) {
+            if ((rc = ensure(h, h->scratch, in_bytes))) return rc;
+            QCM_CUDA(h, cudaMemcpyAsync(h->scratch.p, h->state, in_bytes, cudaMemcpyDeviceToDevice, h->stream));
+            h->timing.bytes_read += in_bytes;      // the scratch copy: one more read and write of the input
+            h->timing.bytes_written += in_bytes;
+        }
+        if (h->prec == QCM_C64) rc = launch_low_mh<float, 2>(h, M - 6, n_in, bp);
+        else rc = launch_low_mh<double, 1>(h, M - 5, n_in, bp);
         if (rc) return rc;
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
         h->n_expand++;
         h->rot_m = M;
         h->rot_nin = n_in;
-        h->timing.bytes_read += in_bytes;          // the scratch copy: one more read and write of the input
-        h->timing.bytes_written += in_bytes;
     } else if (bp.tree) {
         const int V = (h->prec == QCM_C64 && n_in >= 1) ? 2 : 1;
         const int threads = bp.trargs.tree_out ? (1 << kChunkBits) / V : 256;     // fused tree: tile == chunk
@@ -868,7 +905,7 @@ int qcm_destroy(qcm_handle h) {
     if (!h) return QCM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree};
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree, &h->scratch, &h->lowpart};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->own_state && h->state) cudaFree(h->state);
@@ -984,9 +1021,42 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
         return cudaEventRecord(h->op_ev[n_ev++], h->stream);
     };
     QCM_CUDA(h, mark());
+    // Rotated last pass (QCM_FLAG_ROTATED_OUTPUT_OK): its kernel reads the input out of place.  When the
+    // program starts from INIT_PRODUCT, everything before the last op fits that input buffer, so the
+    // whole prefix runs IN the scratch buffer and no copy is needed; otherwise the input is copied.
+    struct StateGuard {
+        qcm_handle h; void *real;
+        ~StateGuard() { if (real) h->state = real; }
+    } guard{h, nullptr};
+    int prefix_until = -1;
+    {
+        int li = -1;
+        for (int i = 0; i < n_ops;) {
+            li = i;
+            i += 1 + (ops[i].kind == QCM_OP_BLOCK ? std::max(0, ops[i].n_ctrl) : 0);
+        }
+        if (li > 0 && ops[0].kind == QCM_OP_INIT_PRODUCT && ops[li].kind == QCM_OP_BLOCK &&
+            (ops[li].flags & QCM_FLAG_ROTATED_OUTPUT_OK) && rotate_enabled() && li + ops[li].n_ctrl == n_ops - 1) {
+            const int n_in = ops[li].n_active_in;
+            bool fits = n_in >= kChunkBits && n_in <= h->n_local;
+            for (int i = 0; i < li && fits; ++i) fits = ops[i].n_active_out <= n_in && ops[i].n_active_in <= n_in;
+            if (fits) {
+                if ((rc = ensure(h, h->scratch, amp_bytes(h->prec) << n_in))) return rc;
+                guard.real = h->state;
+                h->state = h->scratch.p;
+                prefix_until = li;
+            }
+        }
+    }
     for (int i = 0; i < n_ops; ++i) {
         const qcm_op &op = ops[i];
         const uint64_t rd0 = h->timing.bytes_read, wr0 = h->timing.bytes_written;
+        bool input_in_scratch = false;
+        if (i == prefix_until) {                          // the last op: back to the real state buffer
+            h->state = guard.real;
+            guard.real = nullptr;
+            input_in_scratch = true;
+        }
         if (op.kind != QCM_OP_INIT_PRODUCT && op.n_active_in != h->n_active)
             return fail(h, QCM_ERR_INVALID, "op %d expects %d materialised qubits, state has %d", i, op.n_active_in, h->n_active);
         if (op.kind != QCM_OP_INIT_PRODUCT && h->rot_m)
@@ -1023,8 +1093,13 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                             op.n_active_out - op.n_active_in == bp.M;
                 if (bp.rotate) {                          // its product tables + the member tables must fit shared memory
                     const int mh = bp.M - (h->prec == QCM_C64 ? 6 : 5);
-                    const size_t per_warp = ((size_t)512 << mh) + 12 * kLowRow * 2 * (h->prec == QCM_C64 ? 4 : 8) + 512;
-                    if (per_warp * (h->prec == QCM_C64 ? 16 : 8) + bp.tree_smem > 200 * 1024) bp.rotate = false;
+                    const size_t per_warp = ((size_t)512 << mh) + 12 * 32 * 2 * (h->prec == QCM_C64 ? 4 : 8);
+                    if (per_warp * (h->prec == QCM_C64 ? 8 : 4) + bp.tree_smem > 200 * 1024) bp.rotate = false;
+                }
+                bp.input_in_scratch = input_in_scratch;
+                if (input_in_scratch && !bp.rotate) {     // the prefix ran in the scratch buffer after all: bring it home
+                    QCM_CUDA(h, cudaMemcpyAsync(h->state, h->scratch.p, amp_bytes(h->prec) << op.n_active_in,
+                                                cudaMemcpyDeviceToDevice, h->stream));
                 }
                 int sub_bits = 0;
                 if (checkpoint) {

@@ -892,22 +892,32 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand_tree(const __grid_
 // The input comes from a scratch copy (the output overwrites it).  A CTA covers 2^kChunkBits
 // inputs, so the sampler's level-0 sum is one value per CTA.
 // ----------------------------------------------------------------------------------
-constexpr int kLowRow = 33;                              // padded row of the lane-indexed product tables (bank spread)
-
-// shared memory per warp: U[NS][32] 16-byte vectors, A[4][33] + B[8][33] complex, 32 x 8 16-bit table offsets
+// shared memory per warp: U[NS][32] 16-byte vectors, A[32][4] + B[32][8] complex
 template <typename R, int MH> __host__ __device__ constexpr size_t low_warp_bytes() {
-    return (size_t)(1 << MH) * 32 * 16 + (size_t)12 * kLowRow * 2 * sizeof(R) + 32 * 16;
+    return (size_t)(1 << MH) * 32 * 16 + (size_t)12 * 32 * 2 * sizeof(R);
 }
-template <typename R> __host__ __device__ constexpr int low_threads() { return sizeof(R) == 4 ? 512 : 256; }
+// small CTAs (8 / 4 warps, several batches each): five or more resident per SM, so one CTA's start-up (table
+// staging) and tail (the sampler's level-0 sum) overlap the others' stores
+template <typename R> __host__ __device__ constexpr int low_threads() { return sizeof(R) == 4 ? 256 : 128; }
 
-template <typename R, int V, int MH>
+// out[j] = sum of the 2^gbits consecutive values in[j << gbits ...], in index order (deterministic)
+static __global__ void __launch_bounds__(kThreads) k_group_sum(const double *in, int gbits, uint64_t n_out, double *out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    double t = 0.0;
+    for (uint64_t i = j << gbits; i < ((j + 1) << gbits); ++i) t += in[i];
+    out[j] = t;
+}
+
+// TB: log2 of the inputs one CTA covers (its tile is 2^(TB + M) output amplitudes, contiguous).  a.tree_out
+// receives one sum per CTA: the sampler's level-0 sums when TB == kChunkBits, partial sums otherwise.
+template <typename R, int V, int MH, int TB>
 __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_constant__ ExpandTreeArgs a, const void *__restrict__ in) {
     constexpr int LB = V == 2 ? 6 : 5;                   // image bits covered by one warp store
     constexpr int J0 = V == 2 ? 1 : 0;                   // first lane-indexed member (member 0 is the vector slot for V == 2)
     constexpr int NS = 1 << MH;                          // warp stores per input
     constexpr int M = LB + MH;
     constexpr int kWarps = low_threads<R>() / 32;
-    static_assert(QCM_MAX_EXPAND == 8, "offset records hold 8 members");
     using C2 = typename CplxOf<R>::T;
     using V16 = typename VecIO<R, V>::T;                  // float4 (two complex64) or double2 (one complex128)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -929,9 +939,8 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + low_warp_bytes<R, MH>() * warp;
     V16 *Us = reinterpret_cast<V16 *>(wbase);                                      // [NS][32]
-    C2 *As = reinterpret_cast<C2 *>(wbase + (size_t)NS * 32 * 16);                 // [4][kLowRow]
-    C2 *Bs = As + 4 * kLowRow;                                                     // [8][kLowRow]
-    uint16_t *Os = reinterpret_cast<uint16_t *>(Bs + 8 * kLowRow);                 // [32][8]
+    C2 *As = reinterpret_cast<C2 *>(wbase + (size_t)NS * 32 * 16);                 // [32][4]: input-major, a lane reads entry lane & 3
+    C2 *Bs = As + 32 * 4;                                                          // [32][8]: a lane reads entry lane >> 2
     auto index_of = [&](const TreeMember &m, uint64_t gi) -> uint32_t {
         uint32_t idx = 0;
 #pragma unroll 1
@@ -939,16 +948,17 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
         return idx;
     };
     auto cmul = [](R ar, R ai, R br, R bi, R &cr, R &ci) { cr = ar * br - ai * bi; ci = ar * bi + ai * br; };
-    const C2 *my_a = As + (lane & 3) * kLowRow, *my_b = Bs + (lane >> 2) * kLowRow;
-    constexpr int kPerWarp = (1 << kChunkBits) / kWarps;                // inputs per warp per tile
-    const uint64_t tile = blockIdx.x;                                   // grid = 2^(n_in - kChunkBits), launch = address order
+    const C2 *my_a = As + (lane & 3), *my_b = Bs + (lane >> 2);
+    constexpr int kPerWarp = (1 << TB) / kWarps;                        // inputs per warp per tile
+    static_assert(kPerWarp >= 32 && kPerWarp % 32 == 0, "a warp takes whole batches of 32 inputs");
+    const uint64_t tile = blockIdx.x;                                   // grid = 2^(n_in - TB), launch = address order
     double wacc = 0.0;
 #pragma unroll 1
     for (int batch = 0; batch < kPerWarp / 32; ++batch) {
         // The warps of a CTA interleave at a granularity of two inputs (a pair shares the sampler's finest
         // sum): at step i of phase B the warps write runs 2 * 2^M amplitudes apart, so the CTA's stores
         // stay inside one moving window instead of one stream per warp (DRAM row locality).
-        const uint64_t x0 = (tile << kChunkBits) + (uint64_t)batch * (32 * kWarps) + 2u * warp;
+        const uint64_t x0 = (tile << TB) + (uint64_t)batch * (32 * kWarps) + 2u * warp;
         auto x_of = [&](int i) -> uint64_t { return x0 + (uint64_t)(i >> 1) * (2 * kWarps) + (i & 1); };
         // ---- phase A: lane i prepares input x_of(i)
         {
@@ -972,11 +982,9 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
                 cmul(pr, pi, tab[a.diag[d].tab_off + 2 * idx], tab[a.diag[d].tab_off + 2 * idx + 1], pr, pi);
             }
             __syncwarp();                                 // the previous batch's phase B is done with the tables
-#pragma unroll 1
-            for (int j = 0; j < M; ++j) Os[lane * 8 + j] = (uint16_t)((uint32_t)a.mem[j].tab_off + 4u * index_of(a.mem[j], gi));
-            const uint4 ow = *reinterpret_cast<const uint4 *>(Os + lane * 8);
-            const uint32_t off[8] = {ow.x & 0xffffu, ow.x >> 16, ow.y & 0xffffu, ow.y >> 16,
-                                     ow.z & 0xffffu, ow.z >> 16, ow.w & 0xffffu, ow.w >> 16};
+            uint32_t off[M];                              // table offset (reals) of member j at this input's index
+#pragma unroll
+            for (int j = 0; j < M; ++j) off[j] = (uint32_t)a.mem[j].tab_off + 4u * index_of(a.mem[j], gi);
             auto fac = [&](int member, int bit, R &fr, R &fi) {          // f_member[bit] at this input's table index
                 const C2 f = *reinterpret_cast<const C2 *>(tab + off[member] + 2 * bit);
                 fr = f.x; fi = f.y;
@@ -1016,7 +1024,7 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
                 fac(J0 + 1, t >> 1, yr, yi);
                 C2 o;
                 cmul(xr, xi, yr, yi, o.x, o.y);
-                As[t * kLowRow + lane] = o;
+                As[lane * 4 + t] = o;
             }
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
@@ -1027,14 +1035,14 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
                 cmul(xr, xi, yr, yi, xr, xi);
                 C2 o;
                 cmul(xr, xi, zr, zi, o.x, o.y);
-                Bs[t * kLowRow + lane] = o;
+                Bs[lane * 8 + t] = o;
             }
             __syncwarp();
         }
         // ---- phase B: all lanes, one input at a time
 #pragma unroll 2
         for (int i = 0; i < 32; ++i) {
-            const C2 fa = my_a[i], fb = my_b[i];
+            const C2 fa = my_a[i * 4], fb = my_b[i * 8];
             R lr, li;
             cmul(fa.x, fa.y, fb.x, fb.y, lr, li);
             const uint64_t obase = (x_of(i) << M) + (uint64_t)lane * V;
