@@ -47,10 +47,34 @@ class _Prepared:
     __slots__ = ('prog', 'fc', 'plan', 'clbit_map', 'n_vars', 'ps', 'name', 'virtual', 'proj')
 
 
-def _keys_to_counts(keys, width):
-    """uint64 keys -> Counts with Aer's key format (clbit width-1 leftmost).  The bit strings are cut
-    out of one unpacked byte buffer: no per-key formatting."""
+_host_lib = None
+
+
+def _host():
+    """qcmrf_b200/_qcm_host.so (csrc/qcm_host.c, CPython C API), or False when it is not built."""
+    global _host_lib
+    if _host_lib is None:
+        import ctypes
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_qcm_host.so')
+        try:
+            L = ctypes.PyDLL(path)
+            L.qcm_counts_dict.restype = ctypes.py_object
+            L.qcm_counts_dict.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_int]
+            _host_lib = L
+        except OSError:
+            _host_lib = False
+    return _host_lib
+
+
+def _keys_to_counts(keys, width, use_native=True):
+    """uint64 keys -> Counts with Aer's key format (clbit width-1 leftmost), keys in ascending order.
+    Native formatter (sort, run lengths, one dict insert per distinct key) when built; the numpy
+    version below gives the same dict (tests/test_circuit_api.py)."""
     width = max(int(width), 1)
+    L = _host() if (use_native and width <= 64) else False
+    if L:
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        return Counts(L.qcm_counts_dict(k.ctypes.data, k.size, width))
     vals, cnt = np.unique(np.asarray(keys, dtype=np.uint64), return_counts=True)
     bits = np.unpackbits(vals.astype('>u8').view(np.uint8).reshape(-1, 8), axis=1)[:, 64 - width:] if width <= 64 else None
     if bits is None:
@@ -164,6 +188,7 @@ class B200Simulator:
         self.small_fusion = small_fusion      # batched small circuits: fused programs are ~30x shorter to plan and ship
         self._handles = {}
         self._last = None
+        self.breakdown_ms = None               # host-side split of the last large-state run (bench.py)
 
     def name(self):
         return self._name
@@ -300,8 +325,12 @@ class B200Simulator:
                 small_ids.append(i)
                 small_prep.append(self.prepare(c, n_vars=n_vars, small=True))
             else:
+                tp = time.perf_counter()
                 pr = self.prepare(c, n_vars=n_vars)
+                tp = (time.perf_counter() - tp) * 1e3
                 entries[i] = self._run_large(c, pr, shots, seed, sid(i), precision)
+                entries[i]['meta']['host_ms']['prepare (lower, fuse, plan)'] = tp
+                self.breakdown_ms = entries[i]['meta']['host_ms']
         if small_ids:
             ps = [pr.ps if pr.ps is not None else (0, 0, 0) for pr in small_prep]
             keys, probs, kept, ms = _native.run_batch_small(
@@ -380,9 +409,12 @@ class B200Simulator:
 
     def _run_large(self, circ, pr, shots, seed, stream, precision):
         pl = pr.plan
+        t0 = time.perf_counter()
         keys, probs, kept = self.execute(pr, shots, seed, stream, precision)
+        t1 = time.perf_counter()
         h = self._last
         counts = _keys_to_counts(keys, pr.prog.n_clbits) if shots else None
+        t2 = time.perf_counter()
         t = h.timing()
         h2d = pl.ops.nbytes + pl.tables.nbytes + (pr.clbit_map.nbytes if shots else 0)
         d2h = (probs.nbytes + 8 if probs is not None else 0) + (keys.nbytes if keys is not None else 0)
@@ -392,7 +424,9 @@ class B200Simulator:
                          'passes': pl.n_passes, 'gates_in': pr.fc.n_gates_in, 'program_ms': t['program_ms'],
                          'sample_ms': t['sample_ms'], 'postselect_ms': t['postselect_ms'],
                          'bytes_read': t['bytes_read'], 'bytes_written': t['bytes_written'],
-                         'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': stream}}
+                         'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': stream,
+                         'host_ms': {'execute (program, shots, post-selection; blocking)': (t1 - t0) * 1e3,
+                                     'counts dict': (t2 - t1) * 1e3}}}
 
     def exact(self, circuit, n=None, precision=None):
         """Exact post-selected probability vector and success probability (no shots)."""

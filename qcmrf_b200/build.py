@@ -27,8 +27,28 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+HOST_LIB = os.path.join(HERE, '_qcm_host.so')
+HOST_SRC = os.path.join(CSRC, 'qcm_host.c')
+
+
+def build_host(force=False, verbose=False):
+    """gcc -> qcmrf_b200/_qcm_host.so: result formatting through the CPython C API (no CUDA)."""
+    if not force and os.path.exists(HOST_LIB) and os.path.getmtime(HOST_LIB) >= os.path.getmtime(HOST_SRC):
+        return HOST_LIB
+    import sysconfig
+    cc = shutil.which('gcc') or shutil.which('cc')
+    if cc is None:
+        raise RuntimeError('gcc not found: cannot build qcmrf_b200/_qcm_host.so')
+    cmd = [cc, '-O2', '-shared', '-fPIC', '-I', sysconfig.get_paths()['include'], HOST_SRC, '-o', HOST_LIB]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.check_call(cmd)
+    return HOST_LIB
+
+
 def build_native(force=False, verbose=False):
     """Compile the engine if sources are newer than the library. Returns the .so path."""
+    build_host(force, verbose)
     if not force and not _stale():
         return LIB
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'

@@ -1,0 +1,64 @@
+/* Host-side result formatting for qcmrf_b200 (CPython C API, loaded with ctypes.PyDLL).
+ *
+ * Result.get_counts() of the reference stack returns {bitstring: count} with clbit width-1 leftmost
+ * (run_experiment.py:57).  Building that dict from the sampled keys is the one
+ * per-shot piece of host work on the path; in Python it costs a slice + a dict insert per distinct
+ * key (~3 ms for 10^4 shots of a 34-clbit circuit), here it is a radix sort, a run-length pass and
+ * one PyDict_SetItem per distinct key.  Not on the GPU path; no CUDA in this file. */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+static void radix_sort_u64(uint64_t *a, uint64_t *tmp, size_t n, int bits) {
+    for (int shift = 0; shift < bits; shift += 8) {
+        size_t count[257];
+        memset(count, 0, sizeof count);
+        for (size_t i = 0; i < n; ++i) count[((a[i] >> shift) & 0xff) + 1]++;
+        for (int b = 0; b < 256; ++b) count[b + 1] += count[b];
+        for (size_t i = 0; i < n; ++i) tmp[count[(a[i] >> shift) & 0xff]++] = a[i];
+        memcpy(a, tmp, n * sizeof(uint64_t));
+    }
+}
+
+/* keys[n] (bit c = sampled value of clbit c) -> new dict {width-character bit string: count},
+ * keys in ascending numeric order (the order np.unique gives the Python fallback). */
+PyObject *qcm_counts_dict(const uint64_t *keys, Py_ssize_t n, int width) {
+    if (width < 1) width = 1;
+    if (width > 64 || n < 0) {
+        PyErr_SetString(PyExc_ValueError, "qcm_counts_dict: width must be 1..64");
+        return NULL;
+    }
+    PyObject *d = PyDict_New();
+    if (!d || n == 0) return d;
+    uint64_t *a = (uint64_t *)malloc(2 * (size_t)n * sizeof(uint64_t));
+    if (!a) {
+        Py_DECREF(d);
+        return PyErr_NoMemory();
+    }
+    memcpy(a, keys, (size_t)n * sizeof(uint64_t));
+    radix_sort_u64(a, a + n, (size_t)n, width);
+    char buf[65];
+    Py_ssize_t i = 0;
+    while (i < n) {
+        const uint64_t v = a[i];
+        Py_ssize_t j = i + 1;
+        while (j < n && a[j] == v) ++j;
+        for (int c = 0; c < width; ++c) buf[width - 1 - c] = (char)('0' + ((v >> c) & 1u));
+        PyObject *k = PyUnicode_FromStringAndSize(buf, width);
+        PyObject *cnt = PyLong_FromSsize_t(j - i);
+        if (!k || !cnt || PyDict_SetItem(d, k, cnt) < 0) {
+            Py_XDECREF(k);
+            Py_XDECREF(cnt);
+            Py_DECREF(d);
+            free(a);
+            return NULL;
+        }
+        Py_DECREF(k);
+        Py_DECREF(cnt);
+        i = j;
+    }
+    free(a);
+    return d;
+}

@@ -121,6 +121,31 @@ class Program:
     global_phase: float = 0.0
     name: str = ''
     metadata: dict = field(default_factory=dict)
+    #: optional shortcut of the producing circuit class: a callable returning the FusedCircuit that
+    #: fusion.fuse(self, 'clique') would compute from `gates`, or None (then the gates are fused)
+    fused_hint: object = field(default=None, compare=False, repr=False)
+
+
+class LazyProgram(Program):
+    """A Program whose gate list is produced on first access (``build(self)`` appends to it): a circuit
+    class that also supplies `fused_hint` usually never needs the gates at all."""
+
+    def __init__(self, n_qubits, n_clbits, name='', build=None):
+        Program.__init__(self, n_qubits, n_clbits, name=name)
+        self._build = build
+        self._gates = None
+
+    @property
+    def gates(self):
+        if self._gates is None:
+            self._gates = []
+            if self._build is not None:
+                self._build(self)
+        return self._gates
+
+    @gates.setter
+    def gates(self, value):
+        self._gates = value
 
 
 def _qindex(circ, q):

@@ -26,6 +26,21 @@ def _is_clique_list(cliques):
             len(cliques[0]) > 0 and type(cliques[0][0]) is int)
 
 
+_BITREV = {}
+
+
+def _bit_reverse(m):
+    """Index array r with r[i] = i with its m bits reversed."""
+    r = _BITREV.get(m)
+    if r is None:
+        i = np.arange(1 << m)
+        r = np.zeros(1 << m, dtype=np.int64)
+        for j in range(m):
+            r |= ((i >> j) & 1) << (m - 1 - j)
+        _BITREV[m] = r
+    return r
+
+
 class QCMRF(QuantumCircuit):
     """Quantum-circuit Markov random field over binary variables.
 
@@ -81,10 +96,23 @@ class QCMRF(QuantumCircuit):
         Emits exactly what ir.lower finds in `.data` (tests/test_circuit_api.py pins the equality)."""
         if self.__dict__.get('_mrf_data') is not None:
             return None
-        from .ir import Gate, Program
+        from .ir import LazyProgram
         n = self._mrf_n
         width = self.num_qubits
-        prog = Program(width, width, name=str(self.name))
+        prog = LazyProgram(width, width, name=str(self.name), build=self._emit_gates)
+        if self._mrf_measure:
+            for ii in range(len(self._mrf_cliques)):
+                prog.measures[n + 1 + ii] = n + 1 + ii
+            for q in range(n):
+                prog.measures[q] = q
+        prog.metadata['num_vertices'] = n
+        prog.fused_hint = self._fused_circuit
+        return prog
+
+    def _emit_gates(self, prog):
+        """The gate list of `_lower_program`'s Program (built on first access)."""
+        from .ir import Gate
+        n = self._mrf_n
         gates = prog.gates
         for q in range(n):
             gates.append(Gate('h', (q,)))
@@ -113,13 +141,44 @@ class QCMRF(QuantumCircuit):
                 gates.append(mark)
             gates.append(Gate('x', (anc,)))
             gates.append(Gate('h', (anc,)))
-            if self._mrf_measure:
-                prog.measures[anc] = anc
-        if self._mrf_measure:
-            for q in range(n):
-                prog.measures[q] = q
-        prog.metadata['num_vertices'] = n
-        return prog
+
+    def _fused_circuit(self):
+        """What the gate-fusion pass makes of this circuit, written down directly:
+        H|0> on the variable qubits, then per clique ONE uniformly-controlled RX(4 gamma) on its
+        ancilla -- [[cos 2g, -i sin 2g], [-i sin 2g, cos 2g]] selected by the clique's variable qubits;
+        terms the constructor skips (gamma ~ 0, QCMRF.py:223) are the identity; the scratch qubit is
+        back on |0> and disappears.  Saves the numeric classification of ~12 gates per clique on the
+        host; tests/test_host_fusion.py pins it against fusion.fuse on the gate list.  Returns None
+        where the shortcut does not apply (edited circuit, repeated vertices, an all-skipped clique)."""
+        if self.__dict__.get('_mrf_data') is not None:
+            return None
+        from .fusion import FusedCircuit, FusedOp
+        n = self._mrf_n
+        gam = np.asarray(self.gamma, dtype=np.float64)
+        keep_all = np.abs(gam) > 1e-8
+        c_all = np.where(keep_all, np.cos(2.0 * gam), 1.0)
+        s_all = np.where(keep_all, np.sin(2.0 * gam), 0.0) * -1j
+        h0 = np.array([1.0, 1.0], dtype=np.complex128) / math.sqrt(2.0)
+        ops = []
+        offset = 0
+        n_gates = n
+        for ii, C in enumerate(self._mrf_cliques):
+            m = len(C)
+            if len(set(C)) != m:
+                return None
+            sl = slice(offset, offset + (1 << m))
+            offset += 1 << m
+            kept = int(keep_all[sl].sum())
+            if not kept:
+                return None
+            # theta index i = sum_j y_j 2^(m-1-j); table index = sum_j y_j 2^j (bit j <-> j-th listed vertex)
+            rev = _bit_reverse(m)
+            table = np.empty((1 << m, 2, 2), dtype=np.complex128)
+            table[rev, 0, 0] = table[rev, 1, 1] = c_all[sl]
+            table[rev, 0, 1] = table[rev, 1, 0] = s_all[sl]
+            ops.append(FusedOp('mux', n + 1 + ii, tuple(n - 1 - v for v in C), table, zero_in=True, n_gates=4 + 2 * kept))
+            n_gates += 4 + 6 * kept
+        return FusedCircuit(self.num_qubits, {q: h0.copy() for q in range(n)}, ops, 0.0, n_gates)
 
     # -- the reference's read-only surface (QCMRF.py:82-157) ------------------------------
     @property

@@ -196,3 +196,23 @@ def test_direct_lowering_equals_walking_the_instruction_list(models):
     c = QCMRF([[0, 1]], gamma=[0.1, 0.2, 0.3, 0.4])
     c.h(0)
     assert ir.lower(c).gates[-1].name == 'h' and len(ir.lower(c).gates) == len(ir.lower(QCMRF([[0, 1]], gamma=[0.1, 0.2, 0.3, 0.4])).gates) + 1
+
+
+def test_native_counts_formatter_equals_numpy():
+    """csrc/qcm_host.c (one dict insert per distinct key, CPython C API) == the numpy formatter: same keys
+    in the same (ascending) order, same counts; widths 1..64, empty input."""
+    from qcmrf_b200 import build
+    from qcmrf_b200.backend import _host, _keys_to_counts
+    build.build_host()
+    assert _host(), '_qcm_host.so did not load'
+    rng = np.random.default_rng(3)
+    for width, n in ((1, 50), (3, 1000), (10, 10000), (34, 10000), (63, 500), (64, 500), (34, 0)):
+        hi = (1 << width) - 1
+        keys = rng.integers(0, hi, size=n, dtype=np.uint64, endpoint=True) if n else np.zeros(0, dtype=np.uint64)
+        if n > 10:
+            keys[: n // 3] = keys[n // 3: 2 * (n // 3)]
+            keys[-1] = hi
+        a = _keys_to_counts(keys, width, use_native=True)
+        b = _keys_to_counts(keys, width, use_native=False)
+        assert type(a) is type(b) and list(a.items()) == list(b.items())
+        assert sum(a.values()) == n and all(len(k) == width for k in a)

@@ -15,7 +15,7 @@ CONFIGS = [('off', False, 1), ('clique', False, 1), ('clique', True, 1), ('cliqu
 
 
 def _logical(prog, mode, lazy, bm, elide=None):
-    fc = fusion.fuse(prog, mode)
+    fc = fusion.fuse(prog, mode, use_hint=False)          # the numeric gate-fusion pass itself (QCMRF's shortcut: below)
     pl = fusion.plan(fc, lazy=lazy, block_max=bm, elide=elide)
     phys, act = em.run_plan(pl)
     return em.logical_state(pl, phys), fc, pl
@@ -79,7 +79,7 @@ def test_fused_tables_are_the_closed_form_rx(models):
     for scale, j, i, C, th in all_models(models):
         if i:
             continue
-        fc = fusion.fuse(ir.lower(QCMRF(C, th)), 'clique')
+        fc = fusion.fuse(ir.lower(QCMRF(C, th)), 'clique', use_hint=False)
         for op, (ctrl, c, s) in zip(fc.ops, program.rx_tables(C, th)):
             assert sorted(op.ctrls) == sorted(ctrl)
             perm = [ctrl.index(q) for q in op.ctrls]               # my bit j <-> oracle bit perm[j]
@@ -264,3 +264,42 @@ def test_release_mode_on_the_emulator(monkeypatch, models):
             obs[int(key, 2)] = v
         assert obs.sum() == 30000 and obs[kp < 1e-15].sum() == 0
         assert 0.5 * np.abs(obs / 3e4 - kp).sum() < 0.5 * np.sqrt(2 * ((kp > 0).sum() * np.log(2) + np.log(1e6)) / 3e4)
+
+
+def test_qcmrf_fused_shortcut_equals_the_fusion_pass(models):
+    """QCMRF._fused_circuit (the closed form of SURVEY.md App. A, used by the backend instead of fusing
+    ~12 gates per clique numerically) is exactly what fusion.fuse makes of the emitted gate list: same
+    sweeps, same index-qubit order, tables equal to rounding; skipped terms (gamma ~ 0, QCMRF.py:223) are
+    identities; an edited circuit falls back to the gate list."""
+    rng = np.random.RandomState(12)
+    cases = [(C, th) for _s, _j, i, C, th in all_models(models) if i < 2]
+    for _ in range(12):
+        n = int(rng.randint(2, 7))
+        C = []
+        for _k in range(int(rng.randint(1, 5))):
+            m = int(rng.randint(1, min(4, n) + 1))
+            C.append([int(v) for v in rng.permutation(n)[:m]])
+        C.append([n - 1])
+        th = -np.abs(rng.randn(sum(2 ** len(c) for c in C)))
+        th[rng.rand(len(th)) < 0.2] = 0.0                      # gamma == 0: the constructor skips the term
+        cases.append((C, list(th)))
+    for C, th in cases:
+        for beta in (1.0, 0.5):
+            prog = ir.lower(QCMRF(C, th, beta=beta))
+            fast = fusion.fuse(prog, 'clique')
+            slow = fusion.fuse(prog, 'clique', use_hint=False)
+            if prog.fused_hint() is None:                      # an all-skipped clique: no shortcut
+                continue
+            assert fast.n_qubits == slow.n_qubits and sorted(fast.init) == sorted(slow.init)
+            for q in fast.init:
+                assert np.abs(fast.init[q] - slow.init[q]).max() < 1e-15
+            assert abs(fast.global_phase - slow.global_phase) < 1e-12
+            assert len(fast.ops) == len(slow.ops)
+            for a, b in zip(fast.ops, slow.ops):
+                assert (a.kind, a.target, tuple(a.ctrls), a.zero_in) == (b.kind, b.target, tuple(b.ctrls), b.zero_in)
+                assert np.abs(a.table - b.table).max() < 1e-14
+    # editing the circuit materialises the instruction list: no shortcut any more
+    c = QCMRF([[0, 1]], [-0.1, -0.2, -0.3, -0.4])
+    c.x(0)
+    prog = ir.lower(c)
+    assert getattr(prog, 'fused_hint', None) is None or prog.fused_hint() is None

@@ -72,7 +72,7 @@ def test_generic_circuit_with_repeated_global_targets(g):
     prog = ir.lower(qc)
     want, _ = sv.run_program(ir.to_oracle_ops(prog), N)
     for lazy, mode in ((False, 'off'), (True, 'off'), (True, 'clique'), (False, 'clique')):
-        fc = fusion.fuse(prog, mode)
+        fc = fusion.fuse(prog, mode, use_hint=False)
         pl = fusion.plan(fc, lazy=lazy, block_max=2)
         for fused in (False, True):
             psi, sps = vc.run_virtual(pl, g, fuse_exchange=fused)
