@@ -41,7 +41,7 @@ def ncu_traffic(workload, world):
     try:
         import csv
         tot = 0.0
-        for row in csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_prof_expand.csv'))):
+        for row in csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_prof_low.csv'))):
             if row and row[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
                 tot += float(row[2].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[row[1]]
         return tot or None
@@ -295,6 +295,7 @@ def main():
         out = sim.execute(prep, SHOTS, seed=1984, stream=0)
         if prof is None:
             prof = sim.op_profile()
+            kernels = sim.op_kernels() if hasattr(sim, 'op_kernels') else []
     ev1.record()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -330,13 +331,18 @@ def main():
     dense = None
     if not args.no_dense:
         sim.close()
-        dense = dense_gate_pass(args, cliques, local_rank, world)
+        try:
+            dense = dense_gate_pass(args, cliques, local_rank, world)
+        except Exception as e:                              # a secondary measurement must not cost the bench line
+            dense = {'error': repr(e)[:500]}
 
     if rank == 0:
         peak, peak_src = load_peaks()
         # dominant launch of one program
         top = max(prof, key=lambda r: r[1])
         kind, top_ms, rd, wr = top
+        # the dominant launch is the last pass of the program; its kernel name comes from the engine
+        kname = (kernels[-1] if kernels and prof.index(top) == len(prof) - 1 and kernels[-1] else 'op kind %d' % kind)
         achieved = (rd + wr) / (top_ms * 1e-3) / 1e9
         total_bytes = sum(r[2] + r[3] for r in prof)
         prog_ms = sum(r[1] for r in prof)
@@ -350,8 +356,8 @@ def main():
                 'gpu_launches': int(launches),
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': ncu_traffic(args.workload, world), 'peak_source': peak_src,
-                             'traffic_source': 'profiles/r01_ncu_prof_expand.csv (ncu --set full, same workload, 1 GPU)',
-                             'kernel': 'k_block (op kind %d): reads %d B, writes %d B in %.3f ms' % (kind, rd, wr, top_ms)},
+                             'traffic_source': 'profiles/r01_ncu_prof_low.csv (ncu --set full of this kernel, same workload, 1 GPU)',
+                             'kernel': '%s: reads %d B, writes %d B in %.3f ms' % (kname, rd, wr, top_ms)},
                 'program': {'passes': [{'kind': r[0], 'ms': r[1], 'read': r[2], 'written': r[3],
                                         'gbs': (r[2] + r[3]) / max(r[1], 1e-9) / 1e6} for r in prof],
                             'program_ms': prog_ms, 'program_gbs': total_bytes / max(prog_ms, 1e-9) / 1e6,
@@ -363,10 +369,13 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_reference(cliques, steps=1, warmup=0)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    sim.close()
+    try:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        sim.close()
+    except Exception as e:
+        print('bench.py: teardown: %r' % (e,), file=sys.stderr)
 
 
 def barrier_factory(torch, dist, world):
@@ -545,8 +554,12 @@ def dense_gate_pass(args, cliques, device, world=1):
         sim = ShardedSimulator(precision='single', fusion='clique', layout='canonical', device=device, seed=1,
                                exchange='p2p')
         prep = sim.prepare(circ)
-        sim.execute(prep, 0, want_probs=False)
-        sim.execute(prep, 0, want_probs=False)
+        try:
+            sim.execute(prep, 0, want_probs=False)
+            sim.execute(prep, 0, want_probs=False)
+        except Exception as e:
+            out['fused_exchange'] = {'error': repr(e)[:500]}
+            return out
         prof2 = sim.op_profile()
         fx = [r for r in prof2 if r[0] == -2]
         s = world.bit_length() - 1

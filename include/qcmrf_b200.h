@@ -248,6 +248,10 @@ int qcm_get_timing(qcm_handle h, qcm_timing *out);
  * the number available.  bench.py derives roofline.achieved from these.                */
 int qcm_get_op_profile(qcm_handle h, int cap, int32_t *kind_out, float *ms_out,
                        uint64_t *bytes_read_out, uint64_t *bytes_written_out, int *n_out);
+/* Name of the kernel that executed op `index` of the last program (the indices of
+ * qcm_get_op_profile), e.g. "k_expand_low<float,2,MH=2,TB=8>"; "" when out of range.  The
+ * string lives in the handle until the next program.                                     */
+const char *qcm_op_kernel_name(qcm_handle h, int index);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -39,7 +39,7 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
            'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile', 'qcm_postselect_device',
            'qcm_sample_sharded_device', 'qcm_run_gather_block', 'qcm_enable_peer_access',
-           'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close']
+           'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close', 'qcm_op_kernel_name']
 
 
 def lib():
@@ -82,6 +82,8 @@ def lib():
     L.qcm_ipc_export.argtypes = [i32, vp, vp, vp]
     L.qcm_ipc_open.argtypes = [i32, vp, vp]
     L.qcm_ipc_close.argtypes = [i32, vp]
+    L.qcm_op_kernel_name.argtypes = [vp, i32]
+    L.qcm_op_kernel_name.restype = ctypes.c_char_p
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
     assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
@@ -260,6 +262,12 @@ class Handle:
         rd = np.zeros(n.value, dtype=np.uint64); wr = np.zeros(n.value, dtype=np.uint64)
         self._check(lib().qcm_get_op_profile(self._h, n.value, _ptr(k), _ptr(ms), _ptr(rd), _ptr(wr), ctypes.byref(n)))
         return [(int(a), float(b), int(c), int(d)) for a, b, c, d in zip(k, ms, rd, wr)]
+
+    def op_kernels(self):
+        """Kernel name per op of the last program (same indices as op_profile; '' where not recorded)."""
+        n = ctypes.c_int()
+        self._check(lib().qcm_get_op_profile(self._h, 0, None, None, None, None, ctypes.byref(n)))
+        return [(lib().qcm_op_kernel_name(self._h, i) or b'').decode() for i in range(n.value)]
 
     def timing(self):
         t = QcmTiming()

@@ -407,6 +407,10 @@ class B200Simulator:
         """Per-launch (kind, ms, bytes_read, bytes_written) of the last executed program."""
         return self._last.op_profile()
 
+    def op_kernels(self):
+        """Kernel name per entry of op_profile() ('' where the engine does not record one)."""
+        return self._last.op_kernels()
+
     def _run_large(self, circ, pr, shots, seed, stream, precision):
         pl = pr.plan
         t0 = time.perf_counter()

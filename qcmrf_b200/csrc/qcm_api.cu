@@ -65,6 +65,8 @@ struct qcm_sim_s {
     std::vector<int32_t> op_kind;
     std::vector<uint64_t> op_rd, op_wr;
     std::vector<float> op_ms;
+    std::vector<std::string> op_kernel;    // kernel that ran each op of the last program
+    std::string cur_kernel;                // set by the launchers, collected per op
 };
 
 namespace {
@@ -392,6 +394,11 @@ static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
         args.tree_out = (double *)h->lowpart.p;
     }
     kern<<<1u << (n_in - TB), low_threads<R>(), smem, h->stream>>>(args, h->scratch.p);
+    {
+        char nm[96];
+        snprintf(nm, sizeof nm, "k_expand_low<%s,%d,MH=%d,TB=%d>", sizeof(R) == 4 ? "float" : "double", V, MH, TB);
+        h->cur_kernel = nm;
+    }
     QCM_CUDA(h, cudaGetLastError());
     if (level0 && TB != kChunkBits) {
         const uint64_t n_out = 1ull << (n_in - kChunkBits);
@@ -445,6 +452,7 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
         h->rot_m = M;
         h->rot_nin = n_in;
     } else if (bp.tree) {
+        h->cur_kernel = h->prec == QCM_C64 ? "k_expand_tree<float>" : "k_expand_tree<double>";
         const int V = (h->prec == QCM_C64 && n_in >= 1) ? 2 : 1;
         const int threads = bp.trargs.tree_out ? (1 << kChunkBits) / V : 256;     // fused tree: tile == chunk
         const uint64_t nvec = (1ull << n_in) / V;
@@ -466,6 +474,7 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
         h->timing.kernel_launches++;
         h->n_expand++;
     } else if (bp.expand) {
+        h->cur_kernel = h->prec == QCM_C64 ? "k_expand<float>" : "k_expand<double>";
         const size_t centry = h->prec == QCM_C64 ? 8 : 16;
         const size_t nent = 1ull << (M + bp.targs.nu);
         if ((rc = ensure(h, h->ctab, nent * centry))) return rc;
@@ -490,6 +499,7 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
         h->n_expand++;
     } else {
         const bool lazy = n_in != n_out;
+        h->cur_kernel = h->prec == QCM_C64 ? "k_block<float>" : "k_block<double>";
         if (h->prec == QCM_C64) {
             const bool vec2 = a.tq[0] >= 1 && (n_out - M) >= 1;
             if (vec2) rc = lazy ? launch_block_m<float, 2, true>(h, M, a, bp.smem) : launch_block_m<float, 2, false>(h, M, a, bp.smem);
@@ -1009,7 +1019,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     h->timing.bytes_read = h->timing.bytes_written = 0;
     QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if ((rc = upload_tables(h, tables, n_tables))) return rc;
-    h->op_kind.clear(); h->op_rd.clear(); h->op_wr.clear(); h->op_ms.clear();
+    h->op_kind.clear(); h->op_rd.clear(); h->op_wr.clear(); h->op_ms.clear(); h->op_kernel.clear(); h->cur_kernel.clear();
     size_t n_ev = 0;
     auto mark = [&](void) -> cudaError_t {
         if (n_ev >= h->op_ev.size()) {
@@ -1143,6 +1153,8 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
         if (!keep_tree) h->tree_valid = false;
         QCM_CUDA(h, mark());
         h->op_kind.push_back(op.kind);
+        h->op_kernel.push_back(h->cur_kernel);
+        h->cur_kernel.clear();
         h->op_rd.push_back(h->timing.bytes_read - rd0);
         h->op_wr.push_back(h->timing.bytes_written - wr0);
     }
@@ -1215,6 +1227,11 @@ int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const doubl
     h->op_wr.assign(1, h->timing.bytes_written);
     h->op_ms.assign(1, ms);
     return QCM_OK;
+}
+
+const char *qcm_op_kernel_name(qcm_handle h, int index) {
+    if (!h || index < 0 || (size_t)index >= h->op_kernel.size()) return "";
+    return h->op_kernel[index].c_str();
 }
 
 int qcm_get_op_profile(qcm_handle h, int cap, int32_t *kind_out, float *ms_out, uint64_t *bytes_read_out,

@@ -882,6 +882,13 @@ class ShardedSimulator:
     def op_profile(self):
         return list(self._profile)
 
+    def op_kernels(self):
+        """Kernel names of the LAST run segment's ops (the segment that holds the dominant final pass)."""
+        try:
+            return self._h.op_kernels() if self._h is not None else []
+        except Exception:
+            return []
+
     def kernel_launches(self):
         live = self._h.timing()['kernel_launches'] if self._h is not None else 0
         return self._launches_closed + live
