@@ -383,13 +383,13 @@ int low_tile_bits() {
 template <typename R, int V, int MH, int TB>
 static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
     auto kern = k_expand_low<R, V, MH, TB>;
-    const size_t smem = low_warp_bytes<R, MH>() * (low_threads<R>() / 32) + bp.tree_smem;
-    if (smem > 200 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "rotated expansion needs %zu B of shared memory", smem);
+    constexpr int warps = low_threads<R>() / 32;
+    const size_t smem = low_warp_bytes<R, MH>() * warps + bp.tree_smem;
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ExpandTreeArgs args = bp.trargs;
     double *level0 = args.tree_out;
-    if (level0 && TB != kChunkBits) {                      // per-CTA partial sums, grouped into level 0 below
-        int rc = ensure(h, h->lowpart, sizeof(double) << (n_in - TB));
+    if (level0) {                                          // per-warp partial sums, grouped into level 0 below
+        int rc = ensure(h, h->lowpart, (sizeof(double) * warps) << (n_in - TB));
         if (rc) return rc;
         args.tree_out = (double *)h->lowpart.p;
     }
@@ -400,9 +400,11 @@ static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
         h->cur_kernel = nm;
     }
     QCM_CUDA(h, cudaGetLastError());
-    if (level0 && TB != kChunkBits) {
+    if (level0) {
+        int wbits = 0;
+        while ((1 << wbits) < warps) ++wbits;
         const uint64_t n_out = 1ull << (n_in - kChunkBits);
-        k_group_sum<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>((const double *)h->lowpart.p, kChunkBits - TB, n_out, level0);
+        k_group_sum<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>((const double *)h->lowpart.p, kChunkBits - TB + wbits, n_out, level0);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
     }
@@ -1103,7 +1105,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                             op.n_active_out - op.n_active_in == bp.M;
                 if (bp.rotate) {                          // its product tables + the member tables must fit shared memory
                     const int mh = bp.M - (h->prec == QCM_C64 ? 6 : 5);
-                    const size_t per_warp = ((size_t)512 << mh) + 12 * 32 * 2 * (h->prec == QCM_C64 ? 4 : 8);
+                    const size_t per_warp = ((size_t)512 << mh) + 12 * kLowRow * 2 * (h->prec == QCM_C64 ? 4 : 8);
                     if (per_warp * (h->prec == QCM_C64 ? 8 : 4) + bp.tree_smem > 200 * 1024) bp.rotate = false;
                 }
                 bp.input_in_scratch = input_in_scratch;

@@ -893,11 +893,13 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand_tree(const __grid_
 // inputs, so the sampler's level-0 sum is one value per CTA.
 // ----------------------------------------------------------------------------------
 // shared memory per warp: U[NS][32] 16-byte vectors, A[32][4] + B[32][8] complex
+constexpr int kLowRow = 33;                              // padded row of the lane-indexed product tables (bank spread)
+
+// shared memory per warp: U[NS][32] 16-byte vectors, A[4][33] + B[8][33] complex
 template <typename R, int MH> __host__ __device__ constexpr size_t low_warp_bytes() {
-    return (size_t)(1 << MH) * 32 * 16 + (size_t)12 * 32 * 2 * sizeof(R);
+    return (size_t)(1 << MH) * 32 * 16 + (size_t)12 * kLowRow * 2 * sizeof(R);
 }
-// small CTAs (8 / 4 warps, several batches each): five or more resident per SM, so one CTA's start-up (table
-// staging) and tail (the sampler's level-0 sum) overlap the others' stores
+// small CTAs (8 / 4 warps): five or more resident per SM, so one CTA's start-up (table staging) overlaps the others' stores
 template <typename R> __host__ __device__ constexpr int low_threads() { return sizeof(R) == 4 ? 256 : 128; }
 
 // out[j] = sum of the 2^gbits consecutive values in[j << gbits ...], in index order (deterministic)
@@ -910,7 +912,8 @@ static __global__ void __launch_bounds__(kThreads) k_group_sum(const double *in,
 }
 
 // TB: log2 of the inputs one CTA covers (its tile is 2^(TB + M) output amplitudes, contiguous).  a.tree_out
-// receives one sum per CTA: the sampler's level-0 sums when TB == kChunkBits, partial sums otherwise.
+// receives one partial sum per WARP (index blockIdx * warps + warp); k_group_sum folds them into the
+// sampler's level-0 sums.
 template <typename R, int V, int MH, int TB>
 __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_constant__ ExpandTreeArgs a, const void *__restrict__ in) {
     constexpr int LB = V == 2 ? 6 : 5;                   // image bits covered by one warp store
@@ -935,12 +938,12 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
         const int n = 2 << a.diag[d].n_ctrl;
         for (int i = threadIdx.x; i < n; i += blockDim.x) tab[a.diag[d].tab_off + i] = gt[a.diag[d].src_off + i];
     }
-    __syncthreads();
+    __syncthreads();                                      // the only block-level barrier: member tables staged
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *wbase = smem_raw + low_warp_bytes<R, MH>() * warp;
     V16 *Us = reinterpret_cast<V16 *>(wbase);                                      // [NS][32]
-    C2 *As = reinterpret_cast<C2 *>(wbase + (size_t)NS * 32 * 16);                 // [32][4]: input-major, a lane reads entry lane & 3
-    C2 *Bs = As + 32 * 4;                                                          // [32][8]: a lane reads entry lane >> 2
+    C2 *As = reinterpret_cast<C2 *>(wbase + (size_t)NS * 32 * 16);                 // [4][kLowRow]: a lane reads row lane & 3
+    C2 *Bs = As + 4 * kLowRow;                                                     // [8][kLowRow]: a lane reads row lane >> 2
     auto index_of = [&](const TreeMember &m, uint64_t gi) -> uint32_t {
         uint32_t idx = 0;
 #pragma unroll 1
@@ -948,7 +951,7 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
         return idx;
     };
     auto cmul = [](R ar, R ai, R br, R bi, R &cr, R &ci) { cr = ar * br - ai * bi; ci = ar * bi + ai * br; };
-    const C2 *my_a = As + (lane & 3), *my_b = Bs + (lane >> 2);
+    const C2 *my_a = As + (lane & 3) * kLowRow, *my_b = Bs + (lane >> 2) * kLowRow;
     constexpr int kPerWarp = (1 << TB) / kWarps;                        // inputs per warp per tile
     static_assert(kPerWarp >= 32 && kPerWarp % 32 == 0, "a warp takes whole batches of 32 inputs");
     const uint64_t tile = blockIdx.x;                                   // grid = 2^(n_in - TB), launch = address order
@@ -1024,7 +1027,7 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
                 fac(J0 + 1, t >> 1, yr, yi);
                 C2 o;
                 cmul(xr, xi, yr, yi, o.x, o.y);
-                As[lane * 4 + t] = o;
+                As[t * kLowRow + lane] = o;
             }
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
@@ -1035,14 +1038,14 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
                 cmul(xr, xi, yr, yi, xr, xi);
                 C2 o;
                 cmul(xr, xi, zr, zi, o.x, o.y);
-                Bs[lane * 8 + t] = o;
+                Bs[t * kLowRow + lane] = o;
             }
             __syncwarp();
         }
         // ---- phase B: all lanes, one input at a time
 #pragma unroll 2
         for (int i = 0; i < 32; ++i) {
-            const C2 fa = my_a[i * 4], fb = my_b[i * 8];
+            const C2 fa = my_a[i], fb = my_b[i];
             R lr, li;
             cmul(fa.x, fa.y, fb.x, fb.y, lr, li);
             const uint64_t obase = (x_of(i) << M) + (uint64_t)lane * V;
@@ -1061,15 +1064,8 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
         }
     }
     if (a.tree_out) {
-        __shared__ double s_w[kWarps];
         wacc = warp_sum(wacc);
-        if (lane == 0) s_w[warp] = wacc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int i = 0; i < kWarps; ++i) t += s_w[i];
-            a.tree_out[tile] = t;
-        }
+        if (lane == 0) a.tree_out[tile * kWarps + warp] = wacc;
     }
 }
 
