@@ -1041,6 +1041,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
         ~StateGuard() { if (real) h->state = real; }
     } guard{h, nullptr};
     int prefix_until = -1;
+    bool no_rotate = false;
     {
         int li = -1;
         for (int i = 0; i < n_ops;) {
@@ -1052,8 +1053,12 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
             const int n_in = ops[li].n_active_in;
             bool fits = n_in >= kChunkBits && n_in <= h->n_local;
             for (int i = 0; i < li && fits; ++i) fits = ops[i].n_active_out <= n_in && ops[i].n_active_in <= n_in;
+            if (fits && ensure(h, h->scratch, amp_bytes(h->prec) << n_in) != QCM_OK) {
+                cudaGetLastError();                       // no room for the scratch buffer: plain in-place schedule
+                fits = false;
+                no_rotate = true;
+            }
             if (fits) {
-                if ((rc = ensure(h, h->scratch, amp_bytes(h->prec) << n_in))) return rc;
                 guard.real = h->state;
                 h->state = h->scratch.p;
                 prefix_until = li;
@@ -1100,13 +1105,17 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 bool checkpoint = last && (op.flags & QCM_FLAG_SAMPLE_CHECKPOINT) && bp.norm_preserving &&
                                   op.n_active_in >= kChunkBits;
                 // rotated output: last op, wide expansion on the product-tree path, enough image bits for a warp store
-                bp.rotate = last && (op.flags & QCM_FLAG_ROTATED_OUTPUT_OK) && bp.tree && rotate_enabled() &&
+                bp.rotate = last && !no_rotate && (op.flags & QCM_FLAG_ROTATED_OUTPUT_OK) && bp.tree && rotate_enabled() &&
                             op.n_active_in >= kChunkBits && bp.M >= (h->prec == QCM_C64 ? 6 : 5) &&
                             op.n_active_out - op.n_active_in == bp.M;
                 if (bp.rotate) {                          // its product tables + the member tables must fit shared memory
                     const int mh = bp.M - (h->prec == QCM_C64 ? 6 : 5);
                     const size_t per_warp = ((size_t)512 << mh) + 12 * kLowRow * 2 * (h->prec == QCM_C64 ? 4 : 8);
                     if (per_warp * (h->prec == QCM_C64 ? 8 : 4) + bp.tree_smem > 200 * 1024) bp.rotate = false;
+                }
+                if (bp.rotate && !input_in_scratch && ensure(h, h->scratch, amp_bytes(h->prec) << op.n_active_in) != QCM_OK) {
+                    cudaGetLastError();                   // no room for the input copy: keep the in-place kernel
+                    bp.rotate = false;
                 }
                 bp.input_in_scratch = input_in_scratch;
                 if (input_in_scratch && !bp.rotate) {     // the prefix ran in the scratch buffer after all: bring it home
