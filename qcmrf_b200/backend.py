@@ -44,7 +44,7 @@ class Counts(dict):
 
 
 class _Prepared:
-    __slots__ = ('prog', 'fc', 'plan', 'clbit_map', 'n_vars', 'ps', 'name', 'virtual', 'proj')
+    __slots__ = ('prog', 'fc', 'plan', 'clbit_map', 'n_vars', 'ps', 'name', 'virtual', 'proj', '_released_tabs')
 
 
 _host_lib = None
@@ -60,6 +60,10 @@ def _host():
             L = ctypes.PyDLL(path)
             L.qcm_counts_dict.restype = ctypes.py_object
             L.qcm_counts_dict.argtypes = [ctypes.c_void_p, ctypes.c_ssize_t, ctypes.c_int]
+            vp = ctypes.c_void_p
+            L.qcm_released_keys.restype = ctypes.c_int
+            L.qcm_released_keys.argtypes = [vp, ctypes.c_int64, vp, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, vp, vp,
+                                            ctypes.c_int, vp]
             _host_lib = L
         except OSError:
             _host_lib = False
@@ -382,6 +386,9 @@ class B200Simulator:
         raw = h.sample(shots, seed, stream, None).astype(np.int64)
         rng = np.random.Generator(np.random.Philox(key=[int(seed) & (2 ** 64 - 1), int(stream) & (2 ** 64 - 1)]))
         u = rng.random((len(pr.virtual), shots))
+        L = _host()
+        if L:
+            return self._released_keys_native(L, pr, raw, u)
         vbits = {}
         for k, v in enumerate(pr.virtual):
             idx = np.zeros(shots, dtype=np.int64)
@@ -394,6 +401,41 @@ class B200Simulator:
                 keys |= vbits[q] << np.uint64(c)
             elif pl.layout[q] < pl.n_phys:
                 keys |= ((raw >> pl.layout[q]) & 1).astype(np.uint64) << np.uint64(c)
+        return keys
+
+    @staticmethod
+    def _released_keys_native(L, pr, raw, u):
+        """The same key assembly in one pass over the shots (csrc/qcm_host.c, qcm_released_keys)."""
+        pl = pr.plan
+        nv, shots = len(pr.virtual), len(raw)
+        tabs = getattr(pr, '_released_tabs', None)
+        if tabs is None:
+            mc = max([len(v['ctrl']) for v in pr.virtual] + [1])
+            n_ctrl = np.array([len(v['ctrl']) for v in pr.virtual], dtype=np.int32)
+            ctrl = np.zeros((nv, mc), dtype=np.int32)
+            for k, v in enumerate(pr.virtual):
+                ctrl[k, :len(v['ctrl'])] = v['ctrl']
+            p1 = np.ascontiguousarray(np.concatenate([np.asarray(v['p1'], dtype=np.float64) for v in pr.virtual]))
+            p1_off = np.concatenate([[0], np.cumsum([len(v['p1']) for v in pr.virtual])[:-1]]).astype(np.int64)
+            vq = {v['qubit']: k for k, v in enumerate(pr.virtual)}
+            vclbit = np.full(nv, -1, dtype=np.int32)
+            n_cl = (max(pr.prog.measures) + 1) if pr.prog.measures else 0
+            clbit_pos = np.full(max(n_cl, 1), -1, dtype=np.int32)
+            for c, q in pr.prog.measures.items():
+                if q in vq:
+                    vclbit[vq[q]] = c
+                elif pl.layout[q] < pl.n_phys:
+                    clbit_pos[c] = pl.layout[q]
+            tabs = pr._released_tabs = (mc, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_cl)
+        mc, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_cl = tabs
+        raw = np.ascontiguousarray(raw, dtype=np.int64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        keys = np.empty(shots, dtype=np.uint64)
+        rc = L.qcm_released_keys(raw.ctypes.data, shots, u.ctypes.data, nv, n_ctrl.ctypes.data, ctrl.ctypes.data, mc,
+                                 p1.ctypes.data, p1_off.ctypes.data, vclbit.ctypes.data, clbit_pos.ctypes.data, n_cl,
+                                 keys.ctypes.data)
+        if rc:
+            raise ValueError('qcm_released_keys: bad arguments')
         return keys
 
     def kernel_launches(self):

@@ -62,3 +62,31 @@ PyObject *qcm_counts_dict(const uint64_t *keys, Py_ssize_t n, int width) {
     free(a);
     return d;
 }
+
+/* Measure-and-release width: full-width keys of a circuit whose released qubits are
+ * not stored.  raw[s] = sampled basis state of the stored qubits (from the GPU sampler);
+ * released qubit k reads 1 when u[k][s] < p1_k[index bits of raw[s] at ctrl_k]; stored qubits are copied
+ * from raw.  One pass over the shots instead of ~10 numpy temporaries per qubit.
+ * ctrl: [nv][max_ctrl] physical positions (first n_ctrl[k] valid); p1: concatenated tables, p1_off[k]
+ * their starts; vclbit[k]: clbit of released qubit k or -1; clbit_pos[c]: physical position feeding
+ * clbit c or -1 (released / unmeasured / never stored).                                              */
+int qcm_released_keys(const int64_t *raw, int64_t shots, const double *u, int nv, const int32_t *n_ctrl,
+                      const int32_t *ctrl, int max_ctrl, const double *p1, const int64_t *p1_off,
+                      const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits, uint64_t *keys_out) {
+    if (!raw || !keys_out || shots < 0 || nv < 0 || n_clbits < 0 || n_clbits > 64) return -1;
+    for (int64_t s = 0; s < shots; ++s) {
+        const uint64_t r = (uint64_t)raw[s];
+        uint64_t key = 0;
+        for (int c = 0; c < n_clbits; ++c)
+            if (clbit_pos[c] >= 0) key |= ((r >> clbit_pos[c]) & 1ull) << c;
+        for (int k = 0; k < nv; ++k) {
+            if (vclbit[k] < 0) continue;
+            uint32_t idx = 0;
+            const int32_t *ck = ctrl + (size_t)k * max_ctrl;
+            for (int j = 0; j < n_ctrl[k]; ++j) idx |= (uint32_t)((r >> ck[j]) & 1ull) << j;
+            if (u[(size_t)k * shots + s] < p1[p1_off[k] + idx]) key |= 1ull << vclbit[k];
+        }
+        keys_out[s] = key;
+    }
+    return 0;
+}
