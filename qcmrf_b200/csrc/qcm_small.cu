@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -189,12 +190,43 @@ __global__ void __launch_bounds__(kThreads) k_small(const SmallArgs a) {
 
 thread_local std::string g_small_error;
 
-template <typename T>
-cudaError_t to_dev(T **d, const T *h, size_t n, cudaStream_t st) {
-    cudaError_t e = cudaMalloc((void **)d, std::max<size_t>(n, 1) * sizeof(T));
-    if (e != cudaSuccess) return e;
-    if (n) e = cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, st);
-    return e;
+// Per-device, grow-only work space of the batched path: ONE device buffer, ONE pinned host buffer for the
+// inputs (a single H2D copy), one stream and two events -- created once, reused by every call (the first
+// version paid ~15 cudaMalloc + cudaFree per batch, 10-25 ms next to a 0.07 ms kernel).  Guarded by a mutex:
+// calls on the same device serialise.
+struct SmallArena {
+    std::mutex mu;
+    void *dev = nullptr;
+    size_t dev_cap = 0;
+    void *pin = nullptr;
+    size_t pin_cap = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+SmallArena g_arena[64];
+
+inline size_t up256(size_t x) { return (x + 255) & ~size_t(255); }
+
+cudaError_t arena_reserve(SmallArena &A, size_t dev_bytes, size_t pin_bytes) {
+    cudaError_t e;
+    if (!A.st) {
+        if ((e = cudaStreamCreateWithFlags(&A.st, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreate(&A.e0)) != cudaSuccess) return e;
+        if ((e = cudaEventCreate(&A.e1)) != cudaSuccess) return e;
+    }
+    if (A.dev_cap < dev_bytes) {
+        if (A.dev) cudaFree(A.dev);
+        A.dev = nullptr; A.dev_cap = 0;
+        if ((e = cudaMalloc(&A.dev, dev_bytes + dev_bytes / 4)) != cudaSuccess) return e;
+        A.dev_cap = dev_bytes + dev_bytes / 4;
+    }
+    if (A.pin_cap < pin_bytes) {
+        if (A.pin) cudaFreeHost(A.pin);
+        A.pin = nullptr; A.pin_cap = 0;
+        if ((e = cudaMallocHost(&A.pin, pin_bytes + pin_bytes / 4)) != cudaSuccess) return e;
+        A.pin_cap = pin_bytes + pin_bytes / 4;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace
@@ -217,7 +249,7 @@ int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t
     if (shots && (!keys_out || !clbit_qubit || !n_clbits)) return QCM_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return QCM_ERR_NO_DEVICE;
-    if (device < 0 || device >= ndev) return QCM_ERR_INVALID;
+    if (device < 0 || device >= ndev || device >= 64) return QCM_ERR_INVALID;
     int maxq = 0;
     std::vector<int64_t> pbeg(n_circuits + 1, 0);
     for (int c = 0; c < n_circuits; ++c) {
@@ -245,71 +277,85 @@ int qcm_run_batch_small(int device, int precision, int n_circuits, const int32_t
     } while (0)
     int rc = QCM_OK;
     SmallArgs a{};
-    int32_t *d_nq = nullptr, *d_cq = nullptr, *d_ncl = nullptr, *d_psb = nullptr, *d_status = nullptr;
-    int64_t *d_ob = nullptr, *d_pb = nullptr;
-    qcm_op *d_ops = nullptr;
-    double *d_tab = nullptr, *d_probs = nullptr, *d_kept = nullptr;
-    uint64_t *d_pm = nullptr, *d_pv = nullptr, *d_keys = nullptr, *d_sid = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaStream_t st = nullptr;
+    SmallArena &A = g_arena[device];
+    std::lock_guard<std::mutex> lock(A.mu);
     std::vector<int32_t> status(n_circuits, 0);
     const size_t amp = precision == QCM_C64 ? 8 : 16;
     const size_t smem = ((size_t)amp + 8) << maxq;
+    const size_t nc = (size_t)n_circuits;
+    // input blob (host pinned, mirrored at the start of the device buffer), then the outputs
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += up256(std::max<size_t>(bytes, 1)); return o; };
+    const size_t o_nq = take(nc * 4), o_ob = take((nc + 1) * 8), o_ops = take((size_t)n_ops * sizeof(qcm_op)),
+                 o_tab = take(n_tables * 8), o_pm = take(nc * 8), o_pv = take(nc * 8), o_psb = take(nc * 4),
+                 o_pb = take((nc + 1) * 8), o_sid = take(stream_ids ? nc * 8 : 0), o_cq = take(shots ? 64 * nc * 4 : 0),
+                 o_ncl = take(shots ? nc * 4 : 0);
+    const size_t in_bytes = off;
+    const size_t o_keys = take(shots ? shots * nc * 8 : 0), o_kept = take(nc * 8), o_status = take(nc * 4),
+                 o_probs = take(probs_out ? (size_t)pbeg[n_circuits] * 8 : 0);
+    const size_t dev_bytes = off;
+    char *hp, *dp;
     SM_CUDA(cudaSetDevice(device));
-    SM_CUDA(cudaEventCreate(&e0));
-    SM_CUDA(cudaEventCreate(&e1));
-    SM_CUDA(to_dev(&d_nq, n_qubits, n_circuits, st));
-    SM_CUDA(to_dev(&d_ob, op_begin, n_circuits + 1, st));
-    SM_CUDA(to_dev(&d_ops, ops, (size_t)n_ops, st));
-    SM_CUDA(to_dev(&d_tab, tables, n_tables, st));
-    SM_CUDA(to_dev(&d_pm, ps_mask, n_circuits, st));
-    SM_CUDA(to_dev(&d_pv, ps_value, n_circuits, st));
-    SM_CUDA(to_dev(&d_psb, ps_bits, n_circuits, st));
-    SM_CUDA(to_dev(&d_pb, pbeg.data(), n_circuits + 1, st));
-    if (stream_ids) SM_CUDA(to_dev(&d_sid, stream_ids, n_circuits, st));
+    SM_CUDA(arena_reserve(A, dev_bytes, in_bytes));
+    hp = (char *)A.pin;
+    dp = (char *)A.dev;
+    memcpy(hp + o_nq, n_qubits, nc * 4);
+    memcpy(hp + o_ob, op_begin, (nc + 1) * 8);
+    memcpy(hp + o_ops, ops, (size_t)n_ops * sizeof(qcm_op));
+    if (n_tables) memcpy(hp + o_tab, tables, n_tables * 8);
+    memcpy(hp + o_pm, ps_mask, nc * 8);
+    memcpy(hp + o_pv, ps_value, nc * 8);
+    memcpy(hp + o_psb, ps_bits, nc * 4);
+    memcpy(hp + o_pb, pbeg.data(), (nc + 1) * 8);
+    if (stream_ids) memcpy(hp + o_sid, stream_ids, nc * 8);
     if (shots) {
-        SM_CUDA(to_dev(&d_cq, clbit_qubit, (size_t)64 * n_circuits, st));
-        SM_CUDA(to_dev(&d_ncl, n_clbits, n_circuits, st));
-        SM_CUDA(cudaMalloc((void **)&d_keys, shots * n_circuits * sizeof(uint64_t)));
+        memcpy(hp + o_cq, clbit_qubit, 64 * nc * 4);
+        memcpy(hp + o_ncl, n_clbits, nc * 4);
     }
-    SM_CUDA(cudaMalloc((void **)&d_kept, n_circuits * sizeof(double)));
-    SM_CUDA(cudaMalloc((void **)&d_status, n_circuits * sizeof(int32_t)));
-    if (probs_out) {
-        SM_CUDA(cudaMalloc((void **)&d_probs, pbeg[n_circuits] * sizeof(double)));
-        SM_CUDA(cudaMemsetAsync(d_probs, 0, pbeg[n_circuits] * sizeof(double), st));
-    }
-    a.n_circuits = n_circuits; a.n_qubits = d_nq; a.op_begin = d_ob; a.ops = d_ops; a.tables = d_tab;
-    a.clbit_qubit = d_cq; a.n_clbits = d_ncl; a.ps_mask = d_pm; a.ps_value = d_pv; a.ps_bits = d_psb;
-    a.probs_begin = d_pb; a.shots = shots; a.seed = seed; a.keys_out = d_keys; a.probs_out = d_probs;
-    a.kept_out = d_kept; a.status_out = d_status; a.stream_ids = d_sid;
+    SM_CUDA(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, A.st));
+    if (probs_out) SM_CUDA(cudaMemsetAsync(dp + o_probs, 0, (size_t)pbeg[n_circuits] * 8, A.st));
+    a.n_circuits = n_circuits;
+    a.n_qubits = (const int32_t *)(dp + o_nq);
+    a.op_begin = (const int64_t *)(dp + o_ob);
+    a.ops = (const qcm_op *)(dp + o_ops);
+    a.tables = (const double *)(dp + o_tab);
+    a.clbit_qubit = shots ? (const int32_t *)(dp + o_cq) : nullptr;
+    a.n_clbits = shots ? (const int32_t *)(dp + o_ncl) : nullptr;
+    a.ps_mask = (const uint64_t *)(dp + o_pm);
+    a.ps_value = (const uint64_t *)(dp + o_pv);
+    a.ps_bits = (const int32_t *)(dp + o_psb);
+    a.probs_begin = (const int64_t *)(dp + o_pb);
+    a.shots = shots;
+    a.seed = seed;
+    a.keys_out = shots ? (uint64_t *)(dp + o_keys) : nullptr;
+    a.probs_out = probs_out ? (double *)(dp + o_probs) : nullptr;
+    a.kept_out = (double *)(dp + o_kept);
+    a.status_out = (int32_t *)(dp + o_status);
+    a.stream_ids = stream_ids ? (const uint64_t *)(dp + o_sid) : nullptr;
     if (precision == QCM_C64) {
         SM_CUDA(cudaFuncSetAttribute(k_small<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SM_CUDA(cudaEventRecord(e0, st));
-        k_small<float><<<n_circuits, kThreads, smem, st>>>(a);
+        SM_CUDA(cudaEventRecord(A.e0, A.st));
+        k_small<float><<<n_circuits, kThreads, smem, A.st>>>(a);
     } else {
         SM_CUDA(cudaFuncSetAttribute(k_small<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SM_CUDA(cudaEventRecord(e0, st));
-        k_small<double><<<n_circuits, kThreads, smem, st>>>(a);
+        SM_CUDA(cudaEventRecord(A.e0, A.st));
+        k_small<double><<<n_circuits, kThreads, smem, A.st>>>(a);
     }
     SM_CUDA(cudaGetLastError());
-    SM_CUDA(cudaEventRecord(e1, st));
-    SM_CUDA(cudaMemcpyAsync(kept_out, d_kept, n_circuits * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SM_CUDA(cudaMemcpyAsync(status.data(), d_status, n_circuits * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (probs_out) SM_CUDA(cudaMemcpyAsync(probs_out, d_probs, pbeg[n_circuits] * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (shots) SM_CUDA(cudaMemcpyAsync(keys_out, d_keys, shots * n_circuits * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SM_CUDA(cudaStreamSynchronize(st));
+    SM_CUDA(cudaEventRecord(A.e1, A.st));
+    SM_CUDA(cudaMemcpyAsync(kept_out, dp + o_kept, nc * sizeof(double), cudaMemcpyDeviceToHost, A.st));
+    SM_CUDA(cudaMemcpyAsync(status.data(), dp + o_status, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, A.st));
+    if (probs_out) SM_CUDA(cudaMemcpyAsync(probs_out, dp + o_probs, (size_t)pbeg[n_circuits] * sizeof(double), cudaMemcpyDeviceToHost, A.st));
+    if (shots) SM_CUDA(cudaMemcpyAsync(keys_out, dp + o_keys, shots * nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, A.st));
+    SM_CUDA(cudaStreamSynchronize(A.st));
     if (device_ms_out) {
         float ms = 0.f;
-        SM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        SM_CUDA(cudaEventElapsedTime(&ms, A.e0, A.e1));
         *device_ms_out = ms;
     }
     for (int c = 0; c < n_circuits; ++c)
         if (status[c]) { g_small_error = "circuit " + std::to_string(c) + ": unsupported op at position " + std::to_string(status[c] - 1); rc = QCM_ERR_INVALID; }
 done:
-    cudaFree(d_nq); cudaFree(d_cq); cudaFree(d_ncl); cudaFree(d_psb); cudaFree(d_status); cudaFree(d_ob); cudaFree(d_pb);
-    cudaFree(d_ops); cudaFree(d_tab); cudaFree(d_probs); cudaFree(d_kept); cudaFree(d_pm); cudaFree(d_pv); cudaFree(d_keys); cudaFree(d_sid);
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
     return rc;
 #undef SM_CUDA
 }
