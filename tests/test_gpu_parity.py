@@ -751,3 +751,25 @@ def test_rotated_expansion_is_transparent(precision, with_diag, flags):
             plain = ops.copy(); plain['flags'] = 0
             h.run_program(plain, tabs)
             assert np.abs(h.get_amplitudes().astype(np.complex128) - want).max() < tol
+
+
+def test_default_schedule_ends_in_the_rotated_expansion_kernel():
+    """The default (lazily materialised) schedule of a QCMRF circuit ends in a wide expansion pass; with
+    shots or without, that pass must be served by the rotated sequential-write kernel (k_expand_low), not
+    by a silent fallback -- and the results are those of brute-force enumeration."""
+    from qcmrf_b200 import workloads
+    n = 11
+    C = workloads.random_tree(n, 0, seed=3)                      # k = 10 ancillas -> passes of 2 and 8 new qubits
+    th = workloads.theta_for(C, seed=4)
+    pb, db, _ = mrf.brute_force_pmf(C, th)
+    for precision, tol in (('single', 1e-5), ('double', 1e-10)):
+        sim = B200Simulator(precision=precision, fusion='blocked', seed=5, small_batch=False)
+        for shots in (0, 4096):
+            res = sim.run(QCMRF(C, th), shots=shots).result()
+            names = sim.op_kernels()
+            assert names and names[-1].startswith('k_expand_low'), names
+            p, d = res.postselected_probabilities(0)
+            assert np.abs(p - pb).max() < tol and abs(d - db) < tol
+            if shots:
+                assert sum(res.get_counts().values()) == shots
+        sim.close()
