@@ -17,13 +17,14 @@ All amplitude arithmetic, the post-selection reduction and the shot sampling run
 the GPU through the C ABI (include/qcmrf_b200.h); this file only lowers, fuses,
 plans and formats.
 """
+import copy
 import os
 import time
 from typing import List, Optional, Sequence
 
 import numpy as np
 
-from . import _native, fusion, ir
+from . import _native, fusion, ir, plancache
 
 __all__ = ['B200Simulator', 'Job', 'Result', 'Counts']
 
@@ -68,6 +69,14 @@ def _host():
         except OSError:
             _host_lib = False
     return _host_lib
+
+
+def _clone_plan(pl, tables, fc):
+    """A cached plan around fresh coefficient tables (plancache.PlanCache rebuild hook)."""
+    q = copy.copy(pl)
+    q.tables = tables[0]
+    q.global_phase = fc.global_phase
+    return q
 
 
 def _keys_to_counts(keys, width, use_native=True):
@@ -172,7 +181,7 @@ class B200Simulator:
     the unseeded Aer run of the reference)."""
 
     def __init__(self, name='qasm_simulator', device=0, precision='double', fusion='blocked', block_max=4,
-                 seed=None, small_batch=True, small_fusion='clique', width='full', expand_max=8):
+                 seed=None, small_batch=True, small_fusion='clique', width='full', expand_max=8, plan_cache=True):
         if fusion not in _FUSION_MODES:
             raise ValueError('fusion must be one of %r' % (_FUSION_MODES,))
         if width not in ('full', 'release'):
@@ -192,6 +201,7 @@ class B200Simulator:
         self.small_fusion = small_fusion      # batched small circuits: fused programs are ~30x shorter to plan and ship
         self._handles = {}
         self._last = None
+        self._plan_cache = plancache.PlanCache() if plan_cache else None
         self.breakdown_ms = None               # host-side split of the last large-state run (bench.py)
 
     def name(self):
@@ -222,8 +232,18 @@ class B200Simulator:
         if release:
             fc, virtual = fusion.split_releasable(fc, keep_below=n_vars or 0)
         lazy = (mode == 'blocked') and not small
-        pl = fusion.plan(fc, lazy=lazy, block_max=block_max or self.block_max, elide=elide,
-                         expand_max=max(block_max or self.block_max, self.expand_max) if block_max is None else block_max)
+        bm = block_max or self.block_max
+        emax = max(bm, self.expand_max) if block_max is None else block_max
+
+        def build(f):
+            p = fusion.plan(f, lazy=lazy, block_max=bm, elide=elide, expand_max=emax)
+            return p, [p.tables]
+
+        if release or self._plan_cache is None:
+            pl = build(fc)[0]
+        else:
+            # same structure as an earlier circuit (a theta / beta sweep): reuse its plan, refresh the tables
+            pl = self._plan_cache.get(fc, ('b200', lazy, bm, elide, emax), build, _clone_plan)
         pr = _Prepared()
         pr.prog, pr.fc, pr.plan = prog, fc, pl
         pr.name = prog.name

@@ -41,6 +41,15 @@ def _bit_reverse(m):
     return r
 
 
+def _bit_reverse_inv(m):
+    """r with table[t] = values[r[t]]: the theta index whose bits are t reversed (its own inverse)."""
+    return _bit_reverse(m)
+
+
+_H0 = np.array([1.0, 1.0], dtype=np.complex128) / math.sqrt(2.0)
+_H0.setflags(write=False)
+
+
 class QCMRF(QuantumCircuit):
     """Quantum-circuit Markov random field over binary variables.
 
@@ -154,31 +163,49 @@ class QCMRF(QuantumCircuit):
             return None
         from .fusion import FusedCircuit, FusedOp
         n = self._mrf_n
-        gam = np.asarray(self.gamma, dtype=np.float64)
+        if self._mrf_gamma is not None:
+            gam = np.asarray(self._mrf_gamma, dtype=np.float64)
+        else:                                          # the `gamma` property, vectorised (same ufuncs, whole array)
+            with np.errstate(invalid='ignore'):
+                gam = 0.5 * np.arccos(np.exp(self._mrf_beta * 0.5 * np.asarray(self._mrf_theta, dtype=np.float64)))
         keep_all = np.abs(gam) > 1e-8
         c_all = np.where(keep_all, np.cos(2.0 * gam), 1.0)
         s_all = np.where(keep_all, np.sin(2.0 * gam), 0.0) * -1j
-        h0 = np.array([1.0, 1.0], dtype=np.complex128) / math.sqrt(2.0)
-        ops = []
-        offset = 0
+        st = self.__dict__.get('_mrf_struct')
+        if st is None:
+            # per clique size m: gather indices into gamma, already in table order (theta index
+            # i = sum_j y_j 2^(m-1-j); table index = sum_j y_j 2^j, bit j <-> j-th listed vertex)
+            by_m, offset = {}, 0
+            for ii, C in enumerate(self._mrf_cliques):
+                m = len(C)
+                if len(set(C)) != m:
+                    st = False
+                    break
+                by_m.setdefault(m, ([], []))
+                by_m[m][0].append(ii)
+                by_m[m][1].append(offset + _bit_reverse_inv(m))
+                offset += 1 << m
+            if st is None:
+                st = [(m, ids, np.stack(idx)) for m, (ids, idx) in by_m.items()]
+            self.__dict__['_mrf_struct'] = st
+        if st is False:
+            return None
+        ops = [None] * len(self._mrf_cliques)
         n_gates = n
-        for ii, C in enumerate(self._mrf_cliques):
-            m = len(C)
-            if len(set(C)) != m:
+        for m, ids, idx in st:
+            kept = keep_all[idx].sum(axis=1)
+            if not kept.all():
                 return None
-            sl = slice(offset, offset + (1 << m))
-            offset += 1 << m
-            kept = int(keep_all[sl].sum())
-            if not kept:
-                return None
-            # theta index i = sum_j y_j 2^(m-1-j); table index = sum_j y_j 2^j (bit j <-> j-th listed vertex)
-            rev = _bit_reverse(m)
-            table = np.empty((1 << m, 2, 2), dtype=np.complex128)
-            table[rev, 0, 0] = table[rev, 1, 1] = c_all[sl]
-            table[rev, 0, 1] = table[rev, 1, 0] = s_all[sl]
-            ops.append(FusedOp('mux', n + 1 + ii, tuple(n - 1 - v for v in C), table, zero_in=True, n_gates=4 + 2 * kept))
-            n_gates += 4 + 6 * kept
-        return FusedCircuit(self.num_qubits, {q: h0.copy() for q in range(n)}, ops, 0.0, n_gates)
+            T = np.empty((len(ids), 1 << m, 2, 2), dtype=np.complex128)
+            T[:, :, 0, 0] = T[:, :, 1, 1] = c_all[idx]
+            T[:, :, 0, 1] = T[:, :, 1, 0] = s_all[idx]
+            for r, ii in enumerate(ids):
+                k = int(kept[r])
+                ops[ii] = FusedOp('mux', n + 1 + ii, tuple(n - 1 - v for v in self._mrf_cliques[ii]), T[r], zero_in=True,
+                                  n_gates=4 + 2 * k)
+                n_gates += 4 + 6 * k
+        h0 = _H0
+        return FusedCircuit(self.num_qubits, {q: h0 for q in range(n)}, ops, 0.0, n_gates)
 
     # -- the reference's read-only surface (QCMRF.py:82-157) ------------------------------
     @property

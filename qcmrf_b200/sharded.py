@@ -32,7 +32,7 @@ from typing import List, Optional, Tuple
 
 import numpy as np
 
-from . import _native, fusion, ir
+from . import _native, fusion, ir, plancache
 QCM_MAX_GATHER = 3
 from .fusion import (OP_DTYPE, QCM_MAX_CTRL, QCM_OP_BLOCK, QCM_OP_DIAG, QCM_OP_EXTEND, QCM_OP_INIT_PRODUCT,
                      QCM_OP_MUX1Q, QCM_OP_SWAP, _Emitter)
@@ -354,13 +354,36 @@ class _ShardPrepared:
     __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions', 'pmf_map', 'pmf_order')
 
 
+def _clone_sharded(payload, tables, fc):
+    """Cached (plan, sharded plan) around fresh coefficient tables (plancache.PlanCache rebuild hook)."""
+    import copy
+    pl, sp = payload
+    pl2 = copy.copy(pl)
+    pl2.tables = tables[0]
+    pl2.global_phase = fc.global_phase
+    sp2 = copy.copy(sp)
+    segs, k = [], 1
+    for seg in sp.segments:
+        if seg[0] == 'run':
+            segs.append(('run', seg[1], tables[k], seg[3]))
+            k += 1
+        elif seg[0] == 'xblock':
+            segs.append(('xblock', seg[1], seg[2], tables[k], seg[4]))
+            k += 1
+        else:
+            segs.append(seg)
+    sp2.segments = segs
+    return pl2, sp2
+
+
 class ShardedSimulator:
     """One rank of a statevector sharded on its g highest physical qubits over the
     2^g ranks of the default (or given) process group.  Same surface as B200Simulator for
     what bench.py and the tests use: prepare / execute / run / exact / close."""
 
     def __init__(self, precision='single', fusion='blocked', block_max=4, device=0, seed=None, group=None,
-                 staging_bytes=1 << 30, name='qasm_simulator', layout='auto', expand_max=8, exchange='nccl'):
+                 staging_bytes=1 << 30, name='qasm_simulator', layout='auto', expand_max=8, exchange='nccl',
+                 plan_cache=True):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -401,6 +424,7 @@ class ShardedSimulator:
         self.exchange_bytes = 0
         self.breakdown_ms = {}
         self.sync_before_exchange = False
+        self._plan_cache = plancache.PlanCache() if plan_cache else None
 
     # ---- storage ---------------------------------------------------------------------------
     def _tensor_device(self):
@@ -496,9 +520,21 @@ class ShardedSimulator:
         ng = 0
         if lazy and self.layout == 'auto' and len(fusion.control_only_qubits(fc)) >= self.g:
             ng = self.g
-        pl = fusion.plan(fc, lazy=lazy, block_max=self.block_max, n_global=ng,
-                         expand_max=max(self.block_max, self.expand_max))
-        sp = shard_plan(pl, self.g, self.rank, fuse_exchange=(self.exchange == 'p2p'))
+        fuse_x = self.exchange == 'p2p'
+
+        def build(f):
+            p = fusion.plan(f, lazy=lazy, block_max=self.block_max, n_global=ng,
+                            expand_max=max(self.block_max, self.expand_max))
+            q = shard_plan(p, self.g, self.rank, fuse_exchange=fuse_x)
+            tabs = [p.tables] + [seg[2] if seg[0] == 'run' else seg[3] for seg in q.segments if seg[0] in ('run', 'xblock')]
+            return (p, q), tabs
+
+        if self._plan_cache is None:
+            pl, sp = build(fc)[0]
+        else:
+            # same structure as an earlier circuit (a theta / beta sweep): reuse plan + per-rank rewrite, refresh tables
+            pl, sp = self._plan_cache.get(fc, ('sharded', lazy, self.block_max, self.expand_max, ng, self.g, self.rank, fuse_x),
+                                          build, _clone_sharded)
         pr = _ShardPrepared()
         pr.prog, pr.fc, pr.plan, pr.sp, pr.name = prog, fc, pl, sp, prog.name
 

@@ -303,3 +303,40 @@ def test_qcmrf_fused_shortcut_equals_the_fusion_pass(models):
     c.x(0)
     prog = ir.lower(c)
     assert getattr(prog, 'fused_hint', None) is None or prog.fused_hint() is None
+
+
+def test_plan_cache_refreshes_tables_only(models):
+    """qcmrf_b200/plancache.py: a later circuit with the structure of an earlier one gets the cached plan
+    with gathered tables -- bit-identical to planning it in full, for every schedule; a structure whose
+    planning does arithmetic on the coefficients is recognised and never served from the cache."""
+    from qcmrf_b200 import plancache, backend
+    rng = np.random.RandomState(3)
+    graphs = [C for _s, _j, i, C, _th in all_models(models) if i == 0][:7] + [[[0, 1], [1, 2], [2, 3], [3, 4], [0, 4]]]
+    for C in graphs:
+        dim = sum(2 ** len(c) for c in C)
+        for lazy, bm in ((True, 4), (True, 1), (False, 1)):
+            pc = plancache.PlanCache()
+
+            def build(f):
+                p = fusion.plan(f, lazy=lazy, block_max=bm)
+                return p, [p.tables]
+            for rep in range(4):
+                th = -np.abs(rng.randn(dim))
+                if rep == 2:
+                    th[rng.randint(dim)] = 0.0
+                fc = fusion.fuse(ir.lower(QCMRF(C, list(th), beta=1.0 - 0.2 * rep)), 'clique')
+                got = pc.get(fc, (lazy, bm), build, backend._clone_plan)
+                want = fusion.plan(fc, lazy=lazy, block_max=bm)
+                assert np.array_equal(got.ops, want.ops) and np.array_equal(got.tables, want.tables)
+                assert got.layout == want.layout and got.n_phys == want.n_phys and got.global_phase == want.global_phase
+            assert pc.misses == 1 and pc.hits == 3
+    # a planner that multiplies coefficients (here: squares the tables) must be found out
+    fc = fusion.fuse(ir.lower(QCMRF([[0, 1]], [-0.1, -0.2, -0.3, -0.4])), 'clique')
+    pc = plancache.PlanCache()
+
+    def bad_build(f):
+        p = fusion.plan(f, lazy=True, block_max=4)
+        return p, [p.tables * p.tables]
+    pc.get(fc, (), bad_build, backend._clone_plan)
+    pc.get(fc, (), bad_build, backend._clone_plan)
+    assert pc.hits == 0 and pc.uncacheable == 1

@@ -67,6 +67,16 @@ def _worker(rank, world, port, q):
                 meta = res.metadata(0)
                 assert meta['exchanges'] == (1 if fus == 'clique' else 0)
                 out[(tuple(map(tuple, C)), fus, layout, prec, xch)] = (dict(counts), float(delta))
+                # a second and third parameter vector on the same graph: the plan cache serves them (same structure,
+                # refreshed tables) -- results must be those of the new parameters
+                for rep in range(2):
+                    th2 = list(-np.abs(rng.randn(len(th))) * 0.6)
+                    if rep == 1:
+                        th2[0] = 0.0                           # gamma == 0: a skipped term (identity entry)
+                    pb2, db2, _ = mrf.brute_force_pmf(C, th2)
+                    p2, d2 = sim.run(QCMRF(C, th2), shots=0).result().postselected_probabilities(0)
+                    assert np.abs(p2 - pb2).max() < tol and abs(d2 - db2) < tol, (fus, layout, 'cached plan')
+                assert sim._plan_cache.hits >= 2 and sim._plan_cache.misses == 1, (sim._plan_cache.hits, sim._plan_cache.misses)
                 sim.close()
         q.put((rank, 'ok', out))
         dist.destroy_process_group()
