@@ -620,26 +620,50 @@ def split_releasable(fc: FusedCircuit, keep_below: int = 0):
     return FusedCircuit(fc.n_qubits, dict(fc.init), core, fc.global_phase, fc.n_gates_in), virtual
 
 
+_MERGE_STEPS = {}
+
+
+def _merge_steps(ctrls):
+    """Structure of merge_diagonals for a list of index-qubit tuples: per member (flush?, union, gather
+    index of the running table, gather index of the member's table) -- depends on the qubits only, so a
+    sweep over one graph computes it once."""
+    steps = _MERGE_STEPS.get(ctrls)
+    if steps is None:
+        steps, cur = [], []
+        for ctrl in ctrls:
+            ctrl = list(ctrl)
+            union = list(cur) + [c for c in ctrl if c not in cur]
+            flush = len(union) > QCM_MAX_CTRL
+            if flush:
+                cur, union = [], ctrl
+            idx = np.arange(1 << len(union))
+            a = np.zeros_like(idx)
+            for j, c in enumerate(cur):
+                a |= ((idx >> union.index(c)) & 1) << j
+            b = np.zeros_like(idx)
+            for j, c in enumerate(ctrl):
+                b |= ((idx >> union.index(c)) & 1) << j
+            steps.append((flush, tuple(union), a, b))
+            cur = union
+        if len(_MERGE_STEPS) > 256:
+            _MERGE_STEPS.clear()
+        _MERGE_STEPS[ctrls] = steps
+    return steps
+
+
 def merge_diagonals(members):
     """Product of diagonal factors [(ctrl positions, complex table 2^m)] over the union of their index
     qubits, at most QCM_MAX_CTRL bits per merged table.  Returns [(ctrl positions, complex table)]."""
+    members = list(members)
+    steps = _merge_steps(tuple(tuple(int(c) for c in ctrl) for ctrl, _d in members))
     out = []
     cur_ctrl, cur_tab = [], np.ones(1, dtype=np.complex128)
-    for ctrl, d in members:
-        ctrl = list(ctrl)
-        union = list(cur_ctrl) + [c for c in ctrl if c not in cur_ctrl]
-        if len(union) > QCM_MAX_CTRL:
+    for (flush, union, a, b), (_ctrl, d) in zip(steps, members):
+        if flush:
             out.append((cur_ctrl, cur_tab))
-            cur_ctrl, cur_tab, union = [], np.ones(1, dtype=np.complex128), ctrl
-        idx = np.arange(1 << len(union))
-        a = np.zeros_like(idx)
-        for j, c in enumerate(cur_ctrl):
-            a |= ((idx >> union.index(c)) & 1) << j
-        b = np.zeros_like(idx)
-        for j, c in enumerate(ctrl):
-            b |= ((idx >> union.index(c)) & 1) << j
+            cur_tab = np.ones(1, dtype=np.complex128)
         cur_tab = cur_tab[a] * np.asarray(d)[b]
-        cur_ctrl = union
+        cur_ctrl = list(union)
     out.append((cur_ctrl, cur_tab))
     return out
 
