@@ -165,6 +165,19 @@ int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits,
 int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id,
                const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out);
 
+/* Shot sampling for the measure-and-release width: `released` qubits are not
+ * stored -- one sweep materialised each from |0> and nothing used it again (a QCMRF clique ancilla,
+ * measured right after its block, QCMRF.py:231-239).  The stored qubits' basis state is sampled as
+ * in qcm_sample; released qubit k then reads 1 with probability p1[p1_off[k] + idx], idx = the
+ * sampled bits at ctrl[k*max_ctrl .. + n_ctrl[k]) (physical positions), drawn on the device from a
+ * Philox stream keyed by (seed, stream_id, shot, k).  vclbit[k]: clbit of released qubit k (or -1);
+ * clbit_pos[c]: physical position feeding clbit c (or -1).  At most 64 released qubits.        */
+int qcm_sample_released(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id,
+                        int n_released, const int32_t *n_ctrl, const int32_t *ctrl, int max_ctrl,
+                        const double *p1, const int64_t *p1_off, int64_t n_p1,
+                        const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits,
+                        uint64_t *keys_out);
+
 /* Sharded sampling, three steps around one all-gather the caller performs:
  *  1. qcm_sample_prepare : builds the local sum tree, returns this rank's mass
  *  2. caller all-gathers the masses of all ranks

@@ -39,7 +39,8 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_small_max_qubits', 'qcm_run_batch_small', 'qcm_state_ptr', 'qcm_set_active',
            'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile', 'qcm_postselect_device',
            'qcm_sample_sharded_device', 'qcm_run_gather_block', 'qcm_enable_peer_access',
-           'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close', 'qcm_op_kernel_name']
+           'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close', 'qcm_op_kernel_name',
+           'qcm_sample_released']
 
 
 def lib():
@@ -83,6 +84,7 @@ def lib():
     L.qcm_ipc_open.argtypes = [i32, vp, vp]
     L.qcm_ipc_close.argtypes = [i32, vp]
     L.qcm_op_kernel_name.argtypes = [vp, i32]
+    L.qcm_sample_released.argtypes = [vp, u64, u64, u64, i32, vp, vp, i32, vp, vp, ctypes.c_int64, vp, vp, i32, vp]
     L.qcm_op_kernel_name.restype = ctypes.c_char_p
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
@@ -189,6 +191,14 @@ class Handle:
         cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
         self._check(lib().qcm_sample(self._h, int(shots), int(seed), int(stream_id), _ptr(cq),
                                      0 if cq is None else len(cq), _ptr(keys)))
+        return keys
+
+    def sample_released(self, shots, seed, stream_id, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_clbits):
+        """qcm_sample_released: full-width keys of a release-width circuit, released qubits drawn on the device."""
+        keys = np.empty(int(shots), dtype=np.uint64)
+        self._check(lib().qcm_sample_released(self._h, int(shots), int(seed), int(stream_id), len(n_ctrl), _ptr(n_ctrl),
+                                              _ptr(ctrl), int(ctrl.shape[1]), _ptr(p1), _ptr(p1_off), int(p1.size),
+                                              _ptr(vclbit), _ptr(clbit_pos), int(n_clbits), _ptr(keys)))
         return keys
 
     def run_gather_block(self, ops, tables, src_slab_ptrs, dst_ptr):

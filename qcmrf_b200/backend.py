@@ -401,8 +401,14 @@ class B200Simulator:
     def _sample_released(self, h, pr, shots, seed, stream):
         """Shots of a circuit whose released qubits are not stored: basis states of the stored qubits
         come from the GPU sampler, each released qubit's outcome from its sweep's coefficients at that
-        basis state (uniforms: numpy Philox keyed by (seed, stream), one column per released qubit)."""
+        basis state.  On the GPU engine that second step runs on the device too (qcm_sample_released); the
+        host version below (numpy Philox keyed by (seed, stream), one column per released qubit) serves an
+        engine without that entry point (the tests' numpy stand-in)."""
         pl = pr.plan
+        if hasattr(h, 'sample_released') and len(pr.virtual) <= 64:
+            # the engine draws the released qubits itself (k_released_keys, device Philox): one call, one read-back
+            mc, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_cl = self._released_tables(pr)
+            return h.sample_released(shots, seed, stream, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_cl)
         raw = h.sample(shots, seed, stream, None).astype(np.int64)
         rng = np.random.Generator(np.random.Philox(key=[int(seed) & (2 ** 64 - 1), int(stream) & (2 ** 64 - 1)]))
         u = rng.random((len(pr.virtual), shots))
@@ -424,10 +430,10 @@ class B200Simulator:
         return keys
 
     @staticmethod
-    def _released_keys_native(L, pr, raw, u):
-        """The same key assembly in one pass over the shots (csrc/qcm_host.c, qcm_released_keys)."""
+    def _released_tables(pr):
+        """Flat arrays describing the released qubits of a prepared circuit (cached on it)."""
         pl = pr.plan
-        nv, shots = len(pr.virtual), len(raw)
+        nv = len(pr.virtual)
         tabs = getattr(pr, '_released_tabs', None)
         if tabs is None:
             mc = max([len(v['ctrl']) for v in pr.virtual] + [1])
@@ -447,7 +453,13 @@ class B200Simulator:
                 elif pl.layout[q] < pl.n_phys:
                     clbit_pos[c] = pl.layout[q]
             tabs = pr._released_tabs = (mc, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_cl)
-        mc, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_cl = tabs
+        return tabs
+
+    @classmethod
+    def _released_keys_native(cls, L, pr, raw, u):
+        """The host-side key assembly in one pass over the shots (csrc/qcm_host.c, qcm_released_keys)."""
+        nv, shots = len(pr.virtual), len(raw)
+        mc, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_cl = cls._released_tables(pr)
         raw = np.ascontiguousarray(raw, dtype=np.int64)
         u = np.ascontiguousarray(u, dtype=np.float64)
         keys = np.empty(shots, dtype=np.uint64)

@@ -43,6 +43,7 @@ struct qcm_sim_s {
     DevBuf tab_f64, tab_real, init_lo, init_hi, probs, partial, keys, mine, tree, ctab, tilectr, subtree;
     DevBuf scratch;                 // input copy of a rotated expansion pass
     DevBuf lowpart;                 // its per-CTA partial sums when a CTA covers fewer inputs than a tree chunk
+    DevBuf relp1;                   // released-qubit probability tables (qcm_sample_released)
     // rotated storage (QCM_FLAG_ROTATED_OUTPUT_OK): logical index i of the 2^n_active state lives at
     // physical address ((i & (2^rot_nin - 1)) << rot_m) | (i >> rot_nin); rot_m == 0: identity
     int rot_m = 0, rot_nin = 0;
@@ -917,7 +918,7 @@ int qcm_destroy(qcm_handle h) {
     if (!h) return QCM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree, &h->scratch, &h->lowpart};
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree, &h->scratch, &h->lowpart, &h->relp1};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->own_state && h->state) cudaFree(h->state);
@@ -1432,6 +1433,59 @@ int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, 
     int rc = qcm_sample_prepare(h, &mass);
     if (rc) return rc;
     return qcm_sample_sharded(h, shots, seed, stream_id, &mass, 1, clbit_qubit, n_clbits, keys_out, nullptr);
+}
+
+int qcm_sample_released(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, int nv, const int32_t *n_ctrl,
+                        const int32_t *ctrl, int max_ctrl, const double *p1, const int64_t *p1_off, int64_t n_p1,
+                        const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits, uint64_t *keys_out) {
+    if (!h || !keys_out || !n_ctrl || !ctrl || !p1 || !p1_off || !vclbit || !clbit_pos) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if (h->n_global != 0) return fail(h, QCM_ERR_UNSUPPORTED, "released-qubit sampling on a sharded state");
+    if (nv < 0 || nv > kMaxReleased || n_clbits < 0 || n_clbits > 64 || max_ctrl < 1) return fail(h, QCM_ERR_INVALID, "bad released-qubit tables");
+    ReleasedArgs a{};
+    for (int k = 0; k < nv; ++k) {
+        if (n_ctrl[k] < 0 || n_ctrl[k] > QCM_MAX_CTRL || n_ctrl[k] > max_ctrl) return fail(h, QCM_ERR_INVALID, "released qubit %d: n_ctrl out of range", k);
+        if (p1_off[k] < 0 || p1_off[k] + (1ll << n_ctrl[k]) > n_p1) return fail(h, QCM_ERR_INVALID, "released qubit %d: table outside p1", k);
+        if (vclbit[k] >= 64) return fail(h, QCM_ERR_INVALID, "released qubit %d: clbit out of range", k);
+        a.n_ctrl[k] = (int8_t)n_ctrl[k];
+        a.p1_off[k] = (int32_t)p1_off[k];
+        a.vclbit[k] = (int8_t)(vclbit[k] < 0 ? -1 : vclbit[k]);
+        for (int j = 0; j < n_ctrl[k]; ++j) {
+            const int c = ctrl[(size_t)k * max_ctrl + j];
+            if (c < 0 || c >= h->n_local) return fail(h, QCM_ERR_INVALID, "released qubit %d: index qubit %d out of range", k, c);
+            a.ctrl[k][j] = (int8_t)c;
+        }
+    }
+    for (int c = 0; c < 64; ++c) a.clbit_pos[c] = -1;
+    for (int c = 0; c < n_clbits; ++c) {
+        if (clbit_pos[c] >= h->n_local) return fail(h, QCM_ERR_INVALID, "clbit %d maps to qubit %d out of range", c, clbit_pos[c]);
+        a.clbit_pos[c] = (int8_t)(clbit_pos[c] < 0 ? -1 : clbit_pos[c]);
+    }
+    // raw basis states of the stored qubits, on the device (the sampler's own stream: seed, stream_id)
+    double mass = 0.0;
+    int rc = qcm_sample_prepare(h, &mass);
+    if (rc) return rc;
+    if (shots == 0) return QCM_OK;
+    if ((rc = ensure(h, h->keys, shots * sizeof(uint64_t)))) return rc;
+    if ((rc = ensure(h, h->relp1, (size_t)n_p1 * sizeof(double)))) return rc;
+    if ((rc = sample_sharded_impl(h, shots, seed, stream_id, &mass, 1, nullptr, 0, (uint64_t *)h->keys.p, nullptr, true))) return rc;
+    QCM_CUDA(h, cudaMemcpyAsync(h->relp1.p, p1, (size_t)n_p1 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    a.keys = (uint64_t *)h->keys.p;
+    a.shots = shots;
+    a.seed = seed;
+    a.stream = stream_id;
+    a.p1 = (const double *)h->relp1.p;
+    a.nv = nv;
+    a.n_clbits = n_clbits;
+    k_released_keys<<<(unsigned)((shots + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>(a);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    QCM_CUDA(h, cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->timing.sample_ms = ms;
+    return QCM_OK;
 }
 
 int qcm_get_timing(qcm_handle h, qcm_timing *out) {

@@ -1461,6 +1461,47 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
 }
 
 // ----------------------------------------------------------------------------------
+// Measure-and-release width: full-width keys from the sampled basis states of the
+// stored qubits.  A released qubit k (never stored: one sweep materialised it from |0> and nothing
+// used it again) reads 1 with probability p1_k[index bits of the sampled state at ctrl_k]; its
+// uniform is Philox keyed by (seed ^ kReleasedKey, stream) at counter shot * nv + k, independent of
+// the sampler's stream.  One thread per shot, in place over the sampler's output.
+// ----------------------------------------------------------------------------------
+constexpr uint64_t kReleasedKey = 0x9E3779B97F4A7C15ull;
+constexpr int kMaxReleased = 64;
+
+struct ReleasedArgs {
+    uint64_t *keys;                 // in: raw basis-state indices (k_sample without a clbit map); out: keys
+    uint64_t shots, seed, stream;
+    const double *p1;               // device: concatenated tables, p1_off[k] their starts
+    int32_t nv, n_clbits;
+    int32_t p1_off[kMaxReleased];
+    int8_t n_ctrl[kMaxReleased];
+    int8_t ctrl[kMaxReleased][QCM_MAX_CTRL];
+    int8_t vclbit[kMaxReleased];    // clbit of released qubit k, or -1
+    int8_t clbit_pos[64];           // physical position feeding clbit c, or -1
+};
+
+static __global__ void __launch_bounds__(kThreads) k_released_keys(const __grid_constant__ ReleasedArgs a) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.shots) return;
+    const uint64_t r = a.keys[s];
+    uint64_t key = 0;
+    for (int c = 0; c < a.n_clbits; ++c) {
+        const int p = a.clbit_pos[c];
+        if (p >= 0) key |= ((r >> p) & 1ull) << c;
+    }
+    for (int k = 0; k < a.nv; ++k) {
+        if (a.vclbit[k] < 0) continue;
+        uint32_t idx = 0;
+        for (int j = 0; j < a.n_ctrl[k]; ++j) idx |= (uint32_t)((r >> a.ctrl[k][j]) & 1ull) << j;
+        const double u = philox_uniform(a.seed ^ kReleasedKey, a.stream, s * (uint64_t)a.nv + (uint64_t)k);
+        if (u < a.p1[a.p1_off[k] + idx]) key |= 1ull << a.vclbit[k];
+    }
+    a.keys[s] = key;
+}
+
+// ----------------------------------------------------------------------------------
 // Post-selection.
 // ----------------------------------------------------------------------------------
 // contiguous kept set (QCMRF: the first 2^n amplitudes): probs[i] = |amp_i|^2 and a
