@@ -33,6 +33,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from .ir import Gate, Program
+from .ir import _CTRL_BASE as _CTRL_BASE_NAME
 
 TOL = 1e-9
 
@@ -73,6 +74,7 @@ class _Block:
         self.cpos: List[int] = []                  # block positions that own a column bit
         self.U = np.ones((1, 1), dtype=np.complex128)
         self.n_gates = 0
+        self._uaddr_of, self._uaddr = None, 0      # address of self.U for the C row mixer (refreshed when U is replaced)
 
     def add_qubit(self, q):
         p = len(self.qubits)
@@ -95,6 +97,22 @@ class _Block:
         for q, v in zip(g.controls, g.ctrl_values):
             cmask |= 1 << self.pos[q]
             cval |= v << self.pos[q]
+        if _HOST_APPLY is not None:
+            # one C pass over the selected row pairs (csrc/qcm_host.c), same arithmetic as below
+            if self._uaddr_of is not U:
+                if not U.flags.c_contiguous:
+                    U = self.U = np.ascontiguousarray(U)
+                self._uaddr_of, self._uaddr = U, U.ctypes.data
+            bk = (g.name if not g.controls else _CTRL_BASE_NAME.get(g.name, g.name), g.params)
+            ent = _B_ADDR.get(bk)
+            if ent is None or ent[0] is not B:
+                Bc = np.ascontiguousarray(B, dtype=np.complex128)
+                ent = _B_ADDR[bk] = (B, Bc, Bc.ctypes.data)
+                if len(_B_ADDR) > 65536:
+                    _B_ADDR.clear()
+            _HOST_APPLY(self._uaddr, U.shape[0], U.shape[1], cmask, cval, 1 << self.pos[g.target], ent[2])
+            self.n_gates += 1
+            return
         r0, r1 = _pair_rows(nq, cmask, cval, 1 << self.pos[g.target])
         b00, b01, b10, b11 = B[0, 0], B[0, 1], B[1, 0], B[1, 1]
         if b01 == 0 and b10 == 0:                       # diagonal: scale rows
@@ -114,6 +132,23 @@ class _Block:
         self.n_gates += 1
 
 
+def _load_host_apply():
+    """qcm_block_apply of qcmrf_b200/_qcm_host.so, or None when the library is not built (numpy path)."""
+    import ctypes
+    import os
+    try:
+        L = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), '_qcm_host.so'))
+        f = L.qcm_block_apply
+    except (OSError, AttributeError):
+        return None
+    f.restype = None
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                  ctypes.c_void_p]
+    return f
+
+
+_HOST_APPLY = _load_host_apply()
+_B_ADDR = {}                                       # (base gate, params) -> (matrix, contiguous copy, its address)
 _PAIR_ROWS = {}
 
 

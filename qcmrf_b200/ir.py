@@ -38,9 +38,28 @@ _CTRL_BASE = {'cx': 'x', 'cy': 'y', 'cz': 'z', 'ch': 'h', 'cp': 'p', 'crz': 'rz'
               'cry': 'ry', 'mcx': 'x', 'mcp': 'p', 'csx': 'sx'}
 
 
+_PARAM_CACHE = {}
+
+
 def one_qubit_matrix(name, params=()):
+    """2x2 matrix of a primitive 1-qubit gate.  Returned arrays are shared: treat them as read-only."""
     if name in _ONEQ:
         return _ONEQ[name]
+    key = (name, params)
+    try:
+        hit = _PARAM_CACHE.get(key)
+    except TypeError:                               # unhashable params (a list): no caching
+        return _one_qubit_matrix(name, params)
+    if hit is None:
+        hit = _one_qubit_matrix(name, params)
+        hit.setflags(write=False)
+        if len(_PARAM_CACHE) > 65536:
+            _PARAM_CACHE.clear()
+        _PARAM_CACHE[key] = hit
+    return hit
+
+
+def _one_qubit_matrix(name, params=()):
     lam = float(params[0]) if params else 0.0
     if name == 'rz':
         return np.array([[np.exp(-0.5j * lam), 0], [0, np.exp(0.5j * lam)]])

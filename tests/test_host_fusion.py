@@ -340,3 +340,41 @@ def test_plan_cache_refreshes_tables_only(models):
     pc.get(fc, (), bad_build, backend._clone_plan)
     pc.get(fc, (), bad_build, backend._clone_plan)
     assert pc.hits == 0 and pc.uncacheable == 1
+
+
+def test_native_block_apply_equals_numpy(monkeypatch):
+    """csrc/qcm_host.c::qcm_block_apply (the fusion pass's row mixer) == the numpy version, gate by gate:
+    random controlled / uncontrolled gates incl. diagonal and X-type fast paths, qubits joining mid-way."""
+    from qcmrf_b200 import build
+    from qcmrf_b200.ir import Gate
+    build.build_host()
+    assert fusion._load_host_apply() is not None
+    rng = np.random.RandomState(8)
+    names1 = ['h', 'x', 'sx', 't', 'z']
+    for trial in range(20):
+        nq = int(rng.randint(2, 7))
+        zero = set(int(q) for q in rng.permutation(nq)[:int(rng.randint(0, nq))])
+        gates = []
+        for _ in range(60):
+            r = rng.rand()
+            q = [int(x) for x in rng.permutation(nq)]
+            if r < 0.3:
+                gates.append(Gate(names1[rng.randint(len(names1))], (q[0],)))
+            elif r < 0.5:
+                gates.append(Gate('rz', (q[0],), (float(rng.uniform(-3, 3)),)))
+            elif r < 0.7:
+                gates.append(Gate('cx', (q[0], q[1]), (), (1,)))
+            elif r < 0.85 and nq >= 3:
+                gates.append(Gate('mcx', (q[0], q[1], q[2]), (), (int(rng.randint(2)), int(rng.randint(2)))))
+            else:
+                gates.append(Gate('cp', (q[0], q[1]), (float(rng.uniform(-3, 3)),), (1,)))
+        a = fusion._Block(zero)
+        for g in gates:
+            a.apply(g)
+        monkeypatch.setattr(fusion, '_HOST_APPLY', None)
+        b = fusion._Block(zero)
+        for g in gates:
+            b.apply(g)
+        monkeypatch.undo()
+        assert a.qubits == b.qubits and a.U.shape == b.U.shape
+        assert np.abs(a.U - b.U).max() < 1e-13
