@@ -116,7 +116,13 @@ def cpu_reference(target_cliques, steps=1, warmup=0, sample_vars=None):
     from oracle import cbridge, program
     from qcmrf_b200 import workloads
     cores = len(os.sched_getaffinity(0))
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    # every host thread, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    os.environ['OMP_NUM_THREADS'] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL('libgomp.so.1').omp_set_num_threads(cores)
+    except OSError:
+        pass
     n_t, k_t, N_t, _ = program.sizes(target_cliques)
     ops_t, _ = program.qcmrf_program(target_cliques, workloads.theta_for(target_cliques))
     g_t = sum(1 for g in ops_t if g[0] not in ('measure', 'barrier'))
