@@ -244,6 +244,17 @@ def _classify(blk: _Block, tol=TOL):
     return None
 
 
+def _unrestored_zero_qubits(blk: _Block, tol=TOL):
+    """Known-|0> qubits of the block that its gates leave with weight on |1> (for some input).  Two or
+    more of them and the block cannot be a single sweep (_classify: such a qubit must be THE target)."""
+    nq = len(blk.qubits)
+    U = blk.U
+    ridx = np.arange(1 << nq)
+    rowmax = np.abs(U).max(axis=1, initial=0.0)
+    return {blk.qubits[p] for p in range(nq)
+            if p not in blk.cpos and rowmax[((ridx >> p) & 1) == 1].max(initial=0.0) >= tol}
+
+
 _MATCH = {}
 
 
@@ -487,6 +498,13 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
                 return False
         return True
 
+    live_from = [0] * (n + 1)                      # distinct qubits used by gates[i:]
+    seen_q: set = set()
+    for gi in range(n - 1, -1, -1):
+        seen_q.update(gates[gi].qubits)
+        live_from[gi] = len(seen_q)
+    doom: Optional[set] = None
+
     i = 0
     while i < n:
         g0 = gates[i]
@@ -514,6 +532,12 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
         blk = _Block(zero)
         best = None
         j = i
+        # `doom`: known-|0> qubits that an earlier block reaching the end of the circuit left on |1>.  If two
+        # of them are still known-|0> here, this block's end cannot classify either (they stay unrestored
+        # for the larger input set too, and such a qubit must be THE target of a sweep): once every qubit
+        # that can still join has joined, applying the tail is pointless.  A transpiled circuit otherwise
+        # re-applies its whole body once per variable of the H layer (rz.sx.rz runs peel one per attempt).
+        doomed = doom is not None and sum(1 for q in doom if q in zero) >= 2
         while j < n:
             g = gates[j]
             new = [q for q in g.qubits if q not in blk.pos]
@@ -527,10 +551,15 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
                     break
             blk.apply(g)
             j += 1
+            if doomed and len(blk.qubits) == live_from[i]:
+                break
         else:
             res = _classify(blk)
             if res is not None:
                 best = (j, res)
+            else:
+                left = _unrestored_zero_qubits(blk)
+                doom = left if len(left) >= 2 else None
         if best is None:
             best = (i + 1, _single_gate_op(gates[i], zero))
         emit(best[1])
