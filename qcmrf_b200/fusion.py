@@ -565,14 +565,21 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
         emit(best[1])
         i = best[0]
 
-    # uncontrolled sweeps on still-|0> qubits belong to the product-state initialiser
+    # uncontrolled sweeps on qubits that nothing has touched yet belong to the product-state initialiser:
+    # the first on a |0> qubit sets its 2-vector, further ones (the rest of a transpiled H: the fusion
+    # loop peels rz.sx.rz gate by gate) multiply it
     init: Dict[int, np.ndarray] = {}
     kept: List[FusedOp] = []
+    entangled: set = set()                         # qubits some kept sweep involves
     for op in ops:
-        if op.kind == 'mux' and not op.ctrls and op.zero_in and op.target not in init:
-            init[op.target] = op.table[0][:, 0].copy()
+        if op.kind == 'mux' and not op.ctrls and op.target not in entangled and (op.zero_in or op.target in init):
+            v = init.get(op.target)
+            init[op.target] = op.table[0][:, 0].copy() if v is None else op.table[0] @ v
         else:
             kept.append(op)
+            entangled.update(op.ctrls)
+            if op.kind == 'mux':
+                entangled.add(op.target)
     return FusedCircuit(prog.n_qubits, init, kept, phase, len(prog.gates))
 
 
