@@ -378,3 +378,25 @@ def test_native_block_apply_equals_numpy(monkeypatch):
         monkeypatch.undo()
         assert a.qubits == b.qubits and a.U.shape == b.U.shape
         assert np.abs(a.U - b.U).max() < 1e-13
+
+
+def test_transpiled_circuits_fuse_to_the_same_program_structure(models):
+    """The reference submits TRANSPILED circuits (run_experiment.py:52, basis cx/id/rz/sx/x).  Their fused
+    form must have the structure of the untranspiled circuit's: the transpiled H layer folds into the
+    initial product state completely, every clique block is ONE multiplexer on its still-|0> ancilla --
+    so the planner emits the same passes (tables differ by per-qubit phases only)."""
+    from qcmrf_b200 import workloads
+    cases = [(C, models['0.5']['THETAS'][str(j)][0]) for j, C in enumerate(models['0.5']['GRAPHS'])]
+    C16 = workloads.random_tree(8, 0, seed=2)                    # 16 qubits: large-state (lazy, blocked) planning
+    cases.append((C16, workloads.theta_for(C16, seed=2)))
+    for C, th in cases:
+        plain = fusion.fuse(ir.lower(QCMRF(C, th)), 'clique', use_hint=False)
+        T = transpile([QCMRF(C, th)], basis_gates=['cx', 'id', 'rz', 'sx', 'x'])[0]
+        fused = fusion.fuse(ir.lower(T), 'clique')
+        assert sorted(fused.init) == sorted(plain.init)
+        assert [(o.kind, o.target, tuple(sorted(o.ctrls)), o.zero_in) for o in fused.ops] == \
+               [(o.kind, o.target, tuple(sorted(o.ctrls)), o.zero_in) for o in plain.ops]
+        pa = fusion.plan(plain, lazy=True, block_max=4)
+        pb = fusion.plan(fused, lazy=True, block_max=4)
+        assert pa.n_phys == pb.n_phys and pa.n_passes == pb.n_passes and pa.layout == pb.layout
+        assert [int(k) for k in pa.ops['kind']] == [int(k) for k in pb.ops['kind']]
