@@ -400,3 +400,28 @@ def test_transpiled_circuits_fuse_to_the_same_program_structure(models):
         pb = fusion.plan(fused, lazy=True, block_max=4)
         assert pa.n_phys == pb.n_phys and pa.n_passes == pb.n_passes and pa.layout == pb.layout
         assert [int(k) for k in pa.ops['kind']] == [int(k) for k in pb.ops['kind']]
+
+
+def test_merge_diagonals_equals_brute_force():
+    """fusion.merge_diagonals (gather structure cached per index-qubit list): the product of the merged
+    tables over any basis state equals the product of the original factors, also when the union of index
+    qubits overflows QCM_MAX_CTRL and a second table is started; a repeated call with other values reuses
+    the cached structure."""
+    rng = np.random.RandomState(21)
+    nq = 14
+    for trial in range(6):
+        ctrls = [tuple(int(c) for c in rng.permutation(nq)[:int(rng.randint(1, 4))]) for _ in range(int(rng.randint(3, 12)))]
+        for rep in range(2):
+            members = [(c, np.exp(1j * rng.uniform(0, 6, 1 << len(c)))) for c in ctrls]
+            merged = fusion.merge_diagonals(members)
+            assert all(len(c) <= fusion.QCM_MAX_CTRL for c, _t in merged)
+            x = rng.randint(0, 1 << nq, size=200)
+
+            def value(ctrl, tab):
+                idx = np.zeros_like(x)
+                for j, c in enumerate(ctrl):
+                    idx |= ((x >> c) & 1) << j
+                return np.asarray(tab)[idx]
+            want = np.prod([value(c, t) for c, t in members], axis=0)
+            got = np.prod([value(c, t) for c, t in merged], axis=0)
+            assert np.abs(got - want).max() < 1e-12
