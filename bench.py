@@ -352,7 +352,7 @@ def main():
         achieved = (rd + wr) / (top_ms * 1e-3) / 1e9
         total_bytes = sum(r[2] + r[3] for r in prof)
         prog_ms = sum(r[1] for r in prof)
-        line = {'metric': METRIC, 'value': world_value(1e3 / ms_per_step), 'unit': 'circuits/s', 'n_gpus': world,
+        line = {'metric': METRIC, 'value': 1e3 / ms_per_step, 'unit': 'circuits/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': workload_config(args, cliques, N),
@@ -580,10 +580,6 @@ def dense_gate_pass(args, cliques, device, world=1):
             out['fused_exchange'] = {'unavailable': getattr(sim, 'p2p_error', 'no fused segment in the plan')}
         sim.close()
     return out
-
-
-def world_value(v):
-    return float(v)
 
 
 if __name__ == '__main__':

@@ -418,8 +418,8 @@ def fold_clean_scratch(gates: List[Gate], n_qubits: int) -> List[Gate]:
                 if s_q in hq and gates[j].ctrl_values[hq.index(s_q)] != 1:
                     break
                 j += 1
-            if j == i + 2 and gates[j].qubits[-1] != s_q:
-                j = n                                    # the scan stopped for another reason
+            if j == i + 2 and (j >= n or gates[j].qubits[-1] != s_q):
+                j = n                                    # the scan stopped for another reason (or ran off the end)
             if (j < n and j > i + 1 and gates[j].qubits == gq and gates[j].name in ('cx', 'mcx')
                     and gates[j].ctrl_values == g.ctrl_values):
                 inner = gates[i + 1:j]
@@ -444,6 +444,27 @@ def fold_clean_scratch(gates: List[Gate], n_qubits: int) -> List[Gate]:
     return out
 
 
+def prune_zero_controls(gates: List[Gate], n_qubits: int) -> List[Gate]:
+    """A qubit no gate has targeted yet is still |0>: a closed control on it never fires (the gate is
+    the identity and is dropped), an open control on it always fires (the control is dropped).  Without
+    this a sweep could be indexed by a qubit the lazy layout never materialises (`cx(2,1)` on |0000>)."""
+    clean = set(range(n_qubits))
+    out: List[Gate] = []
+    for g in gates:
+        gq = g.qubits
+        if len(gq) > 1 and not clean.isdisjoint(gq[:-1]):
+            if any(q in clean and v == 1 for q, v in zip(gq, g.ctrl_values)):
+                continue
+            keep = [(q, v) for q, v in zip(gq, g.ctrl_values) if q not in clean]
+            if keep:
+                g = Gate(g.name, tuple(q for q, _ in keep) + (gq[-1],), g.params, tuple(v for _, v in keep))
+            else:
+                g = Gate(_CTRL_BASE_NAME.get(g.name, g.name), (gq[-1],), g.params, ())
+        out.append(g)
+        clean.discard(gq[-1])
+    return out
+
+
 _MC_NAME = {'cx': 'mcx', 'mcx': 'mcx', 'cp': 'mcp', 'mcp': 'mcp'}
 
 
@@ -465,7 +486,7 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
     zero = set(range(prog.n_qubits))
     ops: List[FusedOp] = []
     phase = prog.global_phase
-    gates: List[Gate] = fold_clean_scratch(prog.gates, prog.n_qubits)
+    gates: List[Gate] = prune_zero_controls(fold_clean_scratch(prog.gates, prog.n_qubits), prog.n_qubits)
     n = len(gates)
     last_use: Dict[int, int] = {}
     first_use: Dict[int, int] = {}
@@ -678,13 +699,18 @@ def split_releasable(fc: FusedCircuit, keep_below: int = 0):
     (QCMRF.py:231-239) -- need not be stored at all.  Returns (core circuit without those sweeps,
     list of the released sweeps).  Qubits below ``keep_below`` (the variable register) are kept."""
     used_later = {}
+    last_targeted = {}
     for k, op in enumerate(fc.ops):
         for q in ((op.target,) if op.kind == 'mux' else ()) + tuple(op.ctrls):
             used_later[q] = k
+        if op.kind == 'mux':
+            last_targeted[op.target] = k
     core, virtual = [], []
     for k, op in enumerate(fc.ops):
+        # the released outcome is drawn from (and its projection applied to) the FINAL value of the
+        # sweep's index qubits: only exact if no later sweep changes them (non-diagonal = 'mux' target)
         if (op.kind == 'mux' and op.zero_in and op.target >= keep_below and used_later[op.target] == k
-                and op.target not in fc.init):
+                and op.target not in fc.init and all(last_targeted.get(c, -1) < k for c in op.ctrls)):
             virtual.append(op)
         else:
             core.append(op)

@@ -181,6 +181,18 @@ def _emit(prog, name, qubits, params, ctrl_values=None):
         return
     if len(set(qubits)) != len(qubits):
         raise ValueError('duplicate qubit arguments in %s%r' % (name, qubits))
+    if prog.measures:
+        # measurements are deferred to the end of the program (sampled from the final state, as Aer does
+        # for this circuit class); that is exact only while nothing touches a qubit after its measurement
+        mq = getattr(prog, '_measured_q', None)
+        if mq is None or len(mq[1]) != len(prog.measures):
+            mq = prog._measured_q = (set(prog.measures.values()), dict(prog.measures))
+        if not mq[0].isdisjoint(qubits):
+            raise ValueError('qcmrf_b200: gate %s%r follows a measurement of one of its qubits; mid-circuit '
+                             'measurement with later use of the qubit is not supported' % (name, qubits))
+    if params and not all(np.isfinite(float(p)) for p in params):
+        raise ValueError('qcmrf_b200: gate %s%r has a non-finite parameter (a QCMRF with theta > 0 has no '
+                         'circuit angle: theta must be <= 0)' % (name, qubits))
     if canon == 'swap':
         a, b = qubits
         for c, t in ((a, b), (b, a), (a, b)):
@@ -225,6 +237,9 @@ def _walk(prog, circ, qmap, cmap):
             continue
         if name in ('barrier', 'delay'):
             continue
+        if name == 'reset' or getattr(op, 'condition', None) is not None:
+            raise ValueError('qcmrf_b200: %s is not supported (measurements are deferred to the end of the '
+                             'program)' % ('reset' if name == 'reset' else 'a classically conditioned gate'))
         canon = _ALIASES.get(name, name)
         primitive = canon in _ONEQ or canon in _PARAM1Q or canon in _CTRL_BASE or canon in ('swap', 'u')
         if primitive:

@@ -126,6 +126,8 @@ class QCMRF(QuantumCircuit):
         for q in range(n):
             gates.append(Gate('h', (q,)))
         gam = self.gamma
+        if not all(math.isfinite(g) for g in gam):
+            raise ValueError('QCMRF: theta must be <= 0 (gamma is not finite)')
         offset = 0
         for ii, C in enumerate(self._mrf_cliques):
             anc = n + 1 + ii
@@ -168,6 +170,10 @@ class QCMRF(QuantumCircuit):
         else:                                          # the `gamma` property, vectorised (same ufuncs, whole array)
             with np.errstate(invalid='ignore'):
                 gam = 0.5 * np.arccos(np.exp(self._mrf_beta * 0.5 * np.asarray(self._mrf_theta, dtype=np.float64)))
+        if not np.isfinite(gam).all():
+            # theta > 0 has no circuit angle (arccos of a value > 1, QCMRF.py:154): the reference emits cp(nan)
+            raise ValueError('QCMRF: theta must be <= 0 (gamma is not finite for %d parameter(s))'
+                             % int((~np.isfinite(gam)).sum()))
         keep_all = np.abs(gam) > 1e-8
         c_all = np.where(keep_all, np.cos(2.0 * gam), 1.0)
         s_all = np.where(keep_all, np.sin(2.0 * gam), 0.0) * -1j

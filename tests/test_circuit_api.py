@@ -193,7 +193,7 @@ def test_direct_lowering_equals_walking_the_instruction_list(models):
                 assert (a.name, a.qubits, a.ctrl_values) == (b.name, b.qubits, b.ctrl_values)
                 assert np.allclose(a.params, b.params, rtol=0, atol=0)
     # gamma-only construction and an edited circuit
-    c = QCMRF([[0, 1]], gamma=[0.1, 0.2, 0.3, 0.4])
+    c = QCMRF([[0, 1]], gamma=[0.1, 0.2, 0.3, 0.4], with_measurements=False)
     c.h(0)
     assert ir.lower(c).gates[-1].name == 'h' and len(ir.lower(c).gates) == len(ir.lower(QCMRF([[0, 1]], gamma=[0.1, 0.2, 0.3, 0.4])).gates) + 1
 

@@ -299,7 +299,7 @@ def test_qcmrf_fused_shortcut_equals_the_fusion_pass(models):
                 assert (a.kind, a.target, tuple(a.ctrls), a.zero_in) == (b.kind, b.target, tuple(b.ctrls), b.zero_in)
                 assert np.abs(a.table - b.table).max() < 1e-14
     # editing the circuit materialises the instruction list: no shortcut any more
-    c = QCMRF([[0, 1]], [-0.1, -0.2, -0.3, -0.4])
+    c = QCMRF([[0, 1]], [-0.1, -0.2, -0.3, -0.4], with_measurements=False)
     c.x(0)
     prog = ir.lower(c)
     assert getattr(prog, 'fused_hint', None) is None or prog.fused_hint() is None
@@ -425,3 +425,97 @@ def test_merge_diagonals_equals_brute_force():
             want = np.prod([value(c, t) for c, t in members], axis=0)
             got = np.prod([value(c, t) for c, t in merged], axis=0)
             assert np.abs(got - want).max() < 1e-12
+
+
+# ---- regression tests for the round-1 advisor findings ---------------------------------------------
+def _gate_by_gate(circ):
+    prog = ir.lower(circ)
+    psi, _ = sv.run_program(ir.to_oracle_ops(prog), prog.n_qubits)
+    return prog, psi
+
+
+def test_ghz_ending_in_cx_onto_clean_qubits():
+    """fold_clean_scratch looked one gate past the end when the second-to-last gate was a cx onto a
+    clean qubit (IndexError on the 3-qubit GHZ)."""
+    from qcmrf_b200.circuit import QuantumCircuit
+    c = QuantumCircuit(3, 3)
+    c.h(0); c.cx(0, 1); c.cx(0, 2)
+    c.measure(range(3), range(3))
+    prog, psi = _gate_by_gate(c)
+    for mode, lazy, bm in CONFIGS:
+        lg, _, _ = _logical(prog, mode, lazy, bm)
+        assert np.abs(lg - psi).max() < 1e-14, (mode, lazy, bm)
+
+
+def test_controls_on_untouched_zero_qubits():
+    """A control on a qubit that is still |0> never fires (closed) / always fires (open): the sweep must not
+    be indexed by a qubit the lazy layout never materialises (`cx(2,1); cx(0,3)` on |0000>)."""
+    from qcmrf_b200.circuit import QuantumCircuit
+    c = QuantumCircuit(4)
+    c.cx(2, 1); c.cx(0, 3)
+    prog, psi = _gate_by_gate(c)
+    for mode, lazy, bm in CONFIGS:
+        lg, _, _ = _logical(prog, mode, lazy, bm)
+        assert np.abs(lg - psi).max() < 1e-14
+    c = QuantumCircuit(4)
+    c.h(1)
+    c.mcx([0, 1], 2, ctrl_state='10')          # qubit 0 open (always fires), qubit 1 closed
+    c.mcx([3, 1], 0)                           # qubit 3 still |0>: identity
+    c.cx(2, 3)
+    prog, psi = _gate_by_gate(c)
+    pruned = fusion.prune_zero_controls(prog.gates, 4)
+    assert [g.qubits for g in pruned] == [(1,), (1, 2), (2, 3)]
+    for mode, lazy, bm in CONFIGS:
+        lg, _, _ = _logical(prog, mode, lazy, bm)
+        assert np.abs(lg - psi).max() < 1e-14
+
+
+def test_release_keeps_sweeps_whose_index_qubits_change_later():
+    """width='release' may drop a sweep only if its index qubits keep their value to the end
+    (`h(0); cx(0,1); h(0)`: the cx must stay in the core program)."""
+    from qcmrf_b200.circuit import QuantumCircuit
+    c = QuantumCircuit(2)
+    c.h(0); c.cx(0, 1); c.h(0)
+    fc = fusion.fuse(ir.lower(c), 'clique')
+    core, virtual = fusion.split_releasable(fc, keep_below=1)
+    assert not virtual and len(core.ops) == len(fc.ops)
+    c = QuantumCircuit(2)
+    c.h(0); c.cx(0, 1)
+    core, virtual = fusion.split_releasable(fusion.fuse(ir.lower(c), 'clique'), keep_below=1)
+    assert len(virtual) == 1 and virtual[0].target == 1
+
+
+def test_gates_after_a_measurement_are_rejected():
+    from qcmrf_b200.circuit import QuantumCircuit
+    c = QuantumCircuit(2, 2)
+    c.measure(0, 0); c.x(0)
+    with pytest.raises(ValueError, match='follows a measurement'):
+        ir.lower(c)
+    c = QuantumCircuit(2, 2)
+    c.h(0); c.measure(0, 0); c.cx(0, 1)                  # measured qubit as a control
+    with pytest.raises(ValueError, match='follows a measurement'):
+        ir.lower(c)
+    c = QuantumCircuit(2, 2)
+    c.h(0); c.measure(0, 0); c.h(1); c.measure(1, 1)     # QCMRF's pattern: measured qubits left alone
+    assert ir.lower(c).measures == {0: 0, 1: 1}
+    with pytest.raises(ValueError, match='follows a measurement'):
+        transpile(_edit(c))
+
+
+def _edit(c):
+    c = c.copy()
+    c.x(0)
+    return c
+
+
+def test_positive_theta_is_an_error_on_both_paths():
+    """theta > 0 has no circuit angle (gamma = NaN, QCMRF.py:154): never a silently plausible pmf."""
+    q = QCMRF([[0]], [0.5, -0.3])
+    with pytest.raises(ValueError, match='theta must be <= 0'):
+        fusion.fuse(ir.lower(q), 'clique')
+    with pytest.raises(ValueError, match='theta must be <= 0'):
+        fusion.fuse(ir.lower(q), 'off')
+    q = QCMRF([[0]], [0.5, -0.3])
+    q.data                                               # materialise the instruction list: generic walk
+    with pytest.raises(ValueError, match='theta must be <= 0'):
+        ir.lower(q)
