@@ -433,6 +433,92 @@ static int launch_low_mh(qcm_handle h, int MH, int n_in, BlockPlan &bp) {
     return fail(h, QCM_ERR_INVALID, "rotated expansion: %d loop levels out of range", MH);
 }
 
+// ---- low-order-target pass ------------------------------------------------------------
+int lowq_enabled() {
+    // QCM_LOWQ=0: serve low targets with k_block (A/B measurement knob)
+    static int v = [] {
+        const char *e = getenv("QCM_LOWQ");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return v;
+}
+
+template <typename R, int V, int UB, int MH>
+static int launch_lowq_t(qcm_handle h, const LowqArgs &a, size_t smem) {
+    auto kern = k_lowq<R, V, UB, MH>;
+    if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int LB = (V == 2 ? 1 : 0) + 5 + UB;
+    const uint64_t nrows = 1ull << (a.n - LB - MH);
+    const uint64_t grid = std::min<uint64_t>(std::max<uint64_t>(1, (nrows + kThreads / 32 - 1) / (kThreads / 32)), 0x7fffffffull);
+    kern<<<(unsigned)grid, kThreads, smem, h->stream>>>(a);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    char nm[64];
+    snprintf(nm, sizeof nm, "k_lowq<%s,%d,UB=%d,MH=%d>", sizeof(R) == 4 ? "float" : "double", V, UB, MH);
+    h->cur_kernel = nm;
+    return QCM_OK;
+}
+
+// Serves an in-place block whose lowest target sits inside a warp's coalesced access.  Returns 1 when the
+// pass was launched, 0 when k_block should take it, < 0 on error.
+static int try_lowq(qcm_handle h, const BlockPlan &bp) {
+    const BlockArgs &b = bp.args;
+    const int M = bp.M, n = b.n_out;
+    if (!lowq_enabled() || b.n_in != b.n_out || M > QCM_MAX_BLOCK || b.tq[0] >= 6) return 0;
+    const int VB = h->prec == QCM_C64 ? 1 : 0;
+    int MH = -1;
+    for (int mh = 0; mh <= kLowqMaxHigh && MH < 0; ++mh) {
+        const int LB = VB + 5 + (3 - mh);
+        int high = 0;
+        for (int j = 0; j < M; ++j) high += b.tq[j] >= LB;
+        if (high == mh && n >= LB + mh) MH = mh;
+    }
+    if (MH < 0) return 0;
+    const int UB = 3 - MH, LB = VB + 5 + UB;
+    LowqArgs a{};
+    a.state = b.state;
+    a.tables = b.tables;
+    a.n = n;
+    a.n_members = b.n_members;
+    a.rank_bits = b.rank_bits;
+    for (int k = 0; k < MH; ++k) a.th[k] = b.tq[M - MH + k];
+    for (int g = 0; g < b.n_members; ++g) {
+        const MemberDesc &s = b.mem[g];
+        LowqMember &m = a.mem[g];
+        if (s.pos < 0) m.pos = -1;
+        else {
+            const int t = b.tq[s.pos];
+            m.pos = (int8_t)(t < LB ? t : LB + (s.pos - (M - MH)));
+        }
+        m.n_ctrl = s.n_ctrl;
+        m.tab_off = s.tab_off;
+        m.src_off = s.src_off;
+        m.rany = 0;
+        for (int j = 0; j < s.n_ctrl; ++j) {
+            const int c = s.ctrl[j];
+            m.ctrl[j] = (int8_t)c;
+            int rb = -1;                                   // register-index bit this qubit is, if any
+            if (VB && c == 0) rb = 0;
+            else if (c >= VB + 5 && c < LB) rb = c - 5;
+            if (rb >= 0) {
+                m.rbit[rb] = (uint16_t)(1u << j);
+                m.rany |= m.rbit[rb];
+            }
+        }
+    }
+    int rc;
+    if (h->prec == QCM_C64) {
+        rc = MH == 0 ? launch_lowq_t<float, 2, 3, 0>(h, a, bp.smem)
+           : MH == 1 ? launch_lowq_t<float, 2, 2, 1>(h, a, bp.smem)
+                     : launch_lowq_t<float, 2, 1, 2>(h, a, bp.smem);
+    } else {
+        rc = MH == 0 ? launch_lowq_t<double, 1, 3, 0>(h, a, bp.smem)
+           : MH == 1 ? launch_lowq_t<double, 1, 2, 1>(h, a, bp.smem)
+                     : launch_lowq_t<double, 1, 1, 2>(h, a, bp.smem);
+    }
+    return rc ? rc : 1;
+}
+
 int launch_block_plan(qcm_handle h, BlockPlan &bp) {
     const BlockArgs &a = bp.args;
     const int M = bp.M, n_in = a.n_in, n_out = a.n_out;
@@ -503,7 +589,11 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
     } else {
         const bool lazy = n_in != n_out;
         h->cur_kernel = h->prec == QCM_C64 ? "k_block<float>" : "k_block<double>";
-        if (h->prec == QCM_C64) {
+        rc = try_lowq(h, bp);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            rc = QCM_OK;
+        } else if (h->prec == QCM_C64) {
             const bool vec2 = a.tq[0] >= 1 && (n_out - M) >= 1;
             if (vec2) rc = lazy ? launch_block_m<float, 2, true>(h, M, a, bp.smem) : launch_block_m<float, 2, false>(h, M, a, bp.smem);
             else rc = lazy ? launch_block_m<float, 1, true>(h, M, a, bp.smem) : launch_block_m<float, 1, false>(h, M, a, bp.smem);

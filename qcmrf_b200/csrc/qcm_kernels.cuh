@@ -261,6 +261,186 @@ __global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ Bloc
 }
 
 // ----------------------------------------------------------------------------------
+// Low-order-target pass (north star (ii)).
+//
+// k_block pairs amplitudes 2^t apart with one 128-bit access per lane: for a target below the
+// width of a warp's access (t = 0: 64-bit loads; t = 1..4: 16-byte pieces at a 2^(t+4)-byte stride)
+// the pairs of a butterfly sit INSIDE the vectors and lanes of one coalesced warp access.  Here a
+// warp owns a contiguous row of 2^LB amplitudes (LB = log2(V * 32 * 2^UB): 512 complex64 = 4 KiB)
+// and every lane holds 2^UB vectors of it, each load/store a full 512-byte warp access:
+//     row bit 0          (V == 2)  the two amplitudes of a lane's 128-bit vector   -> in registers
+//     row bits VB..VB+4            the lane                                        -> __shfl_xor_sync
+//     row bits VB+5..LB-1          the lane's 2^UB vectors                         -> in registers
+// so a gate on ANY of the LB low qubits is a butterfly on data the warp already holds: no strided
+// access, no shared-memory staging of amplitudes (shared memory only holds the coefficient tables).
+// Up to two further targets above the row (MH of them; UB shrinks to keep 32 data registers) ride
+// along as a register dimension, their row copies 2^th amplitudes apart, so a blocked pass that mixes
+// low and high targets stays one sweep.  Members are applied in order, as in k_block.
+// ----------------------------------------------------------------------------------
+constexpr int kLowqMaxHigh = 2;
+constexpr int kLowqRegBits = 4;             // register-index bits that can feed a table index (v + u bits)
+
+struct LowqMember {
+    int8_t pos;                     // target: row bit 0..LB-1; LB + k: high target k; -1: diagonal member
+    int8_t n_ctrl;
+    int8_t ctrl[QCM_MAX_CTRL];      // qubit feeding table-index bit j (any qubit but the pass's targets)
+    uint16_t rbit[kLowqRegBits];    // table-index bit fed by register-index bit b (v, then the u bits), else 0
+    uint16_t rany;                  // OR of rbit[]: 0 => one table entry serves all of a thread's registers
+    int32_t tab_off, src_off;       // reals: shared-memory / global offsets of the member's table
+};
+
+struct LowqArgs {
+    void *state;
+    const void *tables;             // device, state's real type
+    int32_t n;                      // materialised qubits (the pass is in place: n_in == n_out)
+    int32_t n_members;
+    int32_t th[kLowqMaxHigh];       // high targets, ascending (>= LB)
+    uint64_t rank_bits;
+    LowqMember mem[QCM_MAX_MEMBERS];
+};
+
+template <typename R, int V, int UB, int MH>
+__global__ void __launch_bounds__(kThreads) k_lowq(const __grid_constant__ LowqArgs a) {
+    constexpr int VB = V == 2 ? 1 : 0;
+    constexpr int LB = VB + 5 + UB;             // row bits
+    constexpr int NU = 1 << UB, NH = 1 << MH;
+    constexpr int NR = V * NU * NH;             // amplitudes per thread; register index r = v | u << VB | h << (VB + UB)
+    constexpr int kWarps = kThreads / 32;
+    using IO = VecIO<R, V>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tab = reinterpret_cast<R *>(smem_raw);
+    for (int g = 0; g < a.n_members; ++g) {
+        const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
+        R *dst = tab + a.mem[g].tab_off;
+        const int cnt = (a.mem[g].pos < 0 ? 2 : 8) << a.mem[g].n_ctrl;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t nrows = 1ull << (a.n - LB - MH);
+    // one row per warp, a CTA's 8 rows adjacent, CTAs in launch (= address) order
+    for (uint64_t row = (uint64_t)blockIdx.x * kWarps + warp; row < nrows; row += (uint64_t)gridDim.x * kWarps) {
+        uint64_t base = row << LB;
+#pragma unroll
+        for (int k = 0; k < MH; ++k) base = insert_zero(base, a.th[k]);
+        R xr[NR], xi[NR];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            uint64_t hb = base;
+#pragma unroll
+            for (int k = 0; k < MH; ++k)
+                if ((h >> k) & 1) hb += 1ull << a.th[k];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                R tr[V], ti[V];
+                IO::load(a.state, hb + ((uint64_t)u * 32 + lane) * V, tr, ti);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    xr[v | (u << VB) | (h << (VB + UB))] = tr[v];
+                    xi[v | (u << VB) | (h << (VB + UB))] = ti[v];
+                }
+            }
+        }
+        // the part of the global index that is the same for all of this thread's registers
+        const uint64_t gi = (base + (uint64_t)lane * V) | a.rank_bits;
+        for (int g = 0; g < a.n_members; ++g) {
+            const LowqMember &m = a.mem[g];
+            const R *mt = tab + m.tab_off;
+            uint32_t idx0 = 0;
+            for (int j = 0; j < m.n_ctrl; ++j) idx0 |= (uint32_t)((gi >> m.ctrl[j]) & 1ull) << j;
+            auto ridx = [&](int r) -> uint32_t {           // r is a compile-time constant after unrolling
+                uint32_t i = idx0;
+#pragma unroll
+                for (int b = 0; b < VB + UB; ++b)
+                    if ((r >> b) & 1) i |= m.rbit[b];
+                return i;
+            };
+            const int pos = m.pos;
+            // UNI: no register-index bit feeds the table index -> one entry serves all of the thread's registers
+            auto apply = [&](auto UNIc) {
+                constexpr bool UNI = decltype(UNIc)::value;
+                if (pos < 0) {                              // diagonal member
+                    R c0 = R(0), s0 = R(0);
+                    if constexpr (UNI) { c0 = mt[2 * idx0]; s0 = mt[2 * idx0 + 1]; }
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        R c = c0, sn = s0;
+                        if constexpr (!UNI) { const uint32_t idx = ridx(r); c = mt[2 * idx]; sn = mt[2 * idx + 1]; }
+                        const R x = xr[r], y = xi[r];
+                        xr[r] = c * x - sn * y;
+                        xi[r] = c * y + sn * x;
+                    }
+                    return;
+                }
+                R q[8];
+                if constexpr (UNI) load_m8<R>(mt + 8 * idx0, q);
+                if (pos >= VB && pos < VB + 5) {
+                    // ---- target = a lane bit: the partner amplitude lives in lane ^ (1 << j)
+                    const int j = pos - VB;
+                    const bool up = (lane >> j) & 1;
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        if constexpr (!UNI) load_m8<R>(mt + 8 * ridx(r), q);
+                        // own coefficient / partner coefficient: row `up` of the 2x2
+                        const R ar = up ? q[6] : q[0], ai = up ? q[7] : q[1];
+                        const R br = up ? q[4] : q[2], bi = up ? q[5] : q[3];
+                        const R pr = __shfl_xor_sync(0xffffffffu, xr[r], 1 << j);
+                        const R pi = __shfl_xor_sync(0xffffffffu, xi[r], 1 << j);
+                        const R x = xr[r], y = xi[r];
+                        xr[r] = ar * x - ai * y + br * pr - bi * pi;
+                        xi[r] = ar * y + ai * x + br * pi + bi * pr;
+                    }
+                    return;
+                }
+                // ---- target = a register bit (vector slot, one of the lane's vectors, or a high target)
+                const int rb = pos < VB ? 0 : (pos < LB ? pos - 5 : VB + UB + (pos - LB));
+                auto in_regs = [&](auto RBc) {
+                    constexpr int RB = decltype(RBc)::value;
+                    if constexpr (RB < VB + UB + MH) {
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            if (r & (1 << RB)) continue;
+                            const int r1 = r | (1 << RB);
+                            if constexpr (!UNI) load_m8<R>(mt + 8 * ridx(r), q);
+                            const R x0 = xr[r], y0 = xi[r], x1 = xr[r1], y1 = xi[r1];
+                            xr[r] = q[0] * x0 - q[1] * y0 + q[2] * x1 - q[3] * y1;
+                            xi[r] = q[0] * y0 + q[1] * x0 + q[2] * y1 + q[3] * x1;
+                            xr[r1] = q[4] * x0 - q[5] * y0 + q[6] * x1 - q[7] * y1;
+                            xi[r1] = q[4] * y0 + q[5] * x0 + q[6] * y1 + q[7] * x1;
+                        }
+                    }
+                };
+                switch (rb) {
+                    case 0: in_regs(std::integral_constant<int, 0>{}); break;
+                    case 1: in_regs(std::integral_constant<int, 1>{}); break;
+                    case 2: in_regs(std::integral_constant<int, 2>{}); break;
+                    default: in_regs(std::integral_constant<int, 3>{}); break;
+                }
+            };
+            if (m.rany == 0) apply(std::true_type{});
+            else apply(std::false_type{});
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            uint64_t hb = base;
+#pragma unroll
+            for (int k = 0; k < MH; ++k)
+                if ((h >> k) & 1) hb += 1ull << a.th[k];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                R tr[V], ti[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    tr[v] = xr[v | (u << VB) | (h << (VB + UB))];
+                    ti[v] = xi[v | (u << VB) | (h << (VB + UB))];
+                }
+                IO::store(a.state, hb + ((uint64_t)u * 32 + lane) * V, tr, ti);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
 // Fused qubit-swap + gate pass over NVLink peer memory (sharded states).
 //
 // A qubit-swap all-to-all brings the s global qubits on-GPU as the s highest local qubits, and the

@@ -241,6 +241,66 @@ def test_random_engine_programs_vs_op_semantics(precision, N):
 
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('N', [9, 12, 17])
+def test_low_order_target_pass(precision, N):
+    """North star (ii): gates whose target lies inside a warp's coalesced access -- the vector slot (qubit 0),
+    the lane bits (warp shuffles) and the lane's further vectors (registers) -- run in k_lowq; single gates on
+    every low target with index qubits all over the place, blocked passes mixing low and high targets, and
+    diagonal members, against the numpy statement of the op semantics."""
+    rng = np.random.RandomState(77 + N)
+    LB = 9 if precision == 'single' else 8
+
+    def rand_u(m):
+        q, _ = np.linalg.qr(rng.randn(1 << m, 2, 2) + 1j * rng.randn(1 << m, 2, 2))
+        return q
+    tol = 1e-12 if precision == 'double' else 3e-6
+    with _native.Handle(N, precision) as h:
+        def check(e, expect_lowq):
+            ops, tabs = e.finish()
+            pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, N
+            want, _ = em.run_plan(pl)
+            h.run_program(ops, tabs)
+            got = h.get_amplitudes().astype(np.complex128)
+            assert np.abs(got - want).max() < tol
+            names = h.op_kernels()
+            if expect_lowq is not None:
+                assert names[-1].startswith('k_lowq') == expect_lowq, names
+
+        def init(e):
+            qv = rng.randn(N, 4)
+            qv /= np.sqrt((qv ** 2).sum(axis=1, keepdims=True))
+            e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=N, table_off=e.table(qv))
+        # (1) one gate per low target, 0..3 index qubits drawn from ALL other qubits (lane, vector, high)
+        for t in range(min(N, LB + 1)):
+            for m in (0, 1, 3, min(5, N - 1)):
+                e = fusion._Emitter()
+                init(e)
+                others = [q for q in range(N) if q != t]
+                ctrl = [int(c) for c in rng.permutation(others)[:m]]
+                e.op(fusion.QCM_OP_MUX1Q, target=t, ctrl=ctrl, n_in=N, n_out=N, table_off=e.table(fusion._mux_table_f64(rand_u(len(ctrl)))))
+                check(e, t < 6 and N >= LB)
+        # (2) blocked passes: all-low, one high, two high targets; repeated targets; diagonal members
+        if N >= 12:
+            for tq in ([0, 1, 2, 3, 4], [0, 5, 8], [1, 3, N - 1], [0, 2, N - 3, N - 1], [2, 6, 7, N - 2], [4, 9, 10]):
+                tq = sorted(set(t for t in tq if t < N))
+                others = [q for q in range(N) if q not in tq]
+                e = fusion._Emitter()
+                init(e)
+                n_mem = 6
+                e.op(fusion.QCM_OP_BLOCK, target=len(tq), ctrl=tq, n_in=N, n_out=N, n_ctrl=n_mem)
+                for g in range(n_mem):
+                    m = int(rng.randint(0, 4))
+                    ctrl = [int(c) for c in rng.permutation(others)[:m]]
+                    if g == 2:
+                        d = np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << m))
+                        e.op(fusion.QCM_OP_DIAG, ctrl=ctrl, n_in=N, n_out=N, table_off=e.table(fusion._diag_table_f64(d)))
+                    else:
+                        e.op(fusion.QCM_OP_MUX1Q, target=tq[g % len(tq)], ctrl=ctrl, n_in=N, n_out=N,
+                             table_off=e.table(fusion._mux_table_f64(rand_u(m))))
+                check(e, None)
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
 def test_lazy_materialisation_ops(precision):
     """Ops that materialise qubits: zero-input targets are never read (the buffer holds NaN
     there), EXTEND zero-fills, get_amplitudes reports implicit zeros."""
