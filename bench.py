@@ -582,28 +582,25 @@ def fixtures_bench(args, world, rank, device, barrier, torch, dist):
 
 
 def sweep_bench(args, world, rank, device, barrier, torch, dist):
-    """BASELINE config 2: 20-variable chain MRF, complex128, 256-point beta-sweep (beta_j = (j+1)/128),
-    the points partitioned round-robin over the GPUs with no communication.  At Aer width the circuit
-    has 40 qubits (16 TiB); it is run measure-and-release (width='release'): the 20 variable qubits are
-    stored (16 MiB per point), every clique ancilla is drawn from its sweep's coefficients and projected
-    for the exact post-selected pmf.  A step = the whole sweep: 256 circuits, each with its 2^20 pmf,
-    delta and 10000 full-width (40-bit) shots."""
+    """BASELINE config 3: 20-variable chain MRF, complex128, 256-point beta-sweep (beta_j = (j+1)/128, QCMRF.py:21,154),
+    the points partitioned round-robin over the GPUs with no communication.  At Aer width the circuit has 40 qubits
+    (16 TiB); it is run measure-and-release (width='release'): the 20 variable qubits are stored (16 MiB per point),
+    every clique ancilla is drawn from its sweep's coefficients and projected for the exact post-selected pmf.
+    All points of a rank go through ONE batched handle: every kernel is launched once for the whole sweep
+    (qcm_create_batched).  A step = the whole sweep: 256 circuits, each with delta, its 2^20 pmf (left on the GPU
+    unless asked for) and 10000 full-width (40-bit) shots."""
     from qcmrf_b200 import QCMRF, B200Simulator, workloads
     points = 256
     cliques, N = workloads.named('chain20')
+    n = 20
     theta = workloads.theta_for(cliques)
     betas = [(j + 1) / 128.0 for j in range(points)]
     mine = list(range(rank, points, world))
     sim = B200Simulator(precision='double', width='release', device=device, seed=1984, small_batch=False)
-    preps = [sim.prepare(QCMRF(cliques, theta, beta=betas[j])) for j in mine]
-
-    def sweep():
-        out = None
-        for j, pr in zip(mine, preps):
-            out = sim.execute(pr, SHOTS, seed=1984, stream=j)
-        return out
+    sw = sim.prepare_sweep([QCMRF(cliques, theta, beta=betas[j]) for j in mine])
+    streams = np.asarray(mine, dtype=np.uint64)
     for _ in range(args.warmup):
-        sweep()
+        sim.execute_sweep(sw, SHOTS, seed=1984, streams=streams)
     l0 = sim.kernel_launches()
     clocks = ClockSampler(device)
     if rank == 0:
@@ -612,18 +609,18 @@ def sweep_bench(args, world, rank, device, barrier, torch, dist):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        keys, probs, kept = sweep()
+        keys, probs, kept = sim.execute_sweep(sw, SHOTS, seed=1984, streams=streams)
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = sim.kernel_launches() - l0
-    prof = sim.op_profile()
-    e2e = []
+    prof = sim.sweep_profile
+    e2e, e2e_keys = [], []
     for i in range(args.steps):
         barrier()
         t1 = time.perf_counter()
-        res = sim.run([QCMRF(cliques, theta, beta=betas[j]) for j in mine], shots=SHOTS, seed=1984 + i,
-                      stream_ids=mine).result()
+        res = sim.run([QCMRF(cliques, theta, beta=betas[j]) for j in mine], shots=SHOTS, seed=1984 + i, stream_ids=mine).result()
+        deltas = [res.success_probability(k) for k in range(len(mine))]
         counts = res.get_counts()
         torch.cuda.synchronize()
         e2e.append((time.perf_counter() - t1) * 1e3)
@@ -633,26 +630,54 @@ def sweep_bench(args, world, rank, device, barrier, torch, dist):
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = (float(x) for x in red.cpu())
     clk = clocks.stop() if rank == 0 else None
+    # parity of this rank's first / middle / last point against brute-force enumeration (2^20 states)
+    chk = {}
+    for k in sorted({0, len(mine) // 2, len(mine) - 1}):
+        p, d = res.postselected_probabilities(k)
+        c = parity_check(cliques, theta, p, d, counts[k], beta=betas[mine[k]], tol=1e-10, rel_tol=1e-9)
+        chk['beta=%g' % betas[mine[k]]] = {kk: c[kk] for kk in ('max_abs_p_error_vs_brute_force', 'rel_p_err', 'delta_rel_err', 'tv',
+                                                               'tv_bound', 'sampled_success_fraction', 'exact_delta', 'parity_ok')}
+    ok = all(v['parity_ok'] for v in chk.values())
+    oks = [None] * world
+    if world > 1:
+        dist.all_gather_object(oks, ok)
+    else:
+        oks = [ok]
     if rank == 0:
         peak, peak_src = load_peaks()
-        top = max(prof, key=lambda r: r[1])
         ms_step = dev_ms / args.steps
+        launches_all = prof['program'] + prof['projection']
+        top = max(launches_all, key=lambda r: r[1][1])
+        top_name, (_kind, top_ms, top_rd, top_wr) = top
+        amp = 16 << n
+        B = len(mine)
+        algo = (sum(r[1][2] + r[1][3] for r in launches_all)      # init write + the projection passes
+                + B * amp                                          # sampler: one read of every state for the sum tree
+                + B * amp + B * (8 << n))                          # post-selection: read the state, write the pmf
         line = {'metric': METRIC, 'value': points / (ms_step * 1e-3), 'unit': 'circuits/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
                 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': 'chain20: 20-variable chain MRF (k=19, N=40 qubits at Aer width), complex128, '
-                                       '256-point beta-sweep, measure-and-release width (20 stored qubits), %d shots + exact '
-                                       'pmf per point' % SHOTS, 'points': points, 'stored_qubits': m['n_phys'],
-                           'released_qubits': m['released_qubits'], 'shots': SHOTS,
-                           'l2': 'a point is 16 MiB: L2-resident by construction, no flush (the sweep is launch/host bound)'},
+                                       '256-point beta-sweep, measure-and-release width (20 stored qubits), %d shots + delta + exact '
+                                       'pmf (device-resident) per point; one batched handle per GPU' % SHOTS, 'points': points,
+                           'points_per_gpu': B, 'stored_qubits': m['n_phys'], 'released_qubits': m['released_qubits'], 'shots': SHOTS,
+                           'l2': 'the %d states of a rank are %.1f GiB in one allocation, swept by every kernel: far beyond the 126 MB L2'
+                                 % (B, B * amp / 2.0 ** 30)},
                 'clocks': clk,
                 'e2e': {'value': points / (e2e_ms * 1e-3), 'unit': 'circuits/s', 'ms_per_step': e2e_ms,
-                        'h2d_bytes_per_step': int(m['h2d_bytes']) * len(mine), 'd2h_bytes_per_step': int(m['d2h_bytes']) * len(mine)},
+                        'h2d_bytes_per_step': int(m['h2d_bytes']) * B, 'd2h_bytes_per_step': int(m['d2h_bytes']) * B,
+                        'what': 'B200Simulator.run(list of 256 QCMRF objects) -> counts dicts (40-bit keys) + delta of every point; '
+                                'pmfs stay on the GPU until asked for'},
                 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'achieved': (top[2] + top[3]) / (top[1] * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
-                             'frac': (top[2] + top[3]) / (top[1] * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
-                             'kernel': 'k_diag projection pass over a 16 MiB state (L2-resident): %.4f ms' % top[1]},
-                'check': {'delta_last_point': float(kept), 'p_sum': float(np.sum(probs) / kept), 'shots': int(sum(counts[-1].values()))}}
+                'roofline': {'bound': 'hbm', 'achieved': (top_rd + top_wr) / (top_ms * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                             'frac': (top_rd + top_wr) / (top_ms * 1e-3) / 1e9 / peak, 'traffic': None, 'peak_source': peak_src,
+                             'kernel': '%s over %d states at once: reads %d B, writes %d B in %.3f ms' % (top_name or 'op', B, top_rd, top_wr, top_ms)},
+                'sweep': {'launches_per_sweep': int(launches) // max(args.steps, 1), 'algorithmic_bytes_per_sweep': int(algo),
+                          'hbm_gbs_whole_sweep': algo / (ms_step * 1e-3) / 1e9, 'frac_of_peak_whole_sweep': algo / (ms_step * 1e-3) / 1e9 / peak,
+                          'passes': [{'kernel': nm, 'ms': r[1], 'gbs': (r[2] + r[3]) / max(r[1], 1e-9) / 1e6} for nm, r in launches_all],
+                          'sample_ms': prof['sample_ms'], 'postselect_ms': prof['postselect_ms']},
+                'check': dict({'points_checked_vs_brute_force': chk, 'all_ranks_ok': bool(all(oks)),
+                               'shots': int(sum(counts[-1].values())), 'delta_first_last': [deltas[0], deltas[-1]]})}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

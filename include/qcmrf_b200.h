@@ -246,6 +246,37 @@ int qcm_run_batch_small(int device, int precision, int n_circuits,
                         uint64_t *keys_out, double *probs_out, double *kept_out,
                         double *device_ms_out);
 
+/* -- batched sweeps ----------------------------------------------------------------- */
+/* A theta / beta sweep over ONE graph (QCMRF's `beta`, /root/reference/QCMRF.py:21,154; BASELINE config 3) is B circuits
+ * with the same program structure and different coefficient tables.  A batched handle holds the B states of
+ * 2^n_local amplitudes in one allocation and runs every kernel of a program ONCE, with the sweep point as the
+ * second grid dimension -- O(10) launches for the whole sweep instead of O(10) per point:
+ *   qcm_run_program    : `tables` holds B consecutive table sets of n_tables doubles each (point-major); the ops
+ *                        (and every table_off) are shared.  Engine-internal output rotation and the sampling
+ *                        checkpoint are not used on batched handles.
+ *   qcm_postselect     : kept_out receives B doubles, probs_out (optional) B consecutive blocks of 2^n_out_bits.
+ *   qcm_postselect_resident : as qcm_postselect, but the B probability blocks STAY in device memory owned by the
+ *                        handle (valid until its next post-selection); qcm_fetch_probs copies (part of) one
+ *                        point's block to the host on demand.  Also serves plain handles (B = 1).
+ *   qcm_sample_batched / qcm_sample_released_batched : as qcm_sample / qcm_sample_released with one Philox stream
+ *                        id per point (stream_ids[B]); keys_out is [B][shots]; released-qubit tables p1 are B
+ *                        consecutive sets of n_p1 doubles.
+ *   qcm_batch_select   : the point that qcm_get_amplitudes / qcm_set_amplitudes address (default 0).
+ * A plain handle is a batched handle with B = 1.                                                       */
+int qcm_create_batched(qcm_handle *out, int device, int n_local, int precision, int batch,
+                       void *ext_state, void *ext_stream);
+int qcm_batch_size(qcm_handle h, int *batch_out);
+int qcm_batch_select(qcm_handle h, int point);
+int qcm_postselect_resident(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *kept_out);
+int qcm_fetch_probs(qcm_handle h, int point, uint64_t first, uint64_t count, double *host_out);
+int qcm_sample_batched(qcm_handle h, uint64_t shots, uint64_t seed, const uint64_t *stream_ids,
+                       const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out);
+int qcm_sample_released_batched(qcm_handle h, uint64_t shots, uint64_t seed, const uint64_t *stream_ids,
+                                int n_released, const int32_t *n_ctrl, const int32_t *ctrl, int max_ctrl,
+                                const double *p1, const int64_t *p1_off, int64_t n_p1,
+                                const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits,
+                                uint64_t *keys_out);
+
 /* -- multi-GPU plumbing ------------------------------------------------------------ */
 /* Packs/unpacks nothing: the qubit-swap all-to-all exchanges contiguous slabs of the
  * top `g` local qubits, which the caller moves with NCCL (torch.distributed).  These

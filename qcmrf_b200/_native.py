@@ -40,7 +40,8 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_get_active', 'qcm_get_timing', 'qcm_get_op_profile', 'qcm_postselect_device',
            'qcm_sample_sharded_device', 'qcm_run_gather_block', 'qcm_enable_peer_access',
            'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close', 'qcm_op_kernel_name',
-           'qcm_sample_released']
+           'qcm_sample_released', 'qcm_create_batched', 'qcm_batch_size', 'qcm_batch_select',
+           'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched']
 
 
 def lib():
@@ -86,6 +87,13 @@ def lib():
     L.qcm_op_kernel_name.argtypes = [vp, i32]
     L.qcm_sample_released.argtypes = [vp, u64, u64, u64, i32, vp, vp, i32, vp, vp, ctypes.c_int64, vp, vp, i32, vp]
     L.qcm_op_kernel_name.restype = ctypes.c_char_p
+    L.qcm_create_batched.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, vp, vp]
+    L.qcm_batch_size.argtypes = [vp, ctypes.POINTER(i32)]
+    L.qcm_batch_select.argtypes = [vp, i32]
+    L.qcm_postselect_resident.argtypes = [vp, u64, u64, i32, vp]
+    L.qcm_fetch_probs.argtypes = [vp, i32, u64, u64, vp]
+    L.qcm_sample_batched.argtypes = [vp, u64, u64, vp, vp, i32, vp]
+    L.qcm_sample_released_batched.argtypes = [vp, u64, u64, vp, i32, vp, vp, i32, vp, vp, ctypes.c_int64, vp, vp, i32, vp]
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
     assert OP_DTYPE.itemsize == 72, OP_DTYPE.itemsize
@@ -136,16 +144,19 @@ def _ptr(a):
 
 
 class Handle:
-    """One statevector on one GPU (see qcm_create)."""
+    """One statevector on one GPU (see qcm_create) -- or, with batch > 1, the `batch` states of a sweep in one
+    allocation, every kernel of a program launched once for all of them (qcm_create_batched)."""
 
-    def __init__(self, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None):
+    def __init__(self, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None, batch=1):
         self._h = ctypes.c_void_p()
+        self.batch = int(batch)
+        self.generation = 0                      # bumped by every post-selection: lazily fetched pmfs check it
         self.n_local = int(n_local)
         self.prec = QCM_C64 if precision in ('single', 'c64', 32) else QCM_C128
         self.cdtype = np.complex64 if self.prec == QCM_C64 else np.complex128
         L = lib()
-        rc = L.qcm_create(ctypes.byref(self._h), int(device), self.n_local, self.prec,
-                          ctypes.c_void_p(ext_state_ptr), ctypes.c_void_p(ext_stream))
+        rc = L.qcm_create_batched(ctypes.byref(self._h), int(device), self.n_local, self.prec, self.batch,
+                                  ctypes.c_void_p(ext_state_ptr), ctypes.c_void_p(ext_stream))
         if rc:
             self._h = ctypes.c_void_p()
             raise NativeError(rc, (L.qcm_last_error(None) or b'').decode())
@@ -175,16 +186,64 @@ class Handle:
         self._check(lib().qcm_set_shard(self._h, int(n_global), int(rank)))
 
     def run_program(self, ops, tables):
+        """tables: the program's coefficient tables; a batched handle takes shape (batch, n_tables), one row per point."""
         ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
         tables = np.ascontiguousarray(tables, dtype=np.float64)
-        self._check(lib().qcm_run_program(self._h, _ptr(ops), len(ops), _ptr(tables), tables.size))
+        if self.batch > 1 and (tables.ndim != 2 or tables.shape[0] != self.batch):
+            raise ValueError('batched handle: tables must have shape (batch, n_tables)')
+        self._check(lib().qcm_run_program(self._h, _ptr(ops), len(ops), _ptr(tables), tables.size // self.batch))
 
     def postselect(self, mask, value, n_out_bits, want_probs=True):
+        """(probs, kept); a batched handle returns arrays of shape (batch, 2^n_out_bits) and (batch,)."""
+        self.generation += 1
+        if self.batch > 1:
+            probs = np.empty((self.batch, 1 << n_out_bits), dtype=np.float64) if want_probs else None
+            kept = np.empty(self.batch, dtype=np.float64)
+            self._check(lib().qcm_postselect(self._h, int(mask), int(value), int(n_out_bits), _ptr(probs), _ptr(kept)))
+            return probs, kept
         probs = np.empty(1 << n_out_bits, dtype=np.float64) if want_probs else None
         kept = ctypes.c_double()
         self._check(lib().qcm_postselect(self._h, int(mask), int(value), int(n_out_bits), _ptr(probs),
                                          ctypes.byref(kept)))
         return probs, kept.value
+
+    def postselect_resident(self, mask, value, n_out_bits):
+        """kept (array of `batch`); the probability blocks stay on the device until the next post-selection on this
+        handle (fetch_probs copies one out)."""
+        self.generation += 1
+        kept = np.empty(self.batch, dtype=np.float64)
+        self._check(lib().qcm_postselect_resident(self._h, int(mask), int(value), int(n_out_bits), _ptr(kept)))
+        return kept
+
+    def fetch_probs(self, point, n_out_bits, first=0, count=None):
+        if count is None:
+            count = (1 << n_out_bits) - first
+        out = np.empty(int(count), dtype=np.float64)
+        self._check(lib().qcm_fetch_probs(self._h, int(point), int(first), int(count), _ptr(out)))
+        return out
+
+    def batch_select(self, point):
+        self._check(lib().qcm_batch_select(self._h, int(point)))
+
+    def sample_batched(self, shots, seed, stream_ids, clbit_qubit=None):
+        keys = np.empty((self.batch, int(shots)), dtype=np.uint64)
+        sid = np.ascontiguousarray(stream_ids, dtype=np.uint64)
+        assert sid.size == self.batch
+        cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
+        self._check(lib().qcm_sample_batched(self._h, int(shots), int(seed), _ptr(sid), _ptr(cq),
+                                             0 if cq is None else len(cq), _ptr(keys)))
+        return keys
+
+    def sample_released_batched(self, shots, seed, stream_ids, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_clbits):
+        """p1: (batch, n_p1) released-qubit probability tables, one row per sweep point."""
+        keys = np.empty((self.batch, int(shots)), dtype=np.uint64)
+        sid = np.ascontiguousarray(stream_ids, dtype=np.uint64)
+        p1 = np.ascontiguousarray(p1, dtype=np.float64)
+        assert sid.size == self.batch and p1.shape[0] == self.batch
+        self._check(lib().qcm_sample_released_batched(self._h, int(shots), int(seed), _ptr(sid), len(n_ctrl), _ptr(n_ctrl),
+                                                      _ptr(ctrl), int(ctrl.shape[1]), _ptr(p1), _ptr(p1_off), int(p1.shape[1]),
+                                                      _ptr(vclbit), _ptr(clbit_pos), int(n_clbits), _ptr(keys)))
+        return keys
 
     def sample(self, shots, seed, stream_id=0, clbit_qubit=None):
         keys = np.empty(int(shots), dtype=np.uint64)

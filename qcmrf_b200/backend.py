@@ -48,6 +48,29 @@ class _Prepared:
     __slots__ = ('prog', 'fc', 'plan', 'clbit_map', 'n_vars', 'ps', 'name', 'virtual', 'proj', '_released_tabs')
 
 
+class _Sweep:
+    """Circuits with ONE program structure (a theta / beta sweep over one graph), stacked for a batched handle:
+    shared ops, per-point coefficient tables as rows."""
+    __slots__ = ('prs', 'ops', 'tables', 'proj_ops', 'proj_tables', 'released', 'p1', 'n_phys', 'ps', 'clbit_map', 'n_vars')
+
+
+class _ResidentProbs:
+    """A post-selected block that was left on the GPU (sweeps: 2^n doubles per point add up quickly); fetched on
+    first use, valid until the handle's next post-selection."""
+    __slots__ = ('handle', 'generation', 'point', 'n_bits', 'value')
+
+    def __init__(self, handle, point, n_bits):
+        self.handle, self.generation, self.point, self.n_bits, self.value = handle, handle.generation, point, n_bits, None
+
+    def get(self):
+        if self.value is None:
+            if self.handle.generation != self.generation or not self.handle._h:
+                raise RuntimeError('the post-selected vector of this sweep point is no longer resident on the GPU (a later run '
+                                   'reused the state); run the sweep with pmf=True to copy every vector to the host')
+            self.value = self.handle.fetch_probs(self.point, self.n_bits)
+        return self.value
+
+
 _host_lib = None
 
 
@@ -133,6 +156,8 @@ class Result:
         e = self._entries[self._idx(experiment)]
         if e['probs'] is None:
             raise ValueError('circuit has no known variable-register width: pass n= to exact() or run a QCMRF')
+        if isinstance(e['probs'], _ResidentProbs):
+            e['probs'] = e['probs'].get()                   # sweep: the vector stayed on the GPU until asked for
         kept = e['kept']
         p = e['probs'] / kept if kept > 0 else e['probs']
         return p, kept
@@ -181,7 +206,8 @@ class B200Simulator:
     the unseeded Aer run of the reference)."""
 
     def __init__(self, name='qasm_simulator', device=0, precision='double', fusion='blocked', block_max=4,
-                 seed=None, small_batch=True, small_fusion='clique', width='full', expand_max=8, plan_cache=True):
+                 seed=None, small_batch=True, small_fusion='clique', width='full', expand_max=8, plan_cache=True,
+                 sweep_batch=True, sweep_state_bytes=1 << 28, sweep_bytes=32 << 30):
         if fusion not in _FUSION_MODES:
             raise ValueError('fusion must be one of %r' % (_FUSION_MODES,))
         if width not in ('full', 'release'):
@@ -200,9 +226,16 @@ class B200Simulator:
         self.small_batch = small_batch
         self.small_fusion = small_fusion      # batched small circuits: fused programs are ~30x shorter to plan and ship
         self._handles = {}
+        self._launches_closed = 0
         self._last = None
         self._plan_cache = plancache.PlanCache() if plan_cache else None
         self.breakdown_ms = None               # host-side split of the last large-state run (bench.py)
+        # circuits of one structure in a run() list (a theta / beta sweep) whose states are at most
+        # sweep_state_bytes each go through ONE batched handle (every kernel launched once for all points),
+        # in chunks of at most sweep_bytes of state
+        self.sweep_batch = sweep_batch
+        self.sweep_state_bytes = int(sweep_state_bytes)
+        self.sweep_bytes = int(sweep_bytes)
 
     def name(self):
         return self._name
@@ -286,13 +319,15 @@ class B200Simulator:
                   table_off=em.table(fusion._diag_table_f64(tab)))
         pr.proj = em.finish()
 
-    def _handle(self, n_phys, precision):
-        key = (n_phys, precision)
+    def _handle(self, n_phys, precision, batch=1):
+        key = (n_phys, precision) if batch == 1 else (n_phys, precision, batch)
         h = self._handles.get(key)
         if h is None:
             for k in list(self._handles):              # one big state at a time
+                self._launches_closed += self._handles[k].timing()['kernel_launches']
                 self._handles.pop(k).close()
-            h = _native.Handle(n_phys, precision, self.device)
+            h = _native.Handle(n_phys, precision, self.device, batch=batch) if batch > 1 else \
+                _native.Handle(n_phys, precision, self.device)
             self._handles[key] = h
         return h
 
@@ -327,9 +362,12 @@ class B200Simulator:
         return probs, kept
 
     # -- public API ---------------------------------------------------------------------
-    def run(self, circuits, shots=1024, seed=None, precision=None, n_vars=None, stream_ids=None, **options):
+    def run(self, circuits, shots=1024, seed=None, precision=None, n_vars=None, stream_ids=None, pmf=None, **options):
         """stream_ids: Philox stream per circuit (default: its index in the list) -- a batch split over
-        several GPUs passes the global indices so that the counts do not depend on the partition."""
+        several GPUs passes the global indices so that the counts do not depend on the partition.
+        pmf: sweeps only (circuits of one structure run through one batched handle) -- True copies every point's
+        post-selected vector to the host, None (default) leaves them on the GPU until
+        Result.postselected_probabilities(i) asks for one, False computes only delta."""
         t0 = time.perf_counter()
         single = not isinstance(circuits, (list, tuple))
         circs = [circuits] if single else list(circuits)
@@ -343,6 +381,7 @@ class B200Simulator:
         entries = [None] * len(circs)
         sid = (lambda i: i) if stream_ids is None else (lambda i: int(stream_ids[i]))
         small_ids, small_prep = [], []
+        large = []
         for i, c in enumerate(circs):
             nq = int(c.n_qubits if isinstance(c, ir.Program) else c.num_qubits)
             if self.small_batch and nq <= small_max:
@@ -351,10 +390,34 @@ class B200Simulator:
             else:
                 tp = time.perf_counter()
                 pr = self.prepare(c, n_vars=n_vars)
-                tp = (time.perf_counter() - tp) * 1e3
-                entries[i] = self._run_large(c, pr, shots, seed, sid(i), precision)
-                entries[i]['meta']['host_ms']['prepare (lower, fuse, plan)'] = tp
-                self.breakdown_ms = entries[i]['meta']['host_ms']
+                large.append((i, pr, (time.perf_counter() - tp) * 1e3))
+        # circuits of one program structure (a theta / beta sweep) go through one batched handle
+        groups = {}
+        if self.sweep_batch and len(large) > 1:
+            for k, (i, pr, tp) in enumerate(large):
+                sig = self._sweep_signature(pr, precision)
+                if sig is not None:
+                    groups.setdefault(sig, []).append(k)
+        swept = set(k for ks in groups.values() if len(ks) >= 2 for k in ks)
+        for k, (i, pr, tp) in enumerate(large):
+            if k in swept:
+                continue
+            entries[i] = self._run_large(circs[i], pr, shots, seed, sid(i), precision)
+            entries[i]['meta']['host_ms']['prepare (lower, fuse, plan)'] = tp
+            self.breakdown_ms = entries[i]['meta']['host_ms']
+        # sweeps last: their post-selected vectors may stay on the GPU, which only holds while the state handle lives
+        for sig, ks in groups.items():
+            if len(ks) < 2:
+                continue
+            for e in entries:                                  # an earlier sweep's resident vectors: bring them home first
+                if e is not None and isinstance(e['probs'], _ResidentProbs):
+                    e['probs'] = e['probs'].get()
+            idxs = [large[k][0] for k in ks]
+            got = self._run_sweep([circs[i] for i in idxs], [large[k][1] for k in ks], shots, seed, [sid(i) for i in idxs],
+                                  precision, pmf)
+            for i, k, e in zip(idxs, ks, got):
+                e['meta']['host_ms'] = {'prepare (lower, fuse, plan)': large[k][2]}
+                entries[i] = e
         if small_ids:
             ps = [pr.ps if pr.ps is not None else (0, 0, 0) for pr in small_prep]
             keys, probs, kept, ms = _native.run_batch_small(
@@ -371,6 +434,121 @@ class B200Simulator:
                              'philox_stream': sid(i)}}
         res = Result(entries, single, self._name, seed, shots, time.perf_counter() - t0)
         return Job(res)
+
+    # -- sweeps: circuits of one structure through a batched handle ------------------------------------
+    def _sweep_signature(self, pr, precision):
+        """Hashable program structure of a prepared circuit, or None when it cannot join a batched sweep."""
+        pl = pr.plan
+        abytes = 8 if precision in ('single', 'c64', 32) else 16
+        if (abytes << pl.n_phys) > self.sweep_state_bytes or len(pr.virtual) > 64:
+            return None
+        if pr.ps is not None and not all(pl.layout[q] == q for q in range(pr.n_vars)):
+            return None                                       # the post-selected block must be the contiguous prefix
+        rel = tuple((v['qubit'], tuple(v['ctrl'])) for v in pr.virtual)
+        proj = (pr.proj[0].tobytes(), pr.proj[1].size) if pr.proj is not None else None
+        return (pl.n_phys, pl.ops.tobytes(), pl.tables.size, pr.clbit_map.tobytes(), pr.ps, rel, proj, pr.prog.n_clbits)
+
+    def prepare_sweep(self, circuits, n_vars=None, precision=None):
+        """Prepare a list of same-structure circuits as ONE sweep (raises if their structures differ)."""
+        precision = precision or self.precision
+        prs = [self.prepare(c, n_vars=n_vars) for c in circuits]
+        sigs = {self._sweep_signature(pr, precision) for pr in prs}
+        if len(sigs) != 1 or None in sigs:
+            raise ValueError('prepare_sweep: the circuits do not share one program structure (or their state is too large '
+                             'for a batched sweep: sweep_state_bytes)')
+        return self._stack_sweep(prs)
+
+    def _stack_sweep(self, prs):
+        sw = _Sweep()
+        p0 = prs[0]
+        sw.prs, sw.ops, sw.n_phys, sw.ps, sw.clbit_map, sw.n_vars = prs, p0.plan.ops, p0.plan.n_phys, p0.ps, p0.clbit_map, p0.n_vars
+        sw.tables = np.stack([pr.plan.tables for pr in prs])
+        sw.proj_ops = sw.proj_tables = sw.released = sw.p1 = None
+        if p0.virtual:
+            sw.proj_ops = p0.proj[0]
+            sw.proj_tables = np.stack([pr.proj[1] for pr in prs])
+            sw.released = self._released_tables(p0)
+            sw.p1 = np.stack([self._released_tables(pr)[3] for pr in prs])
+        return sw
+
+    def execute_sweep(self, sw, shots, seed=0, streams=None, precision=None, pmf=None, first=0, count=None):
+        """Run points [first, first + count) of a prepared sweep through one batched handle: program, shots (released
+        qubits drawn on the device), projection + post-selection.  Returns (keys (count, shots) or None, probs --
+        (count, 2^n) array if pmf is True, a list of _ResidentProbs if pmf is None, else None --, kept (count,) or None)."""
+        precision = precision or self.precision
+        B = len(sw.prs) - first if count is None else count
+        sl = slice(first, first + B)
+        if streams is None:
+            streams = np.arange(first, first + B, dtype=np.uint64)
+        if B == 1:
+            raise ValueError('a sweep chunk needs at least two points')
+        h = self._handle(sw.n_phys, precision, batch=B)
+        self._last = h
+        h.run_program(sw.ops, sw.tables[sl])
+        prof = {'program': list(zip(h.op_kernels(), h.op_profile())), 'projection': [], 'points': B}
+        keys = None
+        if shots:
+            if sw.released is not None:
+                mc, n_ctrl, ctrl, _p1, p1_off, vclbit, clbit_pos, n_cl = sw.released
+                keys = h.sample_released_batched(shots, seed, streams, n_ctrl, ctrl, sw.p1[sl], p1_off, vclbit, clbit_pos, n_cl)
+            else:
+                keys = h.sample_batched(shots, seed, streams, sw.clbit_map if len(sw.clbit_map) else None)
+        probs = kept = None
+        if pmf is not False and sw.ps is not None and sw.n_vars <= 30:
+            if sw.proj_ops is not None:
+                h.run_program(sw.proj_ops, sw.proj_tables[sl])      # project the released qubits on 0 (after the shots)
+                prof['projection'] = list(zip(h.op_kernels(), h.op_profile()))
+            mask, value, n = sw.ps
+            if pmf:
+                probs, kept = h.postselect(mask, value, n)
+            else:
+                kept = h.postselect_resident(mask, value, n)
+                probs = [_ResidentProbs(h, y, n) for y in range(B)]
+        t = h.timing()
+        prof['sample_ms'], prof['postselect_ms'] = (t['sample_ms'] if shots else 0.0), (t['postselect_ms'] if kept is not None else 0.0)
+        self.sweep_profile = prof                             # per-launch record of the last sweep chunk (bench.py)
+        return keys, probs, kept
+
+    def _run_sweep(self, circs, prs, shots, seed, streams, precision, pmf):
+        sw = self._stack_sweep(prs)
+        abytes = 8 if precision in ('single', 'c64', 32) else 16
+        cap = max(2, int(self.sweep_bytes // (abytes << sw.n_phys)))
+        entries = []
+        n = len(prs)
+        first = 0
+        while first < n:
+            B = min(cap, n - first)
+            if n - first - B == 1:                            # never leave a chunk of one point
+                B -= 1
+            if B < 2:                                         # (n - first == 1 cannot happen: chunks are >= 2)
+                B = n - first
+            t0 = time.perf_counter()
+            # a later chunk reuses the handle: resident vectors of the earlier chunk must come to the host first
+            for e in entries:
+                if isinstance(e['probs'], _ResidentProbs):
+                    e['probs'] = e['probs'].get()
+            keys, probs, kept = self.execute_sweep(sw, shots, seed, np.asarray(streams[first:first + B], dtype=np.uint64), precision,
+                                                   pmf, first, B)
+            t1 = time.perf_counter()
+            h = self._last
+            t = h.timing()
+            for y in range(B):
+                pr = prs[first + y]
+                counts = _keys_to_counts(keys[y], pr.prog.n_clbits) if shots else None
+                pv = None if probs is None else probs[y]
+                entries.append({'circuit': circs[first + y], 'name': pr.name, 'counts': counts, 'probs': pv,
+                                'kept': None if kept is None else float(kept[y]),
+                                'meta': {'path': 'sweep', 'width': 'release' if pr.virtual else 'full', 'sweep_points': B,
+                                         'released_qubits': len(pr.virtual), 'n_qubits': pr.prog.n_qubits, 'n_phys': sw.n_phys,
+                                         'passes': pr.plan.n_passes, 'gates_in': pr.fc.n_gates_in, 'philox_stream': int(streams[first + y]),
+                                         'h2d_bytes': int(sw.tables[0].nbytes + sw.ops.nbytes + (sw.proj_tables[0].nbytes if sw.proj_tables is not None else 0)
+                                                          + (sw.p1[0].nbytes if sw.p1 is not None else 0)),
+                                         'd2h_bytes': int((keys[y].nbytes if keys is not None else 0) + 8
+                                                          + (probs[y].nbytes if isinstance(probs, np.ndarray) else 0)),
+                                         'sweep_execute_ms': (t1 - t0) * 1e3, 'sample_ms': t['sample_ms'],
+                                         'postselect_ms': t['postselect_ms']}})
+            first += B
+        return entries
 
     def execute(self, pr, shots, seed=0, stream=0, precision=None, want_probs=True):
         """Run one prepared circuit on the large-state path: program, post-selection, shots.
@@ -472,7 +650,7 @@ class B200Simulator:
 
     def kernel_launches(self):
         """Kernels launched so far by the live state handles (bench.py's gpu_launches)."""
-        return sum(h.timing()['kernel_launches'] for h in self._handles.values())
+        return self._launches_closed + sum(h.timing()['kernel_launches'] for h in self._handles.values())
 
     def last_timing(self):
         return self._last.timing() if self._last is not None else None

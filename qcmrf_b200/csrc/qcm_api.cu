@@ -33,6 +33,11 @@ struct qcm_sim_s {
     int n_active = 0;
     int n_global = 0;
     uint64_t rank = 0;
+    int batch = 1;                  // sweep points held by this handle (qcm_create_batched); kernels run with gridDim.y = batch
+    int cur_point = 0;              // point addressed by qcm_get_amplitudes / qcm_set_amplitudes (qcm_batch_select)
+    size_t tab_stride = 0;          // doubles per point in the uploaded tables
+    uint64_t tree_total = 0;        // doubles per point in the sum-tree buffer
+    uint64_t probs_n = 0;           // entries per point of the resident post-selected block (qcm_postselect_resident)
     void *state = nullptr;
     bool own_state = false;
     cudaStream_t stream = nullptr;
@@ -44,6 +49,7 @@ struct qcm_sim_s {
     DevBuf scratch;                 // input copy of a rotated expansion pass
     DevBuf lowpart;                 // its per-CTA partial sums when a CTA covers fewer inputs than a tree chunk
     DevBuf relp1;                   // released-qubit probability tables (qcm_sample_released)
+    DevBuf streams, totals;         // batched sampling: per-point Philox streams and total masses
     // rotated storage (QCM_FLAG_ROTATED_OUTPUT_OK): logical index i of the 2^n_active state lives at
     // physical address ((i & (2^rot_nin - 1)) << rot_m) | (i >> rot_nin); rot_m == 0: identity
     int rot_m = 0, rot_nin = 0;
@@ -102,6 +108,12 @@ int ensure(qcm_handle h, DevBuf &b, size_t bytes) {
 }
 
 inline size_t amp_bytes(int prec) { return prec == QCM_C64 ? 8 : 16; }
+inline size_t real_bytes(const qcm_sim_s *h) { return h->prec == QCM_C64 ? 4 : 8; }
+// batch strides (bytes) of the state and of the per-point tables in the state's real type / in fp64
+inline uint64_t bstate(const qcm_sim_s *h) { return (uint64_t)amp_bytes(h->prec) << h->n_local; }
+inline uint64_t btab(const qcm_sim_s *h) { return (uint64_t)h->tab_stride * real_bytes(h); }
+inline uint64_t btab64(const qcm_sim_s *h) { return (uint64_t)h->tab_stride * sizeof(double); }
+inline dim3 bgrid(const qcm_sim_s *h, uint64_t gx) { return dim3((unsigned)gx, (unsigned)h->batch, 1u); }
 inline uint64_t rank_bits(const qcm_sim_s *h) { return h->n_global ? (h->rank << h->n_local) : 0ull; }
 
 int grid_mult() {
@@ -135,7 +147,7 @@ int launch_block_t(qcm_handle h, const BlockArgs &a, size_t smem) {
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t nvec = (1ull << (a.n_out - M)) / V;
     const int grid = grid_for(h, kern, smem, (uint64_t)kThreads * U, nvec);
-    kern<<<grid, kThreads, smem, h->stream>>>(a);
+    kern<<<bgrid(h, grid), kThreads, smem, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;
@@ -200,7 +212,7 @@ int launch_expand_t(qcm_handle h, const ExpandArgs &a, size_t smem) {
         grid = std::min<uint64_t>(need, (uint64_t)h->num_sms * occ);
     }
     grid = std::min<uint64_t>(grid, 0x7fffffffull);
-    kern<<<(unsigned)grid, threads, smem, h->stream>>>(a);
+    kern<<<bgrid(h, grid), threads, smem, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;
@@ -252,6 +264,8 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     a.n_members = n_mem;
     a.ctrl_below_32 = 1;
     a.rank_bits = rank_bits(h);
+    a.bstate = bstate(h);
+    a.btab = btab(h);
     for (int j = 0; j < M; ++j) {
         if (tq[j] < 0 || tq[j] >= n_out) return fail(h, QCM_ERR_INVALID, "block qubit %d outside the active state (%d)", tq[j], n_out);
         if (j && tq[j] <= tq[j - 1]) return fail(h, QCM_ERR_INVALID, "block qubits must be strictly ascending");
@@ -315,6 +329,8 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
         t.n_diag = 0;
         t.ctrl_below_32 = a.ctrl_below_32;
         t.rank_bits = rank_bits(h);
+        t.bstate = bstate(h);
+        t.btab = btab(h);
         size_t off = 0;
         for (int g = 0; g < n_mem; ++g) {
             TreeMember &m = a.mem[g].pos < 0 ? t.diag[t.n_diag++] : t.mem[a.mem[g].pos];
@@ -361,6 +377,10 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
             for (int k = 0; k < nu; ++k) e.cu[k] = cu[k];
             e.cu_below_32 = (nu == 0 || cu[nu - 1] < 32) ? 1 : 0;
             e.rank_bits = rank_bits(h);
+            e.bstate = bstate(h);
+            e.bctab = (uint64_t)amp_bytes(h->prec) << (M + nu);
+            t.btab64 = btab64(h);
+            t.bctab = e.bctab;
         }
     }
     if (expand && tree && M >= 5) expand = false;             // M <= 4: the precombined table wins; wider: the tree
@@ -450,7 +470,7 @@ static int launch_lowq_t(qcm_handle h, const LowqArgs &a, size_t smem) {
     constexpr int LB = (V == 2 ? 1 : 0) + 5 + UB;
     const uint64_t nrows = 1ull << (a.n - LB - MH);
     const uint64_t grid = std::min<uint64_t>(std::max<uint64_t>(1, (nrows + kThreads / 32 - 1) / (kThreads / 32)), 0x7fffffffull);
-    kern<<<(unsigned)grid, kThreads, smem, h->stream>>>(a);
+    kern<<<bgrid(h, grid), kThreads, smem, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     char nm[64];
@@ -481,6 +501,8 @@ static int try_lowq(qcm_handle h, const BlockPlan &bp) {
     a.n = n;
     a.n_members = b.n_members;
     a.rank_bits = b.rank_bits;
+    a.bstate = b.bstate;
+    a.btab = b.btab;
     for (int k = 0; k < MH; ++k) a.th[k] = b.tq[M - MH + k];
     for (int g = 0; g < b.n_members; ++g) {
         const MemberDesc &s = b.mem[g];
@@ -550,14 +572,14 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
         if (h->prec == QCM_C64) {
             if (V == 2) {
                 if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k_expand_tree<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_expand_tree<float, 2><<<(unsigned)grid, threads, smem, h->stream>>>(bp.trargs);
+                k_expand_tree<float, 2><<<bgrid(h, grid), threads, smem, h->stream>>>(bp.trargs);
             } else {
                 if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k_expand_tree<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_expand_tree<float, 1><<<(unsigned)grid, threads, smem, h->stream>>>(bp.trargs);
+                k_expand_tree<float, 1><<<bgrid(h, grid), threads, smem, h->stream>>>(bp.trargs);
             }
         } else {
             if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k_expand_tree<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_expand_tree<double, 1><<<(unsigned)grid, threads, smem, h->stream>>>(bp.trargs);
+            k_expand_tree<double, 1><<<bgrid(h, grid), threads, smem, h->stream>>>(bp.trargs);
         }
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
@@ -566,13 +588,13 @@ int launch_block_plan(qcm_handle h, BlockPlan &bp) {
         h->cur_kernel = h->prec == QCM_C64 ? "k_expand<float>" : "k_expand<double>";
         const size_t centry = h->prec == QCM_C64 ? 8 : 16;
         const size_t nent = 1ull << (M + bp.targs.nu);
-        if ((rc = ensure(h, h->ctab, nent * centry))) return rc;
+        if ((rc = ensure(h, h->ctab, nent * centry * h->batch))) return rc;
         if ((rc = ensure(h, h->tilectr, sizeof(unsigned long long)))) return rc;
         bp.targs.tables = (const double *)h->tab_f64.p;
         bp.targs.ctab = h->ctab.p;
         bp.targs.tile_counter = expand_use_counter() ? (unsigned long long *)h->tilectr.p : nullptr;
         bp.eargs.tile_counter = bp.targs.tile_counter;
-        k_expand_table<<<(unsigned)((nent + 255) / 256), 256, 0, h->stream>>>(bp.targs);
+        k_expand_table<<<bgrid(h, (nent + 255) / 256), 256, 0, h->stream>>>(bp.targs);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
         bp.eargs.ctab = h->ctab.p;
@@ -617,6 +639,8 @@ int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
     a.n_ctrl = op.n_ctrl;
     a.n_active = op.n_active_in;
     a.rank_bits = rank_bits(h);
+    a.bstate = bstate(h);
+    a.btab = btab(h);
     for (int j = 0; j < op.n_ctrl; ++j) {
         if (op.ctrl[j] < 0 || op.ctrl[j] >= h->n_local + h->n_global) return fail(h, QCM_ERR_INVALID, "DIAG: qubit %d out of range", op.ctrl[j]);
         a.ctrl[j] = (int8_t)op.ctrl[j];
@@ -628,15 +652,15 @@ int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
         if (a.n_active >= 1) {
             auto k = k_diag<float, 2, 4>;
             int grid = grid_for(h, k, smem, kThreads * 4, (1ull << a.n_active) / 2);
-            k<<<grid, kThreads, smem, h->stream>>>(a);
+            k<<<bgrid(h, grid), kThreads, smem, h->stream>>>(a);
         } else {
             auto k = k_diag<float, 1, 4>;
-            k<<<1, kThreads, smem, h->stream>>>(a);
+            k<<<bgrid(h, 1), kThreads, smem, h->stream>>>(a);
         }
     } else {
         auto k = k_diag<double, 1, 4>;
         int grid = grid_for(h, k, smem, kThreads * 4, 1ull << a.n_active);
-        k<<<grid, kThreads, smem, h->stream>>>(a);
+        k<<<bgrid(h, grid), kThreads, smem, h->stream>>>(a);
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
@@ -652,25 +676,27 @@ int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
         return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT: table (max(n,1)*4 doubles) outside tables");
     const int L = n >= 1 ? std::max(1, n / 2) : 0;   // a 2-amplitude vector must share one `hi` factor
     int rc;
-    if ((rc = ensure(h, h->init_lo, sizeof(double2) << L))) return rc;
-    if ((rc = ensure(h, h->init_hi, sizeof(double2) << (n - L)))) return rc;
+    const uint64_t blo = sizeof(double2) << L, bhi = sizeof(double2) << (n - L), bst = bstate(h);
+    if ((rc = ensure(h, h->init_lo, blo * h->batch))) return rc;
+    if ((rc = ensure(h, h->init_hi, bhi * h->batch))) return rc;
     const double *qv = (const double *)h->tab_f64.p + op.table_off;
     const uint64_t nt = (1ull << L) + (1ull << (n - L));
-    k_init_tables<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(qv, n, L, h->init_lo.p, (double2 *)h->init_hi.p, h->prec == QCM_C64 ? 1 : 0);
+    k_init_tables<<<bgrid(h, (nt + 255) / 256), 256, 0, h->stream>>>(qv, n, L, h->init_lo.p, (double2 *)h->init_hi.p, h->prec == QCM_C64 ? 1 : 0,
+                                                                     btab64(h), blo, bhi);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     if (h->prec == QCM_C64) {
         if (n >= 1) {
             auto k = k_init<float, 2>;
             int grid = grid_for(h, k, 0, (uint64_t)kThreads * kInitU, (1ull << n) / 2);
-            k<<<grid, kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+            k<<<bgrid(h, grid), kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L, bst, blo, bhi);
         } else {
-            k_init<float, 1><<<1, kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+            k_init<float, 1><<<bgrid(h, 1), kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L, bst, blo, bhi);
         }
     } else {
         auto k = k_init<double, 1>;
         int grid = grid_for(h, k, 0, (uint64_t)kThreads * kInitU, 1ull << n);
-        k<<<grid, kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L);
+        k<<<bgrid(h, grid), kThreads, 0, h->stream>>>(h->state, h->init_lo.p, (const double2 *)h->init_hi.p, n, L, bst, blo, bhi);
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
@@ -684,10 +710,10 @@ int launch_extend(qcm_handle h, int n_in, int n_out) {
     const uint64_t first = 1ull << n_in, count = (1ull << n_out) - first;
     if (h->prec == QCM_C64) {
         auto k = k_zero<float>;
-        k<<<grid_for(h, k, 0, (uint64_t)kThreads * kInitU, count), kThreads, 0, h->stream>>>(h->state, first, count);
+        k<<<bgrid(h, grid_for(h, k, 0, (uint64_t)kThreads * kInitU, count)), kThreads, 0, h->stream>>>(h->state, first, count, bstate(h));
     } else {
         auto k = k_zero<double>;
-        k<<<grid_for(h, k, 0, (uint64_t)kThreads * kInitU, count), kThreads, 0, h->stream>>>(h->state, first, count);
+        k<<<bgrid(h, grid_for(h, k, 0, (uint64_t)kThreads * kInitU, count)), kThreads, 0, h->stream>>>(h->state, first, count, bstate(h));
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
@@ -704,14 +730,14 @@ int launch_swap(qcm_handle h, const qcm_op &op) {
     if (h->prec == QCM_C64) {
         if (qa >= 1 && n >= 3) {
             auto k = k_swap<float, 2>;
-            k<<<grid_for(h, k, 0, kThreads, quads / 2), kThreads, 0, h->stream>>>(h->state, qa, qb, n);
+            k<<<bgrid(h, grid_for(h, k, 0, kThreads, quads / 2)), kThreads, 0, h->stream>>>(h->state, qa, qb, n, bstate(h));
         } else {
             auto k = k_swap<float, 1>;
-            k<<<grid_for(h, k, 0, kThreads, quads), kThreads, 0, h->stream>>>(h->state, qa, qb, n);
+            k<<<bgrid(h, grid_for(h, k, 0, kThreads, quads)), kThreads, 0, h->stream>>>(h->state, qa, qb, n, bstate(h));
         }
     } else {
         auto k = k_swap<double, 1>;
-        k<<<grid_for(h, k, 0, kThreads, quads), kThreads, 0, h->stream>>>(h->state, qa, qb, n);
+        k<<<bgrid(h, grid_for(h, k, 0, kThreads, quads)), kThreads, 0, h->stream>>>(h->state, qa, qb, n, bstate(h));
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
@@ -720,7 +746,9 @@ int launch_swap(qcm_handle h, const qcm_op &op) {
     return QCM_OK;
 }
 
-int upload_tables(qcm_handle h, const double *tables, size_t n_tables) {
+int upload_tables(qcm_handle h, const double *tables, size_t n_per_point) {
+    h->tab_stride = n_per_point;
+    const size_t n_tables = n_per_point * (size_t)h->batch;      // batched handle: `batch` consecutive table sets
     if (!n_tables) return QCM_OK;
     int rc;
     if ((rc = ensure(h, h->tab_f64, n_tables * sizeof(double)))) return rc;
@@ -753,7 +781,8 @@ int tree_layout(qcm_handle h, int na) {
         n = (n + (1ull << kFanBits) - 1) >> kFanBits;
     }
     int rc;
-    if ((rc = ensure(h, h->tree, total * sizeof(double)))) return rc;
+    h->tree_total = total;
+    if ((rc = ensure(h, h->tree, total * sizeof(double) * h->batch))) return rc;
     double *p = (double *)h->tree.p;
     for (int l = 0; l < levels; ++l) {
         h->tree_ptr[l] = p;
@@ -769,8 +798,9 @@ int tree_level0(qcm_handle h, int na) {
     const uint64_t warps_per_block = kThreads / 32;
     const uint64_t n0 = h->tree_n[0];
     uint64_t blocks = std::min<uint64_t>((n0 + warps_per_block - 1) / warps_per_block, 0x7fffffffull);
-    if (h->prec == QCM_C64) k_chunk_sums<float><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
-    else k_chunk_sums<double><<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0]);
+    const uint64_t btree = h->tree_total * sizeof(double);
+    if (h->prec == QCM_C64) k_chunk_sums<float><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0], bstate(h), btree);
+    else k_chunk_sums<double><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0], bstate(h), btree);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;
@@ -780,13 +810,30 @@ int tree_level0(qcm_handle h, int na) {
 int tree_finish(qcm_handle h, int na) {
     const uint64_t warps_per_block = kThreads / 32;
     const int levels = h->tree_levels;
+    const uint64_t btree = h->tree_total * sizeof(double);
     for (int l = 1; l < levels; ++l) {
         uint64_t blocks = std::min<uint64_t>((h->tree_n[l] + warps_per_block - 1) / warps_per_block, (uint64_t)h->num_sms * 8);
-        k_tree_level<<<(unsigned)blocks, kThreads, 0, h->stream>>>(h->tree_ptr[l - 1], h->tree_n[l - 1], h->tree_ptr[l], h->tree_n[l]);
+        k_tree_level<<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->tree_ptr[l - 1], h->tree_n[l - 1], h->tree_ptr[l], h->tree_n[l], btree, btree);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
     }
     const uint64_t ntop = h->tree_n[levels - 1];
+    if (h->batch > 1) {
+        // per-point totals stay on the device (k_sample reads them): no host round trip in a sweep
+        int rc;
+        if ((rc = ensure(h, h->totals, sizeof(double) * h->batch))) return rc;
+        k_batch_totals<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->tree_ptr[levels - 1], ntop, btree, (double *)h->totals.p, h->batch);
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+        h->local_mass = 0.0;
+        h->tree_valid = true;
+        h->tree_for_active = na;
+        h->tree_base_bits = na;
+        h->tree_cond_bits = 0;
+        h->tree_sub_bits = 0;
+        h->tree_has_sub = false;
+        return QCM_OK;
+    }
     h->h_top.resize(ntop);
     QCM_CUDA(h, cudaMemcpyAsync(h->h_top.data(), h->tree_ptr[levels - 1], ntop * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -967,8 +1014,13 @@ int qcm_ipc_close(int device, void *base) {
 const char *qcm_last_error(qcm_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
 int qcm_create(qcm_handle *out, int device, int n_local, int precision, void *ext_state, void *ext_stream) {
+    return qcm_create_batched(out, device, n_local, precision, 1, ext_state, ext_stream);
+}
+
+int qcm_create_batched(qcm_handle *out, int device, int n_local, int precision, int batch, void *ext_state, void *ext_stream) {
     if (!out) return fail(nullptr, QCM_ERR_INVALID, "out is NULL");
     *out = nullptr;
+    if (batch < 1 || batch > 65535) return fail(nullptr, QCM_ERR_INVALID, "batch %d out of range [1, 65535]", batch);
     if (precision != QCM_C64 && precision != QCM_C128) return fail(nullptr, QCM_ERR_INVALID, "precision must be 32 or 64");
     if (n_local < 0 || n_local > 40) return fail(nullptr, QCM_ERR_INVALID, "n_local %d out of range [0, 40]", n_local);
     int ndev = 0;
@@ -980,6 +1032,7 @@ int qcm_create(qcm_handle *out, int device, int n_local, int precision, void *ex
     h->device = device;
     h->n_local = n_local;
     h->prec = precision;
+    h->batch = batch;
     h->stream = (cudaStream_t)ext_stream;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -989,7 +1042,7 @@ int qcm_create(qcm_handle *out, int device, int n_local, int precision, void *ex
         if (ext_state) {
             h->state = ext_state;
         } else {
-            e = cudaMalloc(&h->state, amp_bytes(precision) << n_local);
+            e = cudaMalloc(&h->state, (amp_bytes(precision) << n_local) * (size_t)batch);
             h->own_state = (e == cudaSuccess);
         }
     }
@@ -1008,7 +1061,7 @@ int qcm_destroy(qcm_handle h) {
     if (!h) return QCM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree, &h->scratch, &h->lowpart, &h->relp1};
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree, &h->scratch, &h->lowpart, &h->relp1, &h->streams, &h->totals};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->own_state && h->state) cudaFree(h->state);
@@ -1044,11 +1097,12 @@ int qcm_get_amplitudes(qcm_handle h, uint64_t first, uint64_t count, void *host_
     const size_t ab = amp_bytes(h->prec);
     const uint64_t valid = 1ull << h->n_active;          // beyond: implicit zeros
     const uint64_t vend = std::min(first + count, valid);
+    const char *const st = (const char *)h->state + (size_t)h->cur_point * bstate(h);
     if (h->rot_m && first < vend) {
         // rotated storage: fetch the active state and undo the rotation on the host (inspection path)
         if (h->n_active > 30) return fail(h, QCM_ERR_UNSUPPORTED, "qcm_get_amplitudes on a rotated state of %d qubits", h->n_active);
         std::vector<char> tmp((size_t)valid * ab);
-        QCM_CUDA(h, cudaMemcpyAsync(tmp.data(), h->state, (size_t)valid * ab, cudaMemcpyDeviceToHost, h->stream));
+        QCM_CUDA(h, cudaMemcpyAsync(tmp.data(), st, (size_t)valid * ab, cudaMemcpyDeviceToHost, h->stream));
         QCM_CUDA(h, cudaStreamSynchronize(h->stream));
         const uint64_t lowm = (1ull << h->rot_nin) - 1ull;
         for (uint64_t i = first; i < vend; ++i) {
@@ -1056,7 +1110,7 @@ int qcm_get_amplitudes(qcm_handle h, uint64_t first, uint64_t count, void *host_
             memcpy((char *)host_out + (i - first) * ab, tmp.data() + phys * ab, ab);
         }
     } else if (first < vend)
-        QCM_CUDA(h, cudaMemcpyAsync(host_out, (const char *)h->state + first * ab, (vend - first) * ab, cudaMemcpyDeviceToHost, h->stream));
+        QCM_CUDA(h, cudaMemcpyAsync(host_out, st + first * ab, (vend - first) * ab, cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaStreamSynchronize(h->stream));
     if (first + count > vend) {
         const uint64_t z0 = std::max(first, vend);
@@ -1072,7 +1126,7 @@ int qcm_set_amplitudes(qcm_handle h, uint64_t first, uint64_t count, const void 
     int rc = check_device(h);
     if (rc) return rc;
     const size_t ab = amp_bytes(h->prec);
-    QCM_CUDA(h, cudaMemcpyAsync((char *)h->state + first * ab, host_in, count * ab, cudaMemcpyHostToDevice, h->stream));
+    QCM_CUDA(h, cudaMemcpyAsync((char *)h->state + (size_t)h->cur_point * bstate(h) + first * ab, host_in, count * ab, cudaMemcpyHostToDevice, h->stream));
     QCM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n_active = n_active;
     h->tree_valid = false;
@@ -1083,7 +1137,20 @@ int qcm_set_amplitudes(qcm_handle h, uint64_t first, uint64_t count, const void 
 int qcm_state_ptr(qcm_handle h, void **dev_ptr_out, uint64_t *bytes_out) {
     if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
     if (dev_ptr_out) *dev_ptr_out = h->state;
-    if (bytes_out) *bytes_out = amp_bytes(h->prec) << h->n_local;
+    if (bytes_out) *bytes_out = (amp_bytes(h->prec) << h->n_local) * (uint64_t)h->batch;
+    return QCM_OK;
+}
+
+int qcm_batch_size(qcm_handle h, int *batch_out) {
+    if (!h || !batch_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    *batch_out = h->batch;
+    return QCM_OK;
+}
+
+int qcm_batch_select(qcm_handle h, int point) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    if (point < 0 || point >= h->batch) return fail(h, QCM_ERR_INVALID, "point %d outside the batch of %d", point, h->batch);
+    h->cur_point = point;
     return QCM_OK;
 }
 
@@ -1139,7 +1206,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
             li = i;
             i += 1 + (ops[i].kind == QCM_OP_BLOCK ? std::max(0, ops[i].n_ctrl) : 0);
         }
-        if (li > 0 && ops[0].kind == QCM_OP_INIT_PRODUCT && ops[li].kind == QCM_OP_BLOCK &&
+        if (li > 0 && h->batch == 1 && ops[0].kind == QCM_OP_INIT_PRODUCT && ops[li].kind == QCM_OP_BLOCK &&
             (ops[li].flags & QCM_FLAG_ROTATED_OUTPUT_OK) && rotate_enabled() && li + ops[li].n_ctrl == n_ops - 1) {
             const int n_in = ops[li].n_active_in;
             bool fits = n_in >= kChunkBits && n_in <= h->n_local;
@@ -1194,9 +1261,9 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 // can be built on the 2^M-times smaller input instead of re-reading the result.
                 const bool last = (i + (op.kind == QCM_OP_BLOCK ? n_mem : 0)) == n_ops - 1;
                 bool checkpoint = last && (op.flags & QCM_FLAG_SAMPLE_CHECKPOINT) && bp.norm_preserving &&
-                                  op.n_active_in >= kChunkBits;
+                                  op.n_active_in >= kChunkBits && h->batch == 1;
                 // rotated output: last op, wide expansion on the product-tree path, enough image bits for a warp store
-                bp.rotate = last && !no_rotate && (op.flags & QCM_FLAG_ROTATED_OUTPUT_OK) && bp.tree && rotate_enabled() &&
+                bp.rotate = last && !no_rotate && h->batch == 1 && (op.flags & QCM_FLAG_ROTATED_OUTPUT_OK) && bp.tree && rotate_enabled() &&
                             op.n_active_in >= kChunkBits && bp.M >= (h->prec == QCM_C64 ? 6 : 5) &&
                             op.n_active_out - op.n_active_in == bp.M;
                 if (bp.rotate) {                          // its product tables + the member tables must fit shared memory
@@ -1257,9 +1324,11 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
         h->op_kind.push_back(op.kind);
         h->op_kernel.push_back(h->cur_kernel);
         h->cur_kernel.clear();
-        h->op_rd.push_back(h->timing.bytes_read - rd0);
-        h->op_wr.push_back(h->timing.bytes_written - wr0);
+        h->op_rd.push_back((h->timing.bytes_read - rd0) * (uint64_t)h->batch);
+        h->op_wr.push_back((h->timing.bytes_written - wr0) * (uint64_t)h->batch);
     }
+    h->timing.bytes_read *= (uint64_t)h->batch;
+    h->timing.bytes_written *= (uint64_t)h->batch;
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
@@ -1275,6 +1344,7 @@ int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const doubl
     if (!h || !ops || n_ops < 1 || !src_slabs || !dst_state) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if (s < 1 || s > QCM_MAX_GATHER || s > h->n_global || s >= h->n_local) return fail(h, QCM_ERR_INVALID, "cannot gather %d qubits", s);
     if (h->n_active != h->n_local) return fail(h, QCM_ERR_INVALID, "gather needs a fully materialised shard");
+    if (h->batch != 1) return fail(h, QCM_ERR_UNSUPPORTED, "gather on a batched handle");
     if (h->rot_m) return fail(h, QCM_ERR_INVALID, "gather on a rotated state");
     if (h->own_state) return fail(h, QCM_ERR_INVALID, "gather needs a caller-owned state buffer (ext_state): peers map it");
     int rc = check_device(h);
@@ -1350,26 +1420,36 @@ int qcm_get_op_profile(qcm_handle h, int cap, int32_t *kind_out, float *ms_out, 
     return QCM_OK;
 }
 
-static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *probs_out, double *kept_out, bool dev) {
+// mode 0: results to host buffers; 1: to caller-provided DEVICE buffers, no synchronisation (unbatched handles);
+// 2: kept to the host, the probability block stays in the handle's device buffer (qcm_fetch_probs).
+// Batched handle: kept_out holds `batch` doubles, probs_out `batch` consecutive blocks of 2^n_out_bits.
+static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *probs_out, double *kept_out, int mode) {
+    const bool dev = mode == 1, resident = mode == 2;
     if (!h || !kept_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if (n_out_bits < 0 || n_out_bits > h->n_local || n_out_bits > 30) return fail(h, QCM_ERR_INVALID, "n_out_bits %d out of range", n_out_bits);
     if (value & ~mask) return fail(h, QCM_ERR_INVALID, "value has bits outside mask");
+    if (dev && h->batch != 1) return fail(h, QCM_ERR_UNSUPPORTED, "device-resident post-selection on a batched handle: use qcm_postselect_resident");
     int rc = check_device(h);
     if (rc) return rc;
     QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     const uint64_t nprob = 1ull << n_out_bits;
+    const uint64_t B = (uint64_t)h->batch;
     const uint64_t local_all = (h->n_local >= 64) ? ~0ull : ((1ull << h->n_local) - 1ull);
     const uint64_t act_all = (1ull << h->n_active) - 1ull;
     const uint64_t rb = rank_bits(h);
+    const bool want_probs = probs_out != nullptr || resident;
     if (dev) {
         QCM_CUDA(h, cudaMemsetAsync(kept_out, 0, sizeof(double), h->stream));
     } else {
-        *kept_out = 0.0;
-        if (probs_out) memset(probs_out, 0, nprob * sizeof(double));
+        for (uint64_t y = 0; y < B; ++y) kept_out[y] = 0.0;
+        if (probs_out) memset(probs_out, 0, nprob * B * sizeof(double));
     }
+    if (!dev && want_probs) h->probs_n = 0;  // the handle's block buffer is about to be overwritten
     // global (rank) bits and never-materialised bits decide emptiness up front
     bool empty = ((rb & mask & ~local_all) != (value & ~local_all));
     if (value & local_all & ~act_all) empty = true;       // demands a 1 on a qubit known |0>
+    if (!dev && want_probs && (rc = ensure(h, h->probs, nprob * B * sizeof(double)))) return rc;
+    double *dprobs = want_probs ? (dev ? probs_out : (double *)h->probs.p) : nullptr;
     if (!empty) {
         const uint64_t lmask = mask & act_all, lval = value & act_all;
         const int nb = std::min(n_out_bits, h->n_active);
@@ -1378,34 +1458,36 @@ static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_ou
         // rotated storage: logical i lives at ((i & low) << rot_m) | (i >> rot_nin); the kept prefix
         // (i < 2^nb <= 2^rot_nin) is then the stride-2^rot_m sequence i << rot_m
         const int pshift = (h->rot_m && nb <= h->rot_nin) ? h->rot_m : 0;
-        const int blocks = h->num_sms * 4;
-        if ((rc = ensure(h, h->partial, (blocks + 1) * sizeof(double)))) return rc;
-        if (probs_out && !dev && (rc = ensure(h, h->probs, nprob * sizeof(double)))) return rc;
-        double *dprobs = probs_out ? (dev ? probs_out : (double *)h->probs.p) : nullptr;
+        // a batched sweep spreads its points over the grid: fewer blocks per point
+        const int blocks = B > 1 ? std::max(8, (int)((uint64_t)h->num_sms * 8 / B)) : h->num_sms * 4;
+        const uint64_t bpart = (uint64_t)(blocks + 1) * sizeof(double), bprobs = nprob * sizeof(double);
+        if ((rc = ensure(h, h->partial, bpart * B))) return rc;
         if (contiguous && (!h->rot_m || pshift)) {
             const uint64_t count = 1ull << nb;
-            if (dprobs && count < nprob) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * sizeof(double), h->stream));
-            if (h->prec == QCM_C64) k_probs_prefix<float><<<blocks, kThreads, 0, h->stream>>>(h->state, count, pshift, dprobs, (double *)h->partial.p);
-            else k_probs_prefix<double><<<blocks, kThreads, 0, h->stream>>>(h->state, count, pshift, dprobs, (double *)h->partial.p);
+            if (dprobs && count < nprob) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * B * sizeof(double), h->stream));
+            if (h->prec == QCM_C64) k_probs_prefix<float><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, count, pshift, dprobs, (double *)h->partial.p, bstate(h), bprobs, bpart);
+            else k_probs_prefix<double><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, count, pshift, dprobs, (double *)h->partial.p, bstate(h), bprobs, bpart);
         } else {
-            if (dprobs) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * sizeof(double), h->stream));
+            if (dprobs) QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * B * sizeof(double), h->stream));
             if (h->prec == QCM_C64)
-                k_postselect_general<float><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, h->rot_m, h->rot_nin, dprobs, (double *)h->partial.p);
+                k_postselect_general<float><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, h->rot_m, h->rot_nin, dprobs, (double *)h->partial.p, bstate(h), bprobs, bpart);
             else
-                k_postselect_general<double><<<blocks, kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, h->rot_m, h->rot_nin, dprobs, (double *)h->partial.p);
+                k_postselect_general<double><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, h->n_active, rb, mask, value, nprob - 1, h->rot_m, h->rot_nin, dprobs, (double *)h->partial.p, bstate(h), bprobs, bpart);
         }
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
-        k_tree_level<<<1, kThreads, 0, h->stream>>>((const double *)h->partial.p, (uint64_t)blocks,
-                                                    dev ? kept_out : (double *)h->partial.p + blocks, 1);
+        // per-point kept mass: the block partials summed in index order, written behind them
+        k_tree_level<<<bgrid(h, 1), kThreads, 0, h->stream>>>((const double *)h->partial.p, (uint64_t)blocks,
+                                                              dev ? kept_out : (double *)h->partial.p + blocks, 1, bpart, dev ? 0 : bpart);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
         if (!dev) {
-            QCM_CUDA(h, cudaMemcpyAsync(kept_out, (double *)h->partial.p + blocks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            if (probs_out) QCM_CUDA(h, cudaMemcpyAsync(probs_out, dprobs, nprob * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            QCM_CUDA(h, cudaMemcpy2DAsync(kept_out, sizeof(double), (double *)h->partial.p + blocks, bpart, sizeof(double), B,
+                                          cudaMemcpyDeviceToHost, h->stream));
+            if (probs_out) QCM_CUDA(h, cudaMemcpyAsync(probs_out, dprobs, nprob * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
-    } else if (dev && probs_out) {
-        QCM_CUDA(h, cudaMemsetAsync(probs_out, 0, nprob * sizeof(double), h->stream));
+    } else if (dprobs) {
+        QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * B * sizeof(double), h->stream));
     }
     if (dev) return QCM_OK;                 // results stay on the device, in stream order: no synchronisation
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -1413,15 +1495,32 @@ static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_ou
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->timing.postselect_ms = ms;
+    if (resident) h->probs_n = nprob;
     return QCM_OK;
 }
 
 int qcm_postselect(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *probs_out, double *kept_out) {
-    return postselect_impl(h, mask, value, n_out_bits, probs_out, kept_out, false);
+    return postselect_impl(h, mask, value, n_out_bits, probs_out, kept_out, 0);
 }
 
 int qcm_postselect_device(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, void *dev_probs_out, void *dev_kept_out) {
-    return postselect_impl(h, mask, value, n_out_bits, (double *)dev_probs_out, (double *)dev_kept_out, true);
+    return postselect_impl(h, mask, value, n_out_bits, (double *)dev_probs_out, (double *)dev_kept_out, 1);
+}
+
+int qcm_postselect_resident(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *kept_out) {
+    return postselect_impl(h, mask, value, n_out_bits, nullptr, kept_out, 2);
+}
+
+int qcm_fetch_probs(qcm_handle h, int point, uint64_t first, uint64_t count, double *host_out) {
+    if (!h || !host_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if (!h->probs_n) return fail(h, QCM_ERR_INVALID, "no resident post-selected block (call qcm_postselect_resident first)");
+    if (point < 0 || point >= h->batch || first + count > h->probs_n) return fail(h, QCM_ERR_INVALID, "range outside the resident block");
+    int rc = check_device(h);
+    if (rc) return rc;
+    QCM_CUDA(h, cudaMemcpyAsync(host_out, (const double *)h->probs.p + (uint64_t)point * h->probs_n + first, count * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->stream));
+    QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QCM_OK;
 }
 
 int qcm_sample_prepare(qcm_handle h, double *local_mass_out) {
@@ -1434,9 +1533,14 @@ int qcm_sample_prepare(qcm_handle h, double *local_mass_out) {
     return QCM_OK;
 }
 
+// stream_ids: batched handles only -- one Philox stream per sweep point (host array of `batch` entries); the
+// keys of point y land at keys_out + y * shots.  Batched sampling is unsharded (n_ranks == 1).
 static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const double *rank_masses, int n_ranks,
-                               const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out, uint8_t *mine_out, bool dev) {
-    if (!h || !keys_out || !rank_masses) return fail(h, QCM_ERR_INVALID, "NULL argument");
+                               const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out, uint8_t *mine_out, bool dev,
+                               const uint64_t *stream_ids = nullptr) {
+    if (!h || !keys_out || (!rank_masses && !stream_ids)) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    if ((h->batch > 1) != (stream_ids != nullptr)) return fail(h, QCM_ERR_INVALID, "batched handles sample with qcm_sample_batched (and only they)");
+    if (stream_ids && (h->n_global != 0 || mine_out)) return fail(h, QCM_ERR_UNSUPPORTED, "batched sampling on a sharded state");
     if (n_ranks < 1 || (uint64_t)n_ranks != (1ull << h->n_global)) return fail(h, QCM_ERR_INVALID, "n_ranks %d does not match %d global qubits", n_ranks, h->n_global);
     if (n_clbits < 0 || n_clbits > 64 || (n_clbits && !clbit_qubit)) return fail(h, QCM_ERR_INVALID, "bad clbit map");
     int rc = check_device(h);
@@ -1463,14 +1567,29 @@ static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint
     a.seed = seed;
     a.stream = stream_id;
     double lo = 0.0, total = 0.0;
-    for (int r = 0; r < n_ranks; ++r) {
-        if ((uint64_t)r == h->rank) lo = total;
-        total += rank_masses[r];
+    const uint64_t B = (uint64_t)h->batch;
+    if (stream_ids) {
+        // per-point totals were left on the device by the tree build; streams go up here
+        if ((rc = ensure(h, h->streams, sizeof(uint64_t) * B))) return rc;
+        QCM_CUDA(h, cudaMemcpyAsync(h->streams.p, stream_ids, sizeof(uint64_t) * B, cudaMemcpyHostToDevice, h->stream));
+        a.streams = (const uint64_t *)h->streams.p;
+        a.totals = (const double *)h->totals.p;
+        a.bstate = bstate(h);
+        a.btree = h->tree_total * sizeof(double);
+        a.bkeys = shots * sizeof(uint64_t);
+        a.rank_lo = 0.0;
+        a.rank_hi = 1e300;
+        a.total = 1.0;
+    } else {
+        for (int r = 0; r < n_ranks; ++r) {
+            if ((uint64_t)r == h->rank) lo = total;
+            total += rank_masses[r];
+        }
+        if (!(total > 0.0)) return fail(h, QCM_ERR_INVALID, "state has zero norm");
+        a.rank_lo = lo;
+        a.rank_hi = ((int)h->rank == n_ranks - 1) ? 1e300 : lo + rank_masses[h->rank];
+        a.total = total;
     }
-    if (!(total > 0.0)) return fail(h, QCM_ERR_INVALID, "state has zero norm");
-    a.rank_lo = lo;
-    a.rank_hi = ((int)h->rank == n_ranks - 1) ? 1e300 : lo + rank_masses[h->rank];
-    a.total = total;
     a.rank_bits = rank_bits(h);
     a.n_clbits = n_clbits;
     for (int c = 0; c < n_clbits; ++c) {
@@ -1481,19 +1600,21 @@ static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint
         a.keys_out = keys_out;
         a.mine_out = mine_out;
     } else {
-        if ((rc = ensure(h, h->keys, shots * sizeof(uint64_t)))) return rc;
+        if ((rc = ensure(h, h->keys, shots * B * sizeof(uint64_t)))) return rc;
         if ((rc = ensure(h, h->mine, shots))) return rc;
         a.keys_out = (uint64_t *)h->keys.p;
-        a.mine_out = (uint8_t *)h->mine.p;
+        a.mine_out = stream_ids ? nullptr : (uint8_t *)h->mine.p;
     }
     const uint64_t wpb = kThreads / 32;
-    const unsigned blocks = (unsigned)std::min<uint64_t>((shots + wpb - 1) / wpb, (uint64_t)h->num_sms * 8);
-    if (h->prec == QCM_C64) k_sample<float><<<blocks, kThreads, 0, h->stream>>>(a);
-    else k_sample<double><<<blocks, kThreads, 0, h->stream>>>(a);
+    // a batched sweep spreads its points over the grid: fewer blocks per point
+    const uint64_t cap = B > 1 ? std::max<uint64_t>(4, (uint64_t)h->num_sms * 16 / B) : (uint64_t)h->num_sms * 8;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((shots + wpb - 1) / wpb, cap);
+    if (h->prec == QCM_C64) k_sample<float><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(a);
+    else k_sample<double><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     if (dev) return QCM_OK;                 // keys / mine stay on the device, in stream order
-    QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * B * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     if (mine_out) QCM_CUDA(h, cudaMemcpyAsync(mine_out, h->mine.p, shots, cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
@@ -1525,11 +1646,43 @@ int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, 
     return qcm_sample_sharded(h, shots, seed, stream_id, &mass, 1, clbit_qubit, n_clbits, keys_out, nullptr);
 }
 
+int qcm_sample_batched(qcm_handle h, uint64_t shots, uint64_t seed, const uint64_t *stream_ids, const int32_t *clbit_qubit, int n_clbits,
+                       uint64_t *keys_out) {
+    if (!h || !stream_ids) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    double mass = 0.0;
+    int rc = qcm_sample_prepare(h, &mass);
+    if (rc) return rc;
+    return sample_sharded_impl(h, shots, seed, 0, nullptr, 1, clbit_qubit, n_clbits, keys_out, nullptr, false, stream_ids);
+}
+
+static int sample_released_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const uint64_t *stream_ids, int nv,
+                                const int32_t *n_ctrl, const int32_t *ctrl, int max_ctrl, const double *p1, const int64_t *p1_off,
+                                int64_t n_p1, const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits, uint64_t *keys_out);
+
 int qcm_sample_released(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, int nv, const int32_t *n_ctrl,
                         const int32_t *ctrl, int max_ctrl, const double *p1, const int64_t *p1_off, int64_t n_p1,
                         const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits, uint64_t *keys_out) {
+    if (h && h->batch != 1) return fail(h, QCM_ERR_INVALID, "batched handle: use qcm_sample_released_batched");
+    return sample_released_impl(h, shots, seed, stream_id, nullptr, nv, n_ctrl, ctrl, max_ctrl, p1, p1_off, n_p1, vclbit, clbit_pos,
+                                n_clbits, keys_out);
+}
+
+int qcm_sample_released_batched(qcm_handle h, uint64_t shots, uint64_t seed, const uint64_t *stream_ids, int nv, const int32_t *n_ctrl,
+                                const int32_t *ctrl, int max_ctrl, const double *p1, const int64_t *p1_off, int64_t n_p1,
+                                const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits, uint64_t *keys_out) {
+    if (!stream_ids) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    return sample_released_impl(h, shots, seed, 0, stream_ids, nv, n_ctrl, ctrl, max_ctrl, p1, p1_off, n_p1, vclbit, clbit_pos,
+                                n_clbits, keys_out);
+}
+
+// p1: `batch` consecutive sets of n_p1 probabilities (one set for a plain handle)
+static int sample_released_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const uint64_t *stream_ids, int nv,
+                                const int32_t *n_ctrl, const int32_t *ctrl, int max_ctrl, const double *p1, const int64_t *p1_off,
+                                int64_t n_p1, const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits, uint64_t *keys_out) {
     if (!h || !keys_out || !n_ctrl || !ctrl || !p1 || !p1_off || !vclbit || !clbit_pos) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if (h->n_global != 0) return fail(h, QCM_ERR_UNSUPPORTED, "released-qubit sampling on a sharded state");
+    if ((h->batch > 1) != (stream_ids != nullptr)) return fail(h, QCM_ERR_INVALID, "batched handles sample with the _batched entry points (and only they)");
+    const uint64_t B = (uint64_t)h->batch;
     if (nv < 0 || nv > kMaxReleased || n_clbits < 0 || n_clbits > 64 || max_ctrl < 1) return fail(h, QCM_ERR_INVALID, "bad released-qubit tables");
     ReleasedArgs a{};
     for (int k = 0; k < nv; ++k) {
@@ -1555,10 +1708,13 @@ int qcm_sample_released(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t st
     int rc = qcm_sample_prepare(h, &mass);
     if (rc) return rc;
     if (shots == 0) return QCM_OK;
-    if ((rc = ensure(h, h->keys, shots * sizeof(uint64_t)))) return rc;
-    if ((rc = ensure(h, h->relp1, (size_t)n_p1 * sizeof(double)))) return rc;
-    if ((rc = sample_sharded_impl(h, shots, seed, stream_id, &mass, 1, nullptr, 0, (uint64_t *)h->keys.p, nullptr, true))) return rc;
-    QCM_CUDA(h, cudaMemcpyAsync(h->relp1.p, p1, (size_t)n_p1 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ensure(h, h->keys, shots * B * sizeof(uint64_t)))) return rc;
+    if ((rc = ensure(h, h->relp1, (size_t)n_p1 * B * sizeof(double)))) return rc;
+    if ((rc = sample_sharded_impl(h, shots, seed, stream_id, &mass, 1, nullptr, 0, (uint64_t *)h->keys.p, nullptr, true, stream_ids))) return rc;
+    QCM_CUDA(h, cudaMemcpyAsync(h->relp1.p, p1, (size_t)n_p1 * B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    a.bkeys = shots * sizeof(uint64_t);
+    a.bp1 = (uint64_t)n_p1 * sizeof(double);
+    a.streams = stream_ids ? (const uint64_t *)h->streams.p : nullptr;
     a.keys = (uint64_t *)h->keys.p;
     a.shots = shots;
     a.seed = seed;
@@ -1566,10 +1722,10 @@ int qcm_sample_released(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t st
     a.p1 = (const double *)h->relp1.p;
     a.nv = nv;
     a.n_clbits = n_clbits;
-    k_released_keys<<<(unsigned)((shots + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>(a);
+    k_released_keys<<<bgrid(h, (shots + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>(a);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
-    QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * B * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;

@@ -16,6 +16,15 @@ namespace qcm {
 
 constexpr int kThreads = 256;
 
+// Batch axis (theta / beta sweeps over one graph, BASELINE config 3): a handle may hold `batch` states of
+// 2^n_local amplitudes in ONE allocation, all running the same program with per-point coefficient tables.
+// Every kernel then runs with the sweep point as blockIdx.y: state, tables and per-point outputs are offset by
+// blockIdx.y times the strides in its argument block (all zero-cost for a plain handle: gridDim.y == 1).
+template <typename T> __device__ __forceinline__ T *batch_ptr(T *p, uint64_t stride_bytes) {
+    return reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(const_cast<typename std::remove_const<T>::type *>(p)) +
+                                 (uint64_t)blockIdx.y * stride_bytes);
+}
+
 __host__ __device__ __forceinline__ uint64_t insert_zero(uint64_t x, int pos) {
     const uint64_t lo = x & ((1ull << pos) - 1ull);
     return ((x >> pos) << (pos + 1)) | lo;
@@ -101,6 +110,7 @@ struct BlockArgs {
     int32_t n_members;
     int32_t ctrl_below_32;          // every index qubit of every member is below 32
     uint64_t rank_bits;             // rank << n_local
+    uint64_t bstate, btab;          // batch strides in BYTES: state, tables (real type)
     MemberDesc mem[QCM_MAX_MEMBERS];
 };
 
@@ -145,8 +155,9 @@ __global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ Bloc
     constexpr int NR = 1 << M;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tab = reinterpret_cast<R *>(smem_raw);
+    void *const state = batch_ptr(a.state, a.bstate);
     for (int g = 0; g < a.n_members; ++g) {
-        const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
+        const R *src = reinterpret_cast<const R *>(batch_ptr(a.tables, a.btab)) + a.mem[g].src_off;
         R *dst = tab + a.mem[g].tab_off;
         const int cnt = (a.mem[g].pos < 0 ? 2 : 8) << a.mem[g].n_ctrl;
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ Bloc
 #pragma unroll
                     for (int j = 0; j < M; ++j)
                         if ((r >> j) & 1) off += toff[j];
-                    IO::load(a.state, off, ar[u][r], ai[u][r]);
+                    IO::load(state, off, ar[u][r], ai[u][r]);
                 } else {
 #pragma unroll
                     for (int v = 0; v < V; ++v) { ar[u][r][v] = R(0); ai[u][r][v] = R(0); }
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) k_block(const __grid_constant__ Bloc
 #pragma unroll
                 for (int j = 0; j < M; ++j)
                     if ((r >> j) & 1) off += toff[j];
-                IO::store(a.state, off, ar[u][r], ai[u][r]);
+                IO::store(state, off, ar[u][r], ai[u][r]);
             }
         }
     }
@@ -296,6 +307,7 @@ struct LowqArgs {
     int32_t n_members;
     int32_t th[kLowqMaxHigh];       // high targets, ascending (>= LB)
     uint64_t rank_bits;
+    uint64_t bstate, btab;          // batch strides in bytes
     LowqMember mem[QCM_MAX_MEMBERS];
 };
 
@@ -309,8 +321,9 @@ __global__ void __launch_bounds__(kThreads) k_lowq(const __grid_constant__ LowqA
     using IO = VecIO<R, V>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tab = reinterpret_cast<R *>(smem_raw);
+    void *const state = batch_ptr(a.state, a.bstate);
     for (int g = 0; g < a.n_members; ++g) {
-        const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
+        const R *src = reinterpret_cast<const R *>(batch_ptr(a.tables, a.btab)) + a.mem[g].src_off;
         R *dst = tab + a.mem[g].tab_off;
         const int cnt = (a.mem[g].pos < 0 ? 2 : 8) << a.mem[g].n_ctrl;
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
@@ -333,7 +346,7 @@ __global__ void __launch_bounds__(kThreads) k_lowq(const __grid_constant__ LowqA
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
                 R tr[V], ti[V];
-                IO::load(a.state, hb + ((uint64_t)u * 32 + lane) * V, tr, ti);
+                IO::load(state, hb + ((uint64_t)u * 32 + lane) * V, tr, ti);
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     xr[v | (u << VB) | (h << (VB + UB))] = tr[v];
@@ -434,7 +447,7 @@ __global__ void __launch_bounds__(kThreads) k_lowq(const __grid_constant__ LowqA
                     tr[v] = xr[v | (u << VB) | (h << (VB + UB))];
                     ti[v] = xi[v | (u << VB) | (h << (VB + UB))];
                 }
-                IO::store(a.state, hb + ((uint64_t)u * 32 + lane) * V, tr, ti);
+                IO::store(state, hb + ((uint64_t)u * 32 + lane) * V, tr, ti);
             }
         }
     }
@@ -725,6 +738,7 @@ struct ExpandArgs {
                                         // sampler's level-0 sums); requires blockDim.x * V == 2^kChunkBits
     double *sub_out;                    // with tree_out: the per-warp sums (32*V amplitudes each), a finer level the
                                         // sampler uses to avoid scanning a whole chunk times 2^M branches
+    uint64_t bstate, bctab;             // batch strides in bytes: state, combined table (tree_out is not batched)
 };
 
 struct ExpandTableArgs {
@@ -736,6 +750,7 @@ struct ExpandTableArgs {
     int8_t mbit[QCM_MAX_MEMBERS][QCM_MAX_CTRL];     // member index bit j <-> cidx bit mbit[g][j]
     int64_t moff[QCM_MAX_MEMBERS];
     unsigned long long *tile_counter;   // reset to 0 here for the pass that follows
+    uint64_t btab64, bctab;             // batch strides in bytes: fp64 tables, combined table
 };
 
 static __global__ void k_expand_table(const __grid_constant__ ExpandTableArgs a) {
@@ -743,6 +758,8 @@ static __global__ void k_expand_table(const __grid_constant__ ExpandTableArgs a)
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e == 0 && a.tile_counter) *a.tile_counter = 0ull;
     if (e >= n) return;
+    const double *const tables = batch_ptr(a.tables, a.btab64);
+    void *const ctab = batch_ptr(a.ctab, a.bctab);
     const uint32_t cidx = e & ((1u << a.nu) - 1u), r = e >> a.nu;
     double re = 1.0, im = 0.0;
     for (int g = 0; g < a.n_members; ++g) {
@@ -750,19 +767,19 @@ static __global__ void k_expand_table(const __grid_constant__ ExpandTableArgs a)
         for (int j = 0; j < a.mnc[g]; ++j) idx |= ((cidx >> a.mbit[g][j]) & 1u) << j;
         double fr, fi;
         if (a.mpos[g] < 0) {
-            fr = a.tables[a.moff[g] + 2 * idx];
-            fi = a.tables[a.moff[g] + 2 * idx + 1];
+            fr = tables[a.moff[g] + 2 * idx];
+            fi = tables[a.moff[g] + 2 * idx + 1];
         } else {
             const int bit = (r >> a.mpos[g]) & 1u;                  // column 0 of the 2x2: m00 / m10
-            fr = a.tables[a.moff[g] + 8 * idx + 4 * bit];
-            fi = a.tables[a.moff[g] + 8 * idx + 4 * bit + 1];
+            fr = tables[a.moff[g] + 8 * idx + 4 * bit];
+            fi = tables[a.moff[g] + 8 * idx + 4 * bit + 1];
         }
         const double nr = re * fr - im * fi;
         im = re * fi + im * fr;
         re = nr;
     }
-    if (a.is_double) reinterpret_cast<double2 *>(a.ctab)[e] = make_double2(re, im);
-    else reinterpret_cast<float2 *>(a.ctab)[e] = make_float2((float)re, (float)im);
+    if (a.is_double) reinterpret_cast<double2 *>(ctab)[e] = make_double2(re, im);
+    else reinterpret_cast<float2 *>(ctab)[e] = make_float2((float)re, (float)im);
 }
 
 // Q0: qubit 0 is an index qubit; the host puts it at cidx bit 0, so the coefficients of the two
@@ -774,8 +791,9 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
     using C2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C2 *tab = reinterpret_cast<C2 *>(smem_raw);
+    void *const state = batch_ptr(a.state, a.bstate);
     {
-        const C2 *src = reinterpret_cast<const C2 *>(a.ctab);
+        const C2 *src = reinterpret_cast<const C2 *>(batch_ptr(a.ctab, a.bctab));
         for (int i = threadIdx.x; i < (NR << a.nu); i += blockDim.x) tab[i] = src[i];
     }
     __syncthreads();
@@ -805,7 +823,7 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
         for (int u = 0; u < U; ++u) {
             const uint64_t bv = bv0 + (uint64_t)u * blockDim.x;
             ok[u] = bv < nvec;
-            if (ok[u]) IO::load(a.state, bv * V, xr[u], xi[u]);
+            if (ok[u]) IO::load(state, bv * V, xr[u], xi[u]);
         }
         if (a.tree_out) {
             // level-0 sums of the sampler's tree over the INPUT (sum_a |out[x,a]|^2 = |in[x]|^2): sub-tile
@@ -863,7 +881,7 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand(const __grid_const
                     orr[1] = c1.x * xr[u][1] - c1.y * xi[u][1];
                     oi[1] = c1.x * xi[u][1] + c1.y * xr[u][1];
                 }
-                IO::store(a.state, b + (uint64_t)r * ostride, orr, oi);
+                IO::store(state, b + (uint64_t)r * ostride, orr, oi);
             }
         }
     }
@@ -901,6 +919,7 @@ struct ExpandTreeArgs {
     uint64_t rank_bits;
     double *tree_out;               // see ExpandArgs
     double *sub_out;                // per-vector |in|^2 sums (the sampler's finest level)
+    uint64_t bstate, btab;          // batch strides in bytes (k_expand_tree; the rotated pass is never batched)
     TreeMember mem[QCM_MAX_EXPAND]; // member j targets qubit n_in + j
     TreeMember diag[4];
 };
@@ -939,7 +958,8 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand_tree(const __grid_
     using IO = VecIO<R, V>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tab = reinterpret_cast<R *>(smem_raw);
-    const R *gt = reinterpret_cast<const R *>(a.tables);
+    void *const state = batch_ptr(a.state, a.bstate);
+    const R *gt = reinterpret_cast<const R *>(batch_ptr(a.tables, a.btab));
     for (int j = 0; j < a.M; ++j) {                       // column 0 of every 2x2: (m00, m10)
         const int n = 1 << a.mem[j].n_ctrl;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -976,7 +996,7 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand_tree(const __grid_
         R xr[V], xi[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) { xr[v] = R(0); xi[v] = R(0); }
-        if (ok) IO::load(a.state, b, xr, xi);
+        if (ok) IO::load(state, b, xr, xi);
         if (a.tree_out) {
             __shared__ double s_w[32];
             double w = 0.0;
@@ -1045,7 +1065,7 @@ __global__ void __launch_bounds__(kExpandThreadsMax) k_expand_tree(const __grid_
                     }
                 }
             }
-            TreeEmit<R, V, kTreeLow>::run(a.state, b + ((uint64_t)rh << (a.n_in + kTreeLow)), ostride, pr, pi, fr, fi, 0u);
+            TreeEmit<R, V, kTreeLow>::run(state, b + ((uint64_t)rh << (a.n_in + kTreeLow)), ostride, pr, pi, fr, fi, 0u);
         }
     }
 }
@@ -1259,14 +1279,16 @@ struct DiagArgs {
     int32_t n_active;
     int8_t ctrl[QCM_MAX_CTRL];
     uint64_t rank_bits;
+    uint64_t bstate, btab;          // batch strides in bytes
 };
 
 template <typename R, int V, int U>
 __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tab = reinterpret_cast<R *>(smem_raw);
+    void *const state = batch_ptr(a.state, a.bstate);
     {
-        const R *g = reinterpret_cast<const R *>(a.table);
+        const R *g = reinterpret_cast<const R *>(batch_ptr(a.table, a.btab));
         for (int i = threadIdx.x; i < (2 << a.n_ctrl); i += blockDim.x) tab[i] = g[i];
     }
     __syncthreads();
@@ -1278,7 +1300,7 @@ __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagA
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
-            if (vi < nvec) IO::load(a.state, vi * V, re[u], im[u]);
+            if (vi < nvec) IO::load(state, vi * V, re[u], im[u]);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -1294,7 +1316,7 @@ __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagA
                 re[u][v] = c * x - s * y;
                 im[u][v] = c * y + s * x;
             }
-            IO::store(a.state, vi * V, re[u], im[u]);
+            IO::store(state, vi * V, re[u], im[u]);
         }
     }
 }
@@ -1306,7 +1328,11 @@ __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagA
 // lo is stored in the state's real type (a lane's vector of V amplitudes is then ONE 128-bit load of
 // V adjacent lo entries, so the factor tables cost no more L2 traffic than the state costs HBM traffic);
 // hi stays fp64: it is warp-uniform and read once per thread.
-static __global__ void k_init_tables(const double *qv /* n*4 */, int n, int L, void *lo, double2 *hi, int lo_is_float) {
+static __global__ void k_init_tables(const double *qv /* n*4 */, int n, int L, void *lo, double2 *hi, int lo_is_float,
+                                     uint64_t bqv, uint64_t blo, uint64_t bhi /* batch strides, bytes */) {
+    qv = batch_ptr(qv, bqv);
+    lo = batch_ptr(lo, blo);
+    hi = batch_ptr(hi, bhi);
     const uint64_t nlo = 1ull << L, nhi = 1ull << (n - L);
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nlo + nhi) return;
@@ -1329,8 +1355,12 @@ static __global__ void k_init_tables(const double *qv /* n*4 */, int n, int L, v
 constexpr int kInitU = 8;                       // vectors per thread: a CTA writes 32 KiB (c64), in address order
 
 template <typename R, int V>
-__global__ void __launch_bounds__(kThreads) k_init(void *state, const void *lo, const double2 *hi, int n, int L) {
+__global__ void __launch_bounds__(kThreads) k_init(void *state, const void *lo, const double2 *hi, int n, int L,
+                                                   uint64_t bstate, uint64_t blo, uint64_t bhi) {
     using IO = VecIO<R, V>;
+    state = batch_ptr(state, bstate);
+    lo = batch_ptr(lo, blo);
+    hi = batch_ptr(hi, bhi);
     const uint64_t nvec = (1ull << n) / V;
     const uint64_t lmask = (1ull << L) - 1ull;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kInitU;
@@ -1361,7 +1391,8 @@ __global__ void __launch_bounds__(kThreads) k_init(void *state, const void *lo, 
 
 // zero-fill amplitudes [first, first+count)
 template <typename R>
-__global__ void __launch_bounds__(kThreads) k_zero(void *state, uint64_t first, uint64_t count) {
+__global__ void __launch_bounds__(kThreads) k_zero(void *state, uint64_t first, uint64_t count, uint64_t bstate) {
+    state = batch_ptr(state, bstate);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kInitU;
     for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * kInitU + threadIdx.x; i0 < count; i0 += stride) {
 #pragma unroll
@@ -1378,8 +1409,9 @@ __global__ void __launch_bounds__(kThreads) k_zero(void *state, uint64_t first, 
 // Qubit exchange (local): amplitudes with (bit a, bit b) = (1,0) <-> (0,1), a < b.
 // ----------------------------------------------------------------------------------
 template <typename R, int V>
-__global__ void __launch_bounds__(kThreads) k_swap(void *state, int qa, int qb, int n_active) {
+__global__ void __launch_bounds__(kThreads) k_swap(void *state, int qa, int qb, int n_active, uint64_t bstate) {
     using IO = VecIO<R, V>;
+    state = batch_ptr(state, bstate);
     const uint64_t nvec = (1ull << (n_active - 2)) / V;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t vi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
@@ -1401,7 +1433,9 @@ __global__ void __launch_bounds__(kThreads) k_swap(void *state, int qa, int qb, 
 // level 0: chunk c = sum_{i in chunk} |amp_i|^2 ; one warp per chunk.  Full-size chunks
 // stream 128-bit loads, eight in flight per lane; the lane-strided order is fixed.
 template <typename R>
-__global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int n_active, double *out) {
+__global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int n_active, double *out, uint64_t bstate, uint64_t bout) {
+    state = batch_ptr(state, bstate);
+    out = batch_ptr(out, bout);
     const int cb = n_active < kChunkBits ? n_active : kChunkBits;
     const uint64_t nchunks = 1ull << (n_active - cb);
     const uint64_t csz = 1ull << cb;
@@ -1456,7 +1490,10 @@ __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int 
 }
 
 // level l+1: node j = sum of up to 1024 children ; one warp per node
-static __global__ void __launch_bounds__(kThreads) k_tree_level(const double *in, uint64_t n_in, double *out, uint64_t n_out) {
+static __global__ void __launch_bounds__(kThreads) k_tree_level(const double *in, uint64_t n_in, double *out, uint64_t n_out,
+                                                                uint64_t bin = 0, uint64_t bout = 0) {
+    in = batch_ptr(in, bin);
+    out = batch_ptr(out, bout);
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1562,6 +1599,11 @@ struct SampleArgs {
     int8_t clbit_qubit[64];
     uint64_t *keys_out;
     uint8_t *mine_out;              // may be null
+    // batch (blockIdx.y = sweep point): strides in bytes of the state, the tree arrays and the keys; per-point
+    // Philox streams and total masses (device arrays; null for a plain handle)
+    uint64_t bstate, btree, bkeys;
+    const uint64_t *streams;
+    const double *totals;
 };
 
 template <typename R>
@@ -1570,18 +1612,22 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const int cb = a.n_active < kChunkBits ? a.n_active : kChunkBits;
+    const void *const state = batch_ptr(a.state, a.bstate);
+    uint64_t *const keys_out = batch_ptr(a.keys_out, a.bkeys);
+    const uint64_t stream = a.streams ? a.streams[blockIdx.y] : a.stream;
+    const double total = a.totals ? a.totals[blockIdx.y] : a.total;
     for (uint64_t s = warp0; s < a.shots; s += nwarps) {
-        double u = philox_uniform(a.seed, a.stream, s) * a.total;
+        double u = philox_uniform(a.seed, stream, s) * total;
         const bool mine = (u >= a.rank_lo) && (u < a.rank_hi);
         if (a.mine_out && lane == 0) a.mine_out[s] = mine ? 1 : 0;
         if (!mine) {
-            if (lane == 0) a.keys_out[s] = 0;
+            if (lane == 0) keys_out[s] = 0;
             continue;
         }
         u -= a.rank_lo;
         uint64_t node = 0;
         for (int l = a.n_levels - 1; l >= 0; --l) {
-            const double *lv = a.level[l];
+            const double *lv = batch_ptr(a.level[l], a.btree);
             const uint64_t first = node << kFanBits;
             const uint64_t left = a.level_n[l] - first;
             const uint32_t cnt = left < (1ull << kFanBits) ? (uint32_t)left : (1u << kFanBits);
@@ -1593,7 +1639,7 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
         uint32_t leaf_cnt = 1u << cb;
         if (a.sub) {
             const uint32_t nsub = 1u << (cb - a.sub_bits);
-            const double *sp = a.sub + (node << (cb - a.sub_bits));
+            const double *sp = a.sub + (node << (cb - a.sub_bits));      // (fused checkpoint only: never batched)
             const uint32_t c = warp_pick([&](uint32_t i) { return sp[i]; }, nsub, u, lane);
             afirst += (uint64_t)c << a.sub_bits;
             leaf_cnt = 1u << a.sub_bits;
@@ -1601,10 +1647,10 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
         const int nb = 1 << a.cond_bits;
         auto amp_w = [&](uint64_t i) -> double {
             if constexpr (sizeof(R) == 4) {
-                const float2 t = reinterpret_cast<const float2 *>(a.state)[i];
+                const float2 t = reinterpret_cast<const float2 *>(state)[i];
                 return (double)t.x * (double)t.x + (double)t.y * (double)t.y;
             } else {
-                const double2 t = reinterpret_cast<const double2 *>(a.state)[i];
+                const double2 t = reinterpret_cast<const double2 *>(state)[i];
                 return t.x * t.x + t.y * t.y;
             }
         };
@@ -1635,9 +1681,19 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
                     if (q >= 0) key |= ((gi >> q) & 1ull) << c;
                 }
             }
-            a.keys_out[s] = key;
+            keys_out[s] = key;
         }
     }
+}
+
+// total[y] = sum of the top tree level of sweep point y, in index order (one thread per point)
+static __global__ void k_batch_totals(const double *top, uint64_t n_top, uint64_t btree, double *totals, int batch) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= batch) return;
+    const double *p = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(top) + (uint64_t)y * btree);
+    double t = 0.0;
+    for (uint64_t i = 0; i < n_top; ++i) t += p[i];
+    totals[y] = t;
 }
 
 // ----------------------------------------------------------------------------------
@@ -1660,12 +1716,17 @@ struct ReleasedArgs {
     int8_t ctrl[kMaxReleased][QCM_MAX_CTRL];
     int8_t vclbit[kMaxReleased];    // clbit of released qubit k, or -1
     int8_t clbit_pos[64];           // physical position feeding clbit c, or -1
+    uint64_t bkeys, bp1;            // batch strides in bytes (keys, p1 tables); per-point Philox streams (or null)
+    const uint64_t *streams;
 };
 
 static __global__ void __launch_bounds__(kThreads) k_released_keys(const __grid_constant__ ReleasedArgs a) {
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.shots) return;
-    const uint64_t r = a.keys[s];
+    uint64_t *const keys = batch_ptr(a.keys, a.bkeys);
+    const double *const p1 = batch_ptr(a.p1, a.bp1);
+    const uint64_t stream = a.streams ? a.streams[blockIdx.y] : a.stream;
+    const uint64_t r = keys[s];
     uint64_t key = 0;
     for (int c = 0; c < a.n_clbits; ++c) {
         const int p = a.clbit_pos[c];
@@ -1675,10 +1736,10 @@ static __global__ void __launch_bounds__(kThreads) k_released_keys(const __grid_
         if (a.vclbit[k] < 0) continue;
         uint32_t idx = 0;
         for (int j = 0; j < a.n_ctrl[k]; ++j) idx |= (uint32_t)((r >> a.ctrl[k][j]) & 1ull) << j;
-        const double u = philox_uniform(a.seed ^ kReleasedKey, a.stream, s * (uint64_t)a.nv + (uint64_t)k);
-        if (u < a.p1[a.p1_off[k] + idx]) key |= 1ull << a.vclbit[k];
+        const double u = philox_uniform(a.seed ^ kReleasedKey, stream, s * (uint64_t)a.nv + (uint64_t)k);
+        if (u < p1[a.p1_off[k] + idx]) key |= 1ull << a.vclbit[k];
     }
-    a.keys[s] = key;
+    keys[s] = key;
 }
 
 // ----------------------------------------------------------------------------------
@@ -1687,8 +1748,12 @@ static __global__ void __launch_bounds__(kThreads) k_released_keys(const __grid_
 // contiguous kept set (QCMRF: the first 2^n amplitudes): probs[i] = |amp_i|^2 and a
 // deterministic two-stage sum (per-block partials, then k_tree_level).
 template <typename R>
-__global__ void __launch_bounds__(kThreads) k_probs_prefix(const void *state, uint64_t count, int shift, double *probs, double *partial) {
+__global__ void __launch_bounds__(kThreads) k_probs_prefix(const void *state, uint64_t count, int shift, double *probs, double *partial,
+                                                           uint64_t bstate = 0, uint64_t bprobs = 0, uint64_t bpartial = 0) {
     __shared__ double wsum[kThreads / 32];
+    state = batch_ptr(state, bstate);
+    if (probs) probs = batch_ptr(probs, bprobs);
+    partial = batch_ptr(partial, bpartial);
     double acc = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
@@ -1717,8 +1782,12 @@ __global__ void __launch_bounds__(kThreads) k_probs_prefix(const void *state, ui
 template <typename R>
 __global__ void __launch_bounds__(kThreads) k_postselect_general(const void *state, int n_active, uint64_t rank_bits,
                                                                   uint64_t mask, uint64_t value, uint64_t out_mask,
-                                                                  int rot_m, int rot_nin, double *probs, double *partial) {
+                                                                  int rot_m, int rot_nin, double *probs, double *partial,
+                                                                  uint64_t bstate = 0, uint64_t bprobs = 0, uint64_t bpartial = 0) {
     __shared__ double wsum[kThreads / 32];
+    state = batch_ptr(state, bstate);
+    if (probs) probs = batch_ptr(probs, bprobs);
+    partial = batch_ptr(partial, bpartial);
     double acc = 0.0;
     const uint64_t count = 1ull << n_active;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

@@ -56,8 +56,16 @@ class Handle:
     """numpy stand-in for _native.Handle.  With ``ext_state_ptr`` the state aliases caller memory
     (a torch CPU tensor in the gloo tests), as the real handle aliases a torch CUDA tensor."""
 
-    def __init__(self, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None):
+    def __new__(cls, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None, batch=1):
+        if batch > 1 and cls is Handle:
+            return object.__new__(BatchedHandle)
+        return object.__new__(cls)
+
+    def __init__(self, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None, batch=1):
         import ctypes
+        self.batch = 1
+        self.generation = 0
+        self._h = True
         self.n_local = n_local
         self.cdtype = np.complex64 if precision in ('single', 'c64', 32) else np.complex128
         self.ext = None
@@ -156,7 +164,68 @@ class Handle:
                     bytes_written=0)
 
     def close(self):
-        pass
+        self._h = None
+
+
+class BatchedHandle(Handle):
+    """numpy stand-in for a batched handle (qcm_create_batched): `batch` independent states, shared ops,
+    per-point tables as rows."""
+
+    def __init__(self, n_local, precision='single', device=0, ext_state_ptr=None, ext_stream=None, batch=1):
+        self.batch = batch
+        self.generation = 0
+        self._h = True
+        self.n_local = n_local
+        self.pts = [Handle(n_local, precision) for _ in range(batch)]
+        self._resident = None
+
+    def run_program(self, ops, tables):
+        tables = np.asarray(tables)
+        assert tables.ndim == 2 and tables.shape[0] == self.batch
+        for h, t in zip(self.pts, tables):
+            h.run_program(ops, t)
+
+    def postselect(self, mask, value, n_out_bits, want_probs=True):
+        self.generation += 1
+        got = [h.postselect(mask, value, n_out_bits) for h in self.pts]
+        return (np.stack([g[0] for g in got]) if want_probs else None), np.array([g[1] for g in got])
+
+    def postselect_resident(self, mask, value, n_out_bits):
+        probs, kept = self.postselect(mask, value, n_out_bits)
+        self._resident = probs
+        return kept
+
+    def fetch_probs(self, point, n_out_bits, first=0, count=None):
+        return self._resident[point][first:None if count is None else first + count].copy()
+
+    def sample_batched(self, shots, seed, stream_ids, clbit_qubit=None):
+        return np.stack([h.sample(shots, seed, int(sid), clbit_qubit) for h, sid in zip(self.pts, stream_ids)])
+
+    def sample_released_batched(self, shots, seed, stream_ids, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_clbits):
+        out = np.zeros((self.batch, shots), dtype=np.uint64)
+        for y, (h, sid) in enumerate(zip(self.pts, stream_ids)):
+            raw = h.sample(shots, seed, int(sid), None).astype(np.int64)
+            rng = np.random.default_rng([seed & 0xffffffff, int(sid), 7])
+            keys = np.zeros(shots, dtype=np.uint64)
+            for c in range(n_clbits):
+                if clbit_pos[c] >= 0:
+                    keys |= ((raw >> int(clbit_pos[c])) & 1).astype(np.uint64) << np.uint64(c)
+            for k in range(len(n_ctrl)):
+                if vclbit[k] < 0:
+                    continue
+                idx = np.zeros(shots, dtype=np.int64)
+                for j in range(int(n_ctrl[k])):
+                    idx |= ((raw >> int(ctrl[k, j])) & 1) << j
+                bit = rng.random(shots) < p1[y][int(p1_off[k]) + idx]
+                keys |= bit.astype(np.uint64) << np.uint64(int(vclbit[k]))
+            out[y] = keys
+        return out
+
+    def timing(self):
+        return dict(program_ms=0.0, sample_ms=0.0, postselect_ms=0.0, kernel_launches=0, bytes_read=0, bytes_written=0)
+
+    def close(self):
+        self._h = None
 
 
 def install(monkeypatch):

@@ -216,3 +216,45 @@ def test_native_counts_formatter_equals_numpy():
         b = _keys_to_counts(keys, width, use_native=False)
         assert type(a) is type(b) and list(a.items()) == list(b.items())
         assert sum(a.values()) == n and all(len(k) == width for k in a)
+
+
+def test_sweep_grouping_through_a_batched_handle(monkeypatch):
+    """A list of same-structure circuits (a beta sweep) goes through ONE batched handle: results equal the
+    one-by-one path, the post-selected vectors stay "on the device" until asked for, mixed lists still work."""
+    import fake_native
+    from oracle import mrf
+    from qcmrf_b200 import B200Simulator
+    from qcmrf_b200.backend import _ResidentProbs
+    fake_native.install(monkeypatch)
+    monkeypatch.setattr(fake_native, 'small_max_qubits', lambda precision='double': 4)
+    import qcmrf_b200._native as nat
+    monkeypatch.setattr(nat, 'small_max_qubits', lambda precision='double': 4)
+    C = [[0, 1], [1, 2], [2, 3]]
+    rng = np.random.RandomState(5)
+    th = list(-np.abs(rng.randn(12)) * 0.5)
+    betas = [0.25, 0.5, 1.0, 2.0, 3.0]
+    other = QCMRF([[0, 1, 2], [2, 3]], list(-np.abs(rng.randn(12))))
+    for width in ('release', 'full'):
+        sim = B200Simulator(precision='double', width=width, seed=3, small_batch=False)
+        circs = [QCMRF(C, th, beta=b) for b in betas] + [other]
+        res = sim.run(circs, shots=2000).result()
+        assert [res.metadata(i)['path'] for i in range(6)] == ['sweep'] * 5 + ['statevector']
+        assert isinstance(res.results()[0]['probs'], _ResidentProbs)
+        for i, b in enumerate(betas):
+            p, d = res.postselected_probabilities(i)
+            pb, db, _ = mrf.brute_force_pmf(C, th, beta=b)
+            assert np.abs(p - pb).max() < 1e-12 and abs(d - db) < 1e-12
+            counts = res.get_counts(i)
+            assert sum(counts.values()) == 2000 and all(len(k) == 8 and k[8 - 1 - 4] == '0' for k in counts)
+        p, d = res.postselected_probabilities(5)
+        pb, db, _ = mrf.brute_force_pmf([[0, 1, 2], [2, 3]], other.theta)
+        assert np.abs(p - pb).max() < 1e-12
+        # pmf=True copies everything, pmf=False computes delta only; chunks of 2 + 3 points
+        sim.sweep_bytes = 2 * (16 << res.metadata(0)['n_phys'])
+        res2 = sim.run(circs[:5], shots=0, pmf=True).result()
+        assert all(isinstance(e['probs'], np.ndarray) for e in res2.results())
+        assert sorted(e['meta']['sweep_points'] for e in res2.results()) == [2, 2, 3, 3, 3]
+        for i, b in enumerate(betas):
+            pb, db, _ = mrf.brute_force_pmf(C, th, beta=b)
+            assert np.abs(res2.postselected_probabilities(i)[0] - pb).max() < 1e-12
+        sim.close()

@@ -301,6 +301,92 @@ def test_low_order_target_pass(precision, N):
 
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('N', [3, 9, 12, 15])
+def test_batched_handle_random_programs(precision, N):
+    """qcm_create_batched: B states in one allocation, every kernel launched once with the sweep point as the
+    second grid dimension, shared ops and per-point coefficient tables -- every point must equal the numpy
+    statement of the op semantics run on its own tables (tables need not be unitary for that)."""
+    rng = np.random.RandomState(4000 + N)
+    B = 5
+    with _native.Handle(N, precision, batch=B) as h:
+        for trial in range(4):
+            ops, tabs = _random_program(rng, N, 10)
+            rows = [tabs] + [tabs * (1.0 + 0.3 * rng.standard_normal(tabs.shape)) for _ in range(B - 1)]
+            h.run_program(ops, np.stack(rows))
+            for y in range(B):
+                pl = _P()
+                pl.ops, pl.tables, pl.n_phys = ops, rows[y], N
+                want, act = em.run_plan(pl)
+                h.batch_select(y)
+                got = h.get_amplitudes().astype(np.complex128)
+                scale = max(np.abs(want).max(), 1e-30)
+                assert np.abs(got - want).max() / scale < (1e-11 if precision == 'double' else 2e-5), (trial, y)
+            # post-selection and sampling per point: mask on the two highest qubits, raw indices
+            if N >= 3:
+                mask = 0b11 << (N - 2)
+                probs, kept = h.postselect(mask, 0, N - 2)
+                keys = h.sample_batched(512, 11, np.arange(B) + 3)
+                for y in range(B):
+                    pl = _P()
+                    pl.ops, pl.tables, pl.n_phys = ops, rows[y], N
+                    want, act = em.run_plan(pl)
+                    w = np.abs(want) ** 2
+                    assert np.allclose(probs[y], w[: 1 << (N - 2)], rtol=1e-9 if precision == 'double' else 2e-4, atol=1e-300)
+                    assert abs(kept[y] - w[: 1 << (N - 2)].sum()) <= (1e-9 if precision == 'double' else 2e-4) * w.sum()
+                    assert (w[keys[y].astype(np.int64)] > 0).all()
+                kept2 = h.postselect_resident(mask, 0, N - 2)
+                assert np.array_equal(kept2, kept)
+                assert np.array_equal(h.fetch_probs(B - 1, N - 2), probs[B - 1])
+
+
+@pytest.mark.parametrize('width', ['release', 'full'])
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_beta_sweep_through_one_batched_handle(width, precision):
+    """BASELINE config 3 in small: a chain MRF swept over beta (QCMRF.py:21,154) -- the list goes through ONE batched
+    handle (O(10) launches for the sweep); every point against brute force, shots through the per-clique marginals,
+    and (release width) bit-identical keys to the one-circuit-at-a-time path."""
+    from qcmrf_b200 import workloads
+    n = 12 if width == 'release' else 8                          # N = 24 / 16 qubits at Aer width
+    C = workloads.chain(n)
+    th = workloads.theta_for(C, seed=9)
+    betas = [(j + 1) / 4.0 for j in range(7)]
+    shots = 20000
+    sim = B200Simulator(precision=precision, width=width, seed=21, small_batch=False)
+    one = B200Simulator(precision=precision, width=width, seed=21, small_batch=False, sweep_batch=False)
+    l0 = sim.kernel_launches()
+    res = sim.run([QCMRF(C, th, beta=b) for b in betas], shots=shots).result()
+    launches = sim.kernel_launches() - l0
+    assert all(res.metadata(i)['path'] == 'sweep' for i in range(len(betas)))
+    assert launches <= 24, launches                              # not O(points)
+    for i, b in enumerate(betas):
+        pb, db, _ = mrf.brute_force_pmf(C, th, beta=b)
+        p, d = res.postselected_probabilities(i)
+        assert_pmf(p, pb, d, db, precision, (width, b))
+        counts = res.get_counts(i)
+        assert sum(counts.values()) == shots
+        # per-clique (x_C, ancilla) marginals of the sampled keys vs the exact law (bench.shot_marginal_tv's statistic)
+        keys = np.array([int(k, 2) for k in counts], dtype=np.uint64)
+        cnt = np.array(list(counts.values()), dtype=np.float64)
+        assert not ((keys >> np.uint64(n)) & np.uint64(1)).any()
+        for ii, cl in enumerate(C):
+            y = np.zeros(len(keys), dtype=np.int64)
+            for v in cl:
+                y = (y << 1) | ((keys >> np.uint64(n - 1 - v)) & np.uint64(1)).astype(np.int64)
+            a = ((keys >> np.uint64(n + 1 + ii)) & np.uint64(1)).astype(np.int64)
+            obs = np.bincount(y + (a << 2), weights=cnt, minlength=8) / shots
+            w = np.exp(b * np.asarray(th[4 * ii:4 * ii + 4]))
+            exact = np.concatenate([w, 1.0 - w]) / 4
+            assert 0.5 * np.abs(obs - exact).sum() < weissman_tv_bound(8, shots, 1e-6 / (len(C) * len(betas)))
+        if width == 'release' and i in (0, 3):
+            r1 = one.run(QCMRF(C, th, beta=b), shots=shots, stream_ids=[i]).result()
+            assert r1.metadata(0)['path'] == 'statevector'
+            assert r1.get_counts(0) == counts
+            assert np.array_equal(r1.postselected_probabilities(0)[0], p)
+    sim.close()
+    one.close()
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
 def test_lazy_materialisation_ops(precision):
     """Ops that materialise qubits: zero-input targets are never read (the buffer holds NaN
     there), EXTEND zero-fills, get_amplitudes reports implicit zeros."""
