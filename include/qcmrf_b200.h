@@ -73,7 +73,8 @@ enum qcm_op_kind {
      * block's qubits, pairwise distinct or repeated; or DIAG, a diagonal factor applied
      * in the same sweep; no member's index qubits among the block's targets) are
      * applied in ONE sweep, in order; `ctrl[0..target-1]` lists the block's `target`
-     * (= count) distinct target qubits in ascending order.                         */
+     * (= count) distinct target qubits in ascending order.  `target` == 0: a diagonal
+     * block -- every member is a DIAG and all of them are applied in one sweep.      */
     QCM_OP_BLOCK = 4,
     /* exchange qubits `target` and `ctrl[0]` (both local)                          */
     QCM_OP_SWAP = 5,

@@ -199,7 +199,8 @@ class Handle:
         if self.batch > 1:
             probs = np.empty((self.batch, 1 << n_out_bits), dtype=np.float64) if want_probs else None
             kept = np.empty(self.batch, dtype=np.float64)
-            self._check(lib().qcm_postselect(self._h, int(mask), int(value), int(n_out_bits), _ptr(probs), _ptr(kept)))
+            self._check(lib().qcm_postselect(self._h, int(mask), int(value), int(n_out_bits), _ptr(probs),
+                                             kept.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
             return probs, kept
         probs = np.empty(1 << n_out_bits, dtype=np.float64) if want_probs else None
         kept = ctypes.c_double()

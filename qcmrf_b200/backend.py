@@ -314,7 +314,10 @@ class B200Simulator:
             diag.append((ctrl, a0))
         em = fusion._Emitter()
         act = pl.final_active
-        for ctrl, tab in fusion.merge_diagonals(diag):
+        merged = fusion.merge_diagonals(diag)
+        if len(merged) > 1:                                   # one sweep for all of them: a BLOCK without targets
+            em.op(fusion.QCM_OP_BLOCK, target=0, ctrl=(), n_in=act, n_out=act, n_ctrl=len(merged))
+        for ctrl, tab in merged:
             em.op(fusion.QCM_OP_DIAG, ctrl=ctrl, n_in=act, n_out=act,
                   table_off=em.table(fusion._diag_table_f64(tab)))
         pr.proj = em.finish()

@@ -64,6 +64,7 @@ struct qcm_sim_s {
     int tree_cond_bits = 0;         // expansion qubits materialised after the tree was built
     int tree_sub_bits = 0;          // subtree holds sums over 2^tree_sub_bits amplitudes ...
     bool tree_has_sub = false;      // ... when this is set (fused checkpoint only)
+    bool tree_sub_strided = false;  // generic tree build: subtree holds k_chunk_sums' 32 lane partials per chunk
     uint64_t n_expand = 0, n_checkpoint = 0;
     double local_mass = 0.0;
     bool tree_valid = false;
@@ -669,6 +670,58 @@ int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
     return QCM_OK;
 }
 
+// BLOCK header with zero targets: every member is a DIAG, all applied in one sweep
+int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_active, size_t n_tables) {
+    if (n_mem < 1 || n_mem > QCM_MAX_MEMBERS) return fail(h, QCM_ERR_INVALID, "diagonal block with %d members (max %d)", n_mem, QCM_MAX_MEMBERS);
+    BlockArgs a{};
+    a.state = h->state;
+    a.tables = h->tab_real.p;
+    a.n_in = a.n_out = n_active;
+    a.n_members = n_mem;
+    a.rank_bits = rank_bits(h);
+    a.bstate = bstate(h);
+    a.btab = btab(h);
+    size_t reals = 0;
+    for (int g = 0; g < n_mem; ++g) {
+        const qcm_op &op = members[g];
+        if (op.kind != QCM_OP_DIAG) return fail(h, QCM_ERR_INVALID, "a BLOCK without targets may only hold DIAG members");
+        if (op.n_ctrl < 0 || op.n_ctrl > QCM_MAX_CTRL) return fail(h, QCM_ERR_INVALID, "DIAG: n_ctrl %d out of range", op.n_ctrl);
+        if (op.table_off < 0 || (size_t)op.table_off + (2ull << op.n_ctrl) > n_tables) return fail(h, QCM_ERR_INVALID, "DIAG: table outside tables");
+        a.mem[g].pos = -1;
+        a.mem[g].n_ctrl = (int8_t)op.n_ctrl;
+        a.mem[g].low_bit = 0;
+        for (int j = 0; j < op.n_ctrl; ++j) {
+            if (op.ctrl[j] < 0 || op.ctrl[j] >= h->n_local + h->n_global) return fail(h, QCM_ERR_INVALID, "DIAG: qubit %d out of range", op.ctrl[j]);
+            if (op.ctrl[j] == 0) a.mem[g].low_bit = (uint16_t)(1u << j);
+            a.mem[g].ctrl[j] = (int8_t)op.ctrl[j];
+        }
+        a.mem[g].src_off = (int32_t)op.table_off;
+        a.mem[g].tab_off = (int32_t)reals;
+        reals += ((2ull << op.n_ctrl) + 3) & ~size_t(3);
+    }
+    const size_t smem = reals * real_bytes(h);
+    if (smem > 200 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "diagonal block tables need %zu B of shared memory", smem);
+    h->cur_kernel = h->prec == QCM_C64 ? "k_diag_multi<float>" : "k_diag_multi<double>";
+    if (h->prec == QCM_C64 && n_active >= 1) {
+        auto k = k_diag_multi<float, 2, 4>;
+        if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, (1ull << n_active) / 2)), kThreads, smem, h->stream>>>(a);
+    } else if (h->prec == QCM_C64) {
+        auto k = k_diag_multi<float, 1, 4>;
+        if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<bgrid(h, 1), kThreads, smem, h->stream>>>(a);
+    } else {
+        auto k = k_diag_multi<double, 1, 4>;
+        if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, 1ull << n_active)), kThreads, smem, h->stream>>>(a);
+    }
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    h->timing.bytes_read += amp_bytes(h->prec) << n_active;
+    h->timing.bytes_written += amp_bytes(h->prec) << n_active;
+    return QCM_OK;
+}
+
 int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
     const int n = op.n_active_out;
     if (n < 0 || n > h->n_local) return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT over %d qubits (n_local %d)", n, h->n_local);
@@ -799,8 +852,18 @@ int tree_level0(qcm_handle h, int na) {
     const uint64_t n0 = h->tree_n[0];
     uint64_t blocks = std::min<uint64_t>((n0 + warps_per_block - 1) / warps_per_block, 0x7fffffffull);
     const uint64_t btree = h->tree_total * sizeof(double);
-    if (h->prec == QCM_C64) k_chunk_sums<float><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0], bstate(h), btree);
-    else k_chunk_sums<double><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0], bstate(h), btree);
+    // finer level (32 strided groups per chunk) while it stays small: 1/32 .. 1/64 of the state
+    double *sub = nullptr;
+    const uint64_t bsub = (sizeof(double) * 32) << (na - std::min(na, kChunkBits));
+    h->tree_sub_strided = false;
+    if (na >= kChunkBits && bsub * h->batch <= (512ull << 20) && ensure(h, h->subtree, bsub * h->batch) == QCM_OK) {
+        sub = (double *)h->subtree.p;
+        h->tree_sub_strided = true;
+    } else {
+        cudaGetLastError();
+    }
+    if (h->prec == QCM_C64) k_chunk_sums<float><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0], bstate(h), btree, sub, bsub);
+    else k_chunk_sums<double><<<bgrid(h, blocks), kThreads, 0, h->stream>>>(h->state, na, h->tree_ptr[0], bstate(h), btree, sub, bsub);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;
@@ -1249,6 +1312,14 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 if (op.kind == QCM_OP_MUX1Q) {
                     int tq[1] = {op.target};
                     if ((rc = plan_block(h, tq, 1, &op, 1, op.n_active_in, op.n_active_out, n_tables, bp))) return rc;
+                } else if (op.target == 0) {
+                    // no targets: a diagonal block (every member DIAG), one sweep for all of them
+                    n_mem = op.n_ctrl;
+                    if (n_mem < 0 || i + n_mem > n_ops - 1) return fail(h, QCM_ERR_INVALID, "op %d: block members run past the program", i);
+                    if (op.n_active_in != op.n_active_out) return fail(h, QCM_ERR_INVALID, "op %d: a diagonal block cannot materialise qubits", i);
+                    if ((rc = launch_diag_multi(h, ops + i + 1, n_mem, op.n_active_in, n_tables))) return rc;
+                    i += n_mem;
+                    break;
                 } else {
                     const int M = op.target;
                     n_mem = op.n_ctrl;
@@ -1295,6 +1366,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 if ((rc = launch_block_plan(h, bp))) return rc;
                 if (checkpoint) {
                     if ((rc = tree_finish(h, op.n_active_in))) return rc;
+                    h->tree_sub_strided = false;
                     h->tree_cond_bits = bp.M;
                     h->tree_cond_low = bp.rotate;
                     h->tree_sub_bits = sub_bits;
@@ -1478,7 +1550,7 @@ static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_ou
         h->timing.kernel_launches++;
         // per-point kept mass: the block partials summed in index order, written behind them
         k_tree_level<<<bgrid(h, 1), kThreads, 0, h->stream>>>((const double *)h->partial.p, (uint64_t)blocks,
-                                                              dev ? kept_out : (double *)h->partial.p + blocks, 1, bpart, dev ? 0 : bpart);
+                                                              dev ? kept_out : (double *)h->partial.p + blocks, 1, bpart, dev ? 0 : bpart, 30);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
         if (!dev) {
@@ -1556,8 +1628,10 @@ static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint
     a.cond_low = (h->tree_cond_bits && h->tree_cond_low) ? 1 : 0;
     a.rot_m = h->rot_m;
     a.rot_nin = h->rot_nin;
-    a.sub = h->tree_has_sub ? (const double *)h->subtree.p : nullptr;
+    a.sub = (h->tree_has_sub || h->tree_sub_strided) ? (const double *)h->subtree.p : nullptr;
     a.sub_bits = h->tree_sub_bits;
+    a.sub_strided = (h->tree_sub_strided && !h->tree_has_sub) ? 1 : 0;
+    a.bsub = (sizeof(double) * 32) << (h->tree_base_bits - std::min(h->tree_base_bits, kChunkBits));
     a.n_levels = h->tree_levels;
     for (int l = 0; l < h->tree_levels; ++l) {
         a.level[l] = h->tree_ptr[l];

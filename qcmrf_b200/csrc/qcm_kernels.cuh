@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(kThreads + 32) k_block_gather_tma(const __grid
 // once and writes its 2^M images: read 2^n_in, write 2^(n_in+M), nothing else.
 // ----------------------------------------------------------------------------------
 constexpr int kChunkBits = 10;                  // 1024 amplitudes per leaf chunk of the sampler's sum tree
-constexpr int kFanBits = 10;                    // 1024 children per tree node
+constexpr int kFanBits = 5;                     // 32 children per tree node: one per lane, a level costs one 256-byte load
 
 __device__ __forceinline__ double warp_sum(double x) {
 #pragma unroll
@@ -1321,6 +1321,57 @@ __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagA
     }
 }
 
+// Several diagonal passes in ONE sweep (a BLOCK header with zero targets whose members are all DIAG): the
+// projections of a release-width circuit's ancillas are 2-3 diagonal tables of <= 10 index bits
+// each; applied together every amplitude crosses HBM once instead of once per table.
+template <typename R, int V, int U>
+__global__ void __launch_bounds__(kThreads) k_diag_multi(const __grid_constant__ BlockArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tab = reinterpret_cast<R *>(smem_raw);
+    void *const state = batch_ptr(a.state, a.bstate);
+    for (int g = 0; g < a.n_members; ++g) {
+        const R *src = reinterpret_cast<const R *>(batch_ptr(a.tables, a.btab)) + a.mem[g].src_off;
+        R *dst = tab + a.mem[g].tab_off;
+        for (int i = threadIdx.x; i < (2 << a.mem[g].n_ctrl); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    using IO = VecIO<R, V>;
+    const uint64_t nvec = (1ull << a.n_out) / V;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * U;
+    for (uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x * U + threadIdx.x; v0 < nvec; v0 += stride) {
+        R re[U][V], im[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+            if (vi < nvec) IO::load(state, vi * V, re[u], im[u]);
+        }
+        for (int g = 0; g < a.n_members; ++g) {
+            const R *mt = tab + a.mem[g].tab_off;
+            const int nc = a.mem[g].n_ctrl;
+            const uint32_t low_bit = a.mem[g].low_bit;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t gi = ((v0 + (uint64_t)u * blockDim.x) * V) | a.rank_bits;
+                uint32_t idx0 = 0;
+                for (int j = 0; j < nc; ++j) idx0 |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const uint32_t idx = v ? (idx0 | low_bit) : idx0;
+                    const R c = mt[2 * idx], sn = mt[2 * idx + 1];
+                    const R x = re[u][v], y = im[u][v];
+                    re[u][v] = c * x - sn * y;
+                    im[u][v] = c * y + sn * x;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+            if (vi < nvec) IO::store(state, vi * V, re[u], im[u]);
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------
 // Product-state initialisation (write-only).  amp[i] = lo[i & (2^L-1)] * hi[i >> L],
 // the two factor tables are built by k_init_tables from the per-qubit 2-vectors.
@@ -1433,9 +1484,14 @@ __global__ void __launch_bounds__(kThreads) k_swap(void *state, int qa, int qb, 
 // level 0: chunk c = sum_{i in chunk} |amp_i|^2 ; one warp per chunk.  Full-size chunks
 // stream 128-bit loads, eight in flight per lane; the lane-strided order is fixed.
 template <typename R>
-__global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int n_active, double *out, uint64_t bstate, uint64_t bout) {
+__global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int n_active, double *out, uint64_t bstate, uint64_t bout,
+                                                         double *sub = nullptr, uint64_t bsub = 0) {
+    // sub (optional, full-size chunks only): the 32 lane partials of every chunk -- lane l's partial covers the
+    // amplitudes it loaded: the STRIDED group {V * (l + 32 j) + v}.  The sampler picks a group, then one of its 32
+    // amplitudes, instead of scanning all 1024 amplitudes of the chunk.
     state = batch_ptr(state, bstate);
     out = batch_ptr(out, bout);
+    if (sub) sub = batch_ptr(sub, bsub);
     const int cb = n_active < kChunkBits ? n_active : kChunkBits;
     const uint64_t nchunks = 1ull << (n_active - cb);
     const uint64_t csz = 1ull << cb;
@@ -1484,6 +1540,7 @@ __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int 
                 }
             }
         }
+        if (sub && cb == kChunkBits) sub[c * 32 + lane] = acc;
         acc = warp_sum(acc);
         if (lane == 0) out[c] = acc;
     }
@@ -1491,15 +1548,15 @@ __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int 
 
 // level l+1: node j = sum of up to 1024 children ; one warp per node
 static __global__ void __launch_bounds__(kThreads) k_tree_level(const double *in, uint64_t n_in, double *out, uint64_t n_out,
-                                                                uint64_t bin = 0, uint64_t bout = 0) {
+                                                                uint64_t bin = 0, uint64_t bout = 0, int fan_bits = kFanBits) {
     in = batch_ptr(in, bin);
     out = batch_ptr(out, bout);
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t j = warp0; j < n_out; j += nwarps) {
-        const uint64_t b = j << kFanBits;
-        const uint64_t e = (b + (1ull << kFanBits)) < n_in ? b + (1ull << kFanBits) : n_in;
+        const uint64_t b = j << fan_bits;
+        const uint64_t e = (b + (1ull << fan_bits)) < n_in ? b + (1ull << fan_bits) : n_in;
         double acc = 0.0;
         for (uint64_t i = b + lane; i < e; i += 32) acc += in[i];
         acc = warp_sum(acc);
@@ -1589,6 +1646,8 @@ struct SampleArgs {
     int32_t n_levels;               // tree levels above the amplitudes (>= 1)
     const double *sub;              // optional finer level under level[0]: sums over 2^sub_bits amplitudes
     int32_t sub_bits;
+    int32_t sub_strided;            // sub holds k_chunk_sums' 32 lane partials per chunk (strided groups, see there)
+    uint64_t bsub;                  // batch stride of sub, bytes
     const double *level[8];         // level[0] = chunk sums ... level[n_levels-1] = top
     uint64_t level_n[8];
     uint64_t shots, seed, stream;
@@ -1637,6 +1696,38 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
         // node = chunk index; search the amplitudes of the chunk (through the finer level if there is one)
         uint64_t afirst = node << cb;
         uint32_t leaf_cnt = 1u << cb;
+        if (a.sub && a.sub_strided) {
+            // strided groups (generic tree build): group g = lane partial g of k_chunk_sums, then one of its 32 amplitudes
+            const double *sp = batch_ptr(a.sub, a.bsub) + node * 32;
+            const uint32_t g = warp_pick([&](uint32_t i) { return sp[i]; }, 32u, u, lane);
+            constexpr uint32_t VV = sizeof(R) == 4 ? 2u : 1u;
+            auto member = [&](uint32_t i) -> uint64_t { return (uint64_t)VV * (g + 32u * (i / VV)) + (i % VV); };
+            auto amp_ws = [&](uint32_t i) -> double {
+                if constexpr (sizeof(R) == 4) {
+                    const float2 t = reinterpret_cast<const float2 *>(state)[afirst + member(i)];
+                    return (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+                } else {
+                    const double2 t = reinterpret_cast<const double2 *>(state)[afirst + member(i)];
+                    return t.x * t.x + t.y * t.y;
+                }
+            };
+            const uint32_t c = warp_pick(amp_ws, 32u, u, lane);
+            if (lane == 0) {
+                uint64_t li = afirst + member(c);
+                if (a.rot_m) li = (li >> a.rot_m) | ((li & ((1ull << a.rot_m) - 1ull)) << a.rot_nin);
+                const uint64_t gi = li | a.rank_bits;
+                uint64_t key = gi;
+                if (a.n_clbits > 0) {
+                    key = 0;
+                    for (int cc = 0; cc < a.n_clbits; ++cc) {
+                        const int q = a.clbit_qubit[cc];
+                        if (q >= 0) key |= ((gi >> q) & 1ull) << cc;
+                    }
+                }
+                keys_out[s] = key;
+            }
+            continue;
+        }
         if (a.sub) {
             const uint32_t nsub = 1u << (cb - a.sub_bits);
             const double *sp = a.sub + (node << (cb - a.sub_bits));      // (fused checkpoint only: never batched)

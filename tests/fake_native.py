@@ -159,6 +159,9 @@ class Handle:
     def op_profile(self):
         return list(self._prof)
 
+    def op_kernels(self):
+        return [''] * len(self._prof)
+
     def timing(self):
         return dict(program_ms=0.0, sample_ms=0.0, postselect_ms=0.0, kernel_launches=0, bytes_read=0,
                     bytes_written=0)
@@ -220,6 +223,12 @@ class BatchedHandle(Handle):
                 keys |= bit.astype(np.uint64) << np.uint64(int(vclbit[k]))
             out[y] = keys
         return out
+
+    def op_profile(self):
+        return self.pts[0].op_profile()
+
+    def op_kernels(self):
+        return self.pts[0].op_kernels()
 
     def timing(self):
         return dict(program_ms=0.0, sample_ms=0.0, postselect_ms=0.0, kernel_launches=0, bytes_read=0, bytes_written=0)

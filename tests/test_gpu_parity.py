@@ -387,6 +387,31 @@ def test_beta_sweep_through_one_batched_handle(width, precision):
 
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
+def test_diagonal_block_is_one_sweep(precision):
+    """A BLOCK header without targets: all of its DIAG members in one sweep (the projection passes of a
+    release-width circuit), index qubits anywhere incl. qubit 0."""
+    N = 13
+    rng = np.random.RandomState(8)
+    with _native.Handle(N, precision) as h:
+        e = fusion._Emitter()
+        qv = rng.randn(N, 4)
+        qv /= np.sqrt((qv ** 2).sum(axis=1, keepdims=True))
+        e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=N, table_off=e.table(qv))
+        ctrls = [[0, 3, 12], [1, 2, 4, 5, 6, 7, 8, 9, 10, 11], [5], []]
+        e.op(fusion.QCM_OP_BLOCK, target=0, ctrl=(), n_in=N, n_out=N, n_ctrl=len(ctrls))
+        for c in ctrls:
+            d = rng.uniform(0.2, 1.0, 1 << len(c)) * np.exp(1j * rng.uniform(0, 6, 1 << len(c)))
+            e.op(fusion.QCM_OP_DIAG, ctrl=c, n_in=N, n_out=N, table_off=e.table(fusion._diag_table_f64(d)))
+        ops, tabs = e.finish()
+        pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, N
+        want, _ = em.run_plan(pl)
+        h.run_program(ops, tabs)
+        got = h.get_amplitudes().astype(np.complex128)
+        assert np.abs(got - want).max() < (1e-12 if precision == 'double' else 3e-6)
+        assert len(h.op_profile()) == 2 and h.op_kernels()[-1].startswith('k_diag_multi')
+
+
+@pytest.mark.parametrize('precision', ['double', 'single'])
 def test_lazy_materialisation_ops(precision):
     """Ops that materialise qubits: zero-input targets are never read (the buffer holds NaN
     there), EXTEND zero-fills, get_amplitudes reports implicit zeros."""
