@@ -202,6 +202,14 @@ int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint6
                               const int32_t *clbit_qubit, int n_clbits,
                               void *dev_keys_out, void *dev_mine_out);
 
+/* As qcm_sample_sharded_device, with the rank masses still in DEVICE memory (e.g. straight out of an NCCL
+ * all-gather): the mass of rank r is the double at dev_rank_masses[r * mass_stride].  Nothing has to come back
+ * to the host between the all-gather and the sampler.                                                       */
+int qcm_sample_sharded_devmass(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id,
+                               const void *dev_rank_masses, int64_t mass_stride, int n_ranks,
+                               const int32_t *clbit_qubit, int n_clbits,
+                               void *dev_keys_out, void *dev_mine_out);
+
 /* Fused qubit-swap + blocked gate pass over NVLink peer memory (sharded states, one box).
  * Replaces "all-to-all that swaps the s global qubits with the s highest local qubits, then the
  * sweeps that target them": ops = a MUX1Q or a BLOCK header + members whose targets are exactly those

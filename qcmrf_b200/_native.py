@@ -41,7 +41,8 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_sample_sharded_device', 'qcm_run_gather_block', 'qcm_enable_peer_access',
            'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close', 'qcm_op_kernel_name',
            'qcm_sample_released', 'qcm_create_batched', 'qcm_batch_size', 'qcm_batch_select',
-           'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched']
+           'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched',
+           'qcm_sample_sharded_devmass']
 
 
 def lib():
@@ -93,6 +94,7 @@ def lib():
     L.qcm_postselect_resident.argtypes = [vp, u64, u64, i32, vp]
     L.qcm_fetch_probs.argtypes = [vp, i32, u64, u64, vp]
     L.qcm_sample_batched.argtypes = [vp, u64, u64, vp, vp, i32, vp]
+    L.qcm_sample_sharded_devmass.argtypes = [vp, u64, u64, u64, vp, ctypes.c_int64, i32, vp, i32, vp, vp]
     L.qcm_sample_released_batched.argtypes = [vp, u64, u64, vp, i32, vp, vp, i32, vp, vp, ctypes.c_int64, vp, vp, i32, vp]
     if L.qcm_abi_version() != 1:
         raise RuntimeError('qcmrf_b200: ABI version mismatch')
@@ -281,6 +283,14 @@ class Handle:
         self._check(lib().qcm_sample_sharded_device(self._h, int(shots), int(seed), int(stream_id), _ptr(rm), len(rm),
                                                     _ptr(cq), 0 if cq is None else len(cq),
                                                     ctypes.c_void_p(dev_keys_ptr), ctypes.c_void_p(dev_mine_ptr)))
+
+    def sample_sharded_devmass(self, shots, seed, stream_id, dev_masses_ptr, mass_stride, n_ranks, clbit_qubit, dev_keys_ptr,
+                               dev_mine_ptr):
+        """qcm_sample_sharded_devmass: rank masses read on the device (no host round trip after the all-gather)."""
+        cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
+        self._check(lib().qcm_sample_sharded_devmass(self._h, int(shots), int(seed), int(stream_id), ctypes.c_void_p(dev_masses_ptr),
+                                                     int(mass_stride), int(n_ranks), _ptr(cq), 0 if cq is None else len(cq),
+                                                     ctypes.c_void_p(dev_keys_ptr), ctypes.c_void_p(dev_mine_ptr)))
 
     def sample_prepare(self):
         m = ctypes.c_double()

@@ -1609,8 +1609,8 @@ int qcm_sample_prepare(qcm_handle h, double *local_mass_out) {
 // keys of point y land at keys_out + y * shots.  Batched sampling is unsharded (n_ranks == 1).
 static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const double *rank_masses, int n_ranks,
                                const int32_t *clbit_qubit, int n_clbits, uint64_t *keys_out, uint8_t *mine_out, bool dev,
-                               const uint64_t *stream_ids = nullptr) {
-    if (!h || !keys_out || (!rank_masses && !stream_ids)) return fail(h, QCM_ERR_INVALID, "NULL argument");
+                               const uint64_t *stream_ids = nullptr, const double *dev_masses = nullptr, int64_t mass_stride = 1) {
+    if (!h || !keys_out || (!rank_masses && !stream_ids && !dev_masses)) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if ((h->batch > 1) != (stream_ids != nullptr)) return fail(h, QCM_ERR_INVALID, "batched handles sample with qcm_sample_batched (and only they)");
     if (stream_ids && (h->n_global != 0 || mine_out)) return fail(h, QCM_ERR_UNSUPPORTED, "batched sampling on a sharded state");
     if (n_ranks < 1 || (uint64_t)n_ranks != (1ull << h->n_global)) return fail(h, QCM_ERR_INVALID, "n_ranks %d does not match %d global qubits", n_ranks, h->n_global);
@@ -1654,6 +1654,11 @@ static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint
         a.rank_lo = 0.0;
         a.rank_hi = 1e300;
         a.total = 1.0;
+    } else if (dev_masses) {
+        a.dev_masses = dev_masses;
+        a.mass_stride = mass_stride;
+        a.n_ranks = n_ranks;
+        a.my_rank = (int)h->rank;
     } else {
         for (int r = 0; r < n_ranks; ++r) {
             if ((uint64_t)r == h->rank) lo = total;
@@ -1708,6 +1713,14 @@ int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint6
     if (!dev_mine_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
     return sample_sharded_impl(h, shots, seed, stream_id, rank_masses, n_ranks, clbit_qubit, n_clbits, (uint64_t *)dev_keys_out,
                                (uint8_t *)dev_mine_out, true);
+}
+
+int qcm_sample_sharded_devmass(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const void *dev_rank_masses,
+                               int64_t mass_stride, int n_ranks, const int32_t *clbit_qubit, int n_clbits, void *dev_keys_out,
+                               void *dev_mine_out) {
+    if (!dev_mine_out || !dev_rank_masses || mass_stride < 1) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    return sample_sharded_impl(h, shots, seed, stream_id, nullptr, n_ranks, clbit_qubit, n_clbits, (uint64_t *)dev_keys_out,
+                               (uint8_t *)dev_mine_out, true, nullptr, (const double *)dev_rank_masses, mass_stride);
 }
 
 int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const int32_t *clbit_qubit, int n_clbits,

@@ -1663,6 +1663,11 @@ struct SampleArgs {
     uint64_t bstate, btree, bkeys;
     const uint64_t *streams;
     const double *totals;
+    // sharded sampling with the rank masses still on the device (right out of an all-gather): mass of rank r at
+    // dev_masses[r * mass_stride]; rank_lo / rank_hi / total are then derived here instead of on the host
+    const double *dev_masses;
+    int64_t mass_stride;
+    int32_t n_ranks, my_rank;
 };
 
 template <typename R>
@@ -1674,16 +1679,27 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
     const void *const state = batch_ptr(a.state, a.bstate);
     uint64_t *const keys_out = batch_ptr(a.keys_out, a.bkeys);
     const uint64_t stream = a.streams ? a.streams[blockIdx.y] : a.stream;
-    const double total = a.totals ? a.totals[blockIdx.y] : a.total;
+    double total = a.totals ? a.totals[blockIdx.y] : a.total;
+    double rank_lo = a.rank_lo, rank_hi = a.rank_hi;
+    if (a.dev_masses) {                              // same left-to-right sums as the host version
+        double t = 0.0, lo = 0.0;
+        for (int r = 0; r < a.n_ranks; ++r) {
+            if (r == a.my_rank) lo = t;
+            t += a.dev_masses[(int64_t)r * a.mass_stride];
+        }
+        total = t;
+        rank_lo = lo;
+        rank_hi = (a.my_rank == a.n_ranks - 1) ? 1e300 : lo + a.dev_masses[(int64_t)a.my_rank * a.mass_stride];
+    }
     for (uint64_t s = warp0; s < a.shots; s += nwarps) {
         double u = philox_uniform(a.seed, stream, s) * total;
-        const bool mine = (u >= a.rank_lo) && (u < a.rank_hi);
+        const bool mine = (u >= rank_lo) && (u < rank_hi);
         if (a.mine_out && lane == 0) a.mine_out[s] = mine ? 1 : 0;
         if (!mine) {
             if (lane == 0) keys_out[s] = 0;
             continue;
         }
-        u -= a.rank_lo;
+        u -= rank_lo;
         uint64_t node = 0;
         for (int l = a.n_levels - 1; l >= 0; --l) {
             const double *lv = batch_ptr(a.level[l], a.btree);

@@ -764,8 +764,8 @@ class ShardedSimulator:
 
     def _finish_on_device(self, h, pr, shots, seed, stream, replica):
         """Post-selection, all-gather of (pmf block, kept, mass), sharded sampling and the key merge with
-        every intermediate on the GPU: one tiny device->host read (the masses, which the sampler takes as
-        arguments) and one final read of pmf + keys into pinned memory."""
+        every intermediate on the GPU (the sampler reads the gathered rank masses in place): one final read of
+        pmf + keys into pinned memory is the only synchronisation."""
         t, dist = self.torch, self.dist
         dev = self._state.device
         m, _ = pr.pmf_map
@@ -791,14 +791,17 @@ class ShardedSimulator:
             b['mine'][-1:].fill_(mass)
         dist.all_gather_into_tensor(b['all'], b['mine'], group=self.group)
         b['h_all'].copy_(b['all'], non_blocking=True)
-        allv = b['all'].view(self.world, blk)
-        masses = allv[:, -1].cpu().numpy()                       # the one mid-way synchronisation (world doubles)
         if replica:
             b['keys'].zero_()
+        elif hasattr(h, 'sample_sharded_devmass'):
+            # the sampler reads the gathered rank masses where the all-gather left them: nothing comes back to the
+            # host between the two collectives (keys of shots that landed on another rank are written as 0)
+            h.sample_sharded_devmass(shots, seed, stream, b['all'].data_ptr() + 8 * (blk - 1), blk, self.world,
+                                     pr.clbit_map if len(pr.clbit_map) else None, b['keys'].data_ptr(), b['flag'].data_ptr())
         else:
+            masses = b['all'].view(self.world, blk)[:, -1].cpu().numpy()
             h.sample_sharded_device(shots, seed, stream, masses, pr.clbit_map if len(pr.clbit_map) else None,
                                     b['keys'].data_ptr(), b['flag'].data_ptr())
-            b['keys'].mul_(b['flag'])                             # keys of shots that landed elsewhere are 0 already; be explicit
         dist.all_reduce(b['keys'], op=dist.ReduceOp.SUM, group=self.group)
         b['h_keys'].copy_(b['keys'], non_blocking=True)
         t.cuda.current_stream(dev).synchronize()
