@@ -286,6 +286,18 @@ int qcm_sample_released_batched(qcm_handle h, uint64_t shots, uint64_t seed, con
                                 const int32_t *vclbit, const int32_t *clbit_pos, int n_clbits,
                                 uint64_t *keys_out);
 
+/* -- exact MRF inference by enumeration ("px" on the GPU) -------------------------------- */
+/* What /root/reference/eval.py:84-93 computes through the proprietary kiopto_native module --
+ * lnZ = px.infer(b, task='partition'), p[xid] = exp(px.logpot(b, xid) - lnZ) -- for binary variables:
+ * energy(xid) = sum_C weights[off_C + y_C], y_C = sum_j x_{C[j]} 2^(|C|-1-j) (itertools.product order,
+ * weights clique-major), x_v = bit n-1-v of xid (x_0 is the most significant bit, eval.py:100-101).
+ * clique_size[n_cliques], clique_vars = the cliques' vertices concatenated.  log_z_out: ln Z.
+ * pmf_out / energies_out (optional, 2^n doubles each).  Stateless; no CPU fallback.                 */
+int qcm_mrf_exact(int device, int n, int n_cliques, const int32_t *clique_size, const int32_t *clique_vars,
+                  const double *weights, double *log_z_out, double *pmf_out, double *energies_out,
+                  double *device_ms_out);
+const char *qcm_mrf_last_error(void);
+
 /* -- multi-GPU plumbing ------------------------------------------------------------ */
 /* Packs/unpacks nothing: the qubit-swap all-to-all exchanges contiguous slabs of the
  * top `g` local qubits, which the caller moves with NCCL (torch.distributed).  These

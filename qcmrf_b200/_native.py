@@ -42,7 +42,7 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close', 'qcm_op_kernel_name',
            'qcm_sample_released', 'qcm_create_batched', 'qcm_batch_size', 'qcm_batch_select',
            'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched',
-           'qcm_sample_sharded_devmass']
+           'qcm_sample_sharded_devmass', 'qcm_mrf_exact', 'qcm_mrf_last_error']
 
 
 def lib():
@@ -94,6 +94,8 @@ def lib():
     L.qcm_postselect_resident.argtypes = [vp, u64, u64, i32, vp]
     L.qcm_fetch_probs.argtypes = [vp, i32, u64, u64, vp]
     L.qcm_sample_batched.argtypes = [vp, u64, u64, vp, vp, i32, vp]
+    L.qcm_mrf_exact.argtypes = [i32, i32, i32, vp, vp, vp, ctypes.POINTER(dbl), vp, vp, ctypes.POINTER(dbl)]
+    L.qcm_mrf_last_error.restype = ctypes.c_char_p
     L.qcm_sample_sharded_devmass.argtypes = [vp, u64, u64, u64, vp, ctypes.c_int64, i32, vp, i32, vp, vp]
     L.qcm_sample_released_batched.argtypes = [vp, u64, u64, vp, i32, vp, vp, i32, vp, vp, ctypes.c_int64, vp, vp, i32, vp]
     if L.qcm_abi_version() != 1:
@@ -399,3 +401,23 @@ def run_batch_small(plans, clbit_maps, ps, shots, seed, precision='double', devi
         raise NativeError(rc, 'qcm_run_batch_small failed')
     plist = [probs[pbeg[i]:pbeg[i + 1]] for i in range(n)] if want_probs else None
     return keys, plist, kept, ms.value
+
+
+def mrf_exact(cliques, weights, n=None, want_pmf=True, want_energies=False, device=0):
+    """qcm_mrf_exact: (ln Z, pmf or None, energies or None, device ms) of a binary MRF by enumeration on the GPU;
+    state id with x_0 as its most significant bit, weights clique-major in itertools.product order."""
+    if n is None:
+        n = max(max(c) for c in cliques) + 1
+    size = np.array([len(c) for c in cliques], dtype=np.int32)
+    var = np.array([v for c in cliques for v in c], dtype=np.int32)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if w.size != int(sum(1 << int(m) for m in size)):
+        raise ValueError('weights: %d entries, the cliques need %d' % (w.size, sum(1 << int(m) for m in size)))
+    pmf = np.empty(1 << n, dtype=np.float64) if want_pmf else None
+    en = np.empty(1 << n, dtype=np.float64) if want_energies else None
+    lz, ms = ctypes.c_double(), ctypes.c_double()
+    rc = lib().qcm_mrf_exact(int(device), int(n), len(size), _ptr(size), _ptr(var), _ptr(w), ctypes.byref(lz), _ptr(pmf), _ptr(en),
+                             ctypes.byref(ms))
+    if rc:
+        raise NativeError(rc, (lib().qcm_mrf_last_error() or b'').decode())
+    return lz.value, pmf, en, ms.value

@@ -1156,18 +1156,24 @@ __global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_co
     static_assert(kPerWarp >= 32 && kPerWarp % 32 == 0, "a warp takes whole batches of 32 inputs");
     const uint64_t tile = blockIdx.x;                                   // grid = 2^(n_in - TB), launch = address order
     double wacc = 0.0;
+    // the next batch's input amplitude is fetched while this batch's stores drain (a CTA with several batches
+    // per warp then never waits on the input read between batches)
+    auto x_first = [&](int batch) -> uint64_t { return (tile << TB) + (uint64_t)batch * (32 * kWarps) + 2u * warp; };
+    C2 next_in = reinterpret_cast<const C2 *>(in)[x_first(0) + (uint64_t)(lane >> 1) * (2 * kWarps) + (lane & 1)];
 #pragma unroll 1
     for (int batch = 0; batch < kPerWarp / 32; ++batch) {
         // The warps of a CTA interleave at a granularity of two inputs (a pair shares the sampler's finest
         // sum): at step i of phase B the warps write runs 2 * 2^M amplitudes apart, so the CTA's stores
         // stay inside one moving window instead of one stream per warp (DRAM row locality).
-        const uint64_t x0 = (tile << TB) + (uint64_t)batch * (32 * kWarps) + 2u * warp;
+        const uint64_t x0 = x_first(batch);
         auto x_of = [&](int i) -> uint64_t { return x0 + (uint64_t)(i >> 1) * (2 * kWarps) + (i & 1); };
         // ---- phase A: lane i prepares input x_of(i)
         {
             const uint64_t x = x_of(lane);
             const uint64_t gi = x | a.rank_bits;
-            const C2 mine = reinterpret_cast<const C2 *>(in)[x];
+            const C2 mine = next_in;
+            if (batch + 1 < kPerWarp / 32)
+                next_in = reinterpret_cast<const C2 *>(in)[x_first(batch + 1) + (uint64_t)(lane >> 1) * (2 * kWarps) + (lane & 1)];
             if (a.tree_out) {
                 const double w = (double)mine.x * (double)mine.x + (double)mine.y * (double)mine.y;
                 if constexpr (V == 2) {

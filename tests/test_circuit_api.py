@@ -258,3 +258,26 @@ def test_sweep_grouping_through_a_batched_handle(monkeypatch):
             pb, db, _ = mrf.brute_force_pmf(C, th, beta=b)
             assert np.abs(res2.postselected_probabilities(i)[0] - pb).max() < 1e-12
         sim.close()
+
+
+def test_px_shim_is_memoised_and_matches_the_oracle():
+    """eval.py:84-93 calls px.infer once and px.logpot 2^n times per model: the stand-in evaluates one state per
+    logpot call (no O(4^n) loop) and memoises ln Z per weight vector."""
+    from oracle import mrf
+    from qcmrf_b200.compat.shim import kiopto_native as px
+    C = [[0, 1, 2], [2, 3], [4], [3, 4, 0, 1]]
+    rng = np.random.RandomState(2)
+    th = -np.abs(rng.randn(8 + 4 + 2 + 16))
+    b = px.backend(C, np.array([2] * 5))
+    assert len(px.weights(b)) == 30
+    px.weights(b)[:] = th
+    lz = px.infer(b, task='partition')
+    calls = []
+    orig = b.energies
+    b.energies = lambda: calls.append(1) or orig()
+    p = np.array([np.exp(px.logpot(b, x) - px.infer(b, task='partition')) for x in range(32)])
+    assert not calls                                            # neither logpot nor the memoised infer enumerates again
+    pb, _db, _ = mrf.brute_force_pmf(C, th)
+    assert np.abs(p - pb).max() < 1e-14
+    px.weights(b)[0] -= 1.0                                     # new weights: ln Z is recomputed
+    assert px.infer(b, task='partition') != lz

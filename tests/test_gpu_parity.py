@@ -958,3 +958,34 @@ def test_default_schedule_ends_in_the_rotated_expansion_kernel():
             if shots:
                 assert sum(res.get_counts().values()) == shots
         sim.close()
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [1, 5, 13, 20, 24])
+def test_exact_mrf_inference_on_the_gpu(n):
+    """px's `infer('partition')` / `logpot` / exact pmf (eval.py:84-93) by enumeration on the GPU
+    against the oracle's brute force -- cliques of size 1..4, state ids with x_0 as the MSB."""
+    from qcmrf_b200 import ExactMRF
+    rng = np.random.RandomState(300 + n)
+    C = []
+    for v in range(n):                                          # every vertex appears; sizes 1..4
+        m = int(rng.randint(1, min(4, n) + 1))
+        others = [int(x) for x in rng.permutation([u for u in range(n) if u != v])[:m - 1]]
+        c = [v] + others
+        rng.shuffle(c)
+        C.append([int(x) for x in c])
+    th = -np.abs(rng.randn(sum(2 ** len(c) for c in C)))
+    pb, db, _ = mrf.brute_force_pmf(C, th)
+    ex = ExactMRF(C, th)
+    p = ex.pmf()
+    lz = ex.log_partition()
+    assert np.abs(p - pb).max() < 1e-12 and (np.abs(p - pb) / pb).max() < 1e-9
+    assert abs(ex.success_probability() - db) < 1e-12 * max(db, 1e-3) + 1e-15
+    for xid in (0, (1 << n) - 1, int(rng.randint(0, 1 << n))):
+        assert abs(np.exp(ex.logpot(xid) - lz) - pb[xid]) < 1e-12
+    # the compat shim's px takes ln Z from the same kernel when a GPU is present
+    from qcmrf_b200.compat.shim import kiopto_native as px
+    b = px.backend(C, np.array([2] * n))
+    px.weights(b)[:] = th
+    assert abs(px.infer(b, task='partition') - lz) < 1e-12
+    assert abs(px.logpot(b, 1) - ex.logpot(1)) < 1e-15
