@@ -314,7 +314,7 @@ class B200Simulator:
             diag.append((ctrl, a0))
         em = fusion._Emitter()
         act = pl.final_active
-        merged = fusion.merge_diagonals(diag)
+        merged = [fusion.sort_diag_ctrl(c, t) for c, t in fusion.merge_diagonals(diag)]
         if len(merged) > 1:                                   # one sweep for all of them: a BLOCK without targets
             em.op(fusion.QCM_OP_BLOCK, target=0, ctrl=(), n_in=act, n_out=act, n_ctrl=len(merged))
         for ctrl, tab in merged:
@@ -385,7 +385,23 @@ class B200Simulator:
         sid = (lambda i: i) if stream_ids is None else (lambda i: int(stream_ids[i]))
         small_ids, small_prep = [], []
         large = []
+        fast_sweeps = []                                      # (indices, prepared sweep): same-graph QCMRF lists at release width
+        claimed = set()
+        if self.sweep_batch and self.width == 'release' and len(circs) > 1:
+            from .mrf import QCMRF as _Q
+            by_graph = {}
+            for i, c in enumerate(circs):
+                if type(c) is _Q and not (self.small_batch and c.num_qubits <= small_max):
+                    by_graph.setdefault((repr(c._mrf_cliques), c._mrf_measure), []).append(i)
+            for idxs in by_graph.values():
+                if len(idxs) >= 2:
+                    sw = self._qcmrf_release_sweep([circs[i] for i in idxs], n_vars, precision)
+                    if sw is not None:
+                        fast_sweeps.append((idxs, sw))
+                        claimed.update(idxs)
         for i, c in enumerate(circs):
+            if i in claimed:
+                continue
             nq = int(c.n_qubits if isinstance(c, ir.Program) else c.num_qubits)
             if self.small_batch and nq <= small_max:
                 small_ids.append(i)
@@ -409,6 +425,15 @@ class B200Simulator:
             entries[i]['meta']['host_ms']['prepare (lower, fuse, plan)'] = tp
             self.breakdown_ms = entries[i]['meta']['host_ms']
         # sweeps last: their post-selected vectors may stay on the GPU, which only holds while the state handle lives
+        for idxs, sw in fast_sweeps:
+            for e in entries:
+                if e is not None and isinstance(e['probs'], _ResidentProbs):
+                    e['probs'] = e['probs'].get()
+            got = self._run_sweep([circs[i] for i in idxs], None, shots, seed, [sid(i) for i in idxs], precision, pmf, sw=sw)
+            for i, e in zip(idxs, got):
+                e['name'] = str(getattr(circs[i], 'name', e['name']))
+                e['meta']['host_ms'] = {'prepare (vectorised over the sweep)': None}
+                entries[i] = e
         for sig, ks in groups.items():
             if len(ks) < 2:
                 continue
@@ -454,12 +479,89 @@ class B200Simulator:
     def prepare_sweep(self, circuits, n_vars=None, precision=None):
         """Prepare a list of same-structure circuits as ONE sweep (raises if their structures differ)."""
         precision = precision or self.precision
+        sw = self._qcmrf_release_sweep(list(circuits), n_vars, precision)
+        if sw is not None:
+            return sw
         prs = [self.prepare(c, n_vars=n_vars) for c in circuits]
         sigs = {self._sweep_signature(pr, precision) for pr in prs}
         if len(sigs) != 1 or None in sigs:
             raise ValueError('prepare_sweep: the circuits do not share one program structure (or their state is too large '
                              'for a batched sweep: sweep_state_bytes)')
         return self._stack_sweep(prs)
+
+    def _qcmrf_release_sweep(self, circs, n_vars, precision):
+        """A theta / beta sweep of pristine QCMRF objects over ONE graph at release width, prepared in one
+        vectorised pass: the first circuit is prepared in full; for the others only the coefficients change, and
+        at release width every one of them is an elementwise function of gamma (P(ancilla = 1 | x_C) = sin^2 2gamma,
+        projection factors = merged products of cos 2gamma) -- computed here for all points at once instead of
+        lowering, fusing and planning 256 circuits.  Returns None whenever the shortcut does not apply."""
+        from .mrf import QCMRF
+        if self.width != 'release' or len(circs) < 2:
+            return None
+        c0 = circs[0]
+        for c in circs:
+            if (type(c) is not QCMRF or c.__dict__.get('_mrf_data') is not None or c._mrf_measure != c0._mrf_measure
+                    or c._mrf_cliques != c0._mrf_cliques):
+                return None
+        pr0 = self.prepare(c0, n_vars=n_vars)
+        if (not pr0.virtual or pr0.fc.ops or pr0.proj is None or self._sweep_signature(pr0, precision) is None
+                or len(pr0.virtual) != len(c0._mrf_cliques)):
+            return None                                   # not every clique sweep is released: general path
+        st = c0.__dict__.get('_mrf_struct')
+        if not st:
+            return None
+        B, dim = len(circs), c0._mrf_dim
+        G = np.empty((B, dim))
+        with np.errstate(invalid='ignore'):
+            for y, c in enumerate(circs):
+                if c._mrf_gamma is not None:
+                    G[y] = c._mrf_gamma
+                else:
+                    G[y] = 0.5 * np.arccos(np.exp(c._mrf_beta * 0.5 * np.asarray(c._mrf_theta, dtype=np.float64)))
+        if not np.isfinite(G).all():
+            raise ValueError('QCMRF: theta must be <= 0 (gamma is not finite)')
+        if not (np.abs(G) > 1e-8).all():
+            return None                                   # skipped terms (QCMRF.py:223) change the structure: general path
+        cosg, sing = np.cos(2.0 * G), np.sin(2.0 * G)
+        gidx = {}
+        for m, ids, idx in st:
+            for r, ii in enumerate(ids):
+                gidx[ii] = idx[r]
+        pl = pr0.plan
+        n = c0._mrf_n
+        diag, p1 = [], []
+        for v in pr0.virtual:                             # released sweeps, in program order: clique ii's ancilla is qubit n+1+ii
+            ii = v['qubit'] - n - 1
+            a0, a1 = cosg[:, gidx[ii]], sing[:, gidx[ii]]
+            w0, w1 = a0 * a0, a1 * a1
+            p1.append(w1 / (w0 + w1))
+            diag.append((v['ctrl'], a0))
+        steps = fusion._merge_steps(tuple(tuple(int(c) for c in ctrl) for ctrl, _d in diag))
+        merged, cur_ctrl, cur = [], [], np.ones((B, 1))
+        for (flush, union, ia, ib), (_ctrl, d) in zip(steps, diag):
+            if flush:
+                merged.append((cur_ctrl, cur))
+                cur = np.ones((B, 1))
+            cur = cur[:, ia] * d[:, ib]
+            cur_ctrl = list(union)
+        merged.append((cur_ctrl, cur))
+        merged = [fusion.sort_diag_ctrl(c, t) for c, t in merged]
+        proj_ops, proj_t0 = pr0.proj
+        dops = [o for o in proj_ops if int(o['kind']) == fusion.QCM_OP_DIAG]
+        if len(dops) != len(merged) or any(list(o['ctrl'][:int(o['n_ctrl'])]) != list(c) for o, (c, _t) in zip(dops, merged)):
+            return None
+        proj_tables = np.zeros((B, proj_t0.size))
+        for o, (_c, t) in zip(dops, merged):
+            off = int(o['table_off'])
+            proj_tables[:, off:off + 2 * t.shape[1]:2] = t          # real parts; the factors are real (cos 2 gamma)
+        sw = _Sweep()
+        sw.prs = [pr0] * B
+        sw.ops, sw.n_phys, sw.ps, sw.clbit_map, sw.n_vars = pl.ops, pl.n_phys, pr0.ps, pr0.clbit_map, pr0.n_vars
+        sw.tables = np.broadcast_to(pl.tables, (B, pl.tables.size))  # the stored qubits' program (H layer) has no theta in it
+        sw.proj_ops, sw.proj_tables = proj_ops, proj_tables
+        sw.released = self._released_tables(pr0)
+        sw.p1 = np.ascontiguousarray(np.concatenate(p1, axis=1))
+        return sw
 
     def _stack_sweep(self, prs):
         sw = _Sweep()
@@ -512,8 +614,10 @@ class B200Simulator:
         self.sweep_profile = prof                             # per-launch record of the last sweep chunk (bench.py)
         return keys, probs, kept
 
-    def _run_sweep(self, circs, prs, shots, seed, streams, precision, pmf):
-        sw = self._stack_sweep(prs)
+    def _run_sweep(self, circs, prs, shots, seed, streams, precision, pmf, sw=None):
+        if sw is None:
+            sw = self._stack_sweep(prs)
+        prs = sw.prs
         abytes = 8 if precision in ('single', 'c64', 32) else 16
         cap = max(2, int(self.sweep_bytes // (abytes << sw.n_phys)))
         entries = []

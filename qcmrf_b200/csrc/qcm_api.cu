@@ -682,6 +682,7 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
     a.bstate = bstate(h);
     a.btab = btab(h);
     size_t reals = 0;
+    DiagMultiRuns runs{};
     for (int g = 0; g < n_mem; ++g) {
         const qcm_op &op = members[g];
         if (op.kind != QCM_OP_DIAG) return fail(h, QCM_ERR_INVALID, "a BLOCK without targets may only hold DIAG members");
@@ -698,6 +699,18 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
         a.mem[g].src_off = (int32_t)op.table_off;
         a.mem[g].tab_off = (int32_t)reals;
         reals += ((2ull << op.n_ctrl) + 3) & ~size_t(3);
+        // runs of consecutive ascending index qubits (index bit j+1 <-> qubit ctrl[j] + 1)
+        IndexRuns &rn = runs.m[g];
+        for (int j = 0; j < op.n_ctrl; ++j) {
+            if (j && op.ctrl[j] == op.ctrl[j - 1] + 1) {
+                rn.len[rn.n_runs - 1]++;
+            } else {
+                rn.start[rn.n_runs] = (int8_t)op.ctrl[j];
+                rn.len[rn.n_runs] = 1;
+                rn.pos[rn.n_runs] = (int8_t)j;
+                rn.n_runs++;
+            }
+        }
     }
     const size_t smem = reals * real_bytes(h);
     if (smem > 200 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "diagonal block tables need %zu B of shared memory", smem);
@@ -705,15 +718,15 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
     if (h->prec == QCM_C64 && n_active >= 1) {
         auto k = k_diag_multi<float, 2, 4>;
         if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, (1ull << n_active) / 2)), kThreads, smem, h->stream>>>(a);
+        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, (1ull << n_active) / 2)), kThreads, smem, h->stream>>>(a, runs);
     } else if (h->prec == QCM_C64) {
         auto k = k_diag_multi<float, 1, 4>;
         if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<bgrid(h, 1), kThreads, smem, h->stream>>>(a);
+        k<<<bgrid(h, 1), kThreads, smem, h->stream>>>(a, runs);
     } else {
         auto k = k_diag_multi<double, 1, 4>;
         if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, 1ull << n_active)), kThreads, smem, h->stream>>>(a);
+        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, 1ull << n_active)), kThreads, smem, h->stream>>>(a, runs);
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;

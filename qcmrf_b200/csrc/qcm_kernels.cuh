@@ -1330,8 +1330,18 @@ __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagA
 // Several diagonal passes in ONE sweep (a BLOCK header with zero targets whose members are all DIAG): the
 // projections of a release-width circuit's ancillas are 2-3 diagonal tables of <= 10 index bits
 // each; applied together every amplitude crosses HBM once instead of once per table.
+// Table index from runs of consecutive index qubits: idx = sum_r ((gi >> start_r) & (2^len_r - 1)) << pos_r.  The
+// planner sorts a diagonal table's index qubits, so 10 of them are usually 1-3 runs (a dozen instructions instead
+// of one shift/mask/or per qubit with a constant-bank load each: the 3-table projection pass of the chain-20 sweep
+// went from instruction-bound 2.3 TB/s to the HBM roofline).
+struct IndexRuns {
+    int8_t n_runs;
+    int8_t start[QCM_MAX_CTRL], len[QCM_MAX_CTRL], pos[QCM_MAX_CTRL];
+};
+struct DiagMultiRuns { IndexRuns m[QCM_MAX_MEMBERS]; };
+
 template <typename R, int V, int U>
-__global__ void __launch_bounds__(kThreads) k_diag_multi(const __grid_constant__ BlockArgs a) {
+__global__ void __launch_bounds__(kThreads) k_diag_multi(const __grid_constant__ BlockArgs a, const __grid_constant__ DiagMultiRuns runs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tab = reinterpret_cast<R *>(smem_raw);
     void *const state = batch_ptr(a.state, a.bstate);
@@ -1353,13 +1363,14 @@ __global__ void __launch_bounds__(kThreads) k_diag_multi(const __grid_constant__
         }
         for (int g = 0; g < a.n_members; ++g) {
             const R *mt = tab + a.mem[g].tab_off;
-            const int nc = a.mem[g].n_ctrl;
+            const IndexRuns &rn = runs.m[g];
             const uint32_t low_bit = a.mem[g].low_bit;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint64_t gi = ((v0 + (uint64_t)u * blockDim.x) * V) | a.rank_bits;
                 uint32_t idx0 = 0;
-                for (int j = 0; j < nc; ++j) idx0 |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+                for (int r = 0; r < rn.n_runs; ++r)
+                    idx0 |= ((uint32_t)(gi >> rn.start[r]) & ((1u << rn.len[r]) - 1u)) << rn.pos[r];
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const uint32_t idx = v ? (idx0 | low_bit) : idx0;

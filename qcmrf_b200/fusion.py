@@ -765,6 +765,28 @@ def merge_diagonals(members):
     return out
 
 
+_SORT_IDX = {}
+
+
+def sort_diag_ctrl(ctrl, tab):
+    """The same diagonal factor with its index qubits in ascending order (the engine extracts runs of consecutive
+    index qubits with one shift + mask each).  Works on a table with leading batch axes."""
+    ctrl = tuple(int(c) for c in ctrl)
+    order = sorted(range(len(ctrl)), key=lambda j: ctrl[j])
+    if order == list(range(len(ctrl))):
+        return list(ctrl), tab
+    idx = _SORT_IDX.get(ctrl)
+    if idx is None:
+        k = np.arange(1 << len(ctrl))
+        idx = np.zeros_like(k)
+        for j, oj in enumerate(order):                        # new index bit j <-> old index bit order[j]
+            idx |= ((k >> j) & 1) << oj
+        if len(_SORT_IDX) > 256:
+            _SORT_IDX.clear()
+        _SORT_IDX[ctrl] = idx
+    return [ctrl[j] for j in order], np.asarray(tab)[..., idx]
+
+
 def control_only_qubits(fc: FusedCircuit) -> List[int]:
     """Product-state qubits that no later sweep targets: they only ever select table entries, so a
     state can be split on them across GPUs with no communication at all."""

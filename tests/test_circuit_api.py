@@ -281,3 +281,31 @@ def test_px_shim_is_memoised_and_matches_the_oracle():
     assert np.abs(p - pb).max() < 1e-14
     px.weights(b)[0] -= 1.0                                     # new weights: ln Z is recomputed
     assert px.infer(b, task='partition') != lz
+
+
+def test_vectorised_sweep_preparation_equals_one_by_one(monkeypatch):
+    """The vectorised release-width preparation of a same-graph QCMRF list yields the tables the per-circuit
+    lower/fuse/plan path yields (projection factors, released-qubit probabilities), for theta/beta and gamma input."""
+    import fake_native
+    from qcmrf_b200 import B200Simulator, workloads
+    fake_native.install(monkeypatch)
+    sim = B200Simulator(precision='double', width='release', small_batch=False)
+    C = workloads.chain(14)
+    th = workloads.theta_for(C, seed=2)
+    circs = [QCMRF(C, th, beta=(j + 1) / 8.0) for j in range(9)]
+    fast = sim._qcmrf_release_sweep(circs, None, 'double')
+    assert fast is not None
+    slow = sim._stack_sweep([sim.prepare(QCMRF(C, th, beta=(j + 1) / 8.0)) for j in range(9)])
+    assert np.array_equal(fast.ops, slow.ops) and np.array_equal(fast.proj_ops, slow.proj_ops)
+    assert np.allclose(fast.tables, slow.tables, rtol=0, atol=0)
+    assert np.allclose(fast.proj_tables, slow.proj_tables, rtol=1e-14, atol=0)
+    assert np.allclose(fast.p1, slow.p1, rtol=1e-14, atol=1e-300)
+    for a, b in zip(fast.released, slow.released):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    # gamma input, and a list the shortcut must refuse (a skipped term changes the program structure)
+    g = [0.1 + 0.01 * k for k in range(4 * 13)]
+    fast = sim._qcmrf_release_sweep([QCMRF(C, gamma=g), QCMRF(C, gamma=[x * 0.5 for x in g])], None, 'double')
+    slow = sim._stack_sweep([sim.prepare(QCMRF(C, gamma=g)), sim.prepare(QCMRF(C, gamma=[x * 0.5 for x in g]))])
+    assert np.allclose(fast.proj_tables, slow.proj_tables, rtol=1e-14, atol=0) and np.allclose(fast.p1, slow.p1, rtol=1e-14)
+    th0 = list(th); th0[5] = 0.0
+    assert sim._qcmrf_release_sweep([QCMRF(C, th), QCMRF(C, th0)], None, 'double') is None

@@ -381,7 +381,7 @@ def test_beta_sweep_through_one_batched_handle(width, precision):
             r1 = one.run(QCMRF(C, th, beta=b), shots=shots, stream_ids=[i]).result()
             assert r1.metadata(0)['path'] == 'statevector'
             assert r1.get_counts(0) == counts
-            assert np.array_equal(r1.postselected_probabilities(0)[0], p)
+            assert np.allclose(r1.postselected_probabilities(0)[0], p, rtol=1e-13 if precision == 'double' else 1e-6, atol=0)
     sim.close()
     one.close()
 
