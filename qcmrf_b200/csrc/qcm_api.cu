@@ -649,10 +649,12 @@ int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
     const size_t real_sz = h->prec == QCM_C64 ? 4 : 8;
     a.table = (const char *)h->tab_real.p + (size_t)op.table_off * real_sz;
     const size_t smem = (2ull << op.n_ctrl) * real_sz;
+    const uint64_t cta_cap = std::max<uint64_t>((uint64_t)(4 * h->num_sms + h->batch - 1) / h->batch,
+                                              (amp_bytes(h->prec) << a.n_active) / (16 * std::max<size_t>(smem, 1024)));
     if (h->prec == QCM_C64) {
         if (a.n_active >= 1) {
             auto k = k_diag<float, 2, 4>;
-            int grid = grid_for(h, k, smem, kThreads * 4, (1ull << a.n_active) / 2);
+            int grid = (int)std::min<uint64_t>(grid_for(h, k, smem, kThreads * 4, (1ull << a.n_active) / 2), cta_cap);
             k<<<bgrid(h, grid), kThreads, smem, h->stream>>>(a);
         } else {
             auto k = k_diag<float, 1, 4>;
@@ -660,7 +662,7 @@ int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
         }
     } else {
         auto k = k_diag<double, 1, 4>;
-        int grid = grid_for(h, k, smem, kThreads * 4, 1ull << a.n_active);
+        int grid = (int)std::min<uint64_t>(grid_for(h, k, smem, kThreads * 4, 1ull << a.n_active), cta_cap);
         k<<<bgrid(h, grid), kThreads, smem, h->stream>>>(a);
     }
     QCM_CUDA(h, cudaGetLastError());
@@ -715,10 +717,15 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
     const size_t smem = reals * real_bytes(h);
     if (smem > 200 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "diagonal block tables need %zu B of shared memory", smem);
     h->cur_kernel = h->prec == QCM_C64 ? "k_diag_multi<float>" : "k_diag_multi<double>";
+    // every CTA stages all tables (up to 16 KiB each): give it at least 16x that much state to sweep, else the
+    // staging traffic rivals the state traffic (a 16 MiB sweep point under 32 KiB of tables: 3.3 -> 6+ TB/s)
+    const uint64_t cta_cap = std::max<uint64_t>((uint64_t)(4 * h->num_sms + h->batch - 1) / h->batch,
+                                              (amp_bytes(h->prec) << n_active) / (16 * std::max<size_t>(smem, 1024)));
+    auto capped = [&](int g) { return (int)std::min<uint64_t>((uint64_t)g, cta_cap); };
     if (h->prec == QCM_C64 && n_active >= 1) {
         auto k = k_diag_multi<float, 2, 4>;
         if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, (1ull << n_active) / 2)), kThreads, smem, h->stream>>>(a, runs);
+        k<<<bgrid(h, capped(grid_for(h, k, smem, kThreads * 4, (1ull << n_active) / 2))), kThreads, smem, h->stream>>>(a, runs);
     } else if (h->prec == QCM_C64) {
         auto k = k_diag_multi<float, 1, 4>;
         if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -726,7 +733,7 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
     } else {
         auto k = k_diag_multi<double, 1, 4>;
         if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<bgrid(h, grid_for(h, k, smem, kThreads * 4, 1ull << n_active)), kThreads, smem, h->stream>>>(a, runs);
+        k<<<bgrid(h, capped(grid_for(h, k, smem, kThreads * 4, 1ull << n_active))), kThreads, smem, h->stream>>>(a, runs);
     }
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
