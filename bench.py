@@ -675,7 +675,8 @@ def sweep_bench(args, world, rank, device, barrier, torch, dist):
                 'sweep': {'launches_per_sweep': int(launches) // max(args.steps, 1), 'algorithmic_bytes_per_sweep': int(algo),
                           'hbm_gbs_whole_sweep': algo / (ms_step * 1e-3) / 1e9, 'frac_of_peak_whole_sweep': algo / (ms_step * 1e-3) / 1e9 / peak,
                           'passes': [{'kernel': nm, 'ms': r[1], 'gbs': (r[2] + r[3]) / max(r[1], 1e-9) / 1e6} for nm, r in launches_all],
-                          'sample_ms': prof['sample_ms'], 'postselect_ms': prof['postselect_ms']},
+                          'sample_ms': prof['sample_ms'], 'postselect_ms': prof['postselect_ms'],
+                          'host_wall_ms_program_shots_projection_postselect': prof.get('host_wall_ms')},
                 'check': dict({'points_checked_vs_brute_force': chk, 'all_ranks_ok': bool(all(oks)),
                                'shots': int(sum(counts[-1].values())), 'delta_first_last': [deltas[0], deltas[-1]]})}
         print(json.dumps(line), flush=True)

@@ -589,7 +589,9 @@ class B200Simulator:
             raise ValueError('a sweep chunk needs at least two points')
         h = self._handle(sw.n_phys, precision, batch=B)
         self._last = h
+        tw = [time.perf_counter()]
         h.run_program(sw.ops, sw.tables[sl])
+        tw.append(time.perf_counter())
         prof = {'program': list(zip(h.op_kernels(), h.op_profile())), 'projection': [], 'points': B}
         keys = None
         if shots:
@@ -598,19 +600,23 @@ class B200Simulator:
                 keys = h.sample_released_batched(shots, seed, streams, n_ctrl, ctrl, sw.p1[sl], p1_off, vclbit, clbit_pos, n_cl)
             else:
                 keys = h.sample_batched(shots, seed, streams, sw.clbit_map if len(sw.clbit_map) else None)
+        tw.append(time.perf_counter())
         probs = kept = None
         if pmf is not False and sw.ps is not None and sw.n_vars <= 30:
             if sw.proj_ops is not None:
                 h.run_program(sw.proj_ops, sw.proj_tables[sl])      # project the released qubits on 0 (after the shots)
                 prof['projection'] = list(zip(h.op_kernels(), h.op_profile()))
+            tw.append(time.perf_counter())
             mask, value, n = sw.ps
             if pmf:
                 probs, kept = h.postselect(mask, value, n)
             else:
                 kept = h.postselect_resident(mask, value, n)
                 probs = [_ResidentProbs(h, y, n) for y in range(B)]
+        tw.append(time.perf_counter())
         t = h.timing()
         prof['sample_ms'], prof['postselect_ms'] = (t['sample_ms'] if shots else 0.0), (t['postselect_ms'] if kept is not None else 0.0)
+        prof['host_wall_ms'] = [round((b - a) * 1e3, 3) for a, b in zip(tw[:-1], tw[1:])]   # program, shots, projection, post-selection
         self.sweep_profile = prof                             # per-launch record of the last sweep chunk (bench.py)
         return keys, probs, kept
 

@@ -110,6 +110,8 @@ int ensure(qcm_handle h, DevBuf &b, size_t bytes) {
 
 inline size_t amp_bytes(int prec) { return prec == QCM_C64 ? 8 : 16; }
 inline size_t real_bytes(const qcm_sim_s *h) { return h->prec == QCM_C64 ? 4 : 8; }
+// the program's tables in the state's real type: a float copy for complex64, the fp64 upload itself for complex128
+inline const void *tabreal(const qcm_sim_s *h) { return h->prec == QCM_C64 ? h->tab_real.p : h->tab_f64.p; }
 // batch strides (bytes) of the state and of the per-point tables in the state's real type / in fp64
 inline uint64_t bstate(const qcm_sim_s *h) { return (uint64_t)amp_bytes(h->prec) << h->n_local; }
 inline uint64_t btab(const qcm_sim_s *h) { return (uint64_t)h->tab_stride * real_bytes(h); }
@@ -259,7 +261,7 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     BlockArgs &a = bp.args;
     bp.M = M;
     a.state = h->state;
-    a.tables = h->tab_real.p;
+    a.tables = tabreal(h);
     a.n_in = n_in;
     a.n_out = n_out;
     a.n_members = n_mem;
@@ -324,7 +326,7 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     if (tree) {
         ExpandTreeArgs &t = bp.trargs;
         t.state = h->state;
-        t.tables = h->tab_real.p;
+        t.tables = tabreal(h);
         t.n_in = n_in;
         t.M = M;
         t.n_diag = 0;
@@ -647,7 +649,7 @@ int launch_diag(qcm_handle h, const qcm_op &op, size_t n_tables) {
         a.ctrl[j] = (int8_t)op.ctrl[j];
     }
     const size_t real_sz = h->prec == QCM_C64 ? 4 : 8;
-    a.table = (const char *)h->tab_real.p + (size_t)op.table_off * real_sz;
+    a.table = (const char *)tabreal(h) + (size_t)op.table_off * real_sz;
     const size_t smem = (2ull << op.n_ctrl) * real_sz;
     const uint64_t cta_cap = std::max<uint64_t>((uint64_t)(4 * h->num_sms + h->batch - 1) / h->batch,
                                               (amp_bytes(h->prec) << a.n_active) / (16 * std::max<size_t>(smem, 1024)));
@@ -677,7 +679,7 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
     if (n_mem < 1 || n_mem > QCM_MAX_MEMBERS) return fail(h, QCM_ERR_INVALID, "diagonal block with %d members (max %d)", n_mem, QCM_MAX_MEMBERS);
     BlockArgs a{};
     a.state = h->state;
-    a.tables = h->tab_real.p;
+    a.tables = tabreal(h);
     a.n_in = a.n_out = n_active;
     a.n_members = n_mem;
     a.rank_bits = rank_bits(h);
@@ -832,10 +834,7 @@ int upload_tables(qcm_handle h, const double *tables, size_t n_per_point) {
         if ((rc = ensure(h, h->tab_real, n_tables * sizeof(float)))) return rc;
         QCM_CUDA(h, cudaMemcpyAsync(h->tab_real.p, f.data(), n_tables * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         QCM_CUDA(h, cudaStreamSynchronize(h->stream));     // f goes out of scope
-    } else {
-        if ((rc = ensure(h, h->tab_real, n_tables * sizeof(double)))) return rc;
-        QCM_CUDA(h, cudaMemcpyAsync(h->tab_real.p, h->tab_f64.p, n_tables * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    }
+    }                                  // complex128: the fp64 upload IS the table in the state's real type (tabreal)
     return QCM_OK;
 }
 
@@ -1468,7 +1467,7 @@ int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const doubl
         a.src[r] = src_slabs[r];
     }
     a.dst = dst_state;
-    a.tables = h->tab_real.p;
+    a.tables = tabreal(h);
     a.n_local = h->n_local;
     a.s = s;
     a.n_members = n_mem;
