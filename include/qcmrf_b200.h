@@ -236,6 +236,19 @@ int qcm_ipc_close(int device, void *base);
 int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
                          const void *const *src_slabs, int s, void *dst_state);
 
+/* The same fused pass IN PLACE (no second state buffer: serves shards that fill the GPU).  The output overwrites this
+ * rank's own slabs; per-(tile, peer) flags in peer-mapped memory order each overwrite behind the peer's read of the
+ * same memory (see k_block_gather_inplace).  flag_ptrs[r] (r < 2^s): device pointer, valid in this process, to the flag
+ * array (uint32, qcm_gather_flag_words entries, zero-initialised once) of the rank with coordinate r -- the entry of this
+ * rank's own coordinate is its local array; epoch: > 0 and larger on every call of the same arrays.  Every rank of the
+ * group must make the call (the kernels signal each other); bracket it with cross-rank barriers as for
+ * qcm_run_gather_block.  A peer that never signals is reported as QCM_ERR_CUDA after QCM_GATHER_SPIN_S seconds
+ * (default 5) instead of hanging the GPU.                                                                  */
+int qcm_gather_flag_words(int n_local, int s, int precision, uint64_t *words_out);
+int qcm_run_gather_block_inplace(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
+                                 const void *const *src_slabs, int s, void *const *flag_ptrs, uint64_t flag_words,
+                                 uint32_t epoch);
+
 /* Batched small circuits (all fixture-sized models in one launch: one thread block
  * per circuit, state resident in shared memory, program + post-selection + sampling
  * fused).  Circuit c has n_qubits[c] <= qcm_small_max_qubits(precision) qubits, ops

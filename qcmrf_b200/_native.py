@@ -42,7 +42,8 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_ipc_export', 'qcm_ipc_open', 'qcm_ipc_close', 'qcm_op_kernel_name',
            'qcm_sample_released', 'qcm_create_batched', 'qcm_batch_size', 'qcm_batch_select',
            'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched',
-           'qcm_sample_sharded_devmass', 'qcm_mrf_exact', 'qcm_mrf_last_error']
+           'qcm_sample_sharded_devmass', 'qcm_mrf_exact', 'qcm_mrf_last_error', 'qcm_gather_flag_words',
+           'qcm_run_gather_block_inplace']
 
 
 def lib():
@@ -94,6 +95,8 @@ def lib():
     L.qcm_postselect_resident.argtypes = [vp, u64, u64, i32, vp]
     L.qcm_fetch_probs.argtypes = [vp, i32, u64, u64, vp]
     L.qcm_sample_batched.argtypes = [vp, u64, u64, vp, vp, i32, vp]
+    L.qcm_gather_flag_words.argtypes = [i32, i32, i32, ctypes.POINTER(u64)]
+    L.qcm_run_gather_block_inplace.argtypes = [vp, vp, i32, vp, ctypes.c_size_t, vp, i32, vp, u64, ctypes.c_uint32]
     L.qcm_mrf_exact.argtypes = [i32, i32, i32, vp, vp, vp, ctypes.POINTER(dbl), vp, vp, ctypes.POINTER(dbl)]
     L.qcm_mrf_last_error.restype = ctypes.c_char_p
     L.qcm_sample_sharded_devmass.argtypes = [vp, u64, u64, u64, vp, ctypes.c_int64, i32, vp, i32, vp, vp]
@@ -274,6 +277,16 @@ class Handle:
         self._check(lib().qcm_run_gather_block(self._h, _ptr(ops), len(ops), _ptr(tables), tables.size, src, s,
                                                ctypes.c_void_p(int(dst_ptr))))
 
+    def run_gather_block_inplace(self, ops, tables, src_slab_ptrs, flag_ptrs, flag_words, epoch):
+        """qcm_run_gather_block_inplace: the fused qubit swap + blocked pass writing over this rank's own slabs."""
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        tables = np.ascontiguousarray(tables, dtype=np.float64)
+        src = (ctypes.c_void_p * len(src_slab_ptrs))(*[ctypes.c_void_p(int(p)) for p in src_slab_ptrs])
+        fl = (ctypes.c_void_p * len(flag_ptrs))(*[ctypes.c_void_p(int(p)) for p in flag_ptrs])
+        s = len(src_slab_ptrs).bit_length() - 1
+        self._check(lib().qcm_run_gather_block_inplace(self._h, _ptr(ops), len(ops), _ptr(tables), tables.size, src, s, fl,
+                                                       int(flag_words), int(epoch)))
+
     def postselect_device(self, mask, value, n_out_bits, dev_probs_ptr, dev_kept_ptr):
         """qcm_postselect_device: results stay on the GPU (device pointers), no synchronisation."""
         self._check(lib().qcm_postselect_device(self._h, int(mask), int(value), int(n_out_bits),
@@ -421,3 +434,11 @@ def mrf_exact(cliques, weights, n=None, want_pmf=True, want_energies=False, devi
     if rc:
         raise NativeError(rc, (lib().qcm_mrf_last_error() or b'').decode())
     return lz.value, pmf, en, ms.value
+
+
+def gather_flag_words(n_local, s, precision):
+    """Entries (uint32) of one rank's flag array for qcm_run_gather_block_inplace."""
+    w = ctypes.c_uint64()
+    _check_global(lib().qcm_gather_flag_words(int(n_local), int(s), QCM_C64 if precision in ('single', 'c64', 32) else QCM_C128,
+                                              ctypes.byref(w)))
+    return w.value

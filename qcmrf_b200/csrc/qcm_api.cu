@@ -50,6 +50,7 @@ struct qcm_sim_s {
     DevBuf lowpart;                 // its per-CTA partial sums when a CTA covers fewer inputs than a tree chunk
     DevBuf relp1;                   // released-qubit probability tables (qcm_sample_released)
     DevBuf streams, totals;         // batched sampling: per-point Philox streams and total masses
+    DevBuf errflag;                 // in-place fused exchange: spin-timeout flag
     // rotated storage (QCM_FLAG_ROTATED_OUTPUT_OK): logical index i of the 2^n_active state lives at
     // physical address ((i & (2^rot_nin - 1)) << rot_m) | (i >> rot_nin); rot_m == 0: identity
     int rot_m = 0, rot_nin = 0;
@@ -1005,6 +1006,32 @@ static int launch_gather_m(qcm_handle h, int M, const GatherArgs &a, size_t smem
     return fail(h, QCM_ERR_INVALID, "gather block of %d qubits out of range", M);
 }
 
+// tiles of the in-place fused exchange: one 16-byte vector per consumer thread (U = 1), K consecutive tiles per CTA
+static uint64_t gather_inplace_tiles(int n_local, int s, int prec) {
+    const uint64_t vec = (1ull << (n_local - s)) / (prec == QCM_C64 ? 2 : 1);
+    return vec / kThreads;
+}
+
+template <typename R, int V, int M>
+static int launch_gather_inplace(qcm_handle h, const GatherArgs &a, const GatherFlags &f, size_t tab_bytes) {
+    constexpr int S = GatherStages<M>::value;
+    auto kern = k_block_gather_inplace<R, V, M, 1, S>;
+    const size_t smem = 256 + (size_t)S * (1 << M) * kGatherTileBytes + tab_bytes;
+    if (smem > 227 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "gather ring needs %zu B of shared memory", smem);
+    QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t tiles = ((1ull << (a.n_local - M)) / V) / kThreads;
+    int K = env_int("QCM_GATHER_K", 16);
+    int p2 = 1;
+    while (p2 * 2 <= K) p2 *= 2;
+    while (p2 > 1 && (tiles % p2 || tiles / p2 < 1)) p2 >>= 1;
+    const uint64_t grid = tiles / p2;
+    if (grid > 0x7fffffffull) return fail(h, QCM_ERR_UNSUPPORTED, "gather grid too large");
+    kern<<<(unsigned)grid, kThreads + 32, smem, h->stream>>>(a, f, p2);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    return QCM_OK;
+}
+
 int check_device(qcm_handle h) {
     QCM_CUDA(h, cudaSetDevice(h->device));
     return QCM_OK;
@@ -1143,7 +1170,7 @@ int qcm_destroy(qcm_handle h) {
     if (!h) return QCM_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree, &h->scratch, &h->lowpart, &h->relp1, &h->streams, &h->totals};
+    DevBuf *bufs[] = {&h->tab_f64, &h->tab_real, &h->init_lo, &h->init_hi, &h->probs, &h->partial, &h->keys, &h->mine, &h->tree, &h->ctab, &h->tilectr, &h->subtree, &h->scratch, &h->lowpart, &h->relp1, &h->streams, &h->totals, &h->errflag};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->own_state && h->state) cudaFree(h->state);
@@ -1430,8 +1457,31 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     return QCM_OK;
 }
 
+static int gather_block_impl(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
+                             const void *const *src_slabs, int s, void *dst_state, void *const *flag_ptrs, uint64_t flag_words,
+                             uint32_t epoch);
+
 int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
                          const void *const *src_slabs, int s, void *dst_state) {
+    return gather_block_impl(h, ops, n_ops, tables, n_tables, src_slabs, s, dst_state, nullptr, 0, 0);
+}
+
+int qcm_gather_flag_words(int n_local, int s, int precision, uint64_t *words_out) {
+    if (!words_out || s < 1 || s > QCM_MAX_GATHER || s >= n_local || (precision != QCM_C64 && precision != QCM_C128))
+        return fail(nullptr, QCM_ERR_INVALID, "bad argument");
+    *words_out = std::max<uint64_t>(1, gather_inplace_tiles(n_local, s, precision)) << s;
+    return QCM_OK;
+}
+
+int qcm_run_gather_block_inplace(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
+                                 const void *const *src_slabs, int s, void *const *flag_ptrs, uint64_t flag_words, uint32_t epoch) {
+    if (!flag_ptrs || !epoch) return fail(h, QCM_ERR_INVALID, "NULL flag array / zero epoch");
+    return gather_block_impl(h, ops, n_ops, tables, n_tables, src_slabs, s, h ? h->state : nullptr, flag_ptrs, flag_words, epoch);
+}
+
+static int gather_block_impl(qcm_handle h, const qcm_op *ops, int n_ops, const double *tables, size_t n_tables,
+                             const void *const *src_slabs, int s, void *dst_state, void *const *flag_ptrs, uint64_t flag_words,
+                             uint32_t epoch) {
     if (!h || !ops || n_ops < 1 || !src_slabs || !dst_state) return fail(h, QCM_ERR_INVALID, "NULL argument");
     if (s < 1 || s > QCM_MAX_GATHER || s > h->n_global || s >= h->n_local) return fail(h, QCM_ERR_INVALID, "cannot gather %d qubits", s);
     if (h->n_active != h->n_local) return fail(h, QCM_ERR_INVALID, "gather needs a fully materialised shard");
@@ -1474,7 +1524,38 @@ int qcm_run_gather_block(qcm_handle h, const qcm_op *ops, int n_ops, const doubl
     a.ctrl_below_32 = bp.args.ctrl_below_32;
     a.rank_bits = rank_bits(h);
     for (int g = 0; g < n_mem; ++g) a.mem[g] = bp.args.mem[g];
-    if (h->prec == QCM_C64) rc = launch_gather_m<float, 2>(h, s, a, bp.smem);
+    if (flag_ptrs) {
+        // in place: the output overwrites this rank's own slabs, ordered against the peers' reads by per-tile flags
+        const uint64_t tiles = gather_inplace_tiles(h->n_local, s, h->prec);
+        if (tiles < 1 || (tiles << s) > flag_words) return fail(h, QCM_ERR_INVALID, "flag arrays too small: %llu words needed", (unsigned long long)(tiles << s));
+        GatherFlags f{};
+        int c_me = 0;
+        for (int r = 0; r < (1 << s); ++r) {
+            if (!flag_ptrs[r]) return fail(h, QCM_ERR_INVALID, "flag_ptrs[%d] is NULL", r);
+            f.flags[r] = (uint32_t *)flag_ptrs[r];
+            if ((const char *)src_slabs[r] >= (const char *)h->state && (const char *)src_slabs[r] < (const char *)h->state + bstate(h)) c_me = r;
+        }
+        f.c_me = c_me;                           // the source that lies inside this rank's own state is its own coordinate
+        f.epoch = epoch;
+        if ((rc = ensure(h, h->errflag, sizeof(int)))) return rc;
+        QCM_CUDA(h, cudaMemsetAsync(h->errflag.p, 0, sizeof(int), h->stream));
+        f.err = (int32_t *)h->errflag.p;
+        int khz = 1900000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+        f.spin_limit = (long long)khz * 1000ll * (long long)std::max(1, env_int("QCM_GATHER_SPIN_S", 5));
+        if (h->prec == QCM_C64) {
+            rc = s == 1 ? launch_gather_inplace<float, 2, 1>(h, a, f, bp.smem) : s == 2 ? launch_gather_inplace<float, 2, 2>(h, a, f, bp.smem)
+                                                                                        : launch_gather_inplace<float, 2, 3>(h, a, f, bp.smem);
+        } else {
+            rc = s == 1 ? launch_gather_inplace<double, 1, 1>(h, a, f, bp.smem) : s == 2 ? launch_gather_inplace<double, 1, 2>(h, a, f, bp.smem)
+                                                                                         : launch_gather_inplace<double, 1, 3>(h, a, f, bp.smem);
+        }
+        if (rc) return rc;
+        int err = 0;
+        QCM_CUDA(h, cudaMemcpyAsync(&err, h->errflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (err) return fail(h, QCM_ERR_CUDA, "in-place fused exchange: a peer did not signal within the spin limit (ranks out of step?)");
+    } else if (h->prec == QCM_C64) rc = launch_gather_m<float, 2>(h, s, a, bp.smem);
     else rc = launch_gather_m<double, 1>(h, s, a, bp.smem);
     if (rc) return rc;
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));

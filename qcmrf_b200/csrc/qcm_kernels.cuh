@@ -704,6 +704,166 @@ __global__ void __launch_bounds__(kThreads + 32) k_block_gather_tma(const __grid
 }
 
 // ----------------------------------------------------------------------------------
+// The fused qubit swap + gate pass IN PLACE: no second state buffer, so it also serves shards that fill the GPU
+// (37 qubits on 8 GPUs: 128 GiB per rank).  Same data flow as k_block_gather_tma -- rank c reads slab c of every
+// peer r and its own, applies the members, and writes the 2^s results over ITS OWN slabs r -- plus one flag per
+// (tile, peer) that orders the two accesses to the same memory:
+//     peer r reads  my.state[slab r][tile t]      (it needs it as its input)
+//     I overwrite   my.state[slab r][tile t]      (with my output)
+// Once my bulk copy of peer r's tile t has landed in shared memory I store `epoch` to peer r's flag
+// [t][c] (st.release.sys over NVLink); before I overwrite my slab r of tile t I wait until MY flag [t][r] shows
+// the epoch (ld.acquire.sys).  Stores are delayed by one tile (results wait in registers), so the flag was
+// raised a whole tile earlier and the wait almost never spins.  Everybody reads before waiting and CTAs are
+// dispatched in tile order on every rank, so there is no circular wait; a spin that exceeds `spin_limit` clocks
+// gives up and raises *err (the host reports it) instead of hanging the GPU.
+// ----------------------------------------------------------------------------------
+struct GatherFlags {
+    uint32_t *flags[1 << QCM_MAX_GATHER];   // flags[r]: rank (coordinate) r's array [tiles][2^s], peer-mapped; [c_me]: local
+    uint32_t epoch;
+    int32_t c_me;
+    int32_t *err;
+    long long spin_limit;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename R, int V, int M, int U, int STAGES>
+__global__ void __launch_bounds__(kThreads + 32) k_block_gather_inplace(const __grid_constant__ GatherArgs a, const __grid_constant__ GatherFlags f,
+                                                                        const int tiles_per_cta) {
+    constexpr int NR = 1 << M;
+    constexpr uint32_t kTile = kGatherTileBytes * U;             // bytes per source per stage
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);     // full[STAGES], empty[STAGES]
+    unsigned char *ring = smem_raw + 256;
+    R *tab = reinterpret_cast<R *>(ring + (size_t)STAGES * NR * kTile);
+    static_assert(2 * STAGES * 8 <= 256, "barrier block");
+    for (int g = 0; g < a.n_members; ++g) {
+        const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
+        R *dst = tab + a.mem[g].tab_off;
+        const int cnt = (a.mem[g].pos < 0 ? 2 : 8) << a.mem[g].n_ctrl;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+    }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < STAGES; ++st) {
+            mbar_init(smem_u32(bars + st), 1);
+            mbar_init(smem_u32(bars + STAGES + st), kThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t slab = 1ull << (a.n_local - M);
+    const uint64_t tile0 = (uint64_t)blockIdx.x * tiles_per_cta;
+    if (threadIdx.x >= kThreads) {
+        if (threadIdx.x == kThreads) {
+            for (int k = 0; k < tiles_per_cta; ++k) {
+                const int st = k % STAGES;
+                if (k >= STAGES) mbar_wait(smem_u32(bars + STAGES + st), ((k / STAGES) - 1) & 1);
+                const uint32_t full = smem_u32(bars + st);
+                mbar_expect_tx(full, NR * kTile);
+#pragma unroll
+                for (int r = 0; r < NR; ++r)
+                    bulk_g2s(smem_u32(ring + ((size_t)st * NR + r) * kTile),
+                             reinterpret_cast<const unsigned char *>(a.src[r]) + (tile0 + k) * kTile, kTile, full);
+            }
+        }
+        return;
+    }
+    using IO = VecIO<R, V>;
+    R pr[U][NR][V], pi[U][NR][V];                                // the previous tile's results, waiting for their flags
+    auto flush = [&](uint64_t tile) {
+        // every peer has read the slabs of `tile` that are about to be overwritten
+        if (threadIdx.x < NR && (int)threadIdx.x != f.c_me) {
+            const uint32_t *p = f.flags[f.c_me] + tile * NR + threadIdx.x;
+            const long long t0 = clock64();
+            while ((int32_t)(ld_acquire_sys(p) - f.epoch) < 0) {
+                if (clock64() - t0 > f.spin_limit) { *f.err = 1; break; }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+        const uint64_t bv0 = tile * ((uint64_t)kThreads * U) + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                IO::store(a.dst, (uint64_t)r * slab + (bv0 + (uint64_t)u * kThreads) * V, pr[u][r], pi[u][r]);
+    };
+    for (int k = 0; k < tiles_per_cta; ++k) {
+        const int st = k % STAGES;
+        mbar_wait(smem_u32(bars + st), (k / STAGES) & 1);
+        // the peers' tile (tile0 + k) is in shared memory: they may overwrite what was read
+        if (threadIdx.x < NR && (int)threadIdx.x != f.c_me)
+            st_release_sys(f.flags[threadIdx.x] + (tile0 + k) * NR + f.c_me, f.epoch);
+        R ar[U][NR][V], ai[U][NR][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const unsigned char *sp = ring + ((size_t)st * NR + r) * kTile + ((size_t)u * kThreads + threadIdx.x) * 16;
+                if constexpr (V == 2) {
+                    const float4 t = *reinterpret_cast<const float4 *>(sp);
+                    ar[u][r][0] = t.x; ai[u][r][0] = t.y; ar[u][r][1] = t.z; ai[u][r][1] = t.w;
+                } else {
+                    const double2 d = *reinterpret_cast<const double2 *>(sp);
+                    ar[u][r][0] = d.x; ai[u][r][0] = d.y;
+                }
+            }
+        if (k > 0) flush(tile0 + k - 1);
+        const uint64_t bv0 = (tile0 + k) * ((uint64_t)kThreads * U) + threadIdx.x;
+        for (int g = 0; g < a.n_members; ++g) {
+            const int pos = a.mem[g].pos;
+            const int nc = a.mem[g].n_ctrl;
+            const R *mt = tab + a.mem[g].tab_off;
+            const uint32_t low_bit = a.mem[g].low_bit;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t gi = ((bv0 + (uint64_t)u * kThreads) * V) | a.rank_bits;
+                uint32_t idx0 = 0;
+                for (int j = 0; j < nc; ++j) idx0 |= (uint32_t)((gi >> a.mem[g].ctrl[j]) & 1ull) << j;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const uint32_t idx = v ? (idx0 | low_bit) : idx0;
+                    if (pos < 0) {
+                        const R c = mt[2 * idx], sn = mt[2 * idx + 1];
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            const R x = ar[u][r][v], y = ai[u][r][v];
+                            ar[u][r][v] = c * x - sn * y;
+                            ai[u][r][v] = c * y + sn * x;
+                        }
+                        continue;
+                    }
+                    R m[8];
+                    load_m8<R>(mt + 8 * idx, m);
+                    switch (pos) {
+                        case 0: butterfly<R, V, NR, 0, false>(ar[u], ai[u], m, v, 0u); break;
+                        case 1: butterfly<R, V, NR, 1, false>(ar[u], ai[u], m, v, 0u); break;
+                        default: butterfly<R, V, NR, 2, false>(ar[u], ai[u], m, v, 0u); break;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+                for (int v = 0; v < V; ++v) { pr[u][r][v] = ar[u][r][v]; pi[u][r][v] = ai[u][r][v]; }
+        // release the stage behind the arithmetic that consumed every register loaded from it (see k_block_gather_tma)
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(bars + STAGES + st));
+    }
+    flush(tile0 + tiles_per_cta - 1);
+}
+
+// ----------------------------------------------------------------------------------
 // Expansion pass (lazy materialisation fast path).
 //
 // All M block qubits are the new qubits n_in .. n_in+M-1, each the target of exactly
@@ -1628,6 +1788,10 @@ __device__ __forceinline__ uint32_t warp_pick(F w, uint32_t cnt, double &u, int 
     else sel = 0;
     const double excl = __shfl_sync(0xffffffffu, incl - mine, sel);
     double rem = u - excl;
+    if (cnt <= 32u) {                                 // one child per lane (a 32-ary tree level): the lane IS the child
+        u = rem < 0.0 ? 0.0 : rem;
+        return (uint32_t)sel < cnt ? (uint32_t)sel : 0u;
+    }
     uint32_t child = 0;
     double before = 0.0;
     if (lane == sel) {

@@ -403,12 +403,17 @@ class ShardedSimulator:
         if layout not in ('auto', 'canonical'):
             raise ValueError("layout must be 'auto' or 'canonical'")
         self.layout = layout      # auto: shard on control-only qubits when the circuit has them (no communication)
-        if exchange not in ('nccl', 'p2p'):
-            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        if exchange not in ('nccl', 'p2p', 'p2p-inplace'):
+            raise ValueError("exchange must be 'nccl', 'p2p' or 'p2p-inplace'")
         # 'p2p': a qubit swap followed by sweeps on the swapped-in qubits runs as ONE kernel that reads the
         # peers' shards over NVLink (CUDA IPC mapped) and writes a second local buffer -- needs 2x the
-        # shard in memory; anything it cannot serve falls back to the NCCL all-to-all + local passes
+        # shard in memory; anything it cannot serve falls back to the NCCL all-to-all + local passes.
+        # 'p2p-inplace': the same kernel writing over the rank's own slabs, ordered against the peers' reads by
+        # per-tile flags in peer-mapped memory (k_block_gather_inplace) -- no second buffer, any shard size
         self.exchange = exchange
+        self._flags = None         # p2p-inplace: local flag tensor; _peer_flags: rank -> its address here
+        self._peer_flags = None
+        self._epoch = 0
         self._bufs = None          # p2p: [A, B] local state tensors
         self._peer_bufs = None     # p2p: rank -> [A, B] device addresses mapped from that rank (CUDA IPC)
         self._ipc_open = {}
@@ -444,7 +449,7 @@ class ShardedSimulator:
         self.close()
         self._h, self._state = self._alloc_state(n_local)
         self._n_local = n_local
-        if self.exchange == 'p2p' and self._state.is_cuda:
+        if self.exchange in ('p2p', 'p2p-inplace') and self._state.is_cuda:
             try:
                 self._map_peers()
             except Exception as e:                       # IPC not available: stay on NCCL
@@ -457,10 +462,16 @@ class ShardedSimulator:
         GPU current (qcm_ipc_open: cudaIpcOpenMemHandle + lazy peer access, the way NCCL's P2P transport
         maps its peers), so kernels launched here dereference them over NVLink."""
         t, dist = self.torch, self.dist
-        other = t.empty_like(self._state)
-        self._bufs = [self._state, other]
+        inplace = self.exchange == 'p2p-inplace'
+        if inplace:
+            self._bufs = [self._state]
+            words = max(_native.gather_flag_words(self._n_local, s, self.precision) for s in range(1, min(self.g, 3) + 1))
+            self._flags = t.zeros(words, dtype=t.int32, device=self._state.device)
+            self._flag_words = words
+        else:
+            self._bufs = [self._state, t.empty_like(self._state)]
         self._cur = 0
-        meta = [_native.ipc_export(self.device, x.data_ptr()) for x in self._bufs]
+        meta = [_native.ipc_export(self.device, x.data_ptr()) for x in self._bufs + ([self._flags] if inplace else [])]
         gathered = [None] * self.world
         dist.all_gather_object(gathered, meta, group=self.group)
         peer_ptrs = {}
@@ -469,7 +480,7 @@ class ShardedSimulator:
         try:
             for r in range(self.world):
                 if r == self.rank:
-                    peer_ptrs[r] = [x.data_ptr() for x in self._bufs]
+                    peer_ptrs[r] = [x.data_ptr() for x in self._bufs + ([self._flags] if inplace else [])]
                     continue
                 ptrs = []
                 for hd, off in gathered[r]:
@@ -484,6 +495,9 @@ class ShardedSimulator:
         if any(errs):
             self._unmap_peers()
             raise RuntimeError('peer mapping failed: %s' % [e for e in errs if e][0])
+        if inplace:
+            self._peer_flags = {r: p[-1] for r, p in peer_ptrs.items()}
+            peer_ptrs = {r: p[:-1] for r, p in peer_ptrs.items()}
         self._peer_bufs = peer_ptrs
 
     def _unmap_peers(self):
@@ -509,7 +523,7 @@ class ShardedSimulator:
             self._h.close()
         self._unmap_peers()
         self._h = self._state = self._stage = None
-        self._bufs = self._peer_bufs = None
+        self._bufs = self._peer_bufs = self._flags = self._peer_flags = None
         self._n_local = None
 
     # ---- preparation -----------------------------------------------------------------------
@@ -520,7 +534,7 @@ class ShardedSimulator:
         ng = 0
         if lazy and self.layout == 'auto' and len(fusion.control_only_qubits(fc)) >= self.g:
             ng = self.g
-        fuse_x = self.exchange == 'p2p'
+        fuse_x = self.exchange in ('p2p', 'p2p-inplace')
 
         def build(f):
             p = fusion.plan(f, lazy=lazy, block_max=self.block_max, n_global=ng,
@@ -661,18 +675,27 @@ class ShardedSimulator:
         for b in betas:
             base &= ~(1 << b)
         slab_bytes = self._state.element_size() * (2 << (sp.n_local - s))
-        src = []
+        src, peers = [], []
         for j in range(1 << s):
             pr = base
             for i, b in enumerate(betas):
                 pr |= ((j >> i) & 1) << b
+            peers.append(pr)
             src.append(self._peer_bufs[pr][self._cur] + c_me * slab_bytes)
-        dst = self._bufs[1 - self._cur]
         t.cuda.synchronize()
         dist.barrier(group=self.group)          # every peer has finished writing the buffers read below
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         e0.record()
         h.set_shard(sp.g, sp.rank & mask)
+        if self._peer_flags is not None:
+            # in place: the kernels of all ranks order their overwrites behind each other's reads with flags
+            self._epoch += 1
+            h.run_gather_block_inplace(ops, tabs, src, [self._peer_flags[pr] for pr in peers], self._flag_words, self._epoch)
+            e1.record()
+            t.cuda.synchronize()
+            dist.barrier(group=self.group)      # every peer's kernel is done: its signals and reads are behind us
+            return e0.elapsed_time(e1)
+        dst = self._bufs[1 - self._cur]
         h.run_gather_block(ops, tabs, src, dst.data_ptr())
         e1.record()
         t.cuda.synchronize()
@@ -910,7 +933,8 @@ class ShardedSimulator:
                             'meta': {'path': 'sharded', 'ranks': self.world, 'n_qubits': pr.prog.n_qubits,
                                      'n_phys': pr.plan.n_phys, 'n_local': pr.sp.n_local, 'passes': pr.plan.n_passes,
                                      'exchanges': pr.sp.n_exchanges, 'exchange_ms': self.exchange_ms,
-                                     'exchange_path': 'p2p-fused' if self._peer_bufs is not None else 'nccl',
+                                     'exchange_path': ('p2p-fused-inplace' if self._peer_flags is not None else 'p2p-fused')
+                                     if self._peer_bufs is not None else 'nccl',
                                      'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': i}})
         return Job(Result(entries, single, self._name, seed, int(shots), time.perf_counter() - t0))
 

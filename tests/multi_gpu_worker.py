@@ -33,7 +33,7 @@ def main():
         kp_full = np.abs(psi) ** 2
     quick = os.environ.get('QCM_MGW_QUICK') == '1'           # smoke(): the default layout + the NCCL exchange, complex64
     layouts = [('blocked', 'auto', 'nccl'), ('blocked', 'canonical', 'nccl'), ('clique', 'canonical', 'nccl'),
-               ('clique', 'canonical', 'p2p')]
+               ('clique', 'canonical', 'p2p'), ('clique', 'canonical', 'p2p-inplace')]
     for prec, tol in ((('single', 1e-5),) if quick else (('double', 1e-10), ('single', 1e-5))):
         for fus, layout, xch in ([layouts[0], layouts[2]] if quick else layouts):
             sim = ShardedSimulator(precision=prec, fusion=fus, layout=layout, device=lr, seed=77, block_max=3,
@@ -48,8 +48,9 @@ def main():
             assert sum(counts.values()) == 200000
             meta = res.metadata(0)
             assert meta['exchanges'] == (1 if fus == 'clique' else 0), meta
-            if xch == 'p2p':
-                assert meta['exchange_path'] == 'p2p-fused', (meta, getattr(sim, 'p2p_error', None))
+            if xch.startswith('p2p'):
+                assert meta['exchange_path'] == {'p2p': 'p2p-fused', 'p2p-inplace': 'p2p-fused-inplace'}[xch], \
+                    (meta, getattr(sim, 'p2p_error', None))
             # every rank must hold identical results
             blob = json.dumps(sorted(counts.items())) + repr(float(delta))
             gathered = [None] * world

@@ -846,6 +846,91 @@ def test_gather_block_on_virtual_peers(precision, s, variant, monkeypatch):
     assert worst < (1e-12 if precision == 'double' else 3e-6)
 
 
+@pytest.mark.parametrize('precision', ['double', 'single'])
+@pytest.mark.parametrize('s', [1, 2, 3])
+def test_gather_block_in_place_on_virtual_peers(precision, s, monkeypatch):
+    """qcm_run_gather_block_inplace: the fused qubit swap + pass writing over each rank's own slabs, ordered by
+    per-tile flags.  The 2^s 'ranks' are handles on this GPU, each on its own stream and launched from its own thread
+    so that their kernels run concurrently and signal each other (a rank that never hears from a peer gives up after
+    QCM_GATHER_SPIN_S seconds and raises).  Expected = numpy qubit swap + the op semantics per rank; run twice (epochs)."""
+    import threading
+    import torch
+    monkeypatch.setenv('QCM_GATHER_SPIN_S', '3')
+    monkeypatch.setenv('QCM_GATHER_K', '4')
+    rng = np.random.RandomState(90 + s)
+    nl = 16
+    N = nl + s
+    world = 1 << s
+    cdt = np.complex128 if precision == 'double' else np.complex64
+    e = fusion._Emitter()
+    tq = list(range(nl - s, nl))
+
+    def rand_u(m):
+        q, _ = np.linalg.qr(rng.randn(1 << m, 2, 2) + 1j * rng.randn(1 << m, 2, 2))
+        return q
+    members = []
+    for t in tq + [tq[0]]:
+        ctrl = [int(c) for c in rng.permutation(nl - s)[:2]] + ([int(nl + rng.randint(s))] if rng.rand() < 0.6 else [])
+        members.append((fusion.QCM_OP_MUX1Q, t, ctrl, fusion._mux_table_f64(rand_u(len(ctrl)))))
+    if s == 1:
+        k, t, c, tab = members[0]
+        e.op(k, target=t, ctrl=c, n_in=nl, n_out=nl, table_off=e.table(tab))
+    else:
+        e.op(fusion.QCM_OP_BLOCK, target=s, ctrl=tq, n_in=nl, n_out=nl, n_ctrl=len(members))
+        for k, t, c, tab in members:
+            e.op(k, target=t, ctrl=c, n_in=nl, n_out=nl, table_off=e.table(tab))
+    ops, tabs = e.finish()
+    idx = np.arange(1 << N)
+    lo_mask = (1 << (nl - s)) - 1
+
+    def swap(psi):
+        a = (idx >> (nl - s)) & (world - 1)
+        b = idx >> nl
+        return psi[(idx & lo_mask) | (b << (nl - s)) | (a << nl)]
+    psi = (rng.randn(1 << N) + 1j * rng.randn(1 << N))
+    psi = (psi / np.linalg.norm(psi)).astype(cdt).astype(np.complex128)
+    states = [torch.from_numpy(np.ascontiguousarray(psi[r << nl:(r + 1) << nl].astype(cdt)).view(np.float64 if precision == 'double' else np.float32)).cuda()
+              for r in range(world)]
+    words = _native.gather_flag_words(nl, s, precision)
+    flags = [torch.zeros(words, dtype=torch.int32, device='cuda') for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    handles = [_native.Handle(nl, precision, ext_state_ptr=states[r].data_ptr(), ext_stream=streams[r].cuda_stream) for r in range(world)]
+    slab_bytes = (1 << (nl - s)) * np.dtype(cdt).itemsize
+    torch.cuda.synchronize()
+    pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, nl
+    try:
+        for epoch in (1, 2):
+            errs = [None] * world
+
+            def work(r):
+                try:
+                    h = handles[r]
+                    h.set_shard(s, r)
+                    h.set_active(nl)
+                    src = [states[j].data_ptr() + r * slab_bytes for j in range(world)]
+                    h.run_gather_block_inplace(ops, tabs, src, [f.data_ptr() for f in flags], words, epoch)
+                except Exception as ex:                       # noqa: BLE001
+                    errs[r] = ex
+            ths = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            assert not any(errs), errs
+            torch.cuda.synchronize()
+            swapped = swap(psi)
+            new = np.empty_like(psi)
+            for r in range(world):
+                want, _ = em.run_plan(pl, n_global=s, rank=r, n_local=nl, psi0=swapped[r << nl:(r + 1) << nl].copy(), active0=nl)
+                got = handles[r].get_amplitudes().astype(np.complex128)
+                assert np.abs(got - want).max() < (1e-12 if precision == 'double' else 3e-6) * (1 if epoch == 1 else 4), (epoch, r)
+                new[r << nl:(r + 1) << nl] = got
+            psi = new                                         # second epoch: the same pass again on the new state
+    finally:
+        for h in handles:
+            h.close()
+
+
 @pytest.mark.parametrize('s', [1, 2, 3])
 def test_gather_tma_ring_is_bit_identical_to_plain_loads(s, monkeypatch):
     """The TMA-ring variant of the fused gather pass against the plain-load variant on a state large
