@@ -614,6 +614,7 @@ def sweep_bench(args, world, rank, device, barrier, torch, dist):
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = sim.kernel_launches() - l0
+    sim.execute_sweep(sw, SHOTS, seed=1984, streams=streams, profile=True)      # untimed: the per-launch record
     prof = sim.sweep_profile
     e2e, e2e_keys = [], []
     for i in range(args.steps):

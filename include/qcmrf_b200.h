@@ -287,6 +287,13 @@ int qcm_run_batch_small(int device, int precision, int n_circuits,
  * A plain handle is a batched handle with B = 1.                                                       */
 int qcm_create_batched(qcm_handle *out, int device, int n_local, int precision, int batch,
                        void *ext_state, void *ext_stream);
+/* Deferred mode: qcm_run_program, qcm_postselect*, qcm_sample* enqueue their kernels and copies on the handle's
+ * stream and return without synchronising (no timings are collected); host output buffers must then be page-locked
+ * (qcm_host_alloc) and are valid after qcm_synchronize.  A sweep becomes ONE synchronisation instead of one per call,
+ * and its result copies overlap the kernels that follow.                                                        */
+int qcm_set_deferred(qcm_handle h, int deferred);
+int qcm_host_alloc(void **host_out, size_t bytes);      /* page-locked host memory (cudaHostAlloc) */
+int qcm_host_free(void *host_ptr);
 int qcm_batch_size(qcm_handle h, int *batch_out);
 int qcm_batch_select(qcm_handle h, int point);
 int qcm_postselect_resident(qcm_handle h, uint64_t mask, uint64_t value, int n_out_bits, double *kept_out);

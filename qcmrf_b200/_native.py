@@ -43,7 +43,7 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_sample_released', 'qcm_create_batched', 'qcm_batch_size', 'qcm_batch_select',
            'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched',
            'qcm_sample_sharded_devmass', 'qcm_mrf_exact', 'qcm_mrf_last_error', 'qcm_gather_flag_words',
-           'qcm_run_gather_block_inplace']
+           'qcm_run_gather_block_inplace', 'qcm_set_deferred', 'qcm_host_alloc', 'qcm_host_free']
 
 
 def lib():
@@ -95,6 +95,9 @@ def lib():
     L.qcm_postselect_resident.argtypes = [vp, u64, u64, i32, vp]
     L.qcm_fetch_probs.argtypes = [vp, i32, u64, u64, vp]
     L.qcm_sample_batched.argtypes = [vp, u64, u64, vp, vp, i32, vp]
+    L.qcm_set_deferred.argtypes = [vp, i32]
+    L.qcm_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.qcm_host_free.argtypes = [vp]
     L.qcm_gather_flag_words.argtypes = [i32, i32, i32, ctypes.POINTER(u64)]
     L.qcm_run_gather_block_inplace.argtypes = [vp, vp, i32, vp, ctypes.c_size_t, vp, i32, vp, u64, ctypes.c_uint32]
     L.qcm_mrf_exact.argtypes = [i32, i32, i32, vp, vp, vp, ctypes.POINTER(dbl), vp, vp, ctypes.POINTER(dbl)]
@@ -215,11 +218,11 @@ class Handle:
                                          ctypes.byref(kept)))
         return probs, kept.value
 
-    def postselect_resident(self, mask, value, n_out_bits):
+    def postselect_resident(self, mask, value, n_out_bits, out=None):
         """kept (array of `batch`); the probability blocks stay on the device until the next post-selection on this
         handle (fetch_probs copies one out)."""
         self.generation += 1
-        kept = np.empty(self.batch, dtype=np.float64)
+        kept = np.empty(self.batch, dtype=np.float64) if out is None else out
         self._check(lib().qcm_postselect_resident(self._h, int(mask), int(value), int(n_out_bits), _ptr(kept)))
         return kept
 
@@ -230,11 +233,15 @@ class Handle:
         self._check(lib().qcm_fetch_probs(self._h, int(point), int(first), int(count), _ptr(out)))
         return out
 
+    def set_deferred(self, flag):
+        """Deferred mode: calls enqueue and return; pass page-locked output arrays (pinned_empty) and call synchronize()."""
+        self._check(lib().qcm_set_deferred(self._h, 1 if flag else 0))
+
     def batch_select(self, point):
         self._check(lib().qcm_batch_select(self._h, int(point)))
 
-    def sample_batched(self, shots, seed, stream_ids, clbit_qubit=None):
-        keys = np.empty((self.batch, int(shots)), dtype=np.uint64)
+    def sample_batched(self, shots, seed, stream_ids, clbit_qubit=None, out=None):
+        keys = np.empty((self.batch, int(shots)), dtype=np.uint64) if out is None else out
         sid = np.ascontiguousarray(stream_ids, dtype=np.uint64)
         assert sid.size == self.batch
         cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
@@ -242,9 +249,9 @@ class Handle:
                                              0 if cq is None else len(cq), _ptr(keys)))
         return keys
 
-    def sample_released_batched(self, shots, seed, stream_ids, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_clbits):
+    def sample_released_batched(self, shots, seed, stream_ids, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_clbits, out=None):
         """p1: (batch, n_p1) released-qubit probability tables, one row per sweep point."""
-        keys = np.empty((self.batch, int(shots)), dtype=np.uint64)
+        keys = np.empty((self.batch, int(shots)), dtype=np.uint64) if out is None else out
         sid = np.ascontiguousarray(stream_ids, dtype=np.uint64)
         p1 = np.ascontiguousarray(p1, dtype=np.float64)
         assert sid.size == self.batch and p1.shape[0] == self.batch
@@ -442,3 +449,25 @@ def gather_flag_words(n_local, s, precision):
     _check_global(lib().qcm_gather_flag_words(int(n_local), int(s), QCM_C64 if precision in ('single', 'c64', 32) else QCM_C128,
                                               ctypes.byref(w)))
     return w.value
+
+
+class PinnedArray:
+    """A numpy array over page-locked host memory (qcm_host_alloc): the target of asynchronous device->host copies.
+    The memory is freed when this object is collected; `array` must not outlive it."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = ctypes.c_void_p()
+        _check_global(lib().qcm_host_alloc(ctypes.byref(p), n))
+        self._p = p
+        buf = (ctypes.c_ubyte * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._p:
+                lib().qcm_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass

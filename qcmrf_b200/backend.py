@@ -226,6 +226,7 @@ class B200Simulator:
         self.small_batch = small_batch
         self.small_fusion = small_fusion      # batched small circuits: fused programs are ~30x shorter to plan and ship
         self._handles = {}
+        self._pinned = {}                      # page-locked result buffers of the last sweep shape
         self._launches_closed = 0
         self._last = None
         self._plan_cache = plancache.PlanCache() if plan_cache else None
@@ -576,10 +577,13 @@ class B200Simulator:
             sw.p1 = np.stack([self._released_tables(pr)[3] for pr in prs])
         return sw
 
-    def execute_sweep(self, sw, shots, seed=0, streams=None, precision=None, pmf=None, first=0, count=None):
+    def execute_sweep(self, sw, shots, seed=0, streams=None, precision=None, pmf=None, first=0, count=None, profile=False):
         """Run points [first, first + count) of a prepared sweep through one batched handle: program, shots (released
         qubits drawn on the device), projection + post-selection.  Returns (keys (count, shots) or None, probs --
-        (count, 2^n) array if pmf is True, a list of _ResidentProbs if pmf is None, else None --, kept (count,) or None)."""
+        (count, 2^n) array if pmf is True, a list of _ResidentProbs if pmf is None, else None --, kept (count,) or None).
+        The calls are enqueued in the engine's deferred mode (one synchronisation at the end, results into page-locked
+        buffers that are reused by the next sweep of the same shape); profile=True runs them one by one instead and
+        leaves the per-launch record in `sweep_profile`."""
         precision = precision or self.precision
         B = len(sw.prs) - first if count is None else count
         sl = slice(first, first + B)
@@ -589,35 +593,57 @@ class B200Simulator:
             raise ValueError('a sweep chunk needs at least two points')
         h = self._handle(sw.n_phys, precision, batch=B)
         self._last = h
-        tw = [time.perf_counter()]
-        h.run_program(sw.ops, sw.tables[sl])
-        tw.append(time.perf_counter())
-        prof = {'program': list(zip(h.op_kernels(), h.op_profile())), 'projection': [], 'points': B}
-        keys = None
-        if shots:
-            if sw.released is not None:
-                mc, n_ctrl, ctrl, _p1, p1_off, vclbit, clbit_pos, n_cl = sw.released
-                keys = h.sample_released_batched(shots, seed, streams, n_ctrl, ctrl, sw.p1[sl], p1_off, vclbit, clbit_pos, n_cl)
-            else:
-                keys = h.sample_batched(shots, seed, streams, sw.clbit_map if len(sw.clbit_map) else None)
-        tw.append(time.perf_counter())
-        probs = kept = None
-        if pmf is not False and sw.ps is not None and sw.n_vars <= 30:
-            if sw.proj_ops is not None:
-                h.run_program(sw.proj_ops, sw.proj_tables[sl])      # project the released qubits on 0 (after the shots)
-                prof['projection'] = list(zip(h.op_kernels(), h.op_profile()))
+        deferred = not profile and hasattr(h, 'set_deferred')
+        keys_out = kept_out = None
+        if deferred:
+            pin = self._pinned.get((B, shots))
+            if pin is None:
+                self._pinned.clear()
+                pin = self._pinned[(B, shots)] = (_native.PinnedArray((B, max(shots, 1)), np.uint64), _native.PinnedArray((B,), np.float64))
+            keys_out, kept_out = pin[0].array, pin[1].array
+            h.set_deferred(True)
+        try:
+            tw = [time.perf_counter()]
+            h.run_program(sw.ops, sw.tables[sl])
             tw.append(time.perf_counter())
-            mask, value, n = sw.ps
-            if pmf:
-                probs, kept = h.postselect(mask, value, n)
-            else:
-                kept = h.postselect_resident(mask, value, n)
-                probs = [_ResidentProbs(h, y, n) for y in range(B)]
+            prof = {'program': [] if deferred else list(zip(h.op_kernels(), h.op_profile())), 'projection': [], 'points': B}
+            keys = None
+            if shots:
+                if sw.released is not None:
+                    mc, n_ctrl, ctrl, _p1, p1_off, vclbit, clbit_pos, n_cl = sw.released
+                    keys = h.sample_released_batched(shots, seed, streams, n_ctrl, ctrl, sw.p1[sl], p1_off, vclbit, clbit_pos, n_cl,
+                                                     **({'out': keys_out} if deferred else {}))
+                else:
+                    keys = h.sample_batched(shots, seed, streams, sw.clbit_map if len(sw.clbit_map) else None,
+                                            **({'out': keys_out} if deferred else {}))
+            tw.append(time.perf_counter())
+            probs = kept = None
+            if pmf is not False and sw.ps is not None and sw.n_vars <= 30:
+                if sw.proj_ops is not None:
+                    h.run_program(sw.proj_ops, sw.proj_tables[sl])      # project the released qubits on 0 (after the shots)
+                    if not deferred:
+                        prof['projection'] = list(zip(h.op_kernels(), h.op_profile()))
+                tw.append(time.perf_counter())
+                mask, value, n = sw.ps
+                if pmf:
+                    if deferred:                                  # the full vectors come to pageable memory: finish what is queued first
+                        h.synchronize()
+                        h.set_deferred(False)
+                    probs, kept = h.postselect(mask, value, n)
+                else:
+                    kept = h.postselect_resident(mask, value, n, **({'out': kept_out} if deferred else {}))
+                    probs = [_ResidentProbs(h, y, n) for y in range(B)]
+            if deferred:
+                h.synchronize()
+        finally:
+            if deferred:
+                h.set_deferred(False)
         tw.append(time.perf_counter())
         t = h.timing()
         prof['sample_ms'], prof['postselect_ms'] = (t['sample_ms'] if shots else 0.0), (t['postselect_ms'] if kept is not None else 0.0)
         prof['host_wall_ms'] = [round((b - a) * 1e3, 3) for a, b in zip(tw[:-1], tw[1:])]   # program, shots, projection, post-selection
-        self.sweep_profile = prof                             # per-launch record of the last sweep chunk (bench.py)
+        prof['deferred'] = bool(deferred)
+        self.sweep_profile = prof                             # record of the last sweep chunk (bench.py)
         return keys, probs, kept
 
     def _run_sweep(self, circs, prs, shots, seed, streams, precision, pmf, sw=None):

@@ -35,6 +35,7 @@ struct qcm_sim_s {
     uint64_t rank = 0;
     int batch = 1;                  // sweep points held by this handle (qcm_create_batched); kernels run with gridDim.y = batch
     int cur_point = 0;              // point addressed by qcm_get_amplitudes / qcm_set_amplitudes (qcm_batch_select)
+    bool deferred = false;          // qcm_set_deferred: calls enqueue their work and return without synchronising
     size_t tab_stride = 0;          // doubles per point in the uploaded tables
     uint64_t tree_total = 0;        // doubles per point in the sum-tree buffer
     uint64_t probs_n = 0;           // entries per point of the resident post-selected block (qcm_postselect_resident)
@@ -704,17 +705,45 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
         a.mem[g].src_off = (int32_t)op.table_off;
         a.mem[g].tab_off = (int32_t)reals;
         reals += ((2ull << op.n_ctrl) + 3) & ~size_t(3);
-        // runs of consecutive ascending index qubits (index bit j+1 <-> qubit ctrl[j] + 1)
+        // runs of consecutive ascending index qubits (index bit j+1 <-> qubit ctrl[j] + 1); a run that would need a
+        // left shift (qubit below its index position: unsorted index qubits) is split into single bits placed by mask
         IndexRuns &rn = runs.m[g];
-        for (int j = 0; j < op.n_ctrl; ++j) {
-            if (j && op.ctrl[j] == op.ctrl[j - 1] + 1) {
-                rn.len[rn.n_runs - 1]++;
-            } else {
-                rn.start[rn.n_runs] = (int8_t)op.ctrl[j];
-                rn.len[rn.n_runs] = 1;
-                rn.pos[rn.n_runs] = (int8_t)j;
+        rn.below_32 = 1;
+        int run_start = 0, run_pos = 0, run_len = 0;
+        auto close_run = [&]() {
+            if (!run_len) return;
+            if (run_start >= run_pos) {
+                rn.mask[rn.n_runs] = ((1u << run_len) - 1u) << run_pos;
+                rn.shift[rn.n_runs] = run_start - run_pos;
                 rn.n_runs++;
+            } else {
+                return;                              // handled by the caller below (never for ascending qubits)
             }
+            run_len = 0;
+        };
+        bool ok_runs = true;
+        for (int j = 0; j < op.n_ctrl; ++j) {
+            if (op.ctrl[j] >= 32) rn.below_32 = 0;
+            if (run_len && op.ctrl[j] == run_start + run_len) {
+                run_len++;
+            } else {
+                close_run();
+                if (run_len) ok_runs = false;
+                run_start = op.ctrl[j];
+                run_pos = j;
+                run_len = 1;
+            }
+        }
+        close_run();
+        if (run_len) ok_runs = false;
+        if (!ok_runs) {
+            // index qubits in an order the run decomposition cannot express with right shifts: one pass per member
+            for (int k = 0; k < n_mem; ++k) {
+                int rc2 = launch_diag(h, members[k], n_tables);
+                if (rc2) return rc2;
+            }
+            h->cur_kernel = "k_diag (diagonal block, one pass per member)";
+            return QCM_OK;
         }
     }
     const size_t smem = reals * real_bytes(h);
@@ -1148,6 +1177,11 @@ int qcm_create_batched(qcm_handle *out, int device, int n_local, int precision, 
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e == cudaSuccess) {
+        // allocated up front: a cudaMalloc between the launches of two co-operating kernels would serialise them
+        e = cudaMalloc(&h->errflag.p, sizeof(int));
+        if (e == cudaSuccess) h->errflag.cap = sizeof(int);
+    }
+    if (e == cudaSuccess) {
         if (ext_state) {
             h->state = ext_state;
         } else {
@@ -1247,6 +1281,31 @@ int qcm_state_ptr(qcm_handle h, void **dev_ptr_out, uint64_t *bytes_out) {
     if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
     if (dev_ptr_out) *dev_ptr_out = h->state;
     if (bytes_out) *bytes_out = (amp_bytes(h->prec) << h->n_local) * (uint64_t)h->batch;
+    return QCM_OK;
+}
+
+int qcm_set_deferred(qcm_handle h, int deferred) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    h->deferred = deferred != 0;
+    return QCM_OK;
+}
+
+int qcm_host_alloc(void **host_out, size_t bytes) {
+    if (!host_out) return fail(nullptr, QCM_ERR_INVALID, "NULL argument");
+    *host_out = nullptr;
+    cudaError_t e = cudaHostAlloc(host_out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, QCM_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return QCM_OK;
+}
+
+int qcm_host_free(void *host_ptr) {
+    if (host_ptr && cudaFreeHost(host_ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, QCM_ERR_CUDA, "cudaFreeHost failed");
+    }
     return QCM_OK;
 }
 
@@ -1448,11 +1507,12 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     h->timing.bytes_read *= (uint64_t)h->batch;
     h->timing.bytes_written *= (uint64_t)h->batch;
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    h->op_ms.assign(h->op_kind.size(), 0.f);
+    if (h->deferred) return QCM_OK;          // enqueued; timings are not collected in deferred mode
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->timing.program_ms = ms;
-    h->op_ms.resize(h->op_kind.size());
     for (size_t k = 0; k < h->op_kind.size(); ++k) QCM_CUDA(h, cudaEventElapsedTime(&h->op_ms[k], h->op_ev[k], h->op_ev[k + 1]));
     return QCM_OK;
 }
@@ -1662,12 +1722,13 @@ static int postselect_impl(qcm_handle h, uint64_t mask, uint64_t value, int n_ou
         QCM_CUDA(h, cudaMemsetAsync(dprobs, 0, nprob * B * sizeof(double), h->stream));
     }
     if (dev) return QCM_OK;                 // results stay on the device, in stream order: no synchronisation
+    if (resident) h->probs_n = nprob;
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (h->deferred) return QCM_OK;         // kept_out / probs_out (pinned host memory) are valid after qcm_synchronize
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->timing.postselect_ms = ms;
-    if (resident) h->probs_n = nprob;
     return QCM_OK;
 }
 
@@ -1796,6 +1857,7 @@ static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint
     QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * B * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     if (mine_out) QCM_CUDA(h, cudaMemcpyAsync(mine_out, h->mine.p, shots, cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (h->deferred) return QCM_OK;
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1914,6 +1976,7 @@ static int sample_released_impl(qcm_handle h, uint64_t shots, uint64_t seed, uin
     h->timing.kernel_launches++;
     QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * B * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (h->deferred) return QCM_OK;
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));

@@ -1495,8 +1495,12 @@ __global__ void __launch_bounds__(kThreads) k_diag(const __grid_constant__ DiagA
 // of one shift/mask/or per qubit with a constant-bank load each: the 3-table projection pass of the chain-20 sweep
 // went from instruction-bound 2.3 TB/s to the HBM roofline).
 struct IndexRuns {
-    int8_t n_runs;
-    int8_t start[QCM_MAX_CTRL], len[QCM_MAX_CTRL], pos[QCM_MAX_CTRL];
+    int32_t n_runs;
+    int32_t below_32;                // every index qubit is below 32: 32-bit shifts
+    // run r contributes  (gi >> shift[r]) & mask[r]  (mask already sits at the run's table-index position; the host
+    // guarantees start >= position, which holds for ascending index qubits)
+    uint32_t mask[QCM_MAX_CTRL];
+    int32_t shift[QCM_MAX_CTRL];
 };
 struct DiagMultiRuns { IndexRuns m[QCM_MAX_MEMBERS]; };
 
@@ -1529,8 +1533,12 @@ __global__ void __launch_bounds__(kThreads) k_diag_multi(const __grid_constant__
             for (int u = 0; u < U; ++u) {
                 const uint64_t gi = ((v0 + (uint64_t)u * blockDim.x) * V) | a.rank_bits;
                 uint32_t idx0 = 0;
-                for (int r = 0; r < rn.n_runs; ++r)
-                    idx0 |= ((uint32_t)(gi >> rn.start[r]) & ((1u << rn.len[r]) - 1u)) << rn.pos[r];
+                if (rn.below_32) {
+                    const uint32_t lo = (uint32_t)gi;
+                    for (int r = 0; r < rn.n_runs; ++r) idx0 |= (lo >> rn.shift[r]) & rn.mask[r];
+                } else {
+                    for (int r = 0; r < rn.n_runs; ++r) idx0 |= (uint32_t)(gi >> rn.shift[r]) & rn.mask[r];
+                }
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const uint32_t idx = v ? (idx0 | low_bit) : idx0;

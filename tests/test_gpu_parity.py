@@ -409,6 +409,18 @@ def test_diagonal_block_is_one_sweep(precision):
         got = h.get_amplitudes().astype(np.complex128)
         assert np.abs(got - want).max() < (1e-12 if precision == 'double' else 3e-6)
         assert len(h.op_profile()) == 2 and h.op_kernels()[-1].startswith('k_diag_multi')
+        # index qubits in descending order: served by one pass per member, same result
+        e = fusion._Emitter()
+        e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=N, table_off=e.table(qv))
+        e.op(fusion.QCM_OP_BLOCK, target=0, ctrl=(), n_in=N, n_out=N, n_ctrl=2)
+        for c in ([7, 3, 0], [2, 1]):
+            d = np.exp(1j * rng.uniform(0, 6, 1 << len(c)))
+            e.op(fusion.QCM_OP_DIAG, ctrl=c, n_in=N, n_out=N, table_off=e.table(fusion._diag_table_f64(d)))
+        ops, tabs = e.finish()
+        pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, N
+        want, _ = em.run_plan(pl)
+        h.run_program(ops, tabs)
+        assert np.abs(h.get_amplitudes().astype(np.complex128) - want).max() < (1e-12 if precision == 'double' else 3e-6)
 
 
 @pytest.mark.parametrize('precision', ['double', 'single'])
@@ -896,6 +908,10 @@ def test_gather_block_in_place_on_virtual_peers(precision, s, monkeypatch):
     streams = [torch.cuda.Stream() for _ in range(world)]
     handles = [_native.Handle(nl, precision, ext_state_ptr=states[r].data_ptr(), ext_stream=streams[r].cuda_stream) for r in range(world)]
     slab_bytes = (1 << (nl - s)) * np.dtype(cdt).itemsize
+    for h in handles:
+        # the handles' table buffers are allocated here: a cudaMalloc while another virtual rank's kernel is already
+        # waiting for signals would hold this rank's launch back (one GPU only; real ranks own their GPU)
+        h.run_program(ops[:0], tabs)
     torch.cuda.synchronize()
     pl = _P(); pl.ops, pl.tables, pl.n_phys = ops, tabs, nl
     try:
