@@ -1047,7 +1047,13 @@ static int launch_gather_inplace(qcm_handle h, const GatherArgs &a, const Gather
     auto kern = k_block_gather_inplace<R, V, M, 1, S>;
     const size_t smem = 256 + (size_t)S * (1 << M) * kGatherTileBytes + tab_bytes;
     if (smem > 227 * 1024) return fail(h, QCM_ERR_UNSUPPORTED, "gather ring needs %zu B of shared memory", smem);
-    QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // set once per kernel and size: changing a function's attributes while an instance of it is running (another rank's
+    // kernel on this GPU, already waiting for signals) would hold this launch back until that instance ends
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+    }
     const uint64_t tiles = ((1ull << (a.n_local - M)) / V) / kThreads;
     int K = env_int("QCM_GATHER_K", 16);
     int p2 = 1;

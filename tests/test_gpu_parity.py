@@ -918,7 +918,11 @@ def test_gather_block_in_place_on_virtual_peers(precision, s, monkeypatch):
         for epoch in (1, 2):
             errs = [None] * world
 
+            walls = [None] * world
+
             def work(r):
+                import time as _t
+                t0 = _t.perf_counter()
                 try:
                     h = handles[r]
                     h.set_shard(s, r)
@@ -927,12 +931,13 @@ def test_gather_block_in_place_on_virtual_peers(precision, s, monkeypatch):
                     h.run_gather_block_inplace(ops, tabs, src, [f.data_ptr() for f in flags], words, epoch)
                 except Exception as ex:                       # noqa: BLE001
                     errs[r] = ex
+                walls[r] = (round(t0, 3), round(_t.perf_counter(), 3))
             ths = [threading.Thread(target=work, args=(r,)) for r in range(world)]
             for th in ths:
                 th.start()
             for th in ths:
                 th.join()
-            assert not any(errs), errs
+            assert not any(errs), (errs, walls, [h.timing()['program_ms'] for h in handles])
             torch.cuda.synchronize()
             swapped = swap(psi)
             new = np.empty_like(psi)
