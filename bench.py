@@ -722,31 +722,48 @@ def dense_gate_pass(args, cliques, device, world=1):
         out['exchange'] = [{'ms': r[1], 'bytes_sent_per_gpu': r[2], 'gbs_per_direction_per_gpu': r[2] / r[1] / 1e6}
                            for r in ex]
     sim.close()
-    if world > 1 and prep.plan.n_phys - (world.bit_length() - 1) <= 32:
-        # the same schedule with the qubit swap and the sweeps on the swapped-in qubits fused into ONE kernel
-        # that reads the peers' shards over NVLink (needs a second local buffer: shards <= 32 GiB here)
+    # the same schedule with the qubit swap and the sweeps on the swapped-in qubits fused into ONE kernel that reads the
+    # peers' shards over NVLink: out of place (a second local buffer: shards <= 32 GiB here) and IN PLACE (per-tile
+    # flags order the overwrites behind the peers' reads: any shard size, e.g. the 128 GiB shards of 37 qubits on 8 GPUs)
+    s = world.bit_length() - 1
+    variants = []
+    if world > 1 and prep.plan.n_phys - s <= 32:
+        variants.append(('fused_exchange', 'p2p'))
+    if world > 1:
+        variants.append(('fused_exchange_inplace', 'p2p-inplace'))
+    for key, xch in variants:
         from qcmrf_b200.sharded import ShardedSimulator
-        sim = ShardedSimulator(precision='single', fusion='clique', layout='canonical', device=device, seed=1,
-                               exchange='p2p')
+        sim = ShardedSimulator(precision='single', fusion='clique', layout='canonical', device=device, seed=1, exchange=xch)
         prep = sim.prepare(circ)
         try:
             sim.execute(prep, 0, want_probs=False)
-            sim.execute(prep, 0, want_probs=False)
+            res2 = sim.execute(prep, 0, want_probs=True)
         except Exception as e:
-            out['fused_exchange'] = {'error': repr(e)[:500]}
-            return out
+            out[key] = {'error': repr(e)[:500]}
+            try:
+                sim.close()
+            except Exception:
+                pass
+            continue
         prof2 = sim.op_profile()
         fx = [r for r in prof2 if r[0] == -2]
-        s = world.bit_length() - 1
         if fx:
             remote = fx[0][2] * (world - 1) // world        # every output pair takes 2^s inputs, all but one from peers
-            out['fused_exchange'] = {'kernel': 'k_block_gather: qubit swap + the %d sweeps on the swapped-in qubits, peers read over '
-                                               'NVLink (CUDA IPC, TMA bulk copies into a shared-memory ring)' % s, 'ms': fx[0][1],
-                                     'replaces_ms': (ex[0][1] if ex else 0.0) + s * ms,
-                                     'remote_bytes_read_per_gpu': remote, 'nvlink_gbs_per_gpu': remote / fx[0][1] / 1e6,
-                                     'circuit_ms': sum(r[1] for r in prof2)}
+            out[key] = {'kernel': '%s: qubit swap + the %d sweeps on the swapped-in qubits, peers read over NVLink (CUDA IPC, TMA '
+                                  'bulk copies into a shared-memory ring)' % ('k_block_gather_inplace' if xch == 'p2p-inplace' else
+                                                                             'k_block_gather_tma', s),
+                        'ms': fx[0][1], 'replaces_ms': (ex[0][1] if ex else 0.0) + s * ms,
+                        'remote_bytes_read_per_gpu': remote, 'nvlink_gbs_per_gpu': remote / fx[0][1] / 1e6,
+                        'circuit_ms': sum(r[1] for r in prof2)}
+            n_v = max(max(c) for c in cliques) + 1
+            if res2[1] is not None and n_v <= 24:
+                pb, db = brute_force_pmf(cliques, workloads.theta_for(cliques))
+                p2 = res2[1] / res2[2]
+                out[key]['check'] = {'rel_p_err_vs_brute_force': float((np.abs(p2 - pb) / pb).max()),
+                                     'delta_rel_err': abs(float(res2[2]) - db) / db,
+                                     'parity_ok': bool((np.abs(p2 - pb) / pb).max() < 2e-4 and abs(float(res2[2]) - db) / db < 2e-4)}
         else:
-            out['fused_exchange'] = {'unavailable': getattr(sim, 'p2p_error', 'no fused segment in the plan')}
+            out[key] = {'unavailable': getattr(sim, 'p2p_error', 'no fused segment in the plan')}
         sim.close()
     return out
 

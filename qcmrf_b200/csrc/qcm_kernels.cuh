@@ -1666,14 +1666,22 @@ __global__ void __launch_bounds__(kThreads) k_swap(void *state, int qa, int qb, 
 // shuffle tree) so that results do not depend on the grid or on the GPU count.
 // ----------------------------------------------------------------------------------
 
+constexpr int kSubCluster = 4;                  // adjacent 16-byte vectors per lane per cluster
+// i-th vector (of 16 or 32) that lane `lane` owns inside a chunk
+__device__ __forceinline__ uint32_t sub_vec(uint32_t lane, uint32_t i) {
+    return kSubCluster * lane + (i % kSubCluster) + 32u * kSubCluster * (i / kSubCluster);
+}
+
 // level 0: chunk c = sum_{i in chunk} |amp_i|^2 ; one warp per chunk.  Full-size chunks
 // stream 128-bit loads, eight in flight per lane; the lane-strided order is fixed.
 template <typename R>
 __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int n_active, double *out, uint64_t bstate, uint64_t bout,
                                                          double *sub = nullptr, uint64_t bsub = 0) {
-    // sub (optional, full-size chunks only): the 32 lane partials of every chunk -- lane l's partial covers the
-    // amplitudes it loaded: the STRIDED group {V * (l + 32 j) + v}.  The sampler picks a group, then one of its 32
-    // amplitudes, instead of scanning all 1024 amplitudes of the chunk.
+    // sub (optional, full-size chunks only): the 32 lane partials of every chunk -- lane l's partial covers the 16-byte
+    // vectors it loaded, sub_vec(l, i): clusters of kSubCluster adjacent vectors (64 bytes), the clusters of a lane
+    // 32 * kSubCluster vectors apart, so a warp's loads stay coalesced AND a group is a few whole DRAM atoms.  The
+    // sampler picks a group, then one of its 32 amplitudes, instead of scanning all 1024 amplitudes of the chunk
+    // (with single-vector strides the leaf reads of 2.5 M shots cost 10 GB of DRAM traffic; clustered: a quarter).
     state = batch_ptr(state, bstate);
     out = batch_ptr(out, bout);
     if (sub) sub = batch_ptr(sub, bsub);
@@ -1693,7 +1701,7 @@ __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int 
                 for (int i0 = 0; i0 < kIter; i0 += 8) {
                     float4 t[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) t[k] = __ldcs(p + lane + 32 * (i0 + k));
+                    for (int k = 0; k < 8; ++k) t[k] = __ldcs(p + sub_vec(lane, i0 + k));
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         acc += ((double)t[k].x * (double)t[k].x + (double)t[k].y * (double)t[k].y) +
@@ -1714,7 +1722,7 @@ __global__ void __launch_bounds__(kThreads) k_chunk_sums(const void *state, int 
                 for (int i0 = 0; i0 < kIter; i0 += 8) {
                     double2 t[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) t[k] = __ldcs(p + lane + 32 * (i0 + k));
+                    for (int k = 0; k < 8; ++k) t[k] = __ldcs(p + sub_vec(lane, i0 + k));
 #pragma unroll
                     for (int k = 0; k < 8; ++k) acc += t[k].x * t[k].x + t[k].y * t[k].y;
                 }
@@ -1906,7 +1914,7 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
             const double *sp = batch_ptr(a.sub, a.bsub) + node * 32;
             const uint32_t g = warp_pick([&](uint32_t i) { return sp[i]; }, 32u, u, lane);
             constexpr uint32_t VV = sizeof(R) == 4 ? 2u : 1u;
-            auto member = [&](uint32_t i) -> uint64_t { return (uint64_t)VV * (g + 32u * (i / VV)) + (i % VV); };
+            auto member = [&](uint32_t i) -> uint64_t { return (uint64_t)VV * sub_vec(g, i / VV) + (i % VV); };
             auto amp_ws = [&](uint32_t i) -> double {
                 if constexpr (sizeof(R) == 4) {
                     const float2 t = reinterpret_cast<const float2 *>(state)[afirst + member(i)];
