@@ -39,7 +39,7 @@ def build_host(force=False, verbose=False):
     cc = shutil.which('gcc') or shutil.which('cc')
     if cc is None:
         raise RuntimeError('gcc not found: cannot build qcmrf_b200/_qcm_host.so')
-    cmd = [cc, '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-I', sysconfig.get_paths()['include'], HOST_SRC, '-o', HOST_LIB]
+    cmd = [cc, '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-I', sysconfig.get_paths()['include'], HOST_SRC, '-o', HOST_LIB, '-lm']
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

@@ -8,6 +8,7 @@
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <stdint.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -136,4 +137,64 @@ void qcm_block_apply(double *U, int64_t n_rows, int64_t n_cols, uint64_t cmask, 
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Basis-gate programs (the output of transpile(..., basis_gates=['cx','id','rz','sx','x']),
+ * /root/reference/run_experiment.py:52) as flat arrays: kind[] (0 rz, 1 sx, 2 x, 3 id, 4 cx), tq[] target,
+ * cq[] control (cx) or -1, par[] angle (rz).  A transpiled fixture circuit has up to ~15 000 gates; walking them
+ * one Python object at a time cost ~110 ms per circuit in the gate-fusion pass -- these two helpers keep the
+ * per-gate work in C and leave the Python side one step per QUBIT that joins a block.
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* keep[g] = 0 for a cx whose control no kept gate has targeted yet (the qubit is still |0>: a closed control on it
+ * never fires), else 1 -- the array twin of fusion.prune_zero_controls.  Returns the number of kept gates. */
+int64_t qcm_basis_prune(const int8_t *kind, const int32_t *tq, const int32_t *cq, int64_t n, int32_t n_qubits, uint8_t *keep) {
+    uint8_t *clean = (uint8_t *)malloc((size_t)(n_qubits > 0 ? n_qubits : 1));
+    if (!clean) return -1;
+    memset(clean, 1, (size_t)(n_qubits > 0 ? n_qubits : 1));
+    int64_t kept = 0;
+    for (int64_t g = 0; g < n; ++g) {
+        if (kind[g] == 4 && cq[g] >= 0 && cq[g] < n_qubits && clean[cq[g]]) {
+            keep[g] = 0;
+            continue;
+        }
+        keep[g] = 1;
+        ++kept;
+        if (tq[g] >= 0 && tq[g] < n_qubits) clean[tq[g]] = 0;
+    }
+    free(clean);
+    return kept;
+}
+
+/* Applies gates j, j+1, ... (< limit) to the block matrix U (complex128, row-major, n_rows x n_cols; row bit p <->
+ * block position p) for as long as every qubit of the gate has a block position (pos[q] >= 0); returns the index of
+ * the first gate that was NOT applied (a gate touching a qubit outside the block, or `limit`). */
+int64_t qcm_basis_apply_run(double *U, int64_t n_rows, int64_t n_cols, const int8_t *kind, const int32_t *tq,
+                            const int32_t *cq, const double *par, int64_t j, int64_t limit, const int32_t *pos) {
+    static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+    static const double SX[8] = {0.5, 0.5, 0.5, -0.5, 0.5, -0.5, 0.5, 0.5};
+    for (; j < limit; ++j) {
+        const int pt = pos[tq[j]];
+        if (pt < 0) break;
+        switch (kind[j]) {
+            case 0: {                                     /* rz(l) = diag(e^{-il/2}, e^{il/2}) */
+                const double h = 0.5 * par[j];
+                const double b[8] = {cos(h), -sin(h), 0, 0, 0, 0, cos(h), sin(h)};
+                qcm_block_apply(U, n_rows, n_cols, 0, 0, 1ull << pt, b);
+                break;
+            }
+            case 1: qcm_block_apply(U, n_rows, n_cols, 0, 0, 1ull << pt, SX); break;
+            case 2: qcm_block_apply(U, n_rows, n_cols, 0, 0, 1ull << pt, X); break;
+            case 3: break;
+            case 4: {
+                const int pc = pos[cq[j]];
+                if (pc < 0) return j;
+                qcm_block_apply(U, n_rows, n_cols, 1ull << pc, 1ull << pc, 1ull << pt, X);
+                break;
+            }
+            default: return -1;
+        }
+    }
+    return j;
 }

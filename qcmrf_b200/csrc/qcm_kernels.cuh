@@ -710,10 +710,11 @@ __global__ void __launch_bounds__(kThreads + 32) k_block_gather_tma(const __grid
 // (tile, peer) that orders the two accesses to the same memory:
 //     peer r reads  my.state[slab r][tile t]      (it needs it as its input)
 //     I overwrite   my.state[slab r][tile t]      (with my output)
-// Once my bulk copy of peer r's tile t has landed in shared memory I store `epoch` to peer r's flag
-// [t][c] (st.release.sys over NVLink); before I overwrite my slab r of tile t I wait until MY flag [t][r] shows
-// the epoch (ld.acquire.sys).  Stores are delayed by one tile (results wait in registers), so the flag was
-// raised a whole tile earlier and the wait almost never spins.  Everybody reads before waiting and CTAs are
+// Once my bulk copy of peer r's tile t has landed in shared memory a dedicated signalling warp stores `epoch` to peer
+// r's flag [t][c] over NVLink -- as soon as the ring stage fills, i.e. up to STAGES-1 tiles before the consumers get to
+// that tile; before the consumers overwrite my slab r of tile t they wait until MY flag [t][r] shows the epoch.  The
+// stores are also delayed by one tile (results wait in registers), so the flag has had several tile times to arrive
+// and the wait almost never spins.  Everybody reads before waiting and CTAs are
 // dispatched in tile order on every rank, so there is no circular wait; a spin that exceeds `spin_limit` clocks
 // gives up and raises *err (the host reports it) instead of hanging the GPU.
 // ----------------------------------------------------------------------------------
@@ -725,17 +726,20 @@ struct GatherFlags {
     long long spin_limit;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// The signal only says "my read of your tile has completed" (the data already sits in my shared memory, observed
+// through the mbarrier): it orders nothing of mine, so a relaxed system-scope store is enough -- a release would fence
+// this thread's own earlier global stores at system scope, microseconds per tile.
+__device__ __forceinline__ void st_relaxed_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) {
     uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
 template <typename R, int V, int M, int U, int STAGES>
-__global__ void __launch_bounds__(kThreads + 32) k_block_gather_inplace(const __grid_constant__ GatherArgs a, const __grid_constant__ GatherFlags f,
+__global__ void __launch_bounds__(kThreads + 64) k_block_gather_inplace(const __grid_constant__ GatherArgs a, const __grid_constant__ GatherFlags f,
                                                                         const int tiles_per_cta) {
     constexpr int NR = 1 << M;
     constexpr uint32_t kTile = kGatherTileBytes * U;             // bytes per source per stage
@@ -773,6 +777,13 @@ __global__ void __launch_bounds__(kThreads + 32) k_block_gather_inplace(const __
                     bulk_g2s(smem_u32(ring + ((size_t)st * NR + r) * kTile),
                              reinterpret_cast<const unsigned char *>(a.src[r]) + (tile0 + k) * kTile, kTile, full);
             }
+        } else if (threadIdx.x >= kThreads + 32) {
+            // signalling warp: lane r tells peer r, as soon as tile k has landed here, that it may overwrite what was read
+            const int r = (int)threadIdx.x - (kThreads + 32);
+            for (int k = 0; k < tiles_per_cta; ++k) {
+                mbar_wait(smem_u32(bars + (k % STAGES)), (k / STAGES) & 1);
+                if (r < NR && r != f.c_me) st_relaxed_sys(f.flags[r] + (tile0 + k) * NR + f.c_me, f.epoch);
+            }
         }
         return;
     }
@@ -782,11 +793,15 @@ __global__ void __launch_bounds__(kThreads + 32) k_block_gather_inplace(const __
         // every peer has read the slabs of `tile` that are about to be overwritten
         if (threadIdx.x < NR && (int)threadIdx.x != f.c_me) {
             const uint32_t *p = f.flags[f.c_me] + tile * NR + threadIdx.x;
-            const long long t0 = clock64();
-            while ((int32_t)(ld_acquire_sys(p) - f.epoch) < 0) {
-                if (clock64() - t0 > f.spin_limit) { *f.err = 1; break; }
+            if ((int32_t)(ld_relaxed_sys(p) - f.epoch) < 0) {
+                const long long t0 = clock64();
+                while ((int32_t)(ld_relaxed_sys(p) - f.epoch) < 0) {
+                    __nanosleep(64);
+                    if (clock64() - t0 > f.spin_limit) { *f.err = 1; break; }
+                }
             }
         }
+        // the overwrite below is control-dependent on the flags; the barrier hands that to the whole consumer group
         asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
         const uint64_t bv0 = tile * ((uint64_t)kThreads * U) + threadIdx.x;
 #pragma unroll
@@ -798,9 +813,6 @@ __global__ void __launch_bounds__(kThreads + 32) k_block_gather_inplace(const __
     for (int k = 0; k < tiles_per_cta; ++k) {
         const int st = k % STAGES;
         mbar_wait(smem_u32(bars + st), (k / STAGES) & 1);
-        // the peers' tile (tile0 + k) is in shared memory: they may overwrite what was read
-        if (threadIdx.x < NR && (int)threadIdx.x != f.c_me)
-            st_release_sys(f.flags[threadIdx.x] + (tile0 + k) * NR + f.c_me, f.epoch);
         R ar[U][NR][V], ai[U][NR][V];
 #pragma unroll
         for (int u = 0; u < U; ++u)

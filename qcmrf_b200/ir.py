@@ -167,6 +167,43 @@ class LazyProgram(Program):
         self._gates = value
 
 
+BASIS_KINDS = ('rz', 'sx', 'x', 'id', 'cx')          # kind codes of a basis-gate program, in this order
+
+
+class BasisProgram(Program):
+    """A program in the reference's target basis (cx, id, rz, sx, x -- run_experiment.py:52) held as flat arrays
+    instead of one Gate object per gate: ``bk`` kind code (index into BASIS_KINDS), ``bq`` target qubit, ``bc``
+    control qubit (cx) or -1, ``bp`` angle (rz).  A transpiled fixture circuit has up to ~15 000 gates; the fusion pass
+    walks the arrays in C (fusion._fuse_basis).  ``gates`` materialises the Gate list on first access for every
+    other consumer."""
+
+    def __init__(self, n_qubits, n_clbits, bk, bq, bc, bp, name='', global_phase=0.0):
+        Program.__init__(self, n_qubits, n_clbits, name=name, global_phase=global_phase)
+        self.bk = np.ascontiguousarray(bk, dtype=np.int8)
+        self.bq = np.ascontiguousarray(bq, dtype=np.int32)
+        self.bc = np.ascontiguousarray(bc, dtype=np.int32)
+        self.bp = np.ascontiguousarray(bp, dtype=np.float64)
+        self._gates = None
+
+    def gate_at(self, i):
+        k, q = int(self.bk[i]), int(self.bq[i])
+        if k == 0:
+            return Gate('rz', (q,), (float(self.bp[i]),))
+        if k == 4:
+            return Gate('cx', (int(self.bc[i]), q), (), (1,))
+        return Gate(BASIS_KINDS[k], (q,))
+
+    @property
+    def gates(self):
+        if self._gates is None:
+            self._gates = [self.gate_at(i) for i in range(len(self.bk))]
+        return self._gates
+
+    @gates.setter
+    def gates(self, value):
+        self._gates = value
+
+
 def _qindex(circ, q):
     if isinstance(q, (int, np.integer)):
         return int(q)

@@ -27,9 +27,84 @@ DEFAULT_BASIS = ('cx', 'id', 'rz', 'sx', 'x')
 _PI = math.pi
 
 
+class _Sink:
+    """Collects the translated gates as flat lists (kind code, target, control, angle): see ir.BasisProgram."""
+
+    def __init__(self, global_phase=0.0):
+        self.k, self.q, self.c, self.p = [], [], [], []
+        self.global_phase = global_phase
+
+    def rz(self, lam, q):
+        self.k.append(0); self.q.append(q); self.c.append(-1); self.p.append(lam)
+
+    def sx(self, q):
+        self.k.append(1); self.q.append(q); self.c.append(-1); self.p.append(0.0)
+
+    def x(self, q):
+        self.k.append(2); self.q.append(q); self.c.append(-1); self.p.append(0.0)
+
+    def id(self, q):
+        self.k.append(3); self.q.append(q); self.c.append(-1); self.p.append(0.0)
+
+    def cx(self, a, b):
+        self.k.append(4); self.q.append(b); self.c.append(a); self.p.append(0.0)
+
+
+class BasisCircuit(QuantumCircuit):
+    """What ``transpile`` returns: a QuantumCircuit in the cx/id/rz/sx/x basis whose instruction list is materialised
+    on first access -- the engine's own lowering takes the flat gate arrays (ir.BasisProgram) instead of walking
+    ~15 000 instruction objects; anything that touches ``.data`` (or edits the circuit) gets the ordinary list."""
+
+    def __init__(self, nq, nc, name, sink, measures):
+        super().__init__(nq, nc, name=name, global_phase=sink.global_phase)
+        self.__dict__['_bc_sink'] = sink
+        self.__dict__['_bc_measures'] = list(measures)
+        self.__dict__['_bc_data'] = None
+
+    @property
+    def _qc_data(self):
+        d = self.__dict__.get('_bc_data')
+        if d is None:
+            d = self.__dict__['_bc_data'] = []
+            snk = self.__dict__.get('_bc_sink')
+            if snk is not None:
+                emit = (self.rz, self.sx, self.x, self.id)
+                for k, q, c, p in zip(snk.k, snk.q, snk.c, snk.p):
+                    if k == 0:
+                        self.rz(p, q)
+                    elif k == 4:
+                        self.cx(c, q)
+                    else:
+                        emit[k](q)
+                for q, c in self.__dict__['_bc_measures']:
+                    self.measure(q, c)
+        return d
+
+    @_qc_data.setter
+    def _qc_data(self, value):
+        self.__dict__['_bc_data'] = value
+
+    def _lower_program(self):
+        """ir.BasisProgram over the gate arrays, or None once the instruction list exists (it may have been edited)."""
+        if self.__dict__.get('_bc_data') is not None or self.__dict__.get('_bc_sink') is None:
+            return None
+        snk = self.__dict__['_bc_sink']
+        prog = ir.BasisProgram(self.num_qubits, self.num_clbits, snk.k, snk.q, snk.c, snk.p, name=str(self.name),
+                               global_phase=float(self.global_phase))
+        for q, c in self.__dict__['_bc_measures']:
+            prog.measures[c] = q
+        if 'num_vertices' in self.metadata:
+            prog.metadata['num_vertices'] = int(self.metadata['num_vertices'])
+        return prog
+
+    def copy(self, name=None):
+        out = QuantumCircuit.copy(self, name)              # materialises: a copy is an ordinary circuit
+        return out
+
+
 class _Out:
-    def __init__(self, circ):
-        self.c = circ
+    def __init__(self, sink):
+        self.c = sink
 
     def rz(self, lam, q):
         lam = math.remainder(lam, 4 * _PI)
@@ -133,7 +208,7 @@ class _Out:
 
 
 def _translate(prog: ir.Program, name) -> QuantumCircuit:
-    out = QuantumCircuit(prog.n_qubits, prog.n_clbits, name=name, global_phase=prog.global_phase)
+    out = _Sink(prog.global_phase)
     o = _Out(out)
     for g in prog.gates:
         if not g.controls:
@@ -162,10 +237,9 @@ def _translate(prog: ir.Program, name) -> QuantumCircuit:
             raise ValueError('transpile: controlled-%s is not supported' % base)
         for c in opens:
             o.x(c)
-    for c, q in sorted(prog.measures.items(), key=lambda cq: (cq[1], cq[0])):
-        out.measure(q, c)
     out.global_phase = math.remainder(out.global_phase, 2 * _PI)
-    return out
+    measures = [(q, c) for c, q in sorted(prog.measures.items(), key=lambda cq: (cq[1], cq[0]))]
+    return BasisCircuit(prog.n_qubits, prog.n_clbits, name, out, measures)
 
 
 def transpile(circuits, backend=None, basis_gates=None, optimization_level=None, **_ignored):
