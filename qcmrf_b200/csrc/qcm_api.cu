@@ -1061,7 +1061,7 @@ static int launch_gather_inplace(qcm_handle h, const GatherArgs &a, const Gather
     while (p2 > 1 && (tiles % p2 || tiles / p2 < 1)) p2 >>= 1;
     const uint64_t grid = tiles / p2;
     if (grid > 0x7fffffffull) return fail(h, QCM_ERR_UNSUPPORTED, "gather grid too large");
-    kern<<<(unsigned)grid, kThreads + 64, smem, h->stream>>>(a, f, p2);
+    kern<<<(unsigned)grid, kThreads + 96, smem, h->stream>>>(a, f, p2);
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     return QCM_OK;

@@ -169,32 +169,103 @@ int64_t qcm_basis_prune(const int8_t *kind, const int32_t *tq, const int32_t *cq
 
 /* Applies gates j, j+1, ... (< limit) to the block matrix U (complex128, row-major, n_rows x n_cols; row bit p <->
  * block position p) for as long as every qubit of the gate has a block position (pos[q] >= 0); returns the index of
- * the first gate that was NOT applied (a gate touching a qubit outside the block, or `limit`). */
+ * the first gate that was NOT applied (a gate touching a qubit outside the block, or `limit`).
+ *
+ * Nine gates in ten of a transpiled circuit are rz (a phase per row) or x / cx (a row permutation): those are kept
+ * LAZY -- logical row r is  e^{i phase[r]} * U[perm[r]]  -- and cost O(rows) instead of O(rows x cols); only sx mixes
+ * rows (it first folds the two rows' pending phases into its coefficients).  The lazy state is folded back into U
+ * before returning. */
 int64_t qcm_basis_apply_run(double *U, int64_t n_rows, int64_t n_cols, const int8_t *kind, const int32_t *tq,
                             const int32_t *cq, const double *par, int64_t j, int64_t limit, const int32_t *pos) {
-    static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
-    static const double SX[8] = {0.5, 0.5, 0.5, -0.5, 0.5, -0.5, 0.5, 0.5};
+    if (n_rows > 65536 || n_rows < 1) return -1;
+    int32_t *perm = (int32_t *)malloc((size_t)n_rows * sizeof(int32_t));
+    double *phase = (double *)malloc((size_t)n_rows * sizeof(double));
+    if (!perm || !phase) {
+        free(perm);
+        free(phase);
+        return -1;
+    }
+    for (int64_t r = 0; r < n_rows; ++r) {
+        perm[r] = (int32_t)r;
+        phase[r] = 0.0;
+    }
+    int dirty = 0;
+    int64_t rc = 0;
     for (; j < limit; ++j) {
         const int pt = pos[tq[j]];
         if (pt < 0) break;
-        switch (kind[j]) {
-            case 0: {                                     /* rz(l) = diag(e^{-il/2}, e^{il/2}) */
-                const double h = 0.5 * par[j];
-                const double b[8] = {cos(h), -sin(h), 0, 0, 0, 0, cos(h), sin(h)};
-                qcm_block_apply(U, n_rows, n_cols, 0, 0, 1ull << pt, b);
-                break;
-            }
-            case 1: qcm_block_apply(U, n_rows, n_cols, 0, 0, 1ull << pt, SX); break;
-            case 2: qcm_block_apply(U, n_rows, n_cols, 0, 0, 1ull << pt, X); break;
-            case 3: break;
-            case 4: {
+        const int64_t tb = (int64_t)1 << pt;
+        const int k = kind[j];
+        if (k == 3) continue;
+        if (k == 0) {                                     /* rz(l) = diag(e^{-il/2}, e^{il/2}) */
+            const double h = 0.5 * par[j];
+            for (int64_t r = 0; r < n_rows; ++r) phase[r] += (r & tb) ? h : -h;
+            dirty = 1;
+        } else if (k == 2 || k == 4) {                    /* x / cx: swap the logical rows of every selected pair */
+            int64_t cb = 0;
+            if (k == 4) {
                 const int pc = pos[cq[j]];
-                if (pc < 0) return j;
-                qcm_block_apply(U, n_rows, n_cols, 1ull << pc, 1ull << pc, 1ull << pt, X);
-                break;
+                if (pc < 0) break;
+                cb = (int64_t)1 << pc;
             }
-            default: return -1;
+            for (int64_t r = 0; r < n_rows; ++r) {
+                if ((r & tb) || (r & cb) != cb) continue;
+                const int32_t tp = perm[r];
+                perm[r] = perm[r | tb];
+                perm[r | tb] = tp;
+                const double tf = phase[r];
+                phase[r] = phase[r | tb];
+                phase[r | tb] = tf;
+            }
+            dirty = 1;
+        } else if (k == 1) {                              /* sx = 0.5 [[1+i, 1-i], [1-i, 1+i]] on rows e^{i f0} u0, e^{i f1} u1 */
+            for (int64_t r = 0; r < n_rows; ++r) {
+                if (r & tb) continue;
+                const double c0 = cos(phase[r]), s0 = sin(phase[r]), c1 = cos(phase[r | tb]), s1 = sin(phase[r | tb]);
+                /* a = (1+i)/2 e^{i f0}, b = (1-i)/2 e^{i f1}, c = (1-i)/2 e^{i f0}, d = (1+i)/2 e^{i f1} */
+                const double ar = 0.5 * (c0 - s0), ai = 0.5 * (c0 + s0), br = 0.5 * (c1 + s1), bi = 0.5 * (s1 - c1);
+                const double cr = 0.5 * (c0 + s0), ci = 0.5 * (s0 - c0), dr = 0.5 * (c1 - s1), di = 0.5 * (c1 + s1);
+                double *p0 = U + 2 * (size_t)perm[r] * (size_t)n_cols;
+                double *p1 = U + 2 * (size_t)perm[r | tb] * (size_t)n_cols;
+                for (int64_t c = 0; c < n_cols; ++c) {
+                    const double x0 = p0[2 * c], y0 = p0[2 * c + 1], x1 = p1[2 * c], y1 = p1[2 * c + 1];
+                    p0[2 * c] = (ar * x0 - ai * y0) + (br * x1 - bi * y1);
+                    p0[2 * c + 1] = (ar * y0 + ai * x0) + (br * y1 + bi * x1);
+                    p1[2 * c] = (cr * x0 - ci * y0) + (dr * x1 - di * y1);
+                    p1[2 * c + 1] = (cr * y0 + ci * x0) + (dr * y1 + di * x1);
+                }
+                phase[r] = 0.0;
+                phase[r | tb] = 0.0;
+            }
+        } else {
+            rc = -1;
+            break;
         }
     }
-    return j;
+    if (dirty && rc == 0) {                               /* fold the pending phases and the row permutation back into U */
+        double *tmp = (double *)malloc(2 * (size_t)n_rows * (size_t)n_cols * sizeof(double));
+        if (!tmp) {
+            rc = -1;
+        } else {
+            for (int64_t r = 0; r < n_rows; ++r) {
+                const double c = cos(phase[r]), sn = sin(phase[r]);
+                const double *src = U + 2 * (size_t)perm[r] * (size_t)n_cols;
+                double *dst = tmp + 2 * (size_t)r * (size_t)n_cols;
+                if (phase[r] == 0.0) {
+                    memcpy(dst, src, 2 * (size_t)n_cols * sizeof(double));
+                } else {
+                    for (int64_t cc = 0; cc < n_cols; ++cc) {
+                        const double x = src[2 * cc], y = src[2 * cc + 1];
+                        dst[2 * cc] = x * c - y * sn;
+                        dst[2 * cc + 1] = x * sn + y * c;
+                    }
+                }
+            }
+            memcpy(U, tmp, 2 * (size_t)n_rows * (size_t)n_cols * sizeof(double));
+            free(tmp);
+        }
+    }
+    free(perm);
+    free(phase);
+    return rc < 0 ? rc : j;
 }

@@ -739,15 +739,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) {
 }
 
 template <typename R, int V, int M, int U, int STAGES>
-__global__ void __launch_bounds__(kThreads + 64) k_block_gather_inplace(const __grid_constant__ GatherArgs a, const __grid_constant__ GatherFlags f,
+__global__ void __launch_bounds__(kThreads + 96) k_block_gather_inplace(const __grid_constant__ GatherArgs a, const __grid_constant__ GatherFlags f,
                                                                         const int tiles_per_cta) {
     constexpr int NR = 1 << M;
     constexpr uint32_t kTile = kGatherTileBytes * U;             // bytes per source per stage
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);     // full[STAGES], empty[STAGES]
+    volatile int *ready = reinterpret_cast<volatile int *>(smem_raw + 240);   // tiles whose peers have all signalled
     unsigned char *ring = smem_raw + 256;
     R *tab = reinterpret_cast<R *>(ring + (size_t)STAGES * NR * kTile);
-    static_assert(2 * STAGES * 8 <= 256, "barrier block");
+    static_assert(2 * STAGES * 8 <= 240, "barrier block");
     for (int g = 0; g < a.n_members; ++g) {
         const R *src = reinterpret_cast<const R *>(a.tables) + a.mem[g].src_off;
         R *dst = tab + a.mem[g].tab_off;
@@ -759,12 +760,36 @@ __global__ void __launch_bounds__(kThreads + 64) k_block_gather_inplace(const __
             mbar_init(smem_u32(bars + st), 1);
             mbar_init(smem_u32(bars + STAGES + st), kThreads / 32);
         }
+        *ready = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     const uint64_t slab = 1ull << (a.n_local - M);
     const uint64_t tile0 = (uint64_t)blockIdx.x * tiles_per_cta;
+    if (threadIdx.x >= kThreads + 64) {
+        // polling warp: watches the peers' flags for this CTA's tiles, ahead of the consumers, and publishes in shared
+        // memory how many tiles may be overwritten -- the consumers never pay the L2 round trip of a system-scope load
+        const int r = (int)threadIdx.x - (kThreads + 64);
+        for (int k = 0; k < tiles_per_cta; ++k) {
+            if (r < NR && r != f.c_me) {
+                const uint32_t *p = f.flags[f.c_me] + (tile0 + k) * NR + r;
+                if ((int32_t)(ld_relaxed_sys(p) - f.epoch) < 0) {
+                    const long long t0 = clock64();
+                    while ((int32_t)(ld_relaxed_sys(p) - f.epoch) < 0) {
+                        __nanosleep(32);
+                        if (clock64() - t0 > f.spin_limit) { *f.err = 1; break; }
+                    }
+                }
+            }
+            __syncwarp();
+            if (r == 0) {
+                __threadfence_block();
+                *ready = k + 1;
+            }
+        }
+        return;
+    }
     if (threadIdx.x >= kThreads) {
         if (threadIdx.x == kThreads) {
             for (int k = 0; k < tiles_per_cta; ++k) {
@@ -777,7 +802,7 @@ __global__ void __launch_bounds__(kThreads + 64) k_block_gather_inplace(const __
                     bulk_g2s(smem_u32(ring + ((size_t)st * NR + r) * kTile),
                              reinterpret_cast<const unsigned char *>(a.src[r]) + (tile0 + k) * kTile, kTile, full);
             }
-        } else if (threadIdx.x >= kThreads + 32) {
+        } else if (threadIdx.x >= kThreads + 32 && threadIdx.x < kThreads + 64) {
             // signalling warp: lane r tells peer r, as soon as tile k has landed here, that it may overwrite what was read
             const int r = (int)threadIdx.x - (kThreads + 32);
             for (int k = 0; k < tiles_per_cta; ++k) {
@@ -790,19 +815,12 @@ __global__ void __launch_bounds__(kThreads + 64) k_block_gather_inplace(const __
     using IO = VecIO<R, V>;
     R pr[U][NR][V], pi[U][NR][V];                                // the previous tile's results, waiting for their flags
     auto flush = [&](uint64_t tile) {
-        // every peer has read the slabs of `tile` that are about to be overwritten
-        if (threadIdx.x < NR && (int)threadIdx.x != f.c_me) {
-            const uint32_t *p = f.flags[f.c_me] + tile * NR + threadIdx.x;
-            if ((int32_t)(ld_relaxed_sys(p) - f.epoch) < 0) {
-                const long long t0 = clock64();
-                while ((int32_t)(ld_relaxed_sys(p) - f.epoch) < 0) {
-                    __nanosleep(64);
-                    if (clock64() - t0 > f.spin_limit) { *f.err = 1; break; }
-                }
-            }
+        // every peer has read the slabs of `tile` that are about to be overwritten: the polling warp says so in shared
+        // memory; each thread's stores below are control-dependent on its own look at that counter
+        const int need = (int)(tile - tile0) + 1;
+        while (*ready < need) {
+            if (*reinterpret_cast<volatile int32_t *>(f.err)) break;       // the polling warp gave up
         }
-        // the overwrite below is control-dependent on the flags; the barrier hands that to the whole consumer group
-        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
         const uint64_t bv0 = tile * ((uint64_t)kThreads * U) + threadIdx.x;
 #pragma unroll
         for (int u = 0; u < U; ++u)

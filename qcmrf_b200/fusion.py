@@ -147,7 +147,25 @@ def _load_host_apply():
     return f
 
 
+def _load_host_basis():
+    """(qcm_basis_prune, qcm_basis_apply_run) of qcmrf_b200/_qcm_host.so, or None when the library is not built."""
+    import ctypes
+    import os
+    try:
+        L = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), '_qcm_host.so'))
+        pr, ar = L.qcm_basis_prune, L.qcm_basis_apply_run
+    except (OSError, AttributeError):
+        return None
+    vp, i64 = ctypes.c_void_p, ctypes.c_int64
+    pr.restype = i64
+    pr.argtypes = [vp, vp, vp, i64, ctypes.c_int32, vp]
+    ar.restype = i64
+    ar.argtypes = [vp, i64, i64, vp, vp, vp, vp, i64, i64, vp]
+    return pr, ar
+
+
 _HOST_APPLY = _load_host_apply()
+_HOST_BASIS = _load_host_basis()
 _B_ADDR = {}                                       # (base gate, params) -> (matrix, contiguous copy, its address)
 _PAIR_ROWS = {}
 
@@ -483,6 +501,8 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
         fc = hint()                                # the producing circuit class knows its own fused form
         if fc is not None:
             return fc
+    if use_hint and _HOST_BASIS is not None and hasattr(prog, 'bk'):
+        return _fuse_basis(prog, q_max)            # basis-gate arrays (transpile's output): the per-gate work runs in C
     zero = set(range(prog.n_qubits))
     ops: List[FusedOp] = []
     phase = prog.global_phase
@@ -586,9 +606,157 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
         emit(best[1])
         i = best[0]
 
-    # uncontrolled sweeps on qubits that nothing has touched yet belong to the product-state initialiser:
-    # the first on a |0> qubit sets its 2-vector, further ones (the rest of a transpiled H: the fusion
-    # loop peels rz.sx.rz gate by gate) multiply it
+    return _fold_init(prog.n_qubits, ops, phase, len(prog.gates))
+
+
+def _fuse_basis(prog, q_max: int = 8) -> FusedCircuit:
+    """``fuse(prog, 'clique')`` for a basis-gate program held as flat arrays (ir.BasisProgram: the output of
+    ``transpile``, run_experiment.py:52).  Same greedy algorithm, same classification (_classify), same result --
+    tests/test_host_fusion.py pins it against the object-per-gate loop above -- but the per-gate work (zero-control
+    pruning, applying a run of gates to the block matrix) happens in C over the arrays; Python advances one step per
+    qubit that joins a block.  A transpiled fixture circuit (up to ~15 000 gates) costs a few ms instead of ~100."""
+    prune, apply_run = _HOST_BASIS
+    n0 = len(prog.bk)
+    keep = np.ones(n0, dtype=np.uint8)
+    if n0:
+        prune(prog.bk.ctypes.data, prog.bq.ctypes.data, prog.bc.ctypes.data, n0, prog.n_qubits, keep.ctypes.data)
+    sel = keep.astype(bool)
+    bk = np.ascontiguousarray(prog.bk[sel])
+    bq = np.ascontiguousarray(prog.bq[sel])
+    bc = np.ascontiguousarray(prog.bc[sel])
+    bp = np.ascontiguousarray(prog.bp[sel])
+    n = len(bk)
+    N = prog.n_qubits
+    zero = set(range(N))
+    ops: List[FusedOp] = []
+    phase = prog.global_phase
+    idx = np.arange(n)
+    # last / first use of every qubit (as target or control), last gate targeting it
+    last_use = np.full(N, -1, dtype=np.int64)
+    first_use = np.full(N, n, dtype=np.int64)
+    last_target = np.full(N, -1, dtype=np.int64)
+    if n:
+        np.maximum.at(last_use, bq, idx)
+        np.minimum.at(first_use, bq, idx)
+        np.maximum.at(last_target, bq, idx)
+        cxs = bc >= 0
+        np.maximum.at(last_use, bc[cxs], idx[cxs])
+        np.minimum.at(first_use, bc[cxs], idx[cxs])
+    # end of the maximal run of gates with the same target that starts at each gate
+    run_end = np.empty(n + 1, dtype=np.int64)
+    run_end[n] = n
+    if n:
+        change = np.flatnonzero(bq[1:] != bq[:-1]) + 1
+        bounds = np.concatenate([change, [n]])
+        run_end[:n] = bounds[np.searchsorted(bounds, idx, side='right')]
+    pos_arr = np.full(max(N, 1), -1, dtype=np.int32)
+    gate_at = _BasisView(bk, bq, bc, bp)
+
+    def emit(res):
+        nonlocal phase
+        new_ops, touched_q, ph = res
+        phase += ph
+        ops.extend(new_ops)
+        zero.difference_update(touched_q)
+
+    def retired(res, j):
+        new_ops = res[0]
+        return len(new_ops) == 1 and new_ops[0].kind == 'mux' and last_use[new_ops[0].target] < j
+
+    def lifetime_fits(t, i):
+        e = int(last_use[t]) + 1
+        qs = np.unique(np.concatenate([bq[i:e], bc[i:e]]))
+        return len(qs) - (1 if len(qs) and qs[0] < 0 else 0) <= q_max
+
+    doom: Optional[set] = None
+    i = 0
+    while i < n:
+        t = int(bq[i])
+        if (bk[i] != 4 and t in zero and (last_target[t] == i or not lifetime_fits(t, i))):
+            B = gate_at(i).base_matrix()
+            emit(([FusedOp('mux', t, (), np.array([B], dtype=np.complex128), True, 1)], [t], 0.0))
+            i += 1
+            continue
+        if first_use[t] == i:
+            j = int(run_end[i])
+            if last_use[t] == j - 1:
+                res = _run_mux([gate_at(g) for g in range(i, j)], t in zero)
+                if res is not None:
+                    emit(res)
+                    i = j
+                    continue
+        blk = _Block(zero)
+        best = None
+        j = i
+        doomed = doom is not None and sum(1 for q in doom if q in zero) >= 2
+        live_i = int((last_use >= i).sum())                    # distinct qubits used by gates[i:]
+        stopped = False
+        while j < n:
+            qs = (int(bq[j]),) if bc[j] < 0 else (int(bc[j]), int(bq[j]))
+            new = [q for q in qs if q not in blk.pos]
+            if new and blk.qubits:
+                res = _classify(blk)
+                if res is not None:
+                    best = (j, res)
+                    if retired(res, j):
+                        stopped = True
+                        break
+                if len(blk.qubits) + len(new) > q_max:
+                    stopped = True
+                    break
+            for q in new:
+                blk.add_qubit(q)
+                pos_arr[q] = blk.pos[q]
+            U = blk.U
+            if not U.flags.c_contiguous:
+                U = blk.U = np.ascontiguousarray(U)
+            # a doomed block stops right after the gate that completes its qubit set (see `doom` in fuse)
+            limit = j + 1 if (doomed and len(blk.qubits) == live_i) else n
+            j2 = int(apply_run(U.ctypes.data, U.shape[0], U.shape[1], bk.ctypes.data, bq.ctypes.data, bc.ctypes.data,
+                               bp.ctypes.data, j, limit, pos_arr.ctypes.data))
+            if j2 < 0:
+                raise ValueError('basis program holds an unknown gate kind')
+            blk.n_gates += j2 - j
+            j = j2
+            if doomed and len(blk.qubits) == live_i:
+                stopped = True
+                break
+        for q in blk.qubits:
+            pos_arr[q] = -1
+        if not stopped:
+            res = _classify(blk)
+            if res is not None:
+                best = (j, res)
+            else:
+                left = _unrestored_zero_qubits(blk)
+                doom = left if len(left) >= 2 else None
+        if best is None:
+            best = (i + 1, _single_gate_op(gate_at(i), zero))
+        emit(best[1])
+        i = best[0]
+    return _fold_init(prog.n_qubits, ops, phase, n0)
+
+
+class _BasisView:
+    """gate i of a basis-gate array program as an ir.Gate (built on demand: only single gates and short runs need it)."""
+
+    def __init__(self, bk, bq, bc, bp):
+        self.bk, self.bq, self.bc, self.bp = bk, bq, bc, bp
+
+    def __call__(self, i):
+        from .ir import BASIS_KINDS
+        k, q = int(self.bk[i]), int(self.bq[i])
+        if k == 0:
+            return Gate('rz', (q,), (float(self.bp[i]),))
+        if k == 4:
+            return Gate('cx', (int(self.bc[i]), q), (), (1,))
+        return Gate(BASIS_KINDS[k], (q,))
+
+
+def _fold_init(n_qubits, ops, phase, n_gates_in) -> FusedCircuit:
+    """Uncontrolled sweeps on qubits that nothing has touched yet belong to the product-state initialiser: the first on
+    a |0> qubit sets its 2-vector, further ones (the rest of a transpiled H: the fusion loop peels rz.sx.rz gate by
+    gate) multiply it."""
     init: Dict[int, np.ndarray] = {}
     kept: List[FusedOp] = []
     entangled: set = set()                         # qubits some kept sweep involves
@@ -601,7 +769,7 @@ def fuse(prog: Program, mode: str = 'clique', q_max: int = 8, use_hint: bool = T
             entangled.update(op.ctrls)
             if op.kind == 'mux':
                 entangled.add(op.target)
-    return FusedCircuit(prog.n_qubits, init, kept, phase, len(prog.gates))
+    return FusedCircuit(n_qubits, init, kept, phase, n_gates_in)
 
 
 # ------------------------------------------------------------------------------------------
