@@ -519,3 +519,57 @@ def test_positive_theta_is_an_error_on_both_paths():
     q.data                                               # materialise the instruction list: generic walk
     with pytest.raises(ValueError, match='theta must be <= 0'):
         ir.lower(q)
+
+
+def test_basis_array_fusion_equals_the_object_loop(models):
+    """transpile() hands the engine flat gate arrays (ir.BasisProgram); fusion._fuse_basis walks them in C.  It must
+    produce exactly what the object-per-gate loop produces from the same gates: same sweeps, same index-qubit order,
+    tables to rounding (the C side accumulates rz phases as angles) -- on every fixture graph and on random circuits."""
+    from qcmrf_b200.transpile import BasisCircuit
+    if fusion._HOST_BASIS is None:
+        pytest.skip('_qcm_host.so not built')
+    cases = [(C, models['0.5']['THETAS'][str(j)][i]) for j, C in enumerate(models['0.5']['GRAPHS']) for i in (0, 7)]
+    cases.append(([[0, 1], [1, 2]], [0.0, -0.3, 0.0, -1.0, -0.2, 0.0, -0.5, -0.1]))      # skipped (gamma ~ 0) terms
+    for C, th in cases:
+        T = transpile(QCMRF(C, th))
+        assert isinstance(T, BasisCircuit) and T.__dict__['_bc_data'] is None
+        prog = ir.lower(T)
+        assert isinstance(prog, ir.BasisProgram) and prog.metadata['num_vertices'] == max(max(c) for c in C) + 1
+        fast = fusion.fuse(prog, 'clique')
+        slow = fusion.fuse(prog, 'clique', use_hint=False)
+        assert sorted(fast.init) == sorted(slow.init) and len(fast.ops) == len(slow.ops)
+        assert fast.n_gates_in == slow.n_gates_in == len(prog.bk)
+        for q in fast.init:
+            assert np.abs(fast.init[q] - slow.init[q]).max() < 1e-12
+        for a, b in zip(fast.ops, slow.ops):
+            assert (a.kind, a.target, tuple(a.ctrls), a.zero_in) == (b.kind, b.target, tuple(b.ctrls), b.zero_in)
+            assert np.abs(a.table - b.table).max() < 1e-12
+        assert abs(fast.global_phase - slow.global_phase) < 1e-12
+        # the lazily materialised instruction list spells the same gates; touching it switches to the generic walk
+        names = {0: 'rz', 1: 'sx', 2: 'x', 3: 'id', 4: 'cx'}
+        data = [i for i in T.data if i.operation.name != 'measure']
+        assert [i.operation.name for i in data] == [names[int(k)] for k in prog.bk]
+        assert [i.qubits[-1] for i in data] == [int(q) for q in prog.bq]
+        assert T._lower_program() is None
+        walked = ir.lower(T)
+        assert not hasattr(walked, 'bk') and len(walked.gates) == len(prog.bk) and walked.measures == prog.measures
+    # random basis-gate circuits (not QCMRF-shaped): cx onto clean qubits, long 1-qubit runs, every qubit used
+    rng = np.random.RandomState(4)
+    for trial in range(25):
+        n = int(rng.randint(2, 7))
+        ng = int(rng.randint(5, 60))
+        bk = rng.choice([0, 0, 1, 2, 3, 4, 4], size=ng).astype(np.int8)
+        bq = rng.randint(0, n, size=ng).astype(np.int32)
+        bc = np.full(ng, -1, dtype=np.int32)
+        for g in range(ng):
+            if bk[g] == 4:
+                bc[g] = int(rng.choice([q for q in range(n) if q != bq[g]]))
+        bp = rng.uniform(-3, 3, size=ng)
+        prog = ir.BasisProgram(n, n, bk, bq, bc, bp)
+        fast = fusion.fuse(prog, 'clique')
+        slow = fusion.fuse(prog, 'clique', use_hint=False)
+        pl_f, pl_s = fusion.plan(fast, lazy=True, block_max=4), fusion.plan(slow, lazy=True, block_max=4)
+        sf = em.logical_state(pl_f, em.run_plan(pl_f)[0])
+        ss = em.logical_state(pl_s, em.run_plan(pl_s)[0])
+        psi, _ = sv.run_program(ir.to_oracle_ops(prog), n)
+        assert np.abs(sf - psi).max() < 1e-12 and np.abs(ss - psi).max() < 1e-12, trial
