@@ -33,20 +33,26 @@ SHOTS = 10000
 METRIC = 'QCMRF circuits/sec'
 
 
+NCU_TRAFFIC_FILES = ('r02_ncu_prof_low.csv', 'r01_ncu_prof_low.csv')      # newest first
+
+
 def ncu_traffic(workload, world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
-    `ncu --set full` capture of this same workload (profiles/), or None."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, file) from the committed `ncu --set full`
+    capture of this same workload (profiles/), or (None, None)."""
     if workload != 'q34' or world != 1:
-        return None
-    try:
-        import csv
-        tot = 0.0
-        for row in csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_prof_low.csv'))):
-            if row and row[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-                tot += float(row[2].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[row[1]]
-        return tot or None
-    except Exception:
-        return None
+        return None, None
+    import csv
+    for fn in NCU_TRAFFIC_FILES:
+        try:
+            tot = 0.0
+            for row in csv.reader(open(os.path.join(ROOT, 'profiles', fn))):
+                if row and row[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                    tot += float(row[2].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[row[1]]
+            if tot:
+                return tot, 'profiles/' + fn
+        except Exception:
+            continue
+    return None, None
 
 
 def load_peaks():
@@ -500,8 +506,8 @@ def main():
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms_mean},
                 'gpu_launches': int(launches),
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                             'traffic': ncu_traffic(args.workload, world), 'peak_source': peak_src,
-                             'traffic_source': 'profiles/r01_ncu_prof_low.csv (ncu --set full of this kernel, same workload, 1 GPU)',
+                             'traffic': ncu_traffic(args.workload, world)[0], 'peak_source': peak_src,
+                             'traffic_source': '%s (ncu --set full of this kernel, same workload, 1 GPU)' % ncu_traffic(args.workload, world)[1],
                              'kernel': '%s: reads %d B, writes %d B in %.3f ms' % (kname, rd, wr, top_ms)},
                 'program': {'passes': [{'kind': r[0], 'ms': r[1], 'read': r[2], 'written': r[3],
                                         'gbs': (r[2] + r[3]) / max(r[1], 1e-9) / 1e6} for r in prof],

@@ -40,14 +40,17 @@ PyObject *qcm_counts_dict(const uint64_t *keys, Py_ssize_t n, int width) {
     }
     memcpy(a, keys, (size_t)n * sizeof(uint64_t));
     radix_sort_u64(a, a + n, (size_t)n, width);
-    char buf[65];
     Py_ssize_t i = 0;
     while (i < n) {
         const uint64_t v = a[i];
         Py_ssize_t j = i + 1;
         while (j < n && a[j] == v) ++j;
-        for (int c = 0; c < width; ++c) buf[width - 1 - c] = (char)('0' + ((v >> c) & 1u));
-        PyObject *k = PyUnicode_FromStringAndSize(buf, width);
+        /* the key is ASCII by construction: fill a compact 1-byte string in place (no decoding pass) */
+        PyObject *k = PyUnicode_New(width, 127);
+        if (k) {
+            Py_UCS1 *d8 = PyUnicode_1BYTE_DATA(k);
+            for (int c = 0; c < width; ++c) d8[width - 1 - c] = (Py_UCS1)('0' + ((v >> c) & 1u));
+        }
         PyObject *cnt = PyLong_FromSsize_t(j - i);
         if (!k || !cnt || PyDict_SetItem(d, k, cnt) < 0) {
             Py_XDECREF(k);

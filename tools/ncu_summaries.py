@@ -59,7 +59,7 @@ def full(tag):
     """gpurun_out/prof_*.ncu-rep and gpurun_out/<tag>_prof_*.ncu-rep -> profiles/<tag>_ncu_prof_<name>[_<kernel>].csv, one
     file per profiled kernel launch of the report."""
     for fn in sorted(os.listdir(OUT)):
-        if not fn.endswith('.ncu-rep') or not (fn.startswith('prof_') or fn.startswith(tag + '_prof_')):
+        if not fn.endswith('.ncu-rep') or not fn.startswith(tag + '_prof_' if tag != 'r01' else 'prof_'):
             continue
         base = fn[:-len('.ncu-rep')]
         if base.startswith(tag + '_'):
@@ -88,7 +88,7 @@ def full(tag):
 
 if __name__ == '__main__':
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
-    launches(tag)
+    launches(tag, 'launches.csv' if tag == 'r01' else tag + '_launches.csv')
     for fn in sorted(os.listdir(OUT)):                       # e.g. gpurun_out/r02_chain20_launches.csv
         if fn.startswith(tag + '_') and fn.endswith('_launches.csv'):
             launches(tag, fn, fn[:-len('_launches.csv')])
