@@ -351,7 +351,8 @@ def _merge_diags(members):
 
 # ------------------------------------------------------------------------------------------
 class _ShardPrepared:
-    __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions', 'pmf_map', 'pmf_order')
+    __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions', 'pmf_map', 'pmf_order',
+                 '_known_masses')
 
 
 def _clone_sharded(payload, tables, fc):
@@ -785,12 +786,90 @@ class ShardedSimulator:
             pr.pmf_order = self._slice_order(pr, m) if tiles else False
         return bool(pr.pmf_order)
 
+    def _known_rank_masses(self, pr):
+        """Total probability mass of every rank when it follows from the plan alone: in the communication-free layout
+        the global qubits are control-only product-state qubits (fusion.control_only_qubits), every later sweep is a
+        unitary selected by them, so rank r holds exactly  prod_p |v_p[r_p]|^2  (times the norm of the local product
+        state).  The sampler can then start without waiting for an all-gather of measured masses; the measured ones
+        travel with the results and are checked against these.  None when the layout gives no such guarantee."""
+        hit = getattr(pr, '_known_masses', 0)
+        if hit != 0:
+            return hit
+        pl, sp = pr.plan, pr.sp
+        out = None
+        if pl.n_global == self.g and self.g and len(pl.global_init) == self.g and len(pl.ops) and \
+                int(pl.ops[0]['kind']) == fusion.QCM_OP_INIT_PRODUCT and sp.mat_mask == (1 << self.g) - 1:
+            n_init = int(pl.ops[0]['n_active_out'])
+            off = int(pl.ops[0]['table_off'])
+            qv = pl.tables[off:off + 4 * max(n_init, 1)].reshape(-1, 4)
+            norm = float(np.prod((qv[:n_init] ** 2).sum(axis=1))) if n_init else 1.0
+            out = np.full(self.world, norm)
+            for p, v in pl.global_init.items():
+                w = np.abs(np.asarray(v, dtype=np.complex128)) ** 2
+                for r in range(self.world):
+                    out[r] *= w[(r >> (p - sp.n_local)) & 1]
+            if not (out > 0).all():
+                out = None
+        pr._known_masses = out
+        return out
+
+    def _finish_one_collective(self, h, pr, shots, seed, stream, known):
+        """Results of a sharded circuit with ONE collective: the rank masses are known from the plan
+        (_known_rank_masses), so post-selection and sampling run back to back and a single all-gather carries every
+        rank's pmf block, kept mass, measured mass and its shots' keys (0 where the shot landed elsewhere); one read
+        into pinned memory, the keys are merged on the host.  Returns None (after the gather, consistently on every
+        rank) if a measured mass contradicts the plan -- the caller then takes the general path."""
+        t, dist = self.torch, self.dist
+        dev = self._state.device
+        m, _ = pr.pmf_map
+        nb = 1 << m
+        words = nb + 3 + shots
+        key = ('one', words)
+        if getattr(self, '_dbuf_key', None) != key:
+            self._dbuf = {
+                'mine': t.zeros(words, dtype=t.float64, device=dev),
+                'all': t.empty(self.world * words, dtype=t.float64, device=dev),
+                'h_all': t.empty(self.world * words, dtype=t.float64, pin_memory=True),
+                'h_small': t.zeros(2, dtype=t.float64, pin_memory=True),
+                'flag': t.zeros(shots, dtype=t.uint8, device=dev),
+            }
+            self._dbuf_key = key
+        b = self._dbuf
+        mask, value, _ = pr.ps
+        mass = h.sample_prepare()                            # the checkpoint tree's total: already on the host
+        base = b['mine'].data_ptr()
+        h.postselect_device(mask, value, m, base, base + 8 * nb)
+        tol = 1e-9 if self.precision in ('double', 'c128', 64) else 2e-5
+        b['h_small'][0] = mass
+        b['h_small'][1] = 1.0 if abs(mass - known[self.rank]) <= tol * known[self.rank] else 0.0
+        b['mine'][nb + 1:nb + 3].copy_(b['h_small'], non_blocking=True)
+        h.sample_sharded_device(shots, seed, stream, known, pr.clbit_map if len(pr.clbit_map) else None,
+                                base + 8 * (nb + 3), b['flag'].data_ptr())
+        dist.all_gather_into_tensor(b['all'], b['mine'], group=self.group)
+        b['h_all'].copy_(b['all'], non_blocking=True)
+        t.cuda.current_stream(dev).synchronize()
+        hall = b['h_all'].numpy().reshape(self.world, words)
+        if not (hall[:, nb + 2] == 1.0).all():
+            return None
+        kept = float(hall[:, nb].sum())
+        blocks = hall[:, :nb]
+        if pr.pmf_order != list(range(self.world)):
+            blocks = blocks[pr.pmf_order]
+        probs = np.ascontiguousarray(blocks).reshape(-1)
+        keys = hall[:, nb + 3:].view(np.int64).sum(axis=0).astype(np.uint64)
+        return keys, probs, kept
+
     def _finish_on_device(self, h, pr, shots, seed, stream, replica):
         """Post-selection, all-gather of (pmf block, kept, mass), sharded sampling and the key merge with
         every intermediate on the GPU (the sampler reads the gathered rank masses in place): one final read of
         pmf + keys into pinned memory is the only synchronisation."""
         t, dist = self.torch, self.dist
         dev = self._state.device
+        known = None if replica else self._known_rank_masses(pr)
+        if known is not None:
+            out = self._finish_one_collective(h, pr, shots, seed, stream, known)
+            if out is not None:
+                return out
         m, _ = pr.pmf_map
         blk = (1 << m) + 2
         key = (blk, shots)
