@@ -792,8 +792,8 @@ class ShardedSimulator:
         unitary selected by them, so rank r holds exactly  prod_p |v_p[r_p]|^2  (times the norm of the local product
         state).  The sampler can then start without waiting for an all-gather of measured masses; the measured ones
         travel with the results and are checked against these.  None when the layout gives no such guarantee."""
-        hit = getattr(pr, '_known_masses', 0)
-        if hit != 0:
+        hit = getattr(pr, '_known_masses', False)
+        if hit is not False:
             return hit
         pl, sp = pr.plan, pr.sp
         out = None
