@@ -36,6 +36,11 @@ struct qcm_sim_s {
     int batch = 1;                  // sweep points held by this handle (qcm_create_batched); kernels run with gridDim.y = batch
     int cur_point = 0;              // point addressed by qcm_get_amplitudes / qcm_set_amplitudes (qcm_batch_select)
     bool deferred = false;          // qcm_set_deferred: calls enqueue their work and return without synchronising
+    // the last program was INIT_PRODUCT and nothing else: the state is a product state over product_n qubits whose
+    // 2-vectors sit at tab_f64 + product_off (per point); shots are then drawn per qubit (k_sample_product)
+    int product_n = -1;
+    int64_t product_off = 0;
+    double product_mass = 0.0;      // norm^2 of point 0's product state
     size_t tab_stride = 0;          // doubles per point in the uploaded tables
     uint64_t tree_total = 0;        // doubles per point in the sum-tree buffer
     uint64_t probs_n = 0;           // entries per point of the resident post-selected block (qcm_postselect_resident)
@@ -774,7 +779,7 @@ int launch_diag_multi(qcm_handle h, const qcm_op *members, int n_mem, int n_acti
     return QCM_OK;
 }
 
-int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
+int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables, const double *host_tables) {
     const int n = op.n_active_out;
     if (n < 0 || n > h->n_local) return fail(h, QCM_ERR_INVALID, "INIT_PRODUCT over %d qubits (n_local %d)", n, h->n_local);
     if (op.table_off < 0 || (size_t)op.table_off + 4ull * (size_t)std::max(n, 1) > n_tables)
@@ -806,7 +811,29 @@ int launch_init(qcm_handle h, const qcm_op &op, size_t n_tables) {
     QCM_CUDA(h, cudaGetLastError());
     h->timing.kernel_launches++;
     h->timing.bytes_written += amp_bytes(h->prec) << n;
+    h->product_n = n;
+    h->product_off = op.table_off;
+    h->product_mass = 1.0;
+    for (int q = 0; q < n; ++q) {
+        const double *v = host_tables + op.table_off + 4 * q;
+        h->product_mass *= v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+    }
     return QCM_OK;
+}
+
+int product_sampling_enabled() {
+    // QCM_PRODUCT_SAMPLE=0: sample product states through the sum tree like any other state (A/B knob)
+    static int v = [] {
+        const char *e = getenv("QCM_PRODUCT_SAMPLE");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return v;
+}
+
+// the state is a product state the sampler may draw qubit by qubit (unsharded, at most 64 qubits, not rotated)
+bool product_state(const qcm_sim_s *h) {
+    return product_sampling_enabled() && h->product_n >= 0 && h->product_n == h->n_active && h->product_n <= 64 &&
+           h->n_global == 0 && !h->rot_m;
 }
 
 int launch_extend(qcm_handle h, int n_in, int n_out) {
@@ -1279,6 +1306,7 @@ int qcm_set_amplitudes(qcm_handle h, uint64_t first, uint64_t count, const void 
     QCM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n_active = n_active;
     h->tree_valid = false;
+    h->product_n = -1;
     h->rot_m = h->rot_nin = 0;
     return QCM_OK;
 }
@@ -1334,6 +1362,7 @@ int qcm_set_active(qcm_handle h, int n_active) {
     if (h->rot_m && n_active != h->n_active) return fail(h, QCM_ERR_INVALID, "the state is stored rotated; start a new program first");
     h->n_active = n_active;
     h->tree_valid = false;
+    h->product_n = -1;
     return QCM_OK;
 }
 
@@ -1349,6 +1378,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     int rc = check_device(h);
     if (rc) return rc;
     h->tree_valid = false;
+    h->product_n = -1;
     bool keep_tree = false;
     h->timing.bytes_read = h->timing.bytes_written = 0;
     QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -1414,7 +1444,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
         if (op.kind == QCM_OP_INIT_PRODUCT) h->rot_m = h->rot_nin = 0;
         switch (op.kind) {
             case QCM_OP_INIT_PRODUCT:
-                if ((rc = launch_init(h, op, n_tables))) return rc;
+                if ((rc = launch_init(h, op, n_tables, tables))) return rc;
                 break;
             case QCM_OP_MUX1Q:
             case QCM_OP_BLOCK: {
@@ -1502,6 +1532,7 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
                 return fail(h, QCM_ERR_INVALID, "op %d: unknown kind %d", i, op.kind);
         }
         h->n_active = op.n_active_out;
+        if (op.kind != QCM_OP_INIT_PRODUCT) h->product_n = -1;
         if (!keep_tree) h->tree_valid = false;
         QCM_CUDA(h, mark());
         h->op_kind.push_back(op.kind);
@@ -1575,6 +1606,7 @@ static int gather_block_impl(qcm_handle h, const qcm_op *ops, int n_ops, const d
     BlockPlan bp;
     if ((rc = plan_block(h, tq, s, members, n_mem, h->n_local, h->n_local, n_tables, bp))) return rc;
     h->tree_valid = false;
+    h->product_n = -1;
     QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     if ((rc = upload_tables(h, tables, n_tables))) return rc;
     GatherArgs a{};
@@ -1766,6 +1798,10 @@ int qcm_sample_prepare(qcm_handle h, double *local_mass_out) {
     if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
     int rc = check_device(h);
     if (rc) return rc;
+    if (product_state(h)) {                  // no tree: the sampler draws a product state qubit by qubit
+        if (local_mass_out) *local_mass_out = h->product_mass;
+        return QCM_OK;
+    }
     if (!h->tree_valid || h->tree_for_active != h->n_active)
         if ((rc = build_tree(h))) return rc;
     if (local_mass_out) *local_mass_out = h->local_mass;
@@ -1784,6 +1820,49 @@ static int sample_sharded_impl(qcm_handle h, uint64_t shots, uint64_t seed, uint
     if (n_clbits < 0 || n_clbits > 64 || (n_clbits && !clbit_qubit)) return fail(h, QCM_ERR_INVALID, "bad clbit map");
     int rc = check_device(h);
     if (rc) return rc;
+    if (product_state(h) && n_ranks == 1 && !dev_masses) {
+        if (shots == 0) return QCM_OK;
+        QCM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        const uint64_t Bp = (uint64_t)h->batch;
+        ProductSampleArgs pa{};
+        pa.qv = (const double *)h->tab_f64.p + h->product_off;
+        pa.n = h->product_n;
+        pa.shots = shots;
+        pa.seed = seed;
+        pa.stream = stream_id;
+        pa.bqv = btab64(h);
+        pa.bkeys = shots * sizeof(uint64_t);
+        if (stream_ids) {
+            if ((rc = ensure(h, h->streams, sizeof(uint64_t) * Bp))) return rc;
+            QCM_CUDA(h, cudaMemcpyAsync(h->streams.p, stream_ids, sizeof(uint64_t) * Bp, cudaMemcpyHostToDevice, h->stream));
+            pa.streams = (const uint64_t *)h->streams.p;
+        }
+        pa.n_clbits = n_clbits;
+        for (int c = 0; c < n_clbits; ++c) {
+            if (clbit_qubit[c] >= h->n_local) return fail(h, QCM_ERR_INVALID, "clbit %d maps to qubit %d out of range", c, clbit_qubit[c]);
+            pa.clbit_qubit[c] = (int8_t)(clbit_qubit[c] < 0 ? -1 : clbit_qubit[c]);
+        }
+        if (dev) {
+            pa.keys_out = keys_out;
+            if (mine_out) QCM_CUDA(h, cudaMemsetAsync(mine_out, 1, shots, h->stream));
+        } else {
+            if ((rc = ensure(h, h->keys, shots * Bp * sizeof(uint64_t)))) return rc;
+            pa.keys_out = (uint64_t *)h->keys.p;
+        }
+        k_sample_product<<<bgrid(h, (shots + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>(pa);
+        QCM_CUDA(h, cudaGetLastError());
+        h->timing.kernel_launches++;
+        if (dev) return QCM_OK;
+        QCM_CUDA(h, cudaMemcpyAsync(keys_out, h->keys.p, shots * Bp * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+        if (mine_out) memset(mine_out, 1, shots);
+        QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        if (h->deferred) return QCM_OK;
+        QCM_CUDA(h, cudaEventSynchronize(h->ev1));
+        float pms = 0.f;
+        QCM_CUDA(h, cudaEventElapsedTime(&pms, h->ev0, h->ev1));
+        h->timing.sample_ms = pms;
+        return QCM_OK;
+    }
     if (!h->tree_valid || h->tree_for_active != h->n_active)
         if ((rc = build_tree(h))) return rc;
     if (shots == 0) return QCM_OK;

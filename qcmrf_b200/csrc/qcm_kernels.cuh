@@ -2020,6 +2020,66 @@ __global__ void __launch_bounds__(kThreads) k_sample(const __grid_constant__ Sam
     }
 }
 
+// ----------------------------------------------------------------------------------
+// Sampling a PRODUCT state (the program was INIT_PRODUCT and nothing else: e.g. the stored qubits of a QCMRF at
+// measure-and-release width, whose clique sweeps are all released -- DESIGN.md 2a): the qubits are independent, so a
+// shot is one Bernoulli draw per qubit from its 2-vector -- no sum tree, no pass over the state at all.  One thread per
+// shot; Philox4x32-10 keyed (seed ^ kProductKey, stream) at counter (shot, qubit / 4) yields four 32-bit draws per call.
+// ----------------------------------------------------------------------------------
+constexpr uint64_t kProductKey = 0xC2B2AE3D27D4EB4Full;
+
+__device__ __forceinline__ void philox4(uint64_t seed, uint64_t stream, uint64_t ctr, uint32_t (&out)[4]) {
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+struct ProductSampleArgs {
+    const double *qv;               // device: n * 4 doubles per point (amp0.re, amp0.im, amp1.re, amp1.im per qubit)
+    int32_t n;                      // qubits of the product state (<= 64)
+    uint64_t shots, seed, stream;
+    const uint64_t *streams;        // batched: per-point streams (or null)
+    uint64_t bqv, bkeys;            // batch strides, bytes
+    int32_t n_clbits;               // 0 => raw indices
+    int8_t clbit_qubit[64];
+    uint64_t *keys_out;
+};
+
+static __global__ void __launch_bounds__(kThreads) k_sample_product(const __grid_constant__ ProductSampleArgs a) {
+    __shared__ double p1[64];
+    const double *qv = batch_ptr(a.qv, a.bqv);
+    if (threadIdx.x < (unsigned)a.n) {
+        const double w0 = qv[4 * threadIdx.x] * qv[4 * threadIdx.x] + qv[4 * threadIdx.x + 1] * qv[4 * threadIdx.x + 1];
+        const double w1 = qv[4 * threadIdx.x + 2] * qv[4 * threadIdx.x + 2] + qv[4 * threadIdx.x + 3] * qv[4 * threadIdx.x + 3];
+        p1[threadIdx.x] = (w0 + w1) > 0.0 ? w1 / (w0 + w1) : 0.0;
+    }
+    __syncthreads();
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.shots) return;
+    const uint64_t stream = a.streams ? a.streams[blockIdx.y] : a.stream;
+    uint64_t idx = 0;
+    for (int q0 = 0; q0 < a.n; q0 += 4) {
+        uint32_t r[4];
+        philox4(a.seed ^ kProductKey, stream, s * 16ull + (uint64_t)(q0 >> 2), r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = q0 + j;
+            if (q < a.n && (double)r[j] * (1.0 / 4294967296.0) < p1[q]) idx |= 1ull << q;
+        }
+    }
+    uint64_t key = idx;
+    if (a.n_clbits > 0) {
+        key = 0;
+        for (int c = 0; c < a.n_clbits; ++c) {
+            const int q = a.clbit_qubit[c];
+            if (q >= 0) key |= ((idx >> q) & 1ull) << c;
+        }
+    }
+    batch_ptr(a.keys_out, a.bkeys)[s] = key;
+}
+
 // total[y] = sum of the top tree level of sweep point y, in index order (one thread per point)
 static __global__ void k_batch_totals(const double *top, uint64_t n_top, uint64_t btree, double *totals, int batch) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;

@@ -423,6 +423,61 @@ def test_diagonal_block_is_one_sweep(precision):
         assert np.abs(h.get_amplitudes().astype(np.complex128) - want).max() < (1e-12 if precision == 'double' else 3e-6)
 
 
+@pytest.mark.parametrize('batch', [1, 3])
+def test_product_state_is_sampled_qubit_by_qubit(batch):
+    """A program that is INIT_PRODUCT and nothing else leaves a product state: shots are one Bernoulli draw per qubit
+    (k_sample_product: no sum tree, no pass over the state) -- histogram against the exact product law, clbit map,
+    seed determinism; any further op switches back to the tree sampler."""
+    N, shots = 8, 200000
+    rng = np.random.RandomState(31)
+    qvs = []
+    for _ in range(batch):
+        qv = rng.randn(N, 4)
+        qv /= np.sqrt((qv ** 2).sum(axis=1, keepdims=True))
+        qvs.append(qv)
+    with _native.Handle(N, 'double', batch=batch) as h:
+        e = fusion._Emitter()
+        e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=N, table_off=e.table(qvs[0]))
+        ops, tabs = e.finish()
+        rows = np.stack([np.concatenate([q.reshape(-1), np.zeros(tabs.size - q.size)]) for q in qvs])
+        l0 = h.timing()['kernel_launches']
+        if batch == 1:
+            h.run_program(ops, rows[0])
+            keys = [h.sample(shots, 5, 2, None)]
+            again = [h.sample(shots, 5, 2, None)]
+            cl = h.sample(1000, 5, 2, np.array([3, -1, 0], dtype=np.int32))
+            raw = h.sample(1000, 5, 2, None)
+            assert np.array_equal(cl, ((raw >> 3) & 1) | (((raw >> 0) & 1) << 2))
+        else:
+            h.run_program(ops, rows)
+            keys = list(h.sample_batched(shots, 5, np.array([2, 9, 11]), None))
+            again = list(h.sample_batched(shots, 5, np.array([2, 9, 11]), None))
+        # init tables + init + one sampling kernel per call: no tree kernels were launched
+        assert h.timing()['kernel_launches'] - l0 == 2 + (4 if batch == 1 else 2)
+        for y in range(batch):
+            assert np.array_equal(keys[y], again[y])
+            p1 = (qvs[y][:, 2] ** 2 + qvs[y][:, 3] ** 2)
+            idx = np.arange(1 << N)
+            exact = np.ones(1 << N)
+            for q in range(N):
+                exact *= np.where((idx >> q) & 1, p1[q], 1 - p1[q])
+            obs = np.bincount(keys[y].astype(np.int64), minlength=1 << N) / shots
+            assert 0.5 * np.abs(obs - exact).sum() < weissman_tv_bound(1 << N, shots)
+        if batch == 1:
+            assert np.array_equal(keys[0], _native_sample_again_after_noop(h, ops, rows[0], shots)) is False
+
+
+def _native_sample_again_after_noop(h, ops, tabs, shots):
+    """The same state after one more (identity) sweep is no longer known to be a product state: the tree sampler
+    serves it -- other random numbers, same distribution."""
+    e = fusion._Emitter()
+    e.op(fusion.QCM_OP_INIT_PRODUCT, n_in=0, n_out=8, table_off=e.table(tabs[:32].reshape(8, 4)))
+    e.op(fusion.QCM_OP_DIAG, ctrl=[1], n_in=8, n_out=8, table_off=e.table(np.array([[1.0, 0.0], [1.0, 0.0]])))
+    ops2, tabs2 = e.finish()
+    h.run_program(ops2, tabs2)
+    return h.sample(shots, 5, 2, None)
+
+
 @pytest.mark.parametrize('precision', ['double', 'single'])
 def test_lazy_materialisation_ops(precision):
     """Ops that materialise qubits: zero-input targets are never read (the buffer holds NaN
