@@ -684,8 +684,10 @@ def sweep_bench(args, world, rank, device, barrier, torch, dist):
         top_name, (_kind, top_ms, top_rd, top_wr) = top
         amp = 16 << n
         B = len(mine)
+        tree_read = B * amp if os.environ.get('QCM_PRODUCT_SAMPLE') == '0' else 0
         algo = (sum(r[1][2] + r[1][3] for r in launches_all)      # init write + the projection passes
-                + B * amp                                          # sampler: one read of every state for the sum tree
+                + tree_read                                        # sampler: the stored state of an all-released QCMRF is a
+                                                                   # product state, drawn per qubit (no sum tree, no state read)
                 + B * amp + B * (8 << n))                          # post-selection: read the state, write the pmf
         line = {'metric': METRIC, 'value': points / (ms_step * 1e-3), 'unit': 'circuits/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
