@@ -688,21 +688,28 @@ class ShardedSimulator:
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         e0.record()
         h.set_shard(sp.g, sp.rank & mask)
-        if self._peer_flags is not None:
-            # in place: the kernels of all ranks order their overwrites behind each other's reads with flags
-            self._epoch += 1
-            h.run_gather_block_inplace(ops, tabs, src, [self._peer_flags[pr] for pr in peers], self._flag_words, self._epoch)
-            e1.record()
-            t.cuda.synchronize()
-            dist.barrier(group=self.group)      # every peer's kernel is done: its signals and reads are behind us
-            return e0.elapsed_time(e1)
-        dst = self._bufs[1 - self._cur]
-        h.run_gather_block(ops, tabs, src, dst.data_ptr())
+        inplace = self._peer_flags is not None
+        err = None
+        try:
+            if inplace:
+                # in place: the kernels of all ranks order their overwrites behind each other's reads with flags
+                self._epoch += 1
+                h.run_gather_block_inplace(ops, tabs, src, [self._peer_flags[pr] for pr in peers], self._flag_words, self._epoch)
+            else:
+                dst = self._bufs[1 - self._cur]
+                h.run_gather_block(ops, tabs, src, dst.data_ptr())
+        except Exception as e:                  # noqa: BLE001 -- every rank must reach the barrier below, then fail together
+            err = e
         e1.record()
         t.cuda.synchronize()
-        dist.barrier(group=self.group)          # every peer has finished reading this rank's old buffer
-        self._cur = 1 - self._cur
-        self._state = dst
+        # every peer's kernel is done: its signals and reads are behind us / it has finished reading this rank's old buffer
+        bad = t.tensor([1 if err is not None else 0], dtype=t.int32, device=self._state.device)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        if int(bad.item()):
+            raise RuntimeError('fused exchange failed on %s: %r' % ('this rank' if err is not None else 'a peer', err))
+        if not inplace:
+            self._cur = 1 - self._cur
+            self._state = dst
         return e0.elapsed_time(e1)
 
     def _is_replica(self, sp):
