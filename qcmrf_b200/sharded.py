@@ -723,6 +723,37 @@ class ShardedSimulator:
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
         return x.cpu().numpy()
 
+    def execute_deferred(self, pr, shots, seed=0, stream=0):
+        """Run the gate program and ENQUEUE the result handling; returns a zero-argument callable that finishes it and
+        returns what execute() returns.  Between the two the next circuit's program can be launched: a stream of
+        circuits then pays the collective, the read-back and the host-side merge behind the next gate program instead
+        of in front of it.  Falls back to plain execute() where the one-collective path does not apply."""
+        sp = pr.sp
+        replica = self._is_replica(sp)
+        if not (pr.ps is not None and pr.n_vars <= 30 and shots and not replica):
+            out = self.execute(pr, shots, seed, stream)
+            return lambda: out
+        t0 = time.perf_counter()
+        h = self._run_segments(sp, keep_flags=True)
+        t1 = time.perf_counter()
+        if not (self._state.is_cuda and hasattr(h, 'postselect_device') and self._device_path_ok(pr)):
+            out = self._finish_general(h, pr, shots, seed, stream, replica, True, t0, t1)
+            return lambda: out
+        known = self._known_rank_masses(pr)
+        if known is None:
+            out = self._finish_on_device(h, pr, shots, seed, stream, replica)
+            return lambda: out
+        rec = self._enqueue_one_collective(h, pr, shots, seed, stream, known)
+        self.breakdown_ms = {'program': (t1 - t0) * 1e3, 'results enqueued (deferred)': (time.perf_counter() - t1) * 1e3}
+
+        def finish():
+            out = self._collect_one_collective(rec)
+            if out is None:
+                raise RuntimeError('a measured rank mass contradicts the plan; results of a deferred execution cannot be '
+                                   'recomputed (the state has moved on): use execute()')
+            return out
+        return finish
+
     def execute(self, pr, shots, seed=0, stream=0, want_probs=True):
         """Returns (keys or None, probs or None, kept or None); identical on every rank."""
         sp = pr.sp
@@ -736,6 +767,9 @@ class ShardedSimulator:
             t2 = time.perf_counter()
             self.breakdown_ms = {'program': (t1 - t0) * 1e3, 'results (device path)': (t2 - t1) * 1e3}
             return keys, probs, kept
+        return self._finish_general(h, pr, shots, seed, stream, replica, want_probs, t0, t1)
+
+    def _finish_general(self, h, pr, shots, seed, stream, replica, want_probs, t0, t1):
         probs = kept = masses = None
         mass = None
         if shots:
@@ -820,12 +854,13 @@ class ShardedSimulator:
         pr._known_masses = out
         return out
 
-    def _finish_one_collective(self, h, pr, shots, seed, stream, known):
+    def _enqueue_one_collective(self, h, pr, shots, seed, stream, known):
         """Results of a sharded circuit with ONE collective: the rank masses are known from the plan
         (_known_rank_masses), so post-selection and sampling run back to back and a single all-gather carries every
-        rank's pmf block, kept mass, measured mass and its shots' keys (0 where the shot landed elsewhere); one read
-        into pinned memory, the keys are merged on the host.  Returns None (after the gather, consistently on every
-        rank) if a measured mass contradicts the plan -- the caller then takes the general path."""
+        rank's pmf block, kept mass, measured mass and its shots' keys (0 where the shot landed elsewhere), followed
+        by one read into pinned memory.  Everything is only ENQUEUED here; the returned record is finished by
+        _collect_one_collective -- in between the next circuit's gate program can already run (the device buffers
+        are reused in stream order, the pinned ones come from a ring of three)."""
         t, dist = self.torch, self.dist
         dev = self._state.device
         m, _ = pr.pmf_map
@@ -836,35 +871,62 @@ class ShardedSimulator:
             self._dbuf = {
                 'mine': t.zeros(words, dtype=t.float64, device=dev),
                 'all': t.empty(self.world * words, dtype=t.float64, device=dev),
-                'h_all': t.empty(self.world * words, dtype=t.float64, pin_memory=True),
-                'h_small': t.zeros(2, dtype=t.float64, pin_memory=True),
+                'h_all': [t.empty(self.world * words, dtype=t.float64, pin_memory=True) for _ in range(3)],
+                'h_small': [t.zeros(2, dtype=t.float64, pin_memory=True) for _ in range(3)],
                 'flag': t.zeros(shots, dtype=t.uint8, device=dev),
+                'slot': 0, 'busy': [None, None, None],
             }
             self._dbuf_key = key
         b = self._dbuf
+        slot = b['slot']
+        b['slot'] = (slot + 1) % 3
+        old = b['busy'][slot]
+        if old is not None and not old['done'].wait(timeout=60):
+            # the pinned buffer of this slot still belongs to a deferred execution three circuits old
+            raise RuntimeError('deferred executions must be finished (call what execute_deferred returned) before three '
+                               'more are started')
         mask, value, _ = pr.ps
         mass = h.sample_prepare()                            # the checkpoint tree's total: already on the host
         base = b['mine'].data_ptr()
         h.postselect_device(mask, value, m, base, base + 8 * nb)
         tol = 1e-9 if self.precision in ('double', 'c128', 64) else 2e-5
-        b['h_small'][0] = mass
-        b['h_small'][1] = 1.0 if abs(mass - known[self.rank]) <= tol * known[self.rank] else 0.0
-        b['mine'][nb + 1:nb + 3].copy_(b['h_small'], non_blocking=True)
+        hs = b['h_small'][slot]
+        hs[0] = mass
+        hs[1] = 1.0 if abs(mass - known[self.rank]) <= tol * known[self.rank] else 0.0
+        b['mine'][nb + 1:nb + 3].copy_(hs, non_blocking=True)
         h.sample_sharded_device(shots, seed, stream, known, pr.clbit_map if len(pr.clbit_map) else None,
                                 base + 8 * (nb + 3), b['flag'].data_ptr())
         dist.all_gather_into_tensor(b['all'], b['mine'], group=self.group)
-        b['h_all'].copy_(b['all'], non_blocking=True)
-        t.cuda.current_stream(dev).synchronize()
-        hall = b['h_all'].numpy().reshape(self.world, words)
-        if not (hall[:, nb + 2] == 1.0).all():
-            return None
-        kept = float(hall[:, nb].sum())
-        blocks = hall[:, :nb]
-        if pr.pmf_order != list(range(self.world)):
-            blocks = blocks[pr.pmf_order]
-        probs = np.ascontiguousarray(blocks).reshape(-1)
-        keys = hall[:, nb + 3:].view(np.int64).sum(axis=0).astype(np.uint64)
-        return keys, probs, kept
+        b['h_all'][slot].copy_(b['all'], non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record()
+        import threading
+        rec = {'event': ev, 'slot': slot, 'nb': nb, 'words': words, 'order': pr.pmf_order, 'done': threading.Event()}
+        b['busy'][slot] = rec
+        return rec
+
+    def _collect_one_collective(self, rec):
+        """(keys, probs, kept) of an enqueued record, or None (consistently on every rank) if a measured rank mass
+        contradicted the plan -- the caller then takes the general path."""
+        b = self._dbuf
+        rec['event'].synchronize()
+        nb, words = rec['nb'], rec['words']
+        hall = b['h_all'][rec['slot']].numpy().reshape(self.world, words)
+        ok = bool((hall[:, nb + 2] == 1.0).all())
+        out = None
+        if ok:
+            kept = float(hall[:, nb].sum())
+            blocks = hall[:, :nb]
+            if rec['order'] != list(range(self.world)):
+                blocks = blocks[rec['order']]
+            probs = np.ascontiguousarray(blocks).reshape(-1)
+            keys = hall[:, nb + 3:].view(np.int64).sum(axis=0).astype(np.uint64)
+            out = (keys, probs, kept)
+        rec['done'].set()                                    # the pinned buffer of this slot may be reused
+        return out
+
+    def _finish_one_collective(self, h, pr, shots, seed, stream, known):
+        return self._collect_one_collective(self._enqueue_one_collective(h, pr, shots, seed, stream, known))
 
     def _finish_on_device(self, h, pr, shots, seed, stream, replica):
         """Post-selection, all-gather of (pmf block, kept, mass), sharded sampling and the key merge with
@@ -1008,21 +1070,40 @@ class ShardedSimulator:
         circs = [circuits] if single else list(circuits)
         if seed is None:
             seed = self.seed if self.seed is not None else 0
-        entries = []
-        for i, c in enumerate(circs):
-            pr = self.prepare(c, n_vars=n_vars)
-            keys, probs, kept = self.execute(pr, int(shots), seed, i)
+        def entry(c, pr, i, finish, exchange_ms):
+            keys, probs, kept = finish()
             counts = _keys_to_counts(keys, pr.prog.n_clbits) if shots else None
             h2d = sum(seg[1].nbytes + seg[2].nbytes for seg in pr.sp.segments if seg[0] == 'run')
             d2h = (probs.nbytes + 8 if probs is not None else 0) + (keys.nbytes if keys is not None else 0)
-            entries.append({'circuit': c, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
-                            'meta': {'path': 'sharded', 'ranks': self.world, 'n_qubits': pr.prog.n_qubits,
-                                     'n_phys': pr.plan.n_phys, 'n_local': pr.sp.n_local, 'passes': pr.plan.n_passes,
-                                     'exchanges': pr.sp.n_exchanges, 'exchange_ms': self.exchange_ms,
-                                     'exchange_path': ('p2p-fused-inplace' if self._peer_flags is not None else 'p2p-fused')
-                                     if self._peer_bufs is not None else 'nccl',
-                                     'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': i}})
+            return {'circuit': c, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
+                    'meta': {'path': 'sharded', 'ranks': self.world, 'n_qubits': pr.prog.n_qubits,
+                             'n_phys': pr.plan.n_phys, 'n_local': pr.sp.n_local, 'passes': pr.plan.n_passes,
+                             'exchanges': pr.sp.n_exchanges, 'exchange_ms': exchange_ms,
+                             'exchange_path': ('p2p-fused-inplace' if self._peer_flags is not None else 'p2p-fused')
+                             if self._peer_bufs is not None else 'nccl',
+                             'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': i}}
+
+        entries = []
+        if len(circs) > 1 and shots and self._state_is_cuda():
+            # a list of circuits is a pipeline: while circuit i+1's gate program runs, a worker thread finishes circuit i
+            # (waits for its collective + read-back, merges the keys, builds the counts dict)
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=1) as pool:
+                futs = []
+                for i, c in enumerate(circs):
+                    pr = self.prepare(c, n_vars=n_vars)
+                    fin = self.execute_deferred(pr, int(shots), seed, i)
+                    futs.append(pool.submit(entry, c, pr, i, fin, self.exchange_ms))
+                entries = [f.result() for f in futs]
+        else:
+            for i, c in enumerate(circs):
+                pr = self.prepare(c, n_vars=n_vars)
+                out = self.execute(pr, int(shots), seed, i)
+                entries.append(entry(c, pr, i, lambda out=out: out, self.exchange_ms))
         return Job(Result(entries, single, self._name, seed, int(shots), time.perf_counter() - t0))
+
+    def _state_is_cuda(self):
+        return self._state is None or bool(getattr(self._state, 'is_cuda', False))
 
     def exact(self, circuit, n=None):
         return self.run(circuit, shots=0, n_vars=n).result().postselected_probabilities(0)

@@ -74,7 +74,24 @@ def main():
                 assert abs(succ - db) < 5 * np.sqrt(db * (1 - db) / 2e5) + 1e-4, (succ, db)
                 report['%s/%s/%s/%s' % (prec, fus, layout, xch)] = {'max_p_err': err, 'tv': float(tv), 'exchanges': meta['exchanges']}
             sim.close()
+    # a LIST of circuits is pipelined (deferred result handling + a worker thread): same results as one at a time
+    sim = ShardedSimulator(precision='double', device=lr, seed=77)
+    ths = [workloads.theta_for(C, seed=60 + k) for k in range(4)]
+    res = sim.run([QCMRF(C, t_) for t_ in ths], shots=20000).result()
+    one = sim.run(QCMRF(C, ths[0]), shots=20000).result()
+    assert res.get_counts(0) == one.get_counts()
+    for k, t_ in enumerate(ths):
+        pk, dk = res.postselected_probabilities(k)
+        pbk, dbk, _ = mrf.brute_force_pmf(C, t_)
+        assert np.abs(pk - pbk).max() < 1e-10 and abs(dk - dbk) < 1e-10, k
+        assert sum(res.get_counts(k).values()) == 20000
+    blob = json.dumps([sorted(c.items()) for c in res.get_counts()])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, blob)
+    assert all(g == gathered[0] for g in gathered)
+    sim.close()
     if rank == 0:
+        report['pipelined_list'] = 'ok'
         print('MULTI_GPU_OK ' + json.dumps(report), flush=True)
     dist.barrier()
     dist.destroy_process_group()
