@@ -432,6 +432,10 @@ def main():
     n_vars = prep.n_vars
     for _ in range(args.warmup):
         out = sim.execute(prep, SHOTS, seed=1984, stream=0)
+    # per-launch record (CUDA events inside the library) of the last warm-up execution: the timed loop of a sharded run
+    # only enqueues its programs, which leaves no per-op timings behind
+    prof = sim.op_profile()
+    kernels = sim.op_kernels() if hasattr(sim, 'op_kernels') else []
     launches0 = sim.kernel_launches()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -440,7 +444,6 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
-    prof = None
     pending = None
     for _ in range(args.steps):
         if hasattr(sim, 'execute_deferred'):
@@ -452,9 +455,6 @@ def main():
             pending = fin
         else:
             out = sim.execute(prep, SHOTS, seed=1984, stream=0)
-        if prof is None:
-            prof = sim.op_profile()
-            kernels = sim.op_kernels() if hasattr(sim, 'op_kernels') else []
     if pending is not None:
         out = pending()
     ev1.record()

@@ -202,6 +202,11 @@ int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint6
                               const int32_t *clbit_qubit, int n_clbits,
                               void *dev_keys_out, void *dev_mine_out);
 
+/* Total |amp|^2 of the local state (per point of a batched handle), summed from the sampler's sum tree on the device
+ * into dev_total_out (DEVICE pointer, `batch` doubles), in stream order -- for callers in deferred mode, where
+ * qcm_sample_prepare cannot report the mass to the host.                                                   */
+int qcm_tree_total_device(qcm_handle h, void *dev_total_out);
+
 /* As qcm_sample_sharded_device, with the rank masses still in DEVICE memory (e.g. straight out of an NCCL
  * all-gather): the mass of rank r is the double at dev_rank_masses[r * mass_stride].  Nothing has to come back
  * to the host between the all-gather and the sampler.                                                       */

@@ -43,7 +43,8 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_sample_released', 'qcm_create_batched', 'qcm_batch_size', 'qcm_batch_select',
            'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched',
            'qcm_sample_sharded_devmass', 'qcm_mrf_exact', 'qcm_mrf_last_error', 'qcm_gather_flag_words',
-           'qcm_run_gather_block_inplace', 'qcm_set_deferred', 'qcm_host_alloc', 'qcm_host_free']
+           'qcm_run_gather_block_inplace', 'qcm_set_deferred', 'qcm_host_alloc', 'qcm_host_free',
+           'qcm_tree_total_device']
 
 
 def lib():
@@ -96,6 +97,7 @@ def lib():
     L.qcm_fetch_probs.argtypes = [vp, i32, u64, u64, vp]
     L.qcm_sample_batched.argtypes = [vp, u64, u64, vp, vp, i32, vp]
     L.qcm_set_deferred.argtypes = [vp, i32]
+    L.qcm_tree_total_device.argtypes = [vp, vp]
     L.qcm_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.qcm_host_free.argtypes = [vp]
     L.qcm_gather_flag_words.argtypes = [i32, i32, i32, ctypes.POINTER(u64)]
@@ -232,6 +234,10 @@ class Handle:
         out = np.empty(int(count), dtype=np.float64)
         self._check(lib().qcm_fetch_probs(self._h, int(point), int(first), int(count), _ptr(out)))
         return out
+
+    def tree_total_device(self, dev_ptr):
+        """qcm_tree_total_device: the local state's total |amp|^2 written to a device double, in stream order."""
+        self._check(lib().qcm_tree_total_device(self._h, ctypes.c_void_p(dev_ptr)))
 
     def set_deferred(self, flag):
         """Deferred mode: calls enqueue and return; pass page-locked output arrays (pinned_empty) and call synchronize()."""

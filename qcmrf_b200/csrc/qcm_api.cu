@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -889,8 +890,8 @@ int upload_tables(qcm_handle h, const double *tables, size_t n_per_point) {
         std::vector<float> f(n_tables);
         for (size_t i = 0; i < n_tables; ++i) f[i] = (float)tables[i];
         if ((rc = ensure(h, h->tab_real, n_tables * sizeof(float)))) return rc;
+        // pageable source: the runtime stages it before the call returns, so `f` may go out of scope (no synchronisation)
         QCM_CUDA(h, cudaMemcpyAsync(h->tab_real.p, f.data(), n_tables * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        QCM_CUDA(h, cudaStreamSynchronize(h->stream));     // f goes out of scope
     }                                  // complex128: the fp64 upload IS the table in the state's real type (tabreal)
     return QCM_OK;
 }
@@ -973,12 +974,18 @@ int tree_finish(qcm_handle h, int na) {
         h->tree_has_sub = false;
         return QCM_OK;
     }
-    h->h_top.resize(ntop);
-    QCM_CUDA(h, cudaMemcpyAsync(h->h_top.data(), h->tree_ptr[levels - 1], ntop * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    QCM_CUDA(h, cudaStreamSynchronize(h->stream));
-    double m = 0.0;
-    for (uint64_t i = 0; i < ntop; ++i) m += h->h_top[i];
-    h->local_mass = m;
+    if (h->deferred) {
+        // deferred mode: nothing is read back (qcm_tree_total_device sums the top level on the device for callers that
+        // continue there); the local mass is unknown on the host
+        h->local_mass = std::nan("");
+    } else {
+        h->h_top.resize(ntop);
+        QCM_CUDA(h, cudaMemcpyAsync(h->h_top.data(), h->tree_ptr[levels - 1], ntop * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        QCM_CUDA(h, cudaStreamSynchronize(h->stream));
+        double m = 0.0;
+        for (uint64_t i = 0; i < ntop; ++i) m += h->h_top[i];
+        h->local_mass = m;
+    }
     h->tree_valid = true;
     h->tree_for_active = na;
     h->tree_base_bits = na;
@@ -1960,6 +1967,20 @@ int qcm_sample_sharded_device(qcm_handle h, uint64_t shots, uint64_t seed, uint6
     if (!dev_mine_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
     return sample_sharded_impl(h, shots, seed, stream_id, rank_masses, n_ranks, clbit_qubit, n_clbits, (uint64_t *)dev_keys_out,
                                (uint8_t *)dev_mine_out, true);
+}
+
+int qcm_tree_total_device(qcm_handle h, void *dev_total_out) {
+    if (!h || !dev_total_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    int rc = check_device(h);
+    if (rc) return rc;
+    if (!h->tree_valid || h->tree_for_active != h->n_active)
+        if ((rc = build_tree(h))) return rc;
+    const int levels = h->tree_levels;
+    k_batch_totals<<<(h->batch + 127) / 128, 128, 0, h->stream>>>(h->tree_ptr[levels - 1], h->tree_n[levels - 1],
+                                                                  h->tree_total * sizeof(double), (double *)dev_total_out, h->batch);
+    QCM_CUDA(h, cudaGetLastError());
+    h->timing.kernel_launches++;
+    return QCM_OK;
 }
 
 int qcm_sample_sharded_devmass(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, const void *dev_rank_masses,
