@@ -1094,16 +1094,17 @@ class ShardedSimulator:
 
         entries = []
         if len(circs) > 1 and shots and self._state_is_cuda():
-            # a list of circuits is a pipeline: while circuit i+1's gate program runs, a worker thread finishes circuit i
-            # (waits for its collective + read-back, merges the keys, builds the counts dict)
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=1) as pool:
-                futs = []
-                for i, c in enumerate(circs):
-                    pr = self.prepare(c, n_vars=n_vars)
-                    fin = self.execute_deferred(pr, int(shots), seed, i)
-                    futs.append(pool.submit(entry, c, pr, i, fin, self.exchange_ms))
-                entries = [f.result() for f in futs]
+            # a list of circuits is a pipeline: circuit i+1 is prepared and its gate program enqueued BEFORE circuit i's
+            # results are collected (collective + read-back awaited, keys merged, counts dict built), so the GPU works on
+            # i+1 while the host finishes i.  One thread: eight ranks with a helper thread each oversubscribed the host.
+            pend = None
+            for i, c in enumerate(circs):
+                pr = self.prepare(c, n_vars=n_vars)
+                fin = self.execute_deferred(pr, int(shots), seed, i)
+                if pend is not None:
+                    entries.append(entry(*pend))
+                pend = (c, pr, i, fin, self.exchange_ms)
+            entries.append(entry(*pend))
         else:
             for i, c in enumerate(circs):
                 pr = self.prepare(c, n_vars=n_vars)
