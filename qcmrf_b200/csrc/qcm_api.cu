@@ -401,21 +401,26 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
     return QCM_OK;
 }
 
-int low_tile_bits() {
-    // QCM_LOW_TB: log2 of the inputs per CTA of the rotated expansion pass (10, 8 or 7): tuning knob.
-    // q34 last pass on a B200: 9.83 ms with 1024 inputs per CTA, 9.70 ms with 256 (profiles/r01_notes.md)
+int low_shape() {
+    // QCM_LOW_SHAPE = <warps per CTA>x<log2 inputs per CTA> of the rotated expansion pass: tuning knob.
+    // Default 2x6: membench4 shows that the smaller the region a CTA writes, the more compact the window of
+    // concurrently written addresses (q34 last pass: see profiles/r02_notes.md for the sweep).
     static int v = [] {
-        const char *e = getenv("QCM_LOW_TB");
-        const int t = e ? atoi(e) : 8;
-        return (t == 10 || t == 7) ? t : 8;
+        const char *e = getenv("QCM_LOW_SHAPE");
+        int w = 2, tb = 6;
+        if (e && sscanf(e, "%dx%d", &w, &tb) == 2) {
+            const bool ok = (w == 8 && (tb == 8 || tb == 10)) || (w == 4 && tb == 7) || (w == 2 && tb == 6) || (w == 1 && tb == 5);
+            if (!ok) { w = 2; tb = 6; }
+        }
+        return w * 100 + tb;
     }();
     return v;
 }
 
-template <typename R, int V, int MH, int TB>
+template <typename R, int V, int MH, int TB, int NW>
 static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
-    auto kern = k_expand_low<R, V, MH, TB>;
-    constexpr int warps = low_threads<R>() / 32;
+    auto kern = k_expand_low<R, V, MH, TB, NW>;
+    constexpr int warps = NW;
     const size_t smem = low_warp_bytes<R, MH>() * warps + bp.tree_smem;
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ExpandTreeArgs args = bp.trargs;
@@ -425,10 +430,10 @@ static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
         if (rc) return rc;
         args.tree_out = (double *)h->lowpart.p;
     }
-    kern<<<1u << (n_in - TB), low_threads<R>(), smem, h->stream>>>(args, h->scratch.p);
+    kern<<<1u << (n_in - TB), NW * 32, smem, h->stream>>>(args, h->scratch.p);
     {
         char nm[96];
-        snprintf(nm, sizeof nm, "k_expand_low<%s,%d,MH=%d,TB=%d>", sizeof(R) == 4 ? "float" : "double", V, MH, TB);
+        snprintf(nm, sizeof nm, "k_expand_low<%s,%d,MH=%d,TB=%d,NW=%d>", sizeof(R) == 4 ? "float" : "double", V, MH, TB, NW);
         h->cur_kernel = nm;
     }
     QCM_CUDA(h, cudaGetLastError());
@@ -445,11 +450,13 @@ static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
 
 template <typename R, int V, int MH>
 static int launch_low(qcm_handle h, int n_in, BlockPlan &bp) {
-    const int tb = low_tile_bits();
-    if (tb == 10) return launch_low_tb<R, V, MH, 10>(h, n_in, bp);
-    if constexpr (low_threads<R>() <= 128)
-        if (tb == 7) return launch_low_tb<R, V, MH, 7>(h, n_in, bp);
-    return launch_low_tb<R, V, MH, 8>(h, n_in, bp);
+    switch (low_shape()) {
+        case 808: return launch_low_tb<R, V, MH, 8, 8>(h, n_in, bp);
+        case 810: return launch_low_tb<R, V, MH, 10, 8>(h, n_in, bp);
+        case 407: return launch_low_tb<R, V, MH, 7, 4>(h, n_in, bp);
+        case 105: return launch_low_tb<R, V, MH, 5, 1>(h, n_in, bp);
+        default: return launch_low_tb<R, V, MH, 6, 2>(h, n_in, bp);
+    }
 }
 
 template <typename R, int V>

@@ -1304,13 +1304,16 @@ static __global__ void __launch_bounds__(kThreads) k_group_sum(const double *in,
 // TB: log2 of the inputs one CTA covers (its tile is 2^(TB + M) output amplitudes, contiguous).  a.tree_out
 // receives one partial sum per WARP (index blockIdx * warps + warp); k_group_sum folds them into the
 // sampler's level-0 sums.
-template <typename R, int V, int MH, int TB>
-__global__ void __launch_bounds__(low_threads<R>()) k_expand_low(const __grid_constant__ ExpandTreeArgs a, const void *__restrict__ in) {
+// NW: warps per CTA.  The size of the region a CTA writes decides how compact the window of concurrently written addresses
+// is (tools/membench4.cu, profiles/r02_notes.md: a bare sequential writer loses 5 % going from 32 KiB to 512 KiB per CTA),
+// so small CTAs -- few warps, one batch of 32 inputs each -- are the default shape.
+template <typename R, int V, int MH, int TB, int NW = low_threads<R>() / 32>
+__global__ void __launch_bounds__(NW * 32) k_expand_low(const __grid_constant__ ExpandTreeArgs a, const void *__restrict__ in) {
     constexpr int LB = V == 2 ? 6 : 5;                   // image bits covered by one warp store
     constexpr int J0 = V == 2 ? 1 : 0;                   // first lane-indexed member (member 0 is the vector slot for V == 2)
     constexpr int NS = 1 << MH;                          // warp stores per input
     constexpr int M = LB + MH;
-    constexpr int kWarps = low_threads<R>() / 32;
+    constexpr int kWarps = NW;
     using C2 = typename CplxOf<R>::T;
     using V16 = typename VecIO<R, V>::T;                  // float4 (two complex64) or double2 (one complex128)
     extern __shared__ __align__(16) unsigned char smem_raw[];
