@@ -402,15 +402,16 @@ int plan_block(qcm_handle h, const int *tq, int M, const qcm_op *members, int n_
 }
 
 int low_shape() {
-    // QCM_LOW_SHAPE = <warps per CTA>x<log2 inputs per CTA> of the rotated expansion pass: tuning knob.
-    // Default 2x6: membench4 shows that the smaller the region a CTA writes, the more compact the window of
-    // concurrently written addresses (q34 last pass: see profiles/r02_notes.md for the sweep).
+    // QCM_LOW_SHAPE = <warps per CTA>x<log2 inputs per CTA> of the rotated expansion pass: tuning knob.  Measured on the
+    // q34 last pass (profiles/r02_notes.md): 8x8 9.74 ms, 4x7 9.77, 1x5 9.87, 8x10 9.86, 2x6 10.02 -- a bare sequential
+    // writer gains 5 % when a CTA's region shrinks from 512 KiB to 32 KiB (tools/membench4.cu), but here the smaller
+    // CTAs pay more for their start-up (table staging, first input load) than the compacter write window returns.
     static int v = [] {
         const char *e = getenv("QCM_LOW_SHAPE");
-        int w = 2, tb = 6;
+        int w = 8, tb = 8;
         if (e && sscanf(e, "%dx%d", &w, &tb) == 2) {
             const bool ok = (w == 8 && (tb == 8 || tb == 10)) || (w == 4 && tb == 7) || (w == 2 && tb == 6) || (w == 1 && tb == 5);
-            if (!ok) { w = 2; tb = 6; }
+            if (!ok) { w = 8; tb = 8; }
         }
         return w * 100 + tb;
     }();
@@ -450,12 +451,14 @@ static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
 
 template <typename R, int V, int MH>
 static int launch_low(qcm_handle h, int n_in, BlockPlan &bp) {
-    switch (low_shape()) {
-        case 808: return launch_low_tb<R, V, MH, 8, 8>(h, n_in, bp);
+    // complex128 CTAs have always been 4 warps (twice the shared memory per warp)
+    const int shape = (sizeof(R) == 8 && low_shape() == 808) ? 407 : low_shape();
+    switch (shape) {
         case 810: return launch_low_tb<R, V, MH, 10, 8>(h, n_in, bp);
         case 407: return launch_low_tb<R, V, MH, 7, 4>(h, n_in, bp);
+        case 206: return launch_low_tb<R, V, MH, 6, 2>(h, n_in, bp);
         case 105: return launch_low_tb<R, V, MH, 5, 1>(h, n_in, bp);
-        default: return launch_low_tb<R, V, MH, 6, 2>(h, n_in, bp);
+        default: return launch_low_tb<R, V, MH, 8, 8>(h, n_in, bp);
     }
 }
 
