@@ -547,7 +547,10 @@ def main():
                                'ranks_identical': bool(same)},
                               **parity_check(cliques, th, p, delta, counts)),
                 'value_note': 'the device-timed arm re-executes one prepared circuit (same theta, seed and Philox stream) '
-                              'every step; e2e uses a fresh theta and seed per step'}
+                              'every step; e2e uses a fresh theta (and seed) per circuit.  At N > 1 both arms run the circuits '
+                              'as a pipeline (ShardedSimulator.execute_deferred / run(list)): programs and result handling are '
+                              'enqueued, every result is collected inside the timed region; the N = 1 arms execute one '
+                              'circuit at a time (blocking), which costs them about 1.5 % against a pipelined N = 1'}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_reference(cliques, steps=1, warmup=0)
         print(json.dumps(line), flush=True)
