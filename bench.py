@@ -64,52 +64,120 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock, power and throttle reasons of one GPU DURING the timed region: NVML polled in-process every few
+    milliseconds (a multi-GPU step is ~1.5 ms and `nvidia-smi -lms` needs a second to print its first line); the
+    nvidia-smi subprocess is the fallback when the NVML binding is missing."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_s=0.004):
         self.index = index
-        self.rows = []
+        self.period = period_s
+        self.rows = []                       # (sm MHz, max MHz, watts, reasons bitmask or None)
         self.proc = None
+        self.nv = None
+        self.stop_flag = threading.Event()
+        self.how = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates every GPU of the box; CUDA_VISIBLE_DEVICES may have renumbered them
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.index
+            handle = None
+            if vis:
+                ids = [v.strip() for v in vis.split(',') if v.strip()]
+                if idx < len(ids) and ids[idx].isdigit():
+                    idx = int(ids[idx])
+                elif idx < len(ids):
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(ids[idx].encode() if hasattr(pynvml, 'c_char_p') else ids[idx])
+            self.nv = (pynvml, handle if handle is not None else pynvml.nvmlDeviceGetHandleByIndex(idx))
+            self.how = 'nvml'
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = 'nvidia-smi -lms 100'
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
-
-    def stop(self):
-        if not self.proc:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
+    def _poll(self):
+        nv, h = self.nv
         try:
-            self.proc.wait(timeout=5)
+            smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
+            smax = None
+        reasons_fn = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons', None)
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    w = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                except Exception:
+                    w = None
+                try:
+                    rs = int(reasons_fn(h)) if reasons_fn else None
+                except Exception:
+                    rs = None
+                self.rows.append((sm, smax, w, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def _read(self):
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(',')]
             if len(r) < 9:
                 continue
             try:
-                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+                mask = 0
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        mask |= bits[nm]
+                self.rows.append((float(r[1]), float(r[2]), float(r[3]), mask))
             except ValueError:
                 continue
-            for nm, v in zip(names, r[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(nm)
+
+    def mark(self):
+        """Index of the next sample: bench.py brackets its timed regions with it."""
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
+        """Summary over samples [lo, hi) -- the timed regions -- falling back to every sample when that window is empty."""
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.how is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no NVML binding and no nvidia-smi']}
+        if self.nv:
+            self.th.join(timeout=1)
+        rows = self.rows[lo:hi] or self.rows
+        window = 'timed regions' if self.rows[lo:hi] else 'whole run (no sample fell inside the timed regions)'
+        # NVML clocks-event-reason bits (nvml.h): sw_power_cap 0x4, hw_slowdown 0x8, sw_thermal 0x20, hw_thermal 0x40
+        bits = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
+        reasons = sorted(nm for nm, b in bits.items() if any(r[3] is not None and (r[3] & b) for r in rows))
+        sm = [r[0] for r in rows]
+        smax = [r[1] for r in rows if r[1] is not None]
+        power = [r[2] for r in rows if r[2] is not None]
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
-                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': reasons,
+                'how': self.how, 'window': window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -441,20 +509,18 @@ def main():
     if rank == 0:
         clocks.start()
     barrier()
+    c_lo = clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
     pending = None
     for _ in range(args.steps):
-        if hasattr(sim, 'execute_deferred'):
-            # sharded: a stream of circuits -- circuit i's collective, read-back and key merge are finished while
-            # circuit i+1's gate program runs (every result is collected inside the timed region)
-            fin = sim.execute_deferred(prep, SHOTS, seed=1984, stream=0)
-            if pending is not None:
-                out = pending()
-            pending = fin
-        else:
-            out = sim.execute(prep, SHOTS, seed=1984, stream=0)
+        # a stream of circuits: circuit i's read-back (and, sharded, its collective and key merge) is finished while
+        # circuit i+1's gate program runs -- every result is collected inside the timed region
+        fin = sim.execute_deferred(prep, SHOTS, seed=1984, stream=0)
+        if pending is not None:
+            out = pending()
+        pending = fin
     if pending is not None:
         out = pending()
     ev1.record()
@@ -462,6 +528,16 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = ev0.elapsed_time(ev1)
     launches = sim.kernel_launches() - launches0
+    prof_source = 'last warm-up execution (blocking; CUDA events around every launch inside the library)'
+    if world == 1:
+        # the per-launch CUDA events of the LAST TIMED step (recorded inside the pipelined stream, read after the loop)
+        try:
+            pt = sim.op_profile()
+            if len(pt) == len(prof) and max(r[1] for r in pt) > 0:
+                prof = pt
+                prof_source = 'last timed step (CUDA events around every launch inside the library, read after the timed loop)'
+        except Exception:
+            pass
     ms = torch.tensor([max(dev_ms, 0.0), wall_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -469,38 +545,34 @@ def main():
     ms_per_step = dev_ms / args.steps
 
     # ---- end-to-end arm: the public call, host objects in, host results out ------------
-    e2e_ms = []
-    h2d = d2h = 0
-    if world > 1:
-        # the public call on a LIST of circuits, as the reference submits them (run_experiment.py:56: one run() for all
-        # circuits): fresh theta per circuit; the sharded backend pipelines the list (see ShardedSimulator.run)
-        ths = [thetas[args.warmup + i + 1] for i in range(args.steps)]
-        barrier()
-        t1 = time.perf_counter()
-        res = sim.run([QCMRF(cliques, t_) for t_ in ths], shots=SHOTS, seed=1984).result()
-        counts_all = res.get_counts()
-        pd = [res.postselected_probabilities(i) for i in range(args.steps)]
-        torch.cuda.synchronize()
-        e2e_ms = [(time.perf_counter() - t1) * 1e3 / args.steps]
-        th, counts, (p, delta) = ths[-1], counts_all[-1], pd[-1]
-        meta = res.metadata(args.steps - 1)
-        h2d, d2h = meta.get('h2d_bytes', 0), meta.get('d2h_bytes', 0)
-    for i in range(args.steps if world == 1 else 0):
-        th = thetas[args.warmup + i + 1]
-        barrier()
-        t1 = time.perf_counter()
-        res = sim.run(QCMRF(cliques, th), shots=SHOTS, seed=1984 + i).result()
-        counts = res.get_counts()
-        p, delta = res.postselected_probabilities(0)
-        torch.cuda.synchronize()
-        e2e_ms.append((time.perf_counter() - t1) * 1e3)
-        meta = res.metadata(0)
-        h2d, d2h = meta.get('h2d_bytes', 0), meta.get('d2h_bytes', 0)
-    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device='cuda')
+    # the public call on a LIST of circuits, as the reference submits them (run_experiment.py:56: one run() for all
+    # circuits): fresh theta per circuit, Philox stream = position in the list; the backend pipelines the list
+    # (B200Simulator.run / ShardedSimulator.run): circuit i+1 is prepared and enqueued while circuit i's counts dict
+    # is built.  Every circuit's tables go up and its keys + pmf come down inside the timed region.
+    ths = [thetas[args.warmup + i + 1] for i in range(args.steps)]
+    barrier()
+    t1 = time.perf_counter()
+    res = sim.run([QCMRF(cliques, t_) for t_ in ths], shots=SHOTS, seed=1984).result()
+    counts_all = res.get_counts()
+    pd = [res.postselected_probabilities(i) for i in range(args.steps)]
+    torch.cuda.synchronize()
+    e2e_ms = [(time.perf_counter() - t1) * 1e3 / args.steps]
+    th, counts, (p, delta) = ths[-1], counts_all[-1], pd[-1]
+    meta = res.metadata(args.steps - 1)
+    h2d, d2h = meta.get('h2d_bytes', 0), meta.get('d2h_bytes', 0)
+    # one more circuit through the blocking single-circuit call (what round 1 timed), for the line's e2e.single_ms
+    barrier()
+    t1 = time.perf_counter()
+    res1 = sim.run(QCMRF(cliques, thetas[0]), shots=SHOTS, seed=7).result()
+    res1.get_counts()
+    res1.postselected_probabilities(0)
+    single_ms = (time.perf_counter() - t1) * 1e3
+    c_hi = clocks.mark()
+    e2e_t = torch.tensor([float(np.mean(e2e_ms)), single_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms_mean = float(e2e_t.cpu())
-    clk = clocks.stop() if rank == 0 else None
+    e2e_ms_mean, single_ms = (float(x) for x in e2e_t.cpu())
+    clk = clocks.stop(c_lo, c_hi) if rank == 0 else None
     same = ranks_identical(dist if world > 1 else None, world, counts, p, delta)
     last_timing = sim.last_timing() if hasattr(sim, 'last_timing') else None
     breakdown = getattr(sim, 'breakdown_ms', None)
@@ -529,12 +601,13 @@ def main():
                 'clocks': clk,
                 'e2e': {'value': 1e3 / e2e_ms_mean, 'unit': 'circuits/s', 'h2d_bytes_per_step': int(h2d),
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_ms_mean,
-                        'what': ('one public run() call on the list of %d circuits (fresh theta each), pipelined by the sharded '
-                                 'backend; time / circuits' % args.steps) if world > 1 else
-                                'one public run() call per circuit (fresh theta and seed each)'},
+                        'what': 'one public run() call on the list of %d circuits (fresh theta each), pipelined by the backend; '
+                                'time / circuits' % args.steps,
+                        'single_circuit_call_ms': single_ms},
                 'gpu_launches': int(launches),
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': ncu_traffic(args.workload, world)[0], 'peak_source': peak_src,
+                             'launch_ms_source': prof_source,
                              'traffic_source': '%s (ncu --set full of this kernel, same workload, 1 GPU)' % ncu_traffic(args.workload, world)[1],
                              'kernel': '%s: reads %d B, writes %d B in %.3f ms' % (kname, rd, wr, top_ms)},
                 'program': {'passes': [{'kind': r[0], 'ms': r[1], 'read': r[2], 'written': r[3],
@@ -547,10 +620,10 @@ def main():
                                'ranks_identical': bool(same)},
                               **parity_check(cliques, th, p, delta, counts)),
                 'value_note': 'the device-timed arm re-executes one prepared circuit (same theta, seed and Philox stream) '
-                              'every step; e2e uses a fresh theta (and seed) per circuit.  At N > 1 both arms run the circuits '
-                              'as a pipeline (ShardedSimulator.execute_deferred / run(list)): programs and result handling are '
-                              'enqueued, every result is collected inside the timed region; the N = 1 arms execute one '
-                              'circuit at a time (blocking), which costs them about 1.5 % against a pipelined N = 1'}
+                              'every step; e2e uses a fresh theta per circuit.  Both arms, at every N, run the circuits as a '
+                              'pipeline (execute_deferred / run(list)): programs and result handling are enqueued, every '
+                              'result is collected inside the timed region; e2e.single_circuit_call_ms is one blocking '
+                              'run() on a single circuit'}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'], _ = cpu_reference(cliques, steps=1, warmup=0)
         print(json.dumps(line), flush=True)

@@ -297,6 +297,13 @@ int qcm_create_batched(qcm_handle *out, int device, int n_local, int precision, 
  * (qcm_host_alloc) and are valid after qcm_synchronize.  A sweep becomes ONE synchronisation instead of one per call,
  * and its result copies overlap the kernels that follow.                                                        */
 int qcm_set_deferred(qcm_handle h, int deferred);
+/* A stream of circuits in deferred mode is a pipeline: qcm_mark records a point in the handle's stream behind
+ * everything enqueued so far and returns its ticket; qcm_wait blocks the host until that point has been reached --
+ * circuit i's page-locked results are then valid while circuit i+1's program (enqueued after the mark) is still
+ * running.  Replaces, for a list of circuits, the blocking result() of the reference's job
+ * (run_experiment.py:56: one run() for all circuits).                                                            */
+int qcm_mark(qcm_handle h, uint64_t *ticket_out);
+int qcm_wait(qcm_handle h, uint64_t ticket);
 int qcm_host_alloc(void **host_out, size_t bytes);      /* page-locked host memory (cudaHostAlloc) */
 int qcm_host_free(void *host_ptr);
 int qcm_batch_size(qcm_handle h, int *batch_out);

@@ -44,7 +44,7 @@ SYMBOLS = ['qcm_abi_version', 'qcm_device_count', 'qcm_last_error', 'qcm_create'
            'qcm_postselect_resident', 'qcm_fetch_probs', 'qcm_sample_batched', 'qcm_sample_released_batched',
            'qcm_sample_sharded_devmass', 'qcm_mrf_exact', 'qcm_mrf_last_error', 'qcm_gather_flag_words',
            'qcm_run_gather_block_inplace', 'qcm_set_deferred', 'qcm_host_alloc', 'qcm_host_free',
-           'qcm_tree_total_device']
+           'qcm_tree_total_device', 'qcm_mark', 'qcm_wait']
 
 
 def lib():
@@ -97,6 +97,8 @@ def lib():
     L.qcm_fetch_probs.argtypes = [vp, i32, u64, u64, vp]
     L.qcm_sample_batched.argtypes = [vp, u64, u64, vp, vp, i32, vp]
     L.qcm_set_deferred.argtypes = [vp, i32]
+    L.qcm_mark.argtypes = [vp, ctypes.POINTER(u64)]
+    L.qcm_wait.argtypes = [vp, u64]
     L.qcm_tree_total_device.argtypes = [vp, vp]
     L.qcm_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
     L.qcm_host_free.argtypes = [vp]
@@ -205,9 +207,15 @@ class Handle:
             raise ValueError('batched handle: tables must have shape (batch, n_tables)')
         self._check(lib().qcm_run_program(self._h, _ptr(ops), len(ops), _ptr(tables), tables.size // self.batch))
 
-    def postselect(self, mask, value, n_out_bits, want_probs=True):
-        """(probs, kept); a batched handle returns arrays of shape (batch, 2^n_out_bits) and (batch,)."""
+    def postselect(self, mask, value, n_out_bits, want_probs=True, out=None):
+        """(probs, kept); a batched handle returns arrays of shape (batch, 2^n_out_bits) and (batch,).
+        out = (probs, kept) page-locked arrays (deferred mode: valid after synchronize() / wait()); returns them."""
         self.generation += 1
+        if out is not None:
+            probs, kept = out
+            self._check(lib().qcm_postselect(self._h, int(mask), int(value), int(n_out_bits), _ptr(probs) if want_probs else None,
+                                             kept.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+            return probs, kept
         if self.batch > 1:
             probs = np.empty((self.batch, 1 << n_out_bits), dtype=np.float64) if want_probs else None
             kept = np.empty(self.batch, dtype=np.float64)
@@ -266,8 +274,18 @@ class Handle:
                                                       _ptr(vclbit), _ptr(clbit_pos), int(n_clbits), _ptr(keys)))
         return keys
 
-    def sample(self, shots, seed, stream_id=0, clbit_qubit=None):
-        keys = np.empty(int(shots), dtype=np.uint64)
+    def mark(self):
+        """qcm_mark: ticket of a point in the handle's stream behind everything enqueued so far."""
+        t = ctypes.c_uint64()
+        self._check(lib().qcm_mark(self._h, ctypes.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        """qcm_wait: block until the marked point has been reached (later work keeps running)."""
+        self._check(lib().qcm_wait(self._h, int(ticket)))
+
+    def sample(self, shots, seed, stream_id=0, clbit_qubit=None, out=None):
+        keys = np.empty(int(shots), dtype=np.uint64) if out is None else out
         cq = None if clbit_qubit is None else np.ascontiguousarray(clbit_qubit, dtype=np.int32)
         self._check(lib().qcm_sample(self._h, int(shots), int(seed), int(stream_id), _ptr(cq),
                                      0 if cq is None else len(cq), _ptr(keys)))

@@ -227,6 +227,7 @@ class B200Simulator:
         self.small_fusion = small_fusion      # batched small circuits: fused programs are ~30x shorter to plan and ship
         self._handles = {}
         self._pinned = {}                      # page-locked result buffers of the last sweep shape
+        self._ring = None                      # page-locked result buffers of execute_deferred (three slots)
         self._launches_closed = 0
         self._last = None
         self._plan_cache = plancache.PlanCache() if plan_cache else None
@@ -338,6 +339,7 @@ class B200Simulator:
     def close(self):
         for k in list(self._handles):
             self._handles.pop(k).close()
+        self._ring = None
 
     def __del__(self):
         try:
@@ -400,6 +402,26 @@ class B200Simulator:
                     if sw is not None:
                         fast_sweeps.append((idxs, sw))
                         claimed.update(idxs)
+        # Large circuits that run alone are a pipeline: circuit k+1 is prepared and enqueued before circuit k's results
+        # are collected (execute_deferred), so the GPU runs the next gate program while the host builds the previous
+        # counts dict -- the reference submits its whole list in one run() too (run_experiment.py:56).
+        pend = [None]
+
+        def pipeline(item):
+            """item = (i, pr, prepare_ms) to enqueue, or None to drain."""
+            nxt = None
+            if item is not None and pend[0] is not None and pend[0][1].plan.n_phys != item[1].plan.n_phys:
+                pipeline(None)                                # another state size replaces the handle: finish what is pending
+            if item is not None:
+                i, pr, tp = item
+                te = time.perf_counter()
+                fin = self.execute_deferred(pr, shots, seed, sid(i), precision)
+                nxt = (i, pr, tp, fin, (time.perf_counter() - te) * 1e3)
+            if pend[0] is not None:
+                j = pend[0][0]
+                entries[j] = self._collect_large(circs[j], *pend[0][1:], sid(j))
+            pend[0] = nxt
+
         for i, c in enumerate(circs):
             if i in claimed:
                 continue
@@ -410,7 +432,12 @@ class B200Simulator:
             else:
                 tp = time.perf_counter()
                 pr = self.prepare(c, n_vars=n_vars)
-                large.append((i, pr, (time.perf_counter() - tp) * 1e3))
+                tp = (time.perf_counter() - tp) * 1e3
+                if self.sweep_batch and len(circs) > 1 and self._sweep_signature(pr, precision) is not None:
+                    large.append((i, pr, tp))                 # may join a sweep: decided once every circuit is prepared
+                else:
+                    pipeline((i, pr, tp))
+        pipeline(None)
         # circuits of one program structure (a theta / beta sweep) go through one batched handle
         groups = {}
         if self.sweep_batch and len(large) > 1:
@@ -419,12 +446,10 @@ class B200Simulator:
                 if sig is not None:
                     groups.setdefault(sig, []).append(k)
         swept = set(k for ks in groups.values() if len(ks) >= 2 for k in ks)
-        for k, (i, pr, tp) in enumerate(large):
-            if k in swept:
-                continue
-            entries[i] = self._run_large(circs[i], pr, shots, seed, sid(i), precision)
-            entries[i]['meta']['host_ms']['prepare (lower, fuse, plan)'] = tp
-            self.breakdown_ms = entries[i]['meta']['host_ms']
+        for k, item in enumerate(large):
+            if k not in swept:
+                pipeline(item)
+        pipeline(None)
         # sweeps last: their post-selected vectors may stay on the GPU, which only holds while the state handle lives
         for idxs, sw in fast_sweeps:
             for e in entries:
@@ -715,6 +740,61 @@ class B200Simulator:
             probs, kept = self._probs_from_handle(h, pr)
         return keys, probs, kept
 
+    def execute_deferred(self, pr, shots, seed=0, stream=0, precision=None):
+        """ENQUEUE one prepared circuit on the large-state path -- program, shots, post-selection, all into page-locked
+        result buffers (a ring of three) -- and return a zero-argument callable that waits for THIS circuit's results
+        (qcm_mark / qcm_wait) and returns what execute() returns.  Between the two calls the next circuit can be prepared
+        and enqueued: a list of circuits then runs back to back on the GPU while the host formats the previous result
+        (run() does exactly that).  Same kernels, same Philox streams, same results as execute().  Falls back to the
+        blocking execute() where the pipeline does not apply (release width, no shots, variables off the low qubits)."""
+        pl = pr.plan
+        precision = precision or self.precision
+        h = self._handle(pl.n_phys, precision)
+        n = pr.n_vars
+        if not (shots and not pr.virtual and pr.ps is not None and n is not None and n <= 30 and hasattr(h, 'mark')
+                and all(pl.layout[q] == q for q in range(n))):
+            out = self.execute(pr, shots, seed, stream, precision)
+            return lambda: out
+        self._last = h
+        key = (1 << n, int(shots))
+        ring = self._ring
+        if ring is None or ring['key'] != key:
+            if ring is not None:
+                for rec in ring['busy']:
+                    if rec is not None and not rec['done']:
+                        raise RuntimeError('deferred executions of another shape are still pending: finish them first')
+            ring = self._ring = {'key': key, 'slot': 0, 'busy': [None] * 3,
+                                 'bufs': [(_native.PinnedArray((int(shots),), np.uint64), _native.PinnedArray((1 << n,), np.float64),
+                                           _native.PinnedArray((1,), np.float64)) for _ in range(3)]}
+        slot = ring['slot']
+        ring['slot'] = (slot + 1) % 3
+        old = ring['busy'][slot]
+        if old is not None and not old['done']:
+            raise RuntimeError('deferred executions must be finished (call what execute_deferred returned) before three '
+                               'more are started')
+        kb, pb, mb = ring['bufs'][slot]
+        mask, value, _ = pr.ps
+        h.set_deferred(True)
+        try:
+            h.run_program(pl.ops, pl.tables)
+            h.sample(shots, seed, stream, pr.clbit_map if len(pr.clbit_map) else None, out=kb.array)
+            h.postselect(mask, value, n, out=(pb.array, mb.array))
+            ticket = h.mark()
+        finally:
+            h.set_deferred(False)
+        rec = {'done': False}
+        ring['busy'][slot] = rec
+
+        def finish():
+            if rec['done']:
+                raise RuntimeError('this deferred execution was already collected')
+            h.wait(ticket)
+            out = (kb.array.copy(), pb.array.copy(), float(mb.array[0]))
+            rec['done'] = True                            # the slot's page-locked buffers may be reused
+            return out
+        finish.deferred = True
+        return finish
+
     def _sample_released(self, h, pr, shots, seed, stream):
         """Shots of a circuit whose released qubits are not stored: basis states of the stored qubits
         come from the GPU sampler, each released qubit's outcome from its sweep's coefficients at that
@@ -802,15 +882,21 @@ class B200Simulator:
         """Kernel name per entry of op_profile() ('' where the engine does not record one)."""
         return self._last.op_kernels()
 
-    def _run_large(self, circ, pr, shots, seed, stream, precision):
+    def _collect_large(self, circ, pr, prepare_ms, finish, enqueue_ms, stream):
+        """Entry of one large-state circuit from its pending execution (see run())."""
         pl = pr.plan
         t0 = time.perf_counter()
-        keys, probs, kept = self.execute(pr, shots, seed, stream, precision)
+        keys, probs, kept = finish()
         t1 = time.perf_counter()
         h = self._last
+        shots = 0 if keys is None else len(keys)
         counts = _keys_to_counts(keys, pr.prog.n_clbits) if shots else None
         t2 = time.perf_counter()
         t = h.timing()
+        if getattr(finish, 'deferred', False):                # enqueued executions collect no per-phase device timings
+            t = dict(t, program_ms=None, sample_ms=None, postselect_ms=None)
+        self.breakdown_ms = {'prepare (lower, fuse, plan)': prepare_ms, 'execute or enqueue (program, shots, post-selection)': enqueue_ms,
+                             'wait for the results': (t1 - t0) * 1e3, 'counts dict': (t2 - t1) * 1e3}
         h2d = pl.ops.nbytes + pl.tables.nbytes + (pr.clbit_map.nbytes if shots else 0)
         d2h = (probs.nbytes + 8 if probs is not None else 0) + (keys.nbytes if keys is not None else 0)
         return {'circuit': circ, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
@@ -820,8 +906,7 @@ class B200Simulator:
                          'sample_ms': t['sample_ms'], 'postselect_ms': t['postselect_ms'],
                          'bytes_read': t['bytes_read'], 'bytes_written': t['bytes_written'],
                          'h2d_bytes': int(h2d), 'd2h_bytes': int(d2h), 'philox_stream': stream,
-                         'host_ms': {'execute (program, shots, post-selection; blocking)': (t1 - t0) * 1e3,
-                                     'counts dict': (t2 - t1) * 1e3}}}
+                         'host_ms': dict(self.breakdown_ms)}}
 
     def exact(self, circuit, n=None, precision=None):
         """Exact post-selected probability vector and success probability (no shots)."""

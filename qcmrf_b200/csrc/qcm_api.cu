@@ -83,6 +83,12 @@ struct qcm_sim_s {
     std::vector<float> op_ms;
     std::vector<std::string> op_kernel;    // kernel that ran each op of the last program
     std::string cur_kernel;                // set by the launchers, collected per op
+    bool op_ms_pending = false;            // the last program ran deferred: its per-op events have not been read yet
+    // qcm_mark / qcm_wait: a ring of events; ticket t lives in slot t % kMarks (a later ticket in the same slot
+    // implies t has completed: one stream)
+    static constexpr int kMarks = 16;
+    cudaEvent_t marks[kMarks] = {nullptr};
+    uint64_t n_marks = 0;
 };
 
 namespace {
@@ -418,23 +424,54 @@ int low_shape() {
     return v;
 }
 
-template <typename R, int V, int MH, int TB, int NW>
+// QCM_LOW_MODE = direct | persist[:<CTAs per SM>] | persist-direct[:<CTAs per SM>]  (see k_expand_low's MODE); the
+// persistent modes take their warps per CTA from QCM_LOW_SHAPE.  Returns mode | CTAs per SM << 8.
+int low_mode() {
+    static int v = [] {
+        const char *e = getenv("QCM_LOW_MODE");
+        if (!e || !*e) return 0;
+        int mode = 0, per_sm = 1;
+        const char *colon = strchr(e, ':');
+        const std::string name(e, colon ? (size_t)(colon - e) : strlen(e));
+        if (name == "direct") mode = kLowDirect;
+        else if (name == "persist") mode = kLowPersist;
+        else if (name == "persist-direct") mode = kLowPersist | kLowDirect;
+        if (colon) per_sm = std::max(1, std::min(32, atoi(colon + 1)));
+        return mode | (per_sm << 8);
+    }();
+    return v;
+}
+
+template <typename R, int V, int MH, int TB, int NW, int MODE>
 static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
-    auto kern = k_expand_low<R, V, MH, TB, NW>;
+    auto kern = k_expand_low<R, V, MH, TB, NW, MODE>;
     constexpr int warps = NW;
-    const size_t smem = low_warp_bytes<R, MH>() * warps + bp.tree_smem;
+    constexpr bool persist = (MODE & kLowPersist) != 0;
+    const size_t smem = low_warp_bytes<R, MH>() * warps + ((MODE & kLowDirect) ? 0 : bp.tree_smem);
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ExpandTreeArgs args = bp.trargs;
     double *level0 = args.tree_out;
-    if (level0) {                                          // per-warp partial sums, grouped into level 0 below
-        int rc = ensure(h, h->lowpart, (sizeof(double) * warps) << (n_in - TB));
+    // partial sums: one per warp of every tile, or (persistent) one per batch of 32 inputs
+    const uint64_t n_part = persist ? (1ull << (n_in - 5)) : ((uint64_t)warps << (n_in - TB));
+    if (level0) {                                          // grouped into level 0 below
+        int rc = ensure(h, h->lowpart, sizeof(double) * n_part);
         if (rc) return rc;
         args.tree_out = (double *)h->lowpart.p;
     }
-    kern<<<1u << (n_in - TB), NW * 32, smem, h->stream>>>(args, h->scratch.p);
+    unsigned grid = 1u << (n_in - TB);
+    if (persist) {
+        int rc = ensure(h, h->tilectr, sizeof(unsigned long long));
+        if (rc) return rc;
+        QCM_CUDA(h, cudaMemsetAsync(h->tilectr.p, 0, sizeof(unsigned long long), h->stream));
+        args.counter = (unsigned long long *)h->tilectr.p;
+        const uint64_t want = (uint64_t)h->num_sms * (uint64_t)(low_mode() >> 8);
+        grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, ((1ull << (n_in - 5)) + warps - 1) / warps));
+    }
+    kern<<<grid, NW * 32, smem, h->stream>>>(args, h->scratch.p);
     {
-        char nm[96];
-        snprintf(nm, sizeof nm, "k_expand_low<%s,%d,MH=%d,TB=%d,NW=%d>", sizeof(R) == 4 ? "float" : "double", V, MH, TB, NW);
+        char nm[112];
+        snprintf(nm, sizeof nm, "k_expand_low<%s,%d,MH=%d,TB=%d,NW=%d%s%s>", sizeof(R) == 4 ? "float" : "double", V, MH, TB, NW,
+                 (MODE & kLowDirect) ? ",direct" : "", persist ? ",persistent" : "");
         h->cur_kernel = nm;
     }
     QCM_CUDA(h, cudaGetLastError());
@@ -442,23 +479,34 @@ static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
         int wbits = 0;
         while ((1 << wbits) < warps) ++wbits;
         const uint64_t n_out = 1ull << (n_in - kChunkBits);
-        k_group_sum<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>((const double *)h->lowpart.p, kChunkBits - TB + wbits, n_out, level0);
+        const int gbits = persist ? kChunkBits - 5 : kChunkBits - TB + wbits;
+        k_group_sum<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>((const double *)h->lowpart.p, gbits, n_out, level0);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
     }
     return QCM_OK;
 }
 
-template <typename R, int V, int MH>
-static int launch_low(qcm_handle h, int n_in, BlockPlan &bp) {
+template <typename R, int V, int MH, int MODE>
+static int launch_low_shape(qcm_handle h, int n_in, BlockPlan &bp) {
     // complex128 CTAs have always been 4 warps (twice the shared memory per warp)
     const int shape = (sizeof(R) == 8 && low_shape() == 808) ? 407 : low_shape();
     switch (shape) {
-        case 810: return launch_low_tb<R, V, MH, 10, 8>(h, n_in, bp);
-        case 407: return launch_low_tb<R, V, MH, 7, 4>(h, n_in, bp);
-        case 206: return launch_low_tb<R, V, MH, 6, 2>(h, n_in, bp);
-        case 105: return launch_low_tb<R, V, MH, 5, 1>(h, n_in, bp);
-        default: return launch_low_tb<R, V, MH, 8, 8>(h, n_in, bp);
+        case 810: return launch_low_tb<R, V, MH, 10, 8, MODE>(h, n_in, bp);
+        case 407: return launch_low_tb<R, V, MH, 7, 4, MODE>(h, n_in, bp);
+        case 206: return launch_low_tb<R, V, MH, 6, 2, MODE>(h, n_in, bp);
+        case 105: return launch_low_tb<R, V, MH, 5, 1, MODE>(h, n_in, bp);
+        default: return launch_low_tb<R, V, MH, 8, 8, MODE>(h, n_in, bp);
+    }
+}
+
+template <typename R, int V, int MH>
+static int launch_low(qcm_handle h, int n_in, BlockPlan &bp) {
+    switch (low_mode() & 0xff) {
+        case kLowDirect: return launch_low_shape<R, V, MH, kLowDirect>(h, n_in, bp);
+        case kLowPersist: return launch_low_shape<R, V, MH, kLowPersist>(h, n_in, bp);
+        case kLowPersist | kLowDirect: return launch_low_shape<R, V, MH, kLowPersist | kLowDirect>(h, n_in, bp);
+        default: return launch_low_shape<R, V, MH, 0>(h, n_in, bp);
     }
 }
 
@@ -1261,6 +1309,7 @@ int qcm_destroy(qcm_handle h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->op_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->marks) if (e) cudaEventDestroy(e);
     delete h;
     return QCM_OK;
 }
@@ -1338,6 +1387,29 @@ int qcm_state_ptr(qcm_handle h, void **dev_ptr_out, uint64_t *bytes_out) {
 int qcm_set_deferred(qcm_handle h, int deferred) {
     if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
     h->deferred = deferred != 0;
+    return QCM_OK;
+}
+
+int qcm_mark(qcm_handle h, uint64_t *ticket_out) {
+    if (!h || !ticket_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
+    int rc = check_device(h);
+    if (rc) return rc;
+    const uint64_t t = h->n_marks;
+    cudaEvent_t &e = h->marks[t % qcm_sim_s::kMarks];
+    if (!e) QCM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    QCM_CUDA(h, cudaEventRecord(e, h->stream));
+    h->n_marks = t + 1;
+    *ticket_out = t;
+    return QCM_OK;
+}
+
+int qcm_wait(qcm_handle h, uint64_t ticket) {
+    if (!h) return fail(nullptr, QCM_ERR_INVALID, "handle is NULL");
+    if (ticket >= h->n_marks) return fail(h, QCM_ERR_INVALID, "ticket %llu was never issued", (unsigned long long)ticket);
+    int rc = check_device(h);
+    if (rc) return rc;
+    // the slot holds this ticket's event or a later one of the same stream: waiting for it is sufficient either way
+    QCM_CUDA(h, cudaEventSynchronize(h->marks[ticket % qcm_sim_s::kMarks]));
     return QCM_OK;
 }
 
@@ -1562,7 +1634,8 @@ int qcm_run_program(qcm_handle h, const qcm_op *ops, int n_ops, const double *ta
     h->timing.bytes_written *= (uint64_t)h->batch;
     QCM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     h->op_ms.assign(h->op_kind.size(), 0.f);
-    if (h->deferred) return QCM_OK;          // enqueued; timings are not collected in deferred mode
+    h->op_ms_pending = h->deferred;
+    if (h->deferred) return QCM_OK;          // enqueued; qcm_get_op_profile collects the per-op timings on demand
     QCM_CUDA(h, cudaEventSynchronize(h->ev1));
     float ms = 0.f;
     QCM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -1698,6 +1771,14 @@ int qcm_get_op_profile(qcm_handle h, int cap, int32_t *kind_out, float *ms_out, 
     if (!h || !n_out) return fail(h, QCM_ERR_INVALID, "NULL argument");
     const int n = (int)h->op_ms.size();
     *n_out = n;
+    if (h->op_ms_pending && cap > 0 && (size_t)n < h->op_ev.size()) {
+        // the last program was only enqueued (deferred mode): wait for its last op and read the events now
+        int rc = check_device(h);
+        if (rc) return rc;
+        QCM_CUDA(h, cudaEventSynchronize(h->op_ev[n]));
+        for (int k = 0; k < n; ++k) QCM_CUDA(h, cudaEventElapsedTime(&h->op_ms[k], h->op_ev[k], h->op_ev[k + 1]));
+        h->op_ms_pending = false;
+    }
     for (int k = 0; k < n && k < cap; ++k) {
         if (kind_out) kind_out[k] = h->op_kind[k];
         if (ms_out) ms_out[k] = h->op_ms[k];
@@ -2008,6 +2089,14 @@ int qcm_sample(qcm_handle h, uint64_t shots, uint64_t seed, uint64_t stream_id, 
     double mass = 0.0;
     int rc = qcm_sample_prepare(h, &mass);
     if (rc) return rc;
+    if (h->deferred && h->batch == 1 && !product_state(h)) {
+        // deferred mode: the tree's total was not read back; it is summed on the device (same index order as the host
+        // sum of the blocking mode, so the shots are identical) and the sampler reads it there
+        if ((rc = ensure(h, h->totals, sizeof(double)))) return rc;
+        if ((rc = qcm_tree_total_device(h, h->totals.p))) return rc;
+        return sample_sharded_impl(h, shots, seed, stream_id, nullptr, 1, clbit_qubit, n_clbits, keys_out, nullptr, false, nullptr,
+                                   (const double *)h->totals.p, 1);
+    }
     return qcm_sample_sharded(h, shots, seed, stream_id, &mass, 1, clbit_qubit, n_clbits, keys_out, nullptr);
 }
 

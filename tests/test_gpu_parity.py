@@ -1150,3 +1150,94 @@ def test_exact_mrf_inference_on_the_gpu(n):
     px.weights(b)[:] = th
     assert abs(px.infer(b, task='partition') - lz) < 1e-12
     assert abs(px.logpot(b, 1) - ex.logpot(1)) < 1e-15
+
+
+# ------------------------------------------------------------------------------------------
+def test_pipelined_list_equals_blocking_single_calls(models):
+    """run(list) on the large-state path is a pipeline (execute_deferred: program, shots and post-selection enqueued
+    into page-locked ring buffers, circuit i collected while circuit i+1 runs; the tree total is summed on the
+    device).  Counts, pmf and delta must be IDENTICAL to one blocking run() per circuit with the same Philox
+    stream -- also across a change of state size in the middle of the list and over more circuits than ring slots."""
+    from qcmrf_b200 import workloads
+    items = []
+    for j, t in ((1, 0), (1, 1), (1, 2), (3, 0), (3, 1), (1, 3), (5, 0), (5, 1), (5, 2), (5, 3)):
+        items.append((models['0.5']['GRAPHS'][j], models['0.5']['THETAS'][str(j)][t]))
+    C = workloads.random_tree(11, 0, seed=3)                    # ends in k_expand_low (rotated storage)
+    items += [(C, workloads.theta_for(C, seed=s)) for s in (4, 5, 6, 7)]
+    for precision in ('double', 'single'):
+        sim = B200Simulator(precision=precision, small_batch=False, sweep_batch=False, seed=77)
+        res = sim.run([QCMRF(c, th) for c, th in items], shots=5000).result()
+        assert all(res.metadata(i)['path'] == 'statevector' for i in range(len(items)))
+        one = B200Simulator(precision=precision, small_batch=False, sweep_batch=False, seed=77)
+        for i, (c, th) in enumerate(items):
+            r1 = one.run(QCMRF(c, th), shots=5000, stream_ids=[i]).result()
+            assert r1.get_counts() == res.get_counts(i), (precision, i)
+            p1, d1 = r1.postselected_probabilities(0)
+            p, d = res.postselected_probabilities(i)
+            assert np.array_equal(p, p1) and d == d1, (precision, i)
+            pb, db, _ = mrf.brute_force_pmf(c, th)
+            assert_pmf(p, pb, d, db, precision, (precision, i))
+        # the callable returned by execute_deferred is single-use, and a fourth pending execution is refused
+        pr = sim.prepare(QCMRF(*items[0]))
+        fins = [sim.execute_deferred(pr, 100, seed=1, stream=s) for s in range(3)]
+        with pytest.raises(RuntimeError):
+            sim.execute_deferred(pr, 100, seed=1, stream=3)
+        outs = [f() for f in fins]
+        with pytest.raises(RuntimeError):
+            fins[0]()
+        k0, p0, m0 = sim.execute(pr, 100, seed=1, stream=0)
+        assert np.array_equal(outs[0][0], k0) and np.array_equal(outs[0][1], p0) and outs[0][2] == m0
+        assert not np.array_equal(outs[0][0], outs[1][0])
+        sim.close(); one.close()
+
+
+_LOW_MODE_CHILD = r'''
+import sys, numpy as np
+sys.path.insert(0, %(tests)r); sys.path.insert(0, %(root)r)
+import test_gpu_parity as T
+from qcmrf_b200 import _native, fusion
+out = {}
+for precision in ('double', 'single'):
+    rng = np.random.RandomState(5)
+    for n0, Ms in ((10, [8]), (11, [6]), (10, [2, 7]), (13, [8]), (16, [5])):
+        for with_diag in (False, True):
+            ops, tabs, act = T._expansion_program(rng, n0, Ms, with_diag, False)
+            fusion._flag_last_pass(ops)
+            ops['flags'][ops['flags'] != 0] = 3
+            with _native.Handle(act, precision) as h:
+                h.run_program(ops, tabs)
+                key = '%%s_%%d_%%s_%%d' %% (precision, n0, '-'.join(map(str, Ms)), with_diag)
+                out['amp_' + key] = h.get_amplitudes()
+                out['keys_' + key] = h.sample(20000, seed=3, stream_id=1)
+                out['kern_' + key] = np.array([h.op_kernels()[-1]])
+np.savez(sys.argv[1], **out)
+'''
+
+
+@pytest.mark.parametrize('mode', ['direct', 'persist:4', 'persist-direct:8'])
+def test_expand_low_launch_modes_are_bit_identical(mode, tmp_path):
+    """QCM_LOW_MODE picks how k_expand_low's work is handed out (member tables read in place instead of staged;
+    resident warps drawing batches from a ticket counter).  The amplitudes must be bit-identical to the default
+    launch, the shots (drawn through partial sums grouped differently) statistically identical."""
+    import subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = _LOW_MODE_CHILD % {'tests': here, 'root': os.path.dirname(here)}
+    got = {}
+    for m in ('', mode):
+        f = str(tmp_path / ('m_%s.npz' % (m.replace(':', '_') or 'default')))
+        env = dict(os.environ, QCM_LOW_MODE=m)
+        r = subprocess.run([sys.executable, '-c', src, f], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got[m] = np.load(f)
+    a, b = got[''], got[mode]
+    n_low = 0
+    for k in a.files:
+        if k.startswith('amp_'):
+            assert np.array_equal(a[k], b[k]), (mode, k)
+        elif k.startswith('kern_'):
+            if str(a[k][0]).startswith('k_expand_low'):
+                n_low += 1
+                assert ('persistent' in str(b[k][0])) == ('persist' in mode) and ('direct' in str(b[k][0])) == ('direct' in mode), (a[k], b[k])
+        else:
+            assert (a[k] == b[k]).mean() > 0.999, (mode, k, (a[k] == b[k]).mean())
+    assert n_low >= 10
