@@ -165,6 +165,7 @@ class Handle:
         self._h = ctypes.c_void_p()
         self.batch = int(batch)
         self.generation = 0                      # bumped by every post-selection: lazily fetched pmfs check it
+        self.deferred = False                    # set_deferred: calls only enqueue
         self.n_local = int(n_local)
         self.prec = QCM_C64 if precision in ('single', 'c64', 32) else QCM_C128
         self.cdtype = np.complex64 if self.prec == QCM_C64 else np.complex128
@@ -250,6 +251,7 @@ class Handle:
     def set_deferred(self, flag):
         """Deferred mode: calls enqueue and return; pass page-locked output arrays (pinned_empty) and call synchronize()."""
         self._check(lib().qcm_set_deferred(self._h, 1 if flag else 0))
+        self.deferred = bool(flag)
 
     def batch_select(self, point):
         self._check(lib().qcm_batch_select(self._h, int(point)))

@@ -424,54 +424,23 @@ int low_shape() {
     return v;
 }
 
-// QCM_LOW_MODE = direct | persist[:<CTAs per SM>] | persist-direct[:<CTAs per SM>]  (see k_expand_low's MODE); the
-// persistent modes take their warps per CTA from QCM_LOW_SHAPE.  Returns mode | CTAs per SM << 8.
-int low_mode() {
-    static int v = [] {
-        const char *e = getenv("QCM_LOW_MODE");
-        if (!e || !*e) return 0;
-        int mode = 0, per_sm = 1;
-        const char *colon = strchr(e, ':');
-        const std::string name(e, colon ? (size_t)(colon - e) : strlen(e));
-        if (name == "direct") mode = kLowDirect;
-        else if (name == "persist") mode = kLowPersist;
-        else if (name == "persist-direct") mode = kLowPersist | kLowDirect;
-        if (colon) per_sm = std::max(1, std::min(32, atoi(colon + 1)));
-        return mode | (per_sm << 8);
-    }();
-    return v;
-}
-
-template <typename R, int V, int MH, int TB, int NW, int MODE>
+template <typename R, int V, int MH, int TB, int NW>
 static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
-    auto kern = k_expand_low<R, V, MH, TB, NW, MODE>;
+    auto kern = k_expand_low<R, V, MH, TB, NW>;
     constexpr int warps = NW;
-    constexpr bool persist = (MODE & kLowPersist) != 0;
-    const size_t smem = low_warp_bytes<R, MH>() * warps + ((MODE & kLowDirect) ? 0 : bp.tree_smem);
+    const size_t smem = low_warp_bytes<R, MH>() * warps + bp.tree_smem;
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ExpandTreeArgs args = bp.trargs;
     double *level0 = args.tree_out;
-    // partial sums: one per warp of every tile, or (persistent) one per batch of 32 inputs
-    const uint64_t n_part = persist ? (1ull << (n_in - 5)) : ((uint64_t)warps << (n_in - TB));
-    if (level0) {                                          // grouped into level 0 below
-        int rc = ensure(h, h->lowpart, sizeof(double) * n_part);
+    if (level0) {                                          // per-warp partial sums, grouped into level 0 below
+        int rc = ensure(h, h->lowpart, (sizeof(double) * warps) << (n_in - TB));
         if (rc) return rc;
         args.tree_out = (double *)h->lowpart.p;
     }
-    unsigned grid = 1u << (n_in - TB);
-    if (persist) {
-        int rc = ensure(h, h->tilectr, sizeof(unsigned long long));
-        if (rc) return rc;
-        QCM_CUDA(h, cudaMemsetAsync(h->tilectr.p, 0, sizeof(unsigned long long), h->stream));
-        args.counter = (unsigned long long *)h->tilectr.p;
-        const uint64_t want = (uint64_t)h->num_sms * (uint64_t)(low_mode() >> 8);
-        grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(want, ((1ull << (n_in - 5)) + warps - 1) / warps));
-    }
-    kern<<<grid, NW * 32, smem, h->stream>>>(args, h->scratch.p);
+    kern<<<1u << (n_in - TB), NW * 32, smem, h->stream>>>(args, h->scratch.p);
     {
-        char nm[112];
-        snprintf(nm, sizeof nm, "k_expand_low<%s,%d,MH=%d,TB=%d,NW=%d%s%s>", sizeof(R) == 4 ? "float" : "double", V, MH, TB, NW,
-                 (MODE & kLowDirect) ? ",direct" : "", persist ? ",persistent" : "");
+        char nm[96];
+        snprintf(nm, sizeof nm, "k_expand_low<%s,%d,MH=%d,TB=%d,NW=%d>", sizeof(R) == 4 ? "float" : "double", V, MH, TB, NW);
         h->cur_kernel = nm;
     }
     QCM_CUDA(h, cudaGetLastError());
@@ -479,34 +448,23 @@ static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
         int wbits = 0;
         while ((1 << wbits) < warps) ++wbits;
         const uint64_t n_out = 1ull << (n_in - kChunkBits);
-        const int gbits = persist ? kChunkBits - 5 : kChunkBits - TB + wbits;
-        k_group_sum<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>((const double *)h->lowpart.p, gbits, n_out, level0);
+        k_group_sum<<<(unsigned)((n_out + kThreads - 1) / kThreads), kThreads, 0, h->stream>>>((const double *)h->lowpart.p, kChunkBits - TB + wbits, n_out, level0);
         QCM_CUDA(h, cudaGetLastError());
         h->timing.kernel_launches++;
     }
     return QCM_OK;
 }
 
-template <typename R, int V, int MH, int MODE>
-static int launch_low_shape(qcm_handle h, int n_in, BlockPlan &bp) {
+template <typename R, int V, int MH>
+static int launch_low(qcm_handle h, int n_in, BlockPlan &bp) {
     // complex128 CTAs have always been 4 warps (twice the shared memory per warp)
     const int shape = (sizeof(R) == 8 && low_shape() == 808) ? 407 : low_shape();
     switch (shape) {
-        case 810: return launch_low_tb<R, V, MH, 10, 8, MODE>(h, n_in, bp);
-        case 407: return launch_low_tb<R, V, MH, 7, 4, MODE>(h, n_in, bp);
-        case 206: return launch_low_tb<R, V, MH, 6, 2, MODE>(h, n_in, bp);
-        case 105: return launch_low_tb<R, V, MH, 5, 1, MODE>(h, n_in, bp);
-        default: return launch_low_tb<R, V, MH, 8, 8, MODE>(h, n_in, bp);
-    }
-}
-
-template <typename R, int V, int MH>
-static int launch_low(qcm_handle h, int n_in, BlockPlan &bp) {
-    switch (low_mode() & 0xff) {
-        case kLowDirect: return launch_low_shape<R, V, MH, kLowDirect>(h, n_in, bp);
-        case kLowPersist: return launch_low_shape<R, V, MH, kLowPersist>(h, n_in, bp);
-        case kLowPersist | kLowDirect: return launch_low_shape<R, V, MH, kLowPersist | kLowDirect>(h, n_in, bp);
-        default: return launch_low_shape<R, V, MH, 0>(h, n_in, bp);
+        case 810: return launch_low_tb<R, V, MH, 10, 8>(h, n_in, bp);
+        case 407: return launch_low_tb<R, V, MH, 7, 4>(h, n_in, bp);
+        case 206: return launch_low_tb<R, V, MH, 6, 2>(h, n_in, bp);
+        case 105: return launch_low_tb<R, V, MH, 5, 1>(h, n_in, bp);
+        default: return launch_low_tb<R, V, MH, 8, 8>(h, n_in, bp);
     }
 }
 

@@ -1110,7 +1110,6 @@ struct ExpandTreeArgs {
     double *tree_out;               // see ExpandArgs
     double *sub_out;                // per-vector |in|^2 sums (the sampler's finest level)
     uint64_t bstate, btab;          // batch strides in bytes (k_expand_tree; the rotated pass is never batched)
-    unsigned long long *counter;    // k_expand_low, persistent mode: the ticket counter (zeroed before the launch)
     TreeMember mem[QCM_MAX_EXPAND]; // member j targets qubit n_in + j
     TreeMember diag[4];
 };
@@ -1308,22 +1307,13 @@ static __global__ void __launch_bounds__(kThreads) k_group_sum(const double *in,
 // NW: warps per CTA.  The size of the region a CTA writes decides how compact the window of concurrently written addresses
 // is (tools/membench4.cu, profiles/r02_notes.md: a bare sequential writer loses 5 % going from 32 KiB to 512 KiB per CTA),
 // so small CTAs -- few warps, one batch of 32 inputs each -- are the default shape.
-// MODE bit 0 (kLowDirect): the member / diagonal factors are read straight from the program's tables in global memory
-// (L1-resident: a few hundred bytes) instead of being staged into shared memory first -- no staging loop and no block
-// barrier, so a CTA's start-up is one input load; this is what makes one- and two-warp CTAs cheap.
-// MODE bit 1 (kLowPersist): resident CTAs, every WARP draws batches of 32 consecutive inputs from a global ticket
-// counter (a.counter) -- batches are handed out in address order like the hardware hands out CTAs, but nothing is
-// re-started between them; the ticket and the input of the next batch are fetched before the current one is emitted.
-// a.tree_out then receives one partial sum per batch (index = ticket).
-constexpr int kLowDirect = 1, kLowPersist = 2;
-template <typename R, int V, int MH, int TB, int NW = low_threads<R>() / 32, int MODE = 0>
+template <typename R, int V, int MH, int TB, int NW = low_threads<R>() / 32>
 __global__ void __launch_bounds__(NW * 32) k_expand_low(const __grid_constant__ ExpandTreeArgs a, const void *__restrict__ in) {
     constexpr int LB = V == 2 ? 6 : 5;                   // image bits covered by one warp store
     constexpr int J0 = V == 2 ? 1 : 0;                   // first lane-indexed member (member 0 is the vector slot for V == 2)
     constexpr int NS = 1 << MH;                          // warp stores per input
     constexpr int M = LB + MH;
     constexpr int kWarps = NW;
-    constexpr bool DIRECT = (MODE & kLowDirect) != 0, PERSIST = (MODE & kLowPersist) != 0;
     using C2 = typename CplxOf<R>::T;
     using V16 = typename VecIO<R, V>::T;                  // float4 (two complex64) or double2 (one complex128)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1332,7 +1322,7 @@ __global__ void __launch_bounds__(NW * 32) k_expand_low(const __grid_constant__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t tile = blockIdx.x;                                   // grid = 2^(n_in - TB), launch = address order
     constexpr int kPerWarp = (1 << TB) / kWarps;                        // inputs per warp per tile
-    static_assert(PERSIST || (kPerWarp >= 32 && kPerWarp % 32 == 0), "a warp takes whole batches of 32 inputs");
+    static_assert(kPerWarp >= 32 && kPerWarp % 32 == 0, "a warp takes whole batches of 32 inputs");
     // The warps of a CTA interleave at a granularity of two inputs (a pair shares the sampler's finest
     // sum): at step i of phase B the warps write runs 2 * 2^M amplitudes apart, so the CTA's stores
     // stay inside one moving window instead of one stream per warp (DRAM row locality).
@@ -1341,23 +1331,20 @@ __global__ void __launch_bounds__(NW * 32) k_expand_low(const __grid_constant__ 
         return reinterpret_cast<const C2 *>(in)[x0 + (uint64_t)(lane >> 1) * pstride + (lane & 1)];
     };
     // the first input amplitude is requested before anything else (its DRAM latency then overlaps the table staging)
-    C2 next_in = C2{};
-    if constexpr (!PERSIST) next_in = in_at(x_first(0), 2 * kWarps);
-    if constexpr (!DIRECT) {
-        for (int j = 0; j < M; ++j) {                     // column 0 of every 2x2: (m00, m10)
-            const int n = 1 << a.mem[j].n_ctrl;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const R *src = gt + a.mem[j].src_off + 8 * i;
-                R *dst = tab + a.mem[j].tab_off + 4 * i;
-                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[4]; dst[3] = src[5];
-            }
+    C2 next_in = in_at(x_first(0), 2 * kWarps);
+    for (int j = 0; j < M; ++j) {                         // column 0 of every 2x2: (m00, m10)
+        const int n = 1 << a.mem[j].n_ctrl;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const R *src = gt + a.mem[j].src_off + 8 * i;
+            R *dst = tab + a.mem[j].tab_off + 4 * i;
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[4]; dst[3] = src[5];
         }
-        for (int d = 0; d < a.n_diag; ++d) {
-            const int n = 2 << a.diag[d].n_ctrl;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) tab[a.diag[d].tab_off + i] = gt[a.diag[d].src_off + i];
-        }
-        __syncthreads();                                  // the only block-level barrier: member tables staged
     }
+    for (int d = 0; d < a.n_diag; ++d) {
+        const int n = 2 << a.diag[d].n_ctrl;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tab[a.diag[d].tab_off + i] = gt[a.diag[d].src_off + i];
+    }
+    __syncthreads();                                      // the only block-level barrier: member tables staged
     unsigned char *wbase = smem_raw + low_warp_bytes<R, MH>() * warp;
     V16 *Us = reinterpret_cast<V16 *>(wbase);                                      // [NS][32]
     C2 *As = reinterpret_cast<C2 *>(wbase + (size_t)NS * 32 * 16);                 // [4][kLowRow]: a lane reads row lane & 3
@@ -1392,24 +1379,15 @@ __global__ void __launch_bounds__(NW * 32) k_expand_low(const __grid_constant__ 
 #pragma unroll 1
             for (int d = 0; d < a.n_diag; ++d) {
                 const uint32_t idx = index_of(a.diag[d], gi);
-                if constexpr (DIRECT) cmul(pr, pi, __ldg(gt + a.diag[d].src_off + 2 * idx), __ldg(gt + a.diag[d].src_off + 2 * idx + 1), pr, pi);
-                else cmul(pr, pi, tab[a.diag[d].tab_off + 2 * idx], tab[a.diag[d].tab_off + 2 * idx + 1], pr, pi);
+                cmul(pr, pi, tab[a.diag[d].tab_off + 2 * idx], tab[a.diag[d].tab_off + 2 * idx + 1], pr, pi);
             }
             __syncwarp();                                 // the previous batch's phase B is done with the tables
             uint32_t off[M];                              // table offset (reals) of member j at this input's index
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
-                if constexpr (DIRECT) off[j] = (uint32_t)a.mem[j].src_off + 8u * index_of(a.mem[j], gi);
-                else off[j] = (uint32_t)a.mem[j].tab_off + 4u * index_of(a.mem[j], gi);
-            }
+            for (int j = 0; j < M; ++j) off[j] = (uint32_t)a.mem[j].tab_off + 4u * index_of(a.mem[j], gi);
             auto fac = [&](int member, int bit, R &fr, R &fi) {          // f_member[bit] at this input's table index
-                if constexpr (DIRECT) {                   // program table entry: m00 m01 m10 m11 (complex); column 0 = reals 0,1 / 4,5
-                    const C2 f = __ldg(reinterpret_cast<const C2 *>(gt + off[member] + 4 * bit));
-                    fr = f.x; fi = f.y;
-                } else {
-                    const C2 f = *reinterpret_cast<const C2 *>(tab + off[member] + 2 * bit);
-                    fr = f.x; fi = f.y;
-                }
+                const C2 f = *reinterpret_cast<const C2 *>(tab + off[member] + 2 * bit);
+                fr = f.x; fi = f.y;
             };
             // U[s][v] = in * diag * f_0[v] * prod_{l < MH} f_{LB+l}[s_l]
             R qr[V], qi[V];
@@ -1483,29 +1461,7 @@ __global__ void __launch_bounds__(NW * 32) k_expand_low(const __grid_constant__ 
         }
     };
 
-    if constexpr (PERSIST) {
-        const uint64_t n_batches = 1ull << (a.n_in - 5);
-        auto ticket = [&]() -> uint64_t {
-            unsigned long long t = 0;
-            if (lane == 0) t = atomicAdd(a.counter, 1ull);
-            return __shfl_sync(0xffffffffu, t, 0);
-        };
-        uint64_t cur = ticket();
-        C2 cur_in = cur < n_batches ? in_at(cur << 5, 2) : C2{};
-        while (cur < n_batches) {
-            // next ticket and its input first: the load is in flight while this batch is emitted
-            const uint64_t nxt = ticket();
-            const C2 nxt_in = nxt < n_batches ? in_at(nxt << 5, 2) : C2{};
-            double wacc = 0.0;
-            do_batch(cur << 5, 2, cur_in, wacc);
-            if (a.tree_out) {
-                wacc = warp_sum(wacc);
-                if (lane == 0) a.tree_out[cur] = wacc;
-            }
-            cur = nxt;
-            cur_in = nxt_in;
-        }
-    } else {
+    {
         double wacc = 0.0;
 #pragma unroll 1
         for (int batch = 0; batch < kPerWarp / 32; ++batch) {

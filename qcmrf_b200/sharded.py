@@ -634,7 +634,8 @@ class ShardedSimulator:
                     ops['flags'] &= ~fusion.QCM_FLAG_SAMPLE_CHECKPOINT     # no shots follow: skip the sampler's checkpoint tree
                 h.set_shard(sp.g, sp.rank & mask)
                 h.run_program(ops, tabs)
-                self._profile.extend(h.op_profile())
+                if not getattr(h, 'deferred', False):       # reading an enqueued program's per-launch events would wait for it
+                    self._profile.extend(h.op_profile())
             elif seg[0] == 'xblock' and self._peer_bufs is not None:
                 _, betas, ops, tabs, mask = seg
                 ms = self._gather_block(h, sp, betas, ops, tabs, mask)

@@ -1189,55 +1189,3 @@ def test_pipelined_list_equals_blocking_single_calls(models):
         assert np.array_equal(outs[0][0], k0) and np.array_equal(outs[0][1], p0) and outs[0][2] == m0
         assert not np.array_equal(outs[0][0], outs[1][0])
         sim.close(); one.close()
-
-
-_LOW_MODE_CHILD = r'''
-import sys, numpy as np
-sys.path.insert(0, %(tests)r); sys.path.insert(0, %(root)r)
-import test_gpu_parity as T
-from qcmrf_b200 import _native, fusion
-out = {}
-for precision in ('double', 'single'):
-    rng = np.random.RandomState(5)
-    for n0, Ms in ((10, [8]), (11, [6]), (10, [2, 7]), (13, [8]), (16, [5])):
-        for with_diag in (False, True):
-            ops, tabs, act = T._expansion_program(rng, n0, Ms, with_diag, False)
-            fusion._flag_last_pass(ops)
-            ops['flags'][ops['flags'] != 0] = 3
-            with _native.Handle(act, precision) as h:
-                h.run_program(ops, tabs)
-                key = '%%s_%%d_%%s_%%d' %% (precision, n0, '-'.join(map(str, Ms)), with_diag)
-                out['amp_' + key] = h.get_amplitudes()
-                out['keys_' + key] = h.sample(20000, seed=3, stream_id=1)
-                out['kern_' + key] = np.array([h.op_kernels()[-1]])
-np.savez(sys.argv[1], **out)
-'''
-
-
-@pytest.mark.parametrize('mode', ['direct', 'persist:4', 'persist-direct:8'])
-def test_expand_low_launch_modes_are_bit_identical(mode, tmp_path):
-    """QCM_LOW_MODE picks how k_expand_low's work is handed out (member tables read in place instead of staged;
-    resident warps drawing batches from a ticket counter).  The amplitudes must be bit-identical to the default
-    launch, the shots (drawn through partial sums grouped differently) statistically identical."""
-    import subprocess, sys
-    here = os.path.dirname(os.path.abspath(__file__))
-    src = _LOW_MODE_CHILD % {'tests': here, 'root': os.path.dirname(here)}
-    got = {}
-    for m in ('', mode):
-        f = str(tmp_path / ('m_%s.npz' % (m.replace(':', '_') or 'default')))
-        env = dict(os.environ, QCM_LOW_MODE=m)
-        r = subprocess.run([sys.executable, '-c', src, f], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        got[m] = np.load(f)
-    a, b = got[''], got[mode]
-    n_low = 0
-    for k in a.files:
-        if k.startswith('amp_'):
-            assert np.array_equal(a[k], b[k]), (mode, k)
-        elif k.startswith('kern_'):
-            if str(a[k][0]).startswith('k_expand_low'):
-                n_low += 1
-                assert ('persistent' in str(b[k][0])) == ('persist' in mode) and ('direct' in str(b[k][0])) == ('direct' in mode), (a[k], b[k])
-        else:
-            assert (a[k] == b[k]).mean() > 0.999, (mode, k, (a[k] == b[k]).mean())
-    assert n_low >= 10
