@@ -424,11 +424,33 @@ int low_shape() {
     return v;
 }
 
+// QCM_LOW_CTAS = resident CTAs per SM of the rotated expansion pass (0 = whatever fits).  A write-only stream is FASTER
+// with fewer resident warps (tools/membench5.cu: a bare sequential writer 7.29 TB/s at 64 warps per SM, 7.42 at 32, 7.57
+// at 8), the kernel needs enough of them to cover its store-free phase A: the launcher pads the dynamic shared memory
+// so that only this many CTAs fit.
+int low_ctas() {
+    static int v = [] {
+        const char *e = getenv("QCM_LOW_CTAS");
+        return e ? std::max(0, std::min(32, atoi(e))) : -1;
+    }();
+    return v;
+}
+
 template <typename R, int V, int MH, int TB, int NW>
 static int launch_low_tb(qcm_handle h, int n_in, BlockPlan &bp) {
     auto kern = k_expand_low<R, V, MH, TB, NW>;
     constexpr int warps = NW;
-    const size_t smem = low_warp_bytes<R, MH>() * warps + bp.tree_smem;
+    size_t smem = low_warp_bytes<R, MH>() * warps + bp.tree_smem;
+    {
+        // default: 24 resident warps per SM for complex64 (q34 last pass, profiles/r02_low_ctas_sweep.txt: 8x8 at 5 / 4 / 3 /
+        // 2 CTAs per SM 9.72 / 9.67 / 9.65 / 10.02 ms, 4x7 at 10 / 8 / 6 / 5 / 4: 9.78 / 9.72 / 9.66 / 9.74 / 10.00);
+        // complex128 CTAs (4 warps, twice the shared memory) already sit at 6 per SM
+        const int want = low_ctas() >= 0 ? low_ctas() : (sizeof(R) == 4 ? std::max(1, 24 / warps) : 0);
+        if (want > 0) {
+            const size_t per_cta = ((size_t)227 * 1024 / want - 1024) & ~(size_t)127;    // 1 KiB per CTA is the system's
+            if (per_cta > smem) smem = per_cta;
+        }
+    }
     if (smem > 48 * 1024) QCM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ExpandTreeArgs args = bp.trargs;
     double *level0 = args.tree_out;
