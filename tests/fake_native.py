@@ -105,18 +105,39 @@ class Handle:
     def _global_index(self):
         return np.arange(1 << self.n_local, dtype=np.int64) | (self.rank << self.n_local)
 
-    def postselect(self, mask, value, n_out_bits, want_probs=True):
+    def postselect(self, mask, value, n_out_bits, want_probs=True, out=None):
         w = np.abs(self.state) ** 2
         w[1 << self.active:] = 0
         idx = self._global_index()
         sel = (idx & mask) == value
-        out = np.zeros(1 << n_out_bits)
-        np.add.at(out, idx[sel] & ((1 << n_out_bits) - 1), w[sel])
-        return out, float(w[sel].sum())
+        res = np.zeros(1 << n_out_bits)
+        np.add.at(res, idx[sel] & ((1 << n_out_bits) - 1), w[sel])
+        if out is not None:                                 # deferred mode of the real handle: caller-owned buffers
+            out[0][:] = res
+            out[1][0] = float(w[sel].sum())
+            return out
+        return res, float(w[sel].sum())
 
-    def sample(self, shots, seed, stream_id=0, clbit_qubit=None):
+    def sample(self, shots, seed, stream_id=0, clbit_qubit=None, out=None):
         rng = np.random.default_rng([seed & 0xffffffff, stream_id])
-        return _keys_from_probs(np.abs(self.state) ** 2, shots, rng, clbit_qubit)
+        keys = _keys_from_probs(np.abs(self.state) ** 2, shots, rng, clbit_qubit)
+        if out is not None:
+            out[:] = keys
+            return out
+        return keys
+
+    # the real handle enqueues in deferred mode and waits per ticket; the emulator runs everything at once, so the
+    # host-side pipeline (ring slots, collection order) is what these exercise
+    def set_deferred(self, flag):
+        self.deferred = bool(flag)
+
+    def mark(self):
+        self._tickets = getattr(self, '_tickets', 0) + 1
+        return self._tickets - 1
+
+    def wait(self, ticket):
+        if ticket >= getattr(self, '_tickets', 0):
+            raise RuntimeError('ticket %d was never issued' % ticket)
 
     def sample_prepare(self):
         w = np.abs(self.state) ** 2
@@ -193,19 +214,29 @@ class BatchedHandle(Handle):
         got = [h.postselect(mask, value, n_out_bits) for h in self.pts]
         return (np.stack([g[0] for g in got]) if want_probs else None), np.array([g[1] for g in got])
 
-    def postselect_resident(self, mask, value, n_out_bits):
+    def postselect_resident(self, mask, value, n_out_bits, out=None):
         probs, kept = self.postselect(mask, value, n_out_bits)
         self._resident = probs
+        if out is not None:
+            out[:] = kept
+            return out
         return kept
+
+    def synchronize(self):
+        pass
 
     def fetch_probs(self, point, n_out_bits, first=0, count=None):
         return self._resident[point][first:None if count is None else first + count].copy()
 
-    def sample_batched(self, shots, seed, stream_ids, clbit_qubit=None):
-        return np.stack([h.sample(shots, seed, int(sid), clbit_qubit) for h, sid in zip(self.pts, stream_ids)])
+    def sample_batched(self, shots, seed, stream_ids, clbit_qubit=None, out=None):
+        keys = np.stack([h.sample(shots, seed, int(sid), clbit_qubit) for h, sid in zip(self.pts, stream_ids)])
+        if out is not None:
+            out[:] = keys
+            return out
+        return keys
 
-    def sample_released_batched(self, shots, seed, stream_ids, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_clbits):
-        out = np.zeros((self.batch, shots), dtype=np.uint64)
+    def sample_released_batched(self, shots, seed, stream_ids, n_ctrl, ctrl, p1, p1_off, vclbit, clbit_pos, n_clbits, out=None):
+        out = np.zeros((self.batch, shots), dtype=np.uint64) if out is None else out
         for y, (h, sid) in enumerate(zip(self.pts, stream_ids)):
             raw = h.sample(shots, seed, int(sid), None).astype(np.int64)
             rng = np.random.default_rng([seed & 0xffffffff, int(sid), 7])
@@ -237,8 +268,16 @@ class BatchedHandle(Handle):
         self._h = None
 
 
+class PinnedArray:
+    """numpy stand-in for _native.PinnedArray (page-locked host memory)."""
+
+    def __init__(self, shape, dtype):
+        self.array = np.zeros(shape, dtype=dtype)
+
+
 def install(monkeypatch):
     from qcmrf_b200 import _native
+    monkeypatch.setattr(_native, 'PinnedArray', PinnedArray)
     monkeypatch.setattr(_native, 'small_max_qubits', small_max_qubits)
     monkeypatch.setattr(_native, 'run_batch_small', run_batch_small)
     monkeypatch.setattr(_native, 'Handle', Handle)

@@ -309,3 +309,46 @@ def test_vectorised_sweep_preparation_equals_one_by_one(monkeypatch):
     assert np.allclose(fast.proj_tables, slow.proj_tables, rtol=1e-14, atol=0) and np.allclose(fast.p1, slow.p1, rtol=1e-14)
     th0 = list(th); th0[5] = 0.0
     assert sim._qcmrf_release_sweep([QCMRF(C, th), QCMRF(C, th0)], None, 'double') is None
+
+
+def test_list_of_large_circuits_is_a_pipeline_with_identical_results(monkeypatch, models):
+    """run(list) on the large-state path enqueues circuit i+1 before collecting circuit i (execute_deferred: a ring of
+    three result buffers, qcm_mark / qcm_wait tickets).  Host logic on the emulator: results equal one blocking run() per
+    circuit with the same Philox stream, across a change of state size inside the list; the ring refuses a fourth
+    pending execution and a second collection."""
+    import fake_native
+    fake_native.install(monkeypatch)
+    from qcmrf_b200 import QCMRF, B200Simulator
+    items = []
+    for j, t in ((1, 0), (1, 1), (3, 0), (1, 2), (5, 0), (5, 1), (5, 2), (5, 3), (1, 3)):
+        items.append((models['0.5']['GRAPHS'][j], models['0.5']['THETAS'][str(j)][t]))
+    sim = B200Simulator(precision='double', small_batch=False, sweep_batch=False, seed=3)
+    calls = []
+    orig = sim.execute_deferred
+    monkeypatch.setattr(sim, 'execute_deferred', lambda *a, **k: (calls.append(a[0]), orig(*a, **k))[1])
+    res = sim.run([QCMRF(c, th) for c, th in items], shots=3000).result()
+    assert len(calls) == len(items)                                    # every circuit went through the pipeline
+    one = B200Simulator(precision='double', small_batch=False, sweep_batch=False, seed=3)
+    for i, (c, th) in enumerate(items):
+        r1 = one.run(QCMRF(c, th), shots=3000, stream_ids=[i]).result()
+        assert r1.get_counts() == res.get_counts(i), i
+        p1, d1 = r1.postselected_probabilities(0)
+        p, d = res.postselected_probabilities(i)
+        assert np.array_equal(p, p1) and d == d1, i
+        assert res.metadata(i)['philox_stream'] == i and res.metadata(i)['path'] == 'statevector'
+    pr = sim.prepare(QCMRF(*items[0]))
+    fins = [sim.execute_deferred(pr, 50, seed=1, stream=s) for s in range(3)]
+    with pytest.raises(RuntimeError):
+        sim.execute_deferred(pr, 50, seed=1, stream=3)
+    outs = [f() for f in fins]
+    with pytest.raises(RuntimeError):
+        fins[1]()
+    k0, p0, m0 = sim.execute(pr, 50, seed=1, stream=0)
+    assert np.array_equal(outs[0][0], k0) and np.array_equal(outs[0][1], p0) and outs[0][2] == m0
+    # results handed out are copies: the ring slot is reused by the fourth execution without changing them
+    keep = outs[0][0].copy()
+    sim.execute_deferred(pr, 50, seed=1, stream=9)()
+    assert np.array_equal(outs[0][0], keep)
+    # no shots / release width: the blocking path answers through the same callable
+    k, p, m = sim.execute_deferred(pr, 0)()
+    assert k is None and np.array_equal(p, p0) and m == m0
