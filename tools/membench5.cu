@@ -336,6 +336,226 @@ void run_ring(float4 *p, const float4 *in, uint64_t nvec, int per_sm) {
     fflush(stdout);
 }
 
+// Software-pipelined k_low: phase A of batch b + 1 (the PAUSE dependent operations and the table stores) is spread over
+// the 32 store iterations of batch b (double-buffered tables), so a warp never stops storing between batches -- only the
+// CTA's first batch has a store-free phase.  NB batches per warp (TB = 8 + log2 NB).
+template <int NB, int PAUSE>
+__global__ void __launch_bounds__(256) k_low_sp(float4 *p, const float4 *in) {
+    __shared__ float4 sh[2][8][32 * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t xt = (uint64_t)blockIdx.x * (256 * NB);
+    auto in_of = [&](int b) { return in[(xt + (uint64_t)b * 256 + 2u * warp + (uint64_t)(lane >> 1) * 16 + (lane & 1)) & 0xfffff]; };
+    float4 mine = in_of(0);
+    float a = mine.x;
+#pragma unroll 1
+    for (int k = 0; k < PAUSE; ++k) a = a * 1.0001f + 0.5f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) sh[0][warp][s * 32 + lane] = make_float4(a, mine.y, mine.z, (float)s);
+    __syncwarp();
+    float acc = 0.f;
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+        const int cur = b & 1;
+        const uint64_t x0 = xt + (uint64_t)b * 256 + 2u * warp;
+        const bool more = b + 1 < NB;
+        float4 nx = more ? in_of(b + 1) : make_float4(0, 0, 0, 0);
+        float an = nx.x;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint64_t x = x0 + (uint64_t)(i >> 1) * 16 + (i & 1);
+            float4 u[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) u[s] = sh[cur][warp][s * 32 + i];
+            float l = 1.f + 1e-3f * lane;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) l = l * 1.0001f + u[k & 3].x;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                __stcs(p + (x << 7) + (uint64_t)s * 32 + lane, make_float4(l * u[s].x, l * u[s].y, l * u[s].z, l * u[s].w));
+            // this iteration's slice of the next batch's phase A
+#pragma unroll
+            for (int k = 0; k < (PAUSE + 31) / 32; ++k) an = an * 1.0001f + 0.5f;
+        }
+        if (more) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) sh[cur ^ 1][warp][s * 32 + lane] = make_float4(an, nx.y, nx.z, (float)s);
+        }
+        __syncwarp();
+        acc += an;
+    }
+    if (acc == 12345.678f) p[0] = make_float4(acc, 0, 0, 0);
+}
+
+template <int NB, int PAUSE>
+void run_low_sp(float4 *p, const float4 *in, uint64_t nvec, int per_sm) {
+    const unsigned grid = (unsigned)((nvec >> 7) / (256 * NB));
+    const int dyn = per_sm <= 0 ? 0 : std::max(0, (227 * 1024) / per_sm - 1024 - 33 * 1024);
+    CK(cudaFuncSetAttribute(k_low_sp<NB, PAUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_low_sp<NB, PAUSE>, 256, dyn));
+    float ms = timeit([&] { k_low_sp<NB, PAUSE><<<grid, 256, dyn>>>(p, in); });
+    printf("low_sp (phase A inside the store loop) %2d batches per warp, PAUSE=%4d, %d CTAs per SM   %8.3f ms  %8.1f GB/s\n", NB, PAUSE, occ, ms,
+           16.0 * nvec / ms / 1e6);
+    fflush(stdout);
+}
+
+// Bare store patterns of a long-lived 8-warp CTA over its 512 KiB (1024 pieces of 512 bytes = one warp store each):
+// P = 0: at step u the 8 warps write the 8 consecutive pieces 8u .. 8u+7 (4 KiB contiguous per step, k_init's order);
+// P = 1: k_expand_low's order -- warp w writes the 4 pieces of input 16k + 2w, then those of input 16k + 2w + 1;
+// P = 2: every warp its own contiguous 64 KiB.
+template <int P>
+__global__ void __launch_bounds__(256) k_pat(float4 *p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *base = p + (uint64_t)blockIdx.x * 1024 * 32;
+#pragma unroll 8
+    for (int u = 0; u < 128; ++u) {
+        int piece;
+        if (P == 0) piece = u * 8 + warp;
+        else if (P == 1) piece = ((u >> 3) * 16 + 2 * warp + ((u >> 2) & 1)) * 4 + (u & 3);
+        else piece = warp * 128 + u;
+        __stcs(base + (size_t)piece * 32 + lane, make_float4(1.f, 2.f, 3.f, (float)u));
+    }
+}
+
+// Cooperative + software-pipelined model: the CTA's 256 threads prepare 256 inputs (thread = input, tables shared by the
+// CTA, double-buffered), phase B walks the 1024 pieces in address order with the 8 warps on 8 consecutive pieces (P = 0's
+// order); the next batch's phase A is spread over the store loop; one __syncthreads per 512 KiB.
+template <int NB, int PAUSE>
+__global__ void __launch_bounds__(256) k_coop_sp(float4 *p, const float4 *in) {
+    extern __shared__ __align__(16) unsigned char dynraw[];
+    float4 (*us)[4][256] = reinterpret_cast<float4 (*)[4][256]>(dynraw);                       // [2][4][256]
+    float2 (*as)[4][257] = reinterpret_cast<float2 (*)[4][257]>(dynraw + 2 * 4 * 256 * 16);     // [2][4][257]
+    float2 (*bs)[8][257] = reinterpret_cast<float2 (*)[8][257]>(dynraw + 2 * 4 * 256 * 16 + 2 * 4 * 257 * 8);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t xt = (uint64_t)blockIdx.x * (256 * NB);
+    float4 mine = in[(xt + threadIdx.x) & 0xfffff];
+    float a = mine.x;
+#pragma unroll 1
+    for (int k = 0; k < PAUSE; ++k) a = a * 1.0001f + 0.5f;
+    auto park = [&](int buf, float av, float4 m) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) us[buf][t][threadIdx.x] = make_float4(av, m.y, m.z, (float)t);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) as[buf][t][threadIdx.x] = make_float2(av, m.y + t);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) bs[buf][t][threadIdx.x] = make_float2(av, m.z + t);
+    };
+    park(0, a, mine);
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+        const int cur = b & 1;
+        const uint64_t x0 = xt + (uint64_t)b * 256;
+        const bool more = b + 1 < NB;
+        float4 nx = more ? in[(x0 + 256 + threadIdx.x) & 0xfffff] : make_float4(0, 0, 0, 0);
+        float an = nx.x;
+#pragma unroll 8
+        for (int k = 0; k < 128; ++k) {
+            const int g = k * 8 + warp, i = g >> 2, t = g & 3;
+            const float2 fa = as[cur][lane & 3][i], fb = bs[cur][lane >> 2][i];
+            const float4 u = us[cur][t][i];
+            const float lr = fa.x * fb.x - fa.y * fb.y, li = fa.x * fb.y + fa.y * fb.x;
+            __stcs(p + ((x0 + i) << 7) + (uint64_t)t * 32 + lane,
+                   make_float4(lr * u.x - li * u.y, lr * u.y + li * u.x, lr * u.z - li * u.w, lr * u.w + li * u.z));
+#pragma unroll
+            for (int q = 0; q < (PAUSE + 127) / 128; ++q) an = an * 1.0001f + 0.5f;
+        }
+        if (more) park(cur ^ 1, an, nx);
+        __syncthreads();
+        acc += an;
+    }
+    if (acc == 12345.678f) p[0] = make_float4(acc, 0, 0, 0);
+}
+
+template <int P> void run_pat(float4 *p, uint64_t nvec, int per_sm) {
+    const unsigned grid = (unsigned)(nvec / (1024 * 32));
+    const int dyn = per_sm >= 8 ? 0 : (227 * 1024) / per_sm - 2048;
+    CK(cudaFuncSetAttribute(k_pat<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pat<P>, 256, dyn));
+    float ms = timeit([&] { k_pat<P><<<grid, 256, dyn>>>(p); });
+    printf("bare pattern %d, %d CTAs per SM   %8.3f ms  %8.1f GB/s\n", P, occ, ms, 16.0 * nvec / ms / 1e6);
+    fflush(stdout);
+}
+
+template <int NB, int PAUSE> void run_coop_sp(float4 *p, const float4 *in, uint64_t nvec, int per_sm) {
+    const unsigned grid = (unsigned)((nvec >> 7) / (256 * NB));
+    const int need = 2 * 4 * 256 * 16 + 2 * 4 * 257 * 8 + 2 * 8 * 257 * 8;
+    const int dyn = std::max(need, (227 * 1024) / per_sm - 2048);
+    CK(cudaFuncSetAttribute(k_coop_sp<NB, PAUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_coop_sp<NB, PAUSE>, 256, dyn));
+    float ms = timeit([&] { k_coop_sp<NB, PAUSE><<<grid, 256, dyn>>>(p, in); });
+    printf("coop_sp %2d x 512 KiB per CTA, PAUSE=%4d, %d CTAs per SM   %8.3f ms  %8.1f GB/s\n", NB, PAUSE, occ, ms, 16.0 * nvec / ms / 1e6);
+    fflush(stdout);
+}
+
+// Is it the READS?  k_low_sp with the per-batch input load (a) as it is, (b) replaced by arithmetic (no global load at
+// all), (c) all of the CTA's loads issued once at the start (registers).
+template <int NB, int PAUSE, int LOADS>
+__global__ void __launch_bounds__(256) k_low_rd(float4 *p, const float4 *in) {
+    __shared__ float4 sh[2][8][32 * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t xt = (uint64_t)blockIdx.x * (256 * NB);
+    auto in_of = [&](int b) -> float4 {
+        if (LOADS == 0) return make_float4(1.f + lane, 2.f + b, 3.f + warp, 4.f);
+        return in[(xt + (uint64_t)b * 256 + 2u * warp + (uint64_t)(lane >> 1) * 16 + (lane & 1)) & 0xfffff];
+    };
+    float4 all[NB];
+    if (LOADS == 2) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) all[b] = in_of(b);
+    }
+    float4 mine = LOADS == 2 ? all[0] : in_of(0);
+    float a = mine.x;
+#pragma unroll 1
+    for (int k = 0; k < PAUSE; ++k) a = a * 1.0001f + 0.5f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) sh[0][warp][s * 32 + lane] = make_float4(a, mine.y, mine.z, (float)s);
+    __syncwarp();
+    float acc = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int cur = b & 1;
+        const uint64_t x0 = xt + (uint64_t)b * 256 + 2u * warp;
+        const bool more = b + 1 < NB;
+        float4 nx = more ? (LOADS == 2 ? all[(b + 1) % NB] : in_of(b + 1)) : make_float4(0, 0, 0, 0);
+        float an = nx.x;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint64_t x = x0 + (uint64_t)(i >> 1) * 16 + (i & 1);
+            float4 u[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) u[s] = sh[cur][warp][s * 32 + i];
+            float l = 1.f + 1e-3f * lane;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) l = l * 1.0001f + u[k & 3].x;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                __stcs(p + (x << 7) + (uint64_t)s * 32 + lane, make_float4(l * u[s].x, l * u[s].y, l * u[s].z, l * u[s].w));
+#pragma unroll
+            for (int k = 0; k < (PAUSE + 31) / 32; ++k) an = an * 1.0001f + 0.5f;
+        }
+        if (more) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) sh[cur ^ 1][warp][s * 32 + lane] = make_float4(an, nx.y, nx.z, (float)s);
+        }
+        __syncwarp();
+        acc += an;
+    }
+    if (acc == 12345.678f) p[0] = make_float4(acc, 0, 0, 0);
+}
+
+template <int NB, int PAUSE, int LOADS>
+void run_low_rd(float4 *p, const float4 *in, uint64_t nvec, int per_sm) {
+    const unsigned grid = (unsigned)((nvec >> 7) / (256 * NB));
+    const int dyn = per_sm <= 0 ? 0 : std::max(0, (227 * 1024) / per_sm - 1024 - 33 * 1024);
+    CK(cudaFuncSetAttribute(k_low_rd<NB, PAUSE, LOADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_low_rd<NB, PAUSE, LOADS>, 256, dyn));
+    float ms = timeit([&] { k_low_rd<NB, PAUSE, LOADS><<<grid, 256, dyn>>>(p, in); });
+    printf("low_rd %2d batches per warp, PAUSE=%4d, loads: %s, %d CTAs per SM   %8.3f ms  %8.1f GB/s\n", NB, PAUSE,
+           LOADS == 0 ? "none        " : LOADS == 1 ? "per batch   " : "all at start", occ, ms, 16.0 * nvec / ms / 1e6);
+    fflush(stdout);
+}
+
 void earlier(float4 *p, const float4 *in, uint64_t nvec, uint64_t bytes) {
     float ms;
     const unsigned ctas = (unsigned)(nvec / (256 * 128));
@@ -397,6 +617,43 @@ void tma_runs(float4 *p, const float4 *in, uint64_t nvec) {
     }
 }
 
+void ring_runs(float4 *p, const float4 *in, uint64_t nvec) {
+    for (int per_sm : {1, 2, 3}) {
+        run_ring<8, 2, 0, 0, 0>(p, in, nvec, per_sm);
+        run_ring<8, 3, 0, 0, 0>(p, in, nvec, per_sm);
+        run_ring<8, 2, 4, 8, 300>(p, in, nvec, per_sm);
+        run_ring<8, 3, 4, 8, 300>(p, in, nvec, per_sm);
+        run_ring<10, 2, 4, 8, 300>(p, in, nvec, per_sm);
+        run_ring<10, 3, 4, 8, 300>(p, in, nvec, per_sm);
+        run_ring<12, 3, 4, 8, 300>(p, in, nvec, per_sm);
+        run_ring<10, 3, 4, 8, 1200>(p, in, nvec, per_sm);
+    }
+}
+
+void sp_runs(float4 *p, const float4 *in, uint64_t nvec) {
+    for (int per_sm : {1, 2, 3, 4, 6}) {
+        run_low_sp<4, 300>(p, in, nvec, per_sm);
+        run_low_sp<8, 300>(p, in, nvec, per_sm);
+        run_low_sp<16, 300>(p, in, nvec, per_sm);
+        run_low_sp<8, 1200>(p, in, nvec, per_sm);
+        run_low_sp<16, 1200>(p, in, nvec, per_sm);
+    }
+}
+
+void pat_runs(float4 *p, const float4 *in, uint64_t nvec) {
+    for (int per_sm : {8, 4, 2, 1}) {
+        run_pat<0>(p, nvec, per_sm);
+        run_pat<1>(p, nvec, per_sm);
+        run_pat<2>(p, nvec, per_sm);
+    }
+    for (int per_sm : {1, 2, 3}) {
+        run_coop_sp<1, 300>(p, in, nvec, per_sm);
+        run_coop_sp<4, 300>(p, in, nvec, per_sm);
+        run_coop_sp<16, 300>(p, in, nvec, per_sm);
+        run_coop_sp<4, 1200>(p, in, nvec, per_sm);
+    }
+}
+
 int main(int argc, char **argv) {
     const uint64_t gib = argc > 1 ? strtoull(argv[1], nullptr, 10) : 32;
     const uint64_t bytes = gib << 30;
@@ -416,15 +673,18 @@ int main(int argc, char **argv) {
     if (argc > 3) {                                            // ./membench5 GiB all tma: the bulk-store writers
         tma_runs(p, in, nvec);
     }
+    if (argc > 4) ring_runs(p, in, nvec);                      // ./membench5 GiB all tma ring
+    if (argc > 5) sp_runs(p, in, nvec);                        // ./membench5 GiB all tma ring sp
+    if (argc > 6) pat_runs(p, in, nvec);                       // ./membench5 GiB all tma ring sp pat
     for (int per_sm : {1, 2, 3}) {
-        run_ring<8, 2, 0, 0, 0>(p, in, nvec, per_sm);
-        run_ring<8, 3, 0, 0, 0>(p, in, nvec, per_sm);
-        run_ring<8, 2, 4, 8, 300>(p, in, nvec, per_sm);
-        run_ring<8, 3, 4, 8, 300>(p, in, nvec, per_sm);
-        run_ring<10, 2, 4, 8, 300>(p, in, nvec, per_sm);
-        run_ring<10, 3, 4, 8, 300>(p, in, nvec, per_sm);
-        run_ring<12, 3, 4, 8, 300>(p, in, nvec, per_sm);
-        run_ring<10, 3, 4, 8, 1200>(p, in, nvec, per_sm);
+        run_low_rd<4, 300, 1>(p, in, nvec, per_sm);
+        run_low_rd<4, 300, 0>(p, in, nvec, per_sm);
+        run_low_rd<4, 300, 2>(p, in, nvec, per_sm);
+        run_low_rd<8, 300, 1>(p, in, nvec, per_sm);
+        run_low_rd<8, 300, 0>(p, in, nvec, per_sm);
+        run_low_rd<8, 300, 2>(p, in, nvec, per_sm);
+        run_low_rd<1, 300, 1>(p, in, nvec, per_sm);
+        run_low_rd<1, 300, 0>(p, in, nvec, per_sm);
     }
     return 0;
 }
