@@ -23,6 +23,14 @@ static void radix_sort_u64(uint64_t *a, uint64_t *tmp, size_t n, int bits) {
     }
 }
 
+static char bits8[256][8];
+static int bits8_ready = 0;
+static void init_bits8(void) {
+    for (int b = 0; b < 256; ++b)
+        for (int j = 0; j < 8; ++j) bits8[b][7 - j] = (char)('0' + ((b >> j) & 1));
+    bits8_ready = 1;
+}
+
 /* keys[n] (bit c = sampled value of clbit c) -> new dict {width-character bit string: count},
  * keys in ascending numeric order (the order np.unique gives the Python fallback). */
 PyObject *qcm_counts_dict(const uint64_t *keys, Py_ssize_t n, int width) {
@@ -31,15 +39,21 @@ PyObject *qcm_counts_dict(const uint64_t *keys, Py_ssize_t n, int width) {
         PyErr_SetString(PyExc_ValueError, "qcm_counts_dict: width must be 1..64");
         return NULL;
     }
-    PyObject *d = PyDict_New();
-    if (!d || n == 0) return d;
+    if (n == 0) return PyDict_New();
+    if (!bits8_ready) init_bits8();                       /* called with the GIL held (PyDLL): no race */
     uint64_t *a = (uint64_t *)malloc(2 * (size_t)n * sizeof(uint64_t));
-    if (!a) {
-        Py_DECREF(d);
-        return PyErr_NoMemory();
-    }
+    if (!a) return PyErr_NoMemory();
     memcpy(a, keys, (size_t)n * sizeof(uint64_t));
     radix_sort_u64(a, a + n, (size_t)n, width);
+    /* the table is sized once for the number of distinct keys: a dict grown entry by entry is rebuilt ~12 times on the
+     * way to 10^4 entries, a third of this function's time */
+    Py_ssize_t distinct = 1;
+    for (Py_ssize_t k = 1; k < n; ++k) distinct += a[k] != a[k - 1];
+    PyObject *d = _PyDict_NewPresized(distinct);
+    if (!d) {
+        free(a);
+        return NULL;
+    }
     Py_ssize_t i = 0;
     while (i < n) {
         const uint64_t v = a[i];
@@ -49,7 +63,10 @@ PyObject *qcm_counts_dict(const uint64_t *keys, Py_ssize_t n, int width) {
         PyObject *k = PyUnicode_New(width, 127);
         if (k) {
             Py_UCS1 *d8 = PyUnicode_1BYTE_DATA(k);
-            for (int c = 0; c < width; ++c) d8[width - 1 - c] = (Py_UCS1)('0' + ((v >> c) & 1u));
+            /* eight characters per step from a table of the 256 byte patterns (most significant bit first) */
+            int c = 0;
+            for (; c + 8 <= width; c += 8) memcpy(d8 + width - 8 - c, bits8[(v >> c) & 0xffu], 8);
+            for (; c < width; ++c) d8[width - 1 - c] = (Py_UCS1)('0' + ((v >> c) & 1u));
         }
         PyObject *cnt = PyLong_FromSsize_t(j - i);
         if (!k || !cnt || PyDict_SetItem(d, k, cnt) < 0) {
