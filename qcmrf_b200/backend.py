@@ -328,6 +328,10 @@ class B200Simulator:
         key = (n_phys, precision) if batch == 1 else (n_phys, precision, batch)
         h = self._handles.get(key)
         if h is None:
+            if self._ring is not None and any(rec is not None and not rec['done'] for rec in self._ring['busy']):
+                # the state of a pending execute_deferred() would be released under its running kernels
+                raise RuntimeError('deferred executions are pending on the state that a new state size would replace: '
+                                   'collect them first (call what execute_deferred returned)')
             for k in list(self._handles):              # one big state at a time
                 self._launches_closed += self._handles[k].timing()['kernel_launches']
                 self._handles.pop(k).close()

@@ -349,6 +349,14 @@ def test_list_of_large_circuits_is_a_pipeline_with_identical_results(monkeypatch
     keep = outs[0][0].copy()
     sim.execute_deferred(pr, 50, seed=1, stream=9)()
     assert np.array_equal(outs[0][0], keep)
+    # another state size while an execution is pending would release the state under it: refused until collected
+    other = sim.prepare(QCMRF(*items[2]))
+    assert other.plan.n_phys != pr.plan.n_phys
+    fin = sim.execute_deferred(pr, 50, seed=1, stream=0)
+    with pytest.raises(RuntimeError, match='pending'):
+        sim.execute_deferred(other, 50, seed=1, stream=0)
+    assert np.array_equal(fin()[0], k0)
+    sim.execute_deferred(other, 50, seed=1, stream=0)()
     # no shots / release width: the blocking path answers through the same callable
     k, p, m = sim.execute_deferred(pr, 0)()
     assert k is None and np.array_equal(p, p0) and m == m0
