@@ -929,7 +929,7 @@ class ShardedSimulator:
             blocks = hall[:, :nb]
             if rec['order'] != list(range(self.world)):
                 blocks = blocks[rec['order']]
-            probs = np.ascontiguousarray(blocks).reshape(-1)
+            probs = np.array(blocks, order='C').reshape(-1)          # always a copy: the pinned buffer is reused
             keys = hall[:, nb + 3:].view(np.int64).sum(axis=0).astype(np.uint64)
             out = (keys, probs, kept)
         rec['done'].set()                                    # the pinned buffer of this slot may be reused
@@ -991,7 +991,7 @@ class ShardedSimulator:
         blocks = hall[:, :-2]
         if pr.pmf_order != list(range(self.world)):
             blocks = blocks[pr.pmf_order]
-        probs = np.ascontiguousarray(blocks).reshape(-1)
+        probs = np.array(blocks, order='C').reshape(-1)          # always a copy: the pinned buffer is reused
         keys = b['h_keys'].numpy().astype(np.uint64)
         return keys, probs, kept
 
@@ -1074,7 +1074,7 @@ class ShardedSimulator:
         return sorted(range(self.world), key=lambda r: self._pmf_where_for_rank(pr, r, m).start)
 
     def run(self, circuits, shots=1024, seed=None, n_vars=None):
-        from .backend import Job, Result, _keys_to_counts
+        from .backend import Job, Result, _keys_to_counts, _normalised
         t0 = time.perf_counter()
         single = not isinstance(circuits, (list, tuple))
         circs = [circuits] if single else list(circuits)
@@ -1085,7 +1085,8 @@ class ShardedSimulator:
             counts = _keys_to_counts(keys, pr.prog.n_clbits) if shots else None
             h2d = sum(seg[1].nbytes + seg[2].nbytes for seg in pr.sp.segments if seg[0] == 'run')
             d2h = (probs.nbytes + 8 if probs is not None else 0) + (keys.nbytes if keys is not None else 0)
-            return {'circuit': c, 'name': pr.name, 'counts': counts, 'probs': probs, 'kept': kept,
+            pmf = _normalised(probs, kept)                 # in place, behind the next circuit's gate program
+            return {'circuit': c, 'name': pr.name, 'counts': counts, 'probs': None if pmf is not None else probs, 'pmf': pmf, 'kept': kept,
                     'meta': {'path': 'sharded', 'ranks': self.world, 'n_qubits': pr.prog.n_qubits,
                              'n_phys': pr.plan.n_phys, 'n_local': pr.sp.n_local, 'passes': pr.plan.n_passes,
                              'exchanges': pr.sp.n_exchanges, 'exchange_ms': exchange_ms,

@@ -335,6 +335,7 @@ def test_list_of_large_circuits_is_a_pipeline_with_identical_results(monkeypatch
         p1, d1 = r1.postselected_probabilities(0)
         p, d = res.postselected_probabilities(i)
         assert np.array_equal(p, p1) and d == d1, i
+        assert abs(p.sum() - 1.0) < 1e-12 and res.postselected_probabilities(i)[0] is p      # normalised once, in the pipeline
         assert res.metadata(i)['philox_stream'] == i and res.metadata(i)['path'] == 'statevector'
     pr = sim.prepare(QCMRF(*items[0]))
     fins = [sim.execute_deferred(pr, 50, seed=1, stream=s) for s in range(3)]
