@@ -483,6 +483,43 @@ def prune_zero_controls(gates: List[Gate], n_qubits: int) -> List[Gate]:
     return out
 
 
+def drop_unmaterialised_controls(fc: 'FusedCircuit') -> 'FusedCircuit':
+    """A sweep's index qubit that is neither initialised nor the target of an earlier sweep is still |0> when the sweep
+    runs: the table is sliced at that index bit = 0 and the qubit leaves the index (a sweep that becomes the identity on a
+    |0> target, or a diagonal without index qubits, disappears).  prune_zero_controls does this gate by gate, but a qubit
+    whose gates only CLASSIFY to "still |0>" (`cx` from a |0> control, `p`, a controlled phase: found by the seeded fuzz in
+    tests/test_host_fusion.py) looked touched to it, and the lazy layout then reserved a position for a qubit that is
+    never materialised ('layout/materialisation order mismatch')."""
+    mat = set(fc.init)
+    ops: List[FusedOp] = []
+    phase = fc.global_phase
+    changed = False
+    for op in fc.ops:
+        dead = [j for j, q in enumerate(op.ctrls) if q not in mat]
+        if dead:
+            changed = True
+            keep = [j for j in range(len(op.ctrls)) if j not in dead]
+            ar = np.arange(1 << len(keep), dtype=np.int64)
+            idx = np.zeros(1 << len(keep), dtype=np.int64)
+            for k2, j in enumerate(keep):
+                idx |= ((ar >> k2) & 1) << j
+            tab = np.ascontiguousarray(op.table[idx])
+            ctrls = tuple(op.ctrls[j] for j in keep)
+            if op.kind == 'diag' and not ctrls:
+                phase += float(np.angle(tab[0]))
+                continue
+            if op.kind == 'mux' and op.target not in mat and np.abs(tab - np.eye(2)).max() == 0.0:
+                continue                                    # the identity on a |0> target: the target stays unmaterialised
+            op = FusedOp(op.kind, op.target, ctrls, tab, op.zero_in, op.n_gates)
+        ops.append(op)
+        if op.kind == 'mux':
+            mat.add(op.target)
+    if not changed:
+        return fc
+    import dataclasses
+    return dataclasses.replace(fc, ops=ops, global_phase=phase)
+
+
 _MC_NAME = {'cx': 'mcx', 'mcx': 'mcx', 'cp': 'mcp', 'mcp': 'mcp'}
 
 
@@ -866,6 +903,7 @@ def split_releasable(fc: FusedCircuit, keep_below: int = 0):
     sweep and never used again -- a QCMRF clique ancilla, measured right after its block
     (QCMRF.py:231-239) -- need not be stored at all.  Returns (core circuit without those sweeps,
     list of the released sweeps).  Qubits below ``keep_below`` (the variable register) are kept."""
+    fc = drop_unmaterialised_controls(fc)
     used_later = {}
     last_targeted = {}
     for k, op in enumerate(fc.ops):
@@ -979,6 +1017,7 @@ def plan(fc: FusedCircuit, lazy: bool = True, block_max: int = 4, elide: Optiona
                   highest physical positions, to be held by the rank index of a 2^g-way
                   sharded state; raises ValueError if the circuit has fewer than g of them.
     """
+    fc = drop_unmaterialised_controls(fc)
     N = fc.n_qubits
     em = _Emitter()
     if elide is None:

@@ -15,6 +15,7 @@ multi-controlled X -- plus the usual single-qubit gates, into that basis:
 The result is what the backend's fusion pass must collapse back into one sweep per
 clique, so tests run every fixture model through this path as well.
 """
+import cmath
 import math
 from typing import Iterable, List
 
@@ -148,14 +149,19 @@ class _Out:
             phi_minus_lam = np.angle(U[1, 0]) - np.angle(-U[0, 1])
         phi = 0.5 * (phi_plus_lam + phi_minus_lam)
         lam = 0.5 * (phi_plus_lam - phi_minus_lam)
-        seq = [('rz', lam), ('sx',), ('rz', theta + _PI), ('sx',), ('rz', phi + _PI)]
-        M = np.eye(2, dtype=np.complex128)
-        for g in seq:
-            G = ir.one_qubit_matrix(g[0], g[1:])
-            M = G @ M
-        k = np.argmax(np.abs(U))
-        ph = np.angle(U.flat[k] / M.flat[k])
-        if np.abs(M * np.exp(1j * ph) - U).max() > 1e-9:
+        # the two angle differences are known modulo 2 pi, their halves modulo pi: (phi, lam) or (phi + pi, lam + pi) --
+        # the second flips the sign of the off-diagonal entries against the diagonal, so exactly one of them is U
+        for shift in (0.0, _PI):
+            seq = [('rz', lam + shift), ('sx',), ('rz', theta + _PI), ('sx',), ('rz', phi + shift + _PI)]
+            M = np.eye(2, dtype=np.complex128)
+            for g in seq:
+                G = ir.one_qubit_matrix(g[0], g[1:])
+                M = G @ M
+            k = np.argmax(np.abs(U))
+            ph = np.angle(U.flat[k] / M.flat[k])
+            if np.abs(M * np.exp(1j * ph) - U).max() <= 1e-9:
+                break
+        else:
             raise AssertionError('ZSX decomposition failed')
         for g in seq:
             if g[0] == 'rz':
@@ -207,6 +213,34 @@ class _Out:
             self.mcp(lam / 2, rest, t)
 
 
+def _controlled_unitary(o, U, ctrls: List[int], t):
+    """(Multi-)controlled arbitrary 1-qubit gate (cy, ch, crz, crx, cry, csx): U = e^{i alpha} Rz(beta) Ry(gamma) Rz(delta),
+    A = Rz(beta) Ry(gamma/2), B = Ry(-gamma/2) Rz(-(delta+beta)/2), C = Rz((delta-beta)/2): A B C = 1 and A X B X C = U e^{-i
+    alpha}, so C^n(U) = C(t), C^nX, B(t), C^nX, A(t) and the phase alpha on the controls alone."""
+    U = np.asarray(U, dtype=np.complex128)
+    alpha = 0.5 * cmath.phase(U[0, 0] * U[1, 1] - U[0, 1] * U[1, 0])
+    V = U * cmath.exp(-1j * alpha)
+    gamma = 2.0 * math.atan2(abs(V[1, 0]), abs(V[0, 0]))
+    plus = 2.0 * cmath.phase(V[1, 1]) if abs(V[1, 1]) > 1e-12 else 0.0          # beta + delta
+    minus = 2.0 * cmath.phase(V[1, 0]) if abs(V[1, 0]) > 1e-12 else 0.0         # beta - delta
+    beta, delta = 0.5 * (plus + minus), 0.5 * (plus - minus)
+
+    def rz(a):
+        return np.array([[cmath.exp(-0.5j * a), 0], [0, cmath.exp(0.5j * a)]])
+
+    def ry(a):
+        c, s_ = math.cos(a / 2), math.sin(a / 2)
+        return np.array([[c, -s_], [s_, c]], dtype=np.complex128)
+    A, B, C = rz(beta) @ ry(gamma / 2), ry(-gamma / 2) @ rz(-(delta + beta) / 2), rz((delta - beta) / 2)
+    o.u1q(C, t)
+    o.mcx(ctrls, t)
+    o.u1q(B, t)
+    o.mcx(ctrls, t)
+    o.u1q(A, t)
+    if abs(math.remainder(alpha, 2 * _PI)) > 1e-15:
+        o.mcp(alpha, ctrls[:-1], ctrls[-1])
+
+
 def _translate(prog: ir.Program, name) -> QuantumCircuit:
     out = _Sink(prog.global_phase)
     o = _Out(out)
@@ -234,7 +268,7 @@ def _translate(prog: ir.Program, name) -> QuantumCircuit:
         elif base in ('p', 'z'):
             o.mcp(g.params[0] if base == 'p' else _PI, list(g.controls), g.target)
         else:
-            raise ValueError('transpile: controlled-%s is not supported' % base)
+            _controlled_unitary(o, g.base_matrix(), list(g.controls), g.target)
         for c in opens:
             o.x(c)
     out.global_phase = math.remainder(out.global_phase, 2 * _PI)

@@ -361,3 +361,56 @@ def test_list_of_large_circuits_is_a_pipeline_with_identical_results(monkeypatch
     # no shots / release width: the blocking path answers through the same callable
     k, p, m = sim.execute_deferred(pr, 0)()
     assert k is None and np.array_equal(p, p0) and m == m0
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_random_generic_circuits_through_the_public_call(monkeypatch, seed):
+    """Seeded fuzz of the generic front end through B200Simulator.run on the emulator: random circuits over the whole gate
+    surface (plain and transpiled to cx/id/rz/sx/x), a random subset of qubits measured into shuffled clbits, a random
+    variable-register width -- post-selected pmf and success probability against an independent textbook simulation,
+    keys only where the exact key distribution has mass, histogram within its Weissman bound; every fusion mode, the
+    batched-small and the large-state path, full and release width."""
+    import fake_native
+    fake_native.install(monkeypatch)
+    from test_host_fusion import _random_circuit, _textbook_state
+    from qcmrf_b200 import B200Simulator, transpile
+    from qcmrf_b200.circuit import QuantumCircuit
+    rng = np.random.RandomState(9100 + seed)
+    checked = 0
+    for trial in range(8):
+        nq = int(rng.randint(1, 6))
+        base = _random_circuit(rng, nq, int(rng.randint(1, 24)))
+        pw = np.abs(_textbook_state(base)) ** 2
+        nv = int(rng.randint(1, nq + 1))
+        mq = [int(q) for q in rng.permutation(nq)[:int(rng.randint(1, nq + 1))]]
+        cbits = [int(b) for b in rng.permutation(len(mq))]
+        c = QuantumCircuit(nq, len(mq))
+        for ins in base.data:
+            c._qc_add(ins.operation, list(ins.qubits))
+        for q, b in zip(mq, cbits):
+            c.measure(q, b)
+        if trial % 2:
+            c = transpile(c, basis_gates=['cx', 'id', 'rz', 'sx', 'x'])
+        kept = pw[:1 << nv].sum()
+        if kept < 1e-9:
+            continue
+        idx = np.arange(1 << nq)
+        key = np.zeros_like(idx)
+        for q, b in zip(mq, cbits):
+            key |= ((idx >> q) & 1) << b
+        kp = np.bincount(key, weights=pw, minlength=1 << len(mq))
+        bound = 0.5 * np.sqrt(2 * ((1 << len(mq)) * np.log(2) + np.log(1e7)) / 2000)
+        for fus, small, width in (('off', True, 'full'), ('clique', False, 'full'), ('blocked', False, 'release'),
+                                  ('blocked', True, 'full')):
+            sim = B200Simulator(precision='double', fusion=fus, small_batch=small, width=width, seed=1)
+            res = sim.run(c, shots=2000, n_vars=nv).result()
+            p, d = res.postselected_probabilities(0)
+            assert np.abs(p - pw[:1 << nv] / kept).max() < 1e-10 and abs(d - kept) < 1e-10, (seed, trial, fus, small, width)
+            cnt = res.get_counts()
+            assert sum(cnt.values()) == 2000 and all(len(k) == len(mq) and kp[int(k, 2)] > 1e-14 for k in cnt)
+            emp = np.zeros(1 << len(mq))
+            for k, v in cnt.items():
+                emp[int(k, 2)] = v / 2000
+            assert 0.5 * np.abs(emp - kp).sum() < bound, (seed, trial, fus, small, width)
+            checked += 1
+    assert checked >= 16

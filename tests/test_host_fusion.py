@@ -573,3 +573,109 @@ def test_basis_array_fusion_equals_the_object_loop(models):
         ss = em.logical_state(pl_s, em.run_plan(pl_s)[0])
         psi, _ = sv.run_program(ir.to_oracle_ops(prog), n)
         assert np.abs(sf - psi).max() < 1e-12 and np.abs(ss - psi).max() < 1e-12, trial
+
+
+def _random_circuit(rng, nq, n_gates):
+    from qcmrf_b200.circuit import QuantumCircuit
+    c = QuantumCircuit(nq)
+    one = ['h', 'x', 'y', 'z', 's', 'sdg', 't', 'tdg', 'sx', 'sxdg', 'id']
+    for _ in range(n_gates):
+        r = rng.rand()
+        q = [int(v) for v in rng.permutation(nq)]
+        if r < 0.3:
+            getattr(c, one[rng.randint(len(one))])(q[0])
+        elif r < 0.45:
+            getattr(c, ['rz', 'rx', 'ry', 'p'][rng.randint(4)])(float(rng.uniform(-3, 3)), q[0])
+        elif r < 0.5:
+            c.u(*[float(v) for v in rng.uniform(-3, 3, 3)], q[0])
+        elif r < 0.7 and nq >= 2:
+            getattr(c, ['cx', 'cz', 'swap'][rng.randint(3)])(q[0], q[1])
+        elif r < 0.8 and nq >= 2:
+            getattr(c, ['cp', 'crz'][rng.randint(2)])(float(rng.uniform(-3, 3)), q[0], q[1])
+        elif r < 0.9 and nq >= 3:
+            m = int(rng.randint(2, min(nq, 4)))
+            c.mcx(q[:m], q[m], ctrl_state=''.join(rng.choice(['0', '1'], m)))
+        elif nq >= 3:
+            m = int(rng.randint(2, min(nq, 4)))
+            c.mcp(float(rng.uniform(-3, 3)), q[:m], q[m])
+        else:
+            c.h(q[0])
+    return c
+
+
+def _textbook_state(circ):
+    """Dense reference for the fuzz test below, independent of the product's gate tables: textbook 2x2 matrices
+    (Qiskit's conventions) applied gate by gate to |0...0>, little-endian."""
+    sq, i = np.sqrt(0.5), 1j
+    fixed = {'h': [[sq, sq], [sq, -sq]], 'x': [[0, 1], [1, 0]], 'y': [[0, -i], [i, 0]], 'z': [[1, 0], [0, -1]],
+             's': [[1, 0], [0, i]], 'sdg': [[1, 0], [0, -i]], 't': [[1, 0], [0, np.exp(i * np.pi / 4)]],
+             'tdg': [[1, 0], [0, np.exp(-i * np.pi / 4)]], 'sx': [[(1 + i) / 2, (1 - i) / 2], [(1 - i) / 2, (1 + i) / 2]],
+             'sxdg': [[(1 - i) / 2, (1 + i) / 2], [(1 + i) / 2, (1 - i) / 2]], 'id': [[1, 0], [0, 1]]}
+
+    def mat(name, p):
+        if name in fixed:
+            return np.array(fixed[name], dtype=complex)
+        if name in ('rz', 'crz'):
+            return np.diag([np.exp(-i * p[0] / 2), np.exp(i * p[0] / 2)])
+        if name == 'rx':
+            c, s_ = np.cos(p[0] / 2), np.sin(p[0] / 2)
+            return np.array([[c, -i * s_], [-i * s_, c]])
+        if name == 'ry':
+            c, s_ = np.cos(p[0] / 2), np.sin(p[0] / 2)
+            return np.array([[c, -s_], [s_, c]], dtype=complex)
+        if name in ('p', 'cp', 'mcp'):
+            return np.diag([1, np.exp(i * p[0])])
+        if name == 'u':
+            c, s_ = np.cos(p[0] / 2), np.sin(p[0] / 2)
+            return np.array([[c, -np.exp(i * p[2]) * s_], [np.exp(i * p[1]) * s_, np.exp(i * (p[1] + p[2])) * c]])
+        if name in ('cx', 'mcx'):
+            return np.array(fixed['x'], dtype=complex)
+        if name == 'cz':
+            return np.array(fixed['z'], dtype=complex)
+        raise ValueError(name)
+
+    n = circ.num_qubits
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[0] = 1.0
+    idx = np.arange(1 << n)
+
+    def apply(u, ctrls, vals, t):
+        sel = np.ones(1 << n, dtype=bool)
+        for c, v in zip(ctrls, vals):
+            sel &= ((idx >> c) & 1) == v
+        lo = idx[sel & (((idx >> t) & 1) == 0)]
+        hi = lo | (1 << t)
+        a, b = psi[lo].copy(), psi[hi].copy()
+        psi[lo] = u[0, 0] * a + u[0, 1] * b
+        psi[hi] = u[1, 0] * a + u[1, 1] * b
+
+    for ins in circ.data:
+        op, qs = ins.operation, tuple(int(q) for q in ins.qubits)
+        if op.name == 'swap':
+            for c, t in ((qs[0], qs[1]), (qs[1], qs[0]), (qs[0], qs[1])):
+                apply(mat('x', ()), (c,), (1,), t)
+            continue
+        vals = tuple(op.ctrl_values) if getattr(op, 'ctrl_values', None) is not None else (1,) * (len(qs) - 1)
+        apply(mat(op.name, op.params), qs[:-1], vals, qs[-1])
+    return psi
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_random_generic_circuits_through_every_fusion_mode(seed):
+    """Seeded fuzz of the generic front end: random circuits over the whole gate surface -- many of them
+    start with controls on untouched |0> qubits, end in gates onto clean qubits, or leave qubits untouched -- lowered,
+    fused, planned (eager and lazy, blocks of 1..5) and run on the engine emulator must give the gate-by-gate
+    state of an independent textbook simulation exactly (no global-phase slack), and the transpiled circuit the same state
+    up to a global phase."""
+    rng = np.random.RandomState(4000 + seed)
+    for trial in range(25):
+        nq = int(rng.randint(1, 7))
+        c = _random_circuit(rng, nq, int(rng.randint(1, 28)))
+        prog, psi = ir.lower(c), _textbook_state(c)
+        for mode, lazy, bm in CONFIGS:
+            lg, _, _ = _logical(prog, mode, lazy, bm)
+            assert np.abs(lg - psi).max() < 1e-12, (seed, trial, mode, lazy, bm)
+        if trial % 5 == 0:
+            tc = transpile(c, basis_gates=['cx', 'id', 'rz', 'sx', 'x'])
+            lg, _, _ = _logical(ir.lower(tc), 'clique', True, 4)
+            assert abs(abs(np.vdot(lg, psi)) - 1.0) < 1e-9, (seed, trial, 'transpiled')
