@@ -350,6 +350,29 @@ def _merge_diags(members):
 
 
 # ------------------------------------------------------------------------------------------
+def plan_for_shards(fc, g, rank, lazy, block_max, n_global, expand_max, fuse_exchange):
+    """(plan, this rank's ShardedPlan).  The lazily materialised layout is used where it is communication-free (every
+    QCMRF circuit: ancillas are materialised where they live).  A circuit that would need a qubit-swap exchange in the
+    middle of a lazily materialised program -- a foreign circuit that targets its high qubits again and again -- is
+    planned densely instead (every qubit materialised up front, one pass per sweep, Aer's width): exchanges of partially
+    materialised shards and rank-dependent pruning around them are where a seeded fuzz of random circuits on 4 ranks
+    found ranks disagreeing on the segment list.  The decision looks at every rank's rewrite, so all ranks take it
+    alike."""
+    def build(lz):
+        p = fusion.plan(fc, lazy=lz, block_max=block_max, n_global=n_global if lz else 0, expand_max=expand_max)
+        return p, shard_plan(p, g, rank, fuse_exchange=fuse_exchange)
+    try:
+        p, q = build(lazy)
+        dense = bool(lazy and g and any(shard_plan(p, g, r, fuse_exchange=fuse_exchange).n_exchanges for r in range(1 << g)))
+    except ValueError:
+        if not lazy:
+            raise
+        dense = True                                         # e.g. too few local qubits for a lazy plan's exchange
+    if dense:
+        p, q = build(False)
+    return p, q
+
+
 class _ShardPrepared:
     __slots__ = ('prog', 'fc', 'plan', 'sp', 'clbit_map', 'n_vars', 'ps', 'name', 'var_positions', 'pmf_map', 'pmf_order',
                  '_known_masses')
@@ -538,9 +561,7 @@ class ShardedSimulator:
         fuse_x = self.exchange in ('p2p', 'p2p-inplace')
 
         def build(f):
-            p = fusion.plan(f, lazy=lazy, block_max=self.block_max, n_global=ng,
-                            expand_max=max(self.block_max, self.expand_max))
-            q = shard_plan(p, self.g, self.rank, fuse_exchange=fuse_x)
+            p, q = plan_for_shards(f, self.g, self.rank, lazy, self.block_max, ng, max(self.block_max, self.expand_max), fuse_x)
             tabs = [p.tables] + [seg[2] if seg[0] == 'run' else seg[3] for seg in q.segments if seg[0] in ('run', 'xblock')]
             return (p, q), tabs
 

@@ -79,3 +79,39 @@ def test_generic_circuit_with_repeated_global_targets(g):
             got = vc.logical_state(pl, psi, sps)
             assert np.abs(got - want).max() < 1e-12, (lazy, mode, fused)
     assert sps[0].n_exchanges >= 1
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_random_generic_circuits_on_virtual_ranks(seed):
+    """Seeded fuzz of the sharded planner (sharded.plan_for_shards, what ShardedSimulator.prepare calls) on 2, 4 and 8
+    virtual ranks: random circuits over the whole gate surface, eager and lazy plans, NCCL-style and fused exchanges.  A
+    lazily materialised plan that would need an exchange is replaced by the dense plan on every rank alike (lazy plans
+    with exchanges had ranks disagreeing on the segment list and exchanges of partially materialised shards); the state
+    must be the textbook one exactly, and no circuit may be refused."""
+    from test_host_fusion import _random_circuit, _textbook_state
+    from qcmrf_b200 import sharded
+    rng = np.random.RandomState(8100 + seed)
+    fallbacks = lazy_kept = 0
+    for trial in range(8):
+        nq = int(rng.randint(4, 8))
+        c = _random_circuit(rng, nq, int(rng.randint(4, 30)))
+        psi = _textbook_state(c)
+        prog = ir.lower(c)
+        for lazy, mode in ((False, 'off'), (True, 'off'), (True, 'clique'), (False, 'clique')):
+            fc = fusion.fuse(prog, mode, use_hint=False)
+            for g in (1, 2, 3):
+                for fused in (False, True):
+                    pairs = [sharded.plan_for_shards(fc, g, r, lazy, 2, 0, 8, fused) for r in range(1 << g)]
+                    pl = pairs[0][0]
+                    assert all(np.array_equal(p.ops, pl.ops) and np.array_equal(p.tables, pl.tables) for p, _ in pairs)
+                    kinds = [[s[0] for s in q.segments] for _, q in pairs]
+                    assert all(k == kinds[0] for k in kinds), (seed, trial, lazy, mode, g, fused)    # one collective schedule
+                    st, sps = vc.run_virtual(pl, g, fuse_exchange=fused)
+                    got = vc.logical_state(pl, st, sps)
+                    assert np.abs(got - psi).max() < 1e-12, (seed, trial, lazy, mode, g, fused)
+                    if lazy:
+                        if any(sp.n_exchanges for sp in sps):
+                            fallbacks += 1
+                        else:
+                            lazy_kept += 1
+    assert fallbacks and lazy_kept
