@@ -853,7 +853,12 @@ class ShardedSimulator:
         """The ranks' pmf blocks tile the pmf (every global qubit a variable, no replicas): the layout
         the planner produces for QCMRF circuits -- results can then stay on the GPU until the end."""
         if pr.pmf_map is None:
-            pr.pmf_map = self._pmf_map(pr)
+            try:
+                pr.pmf_map = self._pmf_map(pr)
+            except NotImplementedError:
+                pr.pmf_map = 'general'                      # variables anywhere: _postselect_general
+        if pr.pmf_map == 'general':
+            return False
         m, where = pr.pmf_map
         if pr.pmf_order is None:
             tiles = isinstance(where, slice) and where.stop - where.start == 1 << m and self._slices_tile(pr, m)
@@ -1023,7 +1028,12 @@ class ShardedSimulator:
         rank's block, its kept mass and (for the sampler) its total mass.  Returns (pmf, kept, masses)."""
         n = pr.n_vars
         if pr.pmf_map is None:
-            pr.pmf_map = self._pmf_map(pr)
+            try:
+                pr.pmf_map = self._pmf_map(pr)
+            except NotImplementedError:
+                pr.pmf_map = 'general'
+        if pr.pmf_map == 'general':
+            return self._postselect_general(h, pr, replica, mass)
         m, where = pr.pmf_map
         mask, value, _ = pr.ps
         mine = np.zeros((1 << m) + 2)
@@ -1058,6 +1068,35 @@ class ShardedSimulator:
             else:
                 np.add.at(out, wr, allx[r, :-2])
         return out, kept, masses
+
+    def _postselect_general(self, h, pr, replica, mass=None):
+        """The same result for ANY layout of the variable qubits (a foreign circuit whose first-use layout scatters
+        them): every rank takes its whole masked local distribution from the engine, adds it into the 2^n pmf by index
+        arithmetic on the host, and one all-reduce sums pmf, kept mass and the ranks' masses.  Small states only."""
+        n, sp = pr.n_vars, pr.sp
+        nl = sp.n_local
+        if nl > 26 or n > 26:
+            raise NotImplementedError('post-selected vector of a sharded state this large needs the variable qubits on the '
+                                      'low local positions')
+        mask, value, _ = pr.ps
+        mine = np.zeros((1 << n) + self.world + 1)
+        if not replica:
+            full, k = h.postselect(mask, value, nl)
+            idx = np.arange(1 << nl, dtype=np.int64)
+            oi = np.zeros(1 << nl, dtype=np.int64)
+            for q in range(n):
+                p = pr.var_positions[q]
+                if p < 0:
+                    continue                                # never materialised: the variable reads 0
+                if p < nl:
+                    oi |= ((idx >> p) & 1) << q
+                else:
+                    oi |= ((sp.rank >> (p - nl)) & 1) << q
+            np.add.at(mine[:1 << n], oi, full)
+            mine[(1 << n) + self.rank] = 0.0 if mass is None else mass
+            mine[-1] = k
+        tot = self._reduce(mine)
+        return tot[:1 << n].copy(), float(tot[-1]), tot[1 << n:-1].copy()
 
     def _pmf_where_for_rank(self, pr, r, m):
         """Index set of rank r's block in the pmf, or None if r is a replica."""

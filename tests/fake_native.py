@@ -96,10 +96,12 @@ class Handle:
     def run_program(self, ops, tables):
         pl = FakePlanHolder()
         pl.ops, pl.tables, pl.n_phys = ops, tables, self.n_local
-        psi0 = self.state if self.active else None
+        # a state of ZERO active qubits (one amplitude: every local qubit still unmaterialised) is a state too
+        psi0 = self.state if getattr(self, '_has_state', False) else None
         psi, self.active = em.run_plan(pl, n_global=self.n_global, rank=self.rank, n_local=self.n_local,
                                        psi0=psi0, active0=self.active if psi0 is not None else 0)
         self._store(psi)
+        self._has_state = True
         self._prof = [(int(o['kind']), 0.0, 0, 0) for o in ops]
 
     def _global_index(self):

@@ -100,3 +100,75 @@ def test_two_rank_gloo():
     for p in procs:
         p.join(timeout=60)
     assert results[0] == results[1]                   # every rank returns the same counts and delta
+
+
+def _fuzz_worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, HERE)
+        sys.path.insert(0, os.path.dirname(HERE))
+        os.environ['MASTER_ADDR'] = '127.0.0.1'
+        os.environ['MASTER_PORT'] = str(port)
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        import fake_native
+        from test_host_fusion import _random_circuit, _textbook_state
+        from qcmrf_b200 import _native, sharded
+        from qcmrf_b200.circuit import QuantumCircuit
+
+        _native.Handle = fake_native.Handle
+
+        class CpuSharded(sharded.ShardedSimulator):
+            def _tensor_device(self):
+                return torch.device('cpu')
+
+        rng = np.random.RandomState(9811)
+        out, general = [], 0
+        for trial in range(12):
+            nq = int(rng.randint(3, 7))
+            base = _random_circuit(rng, nq, int(rng.randint(3, 24)))
+            pw = np.abs(_textbook_state(base)) ** 2
+            nv = int(rng.randint(1, nq + 1))
+            c = QuantumCircuit(nq, nq)
+            for ins in base.data:
+                c._qc_add(ins.operation, list(ins.qubits))
+            c.measure(range(nq), range(nq))
+            kept = pw[:1 << nv].sum()
+            for fus, layout, xch in (('blocked', 'auto', 'nccl'), ('blocked', 'canonical', 'nccl'), ('clique', 'canonical', 'nccl'),
+                                     ('clique', 'canonical', 'p2p'), ('off', 'canonical', 'nccl')):
+                sim = CpuSharded(precision='double', fusion=fus, layout=layout, block_max=2, seed=5, staging_bytes=1 << 9, exchange=xch)
+                res = sim.run(c, shots=1000, n_vars=nv).result()
+                p, d = res.postselected_probabilities(0)
+                assert abs(d - kept) < 1e-10, (trial, fus, layout, xch)
+                if kept > 1e-9:
+                    assert np.abs(p - pw[:1 << nv] / kept).max() < 1e-10, (trial, fus, layout, xch)
+                cnt = res.get_counts()
+                assert sum(cnt.values()) == 1000 and all(pw[int(k, 2)] > 1e-14 for k in cnt), (trial, fus, layout, xch)
+                out.append((dict(cnt), float(d)))
+                sim.close()
+        q.put((rank, 'ok', out))
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, 'fail', traceback.format_exc()))
+
+
+def test_two_rank_gloo_random_generic_circuits():
+    """Seeded fuzz of ShardedSimulator.run on 2 gloo ranks: random foreign circuits (variables anywhere in the first-use
+    layout: the general post-selection path; targets on the global qubit: dense re-planning), every layout / fusion /
+    exchange setting -- pmf and success probability against a textbook simulation, keys only where the exact
+    distribution has mass, both ranks the same counts."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fuzz_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in procs:
+        rank, status, payload = q.get(timeout=600)
+        assert status == 'ok', payload
+        results[rank] = payload
+    for p in procs:
+        p.join(timeout=60)
+    assert results[0] == results[1] and len(results[0]) == 60
